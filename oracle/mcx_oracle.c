@@ -1,0 +1,709 @@
+/*
+ * oracle/mcx_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C, single-threaded CPU restatement of the `mccortex build` hot path
+ * (read -> contigs -> k-mer -> canonical key -> Lookup3 -> find-or-insert ->
+ * coverage / edges -> sorted .ctx v6 bytes).  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline leg may load this library; the product
+ * (mccortex_b200/, include/) never links, imports or executes it.
+ *
+ * Every function cites the reference file:line (relative to /root/reference)
+ * it restates.  Parity pinned: tests/test_oracle_vs_ref.py compares the bytes
+ * this file produces with the compiled, unmodified reference (oracle/_ref/,
+ * built by oracle/Makefile) and with the golden vectors in tests/golden/.
+ *
+ * The hash set below is deliberately NOT the reference's bucketed layout: the
+ * reference's unsorted iteration order is seed/thread dependent, so
+ * the contract is the sorted dump; any exact set with the same update rules
+ * gives the same bytes.
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <zlib.h>
+
+#define ORC_MAXW 2
+
+typedef struct { uint64_t b[ORC_MAXW]; } OrcKmer; /* b[0] = most significant word (binary_kmer.h:7,39-49) */
+
+/* ------------------------------------------------------------------ row A */
+/* src/basic/dna.c:8-25 : A/a=0 C/c=1 G/g=2 T/t=3, N/n=4, everything else 8 */
+uint8_t orc_char_to_nuc(char c)
+{
+  switch(c) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    case 'N': case 'n': return 4;
+    default: return 8;
+  }
+}
+/* src/basic/dna.h:15-16 */
+static inline int orc_is_acgt(char c) { return orc_char_to_nuc(c) < 4; }
+
+/* ------------------------------------------------------------------ row B */
+/* src/basic/seq_reader.c:61-117 (seq_contig_start2) */
+size_t orc_contig_start(const char *seq, size_t seqlen, const char *qual, size_t quallen,
+                        size_t offset, size_t k, uint8_t qual_cutoff, uint8_t hp_cutoff)
+{
+  if(!qual || !quallen) { qual = NULL; quallen = 0; }
+  size_t kmerend, pos = offset;
+  while((kmerend = pos + k) <= seqlen)
+  {
+    size_t i = kmerend;
+    while(i > pos && orc_is_acgt(seq[i-1])) i--;
+    if(i > pos) { pos = i; continue; }
+
+    if(qual && qual_cutoff > 0) {
+      i = kmerend < quallen ? kmerend : quallen;
+      /* `char` vs uint8_t compare after integer promotion, as in the reference */
+      while(i > pos && qual[i-1] > qual_cutoff) i--;
+      if(i > pos) { pos = i; continue; }
+    }
+
+    if(hp_cutoff > 0) {
+      size_t run_length = 1;
+      for(i = kmerend-1; i > pos; i--) {
+        if(seq[i-1] == seq[i]) { run_length++; if(run_length == (size_t)hp_cutoff) break; }
+        else run_length = 1;
+      }
+      if(i > pos) { pos = i; continue; }
+    }
+    return pos;
+  }
+  return seqlen;
+}
+
+/* src/basic/seq_reader.c:127-172 (seq_contig_end2) */
+size_t orc_contig_end(const char *seq, size_t seqlen, const char *qual, size_t quallen,
+                      size_t contig_start, size_t k, uint8_t qual_cutoff, uint8_t hp_cutoff,
+                      size_t *search_start)
+{
+  if(!qual || !quallen) { qual = NULL; quallen = 0; }
+  size_t contig_end = contig_start + k;
+  size_t hp_run = 1;
+  if(hp_cutoff > 0) {
+    while(hp_run < contig_end && seq[contig_end-1-hp_run] == seq[contig_end-1]) hp_run++;
+  }
+  for(; contig_end < seqlen; contig_end++)
+  {
+    if(!orc_is_acgt(seq[contig_end]) ||
+       (contig_end < quallen && qual[contig_end] < qual_cutoff)) break;
+    if(hp_cutoff > 0) {
+      if(seq[contig_end] == seq[contig_end-1]) { hp_run++; if(hp_run >= (size_t)hp_cutoff) break; }
+      else hp_run = 1;
+    }
+  }
+  if(hp_cutoff > 0 && hp_run >= (size_t)hp_cutoff) *search_start = contig_end - (size_t)hp_cutoff + 1;
+  else *search_start = contig_end;
+  return contig_end;
+}
+
+/* ------------------------------------------------------------------ row C */
+static inline int orc_nwords(size_t k) { return (int)((k + 31) / 32); }       /* binary_kmer.h:10-11 */
+static inline unsigned orc_top_bases(size_t k) { return (unsigned)(k & 31); } /* bases in b[0]; k odd => 1..31 */
+
+/* src/graph/binary_kmer.h:139-146,160-167 + binary_kmer.c:80-97 */
+static void orc_left_shift_add(OrcKmer *bk, size_t k, uint8_t nuc)
+{
+  int W = orc_nwords(k), i;
+  for(i = 0; i + 1 < W; i++) bk->b[i] = (bk->b[i] << 2) | (bk->b[i+1] >> 62);
+  bk->b[W-1] = (bk->b[W-1] << 2) | nuc;
+  bk->b[0] &= (UINT64_MAX >> (64 - 2*orc_top_bases(k)));
+}
+
+/* src/graph/binary_kmer.c:156-186 */
+OrcKmer orc_bkmer_from_str(const char *seq, size_t k)
+{
+  OrcKmer bk; size_t i;
+  memset(&bk, 0, sizeof(bk));
+  for(i = 0; i < k; i++) orc_left_shift_add(&bk, k, orc_char_to_nuc(seq[i]));
+  return bk;
+}
+
+/* ------------------------------------------------------------------ row D */
+/* src/graph/binary_kmer.c:102-133 : per word byte-swap, swap the 2-bit fields
+ * inside each byte, NOT, reverse word order, then shift the whole W-word value
+ * right by 64 - 2*(k&31) bits.  Written here base by base (the slow, obviously
+ * correct way) so that it is independent of the bit tricks the GPU code uses. */
+OrcKmer orc_revcomp(OrcKmer bk, size_t k)
+{
+  int W = orc_nwords(k);
+  OrcKmer rc; size_t i;
+  memset(&rc, 0, sizeof(rc));
+  for(i = 0; i < k; i++) {
+    /* base i counted from the LAST base of bk (least significant 2 bits) */
+    size_t word = (size_t)(W - 1) - i / 32, sh = 2 * (i % 32);
+    uint8_t nuc = (uint8_t)((bk.b[word] >> sh) & 3);
+    orc_left_shift_add(&rc, k, (uint8_t)(~nuc & 3)); /* dna.h:22 complement */
+  }
+  return rc;
+}
+
+static inline int orc_kmer_lt(const OrcKmer *a, const OrcKmer *b, int W) /* binary_kmer.h:79-94 */
+{
+  int i;
+  for(i = 0; i < W; i++) if(a->b[i] != b->b[i]) return a->b[i] < b->b[i];
+  return 0;
+}
+static inline int orc_kmer_eq(const OrcKmer *a, const OrcKmer *b, int W)
+{
+  int i;
+  for(i = 0; i < W; i++) if(a->b[i] != b->b[i]) return 0;
+  return 1;
+}
+
+/* src/graph/binary_kmer.c:43-57 ; orientation db_node.h:109-110 (0 FORWARD, 1 REVERSE) */
+OrcKmer orc_get_key(OrcKmer bk, size_t k, int *orient)
+{
+  int W = orc_nwords(k);
+  OrcKmer rc = orc_revcomp(bk, k);
+  if(orc_kmer_lt(&rc, &bk, W)) { if(orient) *orient = 1; return rc; }
+  if(orient) *orient = 0;
+  return bk;
+}
+
+/* ------------------------------------------------------------------ row E */
+#define ORC_ROT(x,k) (((x)<<(k)) | ((x)>>(32-(k))))
+/* src/kmer/kmer_hash.h:89-97 */
+#define ORC_MIX(a,b,c) { \
+  a -= c;  a ^= ORC_ROT(c, 4);  c += b; \
+  b -= a;  b ^= ORC_ROT(a, 6);  a += c; \
+  c -= b;  c ^= ORC_ROT(b, 8);  b += a; \
+  a -= c;  a ^= ORC_ROT(c,16);  c += b; \
+  b -= a;  b ^= ORC_ROT(a,19);  a += c; \
+  c -= b;  c ^= ORC_ROT(b, 4);  b += a; }
+/* src/kmer/kmer_hash.h:124-133 */
+#define ORC_FINAL(a,b,c) { \
+  c ^= b; c -= ORC_ROT(b,14); \
+  a ^= c; a -= ORC_ROT(c,11); \
+  b ^= a; b -= ORC_ROT(a,25); \
+  c ^= b; c -= ORC_ROT(b,16); \
+  a ^= c; a -= ORC_ROT(c,4);  \
+  b ^= a; b -= ORC_ROT(a,14); \
+  c ^= b; c -= ORC_ROT(b,24); }
+
+/* src/kmer/kmer_hash.h:162-211 specialised to 8*W key bytes read as
+ * little-endian u32 from the in-memory BinaryKmer {b[0], b[1]}.
+ * If b_out != NULL it also returns the second 32-bit lane (`b` after final),
+ * which lookup3's hashlittle2 exposes; the reference only uses `c`. */
+uint32_t orc_lookup3(const uint64_t *kb, int W, uint32_t initval, uint32_t *b_out)
+{
+  uint32_t a, b, c;
+  a = b = c = 0xdeadbeefu + (uint32_t)(8*W) + initval;
+  if(W == 1) {
+    a += (uint32_t)kb[0]; b += (uint32_t)(kb[0] >> 32);
+  } else {
+    a += (uint32_t)kb[0]; b += (uint32_t)(kb[0] >> 32); c += (uint32_t)kb[1];
+    ORC_MIX(a, b, c);
+    a += (uint32_t)(kb[1] >> 32);
+  }
+  ORC_FINAL(a, b, c);
+  if(b_out) *b_out = b;
+  return c;
+}
+
+/* XOR of hashes of {b[0]=i} for i in [0,n): what `mccortex31 hashtest -F n`
+ * prints (src/commands/ctx_exp_hashtest.c:40-69 fast-hash loop). */
+uint32_t orc_hashtest_xor(uint64_t n)
+{
+  uint64_t i; uint32_t x = 0;
+  for(i = 0; i < n; i++) { uint64_t kb[1] = { i }; x ^= orc_lookup3(kb, 1, 0, NULL); }
+  return x;
+}
+
+/* --------------------------------------------------------------- rows F, G */
+#define ORC_FLAG (1ULL << 63) /* BKMER_SET_FLAG, src/graph/hash_table.h:14-15 */
+
+typedef struct {
+  uint64_t total_bases_read, total_bases_loaded, contigs_parsed;
+  uint64_t num_kmers_loaded, num_kmers_novel;
+  uint64_t num_se_reads, num_pe_reads, num_good_reads, num_bad_reads;
+} OrcStats; /* subset of src/basic/seq_loading_stats.h:5-14 */
+
+typedef struct {
+  uint32_t mean_read_length;
+  uint64_t total_sequence;
+  long double seq_err;
+  char name[256];
+} OrcGInfo; /* src/basic/graph_info.h:20-27 (cleaning is all-default for build) */
+
+typedef struct {
+  size_t k, ncols; int W;
+  uint64_t cap, mask, nkmers, limit; /* limit = "capacity" the caller asked for */
+  uint64_t *keys;  /* cap * W, word 0 carries ORC_FLAG when assigned */
+  uint32_t *covgs; /* cap * ncols   (db_graph.h:39, db_node.h:284-285) */
+  uint8_t  *edges; /* cap * ncols   (db_graph.h:40) */
+  OrcGInfo *ginfo;
+  int full;
+} OrcGraph;
+
+static void orc_ginfo_init(OrcGInfo *g) /* src/basic/graph_info.c:60-67 */
+{
+  strcpy(g->name, "undefined");
+  g->total_sequence = 0; g->mean_read_length = 0; g->seq_err = 0.01;
+}
+
+OrcGraph *orc_graph_new(size_t k, size_t ncols, uint64_t capacity)
+{
+  OrcGraph *g = (OrcGraph*)calloc(1, sizeof(*g));
+  size_t i;
+  g->k = k; g->ncols = ncols; g->W = orc_nwords(k);
+  g->limit = capacity;
+  g->cap = 1024; while(g->cap < capacity * 2) g->cap <<= 1;
+  g->mask = g->cap - 1;
+  g->keys  = (uint64_t*)calloc(g->cap * (size_t)g->W, 8);
+  g->covgs = (uint32_t*)calloc(g->cap * ncols, 4);
+  g->edges = (uint8_t*)calloc(g->cap * ncols, 1);
+  g->ginfo = (OrcGInfo*)calloc(ncols, sizeof(OrcGInfo));
+  for(i = 0; i < ncols; i++) orc_ginfo_init(&g->ginfo[i]);
+  return g;
+}
+
+void orc_graph_free(OrcGraph *g)
+{
+  if(!g) return;
+  free(g->keys); free(g->covgs); free(g->edges); free(g->ginfo); free(g);
+}
+
+uint64_t orc_graph_nkmers(const OrcGraph *g) { return g->nkmers; }
+int orc_graph_is_full(const OrcGraph *g) { return g->full; }
+void orc_graph_set_name(OrcGraph *g, size_t col, const char *name)
+{
+  strncpy(g->ginfo[col].name, name, sizeof(g->ginfo[col].name)-1);
+}
+
+/* find-or-insert semantics of src/graph/hash_table.c:250-281: returns slot, sets *found.
+ * "Hash table is full" (hash_table.c:119-123) becomes g->full once the caller's
+ * requested capacity is exhausted. */
+static uint64_t orc_find_or_insert(OrcGraph *g, const OrcKmer *key, int *found)
+{
+  int W = g->W, i;
+  uint64_t h = orc_lookup3(key->b, W, 0, NULL) & g->mask;
+  for(;; h = (h + 1) & g->mask) {
+    uint64_t *s = g->keys + h * (uint64_t)W;
+    if(s[0] == 0) {
+      if(g->nkmers >= g->limit) { g->full = 1; }
+      s[0] = key->b[0] | ORC_FLAG;
+      for(i = 1; i < W; i++) s[i] = key->b[i];
+      g->nkmers++;
+      *found = 0;
+      return h;
+    }
+    if(s[0] == (key->b[0] | ORC_FLAG)) {
+      for(i = 1; i < W && s[i] == key->b[i]; i++) {}
+      if(i == W) { *found = 1; return h; }
+    }
+  }
+}
+
+typedef struct { uint64_t slot; int orient; } OrcNode;
+
+/* src/tools/build_graph.c:99-117 (_find_or_insert, must_exist_in_graph=false)
+ * + src/graph/db_graph.c:101-105,126-134 + src/graph/db_node.c:139-144 */
+static OrcNode orc_add_kmer(OrcGraph *g, OrcKmer bk, size_t colour, int *found)
+{
+  OrcNode n;
+  OrcKmer key = orc_get_key(bk, g->k, &n.orient);
+  n.slot = orc_find_or_insert(g, &key, found);
+  uint32_t *cv = &g->covgs[n.slot * g->ncols + colour];
+  if(*cv < UINT32_MAX) (*cv)++; /* saturating */
+  return n;
+}
+
+/* src/tools/build_graph.c:122-150 (build_graph_from_str_mt) with
+ * src/graph/db_graph.c:152-166 (db_graph_add_edge_mt) and db_node.h:180,273-274.
+ * Returns the number of non-novel k-mers. */
+size_t orc_graph_add_contig(OrcGraph *g, size_t colour, const char *seq, size_t len)
+{
+  size_t k = g->k, i, nonnovel = 0;
+  int found;
+  OrcKmer bk = orc_bkmer_from_str(seq, k);
+  OrcNode prev = orc_add_kmer(g, bk, colour, &found), curr;
+  nonnovel += (size_t)found;
+  for(i = k; i < len; i++, prev = curr) {
+    uint8_t nuc = orc_char_to_nuc(seq[i]);
+    orc_left_shift_add(&bk, k, nuc);
+    curr = orc_add_kmer(g, bk, colour, &found);
+    /* lhs = first base of prev as read, rhs = last base of curr as read */
+    uint8_t lhs = orc_char_to_nuc(seq[i - k]), rhs = nuc;
+    uint8_t lhs_rev = (uint8_t)(~lhs & 3);
+    g->edges[prev.slot * g->ncols + colour] |= (uint8_t)(1u << (rhs + 4 * prev.orient));
+    g->edges[curr.slot * g->ncols + colour] |= (uint8_t)(1u << (lhs_rev + 4 * (!curr.orient)));
+    nonnovel += (size_t)found;
+  }
+  return nonnovel;
+}
+
+/* src/tools/build_graph.c:154-189 (load_read) + :192-231 (build_graph_from_reads_mt,
+ * single-end, no PCR-duplicate removal).  fq_cutoff is the raw -Q value;
+ * fq_offset is added only when fq_cutoff != 0 (build_graph.c:202-207). */
+void orc_graph_add_read(OrcGraph *g, const char *seq, size_t seqlen, const char *qual, size_t quallen,
+                        size_t colour, uint8_t fq_cutoff, uint8_t fq_offset, uint8_t hp_cutoff,
+                        OrcStats *st)
+{
+  size_t k = g->k, cs, ce, search = 0, ncontigs = 0;
+  uint8_t qcut = fq_cutoff ? (uint8_t)(fq_cutoff + fq_offset) : 0;
+  st->total_bases_read += seqlen;
+  st->num_se_reads += 1;
+  while((cs = orc_contig_start(seq, seqlen, qual, quallen, search, k, qcut, hp_cutoff)) < seqlen) {
+    ce = orc_contig_end(seq, seqlen, qual, quallen, cs, k, qcut, hp_cutoff, &search);
+    size_t clen = ce - cs;
+    size_t nonnovel = orc_graph_add_contig(g, colour, seq + cs, clen);
+    size_t ck = clen + 1 - k;
+    st->total_bases_loaded += clen;
+    st->num_kmers_loaded += ck;
+    st->num_kmers_novel += ck - nonnovel;
+    ncontigs++;
+  }
+  st->contigs_parsed += ncontigs;
+  st->num_good_reads += (ncontigs > 0);
+  st->num_bad_reads += (ncontigs == 0);
+}
+
+/* Per-window view of one read, for tuple-level checks of the GPU kernel:
+ * for every window start p in [0, seqlen-k] writes in_contig[p] (0/1) and, if 1,
+ * key words, orientation and the edge bits this occurrence contributes
+ * (the two ORs of db_graph_add_edge_mt that land on THIS node: the edge to the
+ * next window and the edge from the previous one).  Derived from the same
+ * sequential contig walk as orc_graph_add_read. */
+void orc_read_windows(const char *seq, size_t seqlen, const char *qual, size_t quallen, size_t k,
+                      uint8_t qcut, uint8_t hp_cutoff,
+                      uint8_t *in_contig, uint64_t *keys /* [n*W] */, uint8_t *orient, uint8_t *emask)
+{
+  int W = orc_nwords(k), j;
+  size_t n = seqlen >= k ? seqlen - k + 1 : 0, cs, ce, search = 0, p;
+  memset(in_contig, 0, n);
+  while((cs = orc_contig_start(seq, seqlen, qual, quallen, search, k, qcut, hp_cutoff)) < seqlen) {
+    ce = orc_contig_end(seq, seqlen, qual, quallen, cs, k, qcut, hp_cutoff, &search);
+    OrcKmer bk = orc_bkmer_from_str(seq + cs, k);
+    for(p = cs; p + k <= ce; p++) {
+      if(p > cs) orc_left_shift_add(&bk, k, orc_char_to_nuc(seq[p + k - 1]));
+      int o; OrcKmer key = orc_get_key(bk, k, &o);
+      uint8_t m = 0;
+      if(p + k < ce) m |= (uint8_t)(1u << (orc_char_to_nuc(seq[p + k]) + 4 * o));
+      if(p > cs)     m |= (uint8_t)(1u << ((~orc_char_to_nuc(seq[p - 1]) & 3) + 4 * (!o)));
+      in_contig[p] = 1; orient[p] = (uint8_t)o; emask[p] = m;
+      for(j = 0; j < W; j++) keys[p * (size_t)W + (size_t)j] = key.b[j];
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ row H */
+/* src/basic/graph_info.c:116-133 */
+static void orc_ginfo_update_contigs(OrcGInfo *gi, uint64_t added_seq, uint64_t num_contigs)
+{
+  if(!added_seq && !num_contigs) return;
+  size_t ginfo_num_contigs = 0;
+  if(gi->total_sequence && gi->mean_read_length)
+    ginfo_num_contigs = ((double)gi->total_sequence / gi->mean_read_length) + 0.5;
+  if(ginfo_num_contigs + num_contigs > 0) {
+    gi->mean_read_length = (uint32_t)((double)(gi->total_sequence + added_seq) /
+                                      (ginfo_num_contigs + num_contigs));
+  }
+  gi->total_sequence += added_seq;
+}
+
+/* src/tools/build_graph.c:295-300 -> graph_info_update_stats (graph_info.c:172-175).
+ * Called once per build_graph() batch with the stats the reference credits to
+ * the batch's FIRST task (quirk Q1, build_graph.c:242). */
+void orc_graph_update_ginfo(OrcGraph *g, size_t colour, const OrcStats *st)
+{
+  orc_ginfo_update_contigs(&g->ginfo[colour], st->total_bases_loaded, st->contigs_parsed);
+}
+
+/* src/basic/graph_info.c:135-170 with dst freshly initialised (graph_writer.c:11-30) */
+static void orc_ginfo_merge(OrcGInfo *dst, const OrcGInfo *src)
+{
+  if(strcmp(src->name, "undefined") != 0) {
+    if(strcmp(dst->name, "undefined") == 0) strcpy(dst->name, src->name);
+    else { strcat(dst->name, ","); strcat(dst->name, src->name); }
+  }
+  uint64_t total_sequence = dst->total_sequence + src->total_sequence;
+  if(total_sequence > 0) {
+    dst->seq_err = (dst->seq_err * dst->total_sequence + src->seq_err * src->total_sequence) / total_sequence;
+    size_t src_num_contigs = 0;
+    if(src->total_sequence && src->mean_read_length)
+      src_num_contigs = ((double)src->total_sequence / src->mean_read_length) + 0.5;
+    orc_ginfo_update_contigs(dst, src->total_sequence, src_num_contigs);
+  }
+  dst->total_sequence = total_sequence;
+}
+
+static size_t orc_put(uint8_t *buf, size_t off, const void *src, size_t n)
+{
+  if(buf) memcpy(buf + off, src, n);
+  return off + n;
+}
+
+/* src/graph/graph_writer.c:62-110 (graph_write_header) + :33-60 (error cleaning object).
+ * buf may be NULL to size the header. */
+size_t orc_graph_write_header(const OrcGraph *g, uint8_t *buf)
+{
+  size_t off = 0, i, ncols = g->ncols;
+  uint32_t version = 6, k32 = (uint32_t)g->k, W32 = (uint32_t)g->W, c32 = (uint32_t)ncols;
+  OrcGInfo *h = (OrcGInfo*)calloc(ncols, sizeof(OrcGInfo));
+  for(i = 0; i < ncols; i++) { orc_ginfo_init(&h[i]); orc_ginfo_merge(&h[i], &g->ginfo[i]); }
+  off = orc_put(buf, off, "CORTEX", 6);
+  off = orc_put(buf, off, &version, 4);
+  off = orc_put(buf, off, &k32, 4);
+  off = orc_put(buf, off, &W32, 4);
+  off = orc_put(buf, off, &c32, 4);
+  for(i = 0; i < ncols; i++) off = orc_put(buf, off, &h[i].mean_read_length, 4);
+  for(i = 0; i < ncols; i++) off = orc_put(buf, off, &h[i].total_sequence, 8);
+  for(i = 0; i < ncols; i++) {
+    uint32_t len = (uint32_t)strlen(h[i].name);
+    off = orc_put(buf, off, &len, 4);
+    off = orc_put(buf, off, h[i].name, len);
+  }
+  for(i = 0; i < ncols; i++) {
+    /* raw x87 long double: 10 value bytes + 6 padding bytes.  The reference
+     * writes whatever is in the padding; it is zero there because the struct
+     * comes from calloc and x87 stores only touch 10 bytes.  We zero it. */
+    uint8_t ld[16]; memset(ld, 0, 16); memcpy(ld, &h[i].seq_err, 10);
+    off = orc_put(buf, off, ld, sizeof(long double));
+  }
+  for(i = 0; i < ncols; i++) {
+    uint8_t flags[4] = {0,0,0,0}; uint32_t z = 0, len = 9;
+    off = orc_put(buf, off, flags, 4);
+    off = orc_put(buf, off, &z, 4);
+    off = orc_put(buf, off, &z, 4);
+    off = orc_put(buf, off, &len, 4);
+    off = orc_put(buf, off, "undefined", 9);
+  }
+  off = orc_put(buf, off, "CORTEX", 6);
+  free(h);
+  return off;
+}
+
+static int orc_W_for_sort;
+static int orc_cmp_keys(const void *a, const void *b)
+{
+  const uint64_t *x = *(const uint64_t * const *)a, *y = *(const uint64_t * const *)b;
+  int i;
+  uint64_t x0 = x[0] & ~ORC_FLAG, y0 = y[0] & ~ORC_FLAG;
+  if(x0 != y0) return x0 < y0 ? -1 : 1;
+  for(i = 1; i < orc_W_for_sort; i++) if(x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
+  return 0;
+}
+
+/* src/graph/graph_writer.c:116-127,182-193 + hash_table.c:362-374: header, then one
+ * record per k-mer in ascending key order: W x u64 key (flag cleared), u32 covg[C], u8 edges[C].
+ * buf may be NULL to size the output.  Returns total bytes. */
+size_t orc_graph_dump_sorted(const OrcGraph *g, uint8_t *buf)
+{
+  size_t off = orc_graph_write_header(g, buf), W = (size_t)g->W, C = g->ncols, i, n = 0;
+  if(!buf) return off + g->nkmers * (8*W + 5*C);
+  const uint64_t **ptrs = (const uint64_t**)malloc((g->nkmers + 1) * sizeof(*ptrs));
+  for(i = 0; i < g->cap; i++) if(g->keys[i*W]) ptrs[n++] = &g->keys[i*W];
+  orc_W_for_sort = g->W;
+  qsort(ptrs, n, sizeof(*ptrs), orc_cmp_keys);
+  for(i = 0; i < n; i++) {
+    size_t slot = (size_t)(ptrs[i] - g->keys) / W, j;
+    uint64_t w0 = ptrs[i][0] & ~ORC_FLAG;
+    off = orc_put(buf, off, &w0, 8);
+    for(j = 1; j < W; j++) off = orc_put(buf, off, &ptrs[i][j], 8);
+    off = orc_put(buf, off, &g->covgs[slot*C], 4*C);
+    off = orc_put(buf, off, &g->edges[slot*C], C);
+  }
+  free(ptrs);
+  return off;
+}
+
+/* ------------------------------------------------------------------ row I */
+/* src/basic/hash_mem.c:5-15 */
+uint64_t orc_hash_table_cap(uint64_t nkmers, uint64_t *nbkts, uint8_t *bktsize)
+{
+  uint64_t num_of_buckets, bucket_size, num_of_bits = 10;
+  while(nkmers / (1UL << num_of_bits) > 48) num_of_bits++;
+  num_of_buckets = 1UL << num_of_bits;
+  bucket_size = (nkmers + num_of_buckets - 1) / num_of_buckets;
+  if(bucket_size < 1) bucket_size = 1;
+  if(nbkts) *nbkts = num_of_buckets;
+  if(bktsize) *bktsize = (uint8_t)bucket_size;
+  return num_of_buckets * bucket_size;
+}
+static size_t orc_ht_mem(size_t bktsize, size_t nbkts, size_t nbits) { return (bktsize*nbkts*nbits)/8 + nbkts*2; } /* hash_mem.h:12-14 */
+/* src/basic/hash_mem.c:27-51 */
+uint64_t orc_hash_table_mem_limit(size_t memlimit, size_t entrybits, uint64_t *nkmers_ptr)
+{
+  size_t bktsize, num_of_bits = 10, num_of_buckets = 1UL << num_of_bits, num_of_kmers;
+  while(orc_ht_mem(48, num_of_buckets, entrybits) < memlimit) { num_of_bits++; num_of_buckets = 1UL << num_of_bits; }
+  bktsize = (memlimit - num_of_buckets*2) / ((num_of_buckets * entrybits) / 8);
+  if(bktsize == 0) {
+    num_of_bits--; num_of_buckets = 1UL << num_of_bits;
+    num_of_kmers = bktsize * num_of_buckets;
+    bktsize = num_of_kmers / num_of_buckets; if(bktsize < 1) bktsize = 1;
+  }
+  if(bktsize > 48) bktsize = 48;
+  if(nkmers_ptr) *nkmers_ptr = num_of_buckets * bktsize;
+  return orc_ht_mem(bktsize, num_of_buckets, entrybits);
+}
+
+/* ------------------------------------------------------------------ row K */
+/* In-memory restatement of libs/seq_file/seq_file.h:245-323 (FASTQ / FASTA /
+ * plain record readers and the first-byte format sniff) over a whole file
+ * that has been inflated by zlib's gzread (seq_file.h:512,573-581: gzopen
+ * reads plain and gzip transparently).  Calls cb(seq,len,qual,qlen,ctx) per read. */
+typedef void (*orc_read_cb)(const char *seq, size_t seqlen, const char *qual, size_t quallen, void *ctx);
+
+typedef struct { const char *p, *end; } OrcCur;
+static int orc_getc(OrcCur *c) { return c->p < c->end ? (unsigned char)*c->p++ : -1; }
+/* append the rest of the current line (including '\n') to dst; returns bytes read */
+static size_t orc_readline(OrcCur *c, char **dst, size_t *len, size_t *cap)
+{
+  const char *s = c->p;
+  while(c->p < c->end && *c->p != '\n') c->p++;
+  if(c->p < c->end) c->p++;
+  size_t n = (size_t)(c->p - s);
+  if(*len + n + 1 > *cap) { *cap = (*len + n + 1) * 2; *dst = (char*)realloc(*dst, *cap); }
+  memcpy(*dst + *len, s, n); *len += n; (*dst)[*len] = 0;
+  return n;
+}
+static void orc_chomp(char *b, size_t *len) { while(*len && (b[*len-1] == '\n' || b[*len-1] == '\r')) (*len)--; b[*len] = 0; }
+static void orc_pushc(char **dst, size_t *len, size_t *cap, char ch)
+{
+  if(*len + 2 > *cap) { *cap = (*len + 2) * 2; *dst = (char*)realloc(*dst, *cap); }
+  (*dst)[(*len)++] = ch; (*dst)[*len] = 0;
+}
+static int orc_isspace(int c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+/* returns number of reads, or -(reads+1) on a malformed record (the reference
+ * stops at the first malformed record, seq_reader.c:445-452) */
+long orc_parse_buffer(const char *buf, size_t n, orc_read_cb cb, void *ctx)
+{
+  OrcCur cur = { buf, buf + n };
+  char *name = NULL, *seq = NULL, *qual = NULL;
+  size_t nl = 0, nc = 0, sl = 0, sc = 0, ql = 0, qc = 0;
+  long nreads = 0; int c, fmt = 0, bad = 0; /* fmt: 1 fastq 2 fasta 3 plain */
+  orc_pushc(&name, &nl, &nc, 0); orc_pushc(&seq, &sl, &sc, 0); orc_pushc(&qual, &ql, &qc, 0);
+
+  /* _read_unknown, seq_file.h:311-323 */
+  while((c = orc_getc(&cur)) != -1 && orc_isspace(c)) if(c != '\n') { while((c = orc_getc(&cur)) != -1 && c != '\n') {} }
+  if(c == -1) goto done;
+  fmt = c == '@' ? 1 : (c == '>' ? 2 : 3);
+  cur.p--;
+
+  for(;;) {
+    nl = sl = ql = 0; name[0] = seq[0] = qual[0] = 0;
+    if(fmt == 1) { /* seq_file.h:245-272 */
+      c = orc_getc(&cur);
+      if(c == -1) break;
+      if(c != '@' || orc_readline(&cur, &name, &nl, &nc) == 0) { bad = 1; break; }
+      orc_chomp(name, &nl);
+      while((c = orc_getc(&cur)) != '+') {
+        if(c == -1) { bad = 1; break; }
+        if(c != '\r' && c != '\n') {
+          orc_pushc(&seq, &sl, &sc, (char)c);
+          if(orc_readline(&cur, &seq, &sl, &sc) == 0) { bad = 1; break; }
+          orc_chomp(seq, &sl);
+        }
+      }
+      if(bad) break;
+      while((c = orc_getc(&cur)) != -1 && c != '\n') {}
+      if(c == -1) { bad = 1; break; }
+      int eof_in_qual = 0;
+      do {
+        if(orc_readline(&cur, &qual, &ql, &qc) > 0) orc_chomp(qual, &ql);
+        else { eof_in_qual = 1; break; }
+      } while(ql < sl);
+      if(!eof_in_qual) { while((c = orc_getc(&cur)) != -1 && c != '@') {} if(c != -1) cur.p--; }
+    } else if(fmt == 2) { /* seq_file.h:274-295 */
+      c = orc_getc(&cur);
+      if(c == -1) break;
+      if(c != '>' || orc_readline(&cur, &name, &nl, &nc) == 0) { bad = 1; break; }
+      orc_chomp(name, &nl);
+      while((c = orc_getc(&cur)) != '>') {
+        if(c == -1) break;
+        if(c != '\r' && c != '\n') {
+          orc_pushc(&seq, &sl, &sc, (char)c);
+          size_t nread = orc_readline(&cur, &seq, &sl, &sc);
+          orc_chomp(seq, &sl);
+          if(nread == 0) break;
+        }
+      }
+      if(c == '>') cur.p--;
+    } else { /* plain, seq_file.h:298-309 */
+      while((c = orc_getc(&cur)) != -1 && orc_isspace(c)) if(c != '\n') { while((c = orc_getc(&cur)) != -1 && c != '\n') {} }
+      if(c == -1) break;
+      orc_pushc(&seq, &sl, &sc, (char)c);
+      orc_readline(&cur, &seq, &sl, &sc);
+      orc_chomp(seq, &sl);
+    }
+    cb(seq, sl, ql ? qual : NULL, ql, ctx);
+    nreads++;
+  }
+done:
+  free(name); free(seq); free(qual);
+  return bad ? -(nreads + 1) : nreads;
+}
+
+typedef struct { OrcGraph *g; size_t colour; uint8_t fq_cutoff, fq_offset, hp_cutoff; OrcStats *st; } OrcLoadCtx;
+static void orc_load_cb(const char *seq, size_t sl, const char *qual, size_t ql, void *ctx)
+{
+  OrcLoadCtx *c = (OrcLoadCtx*)ctx;
+  orc_graph_add_read(c->g, seq, sl, qual, ql, c->colour, c->fq_cutoff, c->fq_offset, c->hp_cutoff, c->st);
+}
+
+/* libs/seq_file/seq_file.h:636-682 restated over the first reads of a parsed
+ * file: min/max over the first <=1000 quality bytes seen while seq bases < 1000. */
+typedef struct { int min, max; size_t count, qcount; } OrcQLim;
+static void orc_qlim_cb(const char *seq, size_t sl, const char *qual, size_t ql, void *ctx)
+{
+  OrcQLim *q = (OrcQLim*)ctx; size_t limit = 1000, len, i;
+  (void)seq;
+  if(q->count >= limit) return;
+  len = ql < limit - q->qcount ? ql : limit - q->qcount;
+  for(i = 0; i < len; i++) { if(qual[i] > q->max) q->max = qual[i]; if(qual[i] < q->min) q->min = qual[i]; }
+  q->count += sl; q->qcount += ql;
+}
+/* returns FASTQ ascii offset (33/64) or 0 if the file has no qualities */
+int orc_guess_fq_offset(const char *buf, size_t n)
+{
+  static const int OFFS[6] = {33, 33, 64, 64, 64, 33}; /* seq_file.h:127 */
+  OrcQLim q = { 0x7fffffff, 0, 0, 0 };
+  int fmt;
+  orc_parse_buffer(buf, n, orc_qlim_cb, &q);
+  if(q.qcount == 0) return 0;
+  if(q.min >= 33 && q.max <= 73) fmt = 1;
+  else if(q.min >= 33 && q.max <= 75) fmt = 5;
+  else if(q.min >= 67 && q.max <= 105) fmt = 4;
+  else if(q.min >= 64 && q.max <= 105) fmt = 3;
+  else if(q.min >= 59 && q.max <= 105) fmt = 2;
+  else fmt = 0;
+  return OFFS[fmt];
+}
+
+static char *orc_slurp(const char *path, size_t *n)
+{
+  gzFile gz = gzopen(path, "r");
+  size_t cap = 1 << 20, len = 0; int r;
+  char *buf;
+  if(!gz) return NULL;
+  buf = (char*)malloc(cap);
+  while((r = gzread(gz, buf + len, (unsigned)(cap - len))) > 0) {
+    len += (size_t)r;
+    if(len == cap) { cap *= 2; buf = (char*)realloc(buf, cap); }
+  }
+  gzclose(gz);
+  *n = len;
+  return buf;
+}
+
+/* One `--seq <file>` task (src/basic/seq_reader.c:421-462 seq_parse_se_sf ->
+ * build_graph.c:233-254).  fq_offset 0 = auto-detect.  Stats accumulate into *st. */
+long orc_graph_load_file(OrcGraph *g, const char *path, size_t colour,
+                         uint8_t fq_cutoff, uint8_t fq_offset, uint8_t hp_cutoff, OrcStats *st)
+{
+  size_t n; long r;
+  char *buf = orc_slurp(path, &n);
+  if(!buf) return -1000000000L;
+  if(fq_offset == 0) fq_offset = (uint8_t)orc_guess_fq_offset(buf, n);
+  OrcLoadCtx c = { g, colour, fq_cutoff, fq_offset, hp_cutoff, st };
+  r = orc_parse_buffer(buf, n, orc_load_cb, &c);
+  free(buf);
+  return r;
+}
