@@ -1,0 +1,141 @@
+/*
+ * mcx_gpu.h -- C ABI of libmcxgpu.so: the B200 (sm_100a) implementation of the
+ * `mccortex build` hot path.  Plain C, plain pointers and sizes; no CUDA or
+ * torch types.  Every entry point returns an int status (MCX_OK == 0) and
+ * never exits the process; the host driver maps non-zero to the reference's
+ * die() texts ("Hash table is full", ...).
+ *
+ * The reference (mcveanlab/mccortex) has no FFI; the boundary below is the
+ * in-process C interface that src/commands/ctx_build.c calls.  Each function
+ * cites the reference interface it replaces (paths relative to the reference
+ * root).  INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Threading: one host thread per mcx_graph at a time (calls are asynchronous
+ * with respect to the GPU; mcx_graph_sync joins).  Several graphs / devices may
+ * be driven from different threads.
+ */
+#ifndef MCX_GPU_H_
+#define MCX_GPU_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------ */
+#define MCX_OK               0
+#define MCX_ERR_BAD_ARG      1
+#define MCX_ERR_CUDA         2  /* see mcx_last_error() */
+#define MCX_ERR_TABLE_FULL   3  /* reference: die("Hash table is full"), src/graph/hash_table.c:119-123,280 */
+#define MCX_ERR_NOMEM        4  /* reference: ctx_malloc dies, src/global/ctx_alloc.h:24-27 */
+#define MCX_ERR_UNSUPPORTED  5
+#define MCX_ERR_NO_DEVICE    6  /* no CUDA device / driver: there is NO CPU fallback */
+
+/* ---- batch description -------------------------------------------------- */
+/* layout of mcx_read_batch.seq */
+#define MCX_LAYOUT_LINES    0  /* every read is followed by exactly one '\n' ("plain" one-read-per-line text) */
+#define MCX_LAYOUT_OFFSETS  1  /* reads abut; offsets[nreads+1] gives their boundaries */
+/* where seq / qual / offsets live */
+#define MCX_MEM_HOST        0  /* pageable or pinned host memory (pinned = no staging copy; see mcx_host_alloc) */
+#define MCX_MEM_DEVICE      1  /* device memory of the graph's GPU: 16-byte aligned, readable up to nbytes rounded up to 16 */
+
+/* Mirrors what build_graph_from_reads_mt() receives per read (src/tools/build_graph.h:57-61)
+ * plus the SeqLoadingPrefs it is called with (src/tools/build_graph.h:18-24), batched. */
+typedef struct {
+  const char     *seq;       /* bases, ASCII; any byte outside ACGTacgt breaks contigs like the reference's LUT (src/basic/dna.c:8-25) */
+  const char     *qual;      /* NULL, or quality bytes parallel to seq (same layout) */
+  const uint64_t *offsets;   /* MCX_LAYOUT_OFFSETS: nreads+1 byte offsets into seq; else NULL */
+  uint64_t        nreads;    /* MCX_LAYOUT_OFFSETS only (LINES: counted from the terminators) */
+  uint64_t        nbytes;    /* bytes in seq (LINES: including the terminators) */
+  uint32_t        layout;    /* MCX_LAYOUT_* */
+  uint32_t        mem;       /* MCX_MEM_* */
+  uint32_t        colour;    /* SeqLoadingPrefs.colour */
+  uint8_t         fq_cutoff; /* 0 = off; else quality threshold ALREADY including the FASTQ ASCII offset (build_graph.c:202-207) */
+  uint8_t         hp_cutoff; /* 0 = off; else break contigs at homopolymer runs >= hp_cutoff (2 <= hp_cutoff <= k) */
+  uint8_t         reserved[2];
+} mcx_read_batch;
+
+/* Counters of SeqLoadingStats (src/basic/seq_loading_stats.h:5-14) that feed the
+ * .ctx header and the per-task log (src/tools/build_graph.c:173-188,352-386). */
+typedef struct {
+  uint64_t total_bases_read;
+  uint64_t total_bases_loaded;
+  uint64_t contigs_parsed;
+  uint64_t num_kmers_loaded;
+  uint64_t num_kmers_novel;
+  uint64_t num_se_reads;
+  uint64_t num_pe_reads;
+  uint64_t num_good_reads;   /* UINT64_MAX when not computed */
+  uint64_t num_bad_reads;    /* UINT64_MAX when not computed */
+} mcx_load_stats;
+
+typedef struct mcx_graph mcx_graph;
+
+/* ---- library ------------------------------------------------------------ */
+/* Number of usable CUDA devices (0 => nothing in this library can run). */
+int mcx_device_count(void);
+/* Text of the last CUDA error seen by the calling thread's last failing call. */
+const char *mcx_last_error(void);
+/* Pinned host memory for read batches (H2D without a staging copy). */
+int mcx_host_alloc(void **ptr, size_t bytes);
+int mcx_host_free(void *ptr);
+
+/* ---- graph life cycle --------------------------------------------------- */
+/* replaces db_graph_alloc(&g, k, ncols, ncols, capacity, EDGES|COVGS|BKTLOCKS)
+ * (src/graph/db_graph.h:62-64, src/commands/ctx_build.c:335-339) + hash_table_alloc
+ * (src/graph/hash_table.c:16-52).  capacity = number of k-mer slots (what
+ * cmd_get_kmers_in_hash returns, src/graph/cmd_mem.c:38-130); 3 <= k <= 63, k odd. */
+int mcx_graph_create(uint32_t kmer_size, uint32_t ncols, uint64_t capacity, int device, uint32_t flags, mcx_graph **out);
+/* replaces db_graph_dealloc (src/graph/db_graph.h:67) */
+int mcx_graph_destroy(mcx_graph *g);
+/* forget all k-mers (table zeroed), keep the allocation */
+int mcx_graph_clear(mcx_graph *g);
+/* run all subsequent device work of this graph on an existing CUDA stream
+ * (a cudaStream_t / CUstream passed as void*; NULL = the graph's own streams) */
+int mcx_graph_set_stream(mcx_graph *g, void *cuda_stream);
+
+/* ---- the hot path ------------------------------------------------------- */
+/* replaces build_graph(&g, tasks, n, nthreads) -> build_graph_from_reads_mt per read
+ * (src/tools/build_graph.c:192-301).  Asynchronous: returns once the batch is
+ * queued (host buffers may be reused after return unless they are pinned, in which
+ * case they must stay valid until mcx_graph_sync). */
+int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *batch);
+/* replaces build_graph_from_str_mt(&g, colour, seq, len, false) (src/tools/build_graph.h:77-79):
+ * one contig-to-be, synchronous. */
+int mcx_graph_add_str(mcx_graph *g, uint32_t colour, const char *seq, size_t len);
+/* join all queued work; *stats (may be NULL) receives the counters accumulated since the
+ * previous sync (the reference merges per-thread stats the same way,
+ * src/tools/build_graph.c:285-288).  Returns MCX_ERR_TABLE_FULL if any insert overflowed. */
+int mcx_graph_sync(mcx_graph *g, mcx_load_stats *stats);
+
+/* replaces hash_table_print_stats inputs (src/graph/hash_table.h:73): occupancy */
+int mcx_graph_stats(mcx_graph *g, uint64_t *nkmers, uint64_t *capacity);
+
+/* ---- dump --------------------------------------------------------------- */
+/* replaces graph_write_all_kmers_direct / HASH_ITERATE[_SORTED] + graph_write_kmer
+ * (src/graph/graph_writer.c:116-127,182-193): builds, on the device, the .ctx v6 record
+ * stream (W x u64 key, ncols x u32 covg, ncols x u8 edges per k-mer), in ascending key order
+ * if sorted != 0.  The host writes the header (it owns GraphInfo) and streams the records. */
+int mcx_graph_export_begin(mcx_graph *g, int sorted, uint64_t *nrecords, uint32_t *record_bytes);
+int mcx_graph_export_read(mcx_graph *g, uint64_t first_record, uint64_t nrecords, void *host_dst);
+int mcx_graph_export_end(mcx_graph *g);
+
+/* ---- multi-GPU pieces (one graph shard per GPU) --------------------------- */
+/* Kernel B: reads -> canonical (key, edge mask) tuples, binned by owner = top bits of the
+ * Lookup3 hash.  All pointers are device memory of g's GPU; batch must be MCX_MEM_DEVICE /
+ * MCX_LAYOUT_LINES.  keys_out holds nparts bins of cap_per_part tuples x W u64, masks_out
+ * nparts x cap_per_part bytes, counts_out nparts u64 (zeroed by the call, filled on the stream).
+ * A bin overflow is reported by the next mcx_graph_sync as MCX_ERR_TABLE_FULL. */
+int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *batch, uint32_t nparts, uint64_t cap_per_part,
+                    uint64_t *keys_out, uint8_t *masks_out, uint64_t *counts_out);
+/* Kernel C: insert n received tuples (device pointers) into this shard. */
+int mcx_graph_insert_tuples(mcx_graph *g, const uint64_t *keys, const uint8_t *masks, uint64_t n, uint32_t colour);
+/* owner of a key, for tests: same function the kernels use */
+uint32_t mcx_key_owner(const uint64_t *key_words, uint32_t kmer_size, uint32_t nparts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCX_GPU_H_ */

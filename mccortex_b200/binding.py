@@ -1,0 +1,212 @@
+"""ctypes mirror of include/mcx_gpu.h (the C ABI of libmcxgpu.so).
+
+Names and argument meaning follow the reference interface the ABI replaces
+(db_graph_alloc / build_graph / build_graph_from_str_mt / graph_writer_save_mkhdr,
+see the header for file:line), so tests read like the reference's own tests.
+Nothing here computes anything: every method is one C call.
+"""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+MCX_LAYOUT_LINES, MCX_LAYOUT_OFFSETS = 0, 1
+MCX_MEM_HOST, MCX_MEM_DEVICE = 0, 1
+
+_STATUS = {0: "MCX_OK", 1: "MCX_ERR_BAD_ARG", 2: "MCX_ERR_CUDA", 3: "MCX_ERR_TABLE_FULL",
+           4: "MCX_ERR_NOMEM", 5: "MCX_ERR_UNSUPPORTED", 6: "MCX_ERR_NO_DEVICE"}
+
+
+class McxError(RuntimeError):
+    def __init__(self, code, what, detail=""):
+        self.code = code
+        self.status = _STATUS.get(code, str(code))
+        super().__init__("%s failed: %s%s" % (what, self.status, (" (" + detail + ")") if detail else ""))
+
+
+class ReadBatch(C.Structure):
+    _fields_ = [("seq", C.c_void_p), ("qual", C.c_void_p), ("offsets", C.c_void_p),
+                ("nreads", C.c_uint64), ("nbytes", C.c_uint64),
+                ("layout", C.c_uint32), ("mem", C.c_uint32), ("colour", C.c_uint32),
+                ("fq_cutoff", C.c_uint8), ("hp_cutoff", C.c_uint8), ("reserved", C.c_uint8 * 2)]
+
+
+class LoadStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "total_bases_read", "total_bases_loaded", "contigs_parsed", "num_kmers_loaded",
+        "num_kmers_novel", "num_se_reads", "num_pe_reads", "num_good_reads", "num_bad_reads")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def lib_path():
+    return os.path.join(HERE, "lib", "libmcxgpu.so")
+
+
+def driver_path():
+    return os.path.join(HERE, "bin", "mccortex-b200")
+
+
+def build_native(targets=("all",)):
+    """Compile libmcxgpu.so (nvcc, sm_100a) and the C host driver in-tree."""
+    subprocess.check_call(["make", "-s", "-C", HERE] + list(targets))
+
+
+_lib = None
+
+
+def lib():
+    """Load libmcxgpu.so.  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise ImportError("%s is missing: run `make -C mccortex_b200` (or __graft_entry__.build()); "
+                          "mccortex_b200 has no CPU fallback" % p)
+    L = C.CDLL(p)
+    vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+    L.mcx_device_count.restype = C.c_int
+    L.mcx_last_error.restype = C.c_char_p
+    L.mcx_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.mcx_host_free.argtypes = [vp]
+    L.mcx_graph_create.argtypes = [u32, u32, u64, C.c_int, u32, C.POINTER(vp)]
+    L.mcx_graph_destroy.argtypes = [vp]
+    L.mcx_graph_clear.argtypes = [vp]
+    L.mcx_graph_set_stream.argtypes = [vp, vp]
+    L.mcx_graph_add_reads.argtypes = [vp, C.POINTER(ReadBatch)]
+    L.mcx_graph_add_str.argtypes = [vp, u32, C.c_char_p, C.c_size_t]
+    L.mcx_graph_sync.argtypes = [vp, C.POINTER(LoadStats)]
+    L.mcx_graph_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.mcx_graph_export_begin.argtypes = [vp, C.c_int, C.POINTER(u64), C.POINTER(u32)]
+    L.mcx_graph_export_read.argtypes = [vp, u64, u64, vp]
+    L.mcx_graph_export_end.argtypes = [vp]
+    L.mcx_kmer_tuples.argtypes = [vp, C.POINTER(ReadBatch), u32, u64, vp, vp, vp]
+    L.mcx_graph_insert_tuples.argtypes = [vp, vp, vp, u64, u32]
+    L.mcx_key_owner.restype = u32
+    L.mcx_key_owner.argtypes = [C.POINTER(u64), u32, u32]
+    _lib = L
+    return L
+
+
+def _ck(code, what):
+    if code != 0:
+        raise McxError(code, what, (lib().mcx_last_error() or b"").decode(errors="replace"))
+
+
+def device_count():
+    return int(lib().mcx_device_count())
+
+
+def host_alloc(nbytes):
+    """Pinned host buffer (address) for read batches: H2D without a staging copy."""
+    p = C.c_void_p()
+    _ck(lib().mcx_host_alloc(C.byref(p), nbytes), "mcx_host_alloc")
+    return p.value
+
+
+def host_free(addr):
+    _ck(lib().mcx_host_free(C.c_void_p(addr)), "mcx_host_free")
+
+
+def key_owner(key_words, k, nparts):
+    arr = (C.c_uint64 * len(key_words))(*key_words)
+    return int(lib().mcx_key_owner(arr, k, nparts))
+
+
+class Graph:
+    """Device-resident coloured de Bruijn graph shard (reference: dBGraph, src/graph/db_graph.h:23-56)."""
+
+    def __init__(self, kmer_size, ncols=1, capacity=1 << 20, device=0):
+        self.k, self.ncols, self.capacity, self.device = kmer_size, ncols, capacity, device
+        self.W = (kmer_size + 31) // 32
+        h = C.c_void_p()
+        _ck(lib().mcx_graph_create(kmer_size, ncols, capacity, device, 0, C.byref(h)), "mcx_graph_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mcx_graph_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self):
+        _ck(lib().mcx_graph_clear(self.h), "mcx_graph_clear")
+
+    def set_stream(self, cuda_stream):
+        _ck(lib().mcx_graph_set_stream(self.h, C.c_void_p(cuda_stream or None)), "mcx_graph_set_stream")
+
+    # -- build_graph() ----------------------------------------------------------------
+    def _batch(self, seq_addr, nbytes, layout, mem, colour, hp_cutoff, offsets_addr=None, nreads=0,
+               qual_addr=None, fq_cutoff=0):
+        b = ReadBatch()
+        b.seq, b.qual, b.offsets = seq_addr, qual_addr, offsets_addr
+        b.nreads, b.nbytes, b.layout, b.mem, b.colour = nreads, nbytes, layout, mem, colour
+        b.fq_cutoff, b.hp_cutoff = fq_cutoff, hp_cutoff
+        return b
+
+    def add_reads_raw(self, seq_addr, nbytes, layout=MCX_LAYOUT_LINES, mem=MCX_MEM_HOST, colour=0, hp_cutoff=0,
+                      offsets_addr=None, nreads=0, qual_addr=None, fq_cutoff=0):
+        b = self._batch(seq_addr, nbytes, layout, mem, colour, hp_cutoff, offsets_addr, nreads, qual_addr, fq_cutoff)
+        _ck(lib().mcx_graph_add_reads(self.h, C.byref(b)), "mcx_graph_add_reads")
+
+    def add_lines(self, data, colour=0, hp_cutoff=0):
+        """data: bytes in LINES layout (each read followed by one newline), host memory."""
+        buf = C.create_string_buffer(bytes(data), len(data))
+        self.add_reads_raw(C.addressof(buf), len(data), MCX_LAYOUT_LINES, MCX_MEM_HOST, colour, hp_cutoff)
+
+    def add_reads(self, reads, colour=0, hp_cutoff=0):
+        """reads: list of bytes/str; shipped in OFFSETS layout (reads abut + offsets[n+1])."""
+        reads = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+        blob = b"".join(reads)
+        offs = (C.c_uint64 * (len(reads) + 1))()
+        o = 0
+        for i, r in enumerate(reads):
+            offs[i] = o
+            o += len(r)
+        offs[len(reads)] = o
+        buf = C.create_string_buffer(blob, max(len(blob), 1))
+        self.add_reads_raw(C.addressof(buf), len(blob), MCX_LAYOUT_OFFSETS, MCX_MEM_HOST, colour, hp_cutoff,
+                           C.addressof(offs), len(reads))
+
+    def add_str(self, seq, colour=0):
+        if isinstance(seq, str):
+            seq = seq.encode()
+        _ck(lib().mcx_graph_add_str(self.h, colour, seq, len(seq)), "mcx_graph_add_str")
+
+    def sync(self):
+        st = LoadStats()
+        _ck(lib().mcx_graph_sync(self.h, C.byref(st)), "mcx_graph_sync")
+        return st
+
+    def stats(self):
+        n, cap = C.c_uint64(), C.c_uint64()
+        _ck(lib().mcx_graph_stats(self.h, C.byref(n), C.byref(cap)), "mcx_graph_stats")
+        return int(n.value), int(cap.value)
+
+    # -- graph_writer: records only (the header belongs to the host driver) --------------
+    def export_records(self, sorted=True):
+        n, rb = C.c_uint64(), C.c_uint32()
+        _ck(lib().mcx_graph_export_begin(self.h, 1 if sorted else 0, C.byref(n), C.byref(rb)), "mcx_graph_export_begin")
+        try:
+            buf = C.create_string_buffer(max(int(n.value) * int(rb.value), 1))
+            _ck(lib().mcx_graph_export_read(self.h, 0, n.value, buf), "mcx_graph_export_read")
+            return buf.raw[:int(n.value) * int(rb.value)], int(n.value), int(rb.value)
+        finally:
+            lib().mcx_graph_export_end(self.h)
+
+    # -- multi-GPU pieces ------------------------------------------------------------------
+    def kmer_tuples(self, seq_dev_addr, nbytes, nparts, cap_per_part, keys_addr, masks_addr, counts_addr, hp_cutoff=0):
+        b = self._batch(seq_dev_addr, nbytes, MCX_LAYOUT_LINES, MCX_MEM_DEVICE, 0, hp_cutoff)
+        _ck(lib().mcx_kmer_tuples(self.h, C.byref(b), nparts, cap_per_part, keys_addr, masks_addr, counts_addr),
+            "mcx_kmer_tuples")
+
+    def insert_tuples(self, keys_addr, masks_addr, n, colour=0):
+        _ck(lib().mcx_graph_insert_tuples(self.h, keys_addr, masks_addr, n, colour), "mcx_graph_insert_tuples")

@@ -1,0 +1,380 @@
+// mcx_abi.cu -- extern "C" layer of libmcxgpu.so (see include/mcx_gpu.h).
+//
+// Owns: the device table, counters, the H2D staging ring for host batches, and the
+// export buffer.  No CPU implementation of any part of the hot path lives here: if
+// there is no CUDA device every entry point fails with MCX_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../include/mcx_gpu.h"
+#include "mcx_build.h"
+#include "mcx_chunk.cuh"
+
+#define MCX_NSTAGE 3
+#define MCX_STAGE_POS (32ull << 20)                 /* positions per staged piece of a host batch */
+#define MCX_STAGE_BYTES (MCX_STAGE_POS + 256ull)    /* + look-back / look-ahead / alignment slack */
+
+static thread_local char g_err[256] = "";
+static int fail_cuda(cudaError_t e, const char *what)
+{
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return e == cudaErrorMemoryAllocation ? MCX_ERR_NOMEM : MCX_ERR_CUDA;
+}
+#define CU(x) do { cudaError_t e_ = (x); if(e_ != cudaSuccess) return fail_cuda(e_, #x); } while(0)
+
+struct mcx_graph {
+  int device;
+  uint32_t k, W, ncols;
+  uint64_t capacity;
+  McxTable table;
+  unsigned long long *d_counters;
+  cudaStream_t streams[MCX_NSTAGE];
+  cudaEvent_t events[MCX_NSTAGE];
+  uint8_t *d_stage[MCX_NSTAGE];
+  uint8_t *h_stage[MCX_NSTAGE];
+  bool stage_ready;
+  int next;
+  cudaStream_t user_stream; bool use_user_stream;
+  uint64_t occ_bound;      // upper bound on occurrences ever sent (saturation guard)
+  uint64_t pend_positions; // byte positions queued since the last sync
+  uint64_t pend_offsets_reads, pend_offsets_bases; // OFFSETS batches: counted on the host
+  uint64_t nkmers;         // slots claimed so far (updated at sync)
+  McxExport exp; bool exp_valid;
+  uint8_t *d_tmp; size_t d_tmp_bytes; // scratch for OFFSETS -> LINES repack
+};
+
+extern "C" int mcx_device_count(void)
+{
+  int n = 0;
+  if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" const char *mcx_last_error(void) { return g_err; }
+
+extern "C" int mcx_host_alloc(void **ptr, size_t bytes)
+{
+  if(!ptr) return MCX_ERR_BAD_ARG;
+  if(mcx_device_count() == 0) return MCX_ERR_NO_DEVICE;
+  CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return MCX_OK;
+}
+extern "C" int mcx_host_free(void *ptr) { if(ptr) CU(cudaFreeHost(ptr)); return MCX_OK; }
+
+static cudaStream_t cur_stream(mcx_graph *g, int slot) { return g->use_user_stream ? g->user_stream : g->streams[slot]; }
+
+extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, int device, uint32_t flags, mcx_graph **out)
+{
+  (void)flags;
+  if(!out || k < 3 || k > 63 || !(k & 1u) || ncols == 0 || ncols > 4096 || capacity == 0) return MCX_ERR_BAD_ARG;
+  int ndev = mcx_device_count();
+  if(ndev == 0) { snprintf(g_err, sizeof(g_err), "no CUDA device: libmcxgpu has no CPU fallback"); return MCX_ERR_NO_DEVICE; }
+  if(device < 0 || device >= ndev) return MCX_ERR_BAD_ARG;
+  CU(cudaSetDevice(device));
+  mcx_graph *g = (mcx_graph *)calloc(1, sizeof(*g));
+  if(!g) return MCX_ERR_NOMEM;
+  g->device = device; g->k = k; g->W = (k + 31u) / 32u; g->ncols = ncols;
+  g->capacity = capacity;
+  g->table.nslots = (capacity + 1ull) & ~1ull;
+  g->table.stride = mcx_slot_words(g->W, ncols);
+  g->table.ncols = ncols;
+  size_t bytes = (size_t)g->table.nslots * g->table.stride * 4u;
+  cudaError_t e = cudaMalloc(&g->table.slots, bytes);
+  if(e != cudaSuccess) { free(g); return fail_cuda(e, "cudaMalloc(table)"); }
+  e = cudaMalloc(&g->d_counters, MCX_NCOUNTERS * sizeof(unsigned long long));
+  if(e != cudaSuccess) { cudaFree(g->table.slots); free(g); return fail_cuda(e, "cudaMalloc(counters)"); }
+  for(int i = 0; i < MCX_NSTAGE; i++) {
+    cudaStreamCreateWithFlags(&g->streams[i], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&g->events[i], cudaEventDisableTiming);
+  }
+  cudaMemsetAsync(g->table.slots, 0, bytes, g->streams[0]);
+  cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), g->streams[0]);
+  e = cudaStreamSynchronize(g->streams[0]);
+  if(e != cudaSuccess) { int r = fail_cuda(e, "memset(table)"); mcx_graph_destroy(g); return r; }
+  *out = g;
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_destroy(mcx_graph *g)
+{
+  if(!g) return MCX_OK;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  mcx_export_free(&g->exp);
+  for(int i = 0; i < MCX_NSTAGE; i++) {
+    if(g->d_stage[i]) cudaFree(g->d_stage[i]);
+    if(g->h_stage[i]) cudaFreeHost(g->h_stage[i]);
+    if(g->streams[i]) cudaStreamDestroy(g->streams[i]);
+    if(g->events[i]) cudaEventDestroy(g->events[i]);
+  }
+  if(g->d_tmp) cudaFree(g->d_tmp);
+  if(g->d_counters) cudaFree(g->d_counters);
+  if(g->table.slots) cudaFree(g->table.slots);
+  free(g);
+  return MCX_OK;
+}
+
+static int sync_all(mcx_graph *g)
+{
+  CU(cudaSetDevice(g->device));
+  for(int i = 0; i < MCX_NSTAGE; i++) CU(cudaStreamSynchronize(g->streams[i]));
+  if(g->use_user_stream) CU(cudaStreamSynchronize(g->user_stream));
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_clear(mcx_graph *g)
+{
+  if(!g) return MCX_ERR_BAD_ARG;
+  int r = sync_all(g); if(r) return r;
+  cudaStream_t st = cur_stream(g, 0);
+  CU(cudaMemsetAsync(g->table.slots, 0, (size_t)g->table.nslots * g->table.stride * 4u, st));
+  CU(cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), st));
+  g->occ_bound = 0; g->pend_positions = 0; g->pend_offsets_reads = g->pend_offsets_bases = 0; g->nkmers = 0;
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_set_stream(mcx_graph *g, void *cuda_stream)
+{
+  if(!g) return MCX_ERR_BAD_ARG;
+  int r = sync_all(g); if(r) return r;
+  g->use_user_stream = cuda_stream != NULL;
+  g->user_stream = (cudaStream_t)cuda_stream;
+  return MCX_OK;
+}
+
+static int ensure_stage(mcx_graph *g)
+{
+  if(g->stage_ready) return MCX_OK;
+  for(int i = 0; i < MCX_NSTAGE; i++) {
+    CU(cudaMalloc(&g->d_stage[i], MCX_STAGE_BYTES));
+    CU(cudaHostAlloc(&g->h_stage[i], MCX_STAGE_BYTES, cudaHostAllocDefault));
+  }
+  g->stage_ready = true;
+  return MCX_OK;
+}
+
+static McxBuildParams make_params(mcx_graph *g, const mcx_read_batch *b, const uint8_t *dseq, uint64_t nbytes,
+                                  uint64_t r_begin, uint64_t r_end)
+{
+  McxBuildParams p;
+  p.seq = dseq; p.nbytes = nbytes; p.r_begin = r_begin; p.r_end = r_end;
+  p.k = g->k; p.hp_cutoff = b->hp_cutoff; p.colour = b->colour;
+  p.may_saturate = g->occ_bound >= 0xF0000000ull;
+  p.counters = g->d_counters;
+  return p;
+}
+
+// LINES batch resident on the device
+static int add_lines_device(mcx_graph *g, const mcx_read_batch *b, const uint8_t *dseq, uint64_t nbytes)
+{
+  if(((uintptr_t)dseq & 15u) != 0) { snprintf(g_err, sizeof(g_err), "device seq buffer must be 16-byte aligned"); return MCX_ERR_BAD_ARG; }
+  g->occ_bound += nbytes;
+  McxBuildParams p = make_params(g, b, dseq, nbytes, 0, nbytes);
+  CU(mcx_launch_build_fused(p, g->table, cur_stream(g, 0)));
+  g->pend_positions += nbytes;
+  return MCX_OK;
+}
+
+// LINES batch in host memory: cut into pieces of MCX_STAGE_POS positions; each piece ships
+// with 16 bytes of look-back and 80 of look-ahead so windows and edges that straddle a cut
+// see their neighbours; H2D and kernels of consecutive pieces overlap on a ring of streams.
+static int add_lines_host(mcx_graph *g, const mcx_read_batch *b, const uint8_t *hseq, uint64_t nbytes)
+{
+  int r = ensure_stage(g); if(r) return r;
+  cudaPointerAttributes attr;
+  bool pinned = (cudaPointerGetAttributes(&attr, hseq) == cudaSuccess) && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  g->occ_bound += nbytes;
+  for(uint64_t pos = 0; pos < nbytes; pos += MCX_STAGE_POS) {
+    uint64_t pend = pos + MCX_STAGE_POS < nbytes ? pos + MCX_STAGE_POS : nbytes;
+    uint64_t b0 = pos ? pos - MCX_LB : 0;
+    uint64_t b1 = pend + MCX_TAIL < nbytes ? pend + MCX_TAIL : nbytes;
+    int s = g->next; g->next = (g->next + 1) % MCX_NSTAGE;
+    cudaStream_t st = cur_stream(g, s);
+    CU(cudaEventSynchronize(g->events[s])); // previous user of this slot is done
+    const uint8_t *src = hseq + b0;
+    if(!pinned) { memcpy(g->h_stage[s], src, b1 - b0); src = g->h_stage[s]; }
+    CU(cudaMemcpyAsync(g->d_stage[s], src, b1 - b0, cudaMemcpyHostToDevice, st));
+    McxBuildParams p = make_params(g, b, g->d_stage[s], b1 - b0, pos - b0, pend - b0);
+    CU(mcx_launch_build_fused(p, g->table, st));
+    CU(cudaEventRecord(g->events[s], st));
+  }
+  g->pend_positions += nbytes;
+  return MCX_OK;
+}
+
+static int ensure_tmp(mcx_graph *g, size_t bytes)
+{
+  if(g->d_tmp_bytes >= bytes) return MCX_OK;
+  int r = sync_all(g); if(r) return r;
+  if(g->d_tmp) cudaFree(g->d_tmp);
+  g->d_tmp = NULL; g->d_tmp_bytes = 0;
+  CU(cudaMalloc(&g->d_tmp, bytes));
+  g->d_tmp_bytes = bytes;
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
+{
+  if(!g || !b || b->colour >= g->ncols) return MCX_ERR_BAD_ARG;
+  if(b->nbytes && !b->seq) return MCX_ERR_BAD_ARG;
+  if(b->hp_cutoff == 1 || b->hp_cutoff > g->k) {
+    snprintf(g_err, sizeof(g_err), "hp_cutoff must be 0 or in [2, k]"); return MCX_ERR_UNSUPPORTED;
+  }
+  if(b->fq_cutoff && b->qual) {
+    snprintf(g_err, sizeof(g_err), "quality cut-off path not built yet"); return MCX_ERR_UNSUPPORTED;
+  }
+  CU(cudaSetDevice(g->device));
+  if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
+
+  if(b->layout == MCX_LAYOUT_LINES) {
+    if(b->nbytes == 0) return MCX_OK;
+    if(b->mem == MCX_MEM_DEVICE) return add_lines_device(g, b, (const uint8_t *)b->seq, b->nbytes);
+    if(b->mem == MCX_MEM_HOST) return add_lines_host(g, b, (const uint8_t *)b->seq, b->nbytes);
+    return MCX_ERR_BAD_ARG;
+  }
+  if(b->layout != MCX_LAYOUT_OFFSETS || (!b->offsets && b->nreads)) return MCX_ERR_BAD_ARG;
+  if(b->nreads == 0) return MCX_OK;
+
+  // OFFSETS -> LINES on the device: read r shifts right by r bytes and gains a terminator
+  const uint64_t lines_bytes = b->nbytes + b->nreads;
+  const size_t off_bytes = (size_t)(b->nreads + 1) * sizeof(uint64_t);
+  const size_t lines_off = 0, offs_off = (lines_bytes + 255) & ~(size_t)255;
+  size_t raw_off = (offs_off + off_bytes + 255) & ~(size_t)255;
+  size_t need = raw_off + (b->mem == MCX_MEM_HOST ? ((b->nbytes + 255) & ~(size_t)255) : 0);
+  int r = ensure_tmp(g, need + 256); if(r) return r;
+  cudaStream_t st = cur_stream(g, 0);
+  uint64_t *d_off = (uint64_t *)(g->d_tmp + offs_off);
+  const uint8_t *d_raw = (const uint8_t *)b->seq;
+  if(b->mem == MCX_MEM_HOST) {
+    if(b->offsets[0] != 0 || b->offsets[b->nreads] != b->nbytes) return MCX_ERR_BAD_ARG;
+    CU(cudaMemcpyAsync(g->d_tmp + raw_off, b->seq, b->nbytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_off, b->offsets, off_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st)); // pageable sources: make "host buffers reusable on return" true
+    d_raw = g->d_tmp + raw_off;
+  } else if(b->mem == MCX_MEM_DEVICE) {
+    CU(cudaMemcpyAsync(d_off, b->offsets, off_bytes, cudaMemcpyDeviceToDevice, st));
+  } else return MCX_ERR_BAD_ARG;
+  CU(mcx_launch_repack_lines(d_raw, d_off, b->nreads, g->d_tmp + lines_off, st));
+  g->occ_bound += lines_bytes;
+  McxBuildParams p = make_params(g, b, g->d_tmp + lines_off, lines_bytes, 0, lines_bytes);
+  CU(mcx_launch_build_fused(p, g->table, st));
+  g->pend_positions += lines_bytes;
+  // d_tmp is reused by the next OFFSETS batch: order it behind this one
+  CU(cudaStreamSynchronize(st));
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_add_str(mcx_graph *g, uint32_t colour, const char *seq, size_t len)
+{
+  if(!g || !seq) return MCX_ERR_BAD_ARG;
+  char *buf = (char *)malloc(len + 1);
+  if(!buf) return MCX_ERR_NOMEM;
+  memcpy(buf, seq, len); buf[len] = '\n';
+  mcx_read_batch b; memset(&b, 0, sizeof(b));
+  b.seq = buf; b.nbytes = len + 1; b.layout = MCX_LAYOUT_LINES; b.mem = MCX_MEM_HOST; b.colour = colour;
+  int r = mcx_graph_add_reads(g, &b);
+  if(r == MCX_OK) r = sync_all(g);
+  free(buf);
+  return r;
+}
+
+extern "C" int mcx_graph_sync(mcx_graph *g, mcx_load_stats *stats)
+{
+  if(!g) return MCX_ERR_BAD_ARG;
+  int r = sync_all(g); if(r) return r;
+  unsigned long long c[MCX_NCOUNTERS];
+  CU(cudaMemcpy(c, g->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+  CU(cudaMemset(g->d_counters, 0, sizeof(c)));
+  g->nkmers += c[MCX_CNT_NOVEL];
+  if(stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->num_kmers_loaded = c[MCX_CNT_KMERS];
+    stats->num_kmers_novel = c[MCX_CNT_NOVEL];
+    stats->contigs_parsed = c[MCX_CNT_CONTIGS];
+    // every contig of n windows spans n + k - 1 bases (build_graph.c:173-176)
+    stats->total_bases_loaded = c[MCX_CNT_KMERS] + (uint64_t)(g->k - 1u) * c[MCX_CNT_CONTIGS];
+    stats->num_se_reads = c[MCX_CNT_READS];
+    stats->total_bases_read = g->pend_positions - c[MCX_CNT_READS];
+    stats->num_good_reads = UINT64_MAX;
+    stats->num_bad_reads = UINT64_MAX;
+  }
+  g->pend_positions = 0;
+  if(c[MCX_CNT_FULL]) { snprintf(g_err, sizeof(g_err), "Hash table is full"); return MCX_ERR_TABLE_FULL; }
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_stats(mcx_graph *g, uint64_t *nkmers, uint64_t *capacity)
+{
+  if(!g) return MCX_ERR_BAD_ARG;
+  if(nkmers) *nkmers = g->nkmers;
+  if(capacity) *capacity = g->capacity;
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_export_begin(mcx_graph *g, int sorted, uint64_t *nrecords, uint32_t *record_bytes)
+{
+  if(!g) return MCX_ERR_BAD_ARG;
+  int r = sync_all(g); if(r) return r;
+  if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
+  cudaError_t e = mcx_export_build(g->table, g->k, sorted != 0, &g->exp, cur_stream(g, 0));
+  if(e != cudaSuccess) return fail_cuda(e, "export");
+  g->exp_valid = true;
+  if(nrecords) *nrecords = g->exp.nrec;
+  if(record_bytes) *record_bytes = g->exp.rec_bytes;
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_export_read(mcx_graph *g, uint64_t first, uint64_t n, void *host_dst)
+{
+  if(!g || !g->exp_valid || first + n > g->exp.nrec || (!host_dst && n)) return MCX_ERR_BAD_ARG;
+  if(n == 0) return MCX_OK;
+  CU(cudaSetDevice(g->device));
+  CU(cudaMemcpy(host_dst, g->exp.records + first * g->exp.rec_bytes, n * g->exp.rec_bytes, cudaMemcpyDeviceToHost));
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_export_end(mcx_graph *g)
+{
+  if(!g) return MCX_ERR_BAD_ARG;
+  mcx_export_free(&g->exp); g->exp_valid = false;
+  return MCX_OK;
+}
+
+extern "C" int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *b, uint32_t nparts, uint64_t cap_per_part,
+                               uint64_t *keys_out, uint8_t *masks_out, uint64_t *counts_out)
+{
+  if(!g || !b || !nparts || !cap_per_part || !keys_out || !masks_out || !counts_out) return MCX_ERR_BAD_ARG;
+  if(b->layout != MCX_LAYOUT_LINES || b->mem != MCX_MEM_DEVICE || ((uintptr_t)b->seq & 15u)) return MCX_ERR_BAD_ARG;
+  if(b->hp_cutoff == 1 || b->hp_cutoff > g->k || (b->fq_cutoff && b->qual)) return MCX_ERR_UNSUPPORTED;
+  CU(cudaSetDevice(g->device));
+  cudaStream_t st = cur_stream(g, 0);
+  CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
+  McxTupleBins bins;
+  bins.keys = keys_out; bins.masks = masks_out; bins.cursor = (unsigned long long *)counts_out;
+  bins.cap = cap_per_part; bins.nparts = nparts;
+  McxBuildParams p = make_params(g, b, (const uint8_t *)b->seq, b->nbytes, 0, b->nbytes);
+  CU(mcx_launch_kmer_tuples(p, bins, st));
+  g->pend_positions += b->nbytes;
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_insert_tuples(mcx_graph *g, const uint64_t *keys, const uint8_t *masks, uint64_t n, uint32_t colour)
+{
+  if(!g || colour >= g->ncols || (n && (!keys || !masks))) return MCX_ERR_BAD_ARG;
+  CU(cudaSetDevice(g->device));
+  if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
+  g->occ_bound += n;
+  CU(mcx_launch_insert_tuples(keys, masks, n, g->k, g->table, colour, g->occ_bound >= 0xF0000000ull, g->d_counters,
+                              cur_stream(g, 0)));
+  return MCX_OK;
+}
+
+extern "C" uint32_t mcx_key_owner(const uint64_t *key_words, uint32_t k, uint32_t nparts)
+{
+  uint32_t hb, hc;
+  if(k <= 31) { McxKmer<1> key; key.b[0] = key_words[0]; hc = mcx_lookup3<1>(key, 0u, &hb); }
+  else { McxKmer<2> key; key.b[0] = key_words[0]; key.b[1] = key_words[1]; hc = mcx_lookup3<2>(key, 0u, &hb); }
+  return mcx_owner(hc, nparts);
+}

@@ -1,0 +1,324 @@
+// mcx_build.cu -- the build hot path on sm_100a.
+//
+// Kernel A  mcx_build_fused_kernel<W>: reads -> k-mers -> canonical key -> Lookup3 ->
+//           find-or-insert -> covg++ -> edge OR, in one pass (single-GPU path; no tuple
+//           round trip through HBM).
+// Kernel B  mcx_kmer_tuples_kernel<W>: same front end, but emits (key, edge-mask) tuples
+//           binned by owning GPU (multi-GPU path, before the all-to-all).
+// Kernel C  mcx_insert_tuples_kernel<W>: inserts received tuples into the local shard.
+//
+// Replaces the reference's per-read CPU loop (relative to /root/reference):
+//   build_graph_from_reads_mt / load_read / build_graph_from_str_mt  src/tools/build_graph.c:122-231
+//   seq_contig_start2 / seq_contig_end2                              src/basic/seq_reader.c:61-172
+//   binary_kmer_from_str / left_shift_add / reverse_complement / get_key  src/graph/binary_kmer.{h,c}
+//   bklk3_hashlittle                                                 src/kmer/kmer_hash.h:162-211
+//   hash_table_find_or_insert_mt, db_graph_update_node_mt, db_graph_add_edge_mt
+//
+// Front end (shared by A and B): persistent CTAs walk 2 KB chunks of the batch byte
+// buffer.  One elected thread streams the next chunk global->shared with a 1-D TMA bulk
+// copy (cp.async.bulk + mbarrier complete_tx) while the CTA works on the current one
+// (double buffer).  Phase 1 turns ASCII into 2-bit packed words + validity bit masks
+// (16 bytes per thread, SWAR); phase 2a evaluates the contig rules per window into a
+// valid-window bit mask; phase 2b gives every thread one window per round: funnel-shift
+// the k-mer out of the packed words, reverse-complement with brev, pick the canonical
+// key, hash, build the edge mask from the neighbouring windows' valid bits.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mcx_chunk.cuh"
+#include "mcx_table.cuh"
+#include "mcx_build.h"
+
+#define MCX_THREADS 256
+
+struct __align__(128) McxChunkSmem {
+  uint8_t raw[2][MCX_RAW];
+  uint32_t pk[MCX_PKW];
+  uint32_t bad[MCX_MSW];
+  uint32_t eq[MCX_MSW];
+  uint32_t vmask[MCX_VW];
+  unsigned long long bar[2];
+  unsigned long long red[MCX_NCOUNTERS];
+};
+
+// ---------------------------------------------------------------- TMA / mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while(!done);
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void issue_chunk_load(McxChunkSmem &sm, const McxBuildParams &p, uint64_t chunk, uint32_t buf)
+{
+  uint64_t cs = chunk * (uint64_t)MCX_T;
+  uint64_t src_off = cs ? cs - MCX_LB : 0;
+  uint32_t dst_off = cs ? 0 : MCX_LB;
+  uint64_t avail = (p.nbytes - src_off + 15ull) & ~15ull; // p.seq is readable up to nbytes rounded up to 16
+  uint32_t want = MCX_RAW - dst_off;
+  uint32_t bytes = avail < want ? (uint32_t)avail : want;
+  mbar_expect_tx(&sm.bar[buf], bytes);
+  tma_load_1d(&sm.raw[buf][dst_off], p.seq + src_off, bytes, &sm.bar[buf]);
+}
+
+// ---------------------------------------------------------------- sinks
+// what to do with one occurrence
+template <int W> struct FusedSink {
+  McxTable t; uint32_t colour; bool may_saturate;
+  __device__ __forceinline__ void operator()(const McxOcc<W> &o, uint64_t &novel, uint32_t &full)
+  {
+    int r = mcx_table_add<W>(t, o.key, o.hc, o.hb, colour, o.emask, may_saturate);
+    novel += (r == 1);
+    full |= (r == 2);
+  }
+};
+
+// tuples binned by owner: bins[d] holds {keys[cap][W], masks[cap]} with an atomic cursor
+template <int W> struct TupleSink {
+  McxTupleBins b;
+  __device__ __forceinline__ void operator()(const McxOcc<W> &o, uint64_t &novel, uint32_t &full)
+  {
+    (void)novel;
+    uint32_t d = mcx_owner(o.hc, b.nparts);
+    // warp-aggregate the cursor bump per destination
+    uint32_t peers = __match_any_sync(__activemask(), d);
+    uint32_t leader = __ffs(peers) - 1u, lane = threadIdx.x & 31u;
+    unsigned long long base = 0;
+    if(lane == leader) base = atomicAdd(&b.cursor[d], (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    uint64_t at = base + __popc(peers & ((1u << lane) - 1u));
+    if(at >= b.cap) { full = 1; return; }
+    uint64_t *kd = b.keys + ((uint64_t)d * b.cap + at) * W;
+#pragma unroll
+    for(int w = 0; w < W; w++) kd[w] = o.key.b[w];
+    b.masks[(uint64_t)d * b.cap + at] = (uint8_t)o.emask;
+  }
+};
+
+// ---------------------------------------------------------------- front end
+template <int W, class Sink>
+__device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sink)
+{
+  __shared__ McxChunkSmem sm;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  const uint64_t c_first = p.r_begin / MCX_T, c_last = (p.r_end + MCX_T - 1) / MCX_T;
+
+  if(tid == 0) {
+    mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if(tid < MCX_NCOUNTERS) sm.red[tid] = 0;
+  // over-read padding of the staged arrays must be defined (it is shifted in, then masked off)
+  if(tid < 4) { sm.pk[MCX_RAW / 16u + tid] = 0; sm.bad[MCX_RAW / 32u + tid] = 0xFFFFFFFFu; sm.eq[MCX_RAW / 32u + tid] = 0; }
+  __syncthreads();
+
+  uint64_t chunk = c_first + blockIdx.x;
+  if(tid == 0 && chunk < c_last) issue_chunk_load(sm, p, chunk, 0);
+
+  uint64_t n_kmers = 0, n_novel = 0, n_contigs = 0, n_reads = 0;
+  uint32_t full = 0;
+
+  for(uint32_t it = 0; chunk < c_last; chunk += gridDim.x, it++) {
+    const uint32_t buf = it & 1u;
+    const uint64_t cs = chunk * (uint64_t)MCX_T;
+    mbar_wait(&sm.bar[buf], (it >> 1) & 1u);
+
+    // ---- phase 1: ASCII -> packed bases + masks, 16 bytes per thread
+    if(tid < MCX_RAW / 16u) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(&sm.raw[buf][tid * 16u]);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t prev = tid ? sm.raw[buf][tid * 16u - 1u] : 0u;
+      uint64_t gpos = cs - MCX_LB + tid * 16ull; // wraps for the look-back of chunk 0: handled in convert16
+      uint32_t pk, b16, e16, n16;
+      mcx_convert16(w, prev, gpos, p.nbytes, &pk, &b16, &e16, &n16);
+      sm.pk[tid] = pk;
+      reinterpret_cast<uint16_t *>(sm.bad)[tid] = (uint16_t)b16;
+      reinterpret_cast<uint16_t *>(sm.eq)[tid] = (uint16_t)e16;
+      // read terminators owned by this launch and this chunk
+      if(n16 && tid >= MCX_LB / 16u && tid < (MCX_LB + MCX_T) / 16u) {
+        for(uint32_t i = 0; i < 16u; i++)
+          if(((n16 >> i) & 1u) && gpos + i >= p.r_begin && gpos + i < p.r_end) n_reads++;
+      }
+    }
+    __syncthreads();
+    // raw[buf^1] was last read in phase 1 of the previous iteration: safe to refill
+    if(tid == 0 && chunk + gridDim.x < c_last) issue_chunk_load(sm, p, chunk + gridDim.x, buf ^ 1u);
+
+    // ---- phase 2a: contig rules -> valid-window bit mask for windows cs-1 .. cs+T
+    for(uint32_t i = tid; i < MCX_VW * 32u; i += MCX_THREADS) {
+      bool ok = (i < MCX_T + 2u) && mcx_chunk_window_ok(sm.bad, sm.eq, i, p.k, p.hp_cutoff);
+      uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+      if(lane == 0) sm.vmask[i >> 5] = m;
+    }
+    __syncthreads();
+
+    // ---- phase 2b: one window per thread per round
+#pragma unroll 1
+    for(uint32_t j = 0; j < MCX_T / MCX_THREADS; j++) {
+      const uint32_t i = 1u + j * MCX_THREADS + tid;
+      const uint64_t g = cs + (i - 1u);
+      if(mcx_get_bit(sm.vmask, i) && g >= p.r_begin && g < p.r_end) {
+        McxOcc<W> o = mcx_chunk_occurrence<W>(sm.pk, sm.vmask, i, p.k);
+        n_kmers++;
+        n_contigs += !mcx_get_bit(sm.vmask, i - 1u);
+        sink(o, n_novel, full);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- counters: warp shuffle -> shared -> one global atomic per CTA per counter
+  for(int s = 16; s > 0; s >>= 1) {
+    n_kmers += __shfl_xor_sync(0xFFFFFFFFu, n_kmers, s);
+    n_novel += __shfl_xor_sync(0xFFFFFFFFu, n_novel, s);
+    n_contigs += __shfl_xor_sync(0xFFFFFFFFu, n_contigs, s);
+    n_reads += __shfl_xor_sync(0xFFFFFFFFu, n_reads, s);
+    full |= __shfl_xor_sync(0xFFFFFFFFu, full, s);
+  }
+  if(lane == 0) {
+    atomicAdd(&sm.red[MCX_CNT_KMERS], (unsigned long long)n_kmers);
+    atomicAdd(&sm.red[MCX_CNT_NOVEL], (unsigned long long)n_novel);
+    atomicAdd(&sm.red[MCX_CNT_CONTIGS], (unsigned long long)n_contigs);
+    atomicAdd(&sm.red[MCX_CNT_READS], (unsigned long long)n_reads);
+    if(full) atomicOr(&sm.red[MCX_CNT_FULL], 1ull);
+  }
+  __syncthreads();
+  if(tid < MCX_NCOUNTERS && sm.red[tid]) {
+    if(tid == MCX_CNT_FULL) atomicOr(&p.counters[tid], 1ull);
+    else atomicAdd(&p.counters[tid], sm.red[tid]);
+  }
+}
+
+template <int W>
+__global__ void __launch_bounds__(MCX_THREADS, 4) mcx_build_fused_kernel(McxBuildParams p, McxTable t)
+{
+  FusedSink<W> sink{t, p.colour, p.may_saturate != 0};
+  mcx_front_end<W>(p, sink);
+}
+
+template <int W>
+__global__ void __launch_bounds__(MCX_THREADS, 4) mcx_kmer_tuples_kernel(McxBuildParams p, McxTupleBins b)
+{
+  TupleSink<W> sink{b};
+  mcx_front_end<W>(p, sink);
+}
+
+// ---------------------------------------------------------------- kernel C
+// one tuple per thread; tuples are (key words, edge mask) already canonical, so only
+// hash + find-or-insert + covg++ + edge OR remain.
+template <int W>
+__global__ void __launch_bounds__(MCX_THREADS, 4) mcx_insert_tuples_kernel(const uint64_t *__restrict__ keys,
+                                                                           const uint8_t *__restrict__ masks,
+                                                                           uint64_t n, McxTable t, uint32_t colour,
+                                                                           int may_saturate, unsigned long long *counters)
+{
+  uint64_t n_novel = 0, n_kmers = 0; uint32_t full = 0;
+  for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    McxKmer<W> key;
+#pragma unroll
+    for(int w = 0; w < W; w++) key.b[w] = keys[i * W + w];
+    uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
+    int r = mcx_table_add<W>(t, key, hc, hb, colour, masks[i], may_saturate != 0);
+    n_novel += (r == 1); full |= (r == 2); n_kmers++;
+  }
+  for(int s = 16; s > 0; s >>= 1) {
+    n_novel += __shfl_xor_sync(0xFFFFFFFFu, n_novel, s);
+    n_kmers += __shfl_xor_sync(0xFFFFFFFFu, n_kmers, s);
+    full |= __shfl_xor_sync(0xFFFFFFFFu, full, s);
+  }
+  if((threadIdx.x & 31u) == 0) {
+    if(n_novel) atomicAdd(&counters[MCX_CNT_NOVEL], (unsigned long long)n_novel);
+    if(n_kmers) atomicAdd(&counters[MCX_CNT_INSERTED], (unsigned long long)n_kmers);
+    if(full) atomicOr(&counters[MCX_CNT_FULL], 1ull);
+  }
+}
+
+// ---------------------------------------------------------------- repack
+// OFFSETS layout (reads abut, offsets[n+1]) -> LINES layout (each read followed by '\n'):
+// read r moves from [off[r], off[r+1]) to [off[r]+r, off[r+1]+r), terminator at off[r+1]+r.
+__global__ void mcx_repack_lines_kernel(const uint8_t *__restrict__ src, const uint64_t *__restrict__ off, uint64_t nreads,
+                                        uint8_t *__restrict__ dst)
+{
+  const uint32_t lane = threadIdx.x & 31u;
+  uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for(uint64_t r = warp; r < nreads; r += nwarps) {
+    uint64_t a = off[r], b = off[r + 1];
+    for(uint64_t i = a + lane; i < b; i += 32) dst[i + r] = src[i];
+    if(lane == 0) dst[b + r] = '\n';
+  }
+}
+
+// ---------------------------------------------------------------- launchers
+static int g_num_sms = 0;
+static int num_sms()
+{
+  if(!g_num_sms) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if(g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static unsigned grid_for_chunks(const McxBuildParams &p, int ctas_per_sm)
+{
+  uint64_t nch = (p.r_end + MCX_T - 1) / MCX_T - p.r_begin / MCX_T;
+  uint64_t g = (uint64_t)num_sms() * ctas_per_sm;
+  return (unsigned)(nch < g ? (nch ? nch : 1) : g);
+}
+
+cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, cudaStream_t st)
+{
+  if(p.r_end <= p.r_begin) return cudaSuccess;
+  unsigned grid = grid_for_chunks(p, 4);
+  if(p.k <= 31) mcx_build_fused_kernel<1><<<grid, MCX_THREADS, 0, st>>>(p, t);
+  else mcx_build_fused_kernel<2><<<grid, MCX_THREADS, 0, st>>>(p, t);
+  return cudaGetLastError();
+}
+
+cudaError_t mcx_launch_kmer_tuples(const McxBuildParams &p, const McxTupleBins &b, cudaStream_t st)
+{
+  if(p.r_end <= p.r_begin) return cudaSuccess;
+  unsigned grid = grid_for_chunks(p, 4);
+  if(p.k <= 31) mcx_kmer_tuples_kernel<1><<<grid, MCX_THREADS, 0, st>>>(p, b);
+  else mcx_kmer_tuples_kernel<2><<<grid, MCX_THREADS, 0, st>>>(p, b);
+  return cudaGetLastError();
+}
+
+cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint8_t *masks, uint64_t n, uint32_t k, const McxTable &t,
+                                     uint32_t colour, int may_saturate, unsigned long long *counters, cudaStream_t st)
+{
+  if(n == 0) return cudaSuccess;
+  uint64_t want = (n + MCX_THREADS - 1) / MCX_THREADS, cap = (uint64_t)num_sms() * 8;
+  unsigned grid = (unsigned)(want < cap ? want : cap);
+  if(k <= 31) mcx_insert_tuples_kernel<1><<<grid, MCX_THREADS, 0, st>>>(keys, masks, n, t, colour, may_saturate, counters);
+  else mcx_insert_tuples_kernel<2><<<grid, MCX_THREADS, 0, st>>>(keys, masks, n, t, colour, may_saturate, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uint64_t nreads, uint8_t *dst, cudaStream_t st)
+{
+  if(nreads == 0) return cudaSuccess;
+  uint64_t want = (nreads * 32 + MCX_THREADS - 1) / MCX_THREADS, cap = (uint64_t)num_sms() * 16;
+  unsigned grid = (unsigned)(want < cap ? want : cap);
+  mcx_repack_lines_kernel<<<grid, MCX_THREADS, 0, st>>>(src, off, nreads, dst);
+  return cudaGetLastError();
+}

@@ -1,0 +1,51 @@
+// mcx_build.h -- internal interface between the kernels (mcx_build.cu, mcx_export.cu)
+// and the C-ABI layer (mcx_abi.cu).  Not part of the public ABI (include/mcx_gpu.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mcx_table.cuh"
+
+enum {
+  MCX_CNT_KMERS = 0,   // k-mer occurrences loaded            (SeqLoadingStats.num_kmers_loaded)
+  MCX_CNT_NOVEL,       // slots claimed                        (num_kmers_novel / ht.num_kmers)
+  MCX_CNT_CONTIGS,     // contigs                              (contigs_parsed)
+  MCX_CNT_READS,       // read terminators seen                (num_se_reads)
+  MCX_CNT_FULL,        // non-zero: table (or tuple bin) overflowed
+  MCX_CNT_INSERTED,    // tuples inserted by kernel C
+  MCX_NCOUNTERS = 8
+};
+
+struct McxBuildParams {
+  const uint8_t *seq;   // LINES layout, 16-byte aligned, readable up to nbytes rounded up to 16
+  uint64_t nbytes;      // bytes of data in seq
+  uint64_t r_begin;     // positions [r_begin, r_end) are owned by this launch (window starts and terminators)
+  uint64_t r_end;
+  uint32_t k;
+  uint32_t hp_cutoff;
+  uint32_t colour;
+  int may_saturate;
+  unsigned long long *counters; // MCX_NCOUNTERS u64, device
+};
+
+struct McxTupleBins {
+  uint64_t *keys;                // nparts * cap * W
+  uint8_t *masks;                // nparts * cap
+  unsigned long long *cursor;    // nparts
+  uint64_t cap;                  // tuples per destination
+  uint32_t nparts;
+};
+
+cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
+cudaError_t mcx_launch_kmer_tuples(const McxBuildParams &p, const McxTupleBins &b, cudaStream_t st);
+cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint8_t *masks, uint64_t n, uint32_t k, const McxTable &t,
+                                     uint32_t colour, int may_saturate, unsigned long long *counters, cudaStream_t st);
+cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uint64_t nreads, uint8_t *dst, cudaStream_t st);
+
+// export (mcx_export.cu)
+struct McxExport {
+  uint8_t *records;   // nrec * rec_bytes, .ctx record layout, ascending key order if sorted
+  uint64_t nrec;
+  uint32_t rec_bytes;
+};
+cudaError_t mcx_export_build(const McxTable &t, uint32_t kmer_size, bool sorted, McxExport *out, cudaStream_t st);
+void mcx_export_free(McxExport *e);

@@ -1,0 +1,172 @@
+// mcx_export.cu -- dump the device table as .ctx v6 records in ascending key order.
+//
+// Replaces (reference, relative to /root/reference):
+//   HASH_ITERATE_SORTED / hash_table_sorted   src/graph/hash_table.h:115-120, hash_table.c:362-374
+//   graph_write_kmer                          src/graph/graph_writer.c:116-127
+// The reference qsorts an array of pointers with an indirect compare and fwrites three
+// fields per k-mer.  Here: compact occupied slots -> LSD radix sort of (key word, slot
+// index) pairs (cub::DeviceRadixSort, the one library call on this path; it only touches
+// 2k key bits) -> one kernel that gathers key/covg/edges of each slot and writes the
+// packed 8W+5C byte records through shared memory so global stores stay coalesced.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <stdint.h>
+#include "mcx_build.h"
+
+#define CK(x) do { cudaError_t e_ = (x); if(e_ != cudaSuccess) { err = e_; goto fail; } } while(0)
+
+// occupied slots -> (low key word, slot index) pairs
+template <int W>
+__global__ void mcx_compact_kernel(McxTable t, uint64_t *__restrict__ keys, uint64_t *__restrict__ slots,
+                                   unsigned long long *cursor)
+{
+  const uint32_t lane = threadIdx.x & 31u;
+  uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t rounds = (t.nslots + nthreads - 1) / nthreads;
+  for(uint64_t r = 0; r < rounds; r++) {
+    uint64_t i = r * nthreads + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    uint64_t k0 = 0;
+    if(i < t.nslots) k0 = *reinterpret_cast<const uint64_t *>(t.slots + i * (uint64_t)t.stride);
+    bool occ = k0 != 0;
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, occ);
+    if(!m) continue;
+    unsigned long long base = 0;
+    if(lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if(occ) {
+      uint64_t at = base + __popc(m & ((1u << lane) - 1u));
+      // sort key of the first pass = least significant key word
+      keys[at] = (W == 1) ? (k0 & ~MCX_KEY_FLAG)
+                          : *reinterpret_cast<const uint64_t *>(t.slots + i * (uint64_t)t.stride + 2);
+      slots[at] = i;
+    }
+  }
+}
+
+// second pass key for W == 2: the most significant word of each (already b[1]-sorted) slot
+__global__ void mcx_gather_hi_kernel(McxTable t, const uint64_t *__restrict__ slots, uint64_t n, uint64_t *__restrict__ keys)
+{
+  for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    keys[i] = *reinterpret_cast<const uint64_t *>(t.slots + slots[i] * (uint64_t)t.stride) & ~MCX_KEY_FLAG;
+}
+
+// record i <- slot order[i] : W x u64 key (flag cleared), C x u32 covg, C x u8 edges
+#define MCX_EXP_RPB 128
+__global__ void __launch_bounds__(MCX_EXP_RPB) mcx_format_kernel(McxTable t, uint32_t W, const uint64_t *__restrict__ order,
+                                                                 uint64_t n, uint32_t rec_bytes, uint8_t *__restrict__ out)
+{
+  extern __shared__ __align__(16) uint8_t tile[];
+  for(uint64_t blk = blockIdx.x; blk * MCX_EXP_RPB < n; blk += gridDim.x) {
+    uint64_t first = blk * MCX_EXP_RPB;
+    uint32_t cnt = (uint32_t)((n - first < MCX_EXP_RPB) ? (n - first) : MCX_EXP_RPB);
+    if(threadIdx.x < cnt) {
+      const uint32_t *s = t.slots + order[first + threadIdx.x] * (uint64_t)t.stride;
+      uint8_t *d = tile + threadIdx.x * rec_bytes;
+      uint32_t C = t.ncols;
+      for(uint32_t w = 0; w < 2u * W + C; w++) {
+        uint32_t v = s[w];
+        if(w == 1u) v &= 0x7FFFFFFFu; // MCX_KEY_FLAG lives in the top bit of key word b[0]
+        d[4 * w + 0] = (uint8_t)v; d[4 * w + 1] = (uint8_t)(v >> 8);
+        d[4 * w + 2] = (uint8_t)(v >> 16); d[4 * w + 3] = (uint8_t)(v >> 24);
+      }
+      for(uint32_t c = 0; c < C; c++) d[8u * W + 4u * C + c] = (uint8_t)(s[2u * W + C + (c >> 2)] >> (8u * (c & 3u)));
+    }
+    __syncthreads();
+    uint64_t obase = first * rec_bytes; // multiple of 128*rec_bytes => 16-byte aligned
+    uint32_t nbytes = cnt * rec_bytes;
+    if((nbytes & 3u) == 0) {
+      uint32_t *o32 = reinterpret_cast<uint32_t *>(out + obase);
+      const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tile);
+      for(uint32_t i = threadIdx.x; i < nbytes / 4u; i += blockDim.x) o32[i] = t32[i];
+    } else {
+      for(uint32_t i = threadIdx.x; i < nbytes; i += blockDim.x) out[obase + i] = tile[i];
+    }
+    __syncthreads();
+  }
+}
+
+static cudaError_t radix_pass(uint64_t **keys, uint64_t **vals, uint64_t **keys_alt, uint64_t **vals_alt, uint64_t n,
+                              int end_bit, void **tmp, size_t *tmp_bytes, cudaStream_t st)
+{
+  cub::DoubleBuffer<uint64_t> dk(*keys, *keys_alt), dv(*vals, *vals_alt);
+  size_t need = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, end_bit, st);
+  if(e != cudaSuccess) return e;
+  if(need > *tmp_bytes) {
+    if(*tmp) cudaFree(*tmp);
+    *tmp = nullptr; *tmp_bytes = 0;
+    e = cudaMalloc(tmp, need);
+    if(e != cudaSuccess) return e;
+    *tmp_bytes = need;
+  }
+  e = cub::DeviceRadixSort::SortPairs(*tmp, need, dk, dv, n, 0, end_bit, st);
+  if(e != cudaSuccess) return e;
+  // leave the sorted data in (*keys,*vals)
+  if(dk.Current() != *keys) { uint64_t *x = *keys; *keys = *keys_alt; *keys_alt = x; }
+  if(dv.Current() != *vals) { uint64_t *x = *vals; *vals = *vals_alt; *vals_alt = x; }
+  return cudaSuccess;
+}
+
+cudaError_t mcx_export_build(const McxTable &t, uint32_t k, bool sorted, McxExport *out, cudaStream_t st)
+{
+  cudaError_t err = cudaSuccess;
+  const uint32_t W = (k + 31u) / 32u;
+  unsigned long long *cursor = nullptr;
+  uint64_t *keys = nullptr, *vals = nullptr, *keys_alt = nullptr, *vals_alt = nullptr;
+  void *tmp = nullptr; size_t tmp_bytes = 0;
+  unsigned long long n = 0;
+  int sms = 148, dev = 0;
+  out->records = nullptr; out->nrec = 0; out->rec_bytes = 8u * W + 5u * t.ncols;
+
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+  CK(cudaMalloc(&cursor, sizeof(*cursor)));
+  CK(cudaMemsetAsync(cursor, 0, sizeof(*cursor), st));
+  // compaction buffers are sized by capacity (occupancy is not trusted from the caller)
+  CK(cudaMalloc(&keys, t.nslots * sizeof(uint64_t)));
+  CK(cudaMalloc(&vals, t.nslots * sizeof(uint64_t)));
+  if(W == 1) mcx_compact_kernel<1><<<sms * 8, 256, 0, st>>>(t, keys, vals, cursor);
+  else mcx_compact_kernel<2><<<sms * 8, 256, 0, st>>>(t, keys, vals, cursor);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&n, cursor, sizeof(n), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+
+  if(n && sorted) {
+    CK(cudaMalloc(&keys_alt, n * sizeof(uint64_t)));
+    CK(cudaMalloc(&vals_alt, n * sizeof(uint64_t)));
+    if(W == 1) {
+      CK(radix_pass(&keys, &vals, &keys_alt, &vals_alt, n, (int)(2u * k), &tmp, &tmp_bytes, st));
+    } else {
+      CK(radix_pass(&keys, &vals, &keys_alt, &vals_alt, n, 64, &tmp, &tmp_bytes, st));
+      mcx_gather_hi_kernel<<<sms * 8, 256, 0, st>>>(t, vals, n, keys);
+      CK(cudaGetLastError());
+      CK(radix_pass(&keys, &vals, &keys_alt, &vals_alt, n, (int)(2u * (k - 32u)), &tmp, &tmp_bytes, st));
+    }
+  }
+  if(n) {
+    CK(cudaMalloc(&out->records, n * (uint64_t)out->rec_bytes + 16));
+    uint64_t nblk = (n + MCX_EXP_RPB - 1) / MCX_EXP_RPB, cap = (uint64_t)sms * 16;
+    size_t smem = (size_t)MCX_EXP_RPB * out->rec_bytes;
+    if(smem > 48 * 1024) CK(cudaFuncSetAttribute(mcx_format_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mcx_format_kernel<<<(unsigned)(nblk < cap ? nblk : cap), MCX_EXP_RPB, smem, st>>>(t, W, vals, n, out->rec_bytes, out->records);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+  }
+  out->nrec = n;
+fail:
+  if(cursor) cudaFree(cursor);
+  if(keys) cudaFree(keys);
+  if(vals) cudaFree(vals);
+  if(keys_alt) cudaFree(keys_alt);
+  if(vals_alt) cudaFree(vals_alt);
+  if(tmp) cudaFree(tmp);
+  if(err != cudaSuccess && out->records) { cudaFree(out->records); out->records = nullptr; }
+  return err;
+}
+
+void mcx_export_free(McxExport *e)
+{
+  if(e && e->records) { cudaFree(e->records); e->records = nullptr; }
+  if(e) e->nrec = 0;
+}

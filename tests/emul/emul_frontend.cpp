@@ -1,0 +1,106 @@
+// tests/emul/emul_frontend.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// Executes the host/device (MCX_HD) math of mccortex_b200/csrc/mcx_device.cuh and
+// mcx_chunk.cuh on the CPU, walking chunks exactly like mcx_front_end() in
+// mcx_build.cu (phase 1 / 2a / 2b over the same staged arrays), and writes the sorted
+// .ctx records + counters so tests can compare them with the oracle WITHOUT a GPU.
+// It exists because the build container has no GPU; it is never linked into
+// libmcxgpu.so and the product never calls it.
+//
+// usage: emul_frontend <lines-file> <k> <hp_cutoff> <r_piece>   -> stdout: records
+//        r_piece: positions per simulated launch (0 = one launch), to exercise the
+//        host-staging cut logic of mcx_abi.cu (look-back 16 / look-ahead 80).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+#include <array>
+#include "../../mccortex_b200/csrc/mcx_chunk.cuh"
+
+struct Rec { uint32_t covg; uint8_t edges; };
+typedef std::map<std::array<uint64_t, 2>, Rec> Table;
+
+struct Counters { uint64_t kmers = 0, novel = 0, contigs = 0, reads = 0; };
+
+template <int W>
+static void run_launch(const uint8_t *seq, uint64_t nbytes, uint64_t r_begin, uint64_t r_end, uint32_t k, uint32_t hp,
+                       Table &tab, Counters &cnt)
+{
+  std::vector<uint8_t> raw(MCX_RAW);
+  std::vector<uint32_t> pk(MCX_PKW), bad(MCX_MSW), eq(MCX_MSW), vmask(MCX_VW);
+  uint64_t c_first = r_begin / MCX_T, c_last = (r_end + MCX_T - 1) / MCX_T;
+  for(uint64_t chunk = c_first; chunk < c_last; chunk++) {
+    uint64_t cs = chunk * (uint64_t)MCX_T;
+    // staging (issue_chunk_load): bytes outside the copied range hold garbage
+    memset(raw.data(), 0x5A, MCX_RAW);
+    uint64_t src_off = cs ? cs - MCX_LB : 0; uint32_t dst_off = cs ? 0 : MCX_LB;
+    uint64_t avail = (nbytes - src_off + 15ull) & ~15ull; uint32_t want = MCX_RAW - dst_off;
+    uint32_t bytes = avail < want ? (uint32_t)avail : want;
+    for(uint32_t i = 0; i < bytes; i++) raw[dst_off + i] = (src_off + i < nbytes) ? seq[src_off + i] : 0xEE;
+    for(uint32_t t = 0; t < 4; t++) { pk[MCX_RAW / 16u + t] = 0; bad[MCX_RAW / 32u + t] = 0xFFFFFFFFu; eq[MCX_RAW / 32u + t] = 0; }
+    // phase 1
+    for(uint32_t tid = 0; tid < MCX_RAW / 16u; tid++) {
+      uint32_t w[4]; memcpy(w, &raw[tid * 16u], 16);
+      uint32_t prev = tid ? raw[tid * 16u - 1u] : 0u;
+      uint64_t gpos = cs - MCX_LB + tid * 16ull;
+      uint32_t p, b16, e16, n16;
+      mcx_convert16(w, prev, gpos, nbytes, &p, &b16, &e16, &n16);
+      pk[tid] = p;
+      ((uint16_t *)bad.data())[tid] = (uint16_t)b16;
+      ((uint16_t *)eq.data())[tid] = (uint16_t)e16;
+      if(n16 && tid >= MCX_LB / 16u && tid < (MCX_LB + MCX_T) / 16u)
+        for(uint32_t i = 0; i < 16u; i++)
+          if(((n16 >> i) & 1u) && gpos + i >= r_begin && gpos + i < r_end) cnt.reads++;
+    }
+    // phase 2a
+    for(uint32_t i = 0; i < MCX_VW * 32u; i++) {
+      bool ok = (i < MCX_T + 2u) && mcx_chunk_window_ok(bad.data(), eq.data(), i, k, hp);
+      if((i & 31u) == 0) vmask[i >> 5] = 0;
+      if(ok) vmask[i >> 5] |= 1u << (i & 31u);
+    }
+    // phase 2b
+    for(uint32_t i = 1; i <= MCX_T; i++) {
+      uint64_t g = cs + (i - 1u);
+      if(mcx_get_bit(vmask.data(), i) && g >= r_begin && g < r_end) {
+        McxOcc<W> o = mcx_chunk_occurrence<W>(pk.data(), vmask.data(), i, k);
+        cnt.kmers++;
+        cnt.contigs += !mcx_get_bit(vmask.data(), i - 1u);
+        std::array<uint64_t, 2> key = {o.key.b[0], W == 2 ? o.key.b[W - 1] : 0};
+        auto it = tab.find(key);
+        if(it == tab.end()) { tab[key] = Rec{1, (uint8_t)o.emask}; cnt.novel++; }
+        else { if(it->second.covg != 0xFFFFFFFFu) it->second.covg++; it->second.edges |= (uint8_t)o.emask; }
+      }
+    }
+  }
+}
+
+int main(int argc, char **argv)
+{
+  if(argc < 5) { fprintf(stderr, "usage: %s <lines-file> <k> <hp> <r_piece>\n", argv[0]); return 2; }
+  FILE *f = fopen(argv[1], "rb"); if(!f) { perror(argv[1]); return 2; }
+  std::vector<uint8_t> data; uint8_t buf[1 << 16]; size_t n;
+  while((n = fread(buf, 1, sizeof(buf), f)) > 0) data.insert(data.end(), buf, buf + n);
+  fclose(f);
+  uint32_t k = (uint32_t)atoi(argv[2]), hp = (uint32_t)atoi(argv[3]);
+  uint64_t piece = strtoull(argv[4], NULL, 10), nbytes = data.size();
+  if(piece == 0) piece = nbytes ? nbytes : 1;
+  Table tab; Counters cnt;
+  for(uint64_t pos = 0; pos < nbytes; pos += piece) {
+    uint64_t pend = pos + piece < nbytes ? pos + piece : nbytes;
+    uint64_t b0 = pos ? pos - MCX_LB : 0, b1 = pend + MCX_TAIL < nbytes ? pend + MCX_TAIL : nbytes;
+    if(b0 % 16) { fprintf(stderr, "piece must be a multiple of 16\n"); return 2; }
+    if(k <= 31) run_launch<1>(data.data() + b0, b1 - b0, pos - b0, pend - b0, k, hp, tab, cnt);
+    else run_launch<2>(data.data() + b0, b1 - b0, pos - b0, pend - b0, k, hp, tab, cnt);
+  }
+  int W = k <= 31 ? 1 : 2;
+  for(auto &kv : tab) {
+    fwrite(&kv.first[0], 8, 1, stdout);
+    if(W == 2) fwrite(&kv.first[1], 8, 1, stdout);
+    fwrite(&kv.second.covg, 4, 1, stdout);
+    fwrite(&kv.second.edges, 1, 1, stdout);
+  }
+  fprintf(stderr, "kmers=%llu novel=%llu contigs=%llu reads=%llu\n", (unsigned long long)cnt.kmers,
+          (unsigned long long)cnt.novel, (unsigned long long)cnt.contigs, (unsigned long long)cnt.reads);
+  return 0;
+}

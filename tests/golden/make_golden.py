@@ -1,0 +1,90 @@
+"""Writes tests/golden/: small inputs + the .ctx the COMPILED REFERENCE produces for them.
+
+Run in the build container (needs oracle/_ref, i.e. /root/reference):
+    python tests/golden/make_golden.py
+The inputs are seeded; the .ctx files and cases.json are committed so the GPU box
+(which has no /root/reference) checks against the reference's own bytes.
+"""
+import hashlib
+import json
+import os
+import random
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import oracle as O  # noqa: E402
+from conftest import rand_reads, EDGE_READS  # noqa: E402
+
+
+def write_fa(path, reads, wrap=None):
+    with open(path, "w") as f:
+        for i, r in enumerate(reads):
+            f.write(">r%d\n" % i)
+            if wrap:
+                for j in range(0, len(r), wrap):
+                    f.write(r[j:j + wrap] + "\n")
+            else:
+                f.write(r + "\n")
+
+
+def write_fq(path, reads, rng, qoff=33, qlo=2, qhi=40):
+    with open(path, "w") as f:
+        for i, r in enumerate(reads):
+            q = "".join(chr(qoff + (rng.randint(qlo, qhi) if rng.random() < 0.15 else rng.randint(25, qhi))) for _ in r)
+            f.write("@r%d\n%s\n+\n%s\n" % (i, r, q))
+
+
+def main():
+    rng = random.Random(424242)
+    cases = []
+
+    def add(name, k, samples):
+        args = []
+        for s in samples:
+            args += ["-s", s["name"]]
+            for t in s["tasks"]:
+                if t.get("fq_cutoff"):
+                    args += ["-Q", str(t["fq_cutoff"])]
+                if t.get("fq_offset"):
+                    args += ["-O", str(t["fq_offset"])]
+                if t.get("hp_cutoff"):
+                    args += ["-H", str(t["hp_cutoff"])]
+                args += ["-1", os.path.join(HERE, t["file"])]
+                # -Q/-O/-H persist for following inputs in the reference: reset explicitly
+                if t.get("fq_cutoff") or t.get("hp_cutoff") or t.get("fq_offset"):
+                    pass
+        ctx = name + ".ctx"
+        data = O.ref_build(k, args, os.path.join(HERE, ctx), threads=3)
+        cases.append(dict(name=name, k=k, samples=samples, ctx=ctx, md5=hashlib.md5(data).hexdigest(),
+                          ref_args=[a.replace(HERE + "/", "") for a in args]))
+        print(name, len(data), cases[-1]["md5"])
+
+    # tiny 2-colour graph from SURVEY 8c
+    open(os.path.join(HERE, "g1.fa"), "w").write(
+        ">r1\nACGTACGTTAGCNNACGTTAGCATCGATCGGATCGAT\n>r2\nacgtacgttagc\n>r3\nAC\n>r4\nTTTTTTTTTTTTTTT\nGGGGGGGGGCA\n")
+    open(os.path.join(HERE, "g2.fa"), "w").write(">s1\nATCGATCCGATCGATGCTAACGT\n")
+    add("tiny_k11_c2", 11, [dict(name="one", tasks=[dict(file="g1.fa")]), dict(name="two", tasks=[dict(file="g2.fa")])])
+
+    write_fa(os.path.join(HERE, "a.fa"), rand_reads(rng, 150, 150, 4000) + EDGE_READS)
+    add("reads_k31", 31, [dict(name="s", tasks=[dict(file="a.fa")])])
+    add("reads_k63", 63, [dict(name="s", tasks=[dict(file="a.fa")])])
+    add("reads_k33", 33, [dict(name="s", tasks=[dict(file="a.fa")])])
+    write_fa(os.path.join(HERE, "b.fa"), rand_reads(rng, 60, (20, 300), 4000), wrap=60)
+    add("two_colours_k21", 21, [dict(name="x", tasks=[dict(file="a.fa")]), dict(name="y", tasks=[dict(file="b.fa")])])
+    add("empty_colour_k31", 31, [dict(name="e", tasks=[]), dict(name="l", tasks=[dict(file="b.fa")])])
+    write_fa(os.path.join(HERE, "long.fa"), rand_reads(rng, 1, 20000, 30000, pN=0.0005), wrap=80)
+    add("long_record_k31", 31, [dict(name="chr", tasks=[dict(file="long.fa")])])
+    add("hp4_k21", 21, [dict(name="h", tasks=[dict(file="a.fa", hp_cutoff=4)])])
+    write_fq(os.path.join(HERE, "q.fq"), rand_reads(rng, 150, (30, 200), 4000, perr=0.02), rng)
+    add("fq10_k21", 21, [dict(name="q", tasks=[dict(file="q.fq", fq_cutoff=10)])])
+    add("fq20_hp5_k15", 15, [dict(name="q", tasks=[dict(file="q.fq", fq_cutoff=20, hp_cutoff=5)])])
+
+    with open(os.path.join(HERE, "cases.json"), "w") as f:
+        json.dump(cases, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

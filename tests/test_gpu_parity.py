@@ -1,0 +1,197 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libmcxgpu.so), against the
+oracle on the same seeded inputs -- bit-exact records and counters."""
+import random
+
+import pytest
+
+from conftest import rand_reads, oracle_records, EDGE_READS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mccortex_b200 as M
+    assert M.device_count() > 0, "GPU tests need a CUDA device"
+    return M
+
+
+def _check_stats(st, ost, nreads):
+    assert st.num_kmers_loaded == ost.num_kmers_loaded
+    assert st.num_kmers_novel == ost.num_kmers_novel
+    assert st.contigs_parsed == ost.contigs_parsed
+    assert st.total_bases_loaded == ost.total_bases_loaded
+    assert st.total_bases_read == ost.total_bases_read
+    assert st.num_se_reads == nreads
+
+
+@pytest.mark.parametrize("k", [3, 11, 21, 31, 33, 47, 63])
+def test_lines_batch_matches_oracle(M, oracle, reads_small, k):
+    recs, ost = oracle_records(oracle, reads_small, k)
+    g = M.Graph(k, 1, 1 << 20)
+    g.add_lines("".join(r + "\n" for r in reads_small).encode())
+    st = g.sync()
+    got, n, rb = g.export_records(sorted=True)
+    assert rb == 8 * g.W + 5
+    assert n == ost.num_kmers_novel
+    assert got == recs
+    _check_stats(st, ost, len(reads_small))
+    assert g.stats()[0] == n
+    g.close()
+
+
+@pytest.mark.parametrize("k", [31, 63])
+def test_offsets_batch_matches_oracle(M, oracle, reads_small, k):
+    recs, ost = oracle_records(oracle, reads_small, k)
+    g = M.Graph(k, 1, 1 << 20)
+    g.add_reads(reads_small)
+    st = g.sync()
+    got, n, _ = g.export_records()
+    assert got == recs
+    _check_stats(st, ost, len(reads_small))
+    g.close()
+
+
+@pytest.mark.parametrize("k,hp", [(11, 2), (21, 5), (31, 4), (31, 31), (63, 6)])
+def test_homopolymer_cutoff(M, oracle, reads_small, k, hp):
+    recs, ost = oracle_records(oracle, reads_small, k, hp_cutoff=hp)
+    g = M.Graph(k, 1, 1 << 20)
+    g.add_lines("".join(r + "\n" for r in reads_small).encode(), hp_cutoff=hp)
+    st = g.sync()
+    got, _, _ = g.export_records()
+    assert got == recs
+    _check_stats(st, ost, len(reads_small))
+    g.close()
+
+
+@pytest.mark.parametrize("k,ncols", [(31, 2), (31, 4), (63, 3), (21, 7)])
+def test_colours(M, oracle, k, ncols):
+    """per-colour covg/edges arrays (reference: col_covgs / col_edges, db_graph.h:39-40)"""
+    rng = random.Random(100 + ncols)
+    og = oracle.Graph(k, ncols, 1 << 20)
+    g = M.Graph(k, ncols, 1 << 20)
+    for c in range(ncols):
+        reads = rand_reads(rng, 120, (40, 200), 3000)  # same genome size, different genomes: some shared k-mers unlikely
+        if c:
+            reads += first[:40]  # make colours share k-mers
+        else:
+            first = reads
+        for r in reads:
+            og.add_read(r, colour=c)
+        g.add_lines("".join(r + "\n" for r in reads).encode(), colour=c)
+    g.sync()
+    full = og.dump_sorted()
+    recs = full[len(og.header()):]
+    got, n, rb = g.export_records()
+    assert rb == 8 * g.W + 5 * ncols
+    assert got == recs
+    g.close()
+
+
+def test_batches_accumulate_and_unsorted_export(M, oracle, reads_small):
+    """several add_reads calls == one; unsorted export is a permutation of the sorted one"""
+    k = 31
+    recs, ost = oracle_records(oracle, reads_small + reads_small[:100], k)
+    g = M.Graph(k, 1, 1 << 20)
+    g.add_lines("".join(r + "\n" for r in reads_small[:150]).encode())
+    g.add_reads(reads_small[150:])
+    for r in reads_small[:100]:
+        if len(r) >= k and all(c in "ACGTacgt" for c in r):
+            g.add_str(r)  # build_graph_from_str_mt
+        else:
+            g.add_reads([r])
+    g.sync()
+    got, n, rb = g.export_records(sorted=True)
+    assert got == recs
+    uns, n2, _ = g.export_records(sorted=False)
+    assert n2 == n
+    assert sorted(uns[i:i + rb] for i in range(0, len(uns), rb)) == sorted(got[i:i + rb] for i in range(0, len(got), rb))
+    g.close()
+
+
+def test_exactly_once_novelty_under_concurrency(M, oracle):
+    """reference hash_table_tests.c:97-129: the same keys inserted from many threads must be
+    novel exactly once.  Here: the same 200k-window batch submitted 6 times on concurrent streams."""
+    rng = random.Random(5)
+    reads = rand_reads(rng, 1500, 150, 50000, perr=0.0, pN=0.0, lower=0.0)
+    blob = "".join(r + "\n" for r in reads).encode()
+    recs, ost = oracle_records(oracle, reads, 31)
+    g = M.Graph(31, 1, 1 << 19)
+    for _ in range(6):
+        g.add_lines(blob)
+    st = g.sync()
+    assert st.num_kmers_novel == ost.num_kmers_novel
+    assert st.num_kmers_loaded == 6 * ost.num_kmers_loaded
+    got, n, rb = g.export_records()
+    # same keys and edges, 6x the coverage
+    assert n == ost.num_kmers_novel
+    for i in range(0, len(recs), rb * 997):
+        assert got[i:i + 8] == recs[i:i + 8]
+        assert int.from_bytes(got[i + 8:i + 12], "little") == 6 * int.from_bytes(recs[i + 8:i + 12], "little")
+        assert got[i + 12] == recs[i + 12]
+    g.close()
+
+
+def test_table_full_is_reported(M):
+    rng = random.Random(9)
+    reads = rand_reads(rng, 200, 150, 20000, perr=0.0, pN=0.0, lower=0.0)
+    g = M.Graph(31, 1, 1024)
+    g.add_lines("".join(r + "\n" for r in reads).encode())
+    with pytest.raises(M.McxError) as e:
+        g.sync()
+    assert e.value.status == "MCX_ERR_TABLE_FULL"
+    g.close()
+
+
+def test_large_host_batch_crosses_staging_pieces(M, oracle):
+    """> 32 Mi positions so the host path cuts the batch (look-back/look-ahead logic on real HW)"""
+    rng = random.Random(77)
+    base = rand_reads(rng, 3000, 150, 200000, perr=0.002, pN=0.001, lower=0.05)
+    blob = "".join(r + "\n" for r in base).encode()
+    reps = (40 << 20) // len(blob) + 1
+    big = blob * reps
+    recs, ost = oracle_records(oracle, base, 31)
+    g = M.Graph(31, 1, 1 << 20)
+    g.add_lines(big)
+    st = g.sync()
+    assert st.num_kmers_loaded == reps * ost.num_kmers_loaded
+    assert st.num_kmers_novel == ost.num_kmers_novel
+    assert st.num_se_reads == reps * len(base)
+    got, n, rb = g.export_records()
+    assert n == ost.num_kmers_novel
+    assert got[:8] == recs[:8] and got[-rb:-rb + 8] == recs[-rb:-rb + 8]
+    for i in range(0, len(recs), rb * 1009):
+        assert int.from_bytes(got[i + 8:i + 12], "little") == reps * int.from_bytes(recs[i + 8:i + 12], "little")
+        assert got[i + 12] == recs[i + 12]
+    g.close()
+
+
+def test_tuple_path_matches_fused_path(M, oracle, reads_small):
+    """kernel B (reads -> binned tuples) + kernel C (insert) == kernel A, and bins respect ownership"""
+    import torch
+    k, nparts = 31, 4
+    blob = "".join(r + "\n" for r in reads_small).encode()
+    recs, ost = oracle_records(oracle, reads_small, k)
+    dev = torch.device("cuda:0")
+    seq = torch.zeros(len(blob) + 64, dtype=torch.uint8, device=dev)
+    seq[:len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+    cap = ost.num_kmers_loaded + 16
+    keys = torch.zeros(nparts * cap, dtype=torch.int64, device=dev)
+    masks = torch.zeros(nparts * cap, dtype=torch.uint8, device=dev)
+    counts = torch.zeros(nparts, dtype=torch.int64, device=dev)
+    g = M.Graph(k, 1, 1 << 20)
+    g.kmer_tuples(seq.data_ptr(), len(blob), nparts, cap, keys.data_ptr(), masks.data_ptr(), counts.data_ptr())
+    st = g.sync()
+    assert st.num_kmers_loaded == ost.num_kmers_loaded and st.contigs_parsed == ost.contigs_parsed
+    cnt = counts.cpu().tolist()
+    assert sum(cnt) == ost.num_kmers_loaded
+    for d in range(nparts):
+        kd = keys[d * cap: d * cap + cnt[d]].cpu().tolist()
+        for x in kd[:50]:
+            assert M.key_owner([x & 0xFFFFFFFFFFFFFFFF], k, nparts) == d
+        g.insert_tuples(keys[d * cap:].data_ptr(), masks[d * cap:].data_ptr(), cnt[d])
+    st2 = g.sync()
+    assert st2.num_kmers_novel == ost.num_kmers_novel
+    got, _, _ = g.export_records()
+    assert got == recs
+    g.close()

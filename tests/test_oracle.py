@@ -1,0 +1,124 @@
+"""CPU tests: the oracle against golden vectors / the compiled reference, and the
+device math (run on the CPU through tests/emul) against the oracle."""
+import hashlib
+import os
+import random
+import subprocess
+
+import pytest
+
+from conftest import ROOT, rand_reads, oracle_records, EDGE_READS
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+# ---- known-answer vectors taken from the compiled reference -------------
+def test_lookup3_known_answers(oracle):
+    # `mccortex31 hashtest -t 1 -k 31 -F N` prints the XOR of bklk3_hashlittle({i}, 0), i < N
+    L = oracle.lib()
+    assert L.orc_hashtest_xor(1) == 1489077439
+    assert L.orc_hashtest_xor(1000) == 2609835747
+    assert L.orc_hashtest_xor(1000000) == 2564219928
+
+
+def test_tiny_two_colour_graph_md5(oracle, tmp_path):
+    g1 = tmp_path / "g1.fa"
+    g2 = tmp_path / "g2.fa"
+    g1.write_text(">r1\nACGTACGTTAGCNNACGTTAGCATCGATCGGATCGAT\n>r2\nacgtacgttagc\n>r3\nAC\n"
+                  ">r4\nTTTTTTTTTTTTTTT\nGGGGGGGGGCA\n")
+    g2.write_text(">s1\nATCGATCCGATCGATGCTAACGT\n")
+    out, _ = oracle.build_ctx(11, [("one", [str(g1)]), ("two", [str(g2)])])
+    assert len(out) == 634
+    assert hashlib.md5(out).hexdigest() == "3e484f5ef0bdd644ffd233cde667c426"
+
+
+def test_seq_err_bytes(oracle):
+    # [probed] header seq_err bytes for a colour with sequence
+    g = oracle.Graph(31, 1, 1024)
+    g.set_name(0, "samp")
+    st = g.add_read("ACGT" * 20)
+    g.update_ginfo(0, st)
+    h = g.header()
+    assert len(h) == 89
+    assert bytes.fromhex("00d8a3703d0ad7a3f83f000000000000") in h
+
+
+def _golden_cases():
+    import json
+    with open(os.path.join(GOLD, "cases.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("case", [c["name"] for c in __import__("json").load(open(os.path.join(GOLD, "cases.json")))])
+def test_oracle_vs_golden_ctx(oracle, case):
+    """tests/golden/*.ctx were written by the compiled reference (make_golden.py)."""
+    c = next(x for x in _golden_cases() if x["name"] == case)
+    samples = [(s["name"], [dict(path=os.path.join(GOLD, t["file"]), fq_cutoff=t.get("fq_cutoff", 0),
+                                 fq_offset=t.get("fq_offset", 0), hp_cutoff=t.get("hp_cutoff", 0))
+                            for t in s["tasks"]]) for s in c["samples"]]
+    out, _ = oracle.build_ctx(c["k"], samples)
+    with open(os.path.join(GOLD, c["ctx"]), "rb") as f:
+        ref = f.read()
+    assert hashlib.md5(ref).hexdigest() == c["md5"]
+    assert out == ref
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "mccortex31")),
+                    reason="oracle/_ref not built")
+@pytest.mark.parametrize("k,seed", [(31, 1), (63, 2), (33, 3), (21, 4), (5, 5)])
+def test_oracle_vs_reference_binary(oracle, tmp_path, k, seed):
+    rng = random.Random(seed)
+    reads = rand_reads(rng, 300, (10, 260), 8000)
+    fa = tmp_path / "r.fa"
+    fa.write_text("".join(">r%d\n%s\n" % (i, r) for i, r in enumerate(reads)))
+    mine, _ = oracle.build_ctx(k, [("s", [str(fa)])])
+    ref = oracle.ref_build(k, ["-s", "s", "-1", str(fa)], str(tmp_path / "ref.ctx"), threads=3)
+    assert mine == ref
+
+
+# ---- table sizing (row I) ----------------------------------------------------------------
+def test_hash_table_cap(oracle):
+    import ctypes as C
+    nb, bs = C.c_uint64(), C.c_uint8()
+    # [probed] `-n 64M` -> 2^21 buckets x 32
+    cap = oracle.lib().orc_hash_table_cap(64 << 20, C.byref(nb), C.byref(bs))
+    assert (nb.value, bs.value, cap) == (1 << 21, 32, 64 << 20)
+    cap = oracle.lib().orc_hash_table_cap(1, C.byref(nb), C.byref(bs))
+    assert (nb.value, bs.value, cap) == (1024, 1, 1024)
+
+
+# ---- device math on the CPU --------------------------------------------------------------
+def _emul(emul, tmp_path, reads, k, hp=0, piece=0):
+    p = tmp_path / "lines.txt"
+    p.write_text("".join(r + "\n" for r in reads))
+    r = subprocess.run([emul, str(p), str(k), str(hp), str(piece)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       check=True)
+    cnt = dict(x.split("=") for x in r.stderr.decode().split())
+    return r.stdout, {a: int(b) for a, b in cnt.items()}
+
+
+@pytest.mark.parametrize("k", [3, 11, 31, 33, 47, 63])
+def test_device_math_matches_oracle(oracle, emul, tmp_path, reads_small, k):
+    recs, st = oracle_records(oracle, reads_small, k)
+    got, cnt = _emul(emul, tmp_path, reads_small, k)
+    assert got == recs
+    assert cnt == dict(kmers=st.num_kmers_loaded, novel=st.num_kmers_novel, contigs=st.contigs_parsed,
+                       reads=len(reads_small))
+
+
+@pytest.mark.parametrize("k,hp", [(11, 2), (21, 5), (31, 4), (31, 31), (63, 6)])
+def test_device_math_homopolymer_cutoff(oracle, emul, tmp_path, reads_small, k, hp):
+    recs, st = oracle_records(oracle, reads_small, k, hp_cutoff=hp)
+    got, cnt = _emul(emul, tmp_path, reads_small, k, hp=hp)
+    assert got == recs
+    assert cnt["contigs"] == st.contigs_parsed and cnt["kmers"] == st.num_kmers_loaded
+
+
+@pytest.mark.parametrize("piece", [16, 160, 2048, 4112])
+def test_device_math_staging_cuts(oracle, emul, tmp_path, reads_small, piece):
+    """host batches are cut into pieces with 16 B look-back / 80 B look-ahead (mcx_abi.cu)"""
+    for k, hp in ((31, 0), (63, 4)):
+        recs, st = oracle_records(oracle, reads_small, k, hp_cutoff=hp)
+        got, cnt = _emul(emul, tmp_path, reads_small, k, hp=hp, piece=piece)
+        assert got == recs
+        assert cnt["kmers"] == st.num_kmers_loaded and cnt["reads"] == len(reads_small)
