@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- k-mers/s inserted during `build` (k=31) on B200, per BASELINE.json.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--reads R]
+
+Own arm (default): one "step" = one whole `build` load phase of the workload
+(BASELINE.json configs[1]: 50M x 150 bp synthetic reads of a 4.6 Mbp genome, 0.1 %
+substitutions, k=31, 1 colour): zero the table, insert every k-mer occurrence.
+  value : inputs resident in HBM (LINES layout), CUDA events on the launching stream.
+  e2e   : the same step through the C ABI with a pinned HOST buffer: H2D copies inside the
+          timed region, counters read back to the host every step.
+Reference arm (--impl reference): the compiled, unmodified reference (oracle/_ref/mccortex31
+build) on the box's host cores, each step a bounded sample of the same workload.
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 31
+READ_LEN = 150
+GENOME = 4_600_000
+P_ERR = 0.001
+DEFAULT_READS = 50_000_000
+B_ALG = 19.25  # algorithmic bytes per k-mer occurrence, k=31 single GPU (SURVEY 8d / DESIGN.md)
+B_ALG_MULTI = 43.25
+
+
+def synth_lib():
+    p = os.path.join(ROOT, "mccortex_b200", "lib", "libmcxsynth.so")
+    L = C.CDLL(p)
+    L.mcx_synth_genome.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    L.mcx_synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64,
+                                  C.c_double, C.c_int, C.c_uint64]
+    L.mcx_synth_read_bytes.restype = C.c_uint64
+    L.mcx_synth_read_bytes.argtypes = [C.c_uint32, C.c_int]
+    return L
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def write_fasta_sample(path, first, nreads, genome_buf, SL):
+    stride = SL.mcx_synth_read_bytes(READ_LEN, 1)
+    block = 1 << 18
+    buf = C.create_string_buffer(int(block * stride))
+    with open(path, "wb") as f:
+        at = 0
+        while at < nreads:
+            m = min(block, nreads - at)
+            SL.mcx_synth_reads(buf, first + at, m, READ_LEN, genome_buf, GENOME, P_ERR, 1, 0)
+            f.write(buf.raw[:int(m * stride)])
+            at += m
+
+
+def run_reference_build(fasta, nreads, threads, tmpdir):
+    """one `mccortex31 build` of the sample; returns (seconds, k-mer occurrences)"""
+    from oracle import oracle as O
+    exe = O.ref_binary(K)
+    out = os.path.join(tmpdir, "ref.ctx")
+    # capacity as the reference would size it: distinct <= genome + 31 * expected errors, / 0.75
+    est = int((GENOME + nreads * READ_LEN * P_ERR * K * 1.1) / 0.75)
+    args = [exe, "build", "-f", "-t", str(threads), "-m", "60G", "-n", str(est), "-k", str(K),
+            "--sample", "s", "--seq", fasta, out]
+    t0 = time.perf_counter()
+    r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    dt = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError("reference build failed: " + r.stderr[-2000:])
+    nk = nreads * (READ_LEN - K + 1)
+    for line in r.stderr.splitlines():
+        if "num kmers:" in line:
+            nk = int(line.split("num kmers:")[1].split()[0].replace(",", ""))
+    try:
+        os.remove(out)
+    except OSError:
+        pass
+    return dt, nk
+
+
+def sample_reads_for(k_plus_w):
+    return int(max(200_000, min(2_000_000, 8_000_000 // max(1, k_plus_w))))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    if O.ref_binary(K) is None:
+        O.build(ref=True)
+    SL = synth_lib()
+    genome = C.create_string_buffer(GENOME)
+    SL.mcx_synth_genome(genome, GENOME, 0)
+    nreads = sample_reads_for(args.steps + args.warmup)
+    threads = min(os.cpu_count() or 1, 32)
+    tmpdir = tempfile.mkdtemp(prefix="mcxref", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    fasta = os.path.join(tmpdir, "sample.fa")
+    write_fasta_sample(fasta, 0, nreads, genome, SL)
+    for _ in range(args.warmup):
+        run_reference_build(fasta, nreads, threads, tmpdir)
+    tot, nk_tot = 0.0, 0
+    for _ in range(args.steps):
+        dt, nk = run_reference_build(fasta, nreads, threads, tmpdir)
+        tot += dt; nk_tot += nk
+    os.remove(fasta); os.rmdir(tmpdir)
+    val = nk_tot / tot
+    sample = "first %d reads (%d k-mer occurrences/step) of the workload; whole `mccortex31 build` process, unsorted dump to tmpfs" % (
+        nreads, nk_tot // max(1, args.steps))
+    line = {
+        "impl": "reference", "metric": "kmers_per_sec_build_k31", "value": val, "unit": "k-mers/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    return {"workload": "configs[1]: %d x %d bp synthetic reads/GPU, genome %d bp, p_err %g, k=%d, 1 colour" % (
+                args.reads, READ_LEN, GENOME, P_ERR, K),
+            "reads_per_gpu": args.reads, "read_len": READ_LEN, "kmer": K, "colours": 1,
+            "l2": "inputs (%.1f GB reads, table >> 126 MB L2) exceed L2; table re-zeroed every step" % (
+                args.reads * (READ_LEN + 1) / 1e9),
+            "parallelism": "1 GPU fused kernel" if n == 1 else "%d GPUs: hash-partitioned shards, all-to-all of (key,mask) tuples" % n}
+
+
+def own_arm(args):
+    import torch
+    import mccortex_b200 as M
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", local)
+    assert M.device_count() > 0, "bench needs a CUDA device: there is no CPU fallback"
+
+    if world > 1:
+        from mccortex_b200.multi import bench_multi
+        return bench_multi(args, rank, world, local, dist)
+
+    # ---- synthetic workload: generated on the host into PINNED memory (e2e source), copied once to HBM
+    SL = synth_lib()
+    R = args.reads
+    stride = READ_LEN + 1
+    nbytes = R * stride
+    genome = C.create_string_buffer(GENOME)
+    SL.mcx_synth_genome(genome, GENOME, 0)
+    t0 = time.perf_counter()
+    host = M.host_alloc(nbytes + 4096)
+    SL.mcx_synth_reads(host, 0, R, READ_LEN, genome, GENOME, P_ERR, 0, 0)
+    t_gen = time.perf_counter() - t0
+    occ_per_step = R * (READ_LEN - K + 1)
+
+    dseq = torch.empty(nbytes + 4096, dtype=torch.uint8, device=dev)
+    harr = (C.c_uint8 * nbytes).from_address(host)
+    hview = torch.frombuffer(harr, dtype=torch.uint8)
+    dseq[:nbytes].copy_(hview)
+    torch.cuda.synchronize()
+
+    distinct_est = int(GENOME + R * READ_LEN * P_ERR * K * 1.05)
+    capacity = int(distinct_est / 0.75)
+    g = M.Graph(K, 1, capacity, device=local)
+    stream = torch.cuda.Stream(device=dev)  # a real (non-null) stream: the library orders all its work on it
+    torch.cuda.set_stream(stream)
+    g.set_stream(stream.cuda_stream)
+
+    def step_device():
+        g.clear()
+        g.add_reads_raw(dseq.data_ptr(), nbytes, M.MCX_LAYOUT_LINES, M.MCX_MEM_DEVICE)
+
+    def step_host():
+        g.clear()
+        g.add_reads_raw(host, nbytes, M.MCX_LAYOUT_LINES, M.MCX_MEM_HOST)
+        return g.sync()  # counters D2H: the host-visible result of a step
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        step_device()
+    st = g.sync()
+    # (clear() also zeroes the counters, so they hold the last step only)
+    assert args.warmup == 0 or st.num_kmers_loaded == occ_per_step, (st.as_dict(), occ_per_step)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- value: device-resident inputs, CUDA events on the launching stream
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for i in range(args.steps):
+        g.clear()
+        kev[i][0].record(stream)
+        g.add_reads_raw(dseq.data_ptr(), nbytes, M.MCX_LAYOUT_LINES, M.MCX_MEM_DEVICE)
+        kev[i][1].record(stream)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms_total = ev0.elapsed_time(ev1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    st = g.sync()
+    assert st.num_kmers_loaded == occ_per_step, (st.as_dict(), occ_per_step)
+    value = occ_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: pinned host buffer through the C ABI, H2D inside, counters read back every step
+    e_steps = max(1, min(args.steps, 5))
+    step_host()  # warm the staging ring
+    torch.cuda.synchronize()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        st_h = step_host()
+        assert st_h.num_kmers_loaded == occ_per_step
+    ee1.record(stream)
+    torch.cuda.synchronize()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = ee0.elapsed_time(ee1)
+    e2e_val = occ_per_step * e_steps / (max(e2e_ms * 1e-3, e2e_wall))
+    distinct = st_h.num_kmers_novel
+    clocks = sampler.stop()
+
+    # ---- export (not in the metric; reported for the whole-job picture)
+    t0 = time.perf_counter()
+    nrec = C.c_uint64(); rb = C.c_uint32()
+    M.binding._ck(M.lib().mcx_graph_export_begin(g.h, 1, C.byref(nrec), C.byref(rb)), "export")
+    t_export = time.perf_counter() - t0
+    M.lib().mcx_graph_export_end(g.h)
+
+    # ---- CPU baseline: the compiled reference on a bounded sample, host cores of this box
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import oracle as O
+            if O.ref_binary(K) is not None:
+                n_s = 2_000_000 if R >= 2_000_000 else R
+                threads = min(os.cpu_count() or 1, 32)
+                tmpdir = tempfile.mkdtemp(prefix="mcxref", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+                fasta = os.path.join(tmpdir, "sample.fa")
+                write_fasta_sample(fasta, 0, n_s, genome, SL)
+                dt, nk = run_reference_build(fasta, n_s, threads, tmpdir)
+                os.remove(fasta); os.rmdir(tmpdir)
+                cpu = {"value": nk / dt, "unit": "k-mers/s", "cores": threads, "kind": "reference",
+                       "sample": "first %d reads (%d k-mer occurrences) of the workload, `mccortex31 build -t %d`, whole process %.1f s" % (
+                           n_s, nk, threads, dt)}
+        except Exception as ex:  # the baseline is informative; never lose the GPU numbers over it
+            cpu = {"value": None, "unit": "k-mers/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % ex}
+
+    peak, peak_src = measured_peaks()
+    achieved = occ_per_step * B_ALG / (kernel_ms * 1e-3) / 1e9
+    tr = ncu_traffic()
+    line = {
+        "metric": "kmers_per_sec_build_k31", "value": value, "unit": "k-mers/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                     "kernel": "mcx_build_fused_kernel<1>", "kernel_ms": kernel_ms,
+                     "alg_bytes_per_kmer": B_ALG, "kmers_per_launch": occ_per_step,
+                     "traffic_note": (tr or {}).get("note")},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_val, "unit": "k-mers/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 64 + 72,
+                "steps": e_steps, "ms_per_step": 1e3 * max(e2e_ms * 1e-3, e2e_wall) / e_steps},
+        "gpu_launches": args.steps,  # one mcx_build_fused_kernel per step in the `value` region
+        "clocks": clocks,
+        "extra": {"distinct_kmers": distinct, "table_slots": capacity, "host_gen_s": t_gen,
+                  "sorted_export_s": t_export, "export_records": int(nrec.value)},
+    }
+    print(json.dumps(line), flush=True)
+    g.close()
+    M.host_free(host)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--reads", type=int, default=DEFAULT_READS, help="reads per GPU (default: configs[1] = 50M)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,8 +30,10 @@ struct mcx_graph {
   uint64_t capacity;
   McxTable table;
   unsigned long long *d_counters;
-  cudaStream_t streams[MCX_NSTAGE];
+  cudaStream_t own_primary;            // used unless the caller installs a stream
+  cudaStream_t streams[MCX_NSTAGE];    // staging ring: H2D + kernel of one piece per slot
   cudaEvent_t events[MCX_NSTAGE];
+  cudaEvent_t ev_fork;
   uint8_t *d_stage[MCX_NSTAGE];
   uint8_t *h_stage[MCX_NSTAGE];
   bool stage_ready;
@@ -62,7 +64,10 @@ extern "C" int mcx_host_alloc(void **ptr, size_t bytes)
 }
 extern "C" int mcx_host_free(void *ptr) { if(ptr) CU(cudaFreeHost(ptr)); return MCX_OK; }
 
-static cudaStream_t cur_stream(mcx_graph *g, int slot) { return g->use_user_stream ? g->user_stream : g->streams[slot]; }
+// All work of a graph is ordered on its primary stream (the caller's, or our own).  The
+// host-staging path fans out to the ring streams and joins back (event fork/join), so
+// events recorded on the primary stream bracket everything a call enqueued.
+static cudaStream_t primary(mcx_graph *g) { return g->use_user_stream ? g->user_stream : g->own_primary; }
 
 extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, int device, uint32_t flags, mcx_graph **out)
 {
@@ -84,13 +89,15 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
   if(e != cudaSuccess) { free(g); return fail_cuda(e, "cudaMalloc(table)"); }
   e = cudaMalloc(&g->d_counters, MCX_NCOUNTERS * sizeof(unsigned long long));
   if(e != cudaSuccess) { cudaFree(g->table.slots); free(g); return fail_cuda(e, "cudaMalloc(counters)"); }
+  cudaStreamCreateWithFlags(&g->own_primary, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
   for(int i = 0; i < MCX_NSTAGE; i++) {
     cudaStreamCreateWithFlags(&g->streams[i], cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&g->events[i], cudaEventDisableTiming);
   }
-  cudaMemsetAsync(g->table.slots, 0, bytes, g->streams[0]);
-  cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), g->streams[0]);
-  e = cudaStreamSynchronize(g->streams[0]);
+  cudaMemsetAsync(g->table.slots, 0, bytes, g->own_primary);
+  cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), g->own_primary);
+  e = cudaStreamSynchronize(g->own_primary);
   if(e != cudaSuccess) { int r = fail_cuda(e, "memset(table)"); mcx_graph_destroy(g); return r; }
   *out = g;
   return MCX_OK;
@@ -108,6 +115,8 @@ extern "C" int mcx_graph_destroy(mcx_graph *g)
     if(g->streams[i]) cudaStreamDestroy(g->streams[i]);
     if(g->events[i]) cudaEventDestroy(g->events[i]);
   }
+  if(g->own_primary) cudaStreamDestroy(g->own_primary);
+  if(g->ev_fork) cudaEventDestroy(g->ev_fork);
   if(g->d_tmp) cudaFree(g->d_tmp);
   if(g->d_counters) cudaFree(g->d_counters);
   if(g->table.slots) cudaFree(g->table.slots);
@@ -119,15 +128,15 @@ static int sync_all(mcx_graph *g)
 {
   CU(cudaSetDevice(g->device));
   for(int i = 0; i < MCX_NSTAGE; i++) CU(cudaStreamSynchronize(g->streams[i]));
-  if(g->use_user_stream) CU(cudaStreamSynchronize(g->user_stream));
+  CU(cudaStreamSynchronize(primary(g)));
   return MCX_OK;
 }
 
 extern "C" int mcx_graph_clear(mcx_graph *g)
 {
   if(!g) return MCX_ERR_BAD_ARG;
-  int r = sync_all(g); if(r) return r;
-  cudaStream_t st = cur_stream(g, 0);
+  CU(cudaSetDevice(g->device));
+  cudaStream_t st = primary(g);
   CU(cudaMemsetAsync(g->table.slots, 0, (size_t)g->table.nslots * g->table.stride * 4u, st));
   CU(cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), st));
   g->occ_bound = 0; g->pend_positions = 0; g->pend_offsets_reads = g->pend_offsets_bases = 0; g->nkmers = 0;
@@ -171,7 +180,7 @@ static int add_lines_device(mcx_graph *g, const mcx_read_batch *b, const uint8_t
   if(((uintptr_t)dseq & 15u) != 0) { snprintf(g_err, sizeof(g_err), "device seq buffer must be 16-byte aligned"); return MCX_ERR_BAD_ARG; }
   g->occ_bound += nbytes;
   McxBuildParams p = make_params(g, b, dseq, nbytes, 0, nbytes);
-  CU(mcx_launch_build_fused(p, g->table, cur_stream(g, 0)));
+  CU(mcx_launch_build_fused(p, g->table, primary(g)));
   g->pend_positions += nbytes;
   return MCX_OK;
 }
@@ -186,13 +195,16 @@ static int add_lines_host(mcx_graph *g, const mcx_read_batch *b, const uint8_t *
   bool pinned = (cudaPointerGetAttributes(&attr, hseq) == cudaSuccess) && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
   g->occ_bound += nbytes;
+  CU(cudaEventRecord(g->ev_fork, primary(g)));
+  bool used[MCX_NSTAGE] = {false, false, false};
   for(uint64_t pos = 0; pos < nbytes; pos += MCX_STAGE_POS) {
     uint64_t pend = pos + MCX_STAGE_POS < nbytes ? pos + MCX_STAGE_POS : nbytes;
     uint64_t b0 = pos ? pos - MCX_LB : 0;
     uint64_t b1 = pend + MCX_TAIL < nbytes ? pend + MCX_TAIL : nbytes;
     int s = g->next; g->next = (g->next + 1) % MCX_NSTAGE;
-    cudaStream_t st = cur_stream(g, s);
-    CU(cudaEventSynchronize(g->events[s])); // previous user of this slot is done
+    cudaStream_t st = g->streams[s];
+    CU(cudaEventSynchronize(g->events[s])); // previous user of this slot's staging buffers is done
+    if(!used[s]) { CU(cudaStreamWaitEvent(st, g->ev_fork, 0)); used[s] = true; }
     const uint8_t *src = hseq + b0;
     if(!pinned) { memcpy(g->h_stage[s], src, b1 - b0); src = g->h_stage[s]; }
     CU(cudaMemcpyAsync(g->d_stage[s], src, b1 - b0, cudaMemcpyHostToDevice, st));
@@ -200,6 +212,7 @@ static int add_lines_host(mcx_graph *g, const mcx_read_batch *b, const uint8_t *
     CU(mcx_launch_build_fused(p, g->table, st));
     CU(cudaEventRecord(g->events[s], st));
   }
+  for(int s = 0; s < MCX_NSTAGE; s++) if(used[s]) CU(cudaStreamWaitEvent(primary(g), g->events[s], 0));
   g->pend_positions += nbytes;
   return MCX_OK;
 }
@@ -244,7 +257,7 @@ extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
   size_t raw_off = (offs_off + off_bytes + 255) & ~(size_t)255;
   size_t need = raw_off + (b->mem == MCX_MEM_HOST ? ((b->nbytes + 255) & ~(size_t)255) : 0);
   int r = ensure_tmp(g, need + 256); if(r) return r;
-  cudaStream_t st = cur_stream(g, 0);
+  cudaStream_t st = primary(g);
   uint64_t *d_off = (uint64_t *)(g->d_tmp + offs_off);
   const uint8_t *d_raw = (const uint8_t *)b->seq;
   if(b->mem == MCX_MEM_HOST) {
@@ -318,7 +331,7 @@ extern "C" int mcx_graph_export_begin(mcx_graph *g, int sorted, uint64_t *nrecor
   if(!g) return MCX_ERR_BAD_ARG;
   int r = sync_all(g); if(r) return r;
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
-  cudaError_t e = mcx_export_build(g->table, g->k, sorted != 0, &g->exp, cur_stream(g, 0));
+  cudaError_t e = mcx_export_build(g->table, g->k, sorted != 0, &g->exp, primary(g));
   if(e != cudaSuccess) return fail_cuda(e, "export");
   g->exp_valid = true;
   if(nrecords) *nrecords = g->exp.nrec;
@@ -349,7 +362,7 @@ extern "C" int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *b, uint32_t n
   if(b->layout != MCX_LAYOUT_LINES || b->mem != MCX_MEM_DEVICE || ((uintptr_t)b->seq & 15u)) return MCX_ERR_BAD_ARG;
   if(b->hp_cutoff == 1 || b->hp_cutoff > g->k || (b->fq_cutoff && b->qual)) return MCX_ERR_UNSUPPORTED;
   CU(cudaSetDevice(g->device));
-  cudaStream_t st = cur_stream(g, 0);
+  cudaStream_t st = primary(g);
   CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
   McxTupleBins bins;
   bins.keys = keys_out; bins.masks = masks_out; bins.cursor = (unsigned long long *)counts_out;
@@ -367,7 +380,7 @@ extern "C" int mcx_graph_insert_tuples(mcx_graph *g, const uint64_t *keys, const
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
   g->occ_bound += n;
   CU(mcx_launch_insert_tuples(keys, masks, n, g->k, g->table, colour, g->occ_bound >= 0xF0000000ull, g->d_counters,
-                              cur_stream(g, 0)));
+                              primary(g)));
   return MCX_OK;
 }
 

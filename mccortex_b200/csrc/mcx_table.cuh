@@ -50,13 +50,17 @@ __device__ __forceinline__ void mcx_cas128(void *p, uint64_t cmp_lo, uint64_t cm
                : "memory");
 }
 
-// saturating coverage increment; `may_saturate` is a launch-uniform flag the host
-// clears while the total number of occurrences ever sent to this graph is far
-// below 2^32 (then a plain RED is exact).
-__device__ __forceinline__ void mcx_covg_inc(uint32_t *cv, bool may_saturate)
+// saturating coverage increment (reference: CAS loop capped at COVG_MAX, db_node.c:139-144).
+// A plain RED is exact unless the counter is within reach of 2^32.  `may_saturate` is a
+// launch-uniform flag the host clears while fewer than ~4e9 occurrences were ever sent to the
+// graph (then no counter can be near the cap).  When it is set, a snapshot of the counter that
+// came with the probe load (possibly stale by the few 1e5 increments in flight) still proves a
+// RED safe if it is below 0xF0000000; otherwise fall back to the reference's CAS loop.
+__device__ __forceinline__ void mcx_covg_inc(uint32_t *cv, bool may_saturate, bool have_snap = false, uint32_t snap = 0)
 {
-  if(!may_saturate) { atomicAdd(cv, 1u); return; }
+  if(!may_saturate || (have_snap && snap < 0xF0000000u)) { atomicAdd(cv, 1u); return; }
   uint32_t v = *(volatile uint32_t *)cv;
+  if(v < 0xF0000000u) { atomicAdd(cv, 1u); return; }
   while(v != 0xFFFFFFFFu) {
     uint32_t old = atomicCAS(cv, v, v + 1u);
     if(old == v) break;
@@ -113,7 +117,7 @@ __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer
         meta = 0; // freshly claimed or raced: treat edges as unknown-empty => OR is issued
       }
       if(hit) {
-        mcx_covg_inc(hit + 2, may_saturate);
+        mcx_covg_inc(hit + 2, may_saturate, true, (uint32_t)meta);
         mcx_edges_or(hit, 1, 1, 0, emask, (uint32_t)(meta >> 32), true);
         return novel;
       }
