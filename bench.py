@@ -29,8 +29,8 @@ sys.path.insert(0, ROOT)
 
 K = 31
 READ_LEN = 150
-GENOME = 4_600_000
-P_ERR = 0.001
+GENOME = int(os.environ.get("MCX_BENCH_GENOME", 4_600_000))   # env overrides are for experiments only
+P_ERR = float(os.environ.get("MCX_BENCH_PERR", 0.001))
 DEFAULT_READS = 50_000_000
 B_ALG = 19.25  # algorithmic bytes per k-mer occurrence, k=31 single GPU (SURVEY 8d / DESIGN.md)
 B_ALG_MULTI = 43.25

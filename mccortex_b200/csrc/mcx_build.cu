@@ -207,8 +207,8 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
   }
 }
 
-template <int W>
-__global__ void __launch_bounds__(MCX_THREADS, 4) mcx_build_fused_kernel(McxBuildParams p, McxTable t)
+template <int W, int MINB>
+__global__ void __launch_bounds__(MCX_THREADS, MINB) mcx_build_fused_kernel(McxBuildParams p, McxTable t)
 {
   FusedSink<W> sink{t, p.colour, p.may_saturate != 0};
   mcx_front_end<W>(p, sink);
@@ -251,6 +251,57 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_insert_tuples_kernel(const
   }
 }
 
+// ---------------------------------------------------------------- front-table flush
+// merge every front entry {key, count, edges} into the big table (count may be > 1, so the
+// saturating add is a CAS loop here; this kernel touches at most front_nslots keys)
+__global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t, unsigned long long *counters)
+{
+  McxTable big = t; big.front = nullptr; big.front_nslots = 0;
+  uint64_t n_novel = 0; uint32_t full = 0;
+  for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < t.front_nslots; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint4 v = *reinterpret_cast<const uint4 *>(t.front + i * 4u);
+    uint64_t keyf = ((uint64_t)v.y << 32) | v.x;
+    if(keyf == 0) continue;
+    McxKmer<1> key; key.b[0] = keyf & ~MCX_KEY_FLAG;
+    uint32_t count = v.z, edges = v.w & 0xFFu;
+    uint32_t hb, hc = mcx_lookup3<1>(key, 0u, &hb);
+    // find-or-insert in the big table with a zero increment, then add the count
+    uint64_t idx = mcx_home_slot(hc, hb, big.nslots) & ~1ull;
+    uint32_t *hit = nullptr;
+    for(uint64_t probes = 0; probes < big.nslots && !hit; probes += 2) {
+      uint32_t *s = big.slots + idx * 4u;
+      for(int w = 0; w < 2 && !hit; w++) {
+        uint64_t cur = *(volatile uint64_t *)(s + 4 * w);
+        if(cur == 0) {
+          cur = atomicCAS((unsigned long long *)(s + 4 * w), 0ull, (unsigned long long)keyf);
+          if(cur == 0) { n_novel++; cur = keyf; }
+        }
+        if(cur == keyf) hit = s + 4 * w;
+      }
+      idx += 2; if(idx >= big.nslots) idx = 0;
+    }
+    if(!hit) { full = 1; continue; }
+    uint32_t cvv = *(volatile uint32_t *)(hit + 2);
+    for(;;) {
+      uint32_t nv = (cvv + count < cvv) ? 0xFFFFFFFFu : cvv + count;
+      uint32_t old = atomicCAS(hit + 2, cvv, nv);
+      if(old == cvv) break;
+      cvv = old;
+    }
+    if(edges) atomicOr(hit + 3, edges);
+  }
+  for(int s = 16; s > 0; s >>= 1) {
+    n_novel += __shfl_xor_sync(0xFFFFFFFFu, n_novel, s);
+    full |= __shfl_xor_sync(0xFFFFFFFFu, full, s);
+  }
+  if((threadIdx.x & 31u) == 0) {
+    if(n_novel) atomicAdd(&counters[MCX_CNT_NOVEL], (unsigned long long)n_novel);
+    if(full) atomicOr(&counters[MCX_CNT_FULL], 1ull);
+  }
+}
+
+cudaError_t mcx_launch_front_flush(const McxTable &t, unsigned long long *counters, cudaStream_t st);
+
 // ---------------------------------------------------------------- repack
 // OFFSETS layout (reads abut, offsets[n+1]) -> LINES layout (each read followed by '\n'):
 // read r moves from [off[r], off[r+1]) to [off[r]+r, off[r+1]+r), terminator at off[r+1]+r.
@@ -268,6 +319,7 @@ __global__ void mcx_repack_lines_kernel(const uint8_t *__restrict__ src, const u
 
 // ---------------------------------------------------------------- launchers
 static int g_num_sms = 0;
+static int g_minb = 4; // resident CTAs per SM the fused kernel is compiled / launched for (experiment knob)
 static int num_sms()
 {
   if(!g_num_sms) {
@@ -288,9 +340,16 @@ static unsigned grid_for_chunks(const McxBuildParams &p, int ctas_per_sm)
 cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, cudaStream_t st)
 {
   if(p.r_end <= p.r_begin) return cudaSuccess;
-  unsigned grid = grid_for_chunks(p, 4);
-  if(p.k <= 31) mcx_build_fused_kernel<1><<<grid, MCX_THREADS, 0, st>>>(p, t);
-  else mcx_build_fused_kernel<2><<<grid, MCX_THREADS, 0, st>>>(p, t);
+  const int minb = g_minb;
+  unsigned grid = grid_for_chunks(p, minb);
+  if(p.k <= 31) {
+    switch(minb) {
+      case 5: mcx_build_fused_kernel<1, 5><<<grid, MCX_THREADS, 0, st>>>(p, t); break;
+      case 6: mcx_build_fused_kernel<1, 6><<<grid, MCX_THREADS, 0, st>>>(p, t); break;
+      case 8: mcx_build_fused_kernel<1, 8><<<grid, MCX_THREADS, 0, st>>>(p, t); break;
+      default: mcx_build_fused_kernel<1, 4><<<grid, MCX_THREADS, 0, st>>>(p, t); break;
+    }
+  } else mcx_build_fused_kernel<2, 4><<<grid, MCX_THREADS, 0, st>>>(p, t);
   return cudaGetLastError();
 }
 
@@ -322,3 +381,16 @@ cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uin
   mcx_repack_lines_kernel<<<grid, MCX_THREADS, 0, st>>>(src, off, nreads, dst);
   return cudaGetLastError();
 }
+
+cudaError_t mcx_launch_front_flush(const McxTable &t, unsigned long long *counters, cudaStream_t st)
+{
+  if(!t.front_nslots) return cudaSuccess;
+  mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, counters);
+  cudaError_t e = cudaGetLastError();
+  if(e != cudaSuccess) return e;
+  return cudaMemsetAsync(t.front, 0, t.front_nslots * 16u, st);
+}
+
+// ---------------------------------------------------------------- tuning knobs (experiments)
+void mcx_set_minb(int minb) { g_minb = (minb == 5 || minb == 6 || minb == 8) ? minb : 4; }
+cudaError_t mcx_set_ld_mode(int mode) { return cudaMemcpyToSymbol(mcx_ld_mode, &mode, sizeof(int)); }

@@ -22,13 +22,40 @@ struct McxTable {
   uint64_t nslots;      // always even
   uint32_t stride;      // u32 words per slot
   uint32_t ncols;
+  // L2-resident front table (16-byte slots {key, count, edges}, k <= 31, one colour only):
+  // a dense write-combining cache in front of the big table.  The big table is >> L2 and a
+  // hot k-mer there drags a whole 128-byte L2 line for 16 useful bytes, so on high-coverage
+  // input the hot set does not fit L2 (ncu: 127 B of DRAM traffic per occurrence, L2 hit
+  // rate 30 %).  Keys that win a front slot (first come, 2-way per 32-byte sector, no
+  // probing beyond it) are counted here at L2 speed and merged into the big table by
+  // mcx_front_flush_kernel; everything else falls through to the big table.  Sums and ORs
+  // commute, so the final table is identical.
+  uint32_t *front;      // front_nslots * 4 u32, or nullptr
+  uint64_t front_nslots;
+  uint32_t front_ways;  // 2 = one sector, 4 = a second sector chosen by an independent hash
 };
 
 #if defined(__CUDACC__)
 
+// 32-byte probe load.  MCX_LD_MODE picks the cache behaviour (measured with ncu, see
+// profiles/): 0 default (.ca), 1 .cg (L2 only), 2 volatile, 3 two 16-byte .cg loads,
+// 4 L1::no_allocate
+#ifndef MCX_LD_MODE_RUNTIME
+#define MCX_LD_MODE_RUNTIME 1
+#endif
+static __device__ int mcx_ld_mode = 0;
 __device__ __forceinline__ void mcx_ld256(const void *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d)
 {
-  asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  switch(mcx_ld_mode) {
+    case 1: asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p)); break;
+    case 2: asm volatile("ld.volatile.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p)); break;
+    case 3:
+      asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+      asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2+16];" : "=l"(c), "=l"(d) : "l"(p));
+      break;
+    case 4: asm volatile("ld.global.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p)); break;
+    default: asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p)); break;
+  }
 }
 
 __device__ __forceinline__ void mcx_ld128(const void *p, uint64_t &a, uint64_t &b)
@@ -93,6 +120,35 @@ __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer
   uint64_t idx = mcx_home_slot(hc, hb, t.nslots);
   int novel = 0;
   if(t.stride == 4u) {
+    if(t.front_nslots) {
+      // front table: two ways per 32-byte sector, claim-if-empty, never evict; with
+      // front_ways == 4 a second sector (independent hash) is tried when the first is taken
+      uint64_t fi = mcx_mulhi64(((uint64_t)hc << 32) | hb, t.front_nslots) & ~1ull;
+#pragma unroll 1
+      for(uint32_t way = 0; way < t.front_ways; way += 2) {
+        uint32_t *s = t.front + fi * 4u;
+        uint64_t k0, m0, k1, m1;
+        mcx_ld256(s, k0, m0, k1, m1);
+        uint32_t *hit = nullptr; uint64_t meta = 0;
+        if(k0 == keyf) { hit = s; meta = m0; }
+        else if(k1 == keyf) { hit = s + 4; meta = m1; }
+        else if(k0 == 0 || k1 == 0) {
+          uint32_t *cand = (k0 == 0) ? s : s + 4;
+          uint64_t old = atomicCAS((unsigned long long *)cand, 0ull, (unsigned long long)keyf);
+          if(old == 0 || old == keyf) hit = cand;
+          else if(cand == s && k1 == 0) {
+            old = atomicCAS((unsigned long long *)(s + 4), 0ull, (unsigned long long)keyf);
+            if(old == 0 || old == keyf) hit = s + 4;
+          }
+        }
+        if(hit) {
+          mcx_covg_inc(hit + 2, true, true, (uint32_t)meta); // front counters always guard against wrap
+          mcx_edges_or(hit, 1, 1, 0, emask, (uint32_t)(meta >> 32), true);
+          return 0; // novelty is decided when the entry is merged into the big table
+        }
+        fi = mcx_mulhi64((((uint64_t)hb * 0x9E3779B1u) << 32) ^ (((uint64_t)hc << 32) | hb) ^ hc, t.front_nslots) & ~1ull;
+      }
+    }
     // 16-byte slots {key, covg, edges}: probe one 32-byte sector (= 2 slots) per load
     idx &= ~1ull;
     for(uint64_t probes = 0; probes < t.nslots; probes += 2) {

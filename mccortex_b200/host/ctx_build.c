@@ -1,0 +1,418 @@
+/* ctx_build.c -- `mccortex-b200 build [options] <out.ctx>`
+ *
+ * Drop-in for the reference's `mccortexNN build` (src/commands/ctx_build.c, dispatched from
+ * src/main/mccortex.c:279-332): same options, same ordering rules, same exit status and the
+ * same .ctx v6 bytes (with -S), but the graph lives on a B200 behind include/mcx_gpu.h.
+ * One binary serves every odd k in 3..63 and writes W = ceil(k/32) in the header, which is
+ * what mccortex31 / mccortex63 write for their k ranges.
+ *
+ * Not (yet) supported, and rejected with an error rather than silently ignored:
+ *   -p/--remove-pcr (order dependent in the reference), -g/--graph, -I/--intersect,
+ *   -Q/--fq-cutoff on inputs that carry qualities, SAM/BAM/CRAM input.
+ */
+#include "mcx_host.h"
+#include <ctype.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <getopt.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+#include <time.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#define CMD "mccortex-b200"
+#define MAX_IO_THREADS 10 /* src/global/global.h:41: tasks per build_graph() call */
+#define MIN_KMER 3
+#define MAX_KMER 63
+
+static const char build_usage[] =
+"usage: "CMD" build [options] <out.ctx>\n"
+"\n"
+"  Build a cortex graph on a B200 GPU.  \n"
+"\n"
+"  -h, --help               This help message\n"
+"  -q, --quiet              Silence status output normally printed to STDERR\n"
+"  -f, --force              Overwrite output files\n"
+"  -m, --memory <mem>       Memory to use\n"
+"  -n, --nkmers <kmers>     Number of hash table entries (e.g. 1G ~ 1 billion)\n"
+"  -t, --threads <T>        Accepted for compatibility (the GPU does the work)\n"
+"  -k, --kmer <kmer>        Kmer size must be odd (63 >= k >= 3)\n"
+"  -s, --sample <name>      Sample name (required before any seq args)\n"
+"  -1, --seq <in.fa>        Load sequence data\n"
+"  -2, --seq2 <in1:in2>     Load paired end sequence data\n"
+"  -i, --seqi <in.fq>       Load paired end sequence from a single file\n"
+"  -Q, --fq-cutoff <Q>      Filter quality scores [default: 0 (off)]\n"
+"  -O, --fq-offset <N>      FASTQ ASCII offset    [default: 0 (auto-detect)]\n"
+"  -H, --cut-hp <bp>        Breaks reads at homopolymers >= <bp> [default: off]\n"
+"  -p, --remove-pcr         Remove (or keep) PCR duplicate reads [not supported]\n"
+"  -P, --keep-pcr           Don't do PCR duplicate removal [default]\n"
+"  -M, --matepair <orient>  Mate pair orientation: FF,FR,RF,RR [default: FR]\n"
+"  -g, --graph <in.ctx>     Load samples from a graph file (.ctx) [not supported]\n"
+"  -I, --intersect <i.ctx>  Only load kmers that appear in i.ctx [not supported]\n"
+"  -S, --sort               Output a graph file ordered by kmer\n"
+"  -D, --device <id>        CUDA device [default: 0]\n"
+"\n"
+"  Note: Argument must come before input file\n"
+"  --sample <name> is required before sequence input can be loaded.\n"
+"  Consecutive sequence options are loaded into the same colour.\n"
+"\n";
+
+static struct option longopts[] = {
+  {"help", no_argument, NULL, 'h'},       {"memory", required_argument, NULL, 'm'},
+  {"nkmers", required_argument, NULL, 'n'}, {"threads", required_argument, NULL, 't'},
+  {"force", no_argument, NULL, 'f'},      {"kmer", required_argument, NULL, 'k'},
+  {"sample", required_argument, NULL, 's'}, {"sort", no_argument, NULL, 'S'},
+  {"seq", required_argument, NULL, '1'},  {"seq2", required_argument, NULL, '2'},
+  {"seqi", required_argument, NULL, 'i'}, {"matepair", required_argument, NULL, 'M'},
+  {"fq-cutoff", required_argument, NULL, 'Q'}, {"fq-offset", required_argument, NULL, 'O'},
+  {"cut-hp", required_argument, NULL, 'H'}, {"remove-pcr", no_argument, NULL, 'p'},
+  {"keep-pcr", no_argument, NULL, 'P'},   {"graph", required_argument, NULL, 'g'},
+  {"intersect", required_argument, NULL, 'I'}, {"device", required_argument, NULL, 'D'},
+  {NULL, 0, NULL, 0}};
+
+typedef struct {
+  McxSeqFile *file;
+  McxLoadPrefs prefs;
+  mcx_load_stats stats;
+} BuildTask;
+
+static BuildTask *tasks = NULL; static size_t ntasks = 0, tasks_cap = 0;
+static char **sample_names = NULL; static size_t nsamples = 0;
+static size_t nthreads = 0, kmer_size = 0, output_colours = 0;
+static bool mem_set = false, nkmers_set = false, force = false, sort_kmers = false;
+static size_t mem_to_use = MCX_DEFAULT_MEM, num_kmers = MCX_DEFAULT_NKMERS;
+static int device = 0;
+static char *out_path = NULL;
+
+#define usage_err(...) mcx_print_usage(build_usage, __VA_ARGS__)
+
+static void opt_name(int c, char *out, size_t n)
+{
+  const struct option *o;
+  snprintf(out, n, "-%c, --Unknown", c);
+  for(o = longopts; o->name; o++) if(o->val == c) { snprintf(out, n, "-%c, --%s", c, o->name); return; }
+}
+
+static size_t parse_size(const char *cmd, const char *arg, bool nonzero)
+{
+  char *end; unsigned long v;
+  if(*arg < '0' || *arg > '9') usage_err("%s requires an int x >= 0: %s", cmd, arg);
+  v = strtoul(arg, &end, 10);
+  if(*end) usage_err("%s requires an int x >= 0: %s", cmd, arg);
+  if(nonzero && v == 0) usage_err("%s <N> must be > 0: %s", cmd, arg);
+  return v;
+}
+static uint8_t parse_uint8(const char *cmd, const char *arg)
+{
+  size_t v = parse_size(cmd, arg, false);
+  if(v > 255) usage_err("%s requires an int 0 <= x < 256: %s", cmd, arg);
+  return (uint8_t)v;
+}
+
+/* src/commands/ctx_build.c:119-131 */
+static void check_sample_name(const char *s)
+{
+  const char *p;
+  if(strlen(s) < 1) mcx_die("Sample name is too short: '%s'", s);
+  if(!strcmp(s, "undefined")) mcx_die("Bad sample name: '%s'", s);
+  if(!strcmp(s, "noname")) mcx_die("Bad sample name: '%s'", s);
+  if(s[0] == '.') mcx_die("Sample name should start with a dot: '%s'", s);
+  for(p = s; *p; p++) {
+    if(isspace((unsigned char)*p)) mcx_die("Sample name should not contain whitespace: '%s'", s);
+    if(!isgraph((unsigned char)*p)) mcx_die("Bad character in sample name: '%s'", s);
+  }
+}
+
+static bool has_ext(const char *p, const char *ext)
+{
+  size_t n = strlen(p), m = strlen(ext);
+  return n >= m && strcasecmp(p + n - m, ext) == 0;
+}
+
+static void push_task(const char *path, char opt, const McxLoadPrefs *prefs)
+{
+  if(has_ext(path, ".sam") || has_ext(path, ".bam") || has_ext(path, ".cram"))
+    mcx_die("SAM/BAM/CRAM input is not supported by "CMD": %s", path);
+  McxSeqFile *sf = mcx_seq_open(path);
+  if(!sf) mcx_die("Cannot open -%c file: %s", opt, path);
+  if(ntasks == tasks_cap) { tasks_cap = tasks_cap ? tasks_cap * 2 : 16; tasks = realloc(tasks, tasks_cap * sizeof(*tasks)); }
+  memset(&tasks[ntasks], 0, sizeof(tasks[ntasks]));
+  tasks[ntasks].file = sf; tasks[ntasks].prefs = *prefs;
+  ntasks++;
+}
+
+/* src/commands/ctx_build.c:99-117 (add_task) + src/basic/async_read_io.c:27-80: without
+ * --remove-pcr a --seq2 pair is two independent single-end tasks */
+static void add_seq_arg(char opt, char *arg, const McxLoadPrefs *prefs)
+{
+  if(prefs->fq_offset >= 128) mcx_die("fq-offset too big: %i", (int)prefs->fq_offset);
+  if(prefs->fq_offset + prefs->fq_cutoff >= 128) mcx_die("fq-cutoff too big: %i", prefs->fq_offset + prefs->fq_cutoff);
+  if(opt == '2') {
+    char *sep = strchr(arg, ':');
+    if(!sep) sep = strchr(arg, ',');
+    if(!sep || strchr(sep + 1, *sep)) mcx_die("Expected -%c <in1>:<in2>", opt);
+    *sep = '\0';
+    push_task(arg, opt, prefs);
+    push_task(sep + 1, opt, prefs);
+  } else push_task(arg, opt, prefs);
+}
+
+static void parse_args(int argc, char **argv)
+{
+  McxLoadPrefs prefs; memset(&prefs, 0, sizeof(prefs));
+  int intocolour = -1, c;
+  bool sample_named = false, pref_unused = false, kmer_given = false, threads_given = false;
+  char cmd[100];
+  const char shortopts[] = "+hm:n:t:fk:s:S1:2:i:M:Q:O:H:pPg:I:D:";
+
+  while((c = getopt_long_only(argc, argv, shortopts + 1, longopts, NULL)) != -1) {
+    opt_name(c, cmd, sizeof(cmd));
+    switch(c) {
+      case 0: break;
+      case 'h': usage_err(NULL); break;
+      case 't': if(threads_given) usage_err("%s given twice", cmd); threads_given = true;
+                nthreads = parse_size(cmd, optarg, true); break;
+      case 'm': if(mem_set) usage_err("-m, --memory <M> specifed more than once");
+                if(!mcx_mem_to_integer(optarg, &mem_to_use)) usage_err("-m, --memory <M> requires a size e.g. 1GB: %s", optarg);
+                if(mem_to_use == 0) usage_err("--memory <M> cannot be zero");
+                mem_set = true; break;
+      case 'n': if(nkmers_set) usage_err("-n, --nkmers <N> specifed more than once");
+                if(!mcx_mem_to_integer(optarg, &num_kmers)) usage_err("-n, --nkmers <M> requires a size e.g. 1G: %s", optarg);
+                if(num_kmers == 0) usage_err("--nkmer <N> cannot be zero");
+                nkmers_set = true; break;
+      case 'f': if(force) usage_err("%s given twice", cmd); force = true; break;
+      case 'k': if(kmer_given) usage_err("%s given twice", cmd); kmer_given = true;
+                kmer_size = parse_size(cmd, optarg, true);
+                if(kmer_size < MIN_KMER || kmer_size > MAX_KMER) mcx_die("Please recompile with correct kmer size (%zu)", kmer_size);
+                if(!(kmer_size & 1)) mcx_die("Invalid kmer-size (%zu): requires odd number %i <= k <= %i", kmer_size, MIN_KMER, MAX_KMER);
+                break;
+      case 's':
+        intocolour++;
+        check_sample_name(optarg);
+        sample_names = realloc(sample_names, (nsamples + 1) * sizeof(char *));
+        sample_names[nsamples++] = optarg;
+        sample_named = true;
+        break;
+      case 'S': if(sort_kmers) usage_err("%s given twice", cmd); sort_kmers = true; break;
+      case '1': case '2': case 'i':
+        pref_unused = false;
+        if(!sample_named) usage_err("Please give sample name first [-s,--sample <name>]");
+        prefs.colour = (uint32_t)intocolour;
+        add_seq_arg((char)c, optarg, &prefs);
+        break;
+      case 'M':
+        if(strcmp(optarg, "FF") && strcmp(optarg, "FR") && strcmp(optarg, "RF") && strcmp(optarg, "RR"))
+          mcx_die("-M,--matepair <orient> must be one of: FF,FR,RF,RR");
+        pref_unused = true; break; /* only matters with --remove-pcr */
+      case 'O': prefs.fq_offset = parse_uint8(cmd, optarg); pref_unused = true; break;
+      case 'Q': prefs.fq_cutoff = parse_uint8(cmd, optarg); pref_unused = true; break;
+      case 'H': prefs.hp_cutoff = parse_uint8(cmd, optarg); pref_unused = true; break;
+      case 'p': mcx_die("--remove-pcr is not supported by "CMD" (order-dependent in the reference)");
+      case 'P': pref_unused = true; break;
+      case 'g': mcx_die("--graph is not supported by "CMD" yet");
+      case 'I': mcx_die("--intersect is not supported by "CMD" yet");
+      case 'D': device = (int)parse_size(cmd, optarg, false); break;
+      case ':': case '?':
+        mcx_die("`"CMD" build -h` for help. Bad option: %s", argv[optind - 1]);
+      default: mcx_die("Bad option: %s", cmd);
+    }
+  }
+  if(!nthreads) nthreads = 2;
+
+  if(optind + 1 > argc) usage_err("Expected exactly one graph file");
+  else if(optind + 1 < argc) usage_err("Expected only one graph file. What is this: '%s'", argv[optind]);
+  out_path = argv[optind];
+  mcx_status("Saving graph to: %s", strcmp(out_path, "-") ? out_path : "STDOUT");
+
+  if(nsamples == 0) usage_err("No inputs given");
+  if(pref_unused) usage_err("Arguments not given BEFORE sequence file");
+  if(!kmer_size) mcx_die("kmer size not set with -k <K>");
+  output_colours = (size_t)(intocolour + (sample_named ? 1 : 0));
+}
+
+/* src/basic/file_util.c:164-174 */
+static void create_output(const char *path)
+{
+  if(strcmp(path, "-") == 0) return;
+  int mode = O_CREAT | O_EXCL | O_WRONLY | O_APPEND;
+  if(force) mode &= ~O_EXCL;
+  int fd = open(path, mode, 0666);
+  if(fd < 0) {
+    if(errno == EEXIST) mcx_die("File already exists: %s", path);
+    else mcx_die("Cannot write to file: %s [%s]", path, strerror(errno));
+  }
+  close(fd);
+}
+
+static void die_mcx(int r, const char *what)
+{
+  if(r == MCX_ERR_TABLE_FULL) mcx_die("Hash table is full"); /* src/graph/hash_table.c:119-123 */
+  if(r == MCX_ERR_NOMEM) mcx_die("Out of memory on the GPU (%s)", mcx_last_error());
+  if(r == MCX_ERR_NO_DEVICE) mcx_die("No CUDA device: "CMD" has no CPU fallback");
+  if(r == MCX_ERR_UNSUPPORTED) mcx_die("%s: not supported (%s)", what, mcx_last_error());
+  mcx_die("%s failed [%i]: %s", what, r, mcx_last_error());
+}
+
+/* src/tools/build_graph.c:352-386 */
+static void print_task_stats(const BuildTask *t)
+{
+  char a[64], b[64], c[64];
+  mcx_status("[task] input: %s colour: %u", mcx_seq_path(t->file), t->prefs.colour);
+  mcx_ulong_to_str(t->stats.num_se_reads, a); mcx_ulong_to_str(t->stats.num_pe_reads, b);
+  mcx_status("  SE reads: %s  PE reads: %s", a, b);
+  if(t->stats.num_good_reads != UINT64_MAX) {
+    mcx_ulong_to_str(t->stats.num_good_reads, a); mcx_ulong_to_str(t->stats.num_bad_reads, b);
+    mcx_status("  good reads: %s  bad reads: %s", a, b);
+  }
+  mcx_status("  dup SE reads: 0  dup PE pairs: 0");
+  mcx_ulong_to_str(t->stats.total_bases_read, a); mcx_ulong_to_str(t->stats.total_bases_loaded, b);
+  mcx_status("  bases read: %s  bases loaded: %s", a, b);
+  mcx_ulong_to_str(t->stats.contigs_parsed, a); mcx_ulong_to_str(t->stats.num_kmers_loaded, b);
+  mcx_ulong_to_str(t->stats.num_kmers_novel, c);
+  mcx_status("  num contigs: %s  num kmers: %s novel kmers: %s", a, b, c);
+}
+
+static int ctx_build(int argc, char **argv)
+{
+  size_t i, s, t;
+  parse_args(argc, argv);
+
+  for(s = t = 0; s < nsamples || t < ntasks;) {
+    if(t == ntasks || (s < nsamples && s <= tasks[t].prefs.colour)) { mcx_status("[sample] %zu: %s", s, sample_names[s]); s++; }
+    else {
+      char off[32] = "auto-detect", cut[32] = "off", hp[32] = "off";
+      if(tasks[t].prefs.fq_offset) sprintf(off, "%u", tasks[t].prefs.fq_offset);
+      if(tasks[t].prefs.fq_cutoff) sprintf(cut, "%u", tasks[t].prefs.fq_cutoff);
+      if(tasks[t].prefs.hp_cutoff) sprintf(hp, "%u", tasks[t].prefs.hp_cutoff);
+      mcx_status("[task] %s; FASTQ offset: %s, threshold: %s; cut homopolymers: %s; remove PCR duplicates: no; colour: %u\n",
+                 mcx_seq_path(tasks[t].file), off, cut, hp, tasks[t].prefs.colour);
+      t++;
+    }
+  }
+
+  /* src/commands/ctx_build.c:285-289 + src/basic/async_read_io.c:313-334: 5 x file bytes */
+  size_t max_kmers = 0;
+  for(t = 0; t < ntasks; t++) {
+    int64_t fsize = mcx_seq_file_size(tasks[t].file);
+    if(fsize < 0) { max_kmers = SIZE_MAX; break; }
+    max_kmers += (size_t)fsize * 5;
+  }
+
+  /* src/commands/ctx_build.c:311-322 */
+  size_t W = (kmer_size + 31) / 32, graph_mem;
+  size_t bits_per_kmer = W * 64 + (32 + 8) * output_colours + (sort_kmers ? 64 : 0);
+  size_t kmers_in_hash = mcx_get_kmers_in_hash(mem_to_use, mem_set, num_kmers, nkmers_set, bits_per_kmer, 0,
+                                               (int64_t)max_kmers, true, &graph_mem);
+  if(graph_mem > mem_to_use) { char m[64]; mcx_bytes_to_str(graph_mem, m); mcx_die("Need to set higher memory limit [ at least -m %s ]", m); }
+
+  create_output(out_path);
+  mcx_status("Writing %zu colour graph to %s\n", output_colours, strcmp(out_path, "-") ? out_path : "STDOUT");
+
+  if(mcx_device_count() == 0) mcx_die("No CUDA device: "CMD" has no CPU fallback");
+  mcx_graph *g = NULL;
+  int r = mcx_graph_create((uint32_t)kmer_size, (uint32_t)output_colours, kmers_in_hash, device, 0, &g);
+  if(r) die_mcx(r, "mcx_graph_create");
+  { char a[64]; mcx_ulong_to_str(kmers_in_hash, a); mcx_status("[hasht] Allocating device table with %s entries on GPU %i", a, device); }
+
+  McxGInfo *ginfo = calloc(output_colours, sizeof(McxGInfo));
+  for(i = 0; i < output_colours; i++) mcx_ginfo_init(&ginfo[i]);
+  for(i = 0; i < nsamples; i++) mcx_ginfo_set_name(&ginfo[i], sample_names[i]);
+
+  /* src/commands/ctx_build.c:389-407: build_graph() on batches of <= 10 tasks.  Quirk Q1
+   * (src/tools/build_graph.c:242 vs :276,:285-300): within one call every task's header
+   * statistics are credited to the batch's FIRST task, i.e. to that task's colour. */
+  size_t start, end;
+  for(start = 0; start < ntasks; start = end) {
+    end = start + MAX_IO_THREADS < ntasks ? start + MAX_IO_THREADS : ntasks;
+    mcx_load_stats credited; memset(&credited, 0, sizeof(credited));
+    for(t = start; t < end; t++) {
+      r = mcx_load_seq_file(g, tasks[t].file, &tasks[t].prefs, &tasks[t].stats);
+      if(r) die_mcx(r, "loading sequence");
+      credited.total_bases_loaded += tasks[t].stats.total_bases_loaded;
+      credited.contigs_parsed += tasks[t].stats.contigs_parsed;
+    }
+    mcx_ginfo_update_contigs(&ginfo[tasks[start].prefs.colour], credited.total_bases_loaded, credited.contigs_parsed);
+  }
+
+  uint64_t nk = 0, cap = 0;
+  mcx_graph_stats(g, &nk, &cap);
+  { char a[64], b[64]; mcx_ulong_to_str(nk, a); mcx_ulong_to_str(cap, b);
+    mcx_status("[hasht] table occupancy: %s / %s (%.2f%%)", a, b, cap ? 100.0 * nk / cap : 0.0); }
+  for(t = 0; t < ntasks; t++) { print_task_stats(&tasks[t]); mcx_seq_close(tasks[t].file); }
+
+  mcx_status("Dumping graph...\n");
+  FILE *fh = strcmp(out_path, "-") ? fopen(out_path, "w") : stdout;
+  if(!fh) mcx_die("Cannot open file: %s [%s]", out_path, strerror(errno));
+  setvbuf(fh, NULL, _IOFBF, 4u << 20);
+  mcx_write_ctx_header(fh, (uint32_t)kmer_size, (uint32_t)output_colours, ginfo);
+
+  uint64_t nrec = 0; uint32_t rec_bytes = 0;
+  r = mcx_graph_export_begin(g, sort_kmers ? 1 : 0, &nrec, &rec_bytes);
+  if(r) die_mcx(r, "mcx_graph_export_begin");
+  size_t chunk_recs = (64u << 20) / rec_bytes;
+  char *buf = malloc(chunk_recs * rec_bytes);
+  for(uint64_t at = 0; at < nrec; at += chunk_recs) {
+    uint64_t n = nrec - at < chunk_recs ? nrec - at : chunk_recs;
+    r = mcx_graph_export_read(g, at, n, buf);
+    if(r) die_mcx(r, "mcx_graph_export_read");
+    if(fwrite(buf, rec_bytes, n, fh) != n) mcx_die("Cannot write to file");
+  }
+  free(buf);
+  mcx_graph_export_end(g);
+  if(fh != stdout) fclose(fh); else fflush(fh);
+  { char a[64]; mcx_ulong_to_str(nrec, a);
+    mcx_status("[graphwriter] Dumped %s kmers in %zu colour%s into: %s (format version: 6)", a, output_colours,
+               output_colours == 1 ? "" : "s", strcmp(out_path, "-") ? out_path : "STDOUT"); }
+
+  for(i = 0; i < output_colours; i++) mcx_ginfo_free(&ginfo[i]);
+  free(ginfo); free(tasks); free(sample_names);
+  mcx_graph_destroy(g);
+  return EXIT_SUCCESS;
+}
+
+/* src/main/mccortex.c:255-277: strip -q / --quiet anywhere on the line */
+static bool remove_quiet_flags(int *argcp, char **argv)
+{
+  bool q = false; int i, j, argc = *argcp;
+  for(i = j = 1; i < argc; i++) {
+    if(!strcmp(argv[i], "--quiet") || !strcmp(argv[i], "-q")) { q = true; continue; }
+    if(argv[i][0] == '-' && argv[i][1] != '-') {
+      char *p, *w;
+      for(p = w = argv[i] + 1; *p; p++) { if(*p == 'q') q = true; else *w++ = *p; }
+      *w = '\0';
+    }
+    argv[j++] = argv[i];
+  }
+  *argcp = j;
+  return q;
+}
+
+int main(int argc, char **argv)
+{
+  time_t t0 = time(NULL);
+  mcx_msg_out = stderr;
+  if(argc < 2 || strcasecmp(argv[1], "build") != 0) {
+    fprintf(stderr, "\nusage: "CMD" build [options] <out.ctx>\n"
+                    "  the only command of this binary; output is a CORTEX v6 graph for the rest of McCortex\n\n");
+    return EXIT_FAILURE;
+  }
+  if(argc == 2) mcx_print_usage(build_usage, NULL);
+  /* command line for the log, before -q is stripped */
+  size_t len = 0; int i;
+  for(i = 0; i < argc; i++) len += strlen(argv[i]) + 1;
+  char *line = malloc(len + 1); line[0] = 0;
+  for(i = 0; i < argc; i++) { strcat(line, argv[i]); if(i + 1 < argc) strcat(line, " "); }
+  if(remove_quiet_flags(&argc, argv)) mcx_msg_out = NULL;
+  mcx_status("[cmd] %s", line);
+  { char cwd[4096]; if(getcwd(cwd, sizeof(cwd))) mcx_status("[cwd] %s", cwd); }
+  mcx_status("[version] "CMD" sm_100a zlib=%s k=%i..%i", ZLIB_VERSION, MIN_KMER, MAX_KMER);
+  free(line);
+
+  char *tmp = argv[1]; argv[1] = argv[0]; argv[0] = tmp;
+  int ret = ctx_build(argc - 1, argv + 1);
+  mcx_status(ret == 0 ? "Done." : "Fail.");
+  mcx_status("[time] %.2lf seconds\n", difftime(time(NULL), t0));
+  return ret;
+}

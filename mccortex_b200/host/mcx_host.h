@@ -1,0 +1,73 @@
+/*
+ * mcx_host.h -- C host side of `mccortex-b200 build` (everything above the C ABI).
+ *
+ * Mirrors, for the build path only, the reference modules named on each
+ * declaration (paths relative to the reference root).  Plain C99.
+ */
+#ifndef MCX_HOST_H_
+#define MCX_HOST_H_
+
+#include <stdint.h>
+#include <stddef.h>
+#include <stdbool.h>
+#include <stdio.h>
+#include "mcx_gpu.h"
+
+/* ---- output conventions: src/global/ctx_output.{c,h} ---------------------- */
+extern FILE *mcx_msg_out;                 /* NULL when -q/--quiet */
+void mcx_status(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+void mcx_warn(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+void mcx_die(const char *fmt, ...) __attribute__((noreturn)) __attribute__((format(printf, 1, 2)));
+void mcx_print_usage(const char *usage, const char *errfmt, ...) __attribute__((noreturn))
+    __attribute__((format(printf, 2, 3)));
+void mcx_ulong_to_str(uint64_t n, char *out);          /* 1,234,567  (util.c ulong_to_str) */
+void mcx_bytes_to_str(uint64_t bytes, char *out);      /* 1.5GB      (util.c bytes_to_str, 1 decimal) */
+bool mcx_mem_to_integer(const char *arg, size_t *bytes); /* src/global/util.c:206-222 */
+
+/* ---- table sizing: src/basic/hash_mem.{c,h}, src/graph/cmd_mem.c ----------- */
+#define MCX_IDEAL_OCCUPANCY 0.75f
+#define MCX_WARN_OCCUPANCY  0.9f
+#define MCX_MAX_BUCKET_SIZE 48
+#define MCX_DEFAULT_MEM     (1UL << 29)
+#define MCX_DEFAULT_NKMERS  (1UL << 22)
+size_t mcx_hash_table_cap(uint64_t nkmers, uint64_t *num_bkts, uint8_t *bkt_size);
+size_t mcx_hash_table_mem(uint64_t nkmers, size_t entrybits, uint64_t *nkmers_out);
+size_t mcx_hash_table_mem_limit(size_t memlimit, size_t entrybits, uint64_t *nkmers_out);
+size_t mcx_get_kmers_in_hash(size_t mem_to_use, bool mem_to_use_set, size_t num_kmers, bool num_kmers_set,
+                             size_t entry_bits, int64_t min_num_kmer_req, int64_t max_num_kmers_req,
+                             bool use_mem_limit, size_t *graph_mem_ptr);
+
+/* ---- header metadata: src/basic/graph_info.{c,h}, src/graph/graph_writer.c -- */
+typedef struct {
+  uint32_t mean_read_length;
+  uint64_t total_sequence;
+  long double seq_err;
+  char *sample_name;          /* malloc'd */
+} McxGInfo;
+void mcx_ginfo_init(McxGInfo *g);
+void mcx_ginfo_free(McxGInfo *g);
+void mcx_ginfo_set_name(McxGInfo *g, const char *name);
+void mcx_ginfo_update_contigs(McxGInfo *g, uint64_t added_seq, uint64_t num_contigs);
+void mcx_ginfo_merge(McxGInfo *dst, const McxGInfo *src);
+/* writes the .ctx v6 header for ncols colours after merging every colour into a fresh
+ * header entry, exactly as graph_writer_mkhdr does; returns bytes written */
+size_t mcx_write_ctx_header(FILE *fh, uint32_t kmer_size, uint32_t ncols, const McxGInfo *ginfo);
+
+/* ---- sequence input: libs/seq_file/seq_file.h, src/basic/seq_reader.c -------- */
+typedef struct McxSeqFile McxSeqFile;
+McxSeqFile *mcx_seq_open(const char *path);            /* gz or plain, "-" = stdin */
+void mcx_seq_close(McxSeqFile *sf);
+const char *mcx_seq_path(const McxSeqFile *sf);
+int64_t mcx_seq_file_size(const McxSeqFile *sf);       /* -1 if unknown (stdin) */
+
+typedef struct {
+  uint8_t fq_cutoff, hp_cutoff, fq_offset;             /* fq_offset 0 = auto-detect */
+  uint32_t colour;
+} McxLoadPrefs;
+
+/* Parse every read of sf (FASTA / FASTQ / plain, sniffed from the first byte like
+ * seq_file.h:311-323) and feed the graph in LINES batches.  Stats of this file are ADDED
+ * to *stats.  Returns 0, or the MCX_ERR_* that stopped the load. */
+int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats);
+
+#endif /* MCX_HOST_H_ */

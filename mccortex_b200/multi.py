@@ -1,0 +1,172 @@
+"""Multi-GPU plumbing for the build path: one process per GPU, one table shard per process.
+
+Per batch: kernel B (`mcx_kmer_tuples`) turns the local reads into canonical
+(key, edge-mask) tuples binned by owner = top bits of the Lookup3 hash; the bins are exchanged
+(one all-to-all step: a count matrix, then point-to-point sends of the ragged bins, NCCL over
+NVLink on the GPUs / gloo in the CPU tests); kernel C (`mcx_graph_insert_tuples`) inserts what
+arrived into the local shard.  No remote atomics, no other collective on the data path.
+
+`exchange_bins` is backend-agnostic so the host-side logic is covered by world_size-2 gloo tests
+on CPU tensors (tests/test_multi_cpu.py).
+"""
+import ctypes as C
+import json
+import os
+import time
+
+
+def exchange_counts(dist, counts):
+    """counts[d] = tuples this rank holds for rank d  ->  recv[s] = tuples rank s holds for us"""
+    import torch
+    recv = torch.empty_like(counts)
+    dist.all_to_all_single(recv, counts)
+    return recv
+
+
+def exchange_bins(dist, rank, world, keys, masks, counts_host, recv_counts_host, cap, W, recv_keys, recv_masks):
+    """Ragged all-to-all of the bins.
+
+    keys: [world*cap*W] int64, masks: [world*cap] uint8 (bin d starts at d*cap); recv_* likewise
+    (bin s = tuples received from rank s).  counts_host / recv_counts_host: python ints.
+    The local bin is copied, the others go through grouped isend/irecv (one NCCL group)."""
+    ops = []
+    for peer in range(world):
+        n_out, n_in = counts_host[peer], recv_counts_host[peer]
+        if n_in > cap:
+            raise RuntimeError("receive bin overflow: %d > %d" % (n_in, cap))
+        if peer == rank:
+            recv_keys[peer * cap * W: (peer * cap + n_in) * W].copy_(keys[peer * cap * W: (peer * cap + n_out) * W])
+            recv_masks[peer * cap: peer * cap + n_in].copy_(masks[peer * cap: peer * cap + n_out])
+            continue
+        if n_out:
+            ops.append(dist.P2POp(dist.isend, keys[peer * cap * W: (peer * cap + n_out) * W], peer))
+            ops.append(dist.P2POp(dist.isend, masks[peer * cap: peer * cap + n_out], peer))
+        if n_in:
+            ops.append(dist.P2POp(dist.irecv, recv_keys[peer * cap * W: (peer * cap + n_in) * W], peer))
+            ops.append(dist.P2POp(dist.irecv, recv_masks[peer * cap: peer * cap + n_in], peer))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+
+class ShardedBuilder:
+    """One rank's side of the sharded build (device tensors owned by torch = plumbing only)."""
+
+    def __init__(self, M, dist, rank, world, device, k, capacity_per_shard, cap_per_part):
+        import torch
+        self.M, self.dist, self.rank, self.world, self.dev = M, dist, rank, world, device
+        self.k, self.W, self.cap = k, (k + 31) // 32, cap_per_part
+        self.g = M.Graph(k, 1, capacity_per_shard, device=device.index)
+        n = world * cap_per_part
+        self.keys = torch.empty(n * self.W, dtype=torch.int64, device=device)
+        self.masks = torch.empty(n, dtype=torch.uint8, device=device)
+        self.rkeys = torch.empty(n * self.W, dtype=torch.int64, device=device)
+        self.rmasks = torch.empty(n, dtype=torch.uint8, device=device)
+        self.counts = torch.zeros(world, dtype=torch.int64, device=device)
+        self.launches = 0
+
+    def set_stream(self, stream):
+        self.g.set_stream(stream.cuda_stream)
+
+    def add_batch(self, seq_addr, nbytes):
+        import torch
+        g, W, cap, world = self.g, self.W, self.cap, self.world
+        g.kmer_tuples(seq_addr, nbytes, world, cap, self.keys.data_ptr(), self.masks.data_ptr(), self.counts.data_ptr())
+        self.launches += 1
+        recv = exchange_counts(self.dist, self.counts)
+        ch, rh = self.counts.tolist(), recv.tolist()
+        if max(ch) > cap:
+            raise RuntimeError("send bin overflow: %d > %d" % (max(ch), cap))
+        exchange_bins(self.dist, self.rank, world, self.keys, self.masks, ch, rh, cap, W, self.rkeys, self.rmasks)
+        for s in range(world):
+            if rh[s]:
+                g.insert_tuples(self.rkeys[s * cap * W:].data_ptr(), self.rmasks[s * cap:].data_ptr(), rh[s])
+                self.launches += 1
+        return sum(ch)
+
+
+def bench_multi(args, rank, world, local, dist):
+    """bench.py body for N > 1 (weak scaling: args.reads reads per GPU, disjoint read index ranges
+    of the same genome)."""
+    import torch
+    import mccortex_b200 as M
+    import bench as B
+
+    dev = torch.device("cuda", local)
+    SL = B.synth_lib()
+    R, stride = args.reads, B.READ_LEN + 1
+    genome = C.create_string_buffer(B.GENOME)
+    SL.mcx_synth_genome(genome, B.GENOME, 0)
+    batch_reads = min(R, 4_000_000)
+    nb = (R + batch_reads - 1) // batch_reads
+    nbytes = R * stride
+    host = M.host_alloc(nbytes + 4096)
+    SL.mcx_synth_reads(host, rank * R, R, B.READ_LEN, genome, B.GENOME, B.P_ERR, 0, 0)
+    dseq = torch.empty(nbytes + 4096, dtype=torch.uint8, device=dev)
+    dseq[:nbytes].copy_(torch.frombuffer((C.c_uint8 * nbytes).from_address(host), dtype=torch.uint8))
+    torch.cuda.synchronize()
+    M.host_free(host)
+
+    occ_per_rank = R * (B.READ_LEN - B.K + 1)
+    distinct_est = int(B.GENOME + world * R * B.READ_LEN * B.P_ERR * B.K * 1.05)
+    cap_shard = int(distinct_est / world / 0.75 * 1.05)
+    cap_part = int(batch_reads * (B.READ_LEN - B.K + 1) / world * 1.25) + 4096
+    sb = ShardedBuilder(M, dist, rank, world, dev, B.K, cap_shard, cap_part)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sb.set_stream(stream)
+
+    def step():
+        sb.g.clear()
+        for b in range(nb):
+            lo = b * batch_reads
+            n = min(batch_reads, R - lo)
+            sb.add_batch(dseq.data_ptr() + lo * stride, n * stride)
+
+    for _ in range(args.warmup):
+        step()
+    st = sb.g.sync()
+    sampler = B.ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sb.launches = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    st = sb.g.sync()
+    tot = torch.tensor([st.num_kmers_loaded, st.num_kmers_novel, sb.launches], dtype=torch.int64, device=dev)
+    dist.all_reduce(tot)
+    clocks = sampler.stop() if rank == 0 else None
+    assert int(tot[0]) == occ_per_rank * world, (int(tot[0]), occ_per_rank * world)
+    ms_total = float(ms[0])
+    value = occ_per_rank * world * args.steps / (ms_total * 1e-3)
+    peak, peak_src = B.measured_peaks()
+    if rank == 0:
+        ach = value * B.B_ALG_MULTI / 1e9 / world
+        line = {
+            "metric": "kmers_per_sec_build_k31", "value": value, "unit": "k-mers/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": B.workload_config(args, world),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "mcx_kmer_tuples + mcx_insert_tuples (per GPU)",
+                         "alg_bytes_per_kmer": B.B_ALG_MULTI},
+            "cpu_baseline": None,
+            "e2e": {"value": None, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "multi-GPU e2e (host buffers) not measured this round"},
+            "gpu_launches": int(tot[2]),
+            "clocks": clocks,
+            "extra": {"distinct_kmers_total": int(tot[1]), "shard_slots": cap_shard, "batches_per_step": nb},
+        }
+        print(json.dumps(line), flush=True)
+    sb.g.close()
+    dist.barrier()
+    dist.destroy_process_group()

@@ -1,0 +1,120 @@
+"""GPU parity tests of the drop-in command line: `mccortex-b200 build -S ...` must write the
+same bytes as the compiled reference did for the committed golden cases (tests/golden/), and
+as oracle/_ref does when it is present, on fresh seeded inputs."""
+import hashlib
+import json
+import os
+import random
+import subprocess
+
+import pytest
+
+from conftest import ROOT, rand_reads, EDGE_READS
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+CASES = json.load(open(os.path.join(GOLD, "cases.json")))
+
+
+def _driver():
+    import mccortex_b200 as M
+    assert M.device_count() > 0
+    assert os.path.exists(M.driver_path())
+    return M.driver_path()
+
+
+def _run(args, cwd=None, check=True):
+    r = subprocess.run([_driver(), "build"] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    if check:
+        assert r.returncode == 0, r.stderr.decode()[-3000:]
+    return r
+
+
+@pytest.mark.parametrize("case", [c["name"] for c in CASES])
+def test_cli_matches_golden_ctx(case, tmp_path):
+    c = next(x for x in CASES if x["name"] == case)
+    out = str(tmp_path / "out.ctx")
+    args = ["-q", "-f", "-m", "1G", "-n", "1M", "-k", str(c["k"]), "-S"]
+    args += [a if not a.endswith((".fa", ".fq")) else os.path.join(GOLD, a) for a in c["ref_args"]] + [out]
+    _run(args)
+    got = open(out, "rb").read()
+    ref = open(os.path.join(GOLD, c["ctx"]), "rb").read()
+    assert hashlib.md5(ref).hexdigest() == c["md5"]
+    assert got == ref
+
+
+def test_cli_many_tasks_header_quirks(tmp_path, oracle):
+    """13 tasks in 2 colours: batches of 10 tasks, stats credited to the first task's colour
+    (quirk Q1) and the lossy mean_read_length round trips (Q4).  Checked against the oracle,
+    which is pinned to the reference on exactly this shape (tests/test_oracle.py)."""
+    rng = random.Random(13)
+    files = []
+    for i in range(13):
+        p = tmp_path / ("t%d.fa" % i)
+        p.write_text("".join(">r\n%s\n" % r for r in rand_reads(rng, 20, (10, 120), 3000)))
+        files.append(str(p))
+    args = ["-q", "-f", "-m", "1G", "-n", "1M", "-k", "15", "-S", "-s", "c0"]
+    for f in files[:12]:
+        args += ["-1", f]
+    args += ["-s", "c1", "-1", files[12], str(tmp_path / "out.ctx")]
+    _run(args)
+    want, _ = oracle.build_ctx(15, [("c0", files[:12]), ("c1", files[12:])])
+    assert open(tmp_path / "out.ctx", "rb").read() == want
+
+
+def test_cli_gz_plain_fastq_inputs(tmp_path, oracle):
+    import gzip
+    rng = random.Random(21)
+    reads = rand_reads(rng, 300, (20, 250), 5000) + EDGE_READS
+    fa_gz = tmp_path / "a.fa.gz"
+    with gzip.open(fa_gz, "wt") as f:
+        for i, r in enumerate(reads):
+            f.write(">r%d some description\n" % i)
+            for j in range(0, len(r), 70):
+                f.write(r[j:j + 70] + "\r\n")
+    plain = tmp_path / "b.txt"
+    plain.write_text("\n".join(r for r in reads if r) + "\n")
+    fq = tmp_path / "c.fq"
+    fq.write_text("".join("@r%d\n%s\n+\n%s\n" % (i, r, "I" * len(r)) for i, r in enumerate(reads) if r))
+    out = tmp_path / "out.ctx"
+    _run(["-q", "-f", "-m", "1G", "-n", "1M", "-k", "31", "-S", "-s", "gz", "-1", str(fa_gz), "-s", "plain", "-1",
+          str(plain), "-s", "fq", "-1", str(fq), str(out)])
+    want, _ = oracle.build_ctx(31, [("gz", [str(fa_gz)]), ("plain", [str(plain)]), ("fq", [str(fq)])])
+    assert open(out, "rb").read() == want
+
+
+def test_cli_refuses_to_overwrite_and_bad_args(tmp_path):
+    fa = os.path.join(GOLD, "a.fa")
+    out = tmp_path / "o.ctx"
+    base = ["-q", "-m", "1G", "-n", "1M", "-k", "31", "-s", "x", "-1", fa, str(out)]
+    _run(base)
+    r = _run(base, check=False)
+    assert r.returncode == 1 and b"File already exists" in r.stderr   # file_util.c:164-174
+    _run(["-f"] + base)
+    assert _run(["-q", "-k", "31", "-1", fa, str(out)], check=False).returncode == 1        # sample first
+    assert _run(["-q", "-k", "30", "-s", "x", "-1", fa, str(out)], check=False).returncode == 1  # even k
+    assert _run(["-q", "-f", "-k", "31", "-s", "x", "-1", fa, "-H", "3", str(out)], check=False).returncode == 1  # trailing pref
+    r = _run(["-q", "-f", "-m", "1G", "-n", "1024", "-k", "31", "-s", "x", "-1", fa, str(out)], check=False)
+    assert r.returncode == 1 and b"Hash table is full" in r.stderr    # hash_table.c:119-123
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "mccortex31")), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("k", [31, 63])
+def test_cli_matches_reference_binary_and_check(tmp_path, oracle, k):
+    """fresh input: bytes equal to the reference binary's `build -S`; the reference's own
+    `check` (edge reciprocity, db_graph_healthcheck) accepts our file"""
+    rng = random.Random(1000 + k)
+    reads = rand_reads(rng, 2000, 150, 30000, perr=0.005)
+    fa = tmp_path / "r.fa"
+    fa.write_text("".join(">r\n%s\n" % r for r in reads))
+    mine = tmp_path / "mine.ctx"
+    _run(["-q", "-f", "-m", "1G", "-n", "4M", "-k", str(k), "-S", "-s", "s", "-1", str(fa), str(mine)])
+    ref = oracle.ref_build(k, ["-s", "s", "-1", str(fa)], str(tmp_path / "ref.ctx"), threads=4, nkmers="4M")
+    assert open(mine, "rb").read() == ref
+    r = oracle.ref_run(k, ["check", "-q", str(mine)], check=False)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    # unsorted output + reference `sort` == sorted output (tests/sort/Makefile:25-45)
+    uns = tmp_path / "uns.ctx"
+    _run(["-q", "-f", "-m", "1G", "-n", "4M", "-k", str(k), "-s", "s", "-1", str(fa), str(uns)])
+    oracle.ref_run(k, ["sort", "-q", str(uns)])
+    assert open(uns, "rb").read() == ref
