@@ -45,14 +45,19 @@ extern "C" {
  * plus the SeqLoadingPrefs it is called with (src/tools/build_graph.h:18-24), batched. */
 typedef struct {
   const char     *seq;       /* bases, ASCII; any byte outside ACGTacgt breaks contigs like the reference's LUT (src/basic/dna.c:8-25) */
-  const char     *qual;      /* NULL, or quality bytes parallel to seq (same layout) */
+  const char     *qual;      /* NULL, or quality bytes parallel to seq: byte i is the quality of base i (bytes at
+                                terminator positions are ignored).  Where a read has no / too short a quality
+                                string the caller stores 0x7F (the reference does not filter those positions,
+                                src/basic/seq_reader.c:82,149).  Only consulted when fq_cutoff != 0. */
   const uint64_t *offsets;   /* MCX_LAYOUT_OFFSETS: nreads+1 byte offsets into seq; else NULL */
   uint64_t        nreads;    /* MCX_LAYOUT_OFFSETS only (LINES: counted from the terminators) */
   uint64_t        nbytes;    /* bytes in seq (LINES: including the terminators) */
   uint32_t        layout;    /* MCX_LAYOUT_* */
   uint32_t        mem;       /* MCX_MEM_* */
   uint32_t        colour;    /* SeqLoadingPrefs.colour */
-  uint8_t         fq_cutoff; /* 0 = off; else quality threshold ALREADY including the FASTQ ASCII offset (build_graph.c:202-207) */
+  uint8_t         fq_cutoff; /* 0 = off; else quality threshold ALREADY including the FASTQ ASCII offset
+                                (build_graph.c:202-207), < 127.  A contig starts at a k-mer whose bases all have
+                                qual > cutoff and extends while qual >= cutoff (seq_reader.c:84,149). */
   uint8_t         hp_cutoff; /* 0 = off; else break contigs at homopolymer runs >= hp_cutoff (2 <= hp_cutoff <= k) */
   uint8_t         reserved[2];
 } mcx_read_batch;

@@ -157,15 +157,28 @@ class Graph:
         b = self._batch(seq_addr, nbytes, layout, mem, colour, hp_cutoff, offsets_addr, nreads, qual_addr, fq_cutoff)
         _ck(lib().mcx_graph_add_reads(self.h, C.byref(b)), "mcx_graph_add_reads")
 
-    def add_lines(self, data, colour=0, hp_cutoff=0):
-        """data: bytes in LINES layout (each read followed by one newline), host memory."""
+    def add_lines(self, data, colour=0, hp_cutoff=0, qual=None, fq_cutoff=0):
+        """data: bytes in LINES layout (each read followed by one newline), host memory.
+        qual: bytes parallel to data (0x7F where a read has no quality); fq_cutoff includes the ASCII offset."""
         buf = C.create_string_buffer(bytes(data), len(data))
-        self.add_reads_raw(C.addressof(buf), len(data), MCX_LAYOUT_LINES, MCX_MEM_HOST, colour, hp_cutoff)
+        qbuf = C.create_string_buffer(bytes(qual), len(qual)) if qual is not None else None
+        assert qbuf is None or len(qual) == len(data)
+        self.add_reads_raw(C.addressof(buf), len(data), MCX_LAYOUT_LINES, MCX_MEM_HOST, colour, hp_cutoff,
+                           qual_addr=C.addressof(qbuf) if qbuf is not None else None, fq_cutoff=fq_cutoff)
 
-    def add_reads(self, reads, colour=0, hp_cutoff=0):
-        """reads: list of bytes/str; shipped in OFFSETS layout (reads abut + offsets[n+1])."""
+    def add_reads(self, reads, colour=0, hp_cutoff=0, quals=None, fq_cutoff=0):
+        """reads: list of bytes/str; shipped in OFFSETS layout (reads abut + offsets[n+1]).
+        quals: optional list of quality strings (padded / cut to the read length here)."""
         reads = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
         blob = b"".join(reads)
+        qbuf = None
+        if quals is not None:
+            qq = []
+            for r, q in zip(reads, quals):
+                q = (q.encode("latin1") if isinstance(q, str) else bytes(q or b""))[:len(r)]
+                qq.append(q + b"\x7f" * (len(r) - len(q)))
+            qblob = b"".join(qq)
+            qbuf = C.create_string_buffer(qblob, max(len(qblob), 1))
         offs = (C.c_uint64 * (len(reads) + 1))()
         o = 0
         for i, r in enumerate(reads):
@@ -174,7 +187,8 @@ class Graph:
         offs[len(reads)] = o
         buf = C.create_string_buffer(blob, max(len(blob), 1))
         self.add_reads_raw(C.addressof(buf), len(blob), MCX_LAYOUT_OFFSETS, MCX_MEM_HOST, colour, hp_cutoff,
-                           C.addressof(offs), len(reads))
+                           C.addressof(offs), len(reads),
+                           qual_addr=C.addressof(qbuf) if qbuf is not None else None, fq_cutoff=fq_cutoff)
 
     def add_str(self, seq, colour=0):
         if isinstance(seq, str):

@@ -211,6 +211,7 @@ static McxBuildParams make_params(mcx_graph *g, const mcx_read_batch *b, const u
   p.k = g->k; p.hp_cutoff = b->hp_cutoff; p.colour = b->colour;
   p.may_saturate = g->occ_bound >= 0xF0000000ull;
   p.counters = g->d_counters;
+  p.qual = nullptr; p.qcut = 0; p.summary = nullptr;
   return p;
 }
 
@@ -269,6 +270,56 @@ static int ensure_tmp(mcx_graph *g, size_t bytes)
   return MCX_OK;
 }
 
+// Quality cut-off batches (reference: qual_cutoff > 0 in seq_contig_start2/end2).  Contig
+// membership then needs a carry across chunks, so a launch must start at a read boundary:
+// the whole batch is brought to the device (seq + qual, LINES layout) and run as ONE launch
+// pair (summary pass + insert pass).  Host batches are copied synchronously (no piece overlap
+// on this path yet).
+static int add_reads_qual(mcx_graph *g, const mcx_read_batch *b)
+{
+  if(b->nbytes == 0) return MCX_OK;
+  cudaStream_t st = primary(g);
+  const bool offsets = b->layout == MCX_LAYOUT_OFFSETS;
+  if(offsets && !b->offsets) return MCX_ERR_BAD_ARG;
+  if(!offsets && b->layout != MCX_LAYOUT_LINES) return MCX_ERR_BAD_ARG;
+  const uint64_t lines_bytes = b->nbytes + (offsets ? b->nreads : 0);
+  const size_t A = 256;
+  size_t seq_off = 0, qual_off = (lines_bytes + 16 + A - 1) / A * A, sum_off = qual_off + (lines_bytes + 16 + A - 1) / A * A;
+  size_t sum_bytes = lines_bytes / MCX_T + 4;
+  size_t raw_seq_off = (sum_off + sum_bytes + A - 1) / A * A, raw_qual_off = raw_seq_off + (b->nbytes + A - 1) / A * A;
+  size_t off_off = raw_qual_off + (b->nbytes + A - 1) / A * A;
+  size_t need = off_off + (offsets ? (size_t)(b->nreads + 1) * 8 : 0) + A;
+  bool direct = !offsets && b->mem == MCX_MEM_DEVICE && (((uintptr_t)b->seq | (uintptr_t)b->qual) & 15u) == 0;
+  int r = ensure_tmp(g, direct ? sum_off + sum_bytes + A : need); if(r) return r;
+  const uint8_t *dseq, *dqual;
+  if(direct) { dseq = (const uint8_t *)b->seq; dqual = (const uint8_t *)b->qual; }
+  else if(!offsets) {
+    cudaMemcpyKind kind = b->mem == MCX_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    CU(cudaMemcpyAsync(g->d_tmp + seq_off, b->seq, b->nbytes, kind, st));
+    CU(cudaMemcpyAsync(g->d_tmp + qual_off, b->qual, b->nbytes, kind, st));
+    dseq = g->d_tmp + seq_off; dqual = g->d_tmp + qual_off;
+  } else {
+    cudaMemcpyKind kind = b->mem == MCX_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const uint8_t *rs = (const uint8_t *)b->seq, *rq = (const uint8_t *)b->qual;
+    if(b->mem == MCX_MEM_HOST) {
+      CU(cudaMemcpyAsync(g->d_tmp + raw_seq_off, b->seq, b->nbytes, kind, st));
+      CU(cudaMemcpyAsync(g->d_tmp + raw_qual_off, b->qual, b->nbytes, kind, st));
+      rs = g->d_tmp + raw_seq_off; rq = g->d_tmp + raw_qual_off;
+    }
+    CU(cudaMemcpyAsync(g->d_tmp + off_off, b->offsets, (size_t)(b->nreads + 1) * 8, kind, st));
+    CU(mcx_launch_repack_lines(rs, (const uint64_t *)(g->d_tmp + off_off), b->nreads, g->d_tmp + seq_off, st));
+    CU(mcx_launch_repack_lines(rq, (const uint64_t *)(g->d_tmp + off_off), b->nreads, g->d_tmp + qual_off, st));
+    dseq = g->d_tmp + seq_off; dqual = g->d_tmp + qual_off;
+  }
+  g->occ_bound += lines_bytes;
+  McxBuildParams p = make_params(g, b, dseq, lines_bytes, 0, lines_bytes);
+  p.qual = dqual; p.qcut = b->fq_cutoff; p.summary = g->d_tmp + sum_off;
+  CU(mcx_launch_build_fused_qual(p, g->table, st));
+  g->pend_positions += lines_bytes;
+  CU(cudaStreamSynchronize(st)); // d_tmp (and pageable host sources) are reused by the next batch
+  return MCX_OK;
+}
+
 extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
 {
   if(!g || !b || b->colour >= g->ncols) return MCX_ERR_BAD_ARG;
@@ -276,11 +327,10 @@ extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
   if(b->hp_cutoff == 1 || b->hp_cutoff > g->k) {
     snprintf(g_err, sizeof(g_err), "hp_cutoff must be 0 or in [2, k]"); return MCX_ERR_UNSUPPORTED;
   }
-  if(b->fq_cutoff && b->qual) {
-    snprintf(g_err, sizeof(g_err), "quality cut-off path not built yet"); return MCX_ERR_UNSUPPORTED;
-  }
+  if(b->fq_cutoff >= 127) { snprintf(g_err, sizeof(g_err), "fq_cutoff (incl. offset) must be < 127"); return MCX_ERR_UNSUPPORTED; }
   CU(cudaSetDevice(g->device));
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
+  if(b->fq_cutoff && b->qual) return add_reads_qual(g, b);
 
   if(b->layout == MCX_LAYOUT_LINES) {
     if(b->nbytes == 0) return MCX_OK;

@@ -32,13 +32,22 @@
 
 struct __align__(128) McxChunkSmem {
   uint8_t raw[2][MCX_RAW];
+  uint8_t qraw[2][MCX_RAW];  // quality bytes of the same positions (quality modes only)
   uint32_t pk[MCX_PKW];
-  uint32_t bad[MCX_MSW];
+  uint32_t bad[MCX_MSW];     // base cannot be in a window that EXTENDS a contig
+  uint32_t bads[MCX_MSW];    // base cannot be in a window that STARTS a contig (quality modes)
   uint32_t eq[MCX_MSW];
-  uint32_t vmask[MCX_VW];
+  uint32_t vmask[MCX_VW];    // in_contig per window
+  uint32_t svm[MCX_VW];      // start-valid windows (quality modes)
+  uint32_t carry_in;
   unsigned long long bar[2];
   unsigned long long red[MCX_NCOUNTERS];
 };
+
+// front-end modes
+enum { MCX_MODE_PLAIN = 0,   // contig rules are window-local (no quality cut-off)
+       MCX_MODE_QUAL = 1,    // quality cut-off: in_contig needs the carry chain + chunk carry-in
+       MCX_MODE_QSUM = 2 };  // quality cut-off, pass 1: only the per-chunk carry summary
 
 // ---------------------------------------------------------------- TMA / mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -75,8 +84,21 @@ __device__ __forceinline__ void issue_chunk_load(McxChunkSmem &sm, const McxBuil
   uint64_t avail = (p.nbytes - src_off + 15ull) & ~15ull; // p.seq is readable up to nbytes rounded up to 16
   uint32_t want = MCX_RAW - dst_off;
   uint32_t bytes = avail < want ? (uint32_t)avail : want;
-  mbar_expect_tx(&sm.bar[buf], bytes);
+  mbar_expect_tx(&sm.bar[buf], p.qual ? 2u * bytes : bytes);
   tma_load_1d(&sm.raw[buf][dst_off], p.seq + src_off, bytes, &sm.bar[buf]);
+  if(p.qual) tma_load_1d(&sm.qraw[buf][dst_off], p.qual + src_off, bytes, &sm.bar[buf]);
+}
+
+// in_contig of the window just before `chunk`: walk back over the per-chunk summaries
+// (bit0 = carry-out if carry-in is 0, bit1 = if it is 1) until one does not depend on its input
+__device__ __forceinline__ uint32_t chunk_carry_in(const uint8_t *summary, uint64_t chunk, uint64_t c_first)
+{
+  while(chunk > c_first) {
+    uint32_t s = summary[--chunk - c_first];
+    if(s == 0u) return 0u;
+    if(s == 3u) return 1u;
+  }
+  return 0u; // launches start at a read boundary
 }
 
 // ---------------------------------------------------------------- sinks
@@ -114,7 +136,7 @@ template <int W> struct TupleSink {
 };
 
 // ---------------------------------------------------------------- front end
-template <int W, class Sink>
+template <int W, int MODE, class Sink>
 __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sink)
 {
   __shared__ McxChunkSmem sm;
@@ -150,10 +172,18 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
       uint32_t pk, b16, e16, n16;
       mcx_convert16(w, prev, gpos, p.nbytes, &pk, &b16, &e16, &n16);
       sm.pk[tid] = pk;
+      if(MODE != MCX_MODE_PLAIN) {
+        const uint4 qv = *reinterpret_cast<const uint4 *>(&sm.qraw[buf][tid * 16u]);
+        const uint32_t q[4] = {qv.x, qv.y, qv.z, qv.w};
+        uint32_t wk16, st16;
+        mcx_qual16(q, p.qcut, &wk16, &st16);
+        reinterpret_cast<uint16_t *>(sm.bads)[tid] = (uint16_t)(b16 | st16);
+        b16 |= wk16;
+      }
       reinterpret_cast<uint16_t *>(sm.bad)[tid] = (uint16_t)b16;
       reinterpret_cast<uint16_t *>(sm.eq)[tid] = (uint16_t)e16;
       // read terminators owned by this launch and this chunk
-      if(n16 && tid >= MCX_LB / 16u && tid < (MCX_LB + MCX_T) / 16u) {
+      if(MODE != MCX_MODE_QSUM && n16 && tid >= MCX_LB / 16u && tid < (MCX_LB + MCX_T) / 16u) {
         for(uint32_t i = 0; i < 16u; i++)
           if(((n16 >> i) & 1u) && gpos + i >= p.r_begin && gpos + i < p.r_end) n_reads++;
       }
@@ -162,17 +192,48 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
     // raw[buf^1] was last read in phase 1 of the previous iteration: safe to refill
     if(tid == 0 && chunk + gridDim.x < c_last) issue_chunk_load(sm, p, chunk + gridDim.x, buf ^ 1u);
 
-    // ---- phase 2a: contig rules -> valid-window bit mask for windows cs-1 .. cs+T
+    // ---- phase 2a: contig rules -> in_contig bit mask for windows cs-1 .. cs+T
     for(uint32_t i = tid; i < MCX_VW * 32u; i += MCX_THREADS) {
       bool ok = (i < MCX_T + 2u) && mcx_chunk_window_ok(sm.bad, sm.eq, i, p.k, p.hp_cutoff);
       uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
       if(lane == 0) sm.vmask[i >> 5] = m;
+      if(MODE != MCX_MODE_PLAIN) {
+        bool sok = ok && mcx_chunk_window_ok(sm.bads, sm.eq, i, p.k, p.hp_cutoff);
+        uint32_t ms = __ballot_sync(0xFFFFFFFFu, sok);
+        if(lane == 0) sm.svm[i >> 5] = ms;
+      }
     }
+    if(MODE == MCX_MODE_QUAL && tid == 32) sm.carry_in = chunk_carry_in(p.summary, chunk, c_first);
     __syncthreads();
+    if(MODE != MCX_MODE_PLAIN) {
+      // vmask holds ev, svm holds sv: resolve in_contig = ev & (sv | in_contig(prev)) (one thread,
+      // ~66 adds).  Bit 0 is the window before the chunk: its value IS the carry-in.
+      if(tid == 0) {
+        if(MODE == MCX_MODE_QUAL) {
+          uint32_t cin = sm.carry_in;
+          sm.vmask[0] = (sm.vmask[0] & ~1u) | cin; sm.svm[0] = (sm.svm[0] & ~1u) | cin;
+          mcx_contig_chain(sm.vmask, sm.svm, MCX_VW, 0u, sm.vmask);
+        } else {
+          // summary of this chunk's own windows (bits 1..T): carry-out for carry-in 0 and 1
+          uint32_t ev0 = sm.vmask[0], sv0 = sm.svm[0], out = 0;
+          for(uint32_t cin = 0; cin < 2u; cin++) {
+            sm.vmask[0] = (ev0 & ~1u) | cin; sm.svm[0] = (sv0 & ~1u) | cin;
+            uint32_t last = 0;
+            // in_contig of bit T: run the chain over the words that cover bits 0..T
+            uint32_t x[MCX_VW];
+            mcx_contig_chain(sm.vmask, sm.svm, MCX_VW, 0u, x);
+            last = mcx_get_bit(x, MCX_T);
+            out |= last << cin;
+          }
+          p.summary[chunk - c_first] = (uint8_t)out;
+        }
+      }
+      __syncthreads();
+    }
 
     // ---- phase 2b: one window per thread per round
 #pragma unroll 1
-    for(uint32_t j = 0; j < MCX_T / MCX_THREADS; j++) {
+    for(uint32_t j = 0; MODE != MCX_MODE_QSUM && j < MCX_T / MCX_THREADS; j++) {
       const uint32_t i = 1u + j * MCX_THREADS + tid;
       const uint64_t g = cs + (i - 1u);
       if(mcx_get_bit(sm.vmask, i) && g >= p.r_begin && g < p.r_end) {
@@ -211,14 +272,28 @@ template <int W, int MINB>
 __global__ void __launch_bounds__(MCX_THREADS, MINB) mcx_build_fused_kernel(McxBuildParams p, McxTable t)
 {
   FusedSink<W> sink{t, p.colour, p.may_saturate != 0};
-  mcx_front_end<W>(p, sink);
+  mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
+}
+
+// quality cut-off variants: pass 1 writes the per-chunk carry summaries, pass 2 inserts
+struct NullSink { template <class O> __device__ __forceinline__ void operator()(const O &, uint64_t &, uint32_t &) {} };
+__global__ void __launch_bounds__(MCX_THREADS, 4) mcx_contig_summary_kernel(McxBuildParams p)
+{
+  NullSink sink;
+  mcx_front_end<1, MCX_MODE_QSUM>(p, sink);
+}
+template <int W>
+__global__ void __launch_bounds__(MCX_THREADS, 4) mcx_build_fused_qual_kernel(McxBuildParams p, McxTable t)
+{
+  FusedSink<W> sink{t, p.colour, p.may_saturate != 0};
+  mcx_front_end<W, MCX_MODE_QUAL>(p, sink);
 }
 
 template <int W>
 __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_kmer_tuples_kernel(McxBuildParams p, McxTupleBins b)
 {
   TupleSink<W> sink{b};
-  mcx_front_end<W>(p, sink);
+  mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
 
 // ---------------------------------------------------------------- kernel C
@@ -350,6 +425,17 @@ cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, c
       default: mcx_build_fused_kernel<1, 4><<<grid, MCX_THREADS, 0, st>>>(p, t); break;
     }
   } else mcx_build_fused_kernel<2, 4><<<grid, MCX_THREADS, 0, st>>>(p, t);
+  return cudaGetLastError();
+}
+
+// quality cut-off: p.qual / p.qcut / p.summary set; the launch must start at a read boundary
+cudaError_t mcx_launch_build_fused_qual(const McxBuildParams &p, const McxTable &t, cudaStream_t st)
+{
+  if(p.r_end <= p.r_begin) return cudaSuccess;
+  unsigned grid = grid_for_chunks(p, 4);
+  mcx_contig_summary_kernel<<<grid, MCX_THREADS, 0, st>>>(p);
+  if(p.k <= 31) mcx_build_fused_qual_kernel<1><<<grid, MCX_THREADS, 0, st>>>(p, t);
+  else mcx_build_fused_qual_kernel<2><<<grid, MCX_THREADS, 0, st>>>(p, t);
   return cudaGetLastError();
 }
 

@@ -25,6 +25,10 @@ struct McxBuildParams {
   uint32_t colour;
   int may_saturate;
   unsigned long long *counters; // MCX_NCOUNTERS u64, device
+  // quality cut-off (all NULL/0 when off)
+  const uint8_t *qual;  // quality bytes parallel to seq (same layout; terminator bytes ignored)
+  uint32_t qcut;        // cut-off including the FASTQ ASCII offset
+  uint8_t *summary;     // one byte per chunk of [r_begin, r_end): carry summaries (pass 1 -> pass 2)
 };
 
 struct McxTupleBins {
@@ -36,6 +40,7 @@ struct McxTupleBins {
 };
 
 cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
+cudaError_t mcx_launch_build_fused_qual(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
 cudaError_t mcx_launch_kmer_tuples(const McxBuildParams &p, const McxTupleBins &b, cudaStream_t st);
 cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint8_t *masks, uint64_t n, uint32_t k, const McxTable &t,
                                      uint32_t colour, int may_saturate, unsigned long long *counters, cudaStream_t st);

@@ -46,6 +46,41 @@ MCX_HD void mcx_convert16(const uint32_t w[4], uint32_t prev, uint64_t gpos, uin
   *pk = p; *bad16 = b; *eq16 = e; *nl16 = n;
 }
 
+// Quality bits of one 16-byte item (reference: seq_contig_start2 requires qual > cutoff for every
+// base of the FIRST k-mer of a contig, seq_contig_end2 extends while qual >= cutoff:
+// src/basic/seq_reader.c:84,149; `char` quality vs uint8_t cutoff compare after integer
+// promotion, so bytes >= 0x80 are negative and fail).  Bit i of *weak16: byte i < cutoff
+// (cannot extend a contig); bit i of *strong16: byte i <= cutoff (cannot start one).
+MCX_HD void mcx_qual16(const uint32_t q[4], uint32_t qcut, uint32_t *weak16, uint32_t *strong16)
+{
+  uint32_t wk = 0, st = 0;
+  for(uint32_t i = 0; i < 16u; i++) {
+    int v = (int)(signed char)((q[i >> 2] >> (8u * (i & 3u))) & 0xFFu);
+    wk |= (uint32_t)(v < (int)qcut) << i;
+    st |= (uint32_t)(v <= (int)qcut) << i;
+  }
+  *weak16 = wk; *strong16 = st;
+}
+
+// Contig membership with a quality cut-off is not a local predicate:
+//   in_contig(p) = ev(p) && (sv(p) || in_contig(p-1))
+// ev = window may EXTEND a contig (all bases ACGT, qual >= cutoff, no homopolymer run),
+// sv = window may START one (qual > cutoff instead).  g = ev&sv generates, ev&~sv propagates:
+// this is the carry chain of the addition ev + (ev&sv), so one 32-bit add resolves 32 windows.
+// ev/sv/x: bit strings of nwords u32; cin = in_contig of the window before bit 0.
+// Writes x (may be NULL) and returns in_contig of the last bit.
+MCX_HD uint32_t mcx_contig_chain(const uint32_t *ev, const uint32_t *sv, uint32_t nwords, uint32_t cin, uint32_t *x)
+{
+  for(uint32_t w = 0; w < nwords; w++) {
+    uint32_t a = ev[w], b = ev[w] & sv[w];
+    uint64_t sum = (uint64_t)a + b + cin;
+    uint32_t into = (uint32_t)sum ^ a ^ b;      // carry INTO each bit
+    cin = (uint32_t)(sum >> 32) & 1u;           // carry out of bit 31
+    if(x) x[w] = (into >> 1) | (cin << 31);     // carry OUT of each bit = in_contig
+  }
+  return cin;
+}
+
 // Phase 2a: is the window with local index i (buffer start = chunk_start - 1 + i) loadable?
 MCX_HD bool mcx_chunk_window_ok(const uint32_t *bad, const uint32_t *eq, uint32_t i, uint32_t k, uint32_t hp_cutoff)
 {

@@ -108,20 +108,49 @@ static inline bool is_space(int c) { return c == ' ' || (c >= '\t' && c <= '\r')
 typedef struct {
   mcx_graph *g; const McxLoadPrefs *prefs; mcx_load_stats *stats;
   Buf lines;          /* LINES batch under construction */
+  Buf qlines;         /* quality bytes parallel to `lines` (only when a quality cut-off is set) */
   Buf qual;           /* quality string of the current FASTQ record */
   uint64_t nreads_total;
   /* FASTQ offset auto-detection (seq_file.h:636-682): min/max of the first <= 1000 quals */
   int qmin, qmax; size_t qcount, bcount; bool saw_qual;
+  bool any_qual, offset_known; uint8_t fq_offset;
   int err;
 } Loader;
 
+/* FASTQ ASCII offset from the quality range of the first reads, exactly the decision list of
+ * seq_guess_fastq_format (libs/seq_file/seq_file.h:666-682) + FASTQ_OFFSET (:127) */
+static uint8_t guess_fq_offset(const Loader *L)
+{
+  static const int OFFS[6] = {33, 33, 64, 64, 64, 33};
+  int fmt, mn = L->qmin, mx = L->qmax;
+  if(L->qcount == 0) return 0; /* no qualities seen: offset stays 0 (seq_reader.c:436-441) */
+  if(mn >= 33 && mx <= 73) fmt = 1;
+  else if(mn >= 33 && mx <= 75) fmt = 5;
+  else if(mn >= 67 && mx <= 105) fmt = 4;
+  else if(mn >= 64 && mx <= 105) fmt = 3;
+  else if(mn >= 59 && mx <= 105) fmt = 2;
+  else fmt = 0;
+  return (uint8_t)OFFS[fmt];
+}
+
 static void flush_batch(Loader *L)
 {
-  if(L->lines.len == 0 || L->err) { L->lines.len = 0; return; }
+  if(L->lines.len == 0 || L->err) { L->lines.len = 0; L->qlines.len = 0; return; }
   mcx_read_batch b; memset(&b, 0, sizeof(b));
   b.seq = L->lines.b; b.nbytes = L->lines.len;
   b.layout = MCX_LAYOUT_LINES; b.mem = MCX_MEM_HOST;
   b.colour = L->prefs->colour; b.hp_cutoff = L->prefs->hp_cutoff;
+  if(L->prefs->fq_cutoff && L->any_qual) {
+    /* build_graph.c:202-207: the ASCII offset is added only when a cut-off is set */
+    if(!L->offset_known) {
+      L->fq_offset = L->prefs->fq_offset ? L->prefs->fq_offset : guess_fq_offset(L);
+      L->offset_known = true;
+      if(L->fq_offset + L->prefs->fq_cutoff >= 127) { L->err = MCX_ERR_UNSUPPORTED; L->lines.len = L->qlines.len = 0; return; }
+    }
+    b.qual = L->qlines.b;
+    b.fq_cutoff = (uint8_t)(L->prefs->fq_cutoff + L->fq_offset);
+  }
+  L->qlines.len = 0;
   int r = mcx_graph_add_reads(L->g, &b);
   if(r != MCX_OK) L->err = r;
   L->lines.len = 0;
@@ -140,6 +169,15 @@ static void end_read(Loader *L, size_t start)
     }
     L->bcount += seqlen; L->qcount += L->qual.len; L->saw_qual = true;
   } else if(L->bcount < 1000) L->bcount += seqlen;
+  if(L->prefs->fq_cutoff) {
+    /* quality bytes parallel to the sequence; 0x7F where the read has none (not filtered there) */
+    size_t have = L->qual.len < seqlen ? L->qual.len : seqlen;
+    buf_reserve(&L->qlines, seqlen + 1);
+    memcpy(L->qlines.b + L->qlines.len, L->qual.b, have);
+    memset(L->qlines.b + L->qlines.len + have, 0x7F, seqlen - have + 1);
+    L->qlines.len += seqlen + 1;
+    if(L->qual.len) L->any_qual = true;
+  }
   buf_push(&L->lines, '\n');
   L->nreads_total++;
   if(L->lines.len >= MCX_BATCH_BYTES) flush_batch(L);
@@ -193,10 +231,6 @@ static int read_fastq(McxSeqFile *sf, Loader *L)
   } while(L->qual.len < seqlen);
   if(!eof_in_qual) {
     while((c = speek(sf)) != -1 && c != '@') sf->in_pos++;
-  }
-  if(L->prefs->fq_cutoff && L->qual.len) {
-    L->err = MCX_ERR_UNSUPPORTED; /* quality cut-off kernel path is not built yet */
-    return -1;
   }
   end_read(L, start);
   return 1;
@@ -252,6 +286,6 @@ int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, m
 
   char n1[64]; mcx_ulong_to_str(L.nreads_total, n1);
   mcx_status("[seq] Loaded %s reads and 0 reads pairs (file: %s)", n1, sf->path);
-  free(L.lines.b); free(L.qual.b);
+  free(L.lines.b); free(L.qual.b); free(L.qlines.b);
   return r;
 }

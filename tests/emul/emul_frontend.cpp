@@ -7,9 +7,12 @@
 // It exists because the build container has no GPU; it is never linked into
 // libmcxgpu.so and the product never calls it.
 //
-// usage: emul_frontend <lines-file> <k> <hp_cutoff> <r_piece>   -> stdout: records
+// usage: emul_frontend <lines-file> <k> <hp_cutoff> <r_piece> [<qual-lines-file> <qcut>]  -> stdout: records
 //        r_piece: positions per simulated launch (0 = one launch), to exercise the
 //        host-staging cut logic of mcx_abi.cu (look-back 16 / look-ahead 80).
+//        qual-lines-file: quality bytes parallel to the lines file (quality cut-off mode:
+//        two passes per launch like mcx_launch_build_fused_qual; launches must start at read
+//        boundaries, so r_piece must be 0).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,11 +28,13 @@ struct Counters { uint64_t kmers = 0, novel = 0, contigs = 0, reads = 0; };
 
 template <int W>
 static void run_launch(const uint8_t *seq, uint64_t nbytes, uint64_t r_begin, uint64_t r_end, uint32_t k, uint32_t hp,
-                       Table &tab, Counters &cnt)
+                       Table &tab, Counters &cnt, const uint8_t *qual = nullptr, uint32_t qcut = 0)
 {
-  std::vector<uint8_t> raw(MCX_RAW);
-  std::vector<uint32_t> pk(MCX_PKW), bad(MCX_MSW), eq(MCX_MSW), vmask(MCX_VW);
+  std::vector<uint8_t> raw(MCX_RAW), qraw(MCX_RAW);
+  std::vector<uint32_t> pk(MCX_PKW), bad(MCX_MSW), bads(MCX_MSW), eq(MCX_MSW), vmask(MCX_VW), svm(MCX_VW);
   uint64_t c_first = r_begin / MCX_T, c_last = (r_end + MCX_T - 1) / MCX_T;
+  std::vector<uint8_t> summary(c_last - c_first + 1);
+  for(int pass = qual ? 0 : 1; pass < 2; pass++)   // pass 0 = summary kernel (quality mode only)
   for(uint64_t chunk = c_first; chunk < c_last; chunk++) {
     uint64_t cs = chunk * (uint64_t)MCX_T;
     // staging (issue_chunk_load): bytes outside the copied range hold garbage
@@ -38,6 +43,7 @@ static void run_launch(const uint8_t *seq, uint64_t nbytes, uint64_t r_begin, ui
     uint64_t avail = (nbytes - src_off + 15ull) & ~15ull; uint32_t want = MCX_RAW - dst_off;
     uint32_t bytes = avail < want ? (uint32_t)avail : want;
     for(uint32_t i = 0; i < bytes; i++) raw[dst_off + i] = (src_off + i < nbytes) ? seq[src_off + i] : 0xEE;
+    if(qual) { memset(qraw.data(), 0x11, MCX_RAW); for(uint32_t i = 0; i < bytes; i++) qraw[dst_off + i] = (src_off + i < nbytes) ? qual[src_off + i] : 0x22; }
     for(uint32_t t = 0; t < 4; t++) { pk[MCX_RAW / 16u + t] = 0; bad[MCX_RAW / 32u + t] = 0xFFFFFFFFu; eq[MCX_RAW / 32u + t] = 0; }
     // phase 1
     for(uint32_t tid = 0; tid < MCX_RAW / 16u; tid++) {
@@ -47,17 +53,41 @@ static void run_launch(const uint8_t *seq, uint64_t nbytes, uint64_t r_begin, ui
       uint32_t p, b16, e16, n16;
       mcx_convert16(w, prev, gpos, nbytes, &p, &b16, &e16, &n16);
       pk[tid] = p;
+      if(qual) {
+        uint32_t q[4]; memcpy(q, &qraw[tid * 16u], 16);
+        uint32_t wk16, st16; mcx_qual16(q, qcut, &wk16, &st16);
+        ((uint16_t *)bads.data())[tid] = (uint16_t)(b16 | st16);
+        b16 |= wk16;
+      }
       ((uint16_t *)bad.data())[tid] = (uint16_t)b16;
       ((uint16_t *)eq.data())[tid] = (uint16_t)e16;
-      if(n16 && tid >= MCX_LB / 16u && tid < (MCX_LB + MCX_T) / 16u)
+      if(pass == 1 && n16 && tid >= MCX_LB / 16u && tid < (MCX_LB + MCX_T) / 16u)
         for(uint32_t i = 0; i < 16u; i++)
           if(((n16 >> i) & 1u) && gpos + i >= r_begin && gpos + i < r_end) cnt.reads++;
     }
     // phase 2a
     for(uint32_t i = 0; i < MCX_VW * 32u; i++) {
       bool ok = (i < MCX_T + 2u) && mcx_chunk_window_ok(bad.data(), eq.data(), i, k, hp);
-      if((i & 31u) == 0) vmask[i >> 5] = 0;
+      if((i & 31u) == 0) { vmask[i >> 5] = 0; svm[i >> 5] = 0; }
       if(ok) vmask[i >> 5] |= 1u << (i & 31u);
+      if(qual && ok && mcx_chunk_window_ok(bads.data(), eq.data(), i, k, hp)) svm[i >> 5] |= 1u << (i & 31u);
+    }
+    if(qual && pass == 0) {
+      uint32_t ev0 = vmask[0], sv0 = svm[0], out = 0;
+      for(uint32_t cin = 0; cin < 2u; cin++) {
+        vmask[0] = (ev0 & ~1u) | cin; svm[0] = (sv0 & ~1u) | cin;
+        std::vector<uint32_t> x(MCX_VW);
+        mcx_contig_chain(vmask.data(), svm.data(), MCX_VW, 0u, x.data());
+        out |= mcx_get_bit(x.data(), MCX_T) << cin;
+      }
+      summary[chunk - c_first] = (uint8_t)out;
+      continue;
+    }
+    if(qual) {
+      uint32_t cin = 0; uint64_t j = chunk;
+      while(j > c_first) { uint32_t sm = summary[--j - c_first]; if(sm == 0u) { cin = 0; break; } if(sm == 3u) { cin = 1; break; } }
+      vmask[0] = (vmask[0] & ~1u) | cin; svm[0] = (svm[0] & ~1u) | cin;
+      mcx_contig_chain(vmask.data(), svm.data(), MCX_VW, 0u, vmask.data());
     }
     // phase 2b
     for(uint32_t i = 1; i <= MCX_T; i++) {
@@ -84,14 +114,23 @@ int main(int argc, char **argv)
   fclose(f);
   uint32_t k = (uint32_t)atoi(argv[2]), hp = (uint32_t)atoi(argv[3]);
   uint64_t piece = strtoull(argv[4], NULL, 10), nbytes = data.size();
+  std::vector<uint8_t> qdata; uint32_t qcut = 0;
+  if(argc >= 7) {
+    FILE *qf = fopen(argv[5], "rb"); if(!qf) { perror(argv[5]); return 2; }
+    while((n = fread(buf, 1, sizeof(buf), qf)) > 0) qdata.insert(qdata.end(), buf, buf + n);
+    fclose(qf);
+    qcut = (uint32_t)atoi(argv[6]);
+    if(qdata.size() != data.size() || piece != 0) { fprintf(stderr, "qual file must parallel the lines file; r_piece must be 0\n"); return 2; }
+  }
+  const uint8_t *qp = qdata.empty() ? nullptr : qdata.data();
   if(piece == 0) piece = nbytes ? nbytes : 1;
   Table tab; Counters cnt;
   for(uint64_t pos = 0; pos < nbytes; pos += piece) {
     uint64_t pend = pos + piece < nbytes ? pos + piece : nbytes;
     uint64_t b0 = pos ? pos - MCX_LB : 0, b1 = pend + MCX_TAIL < nbytes ? pend + MCX_TAIL : nbytes;
     if(b0 % 16) { fprintf(stderr, "piece must be a multiple of 16\n"); return 2; }
-    if(k <= 31) run_launch<1>(data.data() + b0, b1 - b0, pos - b0, pend - b0, k, hp, tab, cnt);
-    else run_launch<2>(data.data() + b0, b1 - b0, pos - b0, pend - b0, k, hp, tab, cnt);
+    if(k <= 31) run_launch<1>(data.data() + b0, b1 - b0, pos - b0, pend - b0, k, hp, tab, cnt, qp ? qp + b0 : nullptr, qcut);
+    else run_launch<2>(data.data() + b0, b1 - b0, pos - b0, pend - b0, k, hp, tab, cnt, qp ? qp + b0 : nullptr, qcut);
   }
   int W = k <= 31 ? 1 : 2;
   for(auto &kv : tab) {

@@ -195,3 +195,70 @@ def test_tuple_path_matches_fused_path(M, oracle, reads_small):
     got, _, _ = g.export_records()
     assert got == recs
     g.close()
+
+
+def _rand_quals(rng, reads, cut, eqp, lo=35, hi=74):
+    quals = ["".join(chr(cut) if rng.random() < eqp else chr(rng.randint(lo, hi)) for _ in r) for r in reads]
+    for i in range(0, len(reads), 7):
+        quals[i] = quals[i][:len(quals[i]) // 2]      # short quality string
+    for i in range(3, len(reads), 11):
+        quals[i] = ""                                # no quality
+    return quals
+
+
+@pytest.mark.parametrize("k,hp,cut,eqp", [(21, 0, 43, 0.05), (31, 0, 50, 0.3), (31, 4, 43, 0.9), (63, 5, 60, 0.5), (11, 0, 43, 0.0)])
+def test_quality_cutoff_matches_oracle(M, oracle, k, hp, cut, eqp):
+    """--fq-cutoff: a contig starts where all k quals are > cutoff and extends while >= cutoff
+    (seq_reader.c:84,149); many bases exactly at the cut-off stress the asymmetry"""
+    rng = random.Random(k * 100 + cut)
+    reads = rand_reads(rng, 400, (1, 500), 6000, perr=0.01, pN=0.005)
+    quals = _rand_quals(rng, reads, cut, eqp)
+    og = oracle.Graph(k, 1, 1 << 21)
+    ost = oracle.Stats()
+    for r, q in zip(reads, quals):
+        og.add_read(r, qual=q.encode("latin1") if q else None, fq_cutoff=cut, fq_offset=0, hp_cutoff=hp, stats=ost)
+    recs = og.dump_sorted()[len(og.header()):]
+    for layout in ("offsets", "lines"):
+        g = M.Graph(k, 1, 1 << 20)
+        if layout == "offsets":
+            g.add_reads(reads, hp_cutoff=hp, quals=quals, fq_cutoff=cut)
+        else:
+            blob = "".join(r + "\n" for r in reads).encode()
+            qb = b"".join((q.encode("latin1")[:len(r)] + b"\x7f" * (len(r) - min(len(r), len(q))) + b"!") for r, q in zip(reads, quals))
+            g.add_lines(blob, hp_cutoff=hp, qual=qb, fq_cutoff=cut)
+        st = g.sync()
+        got, _, _ = g.export_records()
+        assert got == recs, layout
+        assert st.num_kmers_loaded == ost.num_kmers_loaded and st.contigs_parsed == ost.contigs_parsed
+        assert st.total_bases_loaded == ost.total_bases_loaded
+        g.close()
+
+
+def test_quality_carry_across_chunks(M, oracle):
+    """long reads whose bases sit exactly AT the cut-off: in_contig is carried over many 2 KB chunks"""
+    rng = random.Random(99)
+    long_reads = rand_reads(rng, 4, 12000, 20000, perr=0, pN=0.0003, lower=0)
+    for mode in range(3):
+        quals = []
+        for r in long_reads:
+            q = [chr(50)] * len(r)
+            for _ in range(3 if mode else 0):
+                s = rng.randrange(0, len(r) - 80)
+                for j in range(s, s + 70):
+                    q[j] = chr(60)
+            if mode == 2:
+                for _ in range(5):
+                    q[rng.randrange(len(r))] = chr(40)
+            quals.append("".join(q))
+        og = oracle.Graph(31, 1, 1 << 20)
+        ost = oracle.Stats()
+        for r, q in zip(long_reads, quals):
+            og.add_read(r, qual=q.encode("latin1"), fq_cutoff=50, stats=ost)
+        recs = og.dump_sorted()[len(og.header()):]
+        g = M.Graph(31, 1, 1 << 20)
+        g.add_reads(long_reads, quals=quals, fq_cutoff=50)
+        st = g.sync()
+        got, _, _ = g.export_records()
+        assert got == recs
+        assert st.num_kmers_loaded == ost.num_kmers_loaded and st.contigs_parsed == ost.contigs_parsed
+        g.close()

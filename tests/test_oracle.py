@@ -122,3 +122,38 @@ def test_device_math_staging_cuts(oracle, emul, tmp_path, reads_small, piece):
         got, cnt = _emul(emul, tmp_path, reads_small, k, hp=hp, piece=piece)
         assert got == recs
         assert cnt["kmers"] == st.num_kmers_loaded and cnt["reads"] == len(reads_small)
+
+
+def _emul_q(emul, tmp_path, reads, quals, k, qcut, hp=0):
+    p = tmp_path / "lines.txt"
+    q = tmp_path / "qual.txt"
+    p.write_text("".join(r + "\n" for r in reads))
+    with open(q, "wb") as f:
+        for r, s in zip(reads, quals):
+            b = s.encode("latin1")[:len(r)]
+            f.write(b + b"\x7f" * (len(r) - len(b)) + b"!")
+    r = subprocess.run([emul, str(p), str(k), str(hp), "0", str(q), str(qcut)], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, check=True)
+    cnt = dict(x.split("=") for x in r.stderr.decode().split())
+    return r.stdout, {a: int(b) for a, b in cnt.items()}
+
+
+@pytest.mark.parametrize("k,hp,cut,eqp", [(21, 0, 43, 0.05), (31, 0, 50, 0.3), (31, 4, 43, 0.9), (63, 5, 60, 0.5)])
+def test_device_math_quality_cutoff(oracle, emul, tmp_path, k, hp, cut, eqp):
+    """start (qual > cutoff) / extend (qual >= cutoff) asymmetry via the carry chain + chunk summaries"""
+    rng = random.Random(k * 100 + cut)
+    reads = rand_reads(rng, 300, (1, 500), 6000, perr=0.01, pN=0.005)
+    reads += rand_reads(rng, 2, 9000, 12000, perr=0, pN=0.0003, lower=0)   # carries across chunks
+    quals = ["".join(chr(cut) if rng.random() < eqp else chr(rng.randint(35, 74)) for _ in r) for r in reads]
+    for i in range(0, len(reads), 7):
+        quals[i] = quals[i][:len(quals[i]) // 2]
+    for i in range(3, len(reads), 11):
+        quals[i] = ""
+    g = oracle.Graph(k, 1, 1 << 21)
+    st = oracle.Stats()
+    for r, q in zip(reads, quals):
+        g.add_read(r, qual=q.encode("latin1") if q else None, fq_cutoff=cut, hp_cutoff=hp, stats=st)
+    recs = g.dump_sorted()[len(g.header()):]
+    got, cnt = _emul_q(emul, tmp_path, reads, quals, k, cut, hp)
+    assert got == recs
+    assert cnt["kmers"] == st.num_kmers_loaded and cnt["contigs"] == st.contigs_parsed
