@@ -122,7 +122,6 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
     }
   }
   // experiment knobs (see profiles/): probe-load flavour and L2 fetch granularity
-  if(const char *m = getenv("MCX_LD_MODE")) mcx_set_ld_mode(atoi(m));
   if(const char *m = getenv("MCX_MINB")) mcx_set_minb(atoi(m));
   if(const char *m = getenv("MCX_L2FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(m));
   *out = g;

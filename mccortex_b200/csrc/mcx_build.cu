@@ -192,38 +192,33 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
     // raw[buf^1] was last read in phase 1 of the previous iteration: safe to refill
     if(tid == 0 && chunk + gridDim.x < c_last) issue_chunk_load(sm, p, chunk + gridDim.x, buf ^ 1u);
 
-    // ---- phase 2a: contig rules -> in_contig bit mask for windows cs-1 .. cs+T
-    for(uint32_t i = tid; i < MCX_VW * 32u; i += MCX_THREADS) {
-      bool ok = (i < MCX_T + 2u) && mcx_chunk_window_ok(sm.bad, sm.eq, i, p.k, p.hp_cutoff);
-      uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
-      if(lane == 0) sm.vmask[i >> 5] = m;
-      if(MODE != MCX_MODE_PLAIN) {
-        bool sok = ok && mcx_chunk_window_ok(sm.bads, sm.eq, i, p.k, p.hp_cutoff);
-        uint32_t ms = __ballot_sync(0xFFFFFFFFu, sok);
-        if(lane == 0) sm.svm[i >> 5] = ms;
-      }
+    // ---- phase 2a: contig rules, 32 windows per thread (word-parallel dilate / erode of the
+    //      bad / eq masks); masks are indexed by staged position
+    if(tid < MCX_VW) {
+      const bool live = tid < (MCX_LB + MCX_T + 32u) / 32u;
+      sm.vmask[tid] = live ? mcx_valid_word(sm.bad, sm.eq, tid, p.k, p.hp_cutoff) : 0u;
+      if(MODE != MCX_MODE_PLAIN) sm.svm[tid] = live ? mcx_valid_word(sm.bads, sm.eq, tid, p.k, p.hp_cutoff) : 0u;
     }
-    if(MODE == MCX_MODE_QUAL && tid == 32) sm.carry_in = chunk_carry_in(p.summary, chunk, c_first);
+    if(MODE == MCX_MODE_QUAL && tid == 96) sm.carry_in = chunk_carry_in(p.summary, chunk, c_first);
     __syncthreads();
     if(MODE != MCX_MODE_PLAIN) {
       // vmask holds ev, svm holds sv: resolve in_contig = ev & (sv | in_contig(prev)) (one thread,
-      // ~66 adds).  Bit 0 is the window before the chunk: its value IS the carry-in.
+      // ~68 adds).  The window before the chunk (position LB-1) carries the chunk's carry-in.
       if(tid == 0) {
+        const uint32_t cb = MCX_LB - 1u, keep = ~0u << cb; // cb < 32: lives in word 0
+        const uint32_t ev0 = sm.vmask[0] & keep & ~(1u << cb), sv0 = sm.svm[0] & keep & ~(1u << cb);
         if(MODE == MCX_MODE_QUAL) {
-          uint32_t cin = sm.carry_in;
-          sm.vmask[0] = (sm.vmask[0] & ~1u) | cin; sm.svm[0] = (sm.svm[0] & ~1u) | cin;
+          const uint32_t cin = sm.carry_in;
+          sm.vmask[0] = ev0 | (cin << cb); sm.svm[0] = sv0 | (cin << cb);
           mcx_contig_chain(sm.vmask, sm.svm, MCX_VW, 0u, sm.vmask);
         } else {
-          // summary of this chunk's own windows (bits 1..T): carry-out for carry-in 0 and 1
-          uint32_t ev0 = sm.vmask[0], sv0 = sm.svm[0], out = 0;
+          // summary of this chunk's own windows: in_contig of its last window for carry-in 0 and 1
+          uint32_t out = 0;
           for(uint32_t cin = 0; cin < 2u; cin++) {
-            sm.vmask[0] = (ev0 & ~1u) | cin; sm.svm[0] = (sv0 & ~1u) | cin;
-            uint32_t last = 0;
-            // in_contig of bit T: run the chain over the words that cover bits 0..T
+            sm.vmask[0] = ev0 | (cin << cb); sm.svm[0] = sv0 | (cin << cb);
             uint32_t x[MCX_VW];
             mcx_contig_chain(sm.vmask, sm.svm, MCX_VW, 0u, x);
-            last = mcx_get_bit(x, MCX_T);
-            out |= last << cin;
+            out |= mcx_get_bit(x, MCX_LB - 1u + MCX_T) << cin;
           }
           p.summary[chunk - c_first] = (uint8_t)out;
         }
@@ -231,17 +226,16 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
       __syncthreads();
     }
 
-    // ---- phase 2b: one window per thread per round
-#pragma unroll 1
-    for(uint32_t j = 0; MODE != MCX_MODE_QSUM && j < MCX_T / MCX_THREADS; j++) {
-      const uint32_t i = 1u + j * MCX_THREADS + tid;
-      const uint64_t g = cs + (i - 1u);
-      if(mcx_get_bit(sm.vmask, i) && g >= p.r_begin && g < p.r_end) {
-        McxOcc<W> o = mcx_chunk_occurrence<W>(sm.pk, sm.vmask, i, p.k);
-        n_kmers++;
-        n_contigs += !mcx_get_bit(sm.vmask, i - 1u);
-        sink(o, n_novel, full);
-      }
+    // ---- phase 2b: 8 consecutive windows per thread, rolling k-mers
+    if(MODE != MCX_MODE_QSUM) {
+      mcx_thread_windows<W>(sm.pk, sm.vmask, tid, p.k, [&](const McxOcc<W> &o, uint32_t j, bool starts) {
+        const uint64_t g = cs + MCX_WPT * tid + j;
+        if(g >= p.r_begin && g < p.r_end) {
+          n_kmers++;
+          n_contigs += starts;
+          sink(o, n_novel, full);
+        }
+      });
     }
     __syncthreads();
   }
@@ -479,4 +473,3 @@ cudaError_t mcx_launch_front_flush(const McxTable &t, unsigned long long *counte
 
 // ---------------------------------------------------------------- tuning knobs (experiments)
 void mcx_set_minb(int minb) { g_minb = (minb == 5 || minb == 6 || minb == 8) ? minb : 4; }
-cudaError_t mcx_set_ld_mode(int mode) { return cudaMemcpyToSymbol(mcx_ld_mode, &mode, sizeof(int)); }

@@ -18,7 +18,7 @@
 #define MCX_RAW   (MCX_LB + MCX_T + MCX_TAIL)   /* 2144 bytes, multiple of 16 */
 #define MCX_PKW   (MCX_RAW / 16u + 4u)  /* packed words + over-read padding */
 #define MCX_MSW   (MCX_RAW / 32u + 4u)  /* mask words + over-read padding */
-#define MCX_VW    ((MCX_T + 2u + 31u) / 32u + 1u) /* valid-mask words for windows -1 .. T */
+#define MCX_VW    ((MCX_LB + MCX_T + 1u + 31u) / 32u + 3u) /* in-contig mask words: staged positions 0 .. LB+T, + over-read padding */
 #define MCX_SEQ_PAD 256u                /* readable slack required after nbytes of a device buffer */
 
 // Phase 1, one 16-byte item: raw bytes -> packed bases, bad / eq / newline bits.
@@ -81,24 +81,120 @@ MCX_HD uint32_t mcx_contig_chain(const uint32_t *ev, const uint32_t *sv, uint32_
   return cin;
 }
 
-// Phase 2a: is the window with local index i (buffer start = chunk_start - 1 + i) loadable?
-MCX_HD bool mcx_chunk_window_ok(const uint32_t *bad, const uint32_t *eq, uint32_t i, uint32_t k, uint32_t hp_cutoff)
+// ---------------------------------------------------------------------------
+// Phase 2a, word-parallel: 32 windows per call instead of one.
+// Masks are indexed by STAGED POSITION q (byte q of raw[]); window q = bases q .. q+k-1.
+// ---------------------------------------------------------------------------
+struct McxBits128 { uint64_t lo, hi; };
+MCX_HD McxBits128 mcx_b128_load(const uint32_t *m, uint32_t j)
 {
-  return mcx_window_ok(bad, eq, MCX_LB - 1u + i, k, hp_cutoff);
+  McxBits128 x;
+  x.lo = ((uint64_t)m[j + 1] << 32) | m[j];
+  x.hi = ((uint64_t)m[j + 3] << 32) | m[j + 2];
+  return x;
+}
+MCX_HD McxBits128 mcx_b128_shr(McxBits128 x, uint32_t s) // 1 <= s <= 63
+{
+  McxBits128 r; r.lo = (x.lo >> s) | (x.hi << (64u - s)); r.hi = x.hi >> s; return r;
+}
+// out[q] = OR_{d<n} in[q+d]   (n >= 1; bits beyond the 128 loaded read as 0)
+MCX_HD McxBits128 mcx_b128_dilate(McxBits128 x, uint32_t n)
+{
+  uint32_t have = 1;
+  while(have < n) {
+    uint32_t s = (n - have < have) ? (n - have) : have;
+    McxBits128 y = mcx_b128_shr(x, s);
+    x.lo |= y.lo; x.hi |= y.hi; have += s;
+  }
+  return x;
+}
+// out[q] = AND_{d<n} in[q+d]
+MCX_HD McxBits128 mcx_b128_erode(McxBits128 x, uint32_t n)
+{
+  uint32_t have = 1;
+  while(have < n) {
+    uint32_t s = (n - have < have) ? (n - have) : have;
+    McxBits128 y = mcx_b128_shr(x, s);
+    x.lo &= y.lo; x.hi &= y.hi; have += s;
+  }
+  return x;
 }
 
-// Phase 2b: everything one occurrence contributes, from the staged arrays.
+// Loadable-window bits for positions 32j .. 32j+31 (row B, local form; see mcx_window_ok in
+// mcx_device.cuh for the per-window statement of the same predicate and DESIGN.md for why it
+// equals seq_contig_start2/seq_contig_end2).  Needs mask words j .. j+3.
+MCX_HD uint32_t mcx_valid_word(const uint32_t *bad, const uint32_t *eq, uint32_t j, uint32_t k, uint32_t hp_cutoff)
+{
+  McxBits128 d = mcx_b128_dilate(mcx_b128_load(bad, j), k);      // any bad base in [q, q+k)
+  uint32_t v = ~(uint32_t)d.lo;
+  if(hp_cutoff > 1u) {
+    // a run of hp equal chars inside the window = hp-1 consecutive eq bits starting in [q+1, q+k-hp+1]
+    McxBits128 a = mcx_b128_erode(mcx_b128_load(eq, j), hp_cutoff - 1u);
+    McxBits128 h = mcx_b128_dilate(mcx_b128_shr(a, 1u), k - hp_cutoff + 1u);
+    v &= ~(uint32_t)h.lo;
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// Phase 2b: one thread walks MCX_WPT consecutive windows with ROLLING forward and
+// reverse-complement k-mers (shift in one base per step) instead of re-extracting and
+// re-reversing every window: ~4x fewer instructions per window (ncu: the first kernel was
+// issue-bound at 15 warp-instructions per occurrence once the table accesses hit L2).
+// ---------------------------------------------------------------------------
+#define MCX_WPT 8u /* windows per thread: 256 threads x 8 = MCX_T */
+
 template <int W> struct McxOcc { McxKmer<W> key; uint32_t hc, hb, emask, orient; };
 
-template <int W>
-MCX_HD McxOcc<W> mcx_chunk_occurrence(const uint32_t *pk, const uint32_t *vmask, uint32_t i, uint32_t k)
+template <int W> MCX_HD void mcx_roll(McxKmer<W> &f, McxKmer<W> &r, uint32_t b, uint32_t k);
+template <> MCX_HD void mcx_roll<1>(McxKmer<1> &f, McxKmer<1> &r, uint32_t b, uint32_t k)
 {
-  McxOcc<W> o;
-  uint32_t p = MCX_LB - 1u + i; // position of the window's first base in the staged arrays
-  McxKmer<W> f = mcx_kmer_at<W>(pk, p, k);
-  o.key = mcx_kmer_key<W>(f, k, &o.orient);
-  o.hc = mcx_lookup3<W>(o.key, 0u, &o.hb);
-  bool has_prev = mcx_get_bit(vmask, i - 1u), has_next = mcx_get_bit(vmask, i + 1u);
-  o.emask = mcx_edge_mask(o.orient, has_prev, mcx_get_base(pk, p - 1u), has_next, mcx_get_base(pk, p + k));
-  return o;
+  f.b[0] = ((f.b[0] << 2) | b) & (~0ull >> (64u - 2u * k));
+  r.b[0] = (r.b[0] >> 2) | ((uint64_t)(3u - b) << (2u * k - 2u));
+}
+template <> MCX_HD void mcx_roll<2>(McxKmer<2> &f, McxKmer<2> &r, uint32_t b, uint32_t k)
+{
+  const uint32_t top = 2u * (k - 32u); // bits used in b[0], 2..62
+  f.b[0] = ((f.b[0] << 2) | (f.b[1] >> 62)) & (~0ull >> (64u - top));
+  f.b[1] = (f.b[1] << 2) | b;
+  r.b[1] = (r.b[1] >> 2) | (r.b[0] << 62);
+  r.b[0] = (r.b[0] >> 2) | ((uint64_t)(3u - b) << (top - 2u));
+}
+template <int W> MCX_HD uint32_t mcx_first_base(const McxKmer<W> &f, uint32_t k)
+{
+  return (uint32_t)(f.b[0] >> (W == 1 ? 2u * k - 2u : 2u * (k - 32u) - 2u)) & 3u;
+}
+
+// Thread t of the CTA: windows at staged positions MCX_LB + 8t + j, j < 8.  `vmask` is indexed by
+// staged position (bit q = window q is in a contig).  fn(occ, j, starts_contig) is called for every
+// window that is in a contig.
+template <int W, class F>
+MCX_HD void mcx_thread_windows(const uint32_t *pk, const uint32_t *vmask, uint32_t t, uint32_t k, F &&fn)
+{
+  const uint32_t p0 = MCX_LB + MCX_WPT * t;
+  // in_contig bits of windows p0-1 .. p0+8 (bit 0 = the window before ours)
+  const uint32_t vb = (uint32_t)(mcx_get64bits(vmask, p0 - 1u)) & 0x3FFu;
+  if(!(vb & 0x1FEu)) return;
+  McxKmer<W> f = mcx_kmer_at<W>(pk, p0, k);
+  McxKmer<W> r = mcx_kmer_revcomp<W>(f, k);
+  const uint64_t nx = mcx_get32bases(pk, p0 + k);      // bases p0+k .. : the ones shifted in
+  uint32_t prev = mcx_get_base(pk, p0 - 1u);           // base before the current window
+  // not unrolled on purpose: fn() inlines the table probe, 8 copies of it cost 80 KB of code
+#pragma unroll 1
+  for(uint32_t j = 0; j < MCX_WPT; j++) {
+    const uint32_t next = (uint32_t)(nx >> (62u - 2u * j)) & 3u;
+    if((vb >> (j + 1u)) & 1u) {
+      McxOcc<W> o;
+      bool rc_lt;
+      if(W == 1) rc_lt = r.b[0] < f.b[0];
+      else rc_lt = (r.b[0] < f.b[0]) || (r.b[0] == f.b[0] && r.b[W - 1] < f.b[W - 1]);
+      o.orient = rc_lt ? 1u : 0u;
+      o.key = rc_lt ? r : f;
+      o.hc = mcx_lookup3<W>(o.key, 0u, &o.hb);
+      o.emask = mcx_edge_mask(o.orient, (vb >> j) & 1u, prev, (vb >> (j + 2u)) & 1u, next);
+      fn(o, j, !((vb >> j) & 1u));
+    }
+    prev = mcx_first_base<W>(f, k);
+    mcx_roll<W>(f, r, next, k);
+  }
 }

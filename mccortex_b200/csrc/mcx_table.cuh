@@ -37,25 +37,12 @@ struct McxTable {
 
 #if defined(__CUDACC__)
 
-// 32-byte probe load.  MCX_LD_MODE picks the cache behaviour (measured with ncu, see
-// profiles/): 0 default (.ca), 1 .cg (L2 only), 2 volatile, 3 two 16-byte .cg loads,
-// 4 L1::no_allocate
-#ifndef MCX_LD_MODE_RUNTIME
-#define MCX_LD_MODE_RUNTIME 1
-#endif
-static __device__ int mcx_ld_mode = 0;
+// 32-byte probe load (SASS: LDG.E.256).  .ca / .cg / volatile / L1::no_allocate flavours and
+// two 16-byte loads were measured (profiles/r1_exp_ld_modes.txt): no difference except that two
+// 16-byte loads are 45 % slower, so the plain form stays.
 __device__ __forceinline__ void mcx_ld256(const void *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d)
 {
-  switch(mcx_ld_mode) {
-    case 1: asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p)); break;
-    case 2: asm volatile("ld.volatile.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p)); break;
-    case 3:
-      asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
-      asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2+16];" : "=l"(c), "=l"(d) : "l"(p));
-      break;
-    case 4: asm volatile("ld.global.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p)); break;
-    default: asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p)); break;
-  }
+  asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
 
 __device__ __forceinline__ void mcx_ld128(const void *p, uint64_t &a, uint64_t &b)

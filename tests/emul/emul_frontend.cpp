@@ -65,42 +65,44 @@ static void run_launch(const uint8_t *seq, uint64_t nbytes, uint64_t r_begin, ui
         for(uint32_t i = 0; i < 16u; i++)
           if(((n16 >> i) & 1u) && gpos + i >= r_begin && gpos + i < r_end) cnt.reads++;
     }
-    // phase 2a
-    for(uint32_t i = 0; i < MCX_VW * 32u; i++) {
-      bool ok = (i < MCX_T + 2u) && mcx_chunk_window_ok(bad.data(), eq.data(), i, k, hp);
-      if((i & 31u) == 0) { vmask[i >> 5] = 0; svm[i >> 5] = 0; }
-      if(ok) vmask[i >> 5] |= 1u << (i & 31u);
-      if(qual && ok && mcx_chunk_window_ok(bads.data(), eq.data(), i, k, hp)) svm[i >> 5] |= 1u << (i & 31u);
-    }
-    if(qual && pass == 0) {
-      uint32_t ev0 = vmask[0], sv0 = svm[0], out = 0;
-      for(uint32_t cin = 0; cin < 2u; cin++) {
-        vmask[0] = (ev0 & ~1u) | cin; svm[0] = (sv0 & ~1u) | cin;
-        std::vector<uint32_t> x(MCX_VW);
-        mcx_contig_chain(vmask.data(), svm.data(), MCX_VW, 0u, x.data());
-        out |= mcx_get_bit(x.data(), MCX_T) << cin;
-      }
-      summary[chunk - c_first] = (uint8_t)out;
-      continue;
+    // phase 2a (word-parallel, masks indexed by staged position)
+    for(uint32_t w = 0; w < MCX_VW; w++) {
+      bool live = w < (MCX_LB + MCX_T + 32u) / 32u;
+      vmask[w] = live ? mcx_valid_word(bad.data(), eq.data(), w, k, hp) : 0u;
+      svm[w] = (qual && live) ? mcx_valid_word(bads.data(), eq.data(), w, k, hp) : 0u;
     }
     if(qual) {
+      const uint32_t cb = MCX_LB - 1u, keep = ~0u << cb;
+      const uint32_t ev0 = vmask[0] & keep & ~(1u << cb), sv0 = svm[0] & keep & ~(1u << cb);
+      if(pass == 0) {
+        uint32_t out = 0;
+        for(uint32_t cin = 0; cin < 2u; cin++) {
+          vmask[0] = ev0 | (cin << cb); svm[0] = sv0 | (cin << cb);
+          std::vector<uint32_t> x(MCX_VW);
+          mcx_contig_chain(vmask.data(), svm.data(), MCX_VW, 0u, x.data());
+          out |= mcx_get_bit(x.data(), MCX_LB - 1u + MCX_T) << cin;
+        }
+        summary[chunk - c_first] = (uint8_t)out;
+        continue;
+      }
       uint32_t cin = 0; uint64_t j = chunk;
       while(j > c_first) { uint32_t sm = summary[--j - c_first]; if(sm == 0u) { cin = 0; break; } if(sm == 3u) { cin = 1; break; } }
-      vmask[0] = (vmask[0] & ~1u) | cin; svm[0] = (svm[0] & ~1u) | cin;
+      vmask[0] = ev0 | (cin << cb); svm[0] = sv0 | (cin << cb);
       mcx_contig_chain(vmask.data(), svm.data(), MCX_VW, 0u, vmask.data());
     }
-    // phase 2b
-    for(uint32_t i = 1; i <= MCX_T; i++) {
-      uint64_t g = cs + (i - 1u);
-      if(mcx_get_bit(vmask.data(), i) && g >= r_begin && g < r_end) {
-        McxOcc<W> o = mcx_chunk_occurrence<W>(pk.data(), vmask.data(), i, k);
-        cnt.kmers++;
-        cnt.contigs += !mcx_get_bit(vmask.data(), i - 1u);
-        std::array<uint64_t, 2> key = {o.key.b[0], W == 2 ? o.key.b[W - 1] : 0};
-        auto it = tab.find(key);
-        if(it == tab.end()) { tab[key] = Rec{1, (uint8_t)o.emask}; cnt.novel++; }
-        else { if(it->second.covg != 0xFFFFFFFFu) it->second.covg++; it->second.edges |= (uint8_t)o.emask; }
-      }
+    // phase 2b: thread t walks 8 consecutive windows with rolling k-mers
+    for(uint32_t t = 0; t < MCX_T / MCX_WPT; t++) {
+      mcx_thread_windows<W>(pk.data(), vmask.data(), t, k, [&](const McxOcc<W> &o, uint32_t j, bool starts) {
+        uint64_t g = cs + MCX_WPT * t + j;
+        if(g >= r_begin && g < r_end) {
+          cnt.kmers++;
+          cnt.contigs += starts;
+          std::array<uint64_t, 2> key = {o.key.b[0], W == 2 ? o.key.b[W - 1] : 0};
+          auto it = tab.find(key);
+          if(it == tab.end()) { tab[key] = Rec{1, (uint8_t)o.emask}; cnt.novel++; }
+          else { if(it->second.covg != 0xFFFFFFFFu) it->second.covg++; it->second.edges |= (uint8_t)o.emask; }
+        }
+      });
     }
   }
 }
