@@ -45,7 +45,6 @@ struct mcx_graph {
   uint64_t nkmers;         // slots claimed so far (updated at sync)
   McxExport exp; bool exp_valid;
   uint8_t *d_tmp; size_t d_tmp_bytes; // scratch for OFFSETS -> LINES repack
-  bool l2_persist;
 };
 
 extern "C" int mcx_device_count(void)
@@ -100,29 +99,23 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
   cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), g->own_primary);
   e = cudaStreamSynchronize(g->own_primary);
   if(e != cudaSuccess) { int r = fail_cuda(e, "memset(table)"); mcx_graph_destroy(g); return r; }
-  // front table (k <= 31, one colour): sized to sit in L2; MCX_FRONT_MB=0 disables it
+  // front table (k <= 31, one colour): sized to sit in L2 (64 MB = 2^21 sets of four 8-byte
+  // slots); MCX_FRONT_BITS=0 disables it, other values are for experiments
   if(g->table.stride == 4u) {
-    size_t front_mb = 64;
-    if(const char *m = getenv("MCX_FRONT_MB")) front_mb = (size_t)atoi(m);
-    if(front_mb) {
-      g->table.front_nslots = (front_mb << 20) / 16u;
-      g->table.front_ways = 2;
-      if(const char *w = getenv("MCX_FRONT_WAYS")) g->table.front_ways = atoi(w) >= 4 ? 4 : 2;
-      e = cudaMalloc(&g->table.front, g->table.front_nslots * 16u);
-      if(e != cudaSuccess) { int r = fail_cuda(e, "cudaMalloc(front)"); mcx_graph_destroy(g); return r; }
-      cudaMemset(g->table.front, 0, g->table.front_nslots * 16u);
-      if(const char *m = getenv("MCX_L2_PERSIST")) {
-        if(atoi(m)) {
-          int maxp = 0; cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, device);
-          size_t want = g->table.front_nslots * 16u; if((size_t)maxp < want) want = (size_t)maxp;
-          cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-          g->l2_persist = true;
-        }
-      }
+    uint32_t bits = 21;
+    if(const char *m = getenv("MCX_FRONT_BITS")) bits = (uint32_t)atoi(m);
+    if(bits) {
+      if(bits < 18) bits = 18; // count field must keep >= 12 bits
+      if(bits > 24) bits = 24;
+      g->table.front_set_bits = bits;
+      e = cudaMalloc(&g->table.front, (4ull << bits) * 8u);
+      if(e != cudaSuccess) { g->table.front_set_bits = 0; int r = fail_cuda(e, "cudaMalloc(front)"); mcx_graph_destroy(g); return r; }
+      cudaMemset(g->table.front, 0, (4ull << bits) * 8u);
     }
   }
   // experiment knobs (see profiles/): probe-load flavour and L2 fetch granularity
   if(const char *m = getenv("MCX_MINB")) mcx_set_minb(atoi(m));
+  if(const char *m = getenv("MCX_G")) mcx_set_inflight(atoi(m));
   if(const char *m = getenv("MCX_L2FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(m));
   *out = g;
   return MCX_OK;
@@ -165,7 +158,7 @@ extern "C" int mcx_graph_clear(mcx_graph *g)
   cudaStream_t st = primary(g);
   CU(cudaMemsetAsync(g->table.slots, 0, (size_t)g->table.nslots * g->table.stride * 4u, st));
   CU(cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), st));
-  if(g->table.front) CU(cudaMemsetAsync(g->table.front, 0, g->table.front_nslots * 16u, st));
+  if(g->table.front) CU(cudaMemsetAsync(g->table.front, 0, (4ull << g->table.front_set_bits) * 8u, st));
   g->occ_bound = 0; g->pend_positions = 0; g->pend_offsets_reads = g->pend_offsets_bases = 0; g->nkmers = 0;
   return MCX_OK;
 }
@@ -190,18 +183,6 @@ static int ensure_stage(mcx_graph *g)
   return MCX_OK;
 }
 
-static void apply_l2_window(mcx_graph *g, cudaStream_t st)
-{
-  if(!g->l2_persist || !g->table.front) return;
-  cudaStreamAttrValue v; memset(&v, 0, sizeof(v));
-  v.accessPolicyWindow.base_ptr = g->table.front;
-  v.accessPolicyWindow.num_bytes = g->table.front_nslots * 16u;
-  v.accessPolicyWindow.hitRatio = 1.0f;
-  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
-}
-
 static McxBuildParams make_params(mcx_graph *g, const mcx_read_batch *b, const uint8_t *dseq, uint64_t nbytes,
                                   uint64_t r_begin, uint64_t r_end)
 {
@@ -220,7 +201,6 @@ static int add_lines_device(mcx_graph *g, const mcx_read_batch *b, const uint8_t
   if(((uintptr_t)dseq & 15u) != 0) { snprintf(g_err, sizeof(g_err), "device seq buffer must be 16-byte aligned"); return MCX_ERR_BAD_ARG; }
   g->occ_bound += nbytes;
   McxBuildParams p = make_params(g, b, dseq, nbytes, 0, nbytes);
-  apply_l2_window(g, primary(g));
   CU(mcx_launch_build_fused(p, g->table, primary(g)));
   g->pend_positions += nbytes;
   return MCX_OK;
@@ -245,7 +225,7 @@ static int add_lines_host(mcx_graph *g, const mcx_read_batch *b, const uint8_t *
     int s = g->next; g->next = (g->next + 1) % MCX_NSTAGE;
     cudaStream_t st = g->streams[s];
     CU(cudaEventSynchronize(g->events[s])); // previous user of this slot's staging buffers is done
-    if(!used[s]) { CU(cudaStreamWaitEvent(st, g->ev_fork, 0)); used[s] = true; apply_l2_window(g, st); }
+    if(!used[s]) { CU(cudaStreamWaitEvent(st, g->ev_fork, 0)); used[s] = true; }
     const uint8_t *src = hseq + b0;
     if(!pinned) { memcpy(g->h_stage[s], src, b1 - b0); src = g->h_stage[s]; }
     CU(cudaMemcpyAsync(g->d_stage[s], src, b1 - b0, cudaMemcpyHostToDevice, st));
@@ -387,7 +367,7 @@ extern "C" int mcx_graph_sync(mcx_graph *g, mcx_load_stats *stats)
 {
   if(!g) return MCX_ERR_BAD_ARG;
   int r = sync_all(g); if(r) return r;
-  CU(mcx_launch_front_flush(g->table, g->d_counters, primary(g)));
+  CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
   CU(cudaStreamSynchronize(primary(g)));
   unsigned long long c[MCX_NCOUNTERS];
   CU(cudaMemcpy(c, g->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
@@ -422,7 +402,7 @@ extern "C" int mcx_graph_export_begin(mcx_graph *g, int sorted, uint64_t *nrecor
 {
   if(!g) return MCX_ERR_BAD_ARG;
   int r = sync_all(g); if(r) return r;
-  CU(mcx_launch_front_flush(g->table, g->d_counters, primary(g)));
+  CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
   cudaError_t e = mcx_export_build(g->table, g->k, sorted != 0, &g->exp, primary(g));
   if(e != cudaSuccess) return fail_cuda(e, "export");

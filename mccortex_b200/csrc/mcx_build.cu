@@ -44,6 +44,17 @@ struct __align__(128) McxChunkSmem {
   unsigned long long red[MCX_NCOUNTERS];
 };
 
+// Occurrences that are not a plain front-table hit (first sight of a k-mer, missing edge bit,
+// count field filling up, k-mer that lives in the big table) are parked here and handled after
+// the chunk's hot pass, one per thread, all lanes busy.  Handling them inline would stall the
+// whole warp on two or three dependent memory round trips whenever ANY of its 32 lanes is slow,
+// which is most rounds (measured: 100-170 ms instead of 59 ms).
+template <int W> struct McxSlowQueue {
+  uint64_t key[MCX_T * W];
+  uint8_t emask[MCX_T];
+  uint32_t n;
+};
+
 // front-end modes
 enum { MCX_MODE_PLAIN = 0,   // contig rules are window-local (no quality cut-off)
        MCX_MODE_QUAL = 1,    // quality cut-off: in_contig needs the carry chain + chunk carry-in
@@ -103,23 +114,84 @@ __device__ __forceinline__ uint32_t chunk_carry_in(const uint8_t *summary, uint6
 
 // ---------------------------------------------------------------- sinks
 // what to do with one occurrence
-template <int W> struct FusedSink {
+template <int W, int G> struct FusedSink { // G = probe loads kept in flight per thread
   McxTable t; uint32_t colour; bool may_saturate;
-  __device__ __forceinline__ void operator()(const McxOcc<W> &o, uint64_t &novel, uint32_t &full)
+  McxSlowQueue<W> *q;
+
+  // one parked occurrence: front table (claim / edge bit / drain), else the big table
+  __device__ __forceinline__ void slow(McxKmer<W> key, uint32_t emask, uint64_t &novel, uint32_t &full)
   {
-    int r = mcx_table_add<W>(t, o.key, o.hc, o.hb, colour, o.emask, may_saturate);
+    uint32_t n = 1u;
+    if(W == 1 && t.front_set_bits) {
+      // returns 0xFFFFFFFF = not absorbed, else the count it drained (0 almost always)
+      uint32_t drained = mcx_front_add_slow(t, key.b[0], emask);
+      if(drained == 0u) return;
+      if(drained != 0xFFFFFFFFu) { n = drained; emask = 0; } // carry a drained count over to the big table
+    }
+    uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
+    int r = mcx_table_add<W>(t, key, hc, hb, colour, emask, n, may_saturate);
     novel += (r == 1);
     full |= (r == 2);
+  }
+  __device__ __forceinline__ void park(const McxKmer<W> &key, uint32_t emask)
+  {
+    const uint32_t at = atomicAdd(&q->n, 1u); // < MCX_T by construction: one slot per window of the chunk
+#pragma unroll
+    for(int w = 0; w < W; w++) q->key[at * W + w] = key.b[w];
+    q->emask[at] = (uint8_t)emask;
+  }
+  __device__ __forceinline__ void consume(const McxKmer<W> keys[MCX_HALF], const uint32_t emasks[MCX_HALF], uint32_t valid,
+                                          uint64_t &novel, uint32_t &full)
+  {
+    (void)novel; (void)full;
+    if(W == 1 && t.front_set_bits) {
+      // hot pass: G probe loads in flight per thread, one 32-bit RED per hit; no Lookup3, no
+      // big-table access for k-mers that live in the L2-resident front table
+      const McxFrontGeom g = mcx_front_geom(t);
+#pragma unroll
+      for(uint32_t h = 0; h < MCX_HALF; h += G) {
+        uint64_t v[G][4], y[G];
+#pragma unroll
+        for(uint32_t i = 0; i < G; i++) {
+          y[i] = mcx_phi(keys[h + i].b[0]);
+          if((valid >> (h + i)) & 1u) mcx_ld256(t.front + ((y[i] >> g.T) << 2), v[i][0], v[i][1], v[i][2], v[i][3]);
+        }
+#pragma unroll
+        for(uint32_t i = 0; i < G; i++) {
+          if((valid >> (h + i)) & 1u) {
+            if(!mcx_front_hit(g, t.front + ((y[i] >> g.T) << 2), y[i] & g.tagmask, (uint64_t)emasks[h + i] << g.T,
+                              v[i][0], v[i][1], v[i][2], v[i][3]))
+              park(keys[h + i], emasks[h + i]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for(uint32_t j = 0; j < MCX_HALF; j++)
+        if((valid >> j) & 1u) park(keys[j], emasks[j]);
+    }
+  }
+  __device__ __forceinline__ void reset() { if(threadIdx.x == 0) q->n = 0; }
+  // after the hot pass of a chunk (all threads of the CTA, between two __syncthreads)
+  __device__ __forceinline__ void drain(uint64_t &novel, uint32_t &full)
+  {
+    const uint32_t n = q->n;
+    for(uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      McxKmer<W> key;
+#pragma unroll
+      for(int w = 0; w < W; w++) key.b[w] = q->key[i * W + w];
+      slow(key, q->emask[i], novel, full);
+    }
   }
 };
 
 // tuples binned by owner: bins[d] holds {keys[cap][W], masks[cap]} with an atomic cursor
 template <int W> struct TupleSink {
   McxTupleBins b;
-  __device__ __forceinline__ void operator()(const McxOcc<W> &o, uint64_t &novel, uint32_t &full)
+  __device__ __noinline__ void one(McxKmer<W> key, uint32_t emask, uint32_t &full)
   {
-    (void)novel;
-    uint32_t d = mcx_owner(o.hc, b.nparts);
+    uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
+    uint32_t d = mcx_owner(hc, b.nparts);
     // warp-aggregate the cursor bump per destination
     uint32_t peers = __match_any_sync(__activemask(), d);
     uint32_t leader = __ffs(peers) - 1u, lane = threadIdx.x & 31u;
@@ -130,9 +202,19 @@ template <int W> struct TupleSink {
     if(at >= b.cap) { full = 1; return; }
     uint64_t *kd = b.keys + ((uint64_t)d * b.cap + at) * W;
 #pragma unroll
-    for(int w = 0; w < W; w++) kd[w] = o.key.b[w];
-    b.masks[(uint64_t)d * b.cap + at] = (uint8_t)o.emask;
+    for(int w = 0; w < W; w++) kd[w] = key.b[w];
+    b.masks[(uint64_t)d * b.cap + at] = (uint8_t)emask;
   }
+  __device__ __forceinline__ void consume(const McxKmer<W> keys[MCX_HALF], const uint32_t emasks[MCX_HALF], uint32_t valid,
+                                          uint64_t &novel, uint32_t &full)
+  {
+    (void)novel;
+#pragma unroll
+    for(uint32_t j = 0; j < MCX_HALF; j++)
+      if((valid >> j) & 1u) one(keys[j], emasks[j], full);
+  }
+  __device__ __forceinline__ void drain(uint64_t &, uint32_t &) {}
+  __device__ __forceinline__ void reset() {}
 };
 
 // ---------------------------------------------------------------- front end
@@ -226,17 +308,29 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
       __syncthreads();
     }
 
-    // ---- phase 2b: 8 consecutive windows per thread, rolling k-mers
+    // ---- phase 2b: 8 consecutive windows per thread, rolling k-mers; keys are built four at a
+    //      time and handed to the sink, which overlaps its table probes
     if(MODE != MCX_MODE_QSUM) {
-      mcx_thread_windows<W>(sm.pk, sm.vmask, tid, p.k, [&](const McxOcc<W> &o, uint32_t j, bool starts) {
-        const uint64_t g = cs + MCX_WPT * tid + j;
-        if(g >= p.r_begin && g < p.r_end) {
-          n_kmers++;
-          n_contigs += starts;
-          sink(o, n_novel, full);
-        }
-      });
+      // windows owned by this launch: positions [r_begin, r_end)
+      const uint64_t g0 = cs + MCX_WPT * tid;
+      const uint32_t lo = p.r_begin > g0 ? (p.r_begin - g0 < MCX_WPT ? (uint32_t)(p.r_begin - g0) : MCX_WPT) : 0u;
+      const uint32_t hi = p.r_end > g0 ? (p.r_end - g0 < MCX_WPT ? (uint32_t)(p.r_end - g0) : MCX_WPT) : 0u;
+      const uint32_t own = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+      mcx_thread_occurrences<W>(sm.pk, sm.vmask, tid, p.k,
+        [&](const McxKmer<W> *keys, const uint32_t *emasks, uint32_t valid, uint32_t starts, uint32_t j0) {
+          valid &= own >> j0;
+          if(valid) {
+            n_kmers += __popc(valid);
+            n_contigs += __popc(starts & valid);
+            sink.consume(keys, emasks, valid, n_novel, full);
+          }
+        });
+      // ---- phase 2c: the parked (slow) occurrences of this chunk, one per thread
+      __syncthreads();
+      sink.drain(n_novel, full);
     }
+    __syncthreads();
+    sink.reset();
     __syncthreads();
   }
 
@@ -262,15 +356,21 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
   }
 }
 
-template <int W, int MINB>
+template <int W, int MINB, int G>
 __global__ void __launch_bounds__(MCX_THREADS, MINB) mcx_build_fused_kernel(McxBuildParams p, McxTable t)
 {
-  FusedSink<W> sink{t, p.colour, p.may_saturate != 0};
+  __shared__ McxSlowQueue<W> q;
+  if(threadIdx.x == 0) q.n = 0;
+  FusedSink<W, G> sink{t, p.colour, p.may_saturate != 0, &q};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
 
 // quality cut-off variants: pass 1 writes the per-chunk carry summaries, pass 2 inserts
-struct NullSink { template <class O> __device__ __forceinline__ void operator()(const O &, uint64_t &, uint32_t &) {} };
+struct NullSink {
+  __device__ __forceinline__ void consume(const McxKmer<1> *, const uint32_t *, uint32_t, uint64_t &, uint32_t &) {}
+  __device__ __forceinline__ void drain(uint64_t &, uint32_t &) {}
+  __device__ __forceinline__ void reset() {}
+};
 __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_contig_summary_kernel(McxBuildParams p)
 {
   NullSink sink;
@@ -279,7 +379,9 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_contig_summary_kernel(McxB
 template <int W>
 __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_build_fused_qual_kernel(McxBuildParams p, McxTable t)
 {
-  FusedSink<W> sink{t, p.colour, p.may_saturate != 0};
+  __shared__ McxSlowQueue<W> q;
+  if(threadIdx.x == 0) q.n = 0;
+  FusedSink<W, 2> sink{t, p.colour, p.may_saturate != 0, &q};
   mcx_front_end<W, MCX_MODE_QUAL>(p, sink);
 }
 
@@ -291,22 +393,44 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_kmer_tuples_kernel(McxBuil
 }
 
 // ---------------------------------------------------------------- kernel C
-// one tuple per thread; tuples are (key words, edge mask) already canonical, so only
-// hash + find-or-insert + covg++ + edge OR remain.
+// received tuples are (key words, edge mask), already canonical: each thread takes MCX_HALF
+// consecutive tuples and hands them to the same sink as kernel A (front table first, probe
+// loads overlapped, big table for the rest).
 template <int W>
 __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_insert_tuples_kernel(const uint64_t *__restrict__ keys,
                                                                            const uint8_t *__restrict__ masks,
                                                                            uint64_t n, McxTable t, uint32_t colour,
                                                                            int may_saturate, unsigned long long *counters)
 {
+  // same sink as kernel A; the parked occurrences of one grid-stride round are drained by the CTA
+  __shared__ McxSlowQueue<W> q;
+  if(threadIdx.x == 0) q.n = 0;
+  __syncthreads();
+  FusedSink<W, 2> sink{t, colour, may_saturate != 0, &q};
   uint64_t n_novel = 0, n_kmers = 0; uint32_t full = 0;
-  for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    McxKmer<W> key;
+  const uint64_t ngroups = (n + MCX_HALF - 1) / MCX_HALF, stride = (uint64_t)gridDim.x * blockDim.x;
+  // every thread of the CTA runs the same number of rounds so that the barriers line up;
+  // a round parks at most blockDim.x * MCX_HALF = 1024 <= MCX_T occurrences
+  for(uint64_t base = blockIdx.x * (uint64_t)blockDim.x; base < ngroups; base += stride) {
+    const uint64_t gi = base + threadIdx.x;
+    if(gi < ngroups) {
+      McxKmer<W> kk[MCX_HALF]; uint32_t em[MCX_HALF], valid = 0;
 #pragma unroll
-    for(int w = 0; w < W; w++) key.b[w] = keys[i * W + w];
-    uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
-    int r = mcx_table_add<W>(t, key, hc, hb, colour, masks[i], may_saturate != 0);
-    n_novel += (r == 1); full |= (r == 2); n_kmers++;
+      for(uint32_t i = 0; i < MCX_HALF; i++) {
+        const uint64_t at = gi * MCX_HALF + i;
+        const bool ok = at < n;
+#pragma unroll
+        for(int w = 0; w < W; w++) kk[i].b[w] = ok ? keys[at * W + w] : 0ull;
+        em[i] = ok ? masks[at] : 0u;
+        valid |= (uint32_t)ok << i;
+      }
+      n_kmers += __popc(valid);
+      sink.consume(kk, em, valid, n_novel, full);
+    }
+    __syncthreads();
+    sink.drain(n_novel, full);
+    __syncthreads();
+    sink.reset();
   }
   for(int s = 16; s > 0; s >>= 1) {
     n_novel += __shfl_xor_sync(0xFFFFFFFFu, n_novel, s);
@@ -321,43 +445,20 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_insert_tuples_kernel(const
 }
 
 // ---------------------------------------------------------------- front-table flush
-// merge every front entry {key, count, edges} into the big table (count may be > 1, so the
-// saturating add is a CAS loop here; this kernel touches at most front_nslots keys)
-__global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t, unsigned long long *counters)
+// merge every front entry into the big table: key = phi^-1(set, tag), covg += count, edges |= edges
+__global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t, int may_saturate, unsigned long long *counters)
 {
-  McxTable big = t; big.front = nullptr; big.front_nslots = 0;
+  const uint32_t T = 62u - t.front_set_bits;
+  const uint64_t nslots = 4ull << t.front_set_bits, tagmask = (1ull << T) - 1ull;
   uint64_t n_novel = 0; uint32_t full = 0;
-  for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < t.front_nslots; i += (uint64_t)gridDim.x * blockDim.x) {
-    uint4 v = *reinterpret_cast<const uint4 *>(t.front + i * 4u);
-    uint64_t keyf = ((uint64_t)v.y << 32) | v.x;
-    if(keyf == 0) continue;
-    McxKmer<1> key; key.b[0] = keyf & ~MCX_KEY_FLAG;
-    uint32_t count = v.z, edges = v.w & 0xFFu;
+  for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nslots; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t v = t.front[i];
+    if(v == 0) continue;
+    McxKmer<1> key; key.b[0] = mcx_phi_inv(((i >> 2) << T) | (v & tagmask));
+    const uint32_t edges = (uint32_t)(v >> T) & 0xFFu, count = (uint32_t)(v >> (T + 8u));
     uint32_t hb, hc = mcx_lookup3<1>(key, 0u, &hb);
-    // find-or-insert in the big table with a zero increment, then add the count
-    uint64_t idx = mcx_home_slot(hc, hb, big.nslots) & ~1ull;
-    uint32_t *hit = nullptr;
-    for(uint64_t probes = 0; probes < big.nslots && !hit; probes += 2) {
-      uint32_t *s = big.slots + idx * 4u;
-      for(int w = 0; w < 2 && !hit; w++) {
-        uint64_t cur = *(volatile uint64_t *)(s + 4 * w);
-        if(cur == 0) {
-          cur = atomicCAS((unsigned long long *)(s + 4 * w), 0ull, (unsigned long long)keyf);
-          if(cur == 0) { n_novel++; cur = keyf; }
-        }
-        if(cur == keyf) hit = s + 4 * w;
-      }
-      idx += 2; if(idx >= big.nslots) idx = 0;
-    }
-    if(!hit) { full = 1; continue; }
-    uint32_t cvv = *(volatile uint32_t *)(hit + 2);
-    for(;;) {
-      uint32_t nv = (cvv + count < cvv) ? 0xFFFFFFFFu : cvv + count;
-      uint32_t old = atomicCAS(hit + 2, cvv, nv);
-      if(old == cvv) break;
-      cvv = old;
-    }
-    if(edges) atomicOr(hit + 3, edges);
+    int r = mcx_table_add<1>(t, key, hc, hb, 0u, edges, count, may_saturate != 0);
+    n_novel += (r == 1); full |= (r == 2);
   }
   for(int s = 16; s > 0; s >>= 1) {
     n_novel += __shfl_xor_sync(0xFFFFFFFFu, n_novel, s);
@@ -368,8 +469,6 @@ __global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t
     if(full) atomicOr(&counters[MCX_CNT_FULL], 1ull);
   }
 }
-
-cudaError_t mcx_launch_front_flush(const McxTable &t, unsigned long long *counters, cudaStream_t st);
 
 // ---------------------------------------------------------------- repack
 // OFFSETS layout (reads abut, offsets[n+1]) -> LINES layout (each read followed by '\n'):
@@ -388,7 +487,8 @@ __global__ void mcx_repack_lines_kernel(const uint8_t *__restrict__ src, const u
 
 // ---------------------------------------------------------------- launchers
 static int g_num_sms = 0;
-static int g_minb = 4; // resident CTAs per SM the fused kernel is compiled / launched for (experiment knob)
+static int g_minb = 4;     // resident CTAs per SM the fused kernel is compiled / launched for (experiment knob)
+static int g_inflight = 2; // front-table probe loads in flight per thread (experiment knob)
 static int num_sms()
 {
   if(!g_num_sms) {
@@ -411,14 +511,17 @@ cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, c
   if(p.r_end <= p.r_begin) return cudaSuccess;
   const int minb = g_minb;
   unsigned grid = grid_for_chunks(p, minb);
+#define MCX_LAUNCH_A(MB, GG) mcx_build_fused_kernel<1, MB, GG><<<grid, MCX_THREADS, 0, st>>>(p, t)
   if(p.k <= 31) {
-    switch(minb) {
-      case 5: mcx_build_fused_kernel<1, 5><<<grid, MCX_THREADS, 0, st>>>(p, t); break;
-      case 6: mcx_build_fused_kernel<1, 6><<<grid, MCX_THREADS, 0, st>>>(p, t); break;
-      case 8: mcx_build_fused_kernel<1, 8><<<grid, MCX_THREADS, 0, st>>>(p, t); break;
-      default: mcx_build_fused_kernel<1, 4><<<grid, MCX_THREADS, 0, st>>>(p, t); break;
+    switch(minb * 10 + g_inflight) {
+      case 31: MCX_LAUNCH_A(3, 1); break; case 32: MCX_LAUNCH_A(3, 2); break; case 34: MCX_LAUNCH_A(3, 4); break;
+      case 41: MCX_LAUNCH_A(4, 1); break; case 42: MCX_LAUNCH_A(4, 2); break; case 44: MCX_LAUNCH_A(4, 4); break;
+      case 51: MCX_LAUNCH_A(5, 1); break; case 52: MCX_LAUNCH_A(5, 2); break; case 54: MCX_LAUNCH_A(5, 4); break;
+      case 61: MCX_LAUNCH_A(6, 1); break; case 62: MCX_LAUNCH_A(6, 2); break;
+      default: MCX_LAUNCH_A(4, 2); break;
     }
-  } else mcx_build_fused_kernel<2, 4><<<grid, MCX_THREADS, 0, st>>>(p, t);
+  } else mcx_build_fused_kernel<2, 4, 1><<<grid, MCX_THREADS, 0, st>>>(p, t);
+#undef MCX_LAUNCH_A
   return cudaGetLastError();
 }
 
@@ -446,7 +549,7 @@ cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint8_t *masks,
                                      uint32_t colour, int may_saturate, unsigned long long *counters, cudaStream_t st)
 {
   if(n == 0) return cudaSuccess;
-  uint64_t want = (n + MCX_THREADS - 1) / MCX_THREADS, cap = (uint64_t)num_sms() * 8;
+  uint64_t want = (n / MCX_HALF + MCX_THREADS) / MCX_THREADS, cap = (uint64_t)num_sms() * 4;
   unsigned grid = (unsigned)(want < cap ? want : cap);
   if(k <= 31) mcx_insert_tuples_kernel<1><<<grid, MCX_THREADS, 0, st>>>(keys, masks, n, t, colour, may_saturate, counters);
   else mcx_insert_tuples_kernel<2><<<grid, MCX_THREADS, 0, st>>>(keys, masks, n, t, colour, may_saturate, counters);
@@ -462,14 +565,15 @@ cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uin
   return cudaGetLastError();
 }
 
-cudaError_t mcx_launch_front_flush(const McxTable &t, unsigned long long *counters, cudaStream_t st)
+cudaError_t mcx_launch_front_flush(const McxTable &t, int may_saturate, unsigned long long *counters, cudaStream_t st)
 {
-  if(!t.front_nslots) return cudaSuccess;
-  mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, counters);
+  if(!t.front_set_bits) return cudaSuccess;
+  mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, may_saturate, counters);
   cudaError_t e = cudaGetLastError();
   if(e != cudaSuccess) return e;
-  return cudaMemsetAsync(t.front, 0, t.front_nslots * 16u, st);
+  return cudaMemsetAsync(t.front, 0, (4ull << t.front_set_bits) * 8u, st);
 }
 
 // ---------------------------------------------------------------- tuning knobs (experiments)
-void mcx_set_minb(int minb) { g_minb = (minb == 5 || minb == 6 || minb == 8) ? minb : 4; }
+void mcx_set_minb(int minb) { g_minb = (minb >= 3 && minb <= 6) ? minb : 4; }
+void mcx_set_inflight(int g) { g_inflight = (g == 1 || g == 2 || g == 4) ? g : 2; }

@@ -46,8 +46,9 @@ cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint8_t *masks,
                                      uint32_t colour, int may_saturate, unsigned long long *counters, cudaStream_t st);
 cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uint64_t nreads, uint8_t *dst, cudaStream_t st);
 
-cudaError_t mcx_launch_front_flush(const McxTable &t, unsigned long long *counters, cudaStream_t st);
+cudaError_t mcx_launch_front_flush(const McxTable &t, int may_saturate, unsigned long long *counters, cudaStream_t st);
 void mcx_set_minb(int minb);
+void mcx_set_inflight(int g);
 
 // export (mcx_export.cu)
 struct McxExport {

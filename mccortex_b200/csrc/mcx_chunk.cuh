@@ -144,7 +144,6 @@ MCX_HD uint32_t mcx_valid_word(const uint32_t *bad, const uint32_t *eq, uint32_t
 // ---------------------------------------------------------------------------
 #define MCX_WPT 8u /* windows per thread: 256 threads x 8 = MCX_T */
 
-template <int W> struct McxOcc { McxKmer<W> key; uint32_t hc, hb, emask, orient; };
 
 template <int W> MCX_HD void mcx_roll(McxKmer<W> &f, McxKmer<W> &r, uint32_t b, uint32_t k);
 template <> MCX_HD void mcx_roll<1>(McxKmer<1> &f, McxKmer<1> &r, uint32_t b, uint32_t k)
@@ -166,10 +165,14 @@ template <int W> MCX_HD uint32_t mcx_first_base(const McxKmer<W> &f, uint32_t k)
 }
 
 // Thread t of the CTA: windows at staged positions MCX_LB + 8t + j, j < 8.  `vmask` is indexed by
-// staged position (bit q = window q is in a contig).  fn(occ, j, starts_contig) is called for every
-// window that is in a contig.
+// staged position (bit q = window q is in a contig).  The windows are produced MCX_HALF at a time:
+// fn(keys, emasks, valid, starts, j0) receives the canonical keys / edge masks of windows
+// j0 .. j0+MCX_HALF-1, the bit mask of those that are in a contig and the subset that begin one.
+// A group is complete before any table access so that the sink can keep several probe loads in
+// flight (the kernel is L2-latency bound otherwise) without holding all eight keys in registers.
+#define MCX_HALF 4u
 template <int W, class F>
-MCX_HD void mcx_thread_windows(const uint32_t *pk, const uint32_t *vmask, uint32_t t, uint32_t k, F &&fn)
+MCX_HD void mcx_thread_occurrences(const uint32_t *pk, const uint32_t *vmask, uint32_t t, uint32_t k, F &&fn)
 {
   const uint32_t p0 = MCX_LB + MCX_WPT * t;
   // in_contig bits of windows p0-1 .. p0+8 (bit 0 = the window before ours)
@@ -179,22 +182,23 @@ MCX_HD void mcx_thread_windows(const uint32_t *pk, const uint32_t *vmask, uint32
   McxKmer<W> r = mcx_kmer_revcomp<W>(f, k);
   const uint64_t nx = mcx_get32bases(pk, p0 + k);      // bases p0+k .. : the ones shifted in
   uint32_t prev = mcx_get_base(pk, p0 - 1u);           // base before the current window
-  // not unrolled on purpose: fn() inlines the table probe, 8 copies of it cost 80 KB of code
-#pragma unroll 1
-  for(uint32_t j = 0; j < MCX_WPT; j++) {
-    const uint32_t next = (uint32_t)(nx >> (62u - 2u * j)) & 3u;
-    if((vb >> (j + 1u)) & 1u) {
-      McxOcc<W> o;
+#pragma unroll
+  for(uint32_t j0 = 0; j0 < MCX_WPT; j0 += MCX_HALF) {
+    McxKmer<W> keys[MCX_HALF]; uint32_t emasks[MCX_HALF];
+#pragma unroll
+    for(uint32_t i = 0; i < MCX_HALF; i++) {
+      const uint32_t j = j0 + i;
+      const uint32_t next = (uint32_t)(nx >> (62u - 2u * j)) & 3u;
       bool rc_lt;
       if(W == 1) rc_lt = r.b[0] < f.b[0];
       else rc_lt = (r.b[0] < f.b[0]) || (r.b[0] == f.b[0] && r.b[W - 1] < f.b[W - 1]);
-      o.orient = rc_lt ? 1u : 0u;
-      o.key = rc_lt ? r : f;
-      o.hc = mcx_lookup3<W>(o.key, 0u, &o.hb);
-      o.emask = mcx_edge_mask(o.orient, (vb >> j) & 1u, prev, (vb >> (j + 2u)) & 1u, next);
-      fn(o, j, !((vb >> j) & 1u));
+      keys[i] = rc_lt ? r : f;
+      emasks[i] = mcx_edge_mask(rc_lt ? 1u : 0u, (vb >> j) & 1u, prev, (vb >> (j + 2u)) & 1u, next);
+      prev = mcx_first_base<W>(f, k);
+      mcx_roll<W>(f, r, next, k);
     }
-    prev = mcx_first_base<W>(f, k);
-    mcx_roll<W>(f, r, next, k);
+    const uint32_t valid = (vb >> (j0 + 1u)) & ((1u << MCX_HALF) - 1u);
+    const uint32_t starts = valid & ~(vb >> j0);
+    if(valid) fn(keys, emasks, valid, starts, j0);
   }
 }

@@ -273,3 +273,33 @@ MCX_HD uint64_t mcx_home_slot(uint32_t c, uint32_t b, uint64_t nslots)
   return mcx_mulhi64(((uint64_t)b << 32) | c, nslots);
 }
 MCX_HD uint32_t mcx_owner(uint32_t c, uint32_t nparts) { return (uint32_t)(((uint64_t)c * nparts) >> 32); }
+
+// ---------------------------------------------------------------------------
+// Front table (k <= 31, one colour): 8-byte slots [count | edges 8 | tag T], four per 32-byte
+// sector.  The set index and the tag are the top s and low T = 62 - s bits of phi(key), phi a
+// BIJECTION on 62-bit values (odd multiplies and xor-shifts), so (set, tag) identifies the key
+// exactly and the full 8-byte key need not be stored: twice as many hot k-mers per L2 byte.
+// ---------------------------------------------------------------------------
+#define MCX_M62 ((1ull << 62) - 1ull)
+#define MCX_PHI_M1 0x2545F4914F6CDD1Dull   /* odd */
+#define MCX_PHI_M2 0x1B03738712FAD5C9ull   /* odd */
+MCX_HD uint64_t mcx_phi(uint64_t x)
+{
+  x = (x * MCX_PHI_M1) & MCX_M62; x ^= x >> 32;
+  x = (x * MCX_PHI_M2) & MCX_M62; x ^= x >> 29;
+  return x;
+}
+MCX_HD uint64_t mcx_inv_odd62(uint64_t a) // multiplicative inverse of odd a modulo 2^62 (Newton)
+{
+  uint64_t x = a; // correct to 3 bits
+  for(int i = 0; i < 6; i++) x *= 2ull - a * x;
+  return x & MCX_M62;
+}
+MCX_HD uint64_t mcx_phi_inv(uint64_t y)
+{
+  y ^= (y >> 29) ^ (y >> 58);
+  y = (y * mcx_inv_odd62(MCX_PHI_M2)) & MCX_M62;
+  y ^= y >> 32;
+  y = (y * mcx_inv_odd62(MCX_PHI_M1)) & MCX_M62;
+  return y;
+}

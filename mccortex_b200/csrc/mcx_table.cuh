@@ -22,17 +22,19 @@ struct McxTable {
   uint64_t nslots;      // always even
   uint32_t stride;      // u32 words per slot
   uint32_t ncols;
-  // L2-resident front table (16-byte slots {key, count, edges}, k <= 31, one colour only):
-  // a dense write-combining cache in front of the big table.  The big table is >> L2 and a
-  // hot k-mer there drags a whole 128-byte L2 line for 16 useful bytes, so on high-coverage
-  // input the hot set does not fit L2 (ncu: 127 B of DRAM traffic per occurrence, L2 hit
-  // rate 30 %).  Keys that win a front slot (first come, 2-way per 32-byte sector, no
-  // probing beyond it) are counted here at L2 speed and merged into the big table by
-  // mcx_front_flush_kernel; everything else falls through to the big table.  Sums and ORs
-  // commute, so the final table is identical.
-  uint32_t *front;      // front_nslots * 4 u32, or nullptr
-  uint64_t front_nslots;
-  uint32_t front_ways;  // 2 = one sector, 4 = a second sector chosen by an independent hash
+  // L2-resident front table (k <= 31, one colour): a dense write-combining cache in front of
+  // the big table.  The big table is >> L2 and a hot k-mer there drags a whole 128-byte L2 line
+  // for 16 useful bytes, so on high-coverage input the hot set does not fit L2 (ncu, first
+  // kernel: 127 B of DRAM traffic per occurrence, L2 hit rate 30 %).  Front slots are 8 bytes,
+  //   [ count : 64-8-T bits | edges : 8 | tag : T = 62 - front_set_bits ]
+  // four per 32-byte sector = one set; set index and tag are the two halves of the bijective
+  // mcx_phi(key), so the key is implied exactly.  A key claims a way if one is free (first
+  // come, never evicted); its occurrences are then counted here at L2 speed.  Counts that fill
+  // 1/8 of the count field are moved to the big table on the fly (atomicAnd returns and clears
+  // the count field), everything else by mcx_front_flush_kernel at sync.  Sums and ORs
+  // commute and every record is merged exactly once, so the final table is identical.
+  unsigned long long *front;   // (4 << front_set_bits) slots, or nullptr
+  uint32_t front_set_bits;     // log2(number of sets); 0 = no front table
 };
 
 #if defined(__CUDACC__)
@@ -64,19 +66,22 @@ __device__ __forceinline__ void mcx_cas128(void *p, uint64_t cmp_lo, uint64_t cm
                : "memory");
 }
 
-// saturating coverage increment (reference: CAS loop capped at COVG_MAX, db_node.c:139-144).
+// saturating coverage add (reference: CAS loop capped at COVG_MAX, db_node.c:139-144).
 // A plain RED is exact unless the counter is within reach of 2^32.  `may_saturate` is a
 // launch-uniform flag the host clears while fewer than ~4e9 occurrences were ever sent to the
 // graph (then no counter can be near the cap).  When it is set, a snapshot of the counter that
 // came with the probe load (possibly stale by the few 1e5 increments in flight) still proves a
-// RED safe if it is below 0xF0000000; otherwise fall back to the reference's CAS loop.
-__device__ __forceinline__ void mcx_covg_inc(uint32_t *cv, bool may_saturate, bool have_snap = false, uint32_t snap = 0)
+// RED safe if it is below 0xF0000000 - n; otherwise fall back to the reference's CAS loop.
+__device__ __forceinline__ void mcx_covg_add(uint32_t *cv, uint32_t n, bool may_saturate, bool have_snap = false,
+                                             uint32_t snap = 0)
 {
-  if(!may_saturate || (have_snap && snap < 0xF0000000u)) { atomicAdd(cv, 1u); return; }
+  if(n == 0) return;
+  if(!may_saturate || (have_snap && snap < 0xF0000000u - n)) { atomicAdd(cv, n); return; }
   uint32_t v = *(volatile uint32_t *)cv;
-  if(v < 0xF0000000u) { atomicAdd(cv, 1u); return; }
+  if(v < 0xF0000000u - n) { atomicAdd(cv, n); return; }
   while(v != 0xFFFFFFFFu) {
-    uint32_t old = atomicCAS(cv, v, v + 1u);
+    uint32_t nv = (v + n < v) ? 0xFFFFFFFFu : v + n;
+    uint32_t old = atomicCAS(cv, v, nv);
     if(old == v) break;
     v = old;
   }
@@ -92,50 +97,21 @@ __device__ __forceinline__ void mcx_edges_or(uint32_t *slot, uint32_t W, uint32_
   if((cur & bits) != bits) atomicOr(e, bits);
 }
 
-// find-or-insert + coverage + edges for one occurrence.
+// find-or-insert in the big table, then covg[colour] += n (saturating) and edges |= emask.
 // Returns 0 = found, 1 = novel, 2 = table full.
 template <int W>
 __device__ __forceinline__ int mcx_table_add(const McxTable &t, const McxKmer<W> &key, uint32_t hc, uint32_t hb,
-                                             uint32_t colour, uint32_t emask, bool may_saturate);
+                                             uint32_t colour, uint32_t emask, uint32_t n, bool may_saturate);
 
 // ---- k <= 31 --------------------------------------------------------------
 template <>
 __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer<1> &key, uint32_t hc, uint32_t hb,
-                                                uint32_t colour, uint32_t emask, bool may_saturate)
+                                                uint32_t colour, uint32_t emask, uint32_t n, bool may_saturate)
 {
   const uint64_t keyf = key.b[0] | MCX_KEY_FLAG;
   uint64_t idx = mcx_home_slot(hc, hb, t.nslots);
   int novel = 0;
   if(t.stride == 4u) {
-    if(t.front_nslots) {
-      // front table: two ways per 32-byte sector, claim-if-empty, never evict; with
-      // front_ways == 4 a second sector (independent hash) is tried when the first is taken
-      uint64_t fi = mcx_mulhi64(((uint64_t)hc << 32) | hb, t.front_nslots) & ~1ull;
-#pragma unroll 1
-      for(uint32_t way = 0; way < t.front_ways; way += 2) {
-        uint32_t *s = t.front + fi * 4u;
-        uint64_t k0, m0, k1, m1;
-        mcx_ld256(s, k0, m0, k1, m1);
-        uint32_t *hit = nullptr; uint64_t meta = 0;
-        if(k0 == keyf) { hit = s; meta = m0; }
-        else if(k1 == keyf) { hit = s + 4; meta = m1; }
-        else if(k0 == 0 || k1 == 0) {
-          uint32_t *cand = (k0 == 0) ? s : s + 4;
-          uint64_t old = atomicCAS((unsigned long long *)cand, 0ull, (unsigned long long)keyf);
-          if(old == 0 || old == keyf) hit = cand;
-          else if(cand == s && k1 == 0) {
-            old = atomicCAS((unsigned long long *)(s + 4), 0ull, (unsigned long long)keyf);
-            if(old == 0 || old == keyf) hit = s + 4;
-          }
-        }
-        if(hit) {
-          mcx_covg_inc(hit + 2, true, true, (uint32_t)meta); // front counters always guard against wrap
-          mcx_edges_or(hit, 1, 1, 0, emask, (uint32_t)(meta >> 32), true);
-          return 0; // novelty is decided when the entry is merged into the big table
-        }
-        fi = mcx_mulhi64((((uint64_t)hb * 0x9E3779B1u) << 32) ^ (((uint64_t)hc << 32) | hb) ^ hc, t.front_nslots) & ~1ull;
-      }
-    }
     // 16-byte slots {key, covg, edges}: probe one 32-byte sector (= 2 slots) per load
     idx &= ~1ull;
     for(uint64_t probes = 0; probes < t.nslots; probes += 2) {
@@ -160,7 +136,7 @@ __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer
         meta = 0; // freshly claimed or raced: treat edges as unknown-empty => OR is issued
       }
       if(hit) {
-        mcx_covg_inc(hit + 2, may_saturate, true, (uint32_t)meta);
+        mcx_covg_add(hit + 2, n, may_saturate, true, (uint32_t)meta);
         mcx_edges_or(hit, 1, 1, 0, emask, (uint32_t)(meta >> 32), true);
         return novel;
       }
@@ -177,7 +153,7 @@ __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer
       if(cur == 0) { novel = 1; cur = keyf; }
     }
     if(cur == keyf) {
-      mcx_covg_inc(s + 2 + colour, may_saturate);
+      mcx_covg_add(s + 2 + colour, n, may_saturate);
       mcx_edges_or(s, 1, t.ncols, colour, emask, 0, false);
       return novel;
     }
@@ -189,7 +165,7 @@ __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer
 // ---- 33 <= k <= 63 ---------------------------------------------------------
 template <>
 __device__ __forceinline__ int mcx_table_add<2>(const McxTable &t, const McxKmer<2> &key, uint32_t hc, uint32_t hb,
-                                                uint32_t colour, uint32_t emask, bool may_saturate)
+                                                uint32_t colour, uint32_t emask, uint32_t n, bool may_saturate)
 {
   const uint64_t k0f = key.b[0] | MCX_KEY_FLAG, k1 = key.b[1];
   uint64_t idx = mcx_home_slot(hc, hb, t.nslots);
@@ -206,7 +182,7 @@ __device__ __forceinline__ int mcx_table_add<2>(const McxTable &t, const McxKmer
       have_meta = false;
     }
     if(c0 == k0f && c1 == k1) {
-      mcx_covg_inc(s + 4 + colour, may_saturate);
+      mcx_covg_add(s + 4 + colour, n, may_saturate);
       // edges word for colour c sits at u32 index 4 + C + (c>>2); with the 256-bit
       // load we hold u32 words 4..7 in (m0, m1)
       uint32_t ew_idx = 4u + t.ncols + (colour >> 2);
@@ -219,6 +195,79 @@ __device__ __forceinline__ int mcx_table_add<2>(const McxTable &t, const McxKmer
     idx++; if(idx >= t.nslots) idx = 0;
   }
   return 2;
+}
+
+// ---- front table ------------------------------------------------------------
+struct McxFrontGeom { uint32_t T; uint64_t tagmask, one; };
+__device__ __forceinline__ McxFrontGeom mcx_front_geom(const McxTable &t)
+{
+  McxFrontGeom g; g.T = 62u - t.front_set_bits; g.tagmask = (1ull << g.T) - 1ull; g.one = 1ull << (g.T + 8u);
+  return g;
+}
+
+// Slow side of the front table for one occurrence of `key` (k <= 31): re-reads the set, claims a
+// free way if the key is not there, drains a count field that is 1/8 full.  Returns true if the
+// Returns 0xFFFFFFFF if the front table did NOT absorb the occurrence; otherwise the count that
+// this thread has just taken OUT of the front table and must add to the big table (0 almost always).
+static __device__ __noinline__ uint32_t mcx_front_add_slow(McxTable t, uint64_t key, uint32_t emask)
+{
+  const McxFrontGeom g = mcx_front_geom(t);
+  const uint64_t y = mcx_phi(key), tag = y & g.tagmask, ebits = (uint64_t)emask << g.T;
+  unsigned long long *set = t.front + ((y >> g.T) << 2);
+  uint64_t v0, v1, v2, v3;
+  mcx_ld256(set, v0, v1, v2, v3);
+  uint32_t drained = 0;
+#pragma unroll
+  for(int w = 0; w < 4; w++) {
+    const uint64_t v = w == 0 ? v0 : (w == 1 ? v1 : (w == 2 ? v2 : v3));
+    if(v != 0 && (v & g.tagmask) == tag) {
+      atomicAdd(&set[w], (unsigned long long)g.one);
+      if((v & ebits) != ebits) atomicOr(&set[w], (unsigned long long)ebits);
+      if((v >> (g.T + 8u)) >= (1ull << (53u - g.T))) {
+        // the count field is 56-T >= 12 bits wide (15 at the default size): move it to the big
+        // table once it is 1/8 full, long before it can wrap (a wrap would need 7/8 of the range,
+        // > 28k increments of ONE address at the default size, inside one load->RED latency; the
+        // L2 atomic unit retires ~1 per clock per address)
+        uint64_t old = atomicAnd(&set[w], (unsigned long long)(g.one - 1ull));
+        drained = (uint32_t)(old >> (g.T + 8u));
+      }
+      return drained;
+    }
+  }
+#pragma unroll
+  for(int w = 0; w < 4; w++) {
+    const uint64_t v = w == 0 ? v0 : (w == 1 ? v1 : (w == 2 ? v2 : v3));
+    if(v == 0) {
+      uint64_t old = atomicCAS(&set[w], 0ull, (unsigned long long)(tag | ebits | g.one));
+      if(old == 0) return 0u;                              // claimed, first count and edges included
+      if((old & g.tagmask) == tag) {                       // lost the race to the same key
+        atomicAdd(&set[w], (unsigned long long)g.one);
+        if((old & ebits) != ebits) atomicOr(&set[w], (unsigned long long)ebits);
+        return 0u;
+      }
+    }
+  }
+  return 0xFFFFFFFFu;
+}
+
+// Fast side: the set has already been loaded (v0..v3).  Handles the overwhelmingly common case --
+// the key sits in the set, its edge bits are already there, its count field is far from full --
+// with ONE RED and returns true; anything else returns false and goes to mcx_front_add_slow.
+__device__ __forceinline__ bool mcx_front_hit(const McxFrontGeom &g, unsigned long long *set, uint64_t tag, uint64_t ebits,
+                                              uint64_t v0, uint64_t v1, uint64_t v2, uint64_t v3)
+{
+  const uint64_t lim = 1ull << (53u - g.T);
+  int w = -1; uint64_t v = 0;
+  if((v0 & g.tagmask) == tag && v0 != 0) { w = 0; v = v0; }
+  else if((v1 & g.tagmask) == tag && v1 != 0) { w = 1; v = v1; }
+  else if((v2 & g.tagmask) == tag && v2 != 0) { w = 2; v = v2; }
+  else if((v3 & g.tagmask) == tag && v3 != 0) { w = 3; v = v3; }
+  if(w < 0 || (v & ebits) != ebits || (v >> (g.T + 8u)) >= lim) return false;
+  // count and edge fields sit entirely in the high 32-bit word (T + 8 >= 32 for every allowed
+  // size), so the increment is a 32-bit RED like the big table's covg++ (64-bit REDs measured
+  // ~30 % slower here)
+  atomicAdd(reinterpret_cast<unsigned int *>(&set[w]) + 1, (unsigned int)(g.one >> 32));
+  return true;
 }
 
 #endif // __CUDACC__

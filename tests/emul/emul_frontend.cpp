@@ -90,19 +90,21 @@ static void run_launch(const uint8_t *seq, uint64_t nbytes, uint64_t r_begin, ui
       vmask[0] = ev0 | (cin << cb); svm[0] = sv0 | (cin << cb);
       mcx_contig_chain(vmask.data(), svm.data(), MCX_VW, 0u, vmask.data());
     }
-    // phase 2b: thread t walks 8 consecutive windows with rolling k-mers
+    // phase 2b: thread t walks 8 consecutive windows with rolling k-mers, four at a time
     for(uint32_t t = 0; t < MCX_T / MCX_WPT; t++) {
-      mcx_thread_windows<W>(pk.data(), vmask.data(), t, k, [&](const McxOcc<W> &o, uint32_t j, bool starts) {
-        uint64_t g = cs + MCX_WPT * t + j;
-        if(g >= r_begin && g < r_end) {
-          cnt.kmers++;
-          cnt.contigs += starts;
-          std::array<uint64_t, 2> key = {o.key.b[0], W == 2 ? o.key.b[W - 1] : 0};
-          auto it = tab.find(key);
-          if(it == tab.end()) { tab[key] = Rec{1, (uint8_t)o.emask}; cnt.novel++; }
-          else { if(it->second.covg != 0xFFFFFFFFu) it->second.covg++; it->second.edges |= (uint8_t)o.emask; }
-        }
-      });
+      mcx_thread_occurrences<W>(pk.data(), vmask.data(), t, k,
+        [&](const McxKmer<W> *keys, const uint32_t *emasks, uint32_t valid, uint32_t starts, uint32_t j0) {
+          for(uint32_t i = 0; i < MCX_HALF; i++) {
+            uint64_t g = cs + MCX_WPT * t + j0 + i;
+            if(!((valid >> i) & 1u) || g < r_begin || g >= r_end) continue;
+            cnt.kmers++;
+            cnt.contigs += (starts >> i) & 1u;
+            std::array<uint64_t, 2> key = {keys[i].b[0], W == 2 ? keys[i].b[W - 1] : 0};
+            auto it = tab.find(key);
+            if(it == tab.end()) { tab[key] = Rec{1, (uint8_t)emasks[i]}; cnt.novel++; }
+            else { if(it->second.covg != 0xFFFFFFFFu) it->second.covg++; it->second.edges |= (uint8_t)emasks[i]; }
+          }
+        });
     }
   }
 }

@@ -262,3 +262,26 @@ def test_quality_carry_across_chunks(M, oracle):
         assert got == recs
         assert st.num_kmers_loaded == ost.num_kmers_loaded and st.contigs_parsed == ost.contigs_parsed
         g.close()
+
+
+def test_high_multiplicity_kmers_drain_the_front_table(M, oracle):
+    """k-mers seen far more often than the front table's count field holds (poly-A, a short
+    tandem repeat): counts are drained to the big table on the fly and nothing is lost"""
+    rng = random.Random(4)
+    reads = ["A" * 150] * 3000 + ["ACGTTGCA" * 20] * 2000 + rand_reads(rng, 500, 150, 5000, perr=0.0, pN=0.0, lower=0.0)
+    rng.shuffle(reads)
+    recs, ost = oracle_records(oracle, reads, 31)
+    g = M.Graph(31, 1, 1 << 18)
+    blob = "".join(r + "\n" for r in reads).encode()
+    for _ in range(3):
+        g.add_lines(blob)
+    st = g.sync()
+    assert st.num_kmers_loaded == 3 * ost.num_kmers_loaded and st.num_kmers_novel == ost.num_kmers_novel
+    got, n, rb = g.export_records()
+    assert n == ost.num_kmers_novel
+    for i in range(0, len(recs), rb):
+        assert got[i:i + 8] == recs[i:i + 8]
+        assert int.from_bytes(got[i + 8:i + 12], "little") == 3 * int.from_bytes(recs[i + 8:i + 12], "little")
+        assert got[i + 12] == recs[i + 12]
+    assert max(int.from_bytes(got[i + 8:i + 12], "little") for i in range(0, len(got), rb)) >= 3 * 3000 * 120
+    g.close()
