@@ -127,16 +127,31 @@ int mcx_graph_export_begin(mcx_graph *g, int sorted, uint64_t *nrecords, uint32_
 int mcx_graph_export_read(mcx_graph *g, uint64_t first_record, uint64_t nrecords, void *host_dst);
 int mcx_graph_export_end(mcx_graph *g);
 
-/* ---- multi-GPU pieces (one graph shard per GPU) --------------------------- */
-/* Kernel B: reads -> canonical (key, edge mask) tuples, binned by owner = top bits of the
- * Lookup3 hash.  All pointers are device memory of g's GPU; batch must be MCX_MEM_DEVICE /
- * MCX_LAYOUT_LINES.  keys_out holds nparts bins of cap_per_part tuples x W u64, masks_out
- * nparts x cap_per_part bytes, counts_out nparts u64 (zeroed by the call, filled on the stream).
- * A bin overflow is reported by the next mcx_graph_sync as MCX_ERR_TABLE_FULL. */
-int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *batch, uint32_t nparts, uint64_t cap_per_part,
-                    uint64_t *keys_out, uint8_t *masks_out, uint64_t *counts_out);
+/* ---- multi-GPU pieces (one graph shard per GPU, one process per GPU) ------------------------
+ * Ownership: owner(key) = (c * nparts) >> 32 with c = Lookup3(key) (the hash the reference uses
+ * for its bucket choice, src/graph/hash_table.c:259).  A tuple is
+ *     key  : W x u64 canonical key words            (W = 1 for k <= 31, 2 for k <= 63)
+ *     meta : u32 = (count << 8) | edge mask         (count occurrences of the key, edges to OR)
+ * Bins: keys_out holds nparts bins of cap_per_part tuples (x W u64), meta_out nparts x
+ * cap_per_part u32, counts_out nparts u64 (zeroed by the call, filled on the stream).  All
+ * pointers are device memory of g's GPU; batches must be MCX_MEM_DEVICE / MCX_LAYOUT_LINES.
+ * A bin overflow is reported by the next mcx_graph_sync as MCX_ERR_TABLE_FULL.
+ *
+ * Sharded build of one step (what bench.py --gpus N drives):
+ *   per batch : mcx_graph_add_reads_sharded  -> exchange bins -> mcx_graph_insert_tuples
+ *   at the end: mcx_graph_flush_sharded      -> exchange bins -> mcx_graph_insert_tuples -> mcx_graph_sync
+ * Hot k-mers are counted in the LOCAL front table whoever owns them and cross the wire once,
+ * aggregated, at the flush; only what the front table could not absorb travels per occurrence. */
+int mcx_graph_add_reads_sharded(mcx_graph *g, const mcx_read_batch *batch, uint32_t nparts, uint32_t my_part,
+                                uint64_t cap_per_part, uint64_t *keys_out, uint32_t *meta_out, uint64_t *counts_out);
+int mcx_graph_flush_sharded(mcx_graph *g, uint32_t nparts, uint32_t my_part, uint64_t cap_per_part,
+                            uint64_t *keys_out, uint32_t *meta_out, uint64_t *counts_out);
 /* Kernel C: insert n received tuples (device pointers) into this shard. */
-int mcx_graph_insert_tuples(mcx_graph *g, const uint64_t *keys, const uint8_t *masks, uint64_t n, uint32_t colour);
+int mcx_graph_insert_tuples(mcx_graph *g, const uint64_t *keys, const uint32_t *meta, uint64_t n, uint32_t colour);
+/* Kernel B alone: reads -> one tuple per occurrence (count 1), binned by owner; nothing is
+ * inserted locally.  Kept as the unaggregated baseline of the exchange and for tests. */
+int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *batch, uint32_t nparts, uint64_t cap_per_part,
+                    uint64_t *keys_out, uint32_t *meta_out, uint64_t *counts_out);
 /* owner of a key, for tests: same function the kernels use */
 uint32_t mcx_key_owner(const uint64_t *key_words, uint32_t kmer_size, uint32_t nparts);
 

@@ -85,6 +85,8 @@ def lib():
     L.mcx_graph_export_end.argtypes = [vp]
     L.mcx_kmer_tuples.argtypes = [vp, C.POINTER(ReadBatch), u32, u64, vp, vp, vp]
     L.mcx_graph_insert_tuples.argtypes = [vp, vp, vp, u64, u32]
+    L.mcx_graph_add_reads_sharded.argtypes = [vp, C.POINTER(ReadBatch), u32, u32, u64, vp, vp, vp]
+    L.mcx_graph_flush_sharded.argtypes = [vp, u32, u32, u64, vp, vp, vp]
     L.mcx_key_owner.restype = u32
     L.mcx_key_owner.argtypes = [C.POINTER(u64), u32, u32]
     _lib = L
@@ -221,6 +223,16 @@ class Graph:
         b = self._batch(seq_dev_addr, nbytes, MCX_LAYOUT_LINES, MCX_MEM_DEVICE, 0, hp_cutoff)
         _ck(lib().mcx_kmer_tuples(self.h, C.byref(b), nparts, cap_per_part, keys_addr, masks_addr, counts_addr),
             "mcx_kmer_tuples")
+
+    def add_reads_sharded(self, seq_dev_addr, nbytes, nparts, my_part, cap_per_part, keys_addr, meta_addr, counts_addr,
+                          hp_cutoff=0, colour=0):
+        b = self._batch(seq_dev_addr, nbytes, MCX_LAYOUT_LINES, MCX_MEM_DEVICE, colour, hp_cutoff)
+        _ck(lib().mcx_graph_add_reads_sharded(self.h, C.byref(b), nparts, my_part, cap_per_part, keys_addr, meta_addr,
+                                              counts_addr), "mcx_graph_add_reads_sharded")
+
+    def flush_sharded(self, nparts, my_part, cap_per_part, keys_addr, meta_addr, counts_addr):
+        _ck(lib().mcx_graph_flush_sharded(self.h, nparts, my_part, cap_per_part, keys_addr, meta_addr, counts_addr),
+            "mcx_graph_flush_sharded")
 
     def insert_tuples(self, keys_addr, masks_addr, n, colour=0):
         _ck(lib().mcx_graph_insert_tuples(self.h, keys_addr, masks_addr, n, colour), "mcx_graph_insert_tuples")

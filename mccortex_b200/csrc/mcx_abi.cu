@@ -45,6 +45,7 @@ struct mcx_graph {
   uint64_t nkmers;         // slots claimed so far (updated at sync)
   McxExport exp; bool exp_valid;
   uint8_t *d_tmp; size_t d_tmp_bytes; // scratch for OFFSETS -> LINES repack
+  bool sharded;  // front table holds records of keys owned by other shards: only mcx_graph_flush_sharded may empty it
 };
 
 extern "C" int mcx_device_count(void)
@@ -159,6 +160,7 @@ extern "C" int mcx_graph_clear(mcx_graph *g)
   CU(cudaMemsetAsync(g->table.slots, 0, (size_t)g->table.nslots * g->table.stride * 4u, st));
   CU(cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), st));
   if(g->table.front) CU(cudaMemsetAsync(g->table.front, 0, (4ull << g->table.front_set_bits) * 8u, st));
+  g->sharded = false;
   g->occ_bound = 0; g->pend_positions = 0; g->pend_offsets_reads = g->pend_offsets_bases = 0; g->nkmers = 0;
   return MCX_OK;
 }
@@ -367,6 +369,7 @@ extern "C" int mcx_graph_sync(mcx_graph *g, mcx_load_stats *stats)
 {
   if(!g) return MCX_ERR_BAD_ARG;
   int r = sync_all(g); if(r) return r;
+  if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must run before sync"); return MCX_ERR_BAD_ARG; }
   CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
   CU(cudaStreamSynchronize(primary(g)));
   unsigned long long c[MCX_NCOUNTERS];
@@ -402,6 +405,7 @@ extern "C" int mcx_graph_export_begin(mcx_graph *g, int sorted, uint64_t *nrecor
 {
   if(!g) return MCX_ERR_BAD_ARG;
   int r = sync_all(g); if(r) return r;
+  if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must run before export"); return MCX_ERR_BAD_ARG; }
   CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
   cudaError_t e = mcx_export_build(g->table, g->k, sorted != 0, &g->exp, primary(g));
@@ -429,7 +433,7 @@ extern "C" int mcx_graph_export_end(mcx_graph *g)
 }
 
 extern "C" int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *b, uint32_t nparts, uint64_t cap_per_part,
-                               uint64_t *keys_out, uint8_t *masks_out, uint64_t *counts_out)
+                               uint64_t *keys_out, uint32_t *masks_out, uint64_t *counts_out)
 {
   if(!g || !b || !nparts || !cap_per_part || !keys_out || !masks_out || !counts_out) return MCX_ERR_BAD_ARG;
   if(b->layout != MCX_LAYOUT_LINES || b->mem != MCX_MEM_DEVICE || ((uintptr_t)b->seq & 15u)) return MCX_ERR_BAD_ARG;
@@ -438,15 +442,55 @@ extern "C" int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *b, uint32_t n
   cudaStream_t st = primary(g);
   CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
   McxTupleBins bins;
-  bins.keys = keys_out; bins.masks = masks_out; bins.cursor = (unsigned long long *)counts_out;
-  bins.cap = cap_per_part; bins.nparts = nparts;
+  bins.keys = keys_out; bins.meta = masks_out; bins.cursor = (unsigned long long *)counts_out;
+  bins.cap = cap_per_part; bins.nparts = nparts; bins.my_part = 0;
   McxBuildParams p = make_params(g, b, (const uint8_t *)b->seq, b->nbytes, 0, b->nbytes);
   CU(mcx_launch_kmer_tuples(p, bins, st));
   g->pend_positions += b->nbytes;
   return MCX_OK;
 }
 
-extern "C" int mcx_graph_insert_tuples(mcx_graph *g, const uint64_t *keys, const uint8_t *masks, uint64_t n, uint32_t colour)
+// sharded build, per batch: local front table + local big table for owned keys + tuples for the rest
+extern "C" int mcx_graph_add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t nparts, uint32_t my_part,
+                                           uint64_t cap_per_part, uint64_t *keys_out, uint32_t *meta_out, uint64_t *counts_out)
+{
+  if(!g || !b || nparts < 2 || my_part >= nparts || !cap_per_part || !keys_out || !meta_out || !counts_out) return MCX_ERR_BAD_ARG;
+  if(b->layout != MCX_LAYOUT_LINES || b->mem != MCX_MEM_DEVICE || ((uintptr_t)b->seq & 15u)) return MCX_ERR_BAD_ARG;
+  if(b->hp_cutoff == 1 || b->hp_cutoff > g->k || (b->fq_cutoff && b->qual)) return MCX_ERR_UNSUPPORTED;
+  if(b->colour >= g->ncols) return MCX_ERR_BAD_ARG;
+  CU(cudaSetDevice(g->device));
+  if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
+  cudaStream_t st = primary(g);
+  CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
+  McxTupleBins bins;
+  bins.keys = keys_out; bins.meta = meta_out; bins.cursor = (unsigned long long *)counts_out;
+  bins.cap = cap_per_part; bins.nparts = nparts; bins.my_part = my_part;
+  g->occ_bound += b->nbytes;
+  McxBuildParams p = make_params(g, b, (const uint8_t *)b->seq, b->nbytes, 0, b->nbytes);
+  CU(mcx_launch_build_sharded(p, g->table, bins, st));
+  g->pend_positions += b->nbytes;
+  g->sharded = true;
+  return MCX_OK;
+}
+
+// sharded build, end of a step: empty the front table -- owned records into the local big table,
+// the others (aggregated: one tuple per k-mer, not per occurrence) into the bins
+extern "C" int mcx_graph_flush_sharded(mcx_graph *g, uint32_t nparts, uint32_t my_part, uint64_t cap_per_part,
+                                       uint64_t *keys_out, uint32_t *meta_out, uint64_t *counts_out)
+{
+  if(!g || nparts < 2 || my_part >= nparts || !cap_per_part || !keys_out || !meta_out || !counts_out) return MCX_ERR_BAD_ARG;
+  CU(cudaSetDevice(g->device));
+  cudaStream_t st = primary(g);
+  CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
+  McxTupleBins bins;
+  bins.keys = keys_out; bins.meta = meta_out; bins.cursor = (unsigned long long *)counts_out;
+  bins.cap = cap_per_part; bins.nparts = nparts; bins.my_part = my_part;
+  CU(mcx_launch_front_flush_sharded(g->table, bins, g->occ_bound >= 0xF0000000ull, g->d_counters, st));
+  g->sharded = false;
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_insert_tuples(mcx_graph *g, const uint64_t *keys, const uint32_t *masks, uint64_t n, uint32_t colour)
 {
   if(!g || colour >= g->ncols || (n && (!keys || !masks))) return MCX_ERR_BAD_ARG;
   CU(cudaSetDevice(g->device));

@@ -114,9 +114,27 @@ __device__ __forceinline__ uint32_t chunk_carry_in(const uint8_t *summary, uint6
 
 // ---------------------------------------------------------------- sinks
 // what to do with one occurrence
+// append one tuple to the bin of shard d (warp-aggregated cursor bump)
+template <int W>
+__device__ __forceinline__ void mcx_bin_push(const McxTupleBins &b, uint32_t d, const McxKmer<W> &key, uint32_t meta, uint32_t &full)
+{
+  uint32_t peers = __match_any_sync(__activemask(), d);
+  uint32_t leader = __ffs(peers) - 1u, lane = threadIdx.x & 31u;
+  unsigned long long base = 0;
+  if(lane == leader) base = atomicAdd(&b.cursor[d], (unsigned long long)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  uint64_t at = base + __popc(peers & ((1u << lane) - 1u));
+  if(at >= b.cap) { full = 1; return; }
+  uint64_t *kd = b.keys + ((uint64_t)d * b.cap + at) * W;
+#pragma unroll
+  for(int w = 0; w < W; w++) kd[w] = key.b[w];
+  b.meta[(uint64_t)d * b.cap + at] = meta;
+}
+
 template <int W, int G> struct FusedSink { // G = probe loads kept in flight per thread
   McxTable t; uint32_t colour; bool may_saturate;
   McxSlowQueue<W> *q;
+  McxTupleBins bins; // bins.nparts > 1: sharded build, keys owned by another shard leave as tuples
 
   // one parked occurrence: front table (claim / edge bit / drain), else the big table
   __device__ __forceinline__ void slow(McxKmer<W> key, uint32_t emask, uint64_t &novel, uint32_t &full)
@@ -129,6 +147,10 @@ template <int W, int G> struct FusedSink { // G = probe loads kept in flight per
       if(drained != 0xFFFFFFFFu) { n = drained; emask = 0; } // carry a drained count over to the big table
     }
     uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
+    if(bins.nparts > 1u) {
+      const uint32_t d = mcx_owner(hc, bins.nparts);
+      if(d != bins.my_part) { mcx_bin_push<W>(bins, d, key, (n << 8) | emask, full); return; }
+    }
     int r = mcx_table_add<W>(t, key, hc, hb, colour, emask, n, may_saturate);
     novel += (r == 1);
     full |= (r == 2);
@@ -185,25 +207,13 @@ template <int W, int G> struct FusedSink { // G = probe loads kept in flight per
   }
 };
 
-// tuples binned by owner: bins[d] holds {keys[cap][W], masks[cap]} with an atomic cursor
+// tuples binned by owner (kernel B): every occurrence leaves as a tuple
 template <int W> struct TupleSink {
   McxTupleBins b;
   __device__ __noinline__ void one(McxKmer<W> key, uint32_t emask, uint32_t &full)
   {
     uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
-    uint32_t d = mcx_owner(hc, b.nparts);
-    // warp-aggregate the cursor bump per destination
-    uint32_t peers = __match_any_sync(__activemask(), d);
-    uint32_t leader = __ffs(peers) - 1u, lane = threadIdx.x & 31u;
-    unsigned long long base = 0;
-    if(lane == leader) base = atomicAdd(&b.cursor[d], (unsigned long long)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    uint64_t at = base + __popc(peers & ((1u << lane) - 1u));
-    if(at >= b.cap) { full = 1; return; }
-    uint64_t *kd = b.keys + ((uint64_t)d * b.cap + at) * W;
-#pragma unroll
-    for(int w = 0; w < W; w++) kd[w] = key.b[w];
-    b.masks[(uint64_t)d * b.cap + at] = (uint8_t)emask;
+    mcx_bin_push<W>(b, mcx_owner(hc, b.nparts), key, (1u << 8) | emask, full);
   }
   __device__ __forceinline__ void consume(const McxKmer<W> keys[MCX_HALF], const uint32_t emasks[MCX_HALF], uint32_t valid,
                                           uint64_t &novel, uint32_t &full)
@@ -361,7 +371,19 @@ __global__ void __launch_bounds__(MCX_THREADS, MINB) mcx_build_fused_kernel(McxB
 {
   __shared__ McxSlowQueue<W> q;
   if(threadIdx.x == 0) q.n = 0;
-  FusedSink<W, G> sink{t, p.colour, p.may_saturate != 0, &q};
+  FusedSink<W, G> sink{t, p.colour, p.may_saturate != 0, &q, McxTupleBins{nullptr, nullptr, nullptr, 0, 1, 0}};
+  mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
+}
+
+// sharded build (one shard per GPU): the front table absorbs ALL hot k-mers locally whoever owns
+// them (they are forwarded, aggregated, at flush); the parked pass inserts owned keys into the
+// local big table and bins the others for the exchange
+template <int W>
+__global__ void __launch_bounds__(MCX_THREADS, 4) mcx_build_sharded_kernel(McxBuildParams p, McxTable t, McxTupleBins b)
+{
+  __shared__ McxSlowQueue<W> q;
+  if(threadIdx.x == 0) q.n = 0;
+  FusedSink<W, 2> sink{t, p.colour, p.may_saturate != 0, &q, b};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
 
@@ -381,7 +403,7 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_build_fused_qual_kernel(Mc
 {
   __shared__ McxSlowQueue<W> q;
   if(threadIdx.x == 0) q.n = 0;
-  FusedSink<W, 2> sink{t, p.colour, p.may_saturate != 0, &q};
+  FusedSink<W, 2> sink{t, p.colour, p.may_saturate != 0, &q, McxTupleBins{nullptr, nullptr, nullptr, 0, 1, 0}};
   mcx_front_end<W, MCX_MODE_QUAL>(p, sink);
 }
 
@@ -393,44 +415,25 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_kmer_tuples_kernel(McxBuil
 }
 
 // ---------------------------------------------------------------- kernel C
-// received tuples are (key words, edge mask), already canonical: each thread takes MCX_HALF
-// consecutive tuples and hands them to the same sink as kernel A (front table first, probe
-// loads overlapped, big table for the rest).
+// received tuples are (key words, meta = count << 8 | edge mask), already canonical and owned by
+// this shard: Lookup3 + big-table find-or-insert + covg += count + edges |= mask, one per thread.
+// (They are what the senders' front tables did NOT absorb, or absorbed and aggregated.)
 template <int W>
 __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_insert_tuples_kernel(const uint64_t *__restrict__ keys,
-                                                                           const uint8_t *__restrict__ masks,
+                                                                           const uint32_t *__restrict__ meta,
                                                                            uint64_t n, McxTable t, uint32_t colour,
                                                                            int may_saturate, unsigned long long *counters)
 {
-  // same sink as kernel A; the parked occurrences of one grid-stride round are drained by the CTA
-  __shared__ McxSlowQueue<W> q;
-  if(threadIdx.x == 0) q.n = 0;
-  __syncthreads();
-  FusedSink<W, 2> sink{t, colour, may_saturate != 0, &q};
+  McxTable big = t; big.front = nullptr; big.front_set_bits = 0;
   uint64_t n_novel = 0, n_kmers = 0; uint32_t full = 0;
-  const uint64_t ngroups = (n + MCX_HALF - 1) / MCX_HALF, stride = (uint64_t)gridDim.x * blockDim.x;
-  // every thread of the CTA runs the same number of rounds so that the barriers line up;
-  // a round parks at most blockDim.x * MCX_HALF = 1024 <= MCX_T occurrences
-  for(uint64_t base = blockIdx.x * (uint64_t)blockDim.x; base < ngroups; base += stride) {
-    const uint64_t gi = base + threadIdx.x;
-    if(gi < ngroups) {
-      McxKmer<W> kk[MCX_HALF]; uint32_t em[MCX_HALF], valid = 0;
+  for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    McxKmer<W> key;
 #pragma unroll
-      for(uint32_t i = 0; i < MCX_HALF; i++) {
-        const uint64_t at = gi * MCX_HALF + i;
-        const bool ok = at < n;
-#pragma unroll
-        for(int w = 0; w < W; w++) kk[i].b[w] = ok ? keys[at * W + w] : 0ull;
-        em[i] = ok ? masks[at] : 0u;
-        valid |= (uint32_t)ok << i;
-      }
-      n_kmers += __popc(valid);
-      sink.consume(kk, em, valid, n_novel, full);
-    }
-    __syncthreads();
-    sink.drain(n_novel, full);
-    __syncthreads();
-    sink.reset();
+    for(int w = 0; w < W; w++) key.b[w] = keys[i * W + w];
+    const uint32_t m = meta[i];
+    uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
+    int r = mcx_table_add<W>(big, key, hc, hb, colour, m & 0xFFu, m >> 8, may_saturate != 0);
+    n_novel += (r == 1); full |= (r == 2); n_kmers += m >> 8;
   }
   for(int s = 16; s > 0; s >>= 1) {
     n_novel += __shfl_xor_sync(0xFFFFFFFFu, n_novel, s);
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_insert_tuples_kernel(const
 
 // ---------------------------------------------------------------- front-table flush
 // merge every front entry into the big table: key = phi^-1(set, tag), covg += count, edges |= edges
-__global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t, int may_saturate, unsigned long long *counters)
+__global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t, McxTupleBins bins, int may_saturate, unsigned long long *counters)
 {
   const uint32_t T = 62u - t.front_set_bits;
   const uint64_t nslots = 4ull << t.front_set_bits, tagmask = (1ull << T) - 1ull;
@@ -457,6 +460,11 @@ __global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t
     McxKmer<1> key; key.b[0] = mcx_phi_inv(((i >> 2) << T) | (v & tagmask));
     const uint32_t edges = (uint32_t)(v >> T) & 0xFFu, count = (uint32_t)(v >> (T + 8u));
     uint32_t hb, hc = mcx_lookup3<1>(key, 0u, &hb);
+    if(bins.nparts > 1u) {
+      // sharded build: an aggregated record of a key owned elsewhere travels as ONE tuple
+      const uint32_t d = mcx_owner(hc, bins.nparts);
+      if(d != bins.my_part) { if(count | edges) mcx_bin_push<1>(bins, d, key, (count << 8) | edges, full); continue; }
+    }
     int r = mcx_table_add<1>(t, key, hc, hb, 0u, edges, count, may_saturate != 0);
     n_novel += (r == 1); full |= (r == 2);
   }
@@ -545,14 +553,14 @@ cudaError_t mcx_launch_kmer_tuples(const McxBuildParams &p, const McxTupleBins &
   return cudaGetLastError();
 }
 
-cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint8_t *masks, uint64_t n, uint32_t k, const McxTable &t,
+cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint32_t *meta, uint64_t n, uint32_t k, const McxTable &t,
                                      uint32_t colour, int may_saturate, unsigned long long *counters, cudaStream_t st)
 {
   if(n == 0) return cudaSuccess;
-  uint64_t want = (n / MCX_HALF + MCX_THREADS) / MCX_THREADS, cap = (uint64_t)num_sms() * 4;
+  uint64_t want = (n + MCX_THREADS - 1) / MCX_THREADS, cap = (uint64_t)num_sms() * 8;
   unsigned grid = (unsigned)(want < cap ? want : cap);
-  if(k <= 31) mcx_insert_tuples_kernel<1><<<grid, MCX_THREADS, 0, st>>>(keys, masks, n, t, colour, may_saturate, counters);
-  else mcx_insert_tuples_kernel<2><<<grid, MCX_THREADS, 0, st>>>(keys, masks, n, t, colour, may_saturate, counters);
+  if(k <= 31) mcx_insert_tuples_kernel<1><<<grid, MCX_THREADS, 0, st>>>(keys, meta, n, t, colour, may_saturate, counters);
+  else mcx_insert_tuples_kernel<2><<<grid, MCX_THREADS, 0, st>>>(keys, meta, n, t, colour, may_saturate, counters);
   return cudaGetLastError();
 }
 
@@ -568,10 +576,29 @@ cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uin
 cudaError_t mcx_launch_front_flush(const McxTable &t, int may_saturate, unsigned long long *counters, cudaStream_t st)
 {
   if(!t.front_set_bits) return cudaSuccess;
-  mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, may_saturate, counters);
+  mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, McxTupleBins{nullptr, nullptr, nullptr, 0, 1, 0}, may_saturate, counters);
   cudaError_t e = cudaGetLastError();
   if(e != cudaSuccess) return e;
   return cudaMemsetAsync(t.front, 0, (4ull << t.front_set_bits) * 8u, st);
+}
+
+cudaError_t mcx_launch_front_flush_sharded(const McxTable &t, const McxTupleBins &b, int may_saturate,
+                                           unsigned long long *counters, cudaStream_t st)
+{
+  if(!t.front_set_bits) return cudaSuccess;
+  mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, b, may_saturate, counters);
+  cudaError_t e = cudaGetLastError();
+  if(e != cudaSuccess) return e;
+  return cudaMemsetAsync(t.front, 0, (4ull << t.front_set_bits) * 8u, st);
+}
+
+cudaError_t mcx_launch_build_sharded(const McxBuildParams &p, const McxTable &t, const McxTupleBins &b, cudaStream_t st)
+{
+  if(p.r_end <= p.r_begin) return cudaSuccess;
+  unsigned grid = grid_for_chunks(p, 4);
+  if(p.k <= 31) mcx_build_sharded_kernel<1><<<grid, MCX_THREADS, 0, st>>>(p, t, b);
+  else mcx_build_sharded_kernel<2><<<grid, MCX_THREADS, 0, st>>>(p, t, b);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------- tuning knobs (experiments)

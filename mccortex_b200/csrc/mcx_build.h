@@ -31,19 +31,28 @@ struct McxBuildParams {
   uint8_t *summary;     // one byte per chunk of [r_begin, r_end): carry summaries (pass 1 -> pass 2)
 };
 
+// tuples for other shards: bin d holds up to cap tuples for shard d
+//   key  : W x u64 canonical key words
+//   meta : u32 = (count << 8) | edge mask     (count 1 for a single occurrence, larger for a
+//          record aggregated in the sender's front table)
 struct McxTupleBins {
   uint64_t *keys;                // nparts * cap * W
-  uint8_t *masks;                // nparts * cap
+  uint32_t *meta;                // nparts * cap
   unsigned long long *cursor;    // nparts
   uint64_t cap;                  // tuples per destination
   uint32_t nparts;
+  uint32_t my_part;              // sharded kernels: tuples owned by my_part are inserted locally instead
 };
 
 cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
 cudaError_t mcx_launch_build_fused_qual(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
 cudaError_t mcx_launch_kmer_tuples(const McxBuildParams &p, const McxTupleBins &b, cudaStream_t st);
-cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint8_t *masks, uint64_t n, uint32_t k, const McxTable &t,
+cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint32_t *meta, uint64_t n, uint32_t k, const McxTable &t,
                                      uint32_t colour, int may_saturate, unsigned long long *counters, cudaStream_t st);
+// sharded build: fused local front table, big-table inserts for owned keys, tuples for the rest
+cudaError_t mcx_launch_build_sharded(const McxBuildParams &p, const McxTable &t, const McxTupleBins &b, cudaStream_t st);
+cudaError_t mcx_launch_front_flush_sharded(const McxTable &t, const McxTupleBins &b, int may_saturate,
+                                           unsigned long long *counters, cudaStream_t st);
 cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uint64_t nreads, uint8_t *dst, cudaStream_t st);
 
 cudaError_t mcx_launch_front_flush(const McxTable &t, int may_saturate, unsigned long long *counters, cudaStream_t st);

@@ -1,10 +1,13 @@
 """Multi-GPU plumbing for the build path: one process per GPU, one table shard per process.
 
-Per batch: kernel B (`mcx_kmer_tuples`) turns the local reads into canonical
-(key, edge-mask) tuples binned by owner = top bits of the Lookup3 hash; the bins are exchanged
-(one all-to-all step: a count matrix, then point-to-point sends of the ragged bins, NCCL over
-NVLink on the GPUs / gloo in the CPU tests); kernel C (`mcx_graph_insert_tuples`) inserts what
-arrived into the local shard.  No remote atomics, no other collective on the data path.
+Ownership = top bits of the Lookup3 hash.  Per batch the sharded kernel
+(`mcx_graph_add_reads_sharded`) counts hot k-mers in the LOCAL L2-resident front table whoever
+owns them, inserts what it owns into its big table, and bins the rest as (key, count<<8|edges)
+tuples; the bins are exchanged (one all-to-all step: a count matrix, then point-to-point sends of
+the ragged bins, NCCL over NVLink on the GPUs / gloo in the CPU tests); kernel C
+(`mcx_graph_insert_tuples`) inserts what arrived.  At the end of a step the front tables are
+flushed the same way, one aggregated tuple per k-mer.  No remote atomics, no other collective
+on the data path.
 
 `exchange_bins` is backend-agnostic so the host-side logic is covered by world_size-2 gloo tests
 on CPU tensors (tests/test_multi_cpu.py).
@@ -59,20 +62,17 @@ class ShardedBuilder:
         self.g = M.Graph(k, 1, capacity_per_shard, device=device.index)
         n = world * cap_per_part
         self.keys = torch.empty(n * self.W, dtype=torch.int64, device=device)
-        self.masks = torch.empty(n, dtype=torch.uint8, device=device)
+        self.masks = torch.empty(n, dtype=torch.int32, device=device)   # meta = count << 8 | edge mask
         self.rkeys = torch.empty(n * self.W, dtype=torch.int64, device=device)
-        self.rmasks = torch.empty(n, dtype=torch.uint8, device=device)
+        self.rmasks = torch.empty(n, dtype=torch.int32, device=device)
         self.counts = torch.zeros(world, dtype=torch.int64, device=device)
         self.launches = 0
 
     def set_stream(self, stream):
         self.g.set_stream(stream.cuda_stream)
 
-    def add_batch(self, seq_addr, nbytes):
-        import torch
+    def _exchange_and_insert(self):
         g, W, cap, world = self.g, self.W, self.cap, self.world
-        g.kmer_tuples(seq_addr, nbytes, world, cap, self.keys.data_ptr(), self.masks.data_ptr(), self.counts.data_ptr())
-        self.launches += 1
         recv = exchange_counts(self.dist, self.counts)
         ch, rh = self.counts.tolist(), recv.tolist()
         if max(ch) > cap:
@@ -83,6 +83,26 @@ class ShardedBuilder:
                 g.insert_tuples(self.rkeys[s * cap * W:].data_ptr(), self.rmasks[s * cap:].data_ptr(), rh[s])
                 self.launches += 1
         return sum(ch)
+
+    def add_batch(self, seq_addr, nbytes, aggregate=True):
+        """one batch of local reads; aggregate=False is the unaggregated baseline (kernel B: every
+        occurrence leaves as a tuple)"""
+        g = self.g
+        if aggregate:
+            g.add_reads_sharded(seq_addr, nbytes, self.world, self.rank, self.cap, self.keys.data_ptr(),
+                                self.masks.data_ptr(), self.counts.data_ptr())
+        else:
+            g.kmer_tuples(seq_addr, nbytes, self.world, self.cap, self.keys.data_ptr(), self.masks.data_ptr(),
+                          self.counts.data_ptr())
+        self.launches += 1
+        return self._exchange_and_insert()
+
+    def flush(self):
+        """end of a step: forward the aggregated front-table records of keys owned elsewhere"""
+        self.g.flush_sharded(self.world, self.rank, self.cap, self.keys.data_ptr(), self.masks.data_ptr(),
+                             self.counts.data_ptr())
+        self.launches += 1
+        return self._exchange_and_insert()
 
 
 def bench_multi(args, rank, world, local, dist):
@@ -105,23 +125,64 @@ def bench_multi(args, rank, world, local, dist):
     dseq = torch.empty(nbytes + 4096, dtype=torch.uint8, device=dev)
     dseq[:nbytes].copy_(torch.frombuffer((C.c_uint8 * nbytes).from_address(host), dtype=torch.uint8))
     torch.cuda.synchronize()
-    M.host_free(host)
+    hview = torch.frombuffer((C.c_uint8 * nbytes).from_address(host), dtype=torch.uint8)  # pinned (cudaHostAlloc)
 
     occ_per_rank = R * (B.READ_LEN - B.K + 1)
     distinct_est = int(B.GENOME + world * R * B.READ_LEN * B.P_ERR * B.K * 1.05)
     cap_shard = int(distinct_est / world / 0.75 * 1.05)
-    cap_part = int(batch_reads * (B.READ_LEN - B.K + 1) / world * 1.25) + 4096
+    # bins: the unaggregated baseline ships every occurrence; the aggregated path ships what the
+    # front table cannot absorb (sized generously: a quarter of the occurrences) and, at the
+    # flush, at most one tuple per front-table slot (8.4 M)
+    per_peer = batch_reads * (B.READ_LEN - B.K + 1) / world
+    aggregate_env = os.environ.get("MCX_MULTI_AGGREGATE", "1") != "0"
+    cap_part = int(max(per_peer * (0.3 if aggregate_env else 1.25), (10 << 20) / max(1, world - 1) * 1.3)) + 4096
     sb = ShardedBuilder(M, dist, rank, world, dev, B.K, cap_shard, cap_part)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     sb.set_stream(stream)
+
+    aggregate = os.environ.get("MCX_MULTI_AGGREGATE", "1") != "0"
 
     def step():
         sb.g.clear()
         for b in range(nb):
             lo = b * batch_reads
             n = min(batch_reads, R - lo)
-            sb.add_batch(dseq.data_ptr() + lo * stride, n * stride)
+            sb.add_batch(dseq.data_ptr() + lo * stride, n * stride, aggregate=aggregate)
+        if aggregate:
+            sb.flush()
+
+    # e2e: the same step fed from the PINNED HOST buffer: H2D of every batch inside the timed region
+    # (double-buffered on a copy stream so batch b+1 uploads while batch b is processed), and the
+    # counters are read back to the host at the end of every step
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [torch.empty(batch_reads * stride + 4096, dtype=torch.uint8, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(b):
+        lo = b * batch_reads
+        n = min(batch_reads, R - lo)
+        s = b % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            stage[s][:n * stride].copy_(hview[lo * stride:(lo + n) * stride], non_blocking=True)
+            ready[s].record(copy_stream)
+        return n
+
+    def step_host():
+        sb.g.clear()
+        n = upload(0)
+        for b in range(nb):
+            s = b % 2
+            stream.wait_event(ready[s])
+            n_next = upload(b + 1) if b + 1 < nb else 0
+            sb.add_batch(stage[s].data_ptr(), n * stride, aggregate=aggregate)
+            freed[s].record(stream)
+            n = n_next
+        if aggregate:
+            sb.flush()
+        return sb.g.sync()
 
     for _ in range(args.warmup):
         step()
@@ -144,6 +205,26 @@ def bench_multi(args, rank, world, local, dist):
     st = sb.g.sync()
     tot = torch.tensor([st.num_kmers_loaded, st.num_kmers_novel, sb.launches], dtype=torch.int64, device=dev)
     dist.all_reduce(tot)
+
+    e_steps = max(1, min(args.steps, 3))
+    step_host()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        st_h = step_host()
+    ee1.record(stream)
+    torch.cuda.synchronize()
+    e_wall = time.perf_counter() - t0
+    dist.barrier()
+    e_ms = torch.tensor([max(ee0.elapsed_time(ee1), e_wall * 1e3)], device=dev)
+    dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e_tot = torch.tensor([st_h.num_kmers_loaded], dtype=torch.int64, device=dev)
+    dist.all_reduce(e_tot)
+    assert int(e_tot[0]) == occ_per_rank * world
+    e2e_val = occ_per_rank * world * e_steps / (float(e_ms[0]) * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
     assert int(tot[0]) == occ_per_rank * world, (int(tot[0]), occ_per_rank * world)
     ms_total = float(ms[0])
@@ -157,16 +238,19 @@ def bench_multi(args, rank, world, local, dist):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": B.workload_config(args, world),
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "mcx_kmer_tuples + mcx_insert_tuples (per GPU)",
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "mcx_build_sharded_kernel + mcx_insert_tuples_kernel (per GPU)",
                          "alg_bytes_per_kmer": B.B_ALG_MULTI},
             "cpu_baseline": None,
-            "e2e": {"value": None, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "note": "multi-GPU e2e (host buffers) not measured this round"},
+            "e2e": {"value": e2e_val, "unit": "k-mers/s", "h2d_bytes_per_step": nbytes * world,
+                    "d2h_bytes_per_step": (64 + 72) * world, "steps": e_steps, "ms_per_step": float(e_ms[0]) / e_steps},
             "gpu_launches": int(tot[2]),
             "clocks": clocks,
-            "extra": {"distinct_kmers_total": int(tot[1]), "shard_slots": cap_shard, "batches_per_step": nb},
+            "extra": {"distinct_kmers_total": int(tot[1]), "shard_slots": cap_shard, "batches_per_step": nb,
+                      "exchange": "front-table aggregated" if aggregate else "every occurrence (baseline)"},
         }
         print(json.dumps(line), flush=True)
     sb.g.close()
+    M.host_free(host)
     dist.barrier()
     dist.destroy_process_group()

@@ -166,35 +166,112 @@ def test_large_host_batch_crosses_staging_pieces(M, oracle):
     g.close()
 
 
+def _to_dev(torch, blob, dev):
+    seq = torch.zeros(len(blob) + 64, dtype=torch.uint8, device=dev)
+    seq[:len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+    return seq
+
+
 def test_tuple_path_matches_fused_path(M, oracle, reads_small):
-    """kernel B (reads -> binned tuples) + kernel C (insert) == kernel A, and bins respect ownership"""
+    """kernel B (reads -> binned tuples, count 1 each) + kernel C (insert) == kernel A, and bins respect ownership"""
     import torch
     k, nparts = 31, 4
     blob = "".join(r + "\n" for r in reads_small).encode()
     recs, ost = oracle_records(oracle, reads_small, k)
     dev = torch.device("cuda:0")
-    seq = torch.zeros(len(blob) + 64, dtype=torch.uint8, device=dev)
-    seq[:len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+    seq = _to_dev(torch, blob, dev)
     cap = ost.num_kmers_loaded + 16
     keys = torch.zeros(nparts * cap, dtype=torch.int64, device=dev)
-    masks = torch.zeros(nparts * cap, dtype=torch.uint8, device=dev)
+    meta = torch.zeros(nparts * cap, dtype=torch.int32, device=dev)
     counts = torch.zeros(nparts, dtype=torch.int64, device=dev)
     g = M.Graph(k, 1, 1 << 20)
-    g.kmer_tuples(seq.data_ptr(), len(blob), nparts, cap, keys.data_ptr(), masks.data_ptr(), counts.data_ptr())
+    g.kmer_tuples(seq.data_ptr(), len(blob), nparts, cap, keys.data_ptr(), meta.data_ptr(), counts.data_ptr())
     st = g.sync()
     assert st.num_kmers_loaded == ost.num_kmers_loaded and st.contigs_parsed == ost.contigs_parsed
     cnt = counts.cpu().tolist()
     assert sum(cnt) == ost.num_kmers_loaded
     for d in range(nparts):
         kd = keys[d * cap: d * cap + cnt[d]].cpu().tolist()
+        md = meta[d * cap: d * cap + cnt[d]].cpu().tolist()
+        assert all((m >> 8) == 1 for m in md)
         for x in kd[:50]:
             assert M.key_owner([x & 0xFFFFFFFFFFFFFFFF], k, nparts) == d
-        g.insert_tuples(keys[d * cap:].data_ptr(), masks[d * cap:].data_ptr(), cnt[d])
+        g.insert_tuples(keys[d * cap:].data_ptr(), meta[d * cap:].data_ptr(), cnt[d])
     st2 = g.sync()
     assert st2.num_kmers_novel == ost.num_kmers_novel
     got, _, _ = g.export_records()
     assert got == recs
     g.close()
+
+
+@pytest.mark.parametrize("k,nparts", [(31, 2), (31, 3), (63, 2), (21, 4)])
+def test_sharded_build_on_one_device(M, oracle, k, nparts):
+    """the multi-GPU algorithm with all shards on cuda:0: each shard runs the sharded kernel on its
+    slice of the reads (local front-table aggregation + owner routing), bins are handed over by
+    pointer, front tables are flushed, and the UNION of the shards' sorted records must equal the
+    oracle's sorted records; every shard holds only keys it owns"""
+    import torch
+    rng = random.Random(31 * nparts + k)
+    # high multiplicity (hot k-mers absorbed by the front tables) + errors (cold path)
+    base = rand_reads(rng, 1500, 150, 8000, perr=0.004, pN=0.001, lower=0.02) + ["A" * 150] * 300
+    rng.shuffle(base)
+    recs, ost = oracle_records(oracle, base, k, capacity=1 << 22)
+    dev = torch.device("cuda:0")
+    W = (k + 31) // 32
+    shards = [M.Graph(k, 1, 1 << 20) for _ in range(nparts)]
+    cap = ost.num_kmers_loaded + 1024
+    bins = []
+    for p in range(nparts):
+        mine = base[p::nparts]
+        blob = "".join(r + "\n" for r in mine).encode()
+        seq = _to_dev(torch, blob, dev)
+        half = (len(mine) // 2)
+        cut = len("".join(r + "\n" for r in mine[:half]))
+        keys = torch.zeros(nparts * cap * W, dtype=torch.int64, device=dev)
+        meta = torch.zeros(nparts * cap, dtype=torch.int32, device=dev)
+        counts = torch.zeros(nparts, dtype=torch.int64, device=dev)
+        # two batches per shard (cut at a read boundary; the device pointer must stay 16-byte aligned)
+        cut -= cut % 16
+        while blob[cut - 1:cut] != b"\n":
+            cut -= 16
+            assert cut > 0
+        for lo, hi in ((0, cut), (cut, len(blob))):
+            shards[p].add_reads_sharded(seq.data_ptr() + lo, hi - lo, nparts, p, cap, keys.data_ptr(), meta.data_ptr(),
+                                        counts.data_ptr())
+            torch.cuda.synchronize()
+            cnt = counts.cpu().tolist()
+            assert cnt[p] == 0
+            for d in range(nparts):
+                if cnt[d]:
+                    shards[d].insert_tuples(keys[d * cap * W:].data_ptr(), meta[d * cap:].data_ptr(), cnt[d])
+            torch.cuda.synchronize()
+        bins.append((keys, meta, counts, seq))
+    for p in range(nparts):
+        keys, meta, counts, _ = bins[p]
+        shards[p].flush_sharded(nparts, p, cap, keys.data_ptr(), meta.data_ptr(), counts.data_ptr())
+        torch.cuda.synchronize()
+        cnt = counts.cpu().tolist()
+        for d in range(nparts):
+            if cnt[d]:
+                shards[d].insert_tuples(keys[d * cap * W:].data_ptr(), meta[d * cap:].data_ptr(), cnt[d])
+        torch.cuda.synchronize()
+    rb = 8 * W + 5
+    allrecs, loaded, novel = [], 0, 0
+    for p in range(nparts):
+        st = shards[p].sync()
+        loaded += st.num_kmers_loaded
+        novel += st.num_kmers_novel
+        got, n, _ = shards[p].export_records()
+        for i in range(0, len(got), rb):
+            key = [int.from_bytes(got[i + 8 * w:i + 8 * w + 8], "little") for w in range(W)]
+            assert M.key_owner(key, k, nparts) == p
+            allrecs.append(got[i:i + rb])
+        shards[p].close()
+    assert loaded == ost.num_kmers_loaded and novel == ost.num_kmers_novel
+
+    def sort_key(r):
+        return tuple(int.from_bytes(r[8 * w:8 * w + 8], "little") for w in range(W))
+    assert b"".join(sorted(allrecs, key=sort_key)) == recs
 
 
 def _rand_quals(rng, reads, cut, eqp, lo=35, hi=74):
