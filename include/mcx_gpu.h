@@ -114,6 +114,11 @@ int mcx_graph_add_str(mcx_graph *g, uint32_t colour, const char *seq, size_t len
  * previous sync (the reference merges per-thread stats the same way,
  * src/tools/build_graph.c:285-288).  Returns MCX_ERR_TABLE_FULL if any insert overflowed. */
 int mcx_graph_sync(mcx_graph *g, mcx_load_stats *stats);
+/* queue (asynchronously, on the graph's stream) the merge of everything the L2-resident front
+ * table has aggregated into the big table; mcx_graph_sync / export do this implicitly.  After it
+ * completes the big table alone holds the graph, as the reference's hash table does after
+ * build_graph() returns (src/tools/build_graph.c:283-300). */
+int mcx_graph_flush(mcx_graph *g);
 
 /* replaces hash_table_print_stats inputs (src/graph/hash_table.h:73): occupancy */
 int mcx_graph_stats(mcx_graph *g, uint64_t *nkmers, uint64_t *capacity);

@@ -79,6 +79,7 @@ def lib():
     L.mcx_graph_add_reads.argtypes = [vp, C.POINTER(ReadBatch)]
     L.mcx_graph_add_str.argtypes = [vp, u32, C.c_char_p, C.c_size_t]
     L.mcx_graph_sync.argtypes = [vp, C.POINTER(LoadStats)]
+    L.mcx_graph_flush.argtypes = [vp]
     L.mcx_graph_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.mcx_graph_export_begin.argtypes = [vp, C.c_int, C.POINTER(u64), C.POINTER(u32)]
     L.mcx_graph_export_read.argtypes = [vp, u64, u64, vp]
@@ -201,6 +202,9 @@ class Graph:
         st = LoadStats()
         _ck(lib().mcx_graph_sync(self.h, C.byref(st)), "mcx_graph_sync")
         return st
+
+    def flush(self):
+        _ck(lib().mcx_graph_flush(self.h), "mcx_graph_flush")
 
     def stats(self):
         n, cap = C.c_uint64(), C.c_uint64()

@@ -393,6 +393,15 @@ extern "C" int mcx_graph_sync(mcx_graph *g, mcx_load_stats *stats)
   return MCX_OK;
 }
 
+extern "C" int mcx_graph_flush(mcx_graph *g)
+{
+  if(!g) return MCX_ERR_BAD_ARG;
+  if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must be used on a sharded graph"); return MCX_ERR_BAD_ARG; }
+  CU(cudaSetDevice(g->device));
+  CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+  return MCX_OK;
+}
+
 extern "C" int mcx_graph_stats(mcx_graph *g, uint64_t *nkmers, uint64_t *capacity)
 {
   if(!g) return MCX_ERR_BAD_ARG;
