@@ -153,6 +153,29 @@ int mcx_graph_flush_sharded(mcx_graph *g, uint32_t nparts, uint32_t my_part, uin
                             uint64_t *keys_out, uint32_t *meta_out, uint64_t *counts_out);
 /* Kernel C: insert n received tuples (device pointers) into this shard. */
 int mcx_graph_insert_tuples(mcx_graph *g, const uint64_t *keys, const uint32_t *meta, uint64_t n, uint32_t colour);
+/* same, with the tuple count in DEVICE memory (min(*n_dev, n_max) tuples are inserted): the count a
+ * sender wrote travels on the stream, the host never waits for it */
+int mcx_graph_insert_tuples_n(mcx_graph *g, const uint64_t *keys, const uint32_t *meta, const uint64_t *n_dev,
+                              uint64_t n_max, uint32_t colour);
+
+/* Routed variants: ONE kernel does the compute step and the all-to-all.  keys_dst[d] / meta_dst[d]
+ * (host arrays of nparts device pointers; entry my_part is ignored) are where tuples for shard d
+ * are appended: normally memory of GPU d mapped into this process (mcx_ipc_open), so the kernel's
+ * stores cross NVLink while it is still hashing the rest of the batch, and no copy or collective
+ * follows -- only the nparts counters (counts_out, local) are exchanged afterwards.  Each sender
+ * owns its own region on the destination (cap_per_part tuples), so there are no remote atomics. */
+int mcx_graph_add_reads_routed(mcx_graph *g, const mcx_read_batch *batch, uint32_t nparts, uint32_t my_part,
+                               uint64_t cap_per_part, uint64_t *const *keys_dst, uint32_t *const *meta_dst,
+                               uint64_t *counts_out);
+int mcx_graph_flush_routed(mcx_graph *g, uint32_t nparts, uint32_t my_part, uint64_t cap_per_part,
+                           uint64_t *const *keys_dst, uint32_t *const *meta_dst, uint64_t *counts_out);
+/* device buffers a peer process can map: cudaMalloc'ed (zeroed) memory, its 64-byte CUDA IPC handle,
+ * and the peer side (opens with lazy peer access: NVLink P2P between the GPUs of one box) */
+int mcx_device_alloc(int device, size_t bytes, void **dptr);
+int mcx_device_free(int device, void *dptr);
+int mcx_ipc_export(const void *dptr, unsigned char handle[64]);
+int mcx_ipc_open(int device, const unsigned char handle[64], void **dptr);
+int mcx_ipc_close(int device, void *dptr);
 /* Kernel B alone: reads -> one tuple per occurrence (count 1), binned by owner; nothing is
  * inserted locally.  Kept as the unaggregated baseline of the exchange and for tests. */
 int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *batch, uint32_t nparts, uint64_t cap_per_part,

@@ -88,6 +88,14 @@ def lib():
     L.mcx_graph_insert_tuples.argtypes = [vp, vp, vp, u64, u32]
     L.mcx_graph_add_reads_sharded.argtypes = [vp, C.POINTER(ReadBatch), u32, u32, u64, vp, vp, vp]
     L.mcx_graph_flush_sharded.argtypes = [vp, u32, u32, u64, vp, vp, vp]
+    L.mcx_graph_insert_tuples_n.argtypes = [vp, vp, vp, vp, u64, u32]
+    L.mcx_graph_add_reads_routed.argtypes = [vp, C.POINTER(ReadBatch), u32, u32, u64, C.POINTER(vp), C.POINTER(vp), vp]
+    L.mcx_graph_flush_routed.argtypes = [vp, u32, u32, u64, C.POINTER(vp), C.POINTER(vp), vp]
+    L.mcx_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
+    L.mcx_device_free.argtypes = [C.c_int, vp]
+    L.mcx_ipc_export.argtypes = [vp, C.c_char_p]
+    L.mcx_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.mcx_ipc_close.argtypes = [C.c_int, vp]
     L.mcx_key_owner.restype = u32
     L.mcx_key_owner.argtypes = [C.POINTER(u64), u32, u32]
     _lib = L
@@ -112,6 +120,33 @@ def host_alloc(nbytes):
 
 def host_free(addr):
     _ck(lib().mcx_host_free(C.c_void_p(addr)), "mcx_host_free")
+
+
+def device_alloc(device, nbytes):
+    """cudaMalloc'ed, zeroed device buffer (address) that a peer process can map through CUDA IPC"""
+    p = C.c_void_p()
+    _ck(lib().mcx_device_alloc(device, nbytes, C.byref(p)), "mcx_device_alloc")
+    return p.value
+
+
+def device_free(device, addr):
+    _ck(lib().mcx_device_free(device, C.c_void_p(addr)), "mcx_device_free")
+
+
+def ipc_export(addr):
+    h = C.create_string_buffer(64)
+    _ck(lib().mcx_ipc_export(C.c_void_p(addr), h), "mcx_ipc_export")
+    return h.raw
+
+
+def ipc_open(device, handle):
+    p = C.c_void_p()
+    _ck(lib().mcx_ipc_open(device, C.create_string_buffer(bytes(handle), 64), C.byref(p)), "mcx_ipc_open")
+    return p.value
+
+
+def ipc_close(device, addr):
+    _ck(lib().mcx_ipc_close(device, C.c_void_p(addr)), "mcx_ipc_close")
 
 
 def key_owner(key_words, k, nparts):
@@ -237,6 +272,25 @@ class Graph:
     def flush_sharded(self, nparts, my_part, cap_per_part, keys_addr, meta_addr, counts_addr):
         _ck(lib().mcx_graph_flush_sharded(self.h, nparts, my_part, cap_per_part, keys_addr, meta_addr, counts_addr),
             "mcx_graph_flush_sharded")
+
+    @staticmethod
+    def _ptrs(addrs):
+        return (C.c_void_p * len(addrs))(*[C.c_void_p(a or None) for a in addrs])
+
+    def add_reads_routed(self, seq_dev_addr, nbytes, nparts, my_part, cap_per_part, keys_addrs, meta_addrs, counts_addr,
+                         hp_cutoff=0, colour=0):
+        """keys_addrs / meta_addrs: one device address per destination shard (local or peer-mapped)"""
+        b = self._batch(seq_dev_addr, nbytes, MCX_LAYOUT_LINES, MCX_MEM_DEVICE, colour, hp_cutoff)
+        _ck(lib().mcx_graph_add_reads_routed(self.h, C.byref(b), nparts, my_part, cap_per_part, self._ptrs(keys_addrs),
+                                             self._ptrs(meta_addrs), counts_addr), "mcx_graph_add_reads_routed")
+
+    def flush_routed(self, nparts, my_part, cap_per_part, keys_addrs, meta_addrs, counts_addr):
+        _ck(lib().mcx_graph_flush_routed(self.h, nparts, my_part, cap_per_part, self._ptrs(keys_addrs),
+                                         self._ptrs(meta_addrs), counts_addr), "mcx_graph_flush_routed")
+
+    def insert_tuples_n(self, keys_addr, masks_addr, n_dev_addr, n_max, colour=0):
+        _ck(lib().mcx_graph_insert_tuples_n(self.h, keys_addr, masks_addr, n_dev_addr, n_max, colour),
+            "mcx_graph_insert_tuples_n")
 
     def insert_tuples(self, keys_addr, masks_addr, n, colour=0):
         _ck(lib().mcx_graph_insert_tuples(self.h, keys_addr, masks_addr, n, colour), "mcx_graph_insert_tuples")

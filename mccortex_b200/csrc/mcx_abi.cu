@@ -441,6 +441,22 @@ extern "C" int mcx_graph_export_end(mcx_graph *g)
   return MCX_OK;
 }
 
+// bins described either by one contiguous allocation (bin d at d * cap) or by one pointer per destination
+static int fill_bins(McxTupleBins *bins, uint32_t W, uint32_t nparts, uint32_t my_part, uint64_t cap,
+                     uint64_t *keys_out, uint32_t *meta_out, uint64_t *const *keys_dst, uint32_t *const *meta_dst,
+                     uint64_t *counts_out)
+{
+  if(nparts > MCX_MAX_PARTS) { snprintf(g_err, sizeof(g_err), "at most %d shards", MCX_MAX_PARTS); return MCX_ERR_UNSUPPORTED; }
+  for(uint32_t d = 0; d < MCX_MAX_PARTS; d++) { bins->keys[d] = nullptr; bins->meta[d] = nullptr; }
+  for(uint32_t d = 0; d < nparts; d++) {
+    bins->keys[d] = keys_dst ? keys_dst[d] : keys_out + (uint64_t)d * cap * W;
+    bins->meta[d] = meta_dst ? meta_dst[d] : meta_out + (uint64_t)d * cap;
+    if(d != my_part && (!bins->keys[d] || !bins->meta[d])) return MCX_ERR_BAD_ARG;
+  }
+  bins->cursor = (unsigned long long *)counts_out; bins->cap = cap; bins->nparts = nparts; bins->my_part = my_part;
+  return MCX_OK;
+}
+
 extern "C" int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *b, uint32_t nparts, uint64_t cap_per_part,
                                uint64_t *keys_out, uint32_t *masks_out, uint64_t *counts_out)
 {
@@ -451,8 +467,8 @@ extern "C" int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *b, uint32_t n
   cudaStream_t st = primary(g);
   CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
   McxTupleBins bins;
-  bins.keys = keys_out; bins.meta = masks_out; bins.cursor = (unsigned long long *)counts_out;
-  bins.cap = cap_per_part; bins.nparts = nparts; bins.my_part = 0;
+  { int r = fill_bins(&bins, g->W, nparts, UINT32_MAX, cap_per_part, keys_out, masks_out, NULL, NULL, counts_out); if(r) return r; }
+  bins.my_part = 0;
   McxBuildParams p = make_params(g, b, (const uint8_t *)b->seq, b->nbytes, 0, b->nbytes);
   CU(mcx_launch_kmer_tuples(p, bins, st));
   g->pend_positions += b->nbytes;
@@ -460,20 +476,21 @@ extern "C" int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *b, uint32_t n
 }
 
 // sharded build, per batch: local front table + local big table for owned keys + tuples for the rest
-extern "C" int mcx_graph_add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t nparts, uint32_t my_part,
-                                           uint64_t cap_per_part, uint64_t *keys_out, uint32_t *meta_out, uint64_t *counts_out)
+static int add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t nparts, uint32_t my_part, uint64_t cap_per_part,
+                             uint64_t *keys_out, uint32_t *meta_out, uint64_t *const *keys_dst, uint32_t *const *meta_dst,
+                             uint64_t *counts_out)
 {
-  if(!g || !b || nparts < 2 || my_part >= nparts || !cap_per_part || !keys_out || !meta_out || !counts_out) return MCX_ERR_BAD_ARG;
+  if(!g || !b || nparts < 2 || my_part >= nparts || !cap_per_part || !counts_out) return MCX_ERR_BAD_ARG;
+  if(!(keys_out && meta_out) && !(keys_dst && meta_dst)) return MCX_ERR_BAD_ARG;
   if(b->layout != MCX_LAYOUT_LINES || b->mem != MCX_MEM_DEVICE || ((uintptr_t)b->seq & 15u)) return MCX_ERR_BAD_ARG;
   if(b->hp_cutoff == 1 || b->hp_cutoff > g->k || (b->fq_cutoff && b->qual)) return MCX_ERR_UNSUPPORTED;
   if(b->colour >= g->ncols) return MCX_ERR_BAD_ARG;
   CU(cudaSetDevice(g->device));
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
   cudaStream_t st = primary(g);
-  CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
   McxTupleBins bins;
-  bins.keys = keys_out; bins.meta = meta_out; bins.cursor = (unsigned long long *)counts_out;
-  bins.cap = cap_per_part; bins.nparts = nparts; bins.my_part = my_part;
+  { int r = fill_bins(&bins, g->W, nparts, my_part, cap_per_part, keys_out, meta_out, keys_dst, meta_dst, counts_out); if(r) return r; }
+  CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
   g->occ_bound += b->nbytes;
   McxBuildParams p = make_params(g, b, (const uint8_t *)b->seq, b->nbytes, 0, b->nbytes);
   CU(mcx_launch_build_sharded(p, g->table, bins, st));
@@ -482,21 +499,46 @@ extern "C" int mcx_graph_add_reads_sharded(mcx_graph *g, const mcx_read_batch *b
   return MCX_OK;
 }
 
+extern "C" int mcx_graph_add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t nparts, uint32_t my_part,
+                                           uint64_t cap_per_part, uint64_t *keys_out, uint32_t *meta_out, uint64_t *counts_out)
+{
+  return add_reads_sharded(g, b, nparts, my_part, cap_per_part, keys_out, meta_out, NULL, NULL, counts_out);
+}
+
+extern "C" int mcx_graph_add_reads_routed(mcx_graph *g, const mcx_read_batch *b, uint32_t nparts, uint32_t my_part,
+                                          uint64_t cap_per_part, uint64_t *const *keys_dst, uint32_t *const *meta_dst,
+                                          uint64_t *counts_out)
+{
+  return add_reads_sharded(g, b, nparts, my_part, cap_per_part, NULL, NULL, keys_dst, meta_dst, counts_out);
+}
+
 // sharded build, end of a step: empty the front table -- owned records into the local big table,
 // the others (aggregated: one tuple per k-mer, not per occurrence) into the bins
-extern "C" int mcx_graph_flush_sharded(mcx_graph *g, uint32_t nparts, uint32_t my_part, uint64_t cap_per_part,
-                                       uint64_t *keys_out, uint32_t *meta_out, uint64_t *counts_out)
+static int flush_sharded(mcx_graph *g, uint32_t nparts, uint32_t my_part, uint64_t cap_per_part, uint64_t *keys_out,
+                         uint32_t *meta_out, uint64_t *const *keys_dst, uint32_t *const *meta_dst, uint64_t *counts_out)
 {
-  if(!g || nparts < 2 || my_part >= nparts || !cap_per_part || !keys_out || !meta_out || !counts_out) return MCX_ERR_BAD_ARG;
+  if(!g || nparts < 2 || my_part >= nparts || !cap_per_part || !counts_out) return MCX_ERR_BAD_ARG;
+  if(!(keys_out && meta_out) && !(keys_dst && meta_dst)) return MCX_ERR_BAD_ARG;
   CU(cudaSetDevice(g->device));
   cudaStream_t st = primary(g);
-  CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
   McxTupleBins bins;
-  bins.keys = keys_out; bins.meta = meta_out; bins.cursor = (unsigned long long *)counts_out;
-  bins.cap = cap_per_part; bins.nparts = nparts; bins.my_part = my_part;
+  { int r = fill_bins(&bins, g->W, nparts, my_part, cap_per_part, keys_out, meta_out, keys_dst, meta_dst, counts_out); if(r) return r; }
+  CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
   CU(mcx_launch_front_flush_sharded(g->table, bins, g->occ_bound >= 0xF0000000ull, g->d_counters, st));
   g->sharded = false;
   return MCX_OK;
+}
+
+extern "C" int mcx_graph_flush_sharded(mcx_graph *g, uint32_t nparts, uint32_t my_part, uint64_t cap_per_part,
+                                       uint64_t *keys_out, uint32_t *meta_out, uint64_t *counts_out)
+{
+  return flush_sharded(g, nparts, my_part, cap_per_part, keys_out, meta_out, NULL, NULL, counts_out);
+}
+
+extern "C" int mcx_graph_flush_routed(mcx_graph *g, uint32_t nparts, uint32_t my_part, uint64_t cap_per_part,
+                                      uint64_t *const *keys_dst, uint32_t *const *meta_dst, uint64_t *counts_out)
+{
+  return flush_sharded(g, nparts, my_part, cap_per_part, NULL, NULL, keys_dst, meta_dst, counts_out);
 }
 
 extern "C" int mcx_graph_insert_tuples(mcx_graph *g, const uint64_t *keys, const uint32_t *masks, uint64_t n, uint32_t colour)
@@ -505,8 +547,65 @@ extern "C" int mcx_graph_insert_tuples(mcx_graph *g, const uint64_t *keys, const
   CU(cudaSetDevice(g->device));
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
   g->occ_bound += n;
-  CU(mcx_launch_insert_tuples(keys, masks, n, g->k, g->table, colour, g->occ_bound >= 0xF0000000ull, g->d_counters,
+  CU(mcx_launch_insert_tuples(keys, masks, n, NULL, g->k, g->table, colour, g->occ_bound >= 0xF0000000ull, g->d_counters,
                               primary(g)));
+  return MCX_OK;
+}
+
+// same, but the number of tuples is a device word (written by the sender, exchanged on the stream):
+// nothing on this path makes the host wait for the GPU
+extern "C" int mcx_graph_insert_tuples_n(mcx_graph *g, const uint64_t *keys, const uint32_t *masks, const uint64_t *n_dev,
+                                         uint64_t n_max, uint32_t colour)
+{
+  if(!g || colour >= g->ncols || !n_dev || (n_max && (!keys || !masks))) return MCX_ERR_BAD_ARG;
+  CU(cudaSetDevice(g->device));
+  if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
+  g->occ_bound += n_max; // every tuple may carry an aggregated count: the saturation guard switches on early, never late
+  CU(mcx_launch_insert_tuples(keys, masks, n_max, n_dev, g->k, g->table, colour, g->occ_bound >= 0xF0000000ull, g->d_counters,
+                              primary(g)));
+  return MCX_OK;
+}
+
+// ---- device buffers that peers can map (one process per GPU: CUDA IPC over NVLink) ----------
+extern "C" int mcx_device_alloc(int device, size_t bytes, void **dptr)
+{
+  if(!dptr) return MCX_ERR_BAD_ARG;
+  if(mcx_device_count() == 0) return MCX_ERR_NO_DEVICE;
+  CU(cudaSetDevice(device));
+  CU(cudaMalloc(dptr, bytes ? bytes : 1));
+  CU(cudaMemset(*dptr, 0, bytes ? bytes : 1));
+  return MCX_OK;
+}
+extern "C" int mcx_device_free(int device, void *dptr)
+{
+  if(!dptr) return MCX_OK;
+  CU(cudaSetDevice(device));
+  CU(cudaFree(dptr));
+  return MCX_OK;
+}
+extern "C" int mcx_ipc_export(const void *dptr, unsigned char handle[64])
+{
+  if(!dptr || !handle) return MCX_ERR_BAD_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, (void *)dptr));
+  memcpy(handle, &h, 64);
+  return MCX_OK;
+}
+extern "C" int mcx_ipc_open(int device, const unsigned char handle[64], void **dptr)
+{
+  if(!dptr || !handle) return MCX_ERR_BAD_ARG;
+  CU(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CU(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MCX_OK;
+}
+extern "C" int mcx_ipc_close(int device, void *dptr)
+{
+  if(!dptr) return MCX_OK;
+  CU(cudaSetDevice(device));
+  CU(cudaIpcCloseMemHandle(dptr));
   return MCX_OK;
 }
 

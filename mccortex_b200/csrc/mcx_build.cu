@@ -125,10 +125,18 @@ __device__ __forceinline__ void mcx_bin_push(const McxTupleBins &b, uint32_t d, 
   base = __shfl_sync(peers, base, leader);
   uint64_t at = base + __popc(peers & ((1u << lane) - 1u));
   if(at >= b.cap) { full = 1; return; }
-  uint64_t *kd = b.keys + ((uint64_t)d * b.cap + at) * W;
+  uint64_t *kd = b.keys[d] + at * W;
 #pragma unroll
   for(int w = 0; w < W; w++) kd[w] = key.b[w];
-  b.meta[(uint64_t)d * b.cap + at] = meta;
+  b.meta[d][at] = meta;
+}
+
+static __host__ __device__ __forceinline__ McxTupleBins mcx_no_bins()
+{
+  McxTupleBins b;
+  for(int i = 0; i < MCX_MAX_PARTS; i++) { b.keys[i] = nullptr; b.meta[i] = nullptr; }
+  b.cursor = nullptr; b.cap = 0; b.nparts = 1; b.my_part = 0;
+  return b;
 }
 
 template <int W, int G> struct FusedSink { // G = probe loads kept in flight per thread
@@ -371,7 +379,7 @@ __global__ void __launch_bounds__(MCX_THREADS, MINB) mcx_build_fused_kernel(McxB
 {
   __shared__ McxSlowQueue<W> q;
   if(threadIdx.x == 0) q.n = 0;
-  FusedSink<W, G> sink{t, p.colour, p.may_saturate != 0, &q, McxTupleBins{nullptr, nullptr, nullptr, 0, 1, 0}};
+  FusedSink<W, G> sink{t, p.colour, p.may_saturate != 0, &q, mcx_no_bins()};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
 
@@ -403,7 +411,7 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_build_fused_qual_kernel(Mc
 {
   __shared__ McxSlowQueue<W> q;
   if(threadIdx.x == 0) q.n = 0;
-  FusedSink<W, 2> sink{t, p.colour, p.may_saturate != 0, &q, McxTupleBins{nullptr, nullptr, nullptr, 0, 1, 0}};
+  FusedSink<W, 2> sink{t, p.colour, p.may_saturate != 0, &q, mcx_no_bins()};
   mcx_front_end<W, MCX_MODE_QUAL>(p, sink);
 }
 
@@ -421,11 +429,13 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_kmer_tuples_kernel(McxBuil
 template <int W>
 __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_insert_tuples_kernel(const uint64_t *__restrict__ keys,
                                                                            const uint32_t *__restrict__ meta,
-                                                                           uint64_t n, McxTable t, uint32_t colour,
+                                                                           uint64_t n, const uint64_t *__restrict__ n_dev,
+                                                                           McxTable t, uint32_t colour,
                                                                            int may_saturate, unsigned long long *counters)
 {
   McxTable big = t; big.front = nullptr; big.front_set_bits = 0;
   uint64_t n_novel = 0, n_kmers = 0; uint32_t full = 0;
+  if(n_dev) { const uint64_t nd = *n_dev; if(nd < n) n = nd; } // count written by the sender (exchanged on the stream)
   for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     McxKmer<W> key;
 #pragma unroll
@@ -553,14 +563,15 @@ cudaError_t mcx_launch_kmer_tuples(const McxBuildParams &p, const McxTupleBins &
   return cudaGetLastError();
 }
 
-cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint32_t *meta, uint64_t n, uint32_t k, const McxTable &t,
-                                     uint32_t colour, int may_saturate, unsigned long long *counters, cudaStream_t st)
+cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint32_t *meta, uint64_t n, const uint64_t *n_dev, uint32_t k,
+                                     const McxTable &t, uint32_t colour, int may_saturate, unsigned long long *counters,
+                                     cudaStream_t st)
 {
   if(n == 0) return cudaSuccess;
   uint64_t want = (n + MCX_THREADS - 1) / MCX_THREADS, cap = (uint64_t)num_sms() * 8;
   unsigned grid = (unsigned)(want < cap ? want : cap);
-  if(k <= 31) mcx_insert_tuples_kernel<1><<<grid, MCX_THREADS, 0, st>>>(keys, meta, n, t, colour, may_saturate, counters);
-  else mcx_insert_tuples_kernel<2><<<grid, MCX_THREADS, 0, st>>>(keys, meta, n, t, colour, may_saturate, counters);
+  if(k <= 31) mcx_insert_tuples_kernel<1><<<grid, MCX_THREADS, 0, st>>>(keys, meta, n, n_dev, t, colour, may_saturate, counters);
+  else mcx_insert_tuples_kernel<2><<<grid, MCX_THREADS, 0, st>>>(keys, meta, n, n_dev, t, colour, may_saturate, counters);
   return cudaGetLastError();
 }
 
@@ -576,7 +587,7 @@ cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uin
 cudaError_t mcx_launch_front_flush(const McxTable &t, int may_saturate, unsigned long long *counters, cudaStream_t st)
 {
   if(!t.front_set_bits) return cudaSuccess;
-  mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, McxTupleBins{nullptr, nullptr, nullptr, 0, 1, 0}, may_saturate, counters);
+  mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, mcx_no_bins(), may_saturate, counters);
   cudaError_t e = cudaGetLastError();
   if(e != cudaSuccess) return e;
   return cudaMemsetAsync(t.front, 0, (4ull << t.front_set_bits) * 8u, st);

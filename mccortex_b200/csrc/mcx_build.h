@@ -35,10 +35,11 @@ struct McxBuildParams {
 //   key  : W x u64 canonical key words
 //   meta : u32 = (count << 8) | edge mask     (count 1 for a single occurrence, larger for a
 //          record aggregated in the sender's front table)
+#define MCX_MAX_PARTS 16
 struct McxTupleBins {
-  uint64_t *keys;                // nparts * cap * W
-  uint32_t *meta;                // nparts * cap
-  unsigned long long *cursor;    // nparts
+  uint64_t *keys[MCX_MAX_PARTS]; // bin of shard d: cap * W words.  Local memory, or memory of GPU d mapped
+  uint32_t *meta[MCX_MAX_PARTS]; // over NVLink (CUDA IPC): then the kernel's stores ARE the all-to-all
+  unsigned long long *cursor;    // nparts, local
   uint64_t cap;                  // tuples per destination
   uint32_t nparts;
   uint32_t my_part;              // sharded kernels: tuples owned by my_part are inserted locally instead
@@ -47,8 +48,10 @@ struct McxTupleBins {
 cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
 cudaError_t mcx_launch_build_fused_qual(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
 cudaError_t mcx_launch_kmer_tuples(const McxBuildParams &p, const McxTupleBins &b, cudaStream_t st);
-cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint32_t *meta, uint64_t n, uint32_t k, const McxTable &t,
-                                     uint32_t colour, int may_saturate, unsigned long long *counters, cudaStream_t st);
+// n_dev (may be NULL): device word holding the tuple count, read by the kernel (min(*n_dev, n) tuples)
+cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint32_t *meta, uint64_t n, const uint64_t *n_dev, uint32_t k,
+                                     const McxTable &t, uint32_t colour, int may_saturate, unsigned long long *counters,
+                                     cudaStream_t st);
 // sharded build: fused local front table, big-table inserts for owned keys, tuples for the rest
 cudaError_t mcx_launch_build_sharded(const McxBuildParams &p, const McxTable &t, const McxTupleBins &b, cudaStream_t st);
 cudaError_t mcx_launch_front_flush_sharded(const McxTable &t, const McxTupleBins &b, int may_saturate,

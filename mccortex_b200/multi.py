@@ -105,6 +105,150 @@ class ShardedBuilder:
         return self._exchange_and_insert()
 
 
+class RoutedBuilder:
+    """One rank's side of the sharded build with the exchange fused into the kernel.
+
+    Every rank owns two receive rings (double buffer) of `world` regions x `cap` tuples, allocated
+    by the library and mapped into every peer process through CUDA IPC.  The sharded kernel of
+    rank s appends the tuples it produces for shard d straight into region s of d's ring -- its
+    stores travel over NVLink while the kernel is still hashing -- so the only thing left to
+    exchange per batch is the `world` tuple counters (one tiny all_to_all, stream ordered: it also
+    tells the receiver that every sender's kernel, and therefore its stores, has completed).  The
+    receiver's insert kernels read their tuple count from device memory, so the host never waits
+    for the GPU inside a step.
+
+    Ring reuse: rank s writes ring j of rank d again in batch b+2; its kernel b+2 is ordered behind
+    the counter all_to_all of batch b+1, which completes only after d has entered it, i.e. after d's
+    inserts of batch b (stream order on d).  Two rings suffice.
+
+    peers: None = IPC (one process per GPU); tests pass rings of sibling builders on the same
+    device instead (see connect_local)."""
+
+    NRING = 2
+
+    def __init__(self, M, dist, rank, world, device, k, capacity_per_shard, cap_per_part, ncols=1):
+        import torch
+        self.M, self.dist, self.rank, self.world, self.dev = M, dist, rank, world, device
+        self.k, self.W, self.cap = k, (k + 31) // 32, cap_per_part
+        self.g = M.Graph(k, ncols, capacity_per_shard, device=device.index)
+        self.kbytes = world * cap_per_part * self.W * 8
+        self.mbytes = world * cap_per_part * 4
+        self.ring_k = [M.device_alloc(device.index, self.kbytes) for _ in range(self.NRING)]
+        self.ring_m = [M.device_alloc(device.index, self.mbytes) for _ in range(self.NRING)]
+        self.counts = [torch.zeros(world, dtype=torch.int64, device=device) for _ in range(self.NRING)]
+        self.rcounts = [torch.zeros(world, dtype=torch.int64, device=device) for _ in range(self.NRING)]
+        self.peer_k = self.peer_m = None   # [ring][dest] addresses of MY region on dest
+        self.opened = []
+        self.batch = 0
+        self.launches = 0
+        self.prof = None
+        self.sent = []
+
+    def set_stream(self, stream):
+        self.g.set_stream(stream.cuda_stream)
+
+    def connect_ipc(self):
+        """exchange the rings' IPC handles (all_gather) and map every peer's rings"""
+        import torch
+        M, dist, world, rank = self.M, self.dist, self.world, self.rank
+        mine = b"".join(M.ipc_export(a) for a in self.ring_k + self.ring_m)
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(self.dev)
+        allh = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allh, t)
+        bases = []
+        for d in range(world):
+            if d == rank:
+                bases.append((list(self.ring_k), list(self.ring_m)))
+                continue
+            raw = bytes(allh[d].cpu().numpy().tobytes())
+            hs = [raw[i * 64:(i + 1) * 64] for i in range(2 * self.NRING)]
+            ptrs = [M.ipc_open(self.dev.index, h) for h in hs]
+            self.opened += ptrs
+            bases.append((ptrs[:self.NRING], ptrs[self.NRING:]))
+        self._set_peers(bases)
+
+    def connect_local(self, builders):
+        """all shards in one process (tests): peers' rings are plain device pointers"""
+        self._set_peers([(list(b.ring_k), list(b.ring_m)) for b in builders])
+
+    def _set_peers(self, bases):
+        r, cap, W = self.rank, self.cap, self.W
+        self.peer_k = [[bases[d][0][j] + r * cap * W * 8 for d in range(self.world)] for j in range(self.NRING)]
+        self.peer_m = [[bases[d][1][j] + r * cap * 4 for d in range(self.world)] for j in range(self.NRING)]
+
+    # the three stages of one batch; the one-process test drives them shard by shard
+    def produce(self, seq_addr, nbytes, colour=0, hp_cutoff=0):
+        j = self.batch % self.NRING
+        self.g.add_reads_routed(seq_addr, nbytes, self.world, self.rank, self.cap, self.peer_k[j], self.peer_m[j],
+                                self.counts[j].data_ptr(), hp_cutoff=hp_cutoff, colour=colour)
+        self.launches += 1
+
+    def produce_flush(self):
+        j = self.batch % self.NRING
+        self.g.flush_routed(self.world, self.rank, self.cap, self.peer_k[j], self.peer_m[j], self.counts[j].data_ptr())
+        self.launches += 1
+
+    def exchange_counts(self):
+        j = self.batch % self.NRING
+        self.dist.all_to_all_single(self.rcounts[j], self.counts[j])
+        if self.prof is not None:
+            self.sent.append(self.counts[j].tolist())
+
+    def consume(self, colour=0):
+        j = self.batch % self.NRING
+        cap, W = self.cap, self.W
+        for s in range(self.world):
+            if s == self.rank:
+                continue
+            self.g.insert_tuples_n(self.ring_k[j] + s * cap * W * 8, self.ring_m[j] + s * cap * 4,
+                                   self.rcounts[j].data_ptr() + 8 * s, cap, colour=colour)
+            self.launches += 1
+        self.batch += 1
+
+    def _mark(self, name):
+        # optional per-stage device timing (MCX_MULTI_PROFILE=1): CUDA events on the current stream
+        if self.prof is not None:
+            import torch
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.prof.append((name, e))
+
+    def add_batch(self, seq_addr, nbytes, colour=0):
+        self._mark("start")
+        self.produce(seq_addr, nbytes, colour)
+        self._mark("produce")
+        self.exchange_counts()
+        self._mark("counts")
+        self.consume(colour)
+        self._mark("consume")
+
+    def flush(self):
+        self._mark("start")
+        self.produce_flush()
+        self._mark("flush_produce")
+        self.exchange_counts()
+        self._mark("counts")
+        self.consume()
+        self._mark("flush_consume")
+
+    def profile_summary(self):
+        tot = {}
+        for (n0, e0), (n1, e1) in zip(self.prof, self.prof[1:]):
+            if n1 != "start":
+                tot[n1] = tot.get(n1, 0.0) + e0.elapsed_time(e1)
+        return tot
+
+    def close(self):
+        M = self.M
+        self.g.close()
+        for p in self.opened:
+            M.ipc_close(self.dev.index, p)
+        self.opened = []
+        for a in self.ring_k + self.ring_m:
+            M.device_free(self.dev.index, a)
+        self.ring_k = self.ring_m = []
+
+
 def bench_multi(args, rank, world, local, dist):
     """bench.py body for N > 1 (weak scaling: args.reads reads per GPU, disjoint read index ranges
     of the same genome)."""
@@ -117,7 +261,7 @@ def bench_multi(args, rank, world, local, dist):
     R, stride = args.reads, B.READ_LEN + 1
     genome = C.create_string_buffer(B.GENOME)
     SL.mcx_synth_genome(genome, B.GENOME, 0)
-    batch_reads = min(R, 4_000_000)
+    batch_reads = min(R, int(os.environ.get("MCX_MULTI_BATCH_READS", 4_000_000)))
     nb = (R + batch_reads - 1) // batch_reads
     nbytes = R * stride
     host = M.host_alloc(nbytes + 4096)
@@ -135,20 +279,32 @@ def bench_multi(args, rank, world, local, dist):
     # flush, at most one tuple per front-table slot (8.4 M)
     per_peer = batch_reads * (B.READ_LEN - B.K + 1) / world
     aggregate_env = os.environ.get("MCX_MULTI_AGGREGATE", "1") != "0"
-    cap_part = int(max(per_peer * (0.3 if aggregate_env else 1.25), (10 << 20) / max(1, world - 1) * 1.3)) + 4096
-    sb = ShardedBuilder(M, dist, rank, world, dev, B.K, cap_shard, cap_part)
+    cap_part = int(max(per_peer * (float(os.environ.get("MCX_MULTI_BIN_FRAC", 0.3)) if aggregate_env else 1.25), (10 << 20) / max(1, world - 1) * 1.3)) + 4096
+    aggregate = aggregate_env
+    # default: the exchange is fused into the kernel (stores into the owners' rings over NVLink);
+    # MCX_MULTI_EXCHANGE=nccl keeps the bins local and moves them with NCCL send/recv (baseline)
+    routed = aggregate and os.environ.get("MCX_MULTI_EXCHANGE", "peer") != "nccl"
+    if routed:
+        sb = RoutedBuilder(M, dist, rank, world, dev, B.K, cap_shard, cap_part)
+        sb.connect_ipc()
+    else:
+        sb = ShardedBuilder(M, dist, rank, world, dev, B.K, cap_shard, cap_part)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     sb.set_stream(stream)
 
-    aggregate = os.environ.get("MCX_MULTI_AGGREGATE", "1") != "0"
+    def add(addr, nbytes_):
+        if routed:
+            sb.add_batch(addr, nbytes_)
+        else:
+            sb.add_batch(addr, nbytes_, aggregate=aggregate)
 
     def step():
         sb.g.clear()
         for b in range(nb):
             lo = b * batch_reads
             n = min(batch_reads, R - lo)
-            sb.add_batch(dseq.data_ptr() + lo * stride, n * stride, aggregate=aggregate)
+            add(dseq.data_ptr() + lo * stride, n * stride)
         if aggregate:
             sb.flush()
 
@@ -177,7 +333,7 @@ def bench_multi(args, rank, world, local, dist):
             s = b % 2
             stream.wait_event(ready[s])
             n_next = upload(b + 1) if b + 1 < nb else 0
-            sb.add_batch(stage[s].data_ptr(), n * stride, aggregate=aggregate)
+            add(stage[s].data_ptr(), n * stride)
             freed[s].record(stream)
             n = n_next
         if aggregate:
@@ -200,6 +356,15 @@ def bench_multi(args, rank, world, local, dist):
     ev1.record(stream)
     torch.cuda.synchronize()
     dist.barrier()
+    if routed and os.environ.get("MCX_MULTI_PROFILE"):
+        import sys
+        sb.prof = []
+        step()
+        torch.cuda.synchronize()
+        print("rank %d stage ms over one step: %s; tuples sent per batch (cap %d): %s" % (
+            rank, json.dumps(sb.profile_summary()), cap_part, sb.sent), file=sys.stderr, flush=True)
+        sb.prof = None
+        dist.barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     st = sb.g.sync()
@@ -240,6 +405,7 @@ def bench_multi(args, rank, world, local, dist):
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": None, "peak_source": peak_src,
                          "kernel": "mcx_build_sharded_kernel + mcx_insert_tuples_kernel (per GPU)",
+                         "note": "achieved = value x 43.25 B / n_gpus; almost all occurrences are absorbed by the local front table and never become tuples",
                          "alg_bytes_per_kmer": B.B_ALG_MULTI},
             "cpu_baseline": None,
             "e2e": {"value": e2e_val, "unit": "k-mers/s", "h2d_bytes_per_step": nbytes * world,
@@ -247,10 +413,17 @@ def bench_multi(args, rank, world, local, dist):
             "gpu_launches": int(tot[2]),
             "clocks": clocks,
             "extra": {"distinct_kmers_total": int(tot[1]), "shard_slots": cap_shard, "batches_per_step": nb,
-                      "exchange": "front-table aggregated" if aggregate else "every occurrence (baseline)"},
+                      "exchange": ("fused into the kernel: peer stores over NVLink (CUDA IPC rings), counters all_to_all"
+                                   if routed else "NCCL send/recv of local bins") +
+                                  (", front-table aggregated" if aggregate else ", every occurrence (baseline)")},
         }
         print(json.dumps(line), flush=True)
-    sb.g.close()
+    torch.cuda.synchronize()
+    dist.barrier()
+    if routed:
+        sb.close()
+    else:
+        sb.g.close()
     M.host_free(host)
     dist.barrier()
     dist.destroy_process_group()

@@ -274,6 +274,72 @@ def test_sharded_build_on_one_device(M, oracle, k, nparts):
     assert b"".join(sorted(allrecs, key=sort_key)) == recs
 
 
+@pytest.mark.parametrize("k,nparts", [(31, 2), (31, 4), (63, 3)])
+def test_routed_build_on_one_device(M, oracle, k, nparts):
+    """the fused compute+exchange path (RoutedBuilder: the sharded kernel appends tuples straight into
+    the OWNER's receive ring, the insert kernel reads its count from device memory) with all shards on
+    cuda:0 -- rings are handed over as plain pointers instead of CUDA IPC mappings, the counter
+    all_to_all is a transpose.  Union of the shards' records == oracle, every shard holds only its keys."""
+    import torch
+    from mccortex_b200.multi import RoutedBuilder
+    rng = random.Random(77 * nparts + k)
+    base = rand_reads(rng, 1800, 150, 9000, perr=0.004, pN=0.001, lower=0.02) + ["C" * 150] * 200
+    rng.shuffle(base)
+    recs, ost = oracle_records(oracle, base, k, capacity=1 << 22)
+    dev = torch.device("cuda:0")
+    W = (k + 31) // 32
+    cap = ost.num_kmers_loaded + 1024
+    sbs = [RoutedBuilder(M, None, p, nparts, dev, k, 1 << 20, cap) for p in range(nparts)]
+    for sb in sbs:
+        sb.connect_local(sbs)
+
+    def exchange():
+        torch.cuda.synchronize()
+        j = sbs[0].batch % RoutedBuilder.NRING
+        for d in range(nparts):
+            for s_ in range(nparts):
+                sbs[d].rcounts[j][s_] = sbs[s_].counts[j][d]
+        torch.cuda.synchronize()
+
+    seqs = []
+    for p in range(nparts):
+        mine = base[p::nparts]
+        third = len(mine) // 3
+        parts = [mine[:third], mine[third:2 * third], mine[2 * third:]]   # three batches: ring reuse
+        blobs = ["".join(r + "\n" for r in part).encode() for part in parts]
+        seqs.append([(_to_dev(torch, b_, dev), len(b_)) for b_ in blobs])
+    for b in range(3):
+        for p in range(nparts):
+            t, n = seqs[p][b]
+            sbs[p].produce(t.data_ptr(), n)
+        exchange()
+        for p in range(nparts):
+            sbs[p].consume()
+    for p in range(nparts):
+        sbs[p].produce_flush()
+    exchange()
+    for p in range(nparts):
+        sbs[p].consume()
+    torch.cuda.synchronize()
+    rb = 8 * W + 5
+    allrecs, loaded, novel = [], 0, 0
+    for p in range(nparts):
+        st = sbs[p].g.sync()
+        loaded += st.num_kmers_loaded
+        novel += st.num_kmers_novel
+        got, n, _ = sbs[p].g.export_records()
+        for i in range(0, len(got), rb):
+            key = [int.from_bytes(got[i + 8 * w:i + 8 * w + 8], "little") for w in range(W)]
+            assert M.key_owner(key, k, nparts) == p
+            allrecs.append(got[i:i + rb])
+        sbs[p].close()
+    assert loaded == ost.num_kmers_loaded and novel == ost.num_kmers_novel
+
+    def sort_key(r):
+        return tuple(int.from_bytes(r[8 * w:8 * w + 8], "little") for w in range(W))
+    assert b"".join(sorted(allrecs, key=sort_key)) == recs
+
+
 def _rand_quals(rng, reads, cut, eqp, lo=35, hi=74):
     quals = ["".join(chr(cut) if rng.random() < eqp else chr(rng.randint(lo, hi)) for _ in r) for r in reads]
     for i in range(0, len(reads), 7):

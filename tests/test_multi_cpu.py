@@ -82,3 +82,85 @@ def test_bin_exchange_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _routed_worker(rank, world, port, q):
+    """RoutedBuilder host logic without a GPU: ring addressing (every sender owns region `rank` of the
+    destination's ring) and the counter all_to_all, with the library calls replaced by recorders."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from mccortex_b200.multi import RoutedBuilder
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        calls = []
+
+        class FakeGraph:
+            def __init__(self, *a, **kw): pass
+            def add_reads_routed(self, seq, nbytes, nparts, my_part, cap, kptrs, mptrs, counts, hp_cutoff=0, colour=0):
+                calls.append(("produce", list(kptrs), list(mptrs)))
+            def flush_routed(self, nparts, my_part, cap, kptrs, mptrs, counts):
+                calls.append(("flush", list(kptrs), list(mptrs)))
+            def insert_tuples_n(self, keys, meta, n_dev, n_max, colour=0):
+                calls.append(("insert", keys, meta, n_dev, n_max))
+            def close(self): pass
+
+        class FakeM:
+            Graph = FakeGraph
+            _next = [1 << 40]
+            @staticmethod
+            def device_alloc(dev, nbytes):
+                a = FakeM._next[0] + (rank << 36)
+                FakeM._next[0] += (nbytes + 255) // 256 * 256
+                return a
+            @staticmethod
+            def device_free(dev, a): pass
+
+        class Dev:
+            index = 0
+        k, W, cap = 63, 2, 1000
+        sb = RoutedBuilder(FakeM, dist, rank, world, torch.device("cpu"), k, 1 << 20, cap)
+        # exchange ring bases the way connect_ipc does, but as plain integers
+        mine = torch.tensor(sb.ring_k + sb.ring_m, dtype=torch.int64)
+        allb = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allb, mine)
+        bases = [(b[:2].tolist(), b[2:].tolist()) for b in allb]
+        sb._set_peers(bases)
+        for j in range(2):
+            for d in range(world):
+                assert sb.peer_k[j][d] == bases[d][0][j] + rank * cap * W * 8
+                assert sb.peer_m[j][d] == bases[d][1][j] + rank * cap * 4
+        for b in range(3):
+            j = b % 2
+            sb.counts[j][:] = torch.tensor([100 * rank + d + b for d in range(world)])
+            sb.produce(0, 0)
+            sb.exchange_counts()
+            assert sb.rcounts[j].tolist() == [100 * s + rank + b for s in range(world)]
+            sb.consume()
+            ins = [c for c in calls if c[0] == "insert"][-(world - 1):]
+            srcs = [s for s in range(world) if s != rank]
+            for c, s in zip(ins, srcs):
+                assert c[1] == sb.ring_k[j] + s * cap * W * 8 and c[2] == sb.ring_m[j] + s * cap * 4
+                assert c[3] == sb.rcounts[j].data_ptr() + 8 * s and c[4] == cap
+        assert sb.batch == 3
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: %r %s" % (e, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_routed_builder_host_logic_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_routed_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
