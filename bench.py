@@ -343,13 +343,15 @@ def own_arm(args):
         "config": workload_config(args, 1),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "mcx_build_fused_kernel<1>", "kernel_ms": kernel_ms,
+                     "kernel": "mcx_build_fused_kernel<1,3,2>", "kernel_ms": kernel_ms,
                      "alg_bytes_per_kmer": B_ALG, "kmers_per_launch": occ_per_step,
                      "traffic_note": (tr or {}).get("note")},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": "k-mers/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 64 + 72,
                 "steps": e_steps, "ms_per_step": 1e3 * max(e2e_ms * 1e-3, e2e_wall) / e_steps},
-        "gpu_launches": 2 * args.steps,  # mcx_build_fused_kernel + mcx_front_flush_kernel per step in the `value` region
+        # per step in the `value` region: one mcx_build_fused_kernel per span of <= 0xEF000000 positions (the front
+        # table's 32-bit counters are merged into the big table between spans) + as many mcx_front_flush_kernel
+        "gpu_launches": 2 * args.steps * (-(-nbytes // 0xEF000000)),
         "clocks": clocks,
         "extra": {"distinct_kmers": distinct, "table_slots": capacity, "host_gen_s": t_gen,
                   "sorted_export_s": t_export, "export_records": int(nrec.value)},

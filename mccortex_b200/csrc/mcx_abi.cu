@@ -45,6 +45,8 @@ struct mcx_graph {
   uint64_t nkmers;         // slots claimed so far (updated at sync)
   McxExport exp; bool exp_valid;
   uint8_t *d_tmp; size_t d_tmp_bytes; // scratch for OFFSETS -> LINES repack
+  size_t persist_bytes;    // experiment: L2 persisting window over the front table
+  uint64_t front_pending;  // positions queued since the front table was last flushed (its counters are 32-bit)
   bool sharded;  // front table holds records of keys owned by other shards: only mcx_graph_flush_sharded may empty it
 };
 
@@ -69,6 +71,19 @@ extern "C" int mcx_host_free(void *ptr) { if(ptr) CU(cudaFreeHost(ptr)); return 
 // host-staging path fans out to the ring streams and joins back (event fork/join), so
 // events recorded on the primary stream bracket everything a call enqueued.
 static cudaStream_t primary(mcx_graph *g) { return g->use_user_stream ? g->user_stream : g->own_primary; }
+static void apply_persist(mcx_graph *g, cudaStream_t st)
+{
+  if(!g->persist_bytes || !g->table.front) return;
+  cudaStreamAttrValue a; memset(&a, 0, sizeof(a));
+  a.accessPolicyWindow.base_ptr = g->table.front;
+  size_t bytes = (4ull << g->table.front_set_bits) * 12u;
+  a.accessPolicyWindow.num_bytes = bytes;
+  a.accessPolicyWindow.hitRatio = g->persist_bytes >= bytes ? 1.0f : (float)g->persist_bytes / (float)bytes;
+  a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a);
+  cudaGetLastError();
+}
 
 extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, int device, uint32_t flags, mcx_graph **out)
 {
@@ -106,18 +121,29 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
     uint32_t bits = 21;
     if(const char *m = getenv("MCX_FRONT_BITS")) bits = (uint32_t)atoi(m);
     if(bits) {
-      if(bits < 18) bits = 18; // count field must keep >= 12 bits
+      if(bits < 16) bits = 16;
       if(bits > 24) bits = 24;
       g->table.front_set_bits = bits;
-      e = cudaMalloc(&g->table.front, (4ull << bits) * 8u);
+      // one allocation: (4 << bits) 8-byte tags, then (4 << bits) 4-byte counters
+      e = cudaMalloc(&g->table.front, (4ull << bits) * 12u);
       if(e != cudaSuccess) { g->table.front_set_bits = 0; int r = fail_cuda(e, "cudaMalloc(front)"); mcx_graph_destroy(g); return r; }
-      cudaMemset(g->table.front, 0, (4ull << bits) * 8u);
+      g->table.front_cnt = reinterpret_cast<unsigned int *>(g->table.front + (4ull << bits));
+      cudaMemset(g->table.front, 0, (4ull << bits) * 12u);
     }
   }
   // experiment knobs (see profiles/): probe-load flavour and L2 fetch granularity
   if(const char *m = getenv("MCX_MINB")) mcx_set_minb(atoi(m));
   if(const char *m = getenv("MCX_G")) mcx_set_inflight(atoi(m));
+  if(const char *m = getenv("MCX_L2_HINTS")) mcx_set_hints((uint32_t)atoi(m));
+  if(const char *m = getenv("MCX_L2_PERSIST_MB")) {
+    // experiment: pin the front table with the L2 persistence controls
+    size_t want = (size_t)atoi(m) << 20;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    g->persist_bytes = want;
+  }
   if(const char *m = getenv("MCX_L2FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(m));
+  apply_persist(g, g->own_primary);
+  for(int i = 0; i < MCX_NSTAGE; i++) apply_persist(g, g->streams[i]);
   *out = g;
   return MCX_OK;
 }
@@ -159,7 +185,8 @@ extern "C" int mcx_graph_clear(mcx_graph *g)
   cudaStream_t st = primary(g);
   CU(cudaMemsetAsync(g->table.slots, 0, (size_t)g->table.nslots * g->table.stride * 4u, st));
   CU(cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), st));
-  if(g->table.front) CU(cudaMemsetAsync(g->table.front, 0, (4ull << g->table.front_set_bits) * 8u, st));
+  if(g->table.front) CU(cudaMemsetAsync(g->table.front, 0, (4ull << g->table.front_set_bits) * 12u, st));
+  g->front_pending = 0;
   g->sharded = false;
   g->occ_bound = 0; g->pend_positions = 0; g->pend_offsets_reads = g->pend_offsets_bases = 0; g->nkmers = 0;
   return MCX_OK;
@@ -171,6 +198,7 @@ extern "C" int mcx_graph_set_stream(mcx_graph *g, void *cuda_stream)
   int r = sync_all(g); if(r) return r;
   g->use_user_stream = cuda_stream != NULL;
   g->user_stream = (cudaStream_t)cuda_stream;
+  apply_persist(g, primary(g));
   return MCX_OK;
 }
 
@@ -197,13 +225,36 @@ static McxBuildParams make_params(mcx_graph *g, const mcx_read_batch *b, const u
   return p;
 }
 
+// The front table's counters are 32 bits wide: merge it into the big table before a counter could
+// wrap, i.e. before 2^32 - 2^28 positions (an upper bound on the occurrences of any one k-mer)
+// have been queued since the last flush.
+#define MCX_FRONT_SPAN 0xEF000000ull  /* most positions one launch may cover */
+static int front_guard(mcx_graph *g, uint64_t positions)
+{
+  if(!g->table.front_set_bits) return MCX_OK;
+  if(positions > MCX_FRONT_SPAN) { snprintf(g_err, sizeof(g_err), "batch too large: split it into pieces of < 3.7e9 bytes"); return MCX_ERR_UNSUPPORTED; }
+  if(g->front_pending + positions >= 0xF0000000ull) {
+    if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must run at least every 4e9 positions"); return MCX_ERR_UNSUPPORTED; }
+    CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+    g->front_pending = 0;
+  }
+  g->front_pending += positions;
+  return MCX_OK;
+}
+
 // LINES batch resident on the device
 static int add_lines_device(mcx_graph *g, const mcx_read_batch *b, const uint8_t *dseq, uint64_t nbytes)
 {
   if(((uintptr_t)dseq & 15u) != 0) { snprintf(g_err, sizeof(g_err), "device seq buffer must be 16-byte aligned"); return MCX_ERR_BAD_ARG; }
   g->occ_bound += nbytes;
-  McxBuildParams p = make_params(g, b, dseq, nbytes, 0, nbytes);
-  CU(mcx_launch_build_fused(p, g->table, primary(g)));
+  // one launch per span of <= MCX_FRONT_SPAN positions (the whole buffer stays visible to every
+  // launch, so windows and edges across a cut see their neighbours)
+  for(uint64_t lo = 0; lo < nbytes; lo += MCX_FRONT_SPAN) {
+    const uint64_t hi = lo + MCX_FRONT_SPAN < nbytes ? lo + MCX_FRONT_SPAN : nbytes;
+    int r = front_guard(g, hi - lo); if(r) return r;
+    McxBuildParams p = make_params(g, b, dseq, nbytes, lo, hi);
+    CU(mcx_launch_build_fused(p, g->table, primary(g)));
+  }
   g->pend_positions += nbytes;
   return MCX_OK;
 }
@@ -218,10 +269,13 @@ static int add_lines_host(mcx_graph *g, const mcx_read_batch *b, const uint8_t *
   bool pinned = (cudaPointerGetAttributes(&attr, hseq) == cudaSuccess) && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
   g->occ_bound += nbytes;
+  for(uint64_t span_lo = 0; span_lo < nbytes; span_lo += MCX_FRONT_SPAN - MCX_FRONT_SPAN % MCX_STAGE_POS) {
+  const uint64_t span_hi = span_lo + (MCX_FRONT_SPAN - MCX_FRONT_SPAN % MCX_STAGE_POS) < nbytes ? span_lo + (MCX_FRONT_SPAN - MCX_FRONT_SPAN % MCX_STAGE_POS) : nbytes;
+  { int rg = front_guard(g, span_hi - span_lo); if(rg) return rg; } // may queue a flush on the primary stream: the previous span has been joined into it
   CU(cudaEventRecord(g->ev_fork, primary(g)));
   bool used[MCX_NSTAGE] = {false, false, false};
-  for(uint64_t pos = 0; pos < nbytes; pos += MCX_STAGE_POS) {
-    uint64_t pend = pos + MCX_STAGE_POS < nbytes ? pos + MCX_STAGE_POS : nbytes;
+  for(uint64_t pos = span_lo; pos < span_hi; pos += MCX_STAGE_POS) {
+    uint64_t pend = pos + MCX_STAGE_POS < span_hi ? pos + MCX_STAGE_POS : span_hi;
     uint64_t b0 = pos ? pos - MCX_LB : 0;
     uint64_t b1 = pend + MCX_TAIL < nbytes ? pend + MCX_TAIL : nbytes;
     int s = g->next; g->next = (g->next + 1) % MCX_NSTAGE;
@@ -236,6 +290,7 @@ static int add_lines_host(mcx_graph *g, const mcx_read_batch *b, const uint8_t *
     CU(cudaEventRecord(g->events[s], st));
   }
   for(int s = 0; s < MCX_NSTAGE; s++) if(used[s]) CU(cudaStreamWaitEvent(primary(g), g->events[s], 0));
+  }
   g->pend_positions += nbytes;
   return MCX_OK;
 }
@@ -311,6 +366,7 @@ extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
   if(b->fq_cutoff >= 127) { snprintf(g_err, sizeof(g_err), "fq_cutoff (incl. offset) must be < 127"); return MCX_ERR_UNSUPPORTED; }
   CU(cudaSetDevice(g->device));
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
+  if((b->fq_cutoff && b->qual) || b->layout != MCX_LAYOUT_LINES) { int r = front_guard(g, b->nbytes + b->nreads); if(r) return r; }
   if(b->fq_cutoff && b->qual) return add_reads_qual(g, b);
 
   if(b->layout == MCX_LAYOUT_LINES) {
@@ -371,6 +427,7 @@ extern "C" int mcx_graph_sync(mcx_graph *g, mcx_load_stats *stats)
   int r = sync_all(g); if(r) return r;
   if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must run before sync"); return MCX_ERR_BAD_ARG; }
   CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+  g->front_pending = 0;
   CU(cudaStreamSynchronize(primary(g)));
   unsigned long long c[MCX_NCOUNTERS];
   CU(cudaMemcpy(c, g->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
@@ -399,6 +456,7 @@ extern "C" int mcx_graph_flush(mcx_graph *g)
   if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must be used on a sharded graph"); return MCX_ERR_BAD_ARG; }
   CU(cudaSetDevice(g->device));
   CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+  g->front_pending = 0;
   return MCX_OK;
 }
 
@@ -416,6 +474,7 @@ extern "C" int mcx_graph_export_begin(mcx_graph *g, int sorted, uint64_t *nrecor
   int r = sync_all(g); if(r) return r;
   if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must run before export"); return MCX_ERR_BAD_ARG; }
   CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+  g->front_pending = 0;
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
   cudaError_t e = mcx_export_build(g->table, g->k, sorted != 0, &g->exp, primary(g));
   if(e != cudaSuccess) return fail_cuda(e, "export");
@@ -490,6 +549,8 @@ static int add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t npa
   cudaStream_t st = primary(g);
   McxTupleBins bins;
   { int r = fill_bins(&bins, g->W, nparts, my_part, cap_per_part, keys_out, meta_out, keys_dst, meta_dst, counts_out); if(r) return r; }
+  g->sharded = true;
+  { int r = front_guard(g, b->nbytes); if(r) return r; }
   CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
   g->occ_bound += b->nbytes;
   McxBuildParams p = make_params(g, b, (const uint8_t *)b->seq, b->nbytes, 0, b->nbytes);
@@ -525,7 +586,7 @@ static int flush_sharded(mcx_graph *g, uint32_t nparts, uint32_t my_part, uint64
   { int r = fill_bins(&bins, g->W, nparts, my_part, cap_per_part, keys_out, meta_out, keys_dst, meta_dst, counts_out); if(r) return r; }
   CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
   CU(mcx_launch_front_flush_sharded(g->table, bins, g->occ_bound >= 0xF0000000ull, g->d_counters, st));
-  g->sharded = false;
+  g->sharded = false; g->front_pending = 0;
   return MCX_OK;
 }
 

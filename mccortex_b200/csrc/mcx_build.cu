@@ -30,30 +30,46 @@
 
 #define MCX_THREADS 256
 
-struct __align__(128) McxChunkSmem {
+// Per-CTA staging of the chunk pipeline.  Three chunks are in flight per CTA (phase 1 of chunk
+// j+2, phase 2a of chunk j+1, phase 2b of chunk j run in the SAME barrier interval), hence the
+// buffer counts: raw x2 (TMA landing zone, read by phase 1), packed bases x3 (written by phase 1
+// of j+2 while phase 2b of j still reads its own), base masks x2 (phase 1 -> phase 2a), window
+// masks x2 (phase 2a -> phase 2b).
+template <bool QUAL> struct __align__(128) McxChunkSmem {
   uint8_t raw[2][MCX_RAW];
-  uint8_t qraw[2][MCX_RAW];  // quality bytes of the same positions (quality modes only)
-  uint32_t pk[MCX_PKW];
-  uint32_t bad[MCX_MSW];     // base cannot be in a window that EXTENDS a contig
-  uint32_t bads[MCX_MSW];    // base cannot be in a window that STARTS a contig (quality modes)
-  uint32_t eq[MCX_MSW];
-  uint32_t vmask[MCX_VW];    // in_contig per window
-  uint32_t svm[MCX_VW];      // start-valid windows (quality modes)
+  uint8_t qraw[QUAL ? 2 : 1][QUAL ? MCX_RAW : 16]; // quality bytes of the same positions (quality modes only)
+  uint32_t pk[3][MCX_PKW];
+  uint32_t bad[2][MCX_MSW];     // base cannot be in a window that EXTENDS a contig
+  uint32_t bads[QUAL ? 2 : 1][QUAL ? MCX_MSW : 1]; // base cannot be in a window that STARTS a contig (quality modes)
+  uint32_t eq[2][MCX_MSW];
+  uint32_t vmask[2][MCX_VW];    // in_contig per window
+  uint32_t svm[QUAL ? 2 : 1][QUAL ? MCX_VW : 1];   // start-valid windows (quality modes)
   uint32_t carry_in;
   unsigned long long bar[2];
   unsigned long long red[MCX_NCOUNTERS];
 };
 
 // Occurrences that are not a plain front-table hit (first sight of a k-mer, missing edge bit,
-// count field filling up, k-mer that lives in the big table) are parked here and handled after
-// the chunk's hot pass, one per thread, all lanes busy.  Handling them inline would stall the
-// whole warp on two or three dependent memory round trips whenever ANY of its 32 lanes is slow,
-// which is most rounds (measured: 100-170 ms instead of 59 ms).
+// count field filling up, k-mer that lives in the big table) are parked here and handled later,
+// one per thread, all lanes busy.  Handling them inline would stall the whole warp on two or
+// three dependent memory round trips whenever ANY of its 32 lanes is slow, which is most rounds
+// (measured: 100-170 ms instead of 59 ms).  The queue holds two chunks' worth of windows and is
+// drained only when the next chunk might not fit (about every tenth chunk on the bench
+// workload): draining after every chunk left most warps idle at the barrier (ncu: 27 % of all
+// stall samples).
+// k > 31 has no front table: everything parks and the queue is drained after every chunk.
+#define MCX_QCAP(W) ((W) == 1 ? 2u * MCX_T : MCX_T)
 template <int W> struct McxSlowQueue {
-  uint64_t key[MCX_T * W];
-  uint8_t emask[MCX_T];
+  uint64_t key[MCX_QCAP(W) * W];
+  uint8_t emask[MCX_QCAP(W)];
   uint32_t n;
 };
+// the queue lives in dynamic shared memory (static + dynamic exceeds the 48 KB static limit)
+extern __shared__ __align__(16) unsigned char mcx_dyn_smem[];
+template <int W> __device__ __forceinline__ McxSlowQueue<W> *mcx_queue()
+{
+  return reinterpret_cast<McxSlowQueue<W> *>(mcx_dyn_smem);
+}
 
 // front-end modes
 enum { MCX_MODE_PLAIN = 0,   // contig rules are window-local (no quality cut-off)
@@ -81,13 +97,28 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
   } while(!done);
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ uint32_t g_mcx_hints = 0;  // MCX_L2_HINTS (see mcx_table.cuh)
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
 {
+  if(g_mcx_hints & 1u) {
+    // the read stream is touched once: let it leave L2 first, the front table lives there
+    const uint64_t pol = mcx_policy_evict_first();
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+  } else
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mcx_apply_hints(McxTable &t)
+{
+  const uint32_t h = g_mcx_hints;
+  t.pol_big = (h & 2u) ? mcx_policy_evict_first() : 0ull;
+  t.pol_front = (h & 4u) ? mcx_policy_evict_last() : 0ull;
+}
+void mcx_set_hints(uint32_t h) { cudaMemcpyToSymbol(g_mcx_hints, &h, sizeof(h)); }
 
-__device__ __forceinline__ void issue_chunk_load(McxChunkSmem &sm, const McxBuildParams &p, uint64_t chunk, uint32_t buf)
+template <bool QUAL>
+__device__ __forceinline__ void issue_chunk_load(McxChunkSmem<QUAL> &sm, const McxBuildParams &p, uint64_t chunk, uint32_t buf)
 {
   uint64_t cs = chunk * (uint64_t)MCX_T;
   uint64_t src_off = cs ? cs - MCX_LB : 0;
@@ -95,9 +126,9 @@ __device__ __forceinline__ void issue_chunk_load(McxChunkSmem &sm, const McxBuil
   uint64_t avail = (p.nbytes - src_off + 15ull) & ~15ull; // p.seq is readable up to nbytes rounded up to 16
   uint32_t want = MCX_RAW - dst_off;
   uint32_t bytes = avail < want ? (uint32_t)avail : want;
-  mbar_expect_tx(&sm.bar[buf], p.qual ? 2u * bytes : bytes);
+  mbar_expect_tx(&sm.bar[buf], QUAL ? 2u * bytes : bytes);
   tma_load_1d(&sm.raw[buf][dst_off], p.seq + src_off, bytes, &sm.bar[buf]);
-  if(p.qual) tma_load_1d(&sm.qraw[buf][dst_off], p.qual + src_off, bytes, &sm.bar[buf]);
+  if(QUAL) tma_load_1d(&sm.qraw[buf][dst_off], p.qual + src_off, bytes, &sm.bar[buf]);
 }
 
 // in_contig of the window just before `chunk`: walk back over the per-chunk summaries
@@ -142,30 +173,12 @@ static __host__ __device__ __forceinline__ McxTupleBins mcx_no_bins()
 template <int W, int G> struct FusedSink { // G = probe loads kept in flight per thread
   McxTable t; uint32_t colour; bool may_saturate;
   McxSlowQueue<W> *q;
+  uint32_t ablate;
   McxTupleBins bins; // bins.nparts > 1: sharded build, keys owned by another shard leave as tuples
 
-  // one parked occurrence: front table (claim / edge bit / drain), else the big table
-  __device__ __forceinline__ void slow(McxKmer<W> key, uint32_t emask, uint64_t &novel, uint32_t &full)
-  {
-    uint32_t n = 1u;
-    if(W == 1 && t.front_set_bits) {
-      // returns 0xFFFFFFFF = not absorbed, else the count it drained (0 almost always)
-      uint32_t drained = mcx_front_add_slow(t, key.b[0], emask);
-      if(drained == 0u) return;
-      if(drained != 0xFFFFFFFFu) { n = drained; emask = 0; } // carry a drained count over to the big table
-    }
-    uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
-    if(bins.nparts > 1u) {
-      const uint32_t d = mcx_owner(hc, bins.nparts);
-      if(d != bins.my_part) { mcx_bin_push<W>(bins, d, key, (n << 8) | emask, full); return; }
-    }
-    int r = mcx_table_add<W>(t, key, hc, hb, colour, emask, n, may_saturate);
-    novel += (r == 1);
-    full |= (r == 2);
-  }
   __device__ __forceinline__ void park(const McxKmer<W> &key, uint32_t emask)
   {
-    const uint32_t at = atomicAdd(&q->n, 1u); // < MCX_T by construction: one slot per window of the chunk
+    const uint32_t at = atomicAdd(&q->n, 1u); // < MCX_QCAP(W): a chunk starts with at least MCX_T free entries
 #pragma unroll
     for(int w = 0; w < W; w++) q->key[at * W + w] = key.b[w];
     q->emask[at] = (uint8_t)emask;
@@ -178,19 +191,36 @@ template <int W, int G> struct FusedSink { // G = probe loads kept in flight per
       // hot pass: G probe loads in flight per thread, one 32-bit RED per hit; no Lookup3, no
       // big-table access for k-mers that live in the L2-resident front table
       const McxFrontGeom g = mcx_front_geom(t);
+      const uint32_t abl = ablate; // experiments only (MCX_L2_HINTS bits 3..5): 0 in production
+      if(abl) {
+#pragma unroll
+        for(uint32_t h = 0; h < MCX_HALF; h++) {
+          if(!((valid >> h) & 1u)) continue;
+          const McxFKey fk = mcx_fhash(keys[h].b[0]);
+          const uint64_t s4 = (uint64_t)(fk.y & g.setmask) << 2;
+          if(abl & 1u) { novel += (fk.x == 0x12345u && fk.y == 77u && emasks[h] == 3u); continue; }   // no table access at all
+          if(abl & 2u) {                                                                              // load + compare only
+            uint64_t v0, v1, v2, v3; mcx_ld256(t.front + s4, v0, v1, v2, v3);
+            novel += ((uint32_t)v0 == fk.x) + ((uint32_t)v1 == fk.x) + ((uint32_t)v2 == fk.x) + ((uint32_t)v3 == fk.x + emasks[h]);
+            continue;
+          }
+          atomicAdd(t.front_cnt + s4 + (fk.x & 3u), 1u);                                              // RED only
+        }
+        return;
+      }
 #pragma unroll
       for(uint32_t h = 0; h < MCX_HALF; h += G) {
-        uint64_t v[G][4], y[G];
+        uint64_t v[G][4]; McxFKey fk[G];
 #pragma unroll
         for(uint32_t i = 0; i < G; i++) {
-          y[i] = mcx_phi(keys[h + i].b[0]);
-          if((valid >> (h + i)) & 1u) mcx_ld256(t.front + ((y[i] >> g.T) << 2), v[i][0], v[i][1], v[i][2], v[i][3]);
+          fk[i] = mcx_fhash(keys[h + i].b[0]);
+          if((valid >> (h + i)) & 1u) mcx_ld256_pol(t.front + ((uint64_t)(fk[i].y & g.setmask) << 2), t.pol_front, v[i][0], v[i][1], v[i][2], v[i][3]);
         }
 #pragma unroll
         for(uint32_t i = 0; i < G; i++) {
           if((valid >> (h + i)) & 1u) {
-            if(!mcx_front_hit(g, t.front + ((y[i] >> g.T) << 2), y[i] & g.tagmask, (uint64_t)emasks[h + i] << g.T,
-                              v[i][0], v[i][1], v[i][2], v[i][3]))
+            if(!mcx_front_hit(g, t.front_cnt + ((uint64_t)(fk[i].y & g.setmask) << 2), t.pol_front, fk[i].x, (fk[i].y >> g.S) | g.occ,
+                              emasks[h + i] << g.eshift, v[i][0], v[i][1], v[i][2], v[i][3]))
               park(keys[h + i], emasks[h + i]);
           }
         }
@@ -202,7 +232,24 @@ template <int W, int G> struct FusedSink { // G = probe loads kept in flight per
     }
   }
   __device__ __forceinline__ void reset() { if(threadIdx.x == 0) q->n = 0; }
-  // after the hot pass of a chunk (all threads of the CTA, between two __syncthreads)
+  // the next chunk may not fit (evaluated per thread just before the step barrier, OR-reduced there)
+  __device__ __forceinline__ bool should_drain() const { return q->n > MCX_QCAP(W) - MCX_T; }
+  // one parked occurrence: front table (claim / edge bit), else the big table
+  __device__ __forceinline__ void slow(McxKmer<W> key, uint32_t emask, uint64_t &novel, uint32_t &full)
+  {
+    if(W == 1 && t.front_set_bits) {
+      if(mcx_front_add_slow(t, key.b[0], emask)) return; // absorbed by the front table
+    }
+    uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
+    if(bins.nparts > 1u) {
+      const uint32_t d = mcx_owner(hc, bins.nparts);
+      if(d != bins.my_part) { mcx_bin_push<W>(bins, d, key, (1u << 8) | emask, full); return; }
+    }
+    int r = mcx_table_add<W>(t, key, hc, hb, colour, emask, 1u, may_saturate);
+    novel += (r == 1);
+    full |= (r == 2);
+  }
+  // all threads of the CTA, between two __syncthreads
   __device__ __forceinline__ void drain(uint64_t &novel, uint32_t &full)
   {
     const uint32_t n = q->n;
@@ -233,15 +280,25 @@ template <int W> struct TupleSink {
   }
   __device__ __forceinline__ void drain(uint64_t &, uint32_t &) {}
   __device__ __forceinline__ void reset() {}
+  __device__ __forceinline__ bool should_drain() const { return false; }
 };
 
 // ---------------------------------------------------------------- front end
+// One CTA = a persistent worker over chunks c_first + blockIdx.x + j * gridDim.x (j = 0, 1, ...).
+// Software pipeline, ONE barrier per chunk: in step s the CTA runs
+//   phase 1  of chunk j = s+2  (threads 0 .. RAW/16-1: ASCII -> packed bases + base masks),
+//   phase 2a of chunk j = s+1  (the last MCX_VW threads: base masks -> window masks),
+//   phase 2b of chunk j = s    (everybody: 8 windows per thread -> sink),
+// then __syncthreads, then one thread refills the raw buffer phase 1 has just consumed (TMA for
+// chunk s+4).  Steps -2 and -1 fill the pipeline.
 template <int W, int MODE, class Sink>
 __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sink)
 {
-  __shared__ McxChunkSmem sm;
+  constexpr bool QUAL = MODE != MCX_MODE_PLAIN;
+  __shared__ McxChunkSmem<QUAL> sm;
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint64_t c_first = p.r_begin / MCX_T, c_last = (p.r_end + MCX_T - 1) / MCX_T;
+  const uint64_t chunk0 = c_first + blockIdx.x, cstride = gridDim.x;
 
   if(tid == 0) {
     mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1);
@@ -249,92 +306,80 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
   }
   if(tid < MCX_NCOUNTERS) sm.red[tid] = 0;
   // over-read padding of the staged arrays must be defined (it is shifted in, then masked off)
-  if(tid < 4) { sm.pk[MCX_RAW / 16u + tid] = 0; sm.bad[MCX_RAW / 32u + tid] = 0xFFFFFFFFu; sm.eq[MCX_RAW / 32u + tid] = 0; }
+  if(tid < 4) {
+#pragma unroll
+    for(int b = 0; b < 3; b++) sm.pk[b][MCX_RAW / 16u + tid] = 0;
+#pragma unroll
+    for(int b = 0; b < 2; b++) {
+      sm.bad[b][MCX_RAW / 32u + tid] = 0xFFFFFFFFu; sm.eq[b][MCX_RAW / 32u + tid] = 0;
+      if(QUAL) sm.bads[b][MCX_RAW / 32u + tid] = 0xFFFFFFFFu;
+    }
+  }
   __syncthreads();
-
-  uint64_t chunk = c_first + blockIdx.x;
-  if(tid == 0 && chunk < c_last) issue_chunk_load(sm, p, chunk, 0);
+  if(tid == 0) {
+    if(chunk0 < c_last) issue_chunk_load<QUAL>(sm, p, chunk0, 0);
+    if(chunk0 + cstride < c_last) issue_chunk_load<QUAL>(sm, p, chunk0 + cstride, 1);
+  }
 
   uint64_t n_kmers = 0, n_novel = 0, n_contigs = 0, n_reads = 0;
   uint32_t full = 0;
 
-  for(uint32_t it = 0; chunk < c_last; chunk += gridDim.x, it++) {
-    const uint32_t buf = it & 1u;
-    const uint64_t cs = chunk * (uint64_t)MCX_T;
-    mbar_wait(&sm.bar[buf], (it >> 1) & 1u);
+  for(int64_t s = -2;; s++) {
+    const uint64_t ch2 = chunk0 + (uint64_t)(s + 2) * cstride;                      // phase 1
+    const uint64_t ch1 = chunk0 + (uint64_t)(s + 1) * cstride;                      // phase 2a
+    const uint64_t ch0 = chunk0 + (uint64_t)(s < 0 ? 0 : s) * cstride;              // phase 2b
+    if(s >= 0 && ch0 >= c_last) break;
 
-    // ---- phase 1: ASCII -> packed bases + masks, 16 bytes per thread
-    if(tid < MCX_RAW / 16u) {
-      const uint4 v = *reinterpret_cast<const uint4 *>(&sm.raw[buf][tid * 16u]);
+    // ---- phase 1 (chunk s+2): ASCII -> packed bases + masks, 16 bytes per thread
+    if(ch2 < c_last && tid < MCX_RAW / 16u) {
+      const uint32_t j = (uint32_t)(s + 2), rb = j & 1u, pb = j % 3u;
+      mbar_wait(&sm.bar[rb], (j >> 1) & 1u);
+      const uint64_t cs = ch2 * (uint64_t)MCX_T;
+      const uint4 v = *reinterpret_cast<const uint4 *>(&sm.raw[rb][tid * 16u]);
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      uint32_t prev = tid ? sm.raw[buf][tid * 16u - 1u] : 0u;
+      uint32_t prev = tid ? sm.raw[rb][tid * 16u - 1u] : 0u;
       uint64_t gpos = cs - MCX_LB + tid * 16ull; // wraps for the look-back of chunk 0: handled in convert16
       uint32_t pk, b16, e16, n16;
       mcx_convert16(w, prev, gpos, p.nbytes, &pk, &b16, &e16, &n16);
-      sm.pk[tid] = pk;
-      if(MODE != MCX_MODE_PLAIN) {
-        const uint4 qv = *reinterpret_cast<const uint4 *>(&sm.qraw[buf][tid * 16u]);
+      sm.pk[pb][tid] = pk;
+      if(QUAL) {
+        const uint4 qv = *reinterpret_cast<const uint4 *>(&sm.qraw[QUAL ? rb : 0][tid * 16u]);
         const uint32_t q[4] = {qv.x, qv.y, qv.z, qv.w};
         uint32_t wk16, st16;
         mcx_qual16(q, p.qcut, &wk16, &st16);
-        reinterpret_cast<uint16_t *>(sm.bads)[tid] = (uint16_t)(b16 | st16);
+        reinterpret_cast<uint16_t *>(sm.bads[QUAL ? rb : 0])[tid] = (uint16_t)(b16 | st16);
         b16 |= wk16;
       }
-      reinterpret_cast<uint16_t *>(sm.bad)[tid] = (uint16_t)b16;
-      reinterpret_cast<uint16_t *>(sm.eq)[tid] = (uint16_t)e16;
+      reinterpret_cast<uint16_t *>(sm.bad[rb])[tid] = (uint16_t)b16;
+      reinterpret_cast<uint16_t *>(sm.eq[rb])[tid] = (uint16_t)e16;
       // read terminators owned by this launch and this chunk
       if(MODE != MCX_MODE_QSUM && n16 && tid >= MCX_LB / 16u && tid < (MCX_LB + MCX_T) / 16u) {
         for(uint32_t i = 0; i < 16u; i++)
           if(((n16 >> i) & 1u) && gpos + i >= p.r_begin && gpos + i < p.r_end) n_reads++;
       }
     }
-    __syncthreads();
-    // raw[buf^1] was last read in phase 1 of the previous iteration: safe to refill
-    if(tid == 0 && chunk + gridDim.x < c_last) issue_chunk_load(sm, p, chunk + gridDim.x, buf ^ 1u);
 
-    // ---- phase 2a: contig rules, 32 windows per thread (word-parallel dilate / erode of the
-    //      bad / eq masks); masks are indexed by staged position
-    if(tid < MCX_VW) {
-      const bool live = tid < (MCX_LB + MCX_T + 32u) / 32u;
-      sm.vmask[tid] = live ? mcx_valid_word(sm.bad, sm.eq, tid, p.k, p.hp_cutoff) : 0u;
-      if(MODE != MCX_MODE_PLAIN) sm.svm[tid] = live ? mcx_valid_word(sm.bads, sm.eq, tid, p.k, p.hp_cutoff) : 0u;
-    }
-    if(MODE == MCX_MODE_QUAL && tid == 96) sm.carry_in = chunk_carry_in(p.summary, chunk, c_first);
-    __syncthreads();
-    if(MODE != MCX_MODE_PLAIN) {
-      // vmask holds ev, svm holds sv: resolve in_contig = ev & (sv | in_contig(prev)) (one thread,
-      // ~68 adds).  The window before the chunk (position LB-1) carries the chunk's carry-in.
-      if(tid == 0) {
-        const uint32_t cb = MCX_LB - 1u, keep = ~0u << cb; // cb < 32: lives in word 0
-        const uint32_t ev0 = sm.vmask[0] & keep & ~(1u << cb), sv0 = sm.svm[0] & keep & ~(1u << cb);
-        if(MODE == MCX_MODE_QUAL) {
-          const uint32_t cin = sm.carry_in;
-          sm.vmask[0] = ev0 | (cin << cb); sm.svm[0] = sv0 | (cin << cb);
-          mcx_contig_chain(sm.vmask, sm.svm, MCX_VW, 0u, sm.vmask);
-        } else {
-          // summary of this chunk's own windows: in_contig of its last window for carry-in 0 and 1
-          uint32_t out = 0;
-          for(uint32_t cin = 0; cin < 2u; cin++) {
-            sm.vmask[0] = ev0 | (cin << cb); sm.svm[0] = sv0 | (cin << cb);
-            uint32_t x[MCX_VW];
-            mcx_contig_chain(sm.vmask, sm.svm, MCX_VW, 0u, x);
-            out |= mcx_get_bit(x, MCX_LB - 1u + MCX_T) << cin;
-          }
-          p.summary[chunk - c_first] = (uint8_t)out;
-        }
-      }
-      __syncthreads();
+    // ---- phase 2a (chunk s+1): contig rules, 32 windows per thread (word-parallel dilate / erode
+    //      of the bad / eq masks); masks are indexed by staged position
+    if(s >= -1 && ch1 < c_last && tid >= MCX_THREADS - MCX_VW) {
+      const uint32_t wi = tid - (MCX_THREADS - MCX_VW), mb = (uint32_t)(s + 1) & 1u;
+      const bool live = wi < (MCX_LB + MCX_T + 32u) / 32u;
+      sm.vmask[mb][wi] = live ? mcx_valid_word(sm.bad[mb], sm.eq[mb], wi, p.k, p.hp_cutoff) : 0u;
+      if(QUAL) sm.svm[QUAL ? mb : 0][wi] = live ? mcx_valid_word(sm.bads[QUAL ? mb : 0], sm.eq[mb], wi, p.k, p.hp_cutoff) : 0u;
+      if(MODE == MCX_MODE_QUAL && wi == 0) sm.carry_in = chunk_carry_in(p.summary, ch1, c_first);
     }
 
-    // ---- phase 2b: 8 consecutive windows per thread, rolling k-mers; keys are built four at a
-    //      time and handed to the sink, which overlaps its table probes
-    if(MODE != MCX_MODE_QSUM) {
+    // ---- phase 2b (chunk s): 8 consecutive windows per thread, rolling k-mers; keys are built
+    //      four at a time and handed to the sink, which overlaps its table probes
+    if(MODE != MCX_MODE_QSUM && s >= 0) {
+      const uint32_t j = (uint32_t)s;
+      const uint64_t cs = ch0 * (uint64_t)MCX_T;
       // windows owned by this launch: positions [r_begin, r_end)
       const uint64_t g0 = cs + MCX_WPT * tid;
       const uint32_t lo = p.r_begin > g0 ? (p.r_begin - g0 < MCX_WPT ? (uint32_t)(p.r_begin - g0) : MCX_WPT) : 0u;
       const uint32_t hi = p.r_end > g0 ? (p.r_end - g0 < MCX_WPT ? (uint32_t)(p.r_end - g0) : MCX_WPT) : 0u;
       const uint32_t own = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
-      mcx_thread_occurrences<W>(sm.pk, sm.vmask, tid, p.k,
+      mcx_thread_occurrences<W>(sm.pk[j % 3u], sm.vmask[j & 1u], tid, p.k,
         [&](const McxKmer<W> *keys, const uint32_t *emasks, uint32_t valid, uint32_t starts, uint32_t j0) {
           valid &= own >> j0;
           if(valid) {
@@ -343,22 +388,61 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
             sink.consume(keys, emasks, valid, n_novel, full);
           }
         });
-      // ---- phase 2c: the parked (slow) occurrences of this chunk, one per thread
-      __syncthreads();
-      sink.drain(n_novel, full);
     }
-    __syncthreads();
-    sink.reset();
-    __syncthreads();
+    // the step's only barrier.  It also decides, CTA-uniformly, whether the parked occurrences must
+    // be drained now: the last thread to arrive evaluates its predicate after every park of the step
+    const int drain_now = __syncthreads_or(sink.should_drain() ? 1 : 0);
+    // raw[(s+2)&1] has been consumed by phase 1: refill it with chunk s+4
+    if(tid == 0) {
+      const uint64_t ch4 = chunk0 + (uint64_t)(s + 4) * cstride;
+      if(ch4 < c_last) issue_chunk_load<QUAL>(sm, p, ch4, (uint32_t)(s + 4) & 1u);
+    }
+
+    if(QUAL && s >= -1 && ch1 < c_last) {
+      // vmask holds ev, svm holds sv of chunk s+1: resolve in_contig = ev & (sv | in_contig(prev))
+      // (one thread, ~68 adds).  The window before the chunk (position LB-1) carries the carry-in.
+      if(tid == 0) {
+        const uint32_t mb = (uint32_t)(s + 1) & 1u;
+        uint32_t *vm = sm.vmask[mb], *sv = sm.svm[QUAL ? mb : 0];
+        const uint32_t cb = MCX_LB - 1u, keep = ~0u << cb; // cb < 32: lives in word 0
+        const uint32_t ev0 = vm[0] & keep & ~(1u << cb), sv0 = sv[0] & keep & ~(1u << cb);
+        if(MODE == MCX_MODE_QUAL) {
+          const uint32_t cin = sm.carry_in;
+          vm[0] = ev0 | (cin << cb); sv[0] = sv0 | (cin << cb);
+          mcx_contig_chain(vm, sv, MCX_VW, 0u, vm);
+        } else {
+          // summary of this chunk's own windows: in_contig of its last window for carry-in 0 and 1
+          uint32_t out = 0;
+          for(uint32_t cin = 0; cin < 2u; cin++) {
+            vm[0] = ev0 | (cin << cb); sv[0] = sv0 | (cin << cb);
+            uint32_t x[MCX_VW];
+            mcx_contig_chain(vm, sv, MCX_VW, 0u, x);
+            out |= mcx_get_bit(x, MCX_LB - 1u + MCX_T) << cin;
+          }
+          p.summary[ch1 - c_first] = (uint8_t)out;
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- parked (slow) occurrences: only when the queue could overflow during the next chunk
+    if(drain_now) {
+      sink.drain(n_novel, full);
+      __syncthreads();
+      sink.reset();
+      __syncthreads();
+    }
   }
+  __syncthreads();
+  sink.drain(n_novel, full);
 
   // ---- counters: warp shuffle -> shared -> one global atomic per CTA per counter
-  for(int s = 16; s > 0; s >>= 1) {
-    n_kmers += __shfl_xor_sync(0xFFFFFFFFu, n_kmers, s);
-    n_novel += __shfl_xor_sync(0xFFFFFFFFu, n_novel, s);
-    n_contigs += __shfl_xor_sync(0xFFFFFFFFu, n_contigs, s);
-    n_reads += __shfl_xor_sync(0xFFFFFFFFu, n_reads, s);
-    full |= __shfl_xor_sync(0xFFFFFFFFu, full, s);
+  for(int sh = 16; sh > 0; sh >>= 1) {
+    n_kmers += __shfl_xor_sync(0xFFFFFFFFu, n_kmers, sh);
+    n_novel += __shfl_xor_sync(0xFFFFFFFFu, n_novel, sh);
+    n_contigs += __shfl_xor_sync(0xFFFFFFFFu, n_contigs, sh);
+    n_reads += __shfl_xor_sync(0xFFFFFFFFu, n_reads, sh);
+    full |= __shfl_xor_sync(0xFFFFFFFFu, full, sh);
   }
   if(lane == 0) {
     atomicAdd(&sm.red[MCX_CNT_KMERS], (unsigned long long)n_kmers);
@@ -377,9 +461,10 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
 template <int W, int MINB, int G>
 __global__ void __launch_bounds__(MCX_THREADS, MINB) mcx_build_fused_kernel(McxBuildParams p, McxTable t)
 {
-  __shared__ McxSlowQueue<W> q;
-  if(threadIdx.x == 0) q.n = 0;
-  FusedSink<W, G> sink{t, p.colour, p.may_saturate != 0, &q, mcx_no_bins()};
+  McxSlowQueue<W> *q = mcx_queue<W>();
+  if(threadIdx.x == 0) q->n = 0;
+  mcx_apply_hints(t);
+  FusedSink<W, G> sink{t, p.colour, p.may_saturate != 0, q, (g_mcx_hints >> 3) & 7u, mcx_no_bins()};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
 
@@ -387,11 +472,12 @@ __global__ void __launch_bounds__(MCX_THREADS, MINB) mcx_build_fused_kernel(McxB
 // them (they are forwarded, aggregated, at flush); the parked pass inserts owned keys into the
 // local big table and bins the others for the exchange
 template <int W>
-__global__ void __launch_bounds__(MCX_THREADS, 4) mcx_build_sharded_kernel(McxBuildParams p, McxTable t, McxTupleBins b)
+__global__ void __launch_bounds__(MCX_THREADS, 3) mcx_build_sharded_kernel(McxBuildParams p, McxTable t, McxTupleBins b)
 {
-  __shared__ McxSlowQueue<W> q;
-  if(threadIdx.x == 0) q.n = 0;
-  FusedSink<W, 2> sink{t, p.colour, p.may_saturate != 0, &q, b};
+  McxSlowQueue<W> *q = mcx_queue<W>();
+  if(threadIdx.x == 0) q->n = 0;
+  mcx_apply_hints(t);
+  FusedSink<W, 2> sink{t, p.colour, p.may_saturate != 0, q, 0u, b};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
 
@@ -400,6 +486,7 @@ struct NullSink {
   __device__ __forceinline__ void consume(const McxKmer<1> *, const uint32_t *, uint32_t, uint64_t &, uint32_t &) {}
   __device__ __forceinline__ void drain(uint64_t &, uint32_t &) {}
   __device__ __forceinline__ void reset() {}
+  __device__ __forceinline__ bool should_drain() const { return false; }
 };
 __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_contig_summary_kernel(McxBuildParams p)
 {
@@ -409,9 +496,9 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_contig_summary_kernel(McxB
 template <int W>
 __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_build_fused_qual_kernel(McxBuildParams p, McxTable t)
 {
-  __shared__ McxSlowQueue<W> q;
-  if(threadIdx.x == 0) q.n = 0;
-  FusedSink<W, 2> sink{t, p.colour, p.may_saturate != 0, &q, mcx_no_bins()};
+  McxSlowQueue<W> *q = mcx_queue<W>();
+  if(threadIdx.x == 0) q->n = 0;
+  FusedSink<W, 2> sink{t, p.colour, p.may_saturate != 0, q, 0u, mcx_no_bins()};
   mcx_front_end<W, MCX_MODE_QUAL>(p, sink);
 }
 
@@ -461,19 +548,30 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_insert_tuples_kernel(const
 // merge every front entry into the big table: key = phi^-1(set, tag), covg += count, edges |= edges
 __global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t, McxTupleBins bins, int may_saturate, unsigned long long *counters)
 {
-  const uint32_t T = 62u - t.front_set_bits;
-  const uint64_t nslots = 4ull << t.front_set_bits, tagmask = (1ull << T) - 1ull;
+  const McxFrontGeom g = mcx_front_geom(t);
+  const uint64_t nslots = 4ull << t.front_set_bits;
   uint64_t n_novel = 0; uint32_t full = 0;
   for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nslots; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t v = t.front[i];
     if(v == 0) continue;
-    McxKmer<1> key; key.b[0] = mcx_phi_inv(((i >> 2) << T) | (v & tagmask));
-    const uint32_t edges = (uint32_t)(v >> T) & 0xFFu, count = (uint32_t)(v >> (T + 8u));
+    const uint32_t hi = (uint32_t)(v >> 32);
+    McxKmer<1> key; key.b[0] = mcx_fhash_inv((uint32_t)v, ((hi & (g.occ - 1u)) << g.S) | (uint32_t)(i >> 2));
+    const uint32_t edges = (hi >> g.eshift) & 0xFFu;
+    uint32_t count = t.front_cnt[i];
     uint32_t hb, hc = mcx_lookup3<1>(key, 0u, &hb);
     if(bins.nparts > 1u) {
-      // sharded build: an aggregated record of a key owned elsewhere travels as ONE tuple
+      // sharded build: an aggregated record of a key owned elsewhere travels as ONE tuple (a tuple
+      // carries a 24-bit count: more than that, which takes a k-mer seen > 16 M times, is split)
       const uint32_t d = mcx_owner(hc, bins.nparts);
-      if(d != bins.my_part) { if(count | edges) mcx_bin_push<1>(bins, d, key, (count << 8) | edges, full); continue; }
+      if(d != bins.my_part) {
+        uint32_t e = edges;
+        while(count | e) {
+          const uint32_t c = count < 0xFFFFFFu ? count : 0xFFFFFFu;
+          mcx_bin_push<1>(bins, d, key, (c << 8) | e, full);
+          count -= c; e = 0;
+        }
+        continue;
+      }
     }
     int r = mcx_table_add<1>(t, key, hc, hb, 0u, edges, count, may_saturate != 0);
     n_novel += (r == 1); full |= (r == 2);
@@ -505,7 +603,7 @@ __global__ void mcx_repack_lines_kernel(const uint8_t *__restrict__ src, const u
 
 // ---------------------------------------------------------------- launchers
 static int g_num_sms = 0;
-static int g_minb = 4;     // resident CTAs per SM the fused kernel is compiled / launched for (experiment knob)
+static int g_minb = 3;     // resident CTAs per SM the fused kernel is compiled / launched for (experiment knob; 3 x 80 registers measured best)
 static int g_inflight = 2; // front-table probe loads in flight per thread (experiment knob)
 static int num_sms()
 {
@@ -515,6 +613,14 @@ static int num_sms()
     if(g_num_sms <= 0) g_num_sms = 148;
   }
   return g_num_sms;
+}
+
+// dynamic shared memory of the kernels that own a slow queue; raises the kernel's limit once
+template <int W, class K> static size_t queue_smem(K kernel)
+{
+  const size_t bytes = sizeof(McxSlowQueue<W>);
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return bytes;
 }
 
 static unsigned grid_for_chunks(const McxBuildParams &p, int ctas_per_sm)
@@ -529,16 +635,17 @@ cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, c
   if(p.r_end <= p.r_begin) return cudaSuccess;
   const int minb = g_minb;
   unsigned grid = grid_for_chunks(p, minb);
-#define MCX_LAUNCH_A(MB, GG) mcx_build_fused_kernel<1, MB, GG><<<grid, MCX_THREADS, 0, st>>>(p, t)
+#define MCX_LAUNCH_A(MB, GG) mcx_build_fused_kernel<1, MB, GG><<<grid, MCX_THREADS, queue_smem<1>(mcx_build_fused_kernel<1, MB, GG>), st>>>(p, t)
   if(p.k <= 31) {
     switch(minb * 10 + g_inflight) {
+      case 21: MCX_LAUNCH_A(2, 1); break; case 22: MCX_LAUNCH_A(2, 2); break; case 24: MCX_LAUNCH_A(2, 4); break;
       case 31: MCX_LAUNCH_A(3, 1); break; case 32: MCX_LAUNCH_A(3, 2); break; case 34: MCX_LAUNCH_A(3, 4); break;
       case 41: MCX_LAUNCH_A(4, 1); break; case 42: MCX_LAUNCH_A(4, 2); break; case 44: MCX_LAUNCH_A(4, 4); break;
       case 51: MCX_LAUNCH_A(5, 1); break; case 52: MCX_LAUNCH_A(5, 2); break; case 54: MCX_LAUNCH_A(5, 4); break;
       case 61: MCX_LAUNCH_A(6, 1); break; case 62: MCX_LAUNCH_A(6, 2); break;
-      default: MCX_LAUNCH_A(4, 2); break;
+      default: MCX_LAUNCH_A(3, 2); break;
     }
-  } else mcx_build_fused_kernel<2, 4, 1><<<grid, MCX_THREADS, 0, st>>>(p, t);
+  } else mcx_build_fused_kernel<2, 4, 1><<<grid, MCX_THREADS, queue_smem<2>(mcx_build_fused_kernel<2, 4, 1>), st>>>(p, t);
 #undef MCX_LAUNCH_A
   return cudaGetLastError();
 }
@@ -549,8 +656,8 @@ cudaError_t mcx_launch_build_fused_qual(const McxBuildParams &p, const McxTable 
   if(p.r_end <= p.r_begin) return cudaSuccess;
   unsigned grid = grid_for_chunks(p, 4);
   mcx_contig_summary_kernel<<<grid, MCX_THREADS, 0, st>>>(p);
-  if(p.k <= 31) mcx_build_fused_qual_kernel<1><<<grid, MCX_THREADS, 0, st>>>(p, t);
-  else mcx_build_fused_qual_kernel<2><<<grid, MCX_THREADS, 0, st>>>(p, t);
+  if(p.k <= 31) mcx_build_fused_qual_kernel<1><<<grid, MCX_THREADS, queue_smem<1>(mcx_build_fused_qual_kernel<1>), st>>>(p, t);
+  else mcx_build_fused_qual_kernel<2><<<grid, MCX_THREADS, queue_smem<2>(mcx_build_fused_qual_kernel<2>), st>>>(p, t);
   return cudaGetLastError();
 }
 
@@ -590,7 +697,7 @@ cudaError_t mcx_launch_front_flush(const McxTable &t, int may_saturate, unsigned
   mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, mcx_no_bins(), may_saturate, counters);
   cudaError_t e = cudaGetLastError();
   if(e != cudaSuccess) return e;
-  return cudaMemsetAsync(t.front, 0, (4ull << t.front_set_bits) * 8u, st);
+  return cudaMemsetAsync(t.front, 0, (4ull << t.front_set_bits) * 12u, st); // tags + counters (one allocation)
 }
 
 cudaError_t mcx_launch_front_flush_sharded(const McxTable &t, const McxTupleBins &b, int may_saturate,
@@ -600,18 +707,18 @@ cudaError_t mcx_launch_front_flush_sharded(const McxTable &t, const McxTupleBins
   mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, b, may_saturate, counters);
   cudaError_t e = cudaGetLastError();
   if(e != cudaSuccess) return e;
-  return cudaMemsetAsync(t.front, 0, (4ull << t.front_set_bits) * 8u, st);
+  return cudaMemsetAsync(t.front, 0, (4ull << t.front_set_bits) * 12u, st); // tags + counters (one allocation)
 }
 
 cudaError_t mcx_launch_build_sharded(const McxBuildParams &p, const McxTable &t, const McxTupleBins &b, cudaStream_t st)
 {
   if(p.r_end <= p.r_begin) return cudaSuccess;
-  unsigned grid = grid_for_chunks(p, 4);
-  if(p.k <= 31) mcx_build_sharded_kernel<1><<<grid, MCX_THREADS, 0, st>>>(p, t, b);
-  else mcx_build_sharded_kernel<2><<<grid, MCX_THREADS, 0, st>>>(p, t, b);
+  unsigned grid = grid_for_chunks(p, 3);
+  if(p.k <= 31) mcx_build_sharded_kernel<1><<<grid, MCX_THREADS, queue_smem<1>(mcx_build_sharded_kernel<1>), st>>>(p, t, b);
+  else mcx_build_sharded_kernel<2><<<grid, MCX_THREADS, queue_smem<2>(mcx_build_sharded_kernel<2>), st>>>(p, t, b);
   return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------- tuning knobs (experiments)
-void mcx_set_minb(int minb) { g_minb = (minb >= 3 && minb <= 6) ? minb : 4; }
+void mcx_set_minb(int minb) { g_minb = (minb >= 2 && minb <= 6) ? minb : 3; }
 void mcx_set_inflight(int g) { g_inflight = (g == 1 || g == 2 || g == 4) ? g : 2; }

@@ -60,6 +60,7 @@ cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uin
 
 cudaError_t mcx_launch_front_flush(const McxTable &t, int may_saturate, unsigned long long *counters, cudaStream_t st);
 void mcx_set_minb(int minb);
+void mcx_set_hints(uint32_t h);
 void mcx_set_inflight(int g);
 
 // export (mcx_export.cu)

@@ -275,31 +275,55 @@ MCX_HD uint64_t mcx_home_slot(uint32_t c, uint32_t b, uint64_t nslots)
 MCX_HD uint32_t mcx_owner(uint32_t c, uint32_t nparts) { return (uint32_t)(((uint64_t)c * nparts) >> 32); }
 
 // ---------------------------------------------------------------------------
-// Front table (k <= 31, one colour): 8-byte slots [count | edges 8 | tag T], four per 32-byte
-// sector.  The set index and the tag are the top s and low T = 62 - s bits of phi(key), phi a
-// BIJECTION on 62-bit values (odd multiplies and xor-shifts), so (set, tag) identifies the key
-// exactly and the full 8-byte key need not be stored: twice as many hot k-mers per L2 byte.
+// Front table (k <= 31, one colour).  TWO regions, because of what the L2 does (measured with
+// scripts/probe_bench*.cu on a B200, 64 MB footprint, random sets): 32-byte loads alone run at
+// 265 G/s, 32-bit REDs alone at 190 G/s, but a load followed by a RED into the SAME region only
+// at 60 G/s -- any mix of reads and writes over one footprint costs 3x.  With the tags in a
+// region that is (almost) only read and the counters in a region that is only written, the same
+// pair runs at ~100 G/s:
+//   tags     : 8-byte slots, four per 32-byte sector (= one set), read by the probe load;
+//              written when a key claims a way and when an edge bit appears (a handful of times
+//              per k-mer)
+//   counters : one u32 per slot, only ever the target of RED.ADD
+// A key (<= 62 bits = a 30-bit high word kh and a 32-bit low word kl) is sent through a
+// BIJECTION built from three Feistel-style steps that use only 32-bit multiplies,
+//     y1 = kh ^ ((kl * C1) >> 2);   x = kl ^ (y1 * C2);   y = y1 ^ ((x * C3) >> 2);
+// (each step xors one half with a function of the other, so it is its own inverse given the
+// other half).  set = low S bits of y, tag = (x, y >> S): together they identify the key exactly,
+// so the key itself is not stored -- twice as many hot k-mers per L2 byte as key-carrying slots.
+//   tag.lo = x
+//   tag.hi = [ 0 ... | edges : 8 | occupied : 1 | y >> S : 30-S bits ]
+// An empty slot is all zero; the occupied bit makes a tag compare against an empty slot fail
+// without a separate test.
 // ---------------------------------------------------------------------------
-#define MCX_M62 ((1ull << 62) - 1ull)
-#define MCX_PHI_M1 0x2545F4914F6CDD1Dull   /* odd */
-#define MCX_PHI_M2 0x1B03738712FAD5C9ull   /* odd */
-MCX_HD uint64_t mcx_phi(uint64_t x)
+#define MCX_FH_C1 0x9E3779B1u   /* odd */
+#define MCX_FH_C2 0x85EBCA6Bu   /* odd */
+#define MCX_FH_C3 0xC2B2AE35u   /* odd */
+struct McxFKey { uint32_t x, y; };
+MCX_HD McxFKey mcx_fhash(uint64_t key)
 {
-  x = (x * MCX_PHI_M1) & MCX_M62; x ^= x >> 32;
-  x = (x * MCX_PHI_M2) & MCX_M62; x ^= x >> 29;
-  return x;
+  const uint32_t kl = (uint32_t)key, kh = (uint32_t)(key >> 32);
+  McxFKey r;
+  uint32_t y = kh ^ ((kl * MCX_FH_C1) >> 2);
+  r.x = kl ^ (y * MCX_FH_C2);
+  r.y = y ^ ((r.x * MCX_FH_C3) >> 2);
+  return r;
 }
-MCX_HD uint64_t mcx_inv_odd62(uint64_t a) // multiplicative inverse of odd a modulo 2^62 (Newton)
+MCX_HD uint64_t mcx_fhash_inv(uint32_t x, uint32_t y)
 {
-  uint64_t x = a; // correct to 3 bits
-  for(int i = 0; i < 6; i++) x *= 2ull - a * x;
-  return x & MCX_M62;
+  const uint32_t y1 = y ^ ((x * MCX_FH_C3) >> 2);
+  const uint32_t kl = x ^ (y1 * MCX_FH_C2);
+  const uint32_t kh = y1 ^ ((kl * MCX_FH_C1) >> 2);
+  return ((uint64_t)kh << 32) | kl;
 }
-MCX_HD uint64_t mcx_phi_inv(uint64_t y)
+// geometry of the tag's hi word for S set bits (16 <= S <= 24)
+struct McxFrontGeom { uint32_t S, setmask, occ, tagmask, eshift; };
+MCX_HD McxFrontGeom mcx_front_geom_bits(uint32_t S)
 {
-  y ^= (y >> 29) ^ (y >> 58);
-  y = (y * mcx_inv_odd62(MCX_PHI_M2)) & MCX_M62;
-  y ^= y >> 32;
-  y = (y * mcx_inv_odd62(MCX_PHI_M1)) & MCX_M62;
-  return y;
+  McxFrontGeom g;
+  g.S = S; g.setmask = (1u << S) - 1u;
+  g.occ = 1u << (30u - S);            // occupied flag, just above the tag bits
+  g.tagmask = (g.occ << 1) - 1u;      // tag bits + occupied flag
+  g.eshift = 31u - S;                 // edges field
+  return g;
 }

@@ -25,16 +25,20 @@ struct McxTable {
   // L2-resident front table (k <= 31, one colour): a dense write-combining cache in front of
   // the big table.  The big table is >> L2 and a hot k-mer there drags a whole 128-byte L2 line
   // for 16 useful bytes, so on high-coverage input the hot set does not fit L2 (ncu, first
-  // kernel: 127 B of DRAM traffic per occurrence, L2 hit rate 30 %).  Front slots are 8 bytes,
-  //   [ count : 64-8-T bits | edges : 8 | tag : T = 62 - front_set_bits ]
-  // four per 32-byte sector = one set; set index and tag are the two halves of the bijective
-  // mcx_phi(key), so the key is implied exactly.  A key claims a way if one is free (first
-  // come, never evicted); its occurrences are then counted here at L2 speed.  Counts that fill
-  // 1/8 of the count field are moved to the big table on the fly (atomicAnd returns and clears
-  // the count field), everything else by mcx_front_flush_kernel at sync.  Sums and ORs
-  // commute and every record is merged exactly once, so the final table is identical.
-  unsigned long long *front;   // (4 << front_set_bits) slots, or nullptr
+  // kernel: 127 B of DRAM traffic per occurrence, L2 hit rate 30 %).  Layout, the bijective hash
+  // that makes (set, tag) identify the key exactly, and why tags and counters live in separate
+  // regions are in mcx_device.cuh.  A key claims a way if one is free (first come, never
+  // evicted); its occurrences are then counted here at L2 speed (one 32-byte load of the read-
+  // mostly tags, one 32-bit RED into the write-only counters).  mcx_front_flush_kernel merges
+  // every record into the big table at sync; sums and ORs commute and every record is merged
+  // exactly once, so the final table is identical.  The counters are 32 bits wide: the host
+  // flushes before 2^32 - 2^28 positions have been queued since the last flush, so none can wrap.
+  unsigned long long *front;   // tags: (4 << front_set_bits) slots, or nullptr
+  unsigned int *front_cnt;     // counters: one per slot
   uint32_t front_set_bits;     // log2(number of sets); 0 = no front table
+  // L2 eviction policies (createpolicy handles) applied by the kernels that set them; 0 = none
+  uint64_t pol_front;          // front-table probe loads and counter REDs
+  uint64_t pol_big;            // big-table probe loads
 };
 
 #if defined(__CUDACC__)
@@ -45,6 +49,27 @@ struct McxTable {
 __device__ __forceinline__ void mcx_ld256(const void *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d)
 {
   asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+
+__device__ __forceinline__ void mcx_ld256_pol(const void *p, uint64_t pol, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d)
+{
+  if(pol) asm volatile("ld.global.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol));
+  else mcx_ld256(p, a, b, c, d);
+}
+__device__ __forceinline__ void mcx_red_add_pol(unsigned int *p, uint32_t v, uint64_t pol)
+{
+  if(pol) asm volatile("red.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+  else atomicAdd(p, v);
+}
+// hint flags (experiments, MCX_L2_HINTS): 1 = input stream evict_first, 2 = big-table probes evict_first,
+// 4 = front table evict_last
+__device__ __forceinline__ uint64_t mcx_policy_evict_first()
+{
+  uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); return pol;
+}
+__device__ __forceinline__ uint64_t mcx_policy_evict_last()
+{
+  uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol)); return pol;
 }
 
 __device__ __forceinline__ void mcx_ld128(const void *p, uint64_t &a, uint64_t &b)
@@ -99,14 +124,26 @@ __device__ __forceinline__ void mcx_edges_or(uint32_t *slot, uint32_t W, uint32_
 
 // find-or-insert in the big table, then covg[colour] += n (saturating) and edges |= emask.
 // Returns 0 = found, 1 = novel, 2 = table full.
+// `pre` (may be NULL): the 32 bytes at mcx_table_home(), already loaded by the caller so that several
+// probes can be in flight per thread (mcx_table_prefetchable() says whether that sector is what the
+// first probe reads).
 template <int W>
 __device__ __forceinline__ int mcx_table_add(const McxTable &t, const McxKmer<W> &key, uint32_t hc, uint32_t hb,
-                                             uint32_t colour, uint32_t emask, uint32_t n, bool may_saturate);
+                                             uint32_t colour, uint32_t emask, uint32_t n, bool may_saturate,
+                                             const uint64_t *pre = nullptr);
+__device__ __forceinline__ bool mcx_table_prefetchable(const McxTable &t) { return t.stride == 4u || t.stride == 8u; }
+__device__ __forceinline__ const uint32_t *mcx_table_home(const McxTable &t, uint32_t hc, uint32_t hb)
+{
+  uint64_t idx = mcx_home_slot(hc, hb, t.nslots);
+  if(t.stride == 4u) idx &= ~1ull;
+  return t.slots + idx * (uint64_t)t.stride;
+}
 
 // ---- k <= 31 --------------------------------------------------------------
 template <>
 __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer<1> &key, uint32_t hc, uint32_t hb,
-                                                uint32_t colour, uint32_t emask, uint32_t n, bool may_saturate)
+                                                uint32_t colour, uint32_t emask, uint32_t n, bool may_saturate,
+                                                const uint64_t *pre)
 {
   const uint64_t keyf = key.b[0] | MCX_KEY_FLAG;
   uint64_t idx = mcx_home_slot(hc, hb, t.nslots);
@@ -117,7 +154,8 @@ __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer
     for(uint64_t probes = 0; probes < t.nslots; probes += 2) {
       uint32_t *s = t.slots + idx * 4u;
       uint64_t k0, m0, k1, m1;
-      mcx_ld256(s, k0, m0, k1, m1);
+      if(probes == 0 && pre) { k0 = pre[0]; m0 = pre[1]; k1 = pre[2]; m1 = pre[3]; }
+      else mcx_ld256_pol(s, t.pol_big, k0, m0, k1, m1);
       uint32_t *hit = nullptr; uint64_t meta = 0;
       if(k0 == keyf) { hit = s; meta = m0; }
       else if(k1 == keyf) { hit = s + 4; meta = m1; }
@@ -147,7 +185,7 @@ __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer
   // generic stride (C > 1)
   for(uint64_t probes = 0; probes < t.nslots; probes++) {
     uint32_t *s = t.slots + idx * (uint64_t)t.stride;
-    uint64_t cur = *(volatile uint64_t *)s;
+    uint64_t cur = (probes == 0 && pre) ? pre[0] : *(volatile uint64_t *)s;
     if(cur == 0) {
       cur = atomicCAS((unsigned long long *)s, 0ull, (unsigned long long)keyf);
       if(cur == 0) { novel = 1; cur = keyf; }
@@ -165,7 +203,8 @@ __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer
 // ---- 33 <= k <= 63 ---------------------------------------------------------
 template <>
 __device__ __forceinline__ int mcx_table_add<2>(const McxTable &t, const McxKmer<2> &key, uint32_t hc, uint32_t hb,
-                                                uint32_t colour, uint32_t emask, uint32_t n, bool may_saturate)
+                                                uint32_t colour, uint32_t emask, uint32_t n, bool may_saturate,
+                                                const uint64_t *pre)
 {
   const uint64_t k0f = key.b[0] | MCX_KEY_FLAG, k1 = key.b[1];
   uint64_t idx = mcx_home_slot(hc, hb, t.nslots);
@@ -174,7 +213,8 @@ __device__ __forceinline__ int mcx_table_add<2>(const McxTable &t, const McxKmer
     uint32_t *s = t.slots + idx * (uint64_t)t.stride;
     uint64_t c0, c1, m0 = 0, m1 = 0;
     bool have_meta = (t.stride == 8u);
-    if(have_meta) mcx_ld256(s, c0, c1, m0, m1); // 32-byte slot: key + covg + edges in one sector
+    if(probes == 0 && pre) { c0 = pre[0]; c1 = pre[1]; m0 = pre[2]; m1 = pre[3]; }
+    else if(have_meta) mcx_ld256_pol(s, t.pol_big, c0, c1, m0, m1); // 32-byte slot: key + covg + edges in one sector
     else mcx_ld128(s, c0, c1); // one 16-byte transaction: never a torn view of a 128-bit CAS
     if(c0 == 0) {
       mcx_cas128(s, 0ull, 0ull, k0f, k1, c0, c1);
@@ -198,75 +238,64 @@ __device__ __forceinline__ int mcx_table_add<2>(const McxTable &t, const McxKmer
 }
 
 // ---- front table ------------------------------------------------------------
-struct McxFrontGeom { uint32_t T; uint64_t tagmask, one; };
-__device__ __forceinline__ McxFrontGeom mcx_front_geom(const McxTable &t)
-{
-  McxFrontGeom g; g.T = 62u - t.front_set_bits; g.tagmask = (1ull << g.T) - 1ull; g.one = 1ull << (g.T + 8u);
-  return g;
-}
+__device__ __forceinline__ McxFrontGeom mcx_front_geom(const McxTable &t) { return mcx_front_geom_bits(t.front_set_bits); }
 
-// Slow side of the front table for one occurrence of `key` (k <= 31): re-reads the set, claims a
-// free way if the key is not there, drains a count field that is 1/8 full.  Returns true if the
-// Returns 0xFFFFFFFF if the front table did NOT absorb the occurrence; otherwise the count that
-// this thread has just taken OUT of the front table and must add to the big table (0 almost always).
-static __device__ __noinline__ uint32_t mcx_front_add_slow(McxTable t, uint64_t key, uint32_t emask)
+// Slow side of the front table for one occurrence of `key` (k <= 31): re-reads the set, counts the
+// occurrence if the key is there, claims a free way if it is not, adds a missing edge bit.
+// Returns false if the front table cannot absorb the occurrence (the set is full of other keys):
+// then it belongs to the big table.
+// (Tried and dropped, profiles/r1g_experiments.txt: letting such keys live "displaced" in the
+// neighbouring sector, and a staged drain that keeps four parked items in flight per thread --
+// the extra probes and the local-memory arrays cost more than the DRAM round trips they saved.)
+static __device__ __noinline__ bool mcx_front_add_slow(McxTable t, uint64_t key, uint32_t emask)
 {
   const McxFrontGeom g = mcx_front_geom(t);
-  const uint64_t y = mcx_phi(key), tag = y & g.tagmask, ebits = (uint64_t)emask << g.T;
-  unsigned long long *set = t.front + ((y >> g.T) << 2);
-  uint64_t v0, v1, v2, v3;
-  mcx_ld256(set, v0, v1, v2, v3);
-  uint32_t drained = 0;
+  const McxFKey fk = mcx_fhash(key);
+  const uint32_t th = (fk.y >> g.S) | g.occ, eb = emask << g.eshift;
+  const uint64_t s4 = (uint64_t)(fk.y & g.setmask) << 2;
+  unsigned long long *set = t.front + s4;
+  uint64_t v[4];
+  mcx_ld256_pol(set, t.pol_front, v[0], v[1], v[2], v[3]);
+  int w = -1; uint32_t seen_hi = 0;
 #pragma unroll
-  for(int w = 0; w < 4; w++) {
-    const uint64_t v = w == 0 ? v0 : (w == 1 ? v1 : (w == 2 ? v2 : v3));
-    if(v != 0 && (v & g.tagmask) == tag) {
-      atomicAdd(&set[w], (unsigned long long)g.one);
-      if((v & ebits) != ebits) atomicOr(&set[w], (unsigned long long)ebits);
-      if((v >> (g.T + 8u)) >= (1ull << (53u - g.T))) {
-        // the count field is 56-T >= 12 bits wide (15 at the default size): move it to the big
-        // table once it is 1/8 full, long before it can wrap (a wrap would need 7/8 of the range,
-        // > 28k increments of ONE address at the default size, inside one load->RED latency; the
-        // L2 atomic unit retires ~1 per clock per address)
-        uint64_t old = atomicAnd(&set[w], (unsigned long long)(g.one - 1ull));
-        drained = (uint32_t)(old >> (g.T + 8u));
-      }
-      return drained;
-    }
+  for(int i = 3; i >= 0; i--) {
+    const uint32_t lo = (uint32_t)v[i], hi = (uint32_t)(v[i] >> 32);
+    if(lo == fk.x && ((hi ^ th) & g.tagmask) == 0u) { w = i; seen_hi = hi; }
   }
+  if(w < 0) {
 #pragma unroll
-  for(int w = 0; w < 4; w++) {
-    const uint64_t v = w == 0 ? v0 : (w == 1 ? v1 : (w == 2 ? v2 : v3));
-    if(v == 0) {
-      uint64_t old = atomicCAS(&set[w], 0ull, (unsigned long long)(tag | ebits | g.one));
-      if(old == 0) return 0u;                              // claimed, first count and edges included
-      if((old & g.tagmask) == tag) {                       // lost the race to the same key
-        atomicAdd(&set[w], (unsigned long long)g.one);
-        if((old & ebits) != ebits) atomicOr(&set[w], (unsigned long long)ebits);
-        return 0u;
+    for(int i = 0; i < 4; i++) {
+      if(w < 0 && v[i] == 0) {
+        const uint64_t mine = ((uint64_t)(th | eb) << 32) | fk.x;
+        const uint64_t old = atomicCAS(&set[i], 0ull, (unsigned long long)mine);
+        const uint32_t olo = (uint32_t)old, ohi = (uint32_t)(old >> 32);
+        if(old == 0) { w = i; seen_hi = th | eb; }                                       // claimed, edges included
+        else if(olo == fk.x && ((ohi ^ th) & g.tagmask) == 0u) { w = i; seen_hi = ohi; } // lost the race to the same key
       }
     }
+    if(w < 0) return false;
   }
-  return 0xFFFFFFFFu;
+  mcx_red_add_pol(t.front_cnt + s4 + (uint32_t)w, 1u, t.pol_front);
+  if((seen_hi & eb) != eb) atomicOr(reinterpret_cast<unsigned int *>(&set[w]) + 1, eb);
+  return true;
 }
 
 // Fast side: the set has already been loaded (v0..v3).  Handles the overwhelmingly common case --
-// the key sits in the set, its edge bits are already there, its count field is far from full --
-// with ONE RED and returns true; anything else returns false and goes to mcx_front_add_slow.
-__device__ __forceinline__ bool mcx_front_hit(const McxFrontGeom &g, unsigned long long *set, uint64_t tag, uint64_t ebits,
+// the key sits in the set and its edge bits are already there -- with ONE 32-bit RED into the
+// counter region and returns true; anything else returns false (-> parked, mcx_front_add_slow).
+__device__ __forceinline__ bool mcx_front_hit(const McxFrontGeom &g, unsigned int *cnt_set, uint64_t pol, uint32_t x, uint32_t th, uint32_t eb,
                                               uint64_t v0, uint64_t v1, uint64_t v2, uint64_t v3)
 {
-  const uint64_t lim = 1ull << (53u - g.T);
-  int w = -1; uint64_t v = 0;
-  if((v0 & g.tagmask) == tag && v0 != 0) { w = 0; v = v0; }
-  else if((v1 & g.tagmask) == tag && v1 != 0) { w = 1; v = v1; }
-  else if((v2 & g.tagmask) == tag && v2 != 0) { w = 2; v = v2; }
-  else if((v3 & g.tagmask) == tag && v3 != 0) { w = 3; v = v3; }
-  if(w < 0 || (v & ebits) != ebits || (v >> (g.T + 8u)) >= lim) return false;
-  // count and edge fields sit entirely in the high 32-bit word (T + 8 >= 32 for every allowed
-  // size), so the increment is a 32-bit RED like the big table's covg++ (64-bit REDs measured
-  // ~30 % slower here)
-  atomicAdd(reinterpret_cast<unsigned int *>(&set[w]) + 1, (unsigned int)(g.one >> 32));
+  const uint32_t mask = g.tagmask;
+  const uint32_t h0 = (uint32_t)(v0 >> 32), h1 = (uint32_t)(v1 >> 32), h2 = (uint32_t)(v2 >> 32), h3 = (uint32_t)(v3 >> 32);
+  const bool m0 = ((uint32_t)v0 == x) & (((h0 ^ th) & mask) == 0u);
+  const bool m1 = ((uint32_t)v1 == x) & (((h1 ^ th) & mask) == 0u);
+  const bool m2 = ((uint32_t)v2 == x) & (((h2 ^ th) & mask) == 0u);
+  const bool m3 = ((uint32_t)v3 == x) & (((h3 ^ th) & mask) == 0u);
+  const uint32_t hi = m0 ? h0 : (m1 ? h1 : (m2 ? h2 : h3));
+  const uint32_t way = m0 ? 0u : (m1 ? 1u : (m2 ? 2u : 3u));
+  if(!(m0 | m1 | m2 | m3) || (hi & eb) != eb) return false;
+  mcx_red_add_pol(cnt_set + way, 1u, pol);
   return true;
 }
 

@@ -411,7 +411,7 @@ def test_high_multiplicity_kmers_drain_the_front_table(M, oracle):
     """k-mers seen far more often than the front table's count field holds (poly-A, a short
     tandem repeat): counts are drained to the big table on the fly and nothing is lost"""
     rng = random.Random(4)
-    reads = ["A" * 150] * 3000 + ["ACGTTGCA" * 20] * 2000 + rand_reads(rng, 500, 150, 5000, perr=0.0, pN=0.0, lower=0.0)
+    reads = ["A" * 150] * 40000 + ["ACGTTGCA" * 20] * 2000 + rand_reads(rng, 500, 150, 5000, perr=0.0, pN=0.0, lower=0.0)
     rng.shuffle(reads)
     recs, ost = oracle_records(oracle, reads, 31)
     g = M.Graph(31, 1, 1 << 18)
@@ -426,5 +426,5 @@ def test_high_multiplicity_kmers_drain_the_front_table(M, oracle):
         assert got[i:i + 8] == recs[i:i + 8]
         assert int.from_bytes(got[i + 8:i + 12], "little") == 3 * int.from_bytes(recs[i + 8:i + 12], "little")
         assert got[i + 12] == recs[i + 12]
-    assert max(int.from_bytes(got[i + 8:i + 12], "little") for i in range(0, len(got), rb)) >= 3 * 3000 * 120
+    assert max(int.from_bytes(got[i + 8:i + 12], "little") for i in range(0, len(got), rb)) >= 3 * 40000 * 120
     g.close()
