@@ -18,6 +18,9 @@ import os
 import time
 
 
+FRONT_SPAN = 0xE0000000  # positions between two flushes of a sharded graph's front table (library limit: 0xF0000000)
+
+
 def exchange_counts(dist, counts):
     """counts[d] = tuples this rank holds for rank d  ->  recv[s] = tuples rank s holds for us"""
     import torch
@@ -67,6 +70,7 @@ class ShardedBuilder:
         self.rmasks = torch.empty(n, dtype=torch.int32, device=device)
         self.counts = torch.zeros(world, dtype=torch.int64, device=device)
         self.launches = 0
+        self.pending = 0
 
     def set_stream(self, stream):
         self.g.set_stream(stream.cuda_stream)
@@ -89,6 +93,9 @@ class ShardedBuilder:
         occurrence leaves as a tuple)"""
         g = self.g
         if aggregate:
+            if self.pending + nbytes >= FRONT_SPAN:   # 32-bit front-table counters (see RoutedBuilder.add_batch)
+                self.flush()
+            self.pending += nbytes
             g.add_reads_sharded(seq_addr, nbytes, self.world, self.rank, self.cap, self.keys.data_ptr(),
                                 self.masks.data_ptr(), self.counts.data_ptr())
         else:
@@ -99,6 +106,7 @@ class ShardedBuilder:
 
     def flush(self):
         """end of a step: forward the aggregated front-table records of keys owned elsewhere"""
+        self.pending = 0
         self.g.flush_sharded(self.world, self.rank, self.cap, self.keys.data_ptr(), self.masks.data_ptr(),
                              self.counts.data_ptr())
         self.launches += 1
@@ -143,6 +151,7 @@ class RoutedBuilder:
         self.launches = 0
         self.prof = None
         self.sent = []
+        self.pending = 0
 
     def set_stream(self, stream):
         self.g.set_stream(stream.cuda_stream)
@@ -214,6 +223,12 @@ class RoutedBuilder:
             self.prof.append((name, e))
 
     def add_batch(self, seq_addr, nbytes, colour=0):
+        # the front table counts in 32 bits: it must be flushed (a collective step: every rank does it
+        # at the same batch, so batches are assumed to be the same size on every rank) before 2^32
+        # positions have gone through it
+        if self.pending + nbytes >= FRONT_SPAN:
+            self.flush()
+        self.pending += nbytes
         self._mark("start")
         self.produce(seq_addr, nbytes, colour)
         self._mark("produce")
@@ -223,6 +238,7 @@ class RoutedBuilder:
         self._mark("consume")
 
     def flush(self):
+        self.pending = 0
         self._mark("start")
         self.produce_flush()
         self._mark("flush_produce")
