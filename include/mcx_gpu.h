@@ -157,6 +157,12 @@ int mcx_graph_insert_tuples(mcx_graph *g, const uint64_t *keys, const uint32_t *
  * sender wrote travels on the stream, the host never waits for it */
 int mcx_graph_insert_tuples_n(mcx_graph *g, const uint64_t *keys, const uint32_t *meta, const uint64_t *n_dev,
                               uint64_t n_max, uint32_t colour);
+/* same, on a CUDA stream of the caller's (cudaStream_t as void*; NULL = the graph's stream): inserting
+ * what arrived for batch b can then overlap the sharded kernel of batch b+1 (table updates commute;
+ * the caller orders the stream against the counter exchange and the ring reuse, and joins it before
+ * mcx_graph_sync) */
+int mcx_graph_insert_tuples_on(mcx_graph *g, void *cuda_stream, const uint64_t *keys, const uint32_t *meta,
+                               const uint64_t *n_dev, uint64_t n_max, uint32_t colour);
 
 /* Routed variants: ONE kernel does the compute step and the all-to-all.  keys_dst[d] / meta_dst[d]
  * (host arrays of nparts device pointers; entry my_part is ignored) are where tuples for shard d

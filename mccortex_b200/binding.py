@@ -89,6 +89,7 @@ def lib():
     L.mcx_graph_add_reads_sharded.argtypes = [vp, C.POINTER(ReadBatch), u32, u32, u64, vp, vp, vp]
     L.mcx_graph_flush_sharded.argtypes = [vp, u32, u32, u64, vp, vp, vp]
     L.mcx_graph_insert_tuples_n.argtypes = [vp, vp, vp, vp, u64, u32]
+    L.mcx_graph_insert_tuples_on.argtypes = [vp, vp, vp, vp, vp, u64, u32]
     L.mcx_graph_add_reads_routed.argtypes = [vp, C.POINTER(ReadBatch), u32, u32, u64, C.POINTER(vp), C.POINTER(vp), vp]
     L.mcx_graph_flush_routed.argtypes = [vp, u32, u32, u64, C.POINTER(vp), C.POINTER(vp), vp]
     L.mcx_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
@@ -287,6 +288,10 @@ class Graph:
     def flush_routed(self, nparts, my_part, cap_per_part, keys_addrs, meta_addrs, counts_addr):
         _ck(lib().mcx_graph_flush_routed(self.h, nparts, my_part, cap_per_part, self._ptrs(keys_addrs),
                                          self._ptrs(meta_addrs), counts_addr), "mcx_graph_flush_routed")
+
+    def insert_tuples_on(self, cuda_stream, keys_addr, masks_addr, n_dev_addr, n_max, colour=0):
+        _ck(lib().mcx_graph_insert_tuples_on(self.h, C.c_void_p(cuda_stream or None), keys_addr, masks_addr, n_dev_addr,
+                                             n_max, colour), "mcx_graph_insert_tuples_on")
 
     def insert_tuples_n(self, keys_addr, masks_addr, n_dev_addr, n_max, colour=0):
         _ck(lib().mcx_graph_insert_tuples_n(self.h, keys_addr, masks_addr, n_dev_addr, n_max, colour),

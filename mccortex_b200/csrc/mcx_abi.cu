@@ -615,6 +615,18 @@ extern "C" int mcx_graph_insert_tuples(mcx_graph *g, const uint64_t *keys, const
 
 // same, but the number of tuples is a device word (written by the sender, exchanged on the stream):
 // nothing on this path makes the host wait for the GPU
+extern "C" int mcx_graph_insert_tuples_on(mcx_graph *g, void *cuda_stream, const uint64_t *keys, const uint32_t *masks,
+                                          const uint64_t *n_dev, uint64_t n_max, uint32_t colour)
+{
+  if(!g || colour >= g->ncols || !n_dev || (n_max && (!keys || !masks))) return MCX_ERR_BAD_ARG;
+  CU(cudaSetDevice(g->device));
+  if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
+  g->occ_bound += n_max;
+  CU(mcx_launch_insert_tuples(keys, masks, n_max, n_dev, g->k, g->table, colour, g->occ_bound >= 0xF0000000ull, g->d_counters,
+                              cuda_stream ? (cudaStream_t)cuda_stream : primary(g)));
+  return MCX_OK;
+}
+
 extern "C" int mcx_graph_insert_tuples_n(mcx_graph *g, const uint64_t *keys, const uint32_t *masks, const uint64_t *n_dev,
                                          uint64_t n_max, uint32_t colour)
 {

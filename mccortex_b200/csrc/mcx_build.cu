@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t
     const uint64_t v = t.front[i];
     if(v == 0) continue;
     const uint32_t hi = (uint32_t)(v >> 32);
-    McxKmer<1> key; key.b[0] = mcx_fhash_inv((uint32_t)v, ((hi & (g.occ - 1u)) << g.S) | (uint32_t)(i >> 2));
+    McxKmer<1> key; key.b[0] = mcx_fhash_inv((uint32_t)v, ((hi & (g.occ - 1u)) << g.S) | ((uint32_t)(i >> 2) ^ (hi >> 31))); // displaced: home = the neighbouring set
     const uint32_t edges = (hi >> g.eshift) & 0xFFu;
     uint32_t count = t.front_cnt[i];
     uint32_t hb, hc = mcx_lookup3<1>(key, 0u, &hb);

@@ -242,17 +242,18 @@ __device__ __forceinline__ McxFrontGeom mcx_front_geom(const McxTable &t) { retu
 
 // Slow side of the front table for one occurrence of `key` (k <= 31): re-reads the set, counts the
 // occurrence if the key is there, claims a free way if it is not, adds a missing edge bit.
-// Returns false if the front table cannot absorb the occurrence (the set is full of other keys):
-// then it belongs to the big table.
-// (Tried and dropped, profiles/r1g_experiments.txt: letting such keys live "displaced" in the
-// neighbouring sector, and a staged drain that keeps four parked items in flight per thread --
-// the extra probes and the local-memory arrays cost more than the DRAM round trips they saved.)
-static __device__ __noinline__ bool mcx_front_add_slow(McxTable t, uint64_t key, uint32_t emask)
+// A key that finds its home sector full of other keys (4.8 % of the hot k-mers of the bench
+// workload: Poisson(2.2) keys per 4-way set) may live DISPLACED in the neighbouring sector
+// (set ^ 1), marked by the top bit of its tag word so that it is never mistaken for a key of that
+// set.  The hot pass only looks at the home sector, so a displaced key is always parked and ends
+// up here: two L2 loads and a RED instead of a DRAM round trip to the big table -- and, in the
+// sharded build, no tuple.  Returns false if the front table cannot absorb the occurrence (both
+// sectors are full of other keys): then it belongs to the big table.
+#define MCX_FRONT_DISPLACED 0x80000000u
+__device__ __forceinline__ bool mcx_front_resolve_sector(const McxTable &t, const McxFrontGeom &g, uint64_t s4, uint32_t x,
+                                                         uint32_t th, uint32_t eb)
 {
-  const McxFrontGeom g = mcx_front_geom(t);
-  const McxFKey fk = mcx_fhash(key);
-  const uint32_t th = (fk.y >> g.S) | g.occ, eb = emask << g.eshift;
-  const uint64_t s4 = (uint64_t)(fk.y & g.setmask) << 2;
+  const uint32_t mask = g.tagmask | MCX_FRONT_DISPLACED;
   unsigned long long *set = t.front + s4;
   uint64_t v[4];
   mcx_ld256_pol(set, t.pol_front, v[0], v[1], v[2], v[3]);
@@ -260,17 +261,17 @@ static __device__ __noinline__ bool mcx_front_add_slow(McxTable t, uint64_t key,
 #pragma unroll
   for(int i = 3; i >= 0; i--) {
     const uint32_t lo = (uint32_t)v[i], hi = (uint32_t)(v[i] >> 32);
-    if(lo == fk.x && ((hi ^ th) & g.tagmask) == 0u) { w = i; seen_hi = hi; }
+    if(lo == x && ((hi ^ th) & mask) == 0u) { w = i; seen_hi = hi; }
   }
   if(w < 0) {
 #pragma unroll
     for(int i = 0; i < 4; i++) {
       if(w < 0 && v[i] == 0) {
-        const uint64_t mine = ((uint64_t)(th | eb) << 32) | fk.x;
+        const uint64_t mine = ((uint64_t)(th | eb) << 32) | x;
         const uint64_t old = atomicCAS(&set[i], 0ull, (unsigned long long)mine);
         const uint32_t olo = (uint32_t)old, ohi = (uint32_t)(old >> 32);
-        if(old == 0) { w = i; seen_hi = th | eb; }                                       // claimed, edges included
-        else if(olo == fk.x && ((ohi ^ th) & g.tagmask) == 0u) { w = i; seen_hi = ohi; } // lost the race to the same key
+        if(old == 0) { w = i; seen_hi = th | eb; }                                  // claimed, edges included
+        else if(olo == x && ((ohi ^ th) & mask) == 0u) { w = i; seen_hi = ohi; }    // lost the race to the same key
       }
     }
     if(w < 0) return false;
@@ -279,6 +280,15 @@ static __device__ __noinline__ bool mcx_front_add_slow(McxTable t, uint64_t key,
   if((seen_hi & eb) != eb) atomicOr(reinterpret_cast<unsigned int *>(&set[w]) + 1, eb);
   return true;
 }
+static __device__ __noinline__ bool mcx_front_add_slow(McxTable t, uint64_t key, uint32_t emask)
+{
+  const McxFrontGeom g = mcx_front_geom(t);
+  const McxFKey fk = mcx_fhash(key);
+  const uint32_t th = (fk.y >> g.S) | g.occ, eb = emask << g.eshift;
+  const uint64_t s4 = (uint64_t)(fk.y & g.setmask) << 2;
+  if(mcx_front_resolve_sector(t, g, s4, fk.x, th, eb)) return true;
+  return mcx_front_resolve_sector(t, g, s4 ^ 4ull, fk.x, th | MCX_FRONT_DISPLACED, eb);
+}
 
 // Fast side: the set has already been loaded (v0..v3).  Handles the overwhelmingly common case --
 // the key sits in the set and its edge bits are already there -- with ONE 32-bit RED into the
@@ -286,7 +296,7 @@ static __device__ __noinline__ bool mcx_front_add_slow(McxTable t, uint64_t key,
 __device__ __forceinline__ bool mcx_front_hit(const McxFrontGeom &g, unsigned int *cnt_set, uint64_t pol, uint32_t x, uint32_t th, uint32_t eb,
                                               uint64_t v0, uint64_t v1, uint64_t v2, uint64_t v3)
 {
-  const uint32_t mask = g.tagmask;
+  const uint32_t mask = g.tagmask | MCX_FRONT_DISPLACED; // a displaced entry belongs to the neighbouring set: never a match here
   const uint32_t h0 = (uint32_t)(v0 >> 32), h1 = (uint32_t)(v1 >> 32), h2 = (uint32_t)(v2 >> 32), h3 = (uint32_t)(v3 >> 32);
   const bool m0 = ((uint32_t)v0 == x) & (((h0 ^ th) & mask) == 0u);
   const bool m1 = ((uint32_t)v1 == x) & (((h1 ^ th) & mask) == 0u);

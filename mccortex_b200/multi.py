@@ -152,6 +152,7 @@ class RoutedBuilder:
         self.prof = None
         self.sent = []
         self.pending = 0
+        self.insert_stream = None
 
     def set_stream(self, stream):
         self.g.set_stream(stream.cuda_stream)
@@ -199,20 +200,48 @@ class RoutedBuilder:
 
     def exchange_counts(self):
         j = self.batch % self.NRING
+        if self.insert_stream is not None and self.batch >= 1:
+            # completing this exchange tells the peers that the ring of the PREVIOUS batch is free again
+            import torch
+            torch.cuda.current_stream().wait_event(self.insert_done[(self.batch - 1) % self.NRING])
         self.dist.all_to_all_single(self.rcounts[j], self.counts[j])
         if self.prof is not None:
             self.sent.append(self.counts[j].tolist())
 
     def consume(self, colour=0):
+        """insert what arrived for this batch.  With an insert stream (use_insert_stream) the kernels
+        run beside the NEXT batch's sharded kernel: they are ordered behind this batch's counter
+        exchange, and the next exchange -- the event that lets peers overwrite this ring two batches
+        later -- waits for them."""
         j = self.batch % self.NRING
         cap, W = self.cap, self.W
+        ist = self.insert_stream
+        if ist is not None:
+            import torch
+            ist.wait_stream(torch.cuda.current_stream())
         for s in range(self.world):
             if s == self.rank:
                 continue
-            self.g.insert_tuples_n(self.ring_k[j] + s * cap * W * 8, self.ring_m[j] + s * cap * 4,
-                                   self.rcounts[j].data_ptr() + 8 * s, cap, colour=colour)
+            args = (self.ring_k[j] + s * cap * W * 8, self.ring_m[j] + s * cap * 4, self.rcounts[j].data_ptr() + 8 * s, cap)
+            if ist is not None:
+                self.g.insert_tuples_on(ist.cuda_stream, *args, colour=colour)
+            else:
+                self.g.insert_tuples_n(*args, colour=colour)
             self.launches += 1
+        if ist is not None:
+            self.insert_done[j].record(ist)
         self.batch += 1
+
+    def use_insert_stream(self, stream):
+        import torch
+        self.insert_stream = stream
+        self.insert_done = [torch.cuda.Event() for _ in range(self.NRING)]
+
+    def join_inserts(self):
+        """make the current stream wait for every insert kernel queued so far"""
+        if self.insert_stream is not None:
+            import torch
+            torch.cuda.current_stream().wait_stream(self.insert_stream)
 
     def _mark(self, name):
         # optional per-stage device timing (MCX_MULTI_PROFILE=1): CUDA events on the current stream
@@ -245,6 +274,7 @@ class RoutedBuilder:
         self.exchange_counts()
         self._mark("counts")
         self.consume()
+        self.join_inserts()
         self._mark("flush_consume")
 
     def profile_summary(self):
@@ -308,6 +338,8 @@ def bench_multi(args, rank, world, local, dist):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     sb.set_stream(stream)
+    if routed and os.environ.get("MCX_MULTI_OVERLAP", "1") != "0":
+        sb.use_insert_stream(torch.cuda.Stream(device=dev))
 
     def add(addr, nbytes_):
         if routed:
