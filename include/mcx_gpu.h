@@ -120,6 +120,19 @@ int mcx_graph_sync(mcx_graph *g, mcx_load_stats *stats);
  * build_graph() returns (src/tools/build_graph.c:283-300). */
 int mcx_graph_flush(mcx_graph *g);
 
+/* replaces graph_load(file, prefs, stats) (src/graph/graphs_load.c:83-208) for records the caller has
+ * read from a .ctx file: nrecords packed records of the FILE's layout (W x u64 key, file_ncols x u32
+ * covg, file_ncols x u8 edges).  (from_col[i], into_col[i]), i < nmap, is the reference's FileFilter
+ * (src/basic/file_filter.h): coverage of file colour from is added (saturating) to graph colour into,
+ * edges are ORed; a k-mer whose selected colours all have zero coverage is skipped.
+ * flags: MCX_LOAD_MUST_EXIST = only k-mers already in the graph (GraphLoadingPrefs.must_exist_in_graph).
+ * Synchronous.  *nkmers_loaded / *nkmers_novel (may be NULL) = GraphLoadingStats of this call.
+ * The novel k-mers are also part of what the next mcx_graph_sync reports as num_kmers_novel. */
+#define MCX_LOAD_MUST_EXIST 1u
+int mcx_graph_load_records(mcx_graph *g, const void *records, uint64_t nrecords, uint32_t file_ncols, uint32_t mem,
+                           const uint32_t *from_col, const uint32_t *into_col, uint32_t nmap, uint32_t flags,
+                           uint64_t *nkmers_loaded, uint64_t *nkmers_novel);
+
 /* replaces hash_table_print_stats inputs (src/graph/hash_table.h:73): occupancy */
 int mcx_graph_stats(mcx_graph *g, uint64_t *nkmers, uint64_t *capacity);
 

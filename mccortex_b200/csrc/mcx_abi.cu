@@ -639,6 +639,43 @@ extern "C" int mcx_graph_insert_tuples_n(mcx_graph *g, const uint64_t *keys, con
   return MCX_OK;
 }
 
+// replaces graph_load() for records the caller has read from a .ctx file (any number of file colours;
+// the (from, into) pairs are the reference's FileFilter).  Synchronous: returns after the records
+// are merged, with the counts the reference keeps in GraphLoadingStats.
+extern "C" int mcx_graph_load_records(mcx_graph *g, const void *records, uint64_t nrecords, uint32_t file_ncols, uint32_t mem,
+                                      const uint32_t *from_col, const uint32_t *into_col, uint32_t nmap, uint32_t flags,
+                                      uint64_t *nkmers_loaded, uint64_t *nkmers_novel)
+{
+  if(!g || !file_ncols || (nrecords && !records) || (nmap && (!from_col || !into_col))) return MCX_ERR_BAD_ARG;
+  for(uint32_t m = 0; m < nmap; m++) if(from_col[m] >= file_ncols || into_col[m] >= g->ncols) return MCX_ERR_BAD_ARG;
+  CU(cudaSetDevice(g->device));
+  if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
+  if(nkmers_loaded) *nkmers_loaded = 0;
+  if(nkmers_novel) *nkmers_novel = 0;
+  if(nrecords == 0 || nmap == 0) return MCX_OK;
+  cudaStream_t st = primary(g);
+  const size_t rec_bytes = 8u * g->W + 5u * (size_t)file_ncols, bytes = rec_bytes * nrecords;
+  const size_t map_off = (bytes + 255) & ~(size_t)255;
+  const uint8_t *drecs = (const uint8_t *)records;
+  int r = ensure_tmp(g, map_off + 8u * (size_t)nmap + 256 + (mem == MCX_MEM_HOST ? 0 : 0)); if(r) return r;
+  if(mem == MCX_MEM_HOST) { CU(cudaMemcpyAsync(g->d_tmp, records, bytes, cudaMemcpyHostToDevice, st)); drecs = g->d_tmp; }
+  else if(mem != MCX_MEM_DEVICE) return MCX_ERR_BAD_ARG;
+  uint32_t *d_from = (uint32_t *)(g->d_tmp + map_off), *d_into = d_from + nmap;
+  CU(cudaMemcpyAsync(d_from, from_col, 4u * (size_t)nmap, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_into, into_col, 4u * (size_t)nmap, cudaMemcpyHostToDevice, st));
+  // counts of THIS call: read the running counters before and after
+  unsigned long long c0[MCX_NCOUNTERS], c1[MCX_NCOUNTERS];
+  CU(cudaMemcpyAsync(c0, g->d_counters, sizeof(c0), cudaMemcpyDeviceToHost, st));
+  g->occ_bound = 0xF0000000ull; // file coverages can be anything: saturation-aware adds from here on
+  CU(mcx_launch_load_records(drecs, nrecords, file_ncols, d_from, d_into, nmap, flags, g->k, g->table, g->d_counters, st));
+  CU(cudaMemcpyAsync(c1, g->d_counters, sizeof(c1), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if(nkmers_loaded) *nkmers_loaded = c1[MCX_CNT_RECS_LOADED] - c0[MCX_CNT_RECS_LOADED];
+  if(nkmers_novel) *nkmers_novel = c1[MCX_CNT_NOVEL] - c0[MCX_CNT_NOVEL];
+  if(c1[MCX_CNT_FULL]) { snprintf(g_err, sizeof(g_err), "Hash table is full"); return MCX_ERR_TABLE_FULL; }
+  return MCX_OK;
+}
+
 // ---- device buffers that peers can map (one process per GPU: CUDA IPC over NVLink) ----------
 extern "C" int mcx_device_alloc(int device, size_t bytes, void **dptr)
 {

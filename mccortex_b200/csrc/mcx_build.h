@@ -12,6 +12,7 @@ enum {
   MCX_CNT_READS,       // read terminators seen                (num_se_reads)
   MCX_CNT_FULL,        // non-zero: table (or tuple bin) overflowed
   MCX_CNT_INSERTED,    // tuples inserted by kernel C
+  MCX_CNT_RECS_LOADED, // graph-file records merged (mcx_ctxload.cu)
   MCX_NCOUNTERS = 8
 };
 
@@ -62,6 +63,11 @@ cudaError_t mcx_launch_front_flush(const McxTable &t, int may_saturate, unsigned
 void mcx_set_minb(int minb);
 void mcx_set_hints(uint32_t h);
 void mcx_set_inflight(int g);
+
+// graph files (mcx_ctxload.cu): from_col / into_col are device arrays of nmap colour pairs; flags bit 0 = must exist
+cudaError_t mcx_launch_load_records(const uint8_t *recs, uint64_t n, uint32_t file_ncols, const uint32_t *from_col,
+                                    const uint32_t *into_col, uint32_t nmap, uint32_t flags, uint32_t k, const McxTable &t,
+                                    unsigned long long *counters, cudaStream_t st);
 
 // export (mcx_export.cu)
 struct McxExport {

@@ -7,8 +7,7 @@
  * what mccortex31 / mccortex63 write for their k ranges.
  *
  * Not (yet) supported, and rejected with an error rather than silently ignored:
- *   -p/--remove-pcr (order dependent in the reference), -g/--graph, -I/--intersect,
- *   -Q/--fq-cutoff on inputs that carry qualities, SAM/BAM/CRAM input.
+ *   -p/--remove-pcr (order dependent in the reference), -I/--intersect, SAM/BAM/CRAM input.
  */
 #include "mcx_host.h"
 #include <ctype.h>
@@ -49,7 +48,7 @@ static const char build_usage[] =
 "  -p, --remove-pcr         Remove (or keep) PCR duplicate reads [not supported]\n"
 "  -P, --keep-pcr           Don't do PCR duplicate removal [default]\n"
 "  -M, --matepair <orient>  Mate pair orientation: FF,FR,RF,RR [default: FR]\n"
-"  -g, --graph <in.ctx>     Load samples from a graph file (.ctx) [not supported]\n"
+"  -g, --graph <in.ctx>     Load samples from a graph file (.ctx)\n"
 "  -I, --intersect <i.ctx>  Only load kmers that appear in i.ctx [not supported]\n"
 "  -S, --sort               Output a graph file ordered by kmer\n"
 "  -D, --device <id>        CUDA device [default: 0]\n"
@@ -79,7 +78,8 @@ typedef struct {
 } BuildTask;
 
 static BuildTask *tasks = NULL; static size_t ntasks = 0, tasks_cap = 0;
-static char **sample_names = NULL; static size_t nsamples = 0;
+static char **sample_names = NULL; static size_t *sample_cols = NULL; static size_t nsamples = 0;
+static McxCtxFile **gfiles = NULL; static size_t ngfiles = 0;
 static size_t nthreads = 0, kmer_size = 0, output_colours = 0;
 static bool mem_set = false, nkmers_set = false, force = false, sort_kmers = false;
 static size_t mem_to_use = MCX_DEFAULT_MEM, num_kmers = MCX_DEFAULT_NKMERS;
@@ -192,6 +192,8 @@ static void parse_args(int argc, char **argv)
         intocolour++;
         check_sample_name(optarg);
         sample_names = realloc(sample_names, (nsamples + 1) * sizeof(char *));
+        sample_cols = realloc(sample_cols, (nsamples + 1) * sizeof(size_t));
+        sample_cols[nsamples] = (size_t)intocolour;
         sample_names[nsamples++] = optarg;
         sample_named = true;
         break;
@@ -211,7 +213,15 @@ static void parse_args(int argc, char **argv)
       case 'H': prefs.hp_cutoff = parse_uint8(cmd, optarg); pref_unused = true; break;
       case 'p': mcx_die("--remove-pcr is not supported by "CMD" (order-dependent in the reference)");
       case 'P': pref_unused = true; break;
-      case 'g': mcx_die("--graph is not supported by "CMD" yet");
+      case 'g': { /* src/commands/ctx_build.c:189-196 */
+        if(intocolour == -1) intocolour = 0;
+        McxCtxFile *gf = mcx_ctx_open(optarg, (size_t)intocolour);
+        if((int)gf->into_ncols - 1 > intocolour) intocolour = (int)gf->into_ncols - 1;
+        gfiles = realloc(gfiles, (ngfiles + 1) * sizeof(*gfiles));
+        gfiles[ngfiles++] = gf;
+        sample_named = false;
+        break;
+      }
       case 'I': mcx_die("--intersect is not supported by "CMD" yet");
       case 'D': device = (int)parse_size(cmd, optarg, false); break;
       case ':': case '?':
@@ -229,6 +239,9 @@ static void parse_args(int argc, char **argv)
   if(nsamples == 0) usage_err("No inputs given");
   if(pref_unused) usage_err("Arguments not given BEFORE sequence file");
   if(!kmer_size) mcx_die("kmer size not set with -k <K>");
+  for(size_t i = 0; i < ngfiles; i++)
+    if(gfiles[i]->kmer_size != kmer_size)
+      usage_err("Input graph kmer_size doesn't match [%u vs %zu]: %s", gfiles[i]->kmer_size, kmer_size, gfiles[i]->input);
   output_colours = (size_t)(intocolour + (sample_named ? 1 : 0));
 }
 
@@ -279,8 +292,13 @@ static int ctx_build(int argc, char **argv)
   size_t i, s, t;
   parse_args(argc, argv);
 
+  size_t max_kmers = 0;
+  for(i = 0; i < ngfiles; i++) {
+    mcx_status("[FileFilter] Reading file %s [%u src colour%s]", gfiles[i]->path, gfiles[i]->num_of_cols, gfiles[i]->num_of_cols == 1 ? "" : "s");
+    max_kmers += gfiles[i]->num_of_kmers < 0 ? 0 : (size_t)gfiles[i]->num_of_kmers;
+  }
   for(s = t = 0; s < nsamples || t < ntasks;) {
-    if(t == ntasks || (s < nsamples && s <= tasks[t].prefs.colour)) { mcx_status("[sample] %zu: %s", s, sample_names[s]); s++; }
+    if(t == ntasks || (s < nsamples && sample_cols[s] <= tasks[t].prefs.colour)) { mcx_status("[sample] %zu: %s", s, sample_names[s]); s++; }
     else {
       char off[32] = "auto-detect", cut[32] = "off", hp[32] = "off";
       if(tasks[t].prefs.fq_offset) sprintf(off, "%u", tasks[t].prefs.fq_offset);
@@ -293,7 +311,6 @@ static int ctx_build(int argc, char **argv)
   }
 
   /* src/commands/ctx_build.c:285-289 + src/basic/async_read_io.c:313-334: 5 x file bytes */
-  size_t max_kmers = 0;
   for(t = 0; t < ntasks; t++) {
     int64_t fsize = mcx_seq_file_size(tasks[t].file);
     if(fsize < 0) { max_kmers = SIZE_MAX; break; }
@@ -318,7 +335,22 @@ static int ctx_build(int argc, char **argv)
 
   McxGInfo *ginfo = calloc(output_colours, sizeof(McxGInfo));
   for(i = 0; i < output_colours; i++) mcx_ginfo_init(&ginfo[i]);
-  for(i = 0; i < nsamples; i++) mcx_ginfo_set_name(&ginfo[i], sample_names[i]);
+
+  /* src/commands/ctx_build.c:362-377: graph files first (their header metadata is merged into the
+   * colours they load into), then the --sample names OVERWRITE the names of the colours they name */
+  for(i = 0; i < ngfiles; i++) {
+    uint64_t nread = 0, nloaded = 0, nnovel = 0;
+    r = mcx_ctx_load(g, gfiles[i], ginfo, output_colours, false, &nread, &nloaded, &nnovel);
+    if(r) die_mcx(r, "loading graph file");
+    mcx_load_stats st; /* fold the novel k-mers of the file into the table occupancy */
+    r = mcx_graph_sync(g, &st);
+    if(r) die_mcx(r, "loading graph file");
+    uint64_t nk0 = 0, cap0 = 0; mcx_graph_stats(g, &nk0, &cap0);
+    { char a[64], b[64]; mcx_ulong_to_str(nk0, a); mcx_ulong_to_str(cap0, b);
+      mcx_status("[hasht] table occupancy: %s / %s (%.2f%%)", a, b, cap0 ? 100.0 * nk0 / cap0 : 0.0); }
+    mcx_ctx_close(gfiles[i]);
+  }
+  for(i = 0; i < nsamples; i++) mcx_ginfo_set_name(&ginfo[sample_cols[i]], sample_names[i]);
 
   /* src/commands/ctx_build.c:389-407: build_graph() on batches of <= 10 tasks.  Quirk Q1
    * (src/tools/build_graph.c:242 vs :276,:285-300): within one call every task's header

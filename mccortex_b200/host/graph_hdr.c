@@ -9,12 +9,47 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* src/basic/graph_info.c:4-10,60-67 */
 void mcx_ginfo_init(McxGInfo *g)
 {
   g->mean_read_length = 0; g->total_sequence = 0; g->seq_err = 0.01;
   g->sample_name = strdup("undefined");
+  memset(&g->cleaning, 0, sizeof(g->cleaning));
+  g->cleaning.intersection_name = strdup("undefined");
 }
-void mcx_ginfo_free(McxGInfo *g) { free(g->sample_name); g->sample_name = NULL; }
+void mcx_ginfo_free(McxGInfo *g)
+{
+  free(g->sample_name); g->sample_name = NULL;
+  free(g->cleaning.intersection_name); g->cleaning.intersection_name = NULL;
+}
+static char *str_append(char *dst, const char *sep, const char *src)
+{
+  size_t n = strlen(dst) + strlen(sep) + strlen(src) + 1;
+  char *s = malloc(n);
+  strcpy(s, dst); strcat(s, sep); strcat(s, src);
+  free(dst);
+  return s;
+}
+/* graph_info_append_intersect, src/basic/graph_info.c:88-101 */
+static void cleaning_append_intersect(McxCleaning *c, const char *name)
+{
+  if(!c->is_graph_intersection) { free(c->intersection_name); c->intersection_name = strdup(name); }
+  else c->intersection_name = str_append(c->intersection_name, ",", name);
+  c->is_graph_intersection = true;
+}
+/* error_cleaning_merge, src/basic/graph_info.c:34-58 */
+static void cleaning_merge(McxCleaning *dst, const McxCleaning *src)
+{
+  dst->cleaned_tips |= src->cleaned_tips;
+  dst->cleaned_unitigs |= src->cleaned_unitigs;
+  dst->cleaned_kmers |= src->cleaned_kmers;
+  if(src->clean_unitigs_thresh > 0 && (dst->clean_unitigs_thresh == 0 || src->clean_unitigs_thresh < dst->clean_unitigs_thresh))
+    dst->clean_unitigs_thresh = src->clean_unitigs_thresh;
+  if(src->clean_kmers_thresh > 0 && (dst->clean_kmers_thresh == 0 || src->clean_kmers_thresh < dst->clean_kmers_thresh))
+    dst->clean_kmers_thresh = src->clean_kmers_thresh;
+  if(src->is_graph_intersection) cleaning_append_intersect(dst, src->intersection_name);
+  dst->is_graph_intersection |= src->is_graph_intersection;
+}
 void mcx_ginfo_set_name(McxGInfo *g, const char *name) { free(g->sample_name); g->sample_name = strdup(name); }
 
 void mcx_ginfo_update_contigs(McxGInfo *g, uint64_t added_seq, uint64_t num_contigs)
@@ -32,12 +67,7 @@ void mcx_ginfo_merge(McxGInfo *dst, const McxGInfo *src)
 {
   if(strcmp(src->sample_name, "undefined") != 0) {
     if(strcmp(dst->sample_name, "undefined") == 0) mcx_ginfo_set_name(dst, src->sample_name);
-    else {
-      size_t n = strlen(dst->sample_name) + 1 + strlen(src->sample_name) + 1;
-      char *s = malloc(n);
-      strcpy(s, dst->sample_name); strcat(s, ","); strcat(s, src->sample_name);
-      free(dst->sample_name); dst->sample_name = s;
-    }
+    else dst->sample_name = str_append(dst->sample_name, ",", src->sample_name);
   }
   uint64_t total = dst->total_sequence + src->total_sequence;
   if(total > 0) {
@@ -47,6 +77,7 @@ void mcx_ginfo_merge(McxGInfo *dst, const McxGInfo *src)
       src_contigs = ((double)src->total_sequence / src->mean_read_length) + 0.5;
     mcx_ginfo_update_contigs(dst, src->total_sequence, src_contigs);
   }
+  cleaning_merge(&dst->cleaning, &src->cleaning);
   dst->total_sequence = total;
 }
 
@@ -76,10 +107,13 @@ size_t mcx_write_ctx_header(FILE *fh, uint32_t kmer_size, uint32_t ncols, const 
     b += put(fh, ld, sizeof(ld));
   }
   for(i = 0; i < ncols; i++) {
-    /* ErrorCleaning of a freshly built graph: nothing cleaned, no intersection (graph_info.c:4-10) */
-    unsigned char flags[4] = {0, 0, 0, 0}; uint32_t zero = 0, len = 9;
-    b += put(fh, flags, 4); b += put(fh, &zero, 4); b += put(fh, &zero, 4);
-    b += put(fh, &len, 4); b += put(fh, "undefined", 9);
+    /* write_error_cleaning_object, src/graph/graph_writer.c:33-58 */
+    const McxCleaning *c = &h[i].cleaning;
+    unsigned char flags[4] = {c->cleaned_tips, c->cleaned_unitigs, c->cleaned_kmers, c->is_graph_intersection};
+    uint32_t len = (uint32_t)strlen(c->intersection_name);
+    uint32_t thr_unitigs = c->cleaned_unitigs ? c->clean_unitigs_thresh : 0, thr_kmers = c->cleaned_kmers ? c->clean_kmers_thresh : 0;
+    b += put(fh, flags, 4); b += put(fh, &thr_unitigs, 4); b += put(fh, &thr_kmers, 4);
+    b += put(fh, &len, 4); b += put(fh, c->intersection_name, len);
   }
   b += put(fh, "CORTEX", 6);
   for(i = 0; i < ncols; i++) mcx_ginfo_free(&h[i]);

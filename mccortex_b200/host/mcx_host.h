@@ -38,11 +38,17 @@ size_t mcx_get_kmers_in_hash(size_t mem_to_use, bool mem_to_use_set, size_t num_
                              bool use_mem_limit, size_t *graph_mem_ptr);
 
 /* ---- header metadata: src/basic/graph_info.{c,h}, src/graph/graph_writer.c -- */
+typedef struct {              /* ErrorCleaning, src/basic/graph_info.h */
+  bool cleaned_tips, cleaned_unitigs, cleaned_kmers, is_graph_intersection;
+  uint32_t clean_unitigs_thresh, clean_kmers_thresh;
+  char *intersection_name;    /* malloc'd, "undefined" by default */
+} McxCleaning;
 typedef struct {
   uint32_t mean_read_length;
   uint64_t total_sequence;
   long double seq_err;
   char *sample_name;          /* malloc'd */
+  McxCleaning cleaning;
 } McxGInfo;
 void mcx_ginfo_init(McxGInfo *g);
 void mcx_ginfo_free(McxGInfo *g);
@@ -52,6 +58,26 @@ void mcx_ginfo_merge(McxGInfo *dst, const McxGInfo *src);
 /* writes the .ctx v6 header for ncols colours after merging every colour into a fresh
  * header entry, exactly as graph_writer_mkhdr does; returns bytes written */
 size_t mcx_write_ctx_header(FILE *fh, uint32_t kmer_size, uint32_t ncols, const McxGInfo *ginfo);
+
+/* ---- graph files: src/graph/graph_file_reader.{c,h}, src/basic/file_filter.{c,h}, src/basic/range.c,
+ *      src/graph/graphs_load.c ------------------------------------------------------------- */
+typedef struct {
+  char *input, *path;           /* "[into:]path[:from]" as given, and the bare path */
+  FILE *fh;
+  uint32_t version, kmer_size, num_of_bitfields, num_of_cols;
+  McxGInfo *ginfo;              /* num_of_cols entries */
+  size_t hdr_size;
+  int64_t file_size, num_of_kmers;   /* -1 if unknown */
+  uint32_t nfilter, *from_col, *into_col;   /* FileFilter, sorted by into */
+  uint32_t into_ncols;          /* max into + 1 */
+} McxCtxFile;
+/* graph_file_open2(file, input, "r", true, into_offset): dies on a malformed file like the reference */
+McxCtxFile *mcx_ctx_open(const char *input, size_t into_offset);
+void mcx_ctx_close(McxCtxFile *f);
+/* graph_load(): merge the header's colours into ginfo[] (graph_load_ginfo) and the records into g.
+ * must_exist: only k-mers already in g.  Returns 0 or an MCX_ERR_*. */
+int mcx_ctx_load(mcx_graph *g, McxCtxFile *f, McxGInfo *ginfo, size_t graph_ncols, bool must_exist,
+                 uint64_t *nkmers_read, uint64_t *nkmers_loaded, uint64_t *nkmers_novel);
 
 /* ---- sequence input: libs/seq_file/seq_file.h, src/basic/seq_reader.c -------- */
 typedef struct McxSeqFile McxSeqFile;

@@ -228,8 +228,12 @@ typedef struct {
   uint32_t mean_read_length;
   uint64_t total_sequence;
   long double seq_err;
-  char name[256];
-} OrcGInfo; /* src/basic/graph_info.h:20-27 (cleaning is all-default for build) */
+  char name[1024];
+  /* ErrorCleaning, src/basic/graph_info.h: all-default unless a graph file is loaded (build --graph) */
+  uint8_t cleaned_tips, cleaned_unitigs, cleaned_kmers, is_graph_intersection;
+  uint32_t clean_unitigs_thresh, clean_kmers_thresh;
+  char isec_name[1024];
+} OrcGInfo; /* src/basic/graph_info.h:20-27 */
 
 typedef struct {
   size_t k, ncols; int W;
@@ -245,6 +249,9 @@ static void orc_ginfo_init(OrcGInfo *g) /* src/basic/graph_info.c:60-67 */
 {
   strcpy(g->name, "undefined");
   g->total_sequence = 0; g->mean_read_length = 0; g->seq_err = 0.01;
+  g->cleaned_tips = g->cleaned_unitigs = g->cleaned_kmers = g->is_graph_intersection = 0;   /* graph_info.c:4-10 */
+  g->clean_unitigs_thresh = g->clean_kmers_thresh = 0;
+  strcpy(g->isec_name, "undefined");
 }
 
 OrcGraph *orc_graph_new(size_t k, size_t ncols, uint64_t capacity)
@@ -430,6 +437,19 @@ static void orc_ginfo_merge(OrcGInfo *dst, const OrcGInfo *src)
       src_num_contigs = ((double)src->total_sequence / src->mean_read_length) + 0.5;
     orc_ginfo_update_contigs(dst, src->total_sequence, src_num_contigs);
   }
+  /* error_cleaning_merge, src/basic/graph_info.c:34-58 (+ graph_info_append_intersect :88-101) */
+  dst->cleaned_tips |= src->cleaned_tips;
+  dst->cleaned_unitigs |= src->cleaned_unitigs;
+  dst->cleaned_kmers |= src->cleaned_kmers;
+  if(src->clean_unitigs_thresh > 0 && (dst->clean_unitigs_thresh == 0 || src->clean_unitigs_thresh < dst->clean_unitigs_thresh))
+    dst->clean_unitigs_thresh = src->clean_unitigs_thresh;
+  if(src->clean_kmers_thresh > 0 && (dst->clean_kmers_thresh == 0 || src->clean_kmers_thresh < dst->clean_kmers_thresh))
+    dst->clean_kmers_thresh = src->clean_kmers_thresh;
+  if(src->is_graph_intersection) {
+    if(!dst->is_graph_intersection) strcpy(dst->isec_name, src->isec_name);
+    else { strcat(dst->isec_name, ","); strcat(dst->isec_name, src->isec_name); }
+    dst->is_graph_intersection = 1;
+  }
   dst->total_sequence = total_sequence;
 }
 
@@ -467,16 +487,89 @@ size_t orc_graph_write_header(const OrcGraph *g, uint8_t *buf)
     off = orc_put(buf, off, ld, sizeof(long double));
   }
   for(i = 0; i < ncols; i++) {
-    uint8_t flags[4] = {0,0,0,0}; uint32_t z = 0, len = 9;
+    uint8_t flags[4] = {h[i].cleaned_tips, h[i].cleaned_unitigs, h[i].cleaned_kmers, h[i].is_graph_intersection};
+    uint32_t tu = h[i].cleaned_unitigs ? h[i].clean_unitigs_thresh : 0, tk = h[i].cleaned_kmers ? h[i].clean_kmers_thresh : 0;
+    uint32_t len = (uint32_t)strlen(h[i].isec_name);
     off = orc_put(buf, off, flags, 4);
-    off = orc_put(buf, off, &z, 4);
-    off = orc_put(buf, off, &z, 4);
+    off = orc_put(buf, off, &tu, 4);
+    off = orc_put(buf, off, &tk, 4);
     off = orc_put(buf, off, &len, 4);
-    off = orc_put(buf, off, "undefined", 9);
+    off = orc_put(buf, off, h[i].isec_name, len);
   }
   off = orc_put(buf, off, "CORTEX", 6);
   free(h);
   return off;
+}
+
+/* ------------------------------------------------------------- build --graph
+ * graph_load(), src/graph/graphs_load.c:83-208, on the records of a .ctx file that the caller has
+ * read; the colour filter is the list of (from, into) pairs of src/basic/file_filter.c.
+ * Per record (graph_file_read, graph_file_reader.c:389-404): covgs[into] = SAFE_ADD(covgs[into],
+ * file covg[from]); edges[into] |= file edges[from]; skipped if every covgs[into] is zero
+ * (graphs_load.c:121-124); find-or-insert (or find only: must_exist_in_graph); then
+ * db_node_add_col_covg (saturating) and col_edges[into] |= edges (edge_mask = 0xff without --intersect). */
+static uint32_t orc_safe_add_covg(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; return s > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s; }
+uint64_t orc_graph_load_records(OrcGraph *g, const uint8_t *recs, uint64_t n, uint32_t file_ncols,
+                                const uint32_t *from, const uint32_t *into, uint32_t nmap, int must_exist, uint64_t *novel_out)
+{
+  const size_t W = (size_t)g->W, C = g->ncols, rec = 8*W + 5*(size_t)file_ncols;
+  uint32_t *cv = (uint32_t*)calloc(C, 4); uint8_t *ed = (uint8_t*)calloc(C, 1);
+  uint64_t i, loaded = 0, novel = 0; uint32_t m; size_t c;
+  for(i = 0; i < n; i++) {
+    const uint8_t *r = recs + i * rec;
+    OrcKmer key; memset(&key, 0, sizeof(key));
+    memcpy(key.b, r, 8*W);
+    memset(cv, 0, 4*C); memset(ed, 0, C);
+    for(m = 0; m < nmap; m++) {
+      uint32_t fc; memcpy(&fc, r + 8*W + 4*(size_t)from[m], 4);
+      cv[into[m]] = orc_safe_add_covg(cv[into[m]], fc);
+      ed[into[m]] |= r[8*W + 4*(size_t)file_ncols + from[m]];
+    }
+    uint32_t keep = 0;
+    for(c = 0; c < C; c++) keep |= cv[c];
+    if(!keep) continue;
+    uint64_t slot; int found = 0;
+    if(must_exist) {
+      /* hash_table_find */
+      uint64_t h = orc_lookup3(key.b, (int)W, 0, NULL) & g->mask; int hit = 0; size_t w;
+      for(;; h = (h + 1) & g->mask) {
+        uint64_t *sl = g->keys + h * W;
+        if(sl[0] == 0) break;
+        if(sl[0] == (key.b[0] | ORC_FLAG)) { for(w = 1; w < W && sl[w] == key.b[w]; w++) {} if(w == W) { hit = 1; break; } }
+      }
+      if(!hit) continue;
+      slot = h;
+    } else {
+      slot = orc_find_or_insert(g, &key, &found);
+      novel += !found;
+    }
+    for(c = 0; c < C; c++) {
+      g->covgs[slot*C + c] = orc_safe_add_covg(g->covgs[slot*C + c], cv[c]);
+      g->edges[slot*C + c] |= ed[c];
+    }
+    loaded++;
+  }
+  free(cv); free(ed);
+  if(novel_out) *novel_out = novel;
+  return loaded;
+}
+
+/* graph_load_ginfo (graphs_load.c:45-76): graph_info_merge(ginfo + into, file header colour).
+ * seq_err16: the 16 bytes of the x87 long double as stored in the file. */
+void orc_graph_merge_file_ginfo(OrcGraph *g, size_t into, uint32_t mean_read_length, uint64_t total_sequence,
+                                const char *name, const uint8_t *seq_err16, const uint8_t *flags4,
+                                uint32_t thr_unitigs, uint32_t thr_kmers, const char *isec_name)
+{
+  OrcGInfo src; orc_ginfo_init(&src);
+  src.mean_read_length = mean_read_length; src.total_sequence = total_sequence;
+  strncpy(src.name, name, sizeof(src.name) - 1); src.name[sizeof(src.name) - 1] = 0;
+  memcpy(&src.seq_err, seq_err16, 10);
+  src.cleaned_tips = flags4[0]; src.cleaned_unitigs = flags4[1]; src.cleaned_kmers = flags4[2]; src.is_graph_intersection = flags4[3];
+  /* graph_file_reader.c:221-243: thresholds without the matching flag are dropped */
+  src.clean_unitigs_thresh = src.cleaned_unitigs ? thr_unitigs : 0;
+  src.clean_kmers_thresh = src.cleaned_kmers ? thr_kmers : 0;
+  strncpy(src.isec_name, isec_name, sizeof(src.isec_name) - 1); src.isec_name[sizeof(src.isec_name) - 1] = 0;
+  orc_ginfo_merge(&g->ginfo[into], &src);
 }
 
 static int orc_W_for_sort;

@@ -74,6 +74,11 @@ def lib():
         L.orc_hash_table_cap.argtypes = [C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)]
         L.orc_hash_table_mem_limit.restype = C.c_uint64
         L.orc_hash_table_mem_limit.argtypes = [C.c_size_t, C.c_size_t, C.POINTER(C.c_uint64)]
+        L.orc_graph_load_records.restype = C.c_uint64
+        L.orc_graph_load_records.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32),
+                                             C.POINTER(C.c_uint32), C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
+        L.orc_graph_merge_file_ginfo.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_char_p, C.c_char_p,
+                                                 C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p]
         L.orc_guess_fq_offset.restype = C.c_int
         L.orc_guess_fq_offset.argtypes = [C.c_char_p, C.c_size_t]
         _lib = L
@@ -122,6 +127,21 @@ class Graph:
             raise IOError("cannot open " + path)
         return st
 
+    def load_ctx(self, spec, into_offset=0, must_exist=False):
+        """graph_load() of `[into:]path[:from]` (file_filter.c syntax); returns (ctx, loaded, novel)"""
+        ctx = CtxFile(spec, into_offset)
+        for fr, into in ctx.filter:
+            h = ctx.ginfo[fr]
+            lib().orc_graph_merge_file_ginfo(self.h, into, h["mean"], h["total"], h["name"], h["seq_err"], h["flags"],
+                                             h["thr_unitigs"], h["thr_kmers"], h["isec_name"])
+        n = len(ctx.records) // ctx.rec_bytes
+        fr = (C.c_uint32 * len(ctx.filter))(*[f for f, _ in ctx.filter])
+        to = (C.c_uint32 * len(ctx.filter))(*[t for _, t in ctx.filter])
+        novel = C.c_uint64(0)
+        loaded = lib().orc_graph_load_records(self.h, ctx.records, n, ctx.ncols, fr, to, len(ctx.filter), int(must_exist),
+                                              C.byref(novel))
+        return ctx, int(loaded), int(novel.value)
+
     def update_ginfo(self, colour, stats):
         lib().orc_graph_update_ginfo(self.h, colour, C.byref(stats))
 
@@ -147,7 +167,131 @@ class Graph:
         return buf.raw[:n]
 
 
+def _parse_range(s, range_max):
+    """src/basic/range.c: '1,3-5' -> [1,3,4,5]; '' -> 0..range_max; descending ranges stop at their end"""
+    out = []
+    for part in [p for p in s.split(",") if p != ""]:
+        if part == "*":
+            out += list(range(0, range_max + 1))
+            continue
+        a, _, b = part.partition("-")
+        a = int(a)
+        b = int(b) if b != "" else a
+        if a > range_max or b > range_max:
+            raise ValueError("Invalid filter path")
+        out += list(range(a, b + 1)) if a <= b else list(range(a, b - 1, -1))
+    return out if out else list(range(0, range_max + 1))
+
+
+class CtxFile:
+    """A .ctx file + colour filter: graph_file_open2 (graph_file_reader.c:272-322), file_filter_set_cols
+    (file_filter.c:77-153).  Test infrastructure: reads the whole file."""
+
+    def __init__(self, spec, into_offset=0):
+        import re
+        import struct
+        m = re.match(r"^(?:([0-9,\-]+):)?(.*?)(?::([0-9,\-]*))?$", spec)
+        into_f, self.path, from_f = m.group(1), m.group(2), m.group(3)
+        data = open(self.path, "rb").read()
+        assert data[:6] == b"CORTEX"
+        self.version, self.k, self.W, self.ncols = struct.unpack_from("<IIII", data, 6)
+        off = 22
+        means = struct.unpack_from("<%dI" % self.ncols, data, off); off += 4 * self.ncols
+        totals = struct.unpack_from("<%dQ" % self.ncols, data, off); off += 8 * self.ncols
+        names = []
+        for _ in range(self.ncols):
+            (ln,) = struct.unpack_from("<I", data, off); off += 4
+            names.append(data[off:off + ln]); off += ln
+        errs = [data[off + 16 * i: off + 16 * i + 16] for i in range(self.ncols)]; off += 16 * self.ncols
+        self.ginfo = []
+        for i in range(self.ncols):
+            flags = data[off:off + 4]; tu, tk, ln = struct.unpack_from("<III", data, off + 4); off += 16
+            isec = data[off:off + ln]; off += ln
+            self.ginfo.append(dict(mean=means[i], total=totals[i], name=names[i].split(b"\0")[0], seq_err=errs[i], flags=flags,
+                                   thr_unitigs=tu, thr_kmers=tk, isec_name=isec.split(b"\0")[0]))
+        assert data[off:off + 6] == b"CORTEX"
+        off += 6
+        self.hdr_size = off
+        self.rec_bytes = 8 * self.W + 5 * self.ncols
+        self.records = data[off:off + (len(data) - off) // self.rec_bytes * self.rec_bytes]
+        frm = _parse_range(from_f or "", self.ncols - 1)
+        if into_f is not None:
+            into = _parse_range(into_f, 1 << 30)
+            if len(into) == 1:
+                into = into * len(frm)
+            assert len(into) == len(frm), "Invalid filter path"
+        else:
+            into = [into_offset + i for i in range(len(frm))]
+        self.filter = sorted(zip(frm, into), key=lambda p: p[1])
+        self.into_ncols = max(i for _, i in self.filter) + 1
+
+
 MAX_IO_THREADS = 10  # src/global/global.h:41
+
+
+def build_ctx_args(k, args, capacity=1 << 20):
+    """Oracle equivalent of `mccortex build -k K -S <args>` for the argument forms
+    `-g [into:]in.ctx[:from]`, `-s name`, `-1 file` (and -Q/-O/-H before a file), in command-line order:
+    colour bookkeeping of ctx_build.c:158-196, graphs loaded before reads (:362-377), --sample names
+    overwrite the names of the colours they name (:379-382), stats credited per batch of <= 10 tasks (Q1)."""
+    intocolour, sample_named = -1, False
+    names, tasks, graphs = [], [], []
+    fq_cutoff = fq_offset = hp_cutoff = 0
+    it = iter(args)
+    for a in it:
+        if a in ("-s", "--sample"):
+            intocolour += 1
+            names.append((intocolour, next(it)))
+            sample_named = True
+        elif a in ("-1", "--seq"):
+            tasks.append((intocolour, dict(path=next(it), fq_cutoff=fq_cutoff, fq_offset=fq_offset, hp_cutoff=hp_cutoff)))
+        elif a in ("-Q", "--fq-cutoff"):
+            fq_cutoff = int(next(it))
+        elif a in ("-O", "--fq-offset"):
+            fq_offset = int(next(it))
+        elif a in ("-H", "--cut-hp"):
+            hp_cutoff = int(next(it))
+        elif a in ("-g", "--graph"):
+            if intocolour == -1:
+                intocolour = 0
+            spec = next(it)
+            ctx = CtxFile(spec, intocolour)
+            assert ctx.k == k
+            intocolour = max(intocolour, ctx.into_ncols - 1)
+            graphs.append((spec, ctx.filter[0][1] if False else None, intocolour, ctx))
+            sample_named = False
+        else:
+            raise ValueError("unsupported build argument for the oracle: " + a)
+    ncols = intocolour + (1 if sample_named else 0)
+    g = Graph(k, ncols, capacity)
+    offs = []
+    # into_offset of each graph = intocolour at the time its -g was parsed
+    intocolour = -1
+    it = iter(args)
+    for a in it:
+        if a in ("-s", "--sample"):
+            intocolour += 1; next(it)
+        elif a in ("-g", "--graph"):
+            if intocolour == -1:
+                intocolour = 0
+            spec = next(it)
+            ctx, _, _ = g.load_ctx(spec, intocolour)
+            intocolour = max(intocolour, ctx.into_ncols - 1)
+        elif a in ("-1", "--seq", "-Q", "--fq-cutoff", "-O", "--fq-offset", "-H", "--cut-hp"):
+            next(it)
+    for col, name in names:
+        g.set_name(col, name)
+    for start in range(0, len(tasks), MAX_IO_THREADS):
+        st = Stats()
+        for col, t in tasks[start:start + MAX_IO_THREADS]:
+            g.load_file(t["path"], col, t["fq_cutoff"], t["fq_offset"], t["hp_cutoff"], st)
+        g.update_ginfo(tasks[start][0], st)
+    out = g.dump_sorted()
+    full = g.full
+    g.close()
+    if full:
+        raise RuntimeError("Hash table is full")
+    return out
 
 
 def build_ctx(k, samples, capacity=1 << 20):

@@ -82,8 +82,28 @@ def main():
     add("fq10_k21", 21, [dict(name="q", tasks=[dict(file="q.fq", fq_cutoff=10)])])
     add("fq20_hp5_k15", 15, [dict(name="q", tasks=[dict(file="q.fq", fq_cutoff=20, hp_cutoff=5)])])
 
+    # build --graph: graph files (the goldens above) merged with reads.  Arguments are
+    # given raw; "@/" stands for this directory.
+    graph_cases = []
+
+    def add_graph(name, k, raw):
+        args = [a.replace("@/", HERE + "/") for a in raw]
+        ctx = name + ".ctx"
+        data = O.ref_build(k, args, os.path.join(HERE, ctx), threads=3)
+        graph_cases.append(dict(name=name, k=k, ctx=ctx, md5=hashlib.md5(data).hexdigest(), ref_args=raw))
+        print(name, len(data), graph_cases[-1]["md5"])
+
+    add_graph("graph_then_reads_k21", 21, ["-g", "@/two_colours_k21.ctx", "-s", "z", "-1", "@/b.fa"])
+    add_graph("graph_from_filter_k21", 21, ["-g", "@/two_colours_k21.ctx:1", "-s", "z", "-1", "@/a.fa"])
+    add_graph("graph_flatten_k21", 21, ["-g", "0:@/two_colours_k21.ctx:0,1", "-s", "z", "-1", "@/b.fa"])
+    add_graph("graphs_same_colour_k31", 31, ["-g", "@/reads_k31.ctx", "-g", "@/long_record_k31.ctx", "-s", "s2", "-1", "@/a.fa"])
+    add_graph("graph_k63", 63, ["-g", "@/reads_k63.ctx", "-s", "t", "-1", "@/b.fa"])
+    add_graph("sample_graph_sample_k21", 21, ["-s", "first", "-1", "@/b.fa", "-g", "@/two_colours_k21.ctx:1,0", "-s", "last", "-1", "@/g1.fa"])
+
     with open(os.path.join(HERE, "cases.json"), "w") as f:
         json.dump(cases, f, indent=1)
+    with open(os.path.join(HERE, "graph_cases.json"), "w") as f:
+        json.dump(graph_cases, f, indent=1)
 
 
 if __name__ == "__main__":

@@ -43,6 +43,24 @@ def test_cli_matches_golden_ctx(case, tmp_path):
     assert got == ref
 
 
+GRAPH_CASES = json.load(open(os.path.join(GOLD, "graph_cases.json")))
+
+
+@pytest.mark.parametrize("case", [c["name"] for c in GRAPH_CASES])
+def test_cli_graph_loading_matches_golden_ctx(case, tmp_path):
+    """build --graph [into:]in.ctx[:from]: graph files are merged on the GPU
+    (mcx_graph_load_records), header metadata on the host; bytes == the compiled reference's"""
+    c = next(x for x in GRAPH_CASES if x["name"] == case)
+    out = str(tmp_path / "out.ctx")
+    args = ["-q", "-f", "-m", "1G", "-n", "1M", "-k", str(c["k"]), "-S"]
+    args += [a.replace("@/", GOLD + "/") for a in c["ref_args"]] + [out]
+    _run(args)
+    got = open(out, "rb").read()
+    ref = open(os.path.join(GOLD, c["ctx"]), "rb").read()
+    assert hashlib.md5(ref).hexdigest() == c["md5"]
+    assert got == ref
+
+
 def test_cli_many_tasks_header_quirks(tmp_path, oracle):
     """13 tasks in 2 colours: batches of 10 tasks, stats credited to the first task's colour
     (quirk Q1) and the lossy mean_read_length round trips (Q4).  Checked against the oracle,
@@ -118,3 +136,30 @@ def test_cli_matches_reference_binary_and_check(tmp_path, oracle, k):
     _run(["-q", "-f", "-m", "1G", "-n", "4M", "-k", str(k), "-s", "s", "-1", str(fa), str(uns)])
     oracle.ref_run(k, ["sort", "-q", str(uns)])
     assert open(uns, "rb").read() == ref
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "mccortex31")), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("k", [27, 41])
+def test_cli_graph_loading_matches_reference_binary(tmp_path, oracle, k):
+    """build --graph on fresh inputs: our own unsorted 2-colour output and a reference-built graph go
+    back in through colour filters; bytes equal to the reference binary given the same arguments,
+    and the reference's `check` accepts the result"""
+    rng = random.Random(2000 + k)
+    fas = []
+    for i in range(3):
+        p = tmp_path / ("r%d.fa" % i)
+        p.write_text("".join(">r%d\n%s\n" % (j, r) for j, r in enumerate(rand_reads(rng, 400, (20, 220), 9000, perr=0.004))))
+        fas.append(str(p))
+    g2 = str(tmp_path / "g2.ctx")   # written by us, unsorted, 2 colours
+    _run(["-q", "-f", "-m", "1G", "-n", "2M", "-k", str(k), "-s", "a", "-1", fas[0], "-s", "b", "-1", fas[1], g2])
+    g1 = str(tmp_path / "g1.ctx")   # written by the reference
+    oracle.ref_build(k, ["-s", "c", "-1", fas[2]], g1, threads=2, nkmers="2M")
+    for n, args in enumerate((["-g", g2, "-g", g1, "-s", "n", "-1", fas[0]],
+                              ["-g", "1:" + g2 + ":0", "-s", "n", "-1", fas[1], "-1", fas[2]],
+                              ["-g", g2 + ":1-0", "-g", "0,0:" + g2, "-s", "n", "-1", fas[2]])):
+        mine = str(tmp_path / ("mine%d.ctx" % n))
+        _run(["-q", "-f", "-m", "1G", "-n", "2M", "-k", str(k), "-S"] + args + [mine])
+        ref = oracle.ref_build(k, args, str(tmp_path / "ref.ctx"), threads=3, nkmers="2M")
+        assert open(mine, "rb").read() == ref, args
+        r = oracle.ref_run(k, ["check", "-q", mine], check=False)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]

@@ -63,6 +63,43 @@ def test_oracle_vs_golden_ctx(oracle, case):
     assert out == ref
 
 
+GRAPH_CASES = __import__("json").load(open(os.path.join(GOLD, "graph_cases.json")))
+
+
+@pytest.mark.parametrize("case", [c["name"] for c in GRAPH_CASES])
+def test_oracle_graph_loading_vs_golden_ctx(oracle, case):
+    """build --graph: the restatement of graph_load / file_filter / graph_info_merge against what the
+    compiled reference wrote (tests/golden/graph_cases.json, make_golden.py)."""
+    c = next(x for x in GRAPH_CASES if x["name"] == case)
+    out = oracle.build_ctx_args(c["k"], [a.replace("@/", GOLD + "/") for a in c["ref_args"]])
+    with open(os.path.join(GOLD, c["ctx"]), "rb") as f:
+        ref = f.read()
+    assert hashlib.md5(ref).hexdigest() == c["md5"]
+    assert out == ref
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "mccortex31")),
+                    reason="oracle/_ref not built")
+def test_oracle_graph_loading_vs_reference_binary(oracle, tmp_path):
+    """fresh seeded inputs: two graphs built by the reference, then merged with reads through filters"""
+    rng = random.Random(99)
+    fas = []
+    for i in range(3):
+        p = tmp_path / ("r%d.fa" % i)
+        p.write_text("".join(">r%d\n%s\n" % (j, r) for j, r in enumerate(rand_reads(rng, 120, (20, 220), 5000))))
+        fas.append(str(p))
+    k = 27
+    g2 = str(tmp_path / "g2.ctx")
+    oracle.ref_build(k, ["-s", "a", "-1", fas[0], "-s", "b", "-1", fas[1]], g2, threads=2)
+    g1 = str(tmp_path / "g1.ctx")
+    oracle.ref_build(k, ["-s", "c", "-1", fas[2]], g1, threads=2, sort=False)
+    for args in (["-g", g2, "-g", g1, "-s", "n", "-1", fas[0]],
+                 ["-g", "1:" + g2 + ":0", "-s", "n", "-1", fas[1], "-1", fas[2]],
+                 ["-g", g2 + ":1-0", "-g", "0,0:" + g2, "-s", "n", "-1", fas[2]]):
+        ref = oracle.ref_build(k, args, str(tmp_path / "ref.ctx"), threads=3)
+        assert oracle.build_ctx_args(k, args) == ref, args
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "mccortex31")),
                     reason="oracle/_ref not built")
 @pytest.mark.parametrize("k,seed", [(31, 1), (63, 2), (33, 3), (21, 4), (5, 5)])
