@@ -59,7 +59,10 @@ typedef struct {
                                 (build_graph.c:202-207), < 127.  A contig starts at a k-mer whose bases all have
                                 qual > cutoff and extends while qual >= cutoff (seq_reader.c:84,149). */
   uint8_t         hp_cutoff; /* 0 = off; else break contigs at homopolymer runs >= hp_cutoff (2 <= hp_cutoff <= k) */
-  uint8_t         reserved[2];
+  uint8_t         must_exist; /* SeqLoadingPrefs.must_exist_in_graph (build --intersect): k-mers are looked up, never
+                                 inserted; coverage and edges only where the k-mers are in the graph
+                                 (src/tools/build_graph.c:99-150).  Not combinable with a quality cut-off yet. */
+  uint8_t         reserved;
 } mcx_read_batch;
 
 /* Counters of SeqLoadingStats (src/basic/seq_loading_stats.h:5-14) that feed the
@@ -92,6 +95,7 @@ int mcx_host_free(void *ptr);
  * (src/graph/db_graph.h:62-64, src/commands/ctx_build.c:335-339) + hash_table_alloc
  * (src/graph/hash_table.c:16-52).  capacity = number of k-mer slots (what
  * cmd_get_kmers_in_hash returns, src/graph/cmd_mem.c:38-130); 3 <= k <= 63, k odd. */
+#define MCX_GRAPH_INTERSECT 1u  /* flags: also allocate the intersection edge set (Edges *isec_edges, ctx_build.c:341-343) */
 int mcx_graph_create(uint32_t kmer_size, uint32_t ncols, uint64_t capacity, int device, uint32_t flags, mcx_graph **out);
 /* replaces db_graph_dealloc (src/graph/db_graph.h:67) */
 int mcx_graph_destroy(mcx_graph *g);
@@ -129,9 +133,17 @@ int mcx_graph_flush(mcx_graph *g);
  * Synchronous.  *nkmers_loaded / *nkmers_novel (may be NULL) = GraphLoadingStats of this call.
  * The novel k-mers are also part of what the next mcx_graph_sync reports as num_kmers_novel. */
 #define MCX_LOAD_MUST_EXIST 1u
+#define MCX_LOAD_INTO_ISEC  2u  /* the file is an intersection graph (ctx_build.c:348-361): k-mers are inserted without
+                                   coverage, the edges of all selected colours go into the intersection edge set */
+#define MCX_LOAD_MASK_ISEC  4u  /* GraphLoadingPrefs.must_exist_in_edges: edges are ANDed with the intersection edge set */
 int mcx_graph_load_records(mcx_graph *g, const void *records, uint64_t nrecords, uint32_t file_ncols, uint32_t mem,
                            const uint32_t *from_col, const uint32_t *into_col, uint32_t nmap, uint32_t flags,
                            uint64_t *nkmers_loaded, uint64_t *nkmers_novel);
+
+/* replaces db_graph_remove_no_covg_kmers + db_graph_intersect_edges (src/graph/db_graph.c:632-673,
+ * ctx_build.c:409-413) at the end of a build --intersect: k-mers without coverage in any colour leave the
+ * graph, every colour's edges are ANDed with the intersection edge set.  *nkmers = k-mers left. */
+int mcx_graph_finish_intersect(mcx_graph *g, uint64_t *nkmers);
 
 /* replaces hash_table_print_stats inputs (src/graph/hash_table.h:73): occupancy */
 int mcx_graph_stats(mcx_graph *g, uint64_t *nkmers, uint64_t *capacity);

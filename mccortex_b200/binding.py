@@ -29,7 +29,7 @@ class ReadBatch(C.Structure):
     _fields_ = [("seq", C.c_void_p), ("qual", C.c_void_p), ("offsets", C.c_void_p),
                 ("nreads", C.c_uint64), ("nbytes", C.c_uint64),
                 ("layout", C.c_uint32), ("mem", C.c_uint32), ("colour", C.c_uint32),
-                ("fq_cutoff", C.c_uint8), ("hp_cutoff", C.c_uint8), ("reserved", C.c_uint8 * 2)]
+                ("fq_cutoff", C.c_uint8), ("hp_cutoff", C.c_uint8), ("must_exist", C.c_uint8), ("reserved", C.c_uint8)]
 
 
 class LoadStats(C.Structure):
@@ -80,6 +80,8 @@ def lib():
     L.mcx_graph_add_str.argtypes = [vp, u32, C.c_char_p, C.c_size_t]
     L.mcx_graph_sync.argtypes = [vp, C.POINTER(LoadStats)]
     L.mcx_graph_flush.argtypes = [vp]
+    L.mcx_graph_finish_intersect.argtypes = [vp, C.POINTER(u64)]
+    L.mcx_graph_load_records.argtypes = [vp, vp, u64, u32, u32, C.POINTER(u32), C.POINTER(u32), u32, u32, C.POINTER(u64), C.POINTER(u64)]
     L.mcx_graph_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.mcx_graph_export_begin.argtypes = [vp, C.c_int, C.POINTER(u64), C.POINTER(u32)]
     L.mcx_graph_export_read.argtypes = [vp, u64, u64, vp]

@@ -45,6 +45,7 @@ struct mcx_graph {
   uint64_t nkmers;         // slots claimed so far (updated at sync)
   McxExport exp; bool exp_valid;
   uint8_t *d_tmp; size_t d_tmp_bytes; // scratch for OFFSETS -> LINES repack
+  uint8_t *d_isec;         // build --intersect: one edge byte per slot (Edges *isec_edges, ctx_build.c:341-343), else NULL
   size_t persist_bytes;    // experiment: L2 persisting window over the front table
   uint64_t front_pending;  // positions queued since the front table was last flushed (its counters are 32-bit)
   bool sharded;  // front table holds records of keys owned by other shards: only mcx_graph_flush_sharded may empty it
@@ -87,7 +88,6 @@ static void apply_persist(mcx_graph *g, cudaStream_t st)
 
 extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, int device, uint32_t flags, mcx_graph **out)
 {
-  (void)flags;
   if(!out || k < 3 || k > 63 || !(k & 1u) || ncols == 0 || ncols > 4096 || capacity == 0) return MCX_ERR_BAD_ARG;
   int ndev = mcx_device_count();
   if(ndev == 0) { snprintf(g_err, sizeof(g_err), "no CUDA device: libmcxgpu has no CPU fallback"); return MCX_ERR_NO_DEVICE; }
@@ -117,7 +117,13 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
   if(e != cudaSuccess) { int r = fail_cuda(e, "memset(table)"); mcx_graph_destroy(g); return r; }
   // front table (k <= 31, one colour): sized to sit in L2 (64 MB = 2^21 sets of four 8-byte
   // slots); MCX_FRONT_BITS=0 disables it, other values are for experiments
-  if(g->table.stride == 4u) {
+  if(flags & MCX_GRAPH_INTERSECT) {
+    e = cudaMalloc(&g->d_isec, (size_t)g->table.nslots + 8);
+    if(e != cudaSuccess) { int r = fail_cuda(e, "cudaMalloc(isec_edges)"); mcx_graph_destroy(g); return r; }
+    cudaMemset(g->d_isec, 0, (size_t)g->table.nslots + 8);
+  }
+  // (an intersected build only looks k-mers up: no front table)
+  if(g->table.stride == 4u && !(flags & MCX_GRAPH_INTERSECT)) {
     uint32_t bits = 21;
     if(const char *m = getenv("MCX_FRONT_BITS")) bits = (uint32_t)atoi(m);
     if(bits) {
@@ -163,6 +169,7 @@ extern "C" int mcx_graph_destroy(mcx_graph *g)
   if(g->own_primary) cudaStreamDestroy(g->own_primary);
   if(g->ev_fork) cudaEventDestroy(g->ev_fork);
   if(g->d_tmp) cudaFree(g->d_tmp);
+  if(g->d_isec) cudaFree(g->d_isec);
   if(g->table.front) cudaFree(g->table.front);
   if(g->d_counters) cudaFree(g->d_counters);
   if(g->table.slots) cudaFree(g->table.slots);
@@ -186,6 +193,7 @@ extern "C" int mcx_graph_clear(mcx_graph *g)
   CU(cudaMemsetAsync(g->table.slots, 0, (size_t)g->table.nslots * g->table.stride * 4u, st));
   CU(cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), st));
   if(g->table.front) CU(cudaMemsetAsync(g->table.front, 0, (4ull << g->table.front_set_bits) * 12u, st));
+  if(g->d_isec) CU(cudaMemsetAsync(g->d_isec, 0, (size_t)g->table.nslots + 8, st));
   g->front_pending = 0;
   g->sharded = false;
   g->occ_bound = 0; g->pend_positions = 0; g->pend_offsets_reads = g->pend_offsets_bases = 0; g->nkmers = 0;
@@ -242,6 +250,13 @@ static int front_guard(mcx_graph *g, uint64_t positions)
   return MCX_OK;
 }
 
+// one launch over [r_begin, r_end) of a LINES buffer: the fused insert kernel, or (must_exist) the lookup kernel
+static cudaError_t launch_build(mcx_graph *g, const mcx_read_batch *b, const McxBuildParams &p, cudaStream_t st)
+{
+  if(b->must_exist) return mcx_launch_build_lookup(p, g->table, st);
+  return mcx_launch_build_fused(p, g->table, st);
+}
+
 // LINES batch resident on the device
 static int add_lines_device(mcx_graph *g, const mcx_read_batch *b, const uint8_t *dseq, uint64_t nbytes)
 {
@@ -253,7 +268,7 @@ static int add_lines_device(mcx_graph *g, const mcx_read_batch *b, const uint8_t
     const uint64_t hi = lo + MCX_FRONT_SPAN < nbytes ? lo + MCX_FRONT_SPAN : nbytes;
     int r = front_guard(g, hi - lo); if(r) return r;
     McxBuildParams p = make_params(g, b, dseq, nbytes, lo, hi);
-    CU(mcx_launch_build_fused(p, g->table, primary(g)));
+    CU(launch_build(g, b, p, primary(g)));
   }
   g->pend_positions += nbytes;
   return MCX_OK;
@@ -286,7 +301,7 @@ static int add_lines_host(mcx_graph *g, const mcx_read_batch *b, const uint8_t *
     if(!pinned) { memcpy(g->h_stage[s], src, b1 - b0); src = g->h_stage[s]; }
     CU(cudaMemcpyAsync(g->d_stage[s], src, b1 - b0, cudaMemcpyHostToDevice, st));
     McxBuildParams p = make_params(g, b, g->d_stage[s], b1 - b0, pos - b0, pend - b0);
-    CU(mcx_launch_build_fused(p, g->table, st));
+    CU(launch_build(g, b, p, st));
     CU(cudaEventRecord(g->events[s], st));
   }
   for(int s = 0; s < MCX_NSTAGE; s++) if(used[s]) CU(cudaStreamWaitEvent(primary(g), g->events[s], 0));
@@ -364,6 +379,14 @@ extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
     snprintf(g_err, sizeof(g_err), "hp_cutoff must be 0 or in [2, k]"); return MCX_ERR_UNSUPPORTED;
   }
   if(b->fq_cutoff >= 127) { snprintf(g_err, sizeof(g_err), "fq_cutoff (incl. offset) must be < 127"); return MCX_ERR_UNSUPPORTED; }
+  if(b->must_exist && b->fq_cutoff && b->qual) {
+    snprintf(g_err, sizeof(g_err), "must_exist (--intersect) cannot be combined with a quality cut-off yet"); return MCX_ERR_UNSUPPORTED;
+  }
+  if(b->must_exist && g->table.front_set_bits) {
+    // everything counted so far must be in the big table before k-mers are looked up there
+    CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+    g->front_pending = 0;
+  }
   CU(cudaSetDevice(g->device));
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
   if((b->fq_cutoff && b->qual) || b->layout != MCX_LAYOUT_LINES) { int r = front_guard(g, b->nbytes + b->nreads); if(r) return r; }
@@ -400,7 +423,7 @@ extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
   CU(mcx_launch_repack_lines(d_raw, d_off, b->nreads, g->d_tmp + lines_off, st));
   g->occ_bound += lines_bytes;
   McxBuildParams p = make_params(g, b, g->d_tmp + lines_off, lines_bytes, 0, lines_bytes);
-  CU(mcx_launch_build_fused(p, g->table, st));
+  CU(launch_build(g, b, p, st));
   g->pend_positions += lines_bytes;
   // d_tmp is reused by the next OFFSETS batch: order it behind this one
   CU(cudaStreamSynchronize(st));
@@ -439,7 +462,8 @@ extern "C" int mcx_graph_sync(mcx_graph *g, mcx_load_stats *stats)
     stats->num_kmers_novel = c[MCX_CNT_NOVEL];
     stats->contigs_parsed = c[MCX_CNT_CONTIGS];
     // every contig of n windows spans n + k - 1 bases (build_graph.c:173-176)
-    stats->total_bases_loaded = c[MCX_CNT_KMERS] + (uint64_t)(g->k - 1u) * c[MCX_CNT_CONTIGS];
+    // (must-exist builds: windows whose k-mer is not in the graph still belong to their contig, build_graph.c:173-181)
+    stats->total_bases_loaded = c[MCX_CNT_KMERS] + c[MCX_CNT_NOTFOUND] + (uint64_t)(g->k - 1u) * c[MCX_CNT_CONTIGS];
     stats->num_se_reads = c[MCX_CNT_READS];
     stats->total_bases_read = g->pend_positions - c[MCX_CNT_READS];
     stats->num_good_reads = UINT64_MAX;
@@ -521,7 +545,7 @@ extern "C" int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *b, uint32_t n
 {
   if(!g || !b || !nparts || !cap_per_part || !keys_out || !masks_out || !counts_out) return MCX_ERR_BAD_ARG;
   if(b->layout != MCX_LAYOUT_LINES || b->mem != MCX_MEM_DEVICE || ((uintptr_t)b->seq & 15u)) return MCX_ERR_BAD_ARG;
-  if(b->hp_cutoff == 1 || b->hp_cutoff > g->k || (b->fq_cutoff && b->qual)) return MCX_ERR_UNSUPPORTED;
+  if(b->hp_cutoff == 1 || b->hp_cutoff > g->k || (b->fq_cutoff && b->qual) || b->must_exist) return MCX_ERR_UNSUPPORTED;
   CU(cudaSetDevice(g->device));
   cudaStream_t st = primary(g);
   CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
@@ -542,7 +566,7 @@ static int add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t npa
   if(!g || !b || nparts < 2 || my_part >= nparts || !cap_per_part || !counts_out) return MCX_ERR_BAD_ARG;
   if(!(keys_out && meta_out) && !(keys_dst && meta_dst)) return MCX_ERR_BAD_ARG;
   if(b->layout != MCX_LAYOUT_LINES || b->mem != MCX_MEM_DEVICE || ((uintptr_t)b->seq & 15u)) return MCX_ERR_BAD_ARG;
-  if(b->hp_cutoff == 1 || b->hp_cutoff > g->k || (b->fq_cutoff && b->qual)) return MCX_ERR_UNSUPPORTED;
+  if(b->hp_cutoff == 1 || b->hp_cutoff > g->k || (b->fq_cutoff && b->qual) || b->must_exist) return MCX_ERR_UNSUPPORTED;
   if(b->colour >= g->ncols) return MCX_ERR_BAD_ARG;
   CU(cudaSetDevice(g->device));
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
@@ -648,6 +672,9 @@ extern "C" int mcx_graph_load_records(mcx_graph *g, const void *records, uint64_
 {
   if(!g || !file_ncols || (nrecords && !records) || (nmap && (!from_col || !into_col))) return MCX_ERR_BAD_ARG;
   for(uint32_t m = 0; m < nmap; m++) if(from_col[m] >= file_ncols || into_col[m] >= g->ncols) return MCX_ERR_BAD_ARG;
+  if((flags & (MCX_LOAD_INTO_ISEC | MCX_LOAD_MASK_ISEC)) && !g->d_isec) {
+    snprintf(g_err, sizeof(g_err), "graph was not created with MCX_GRAPH_INTERSECT"); return MCX_ERR_BAD_ARG;
+  }
   CU(cudaSetDevice(g->device));
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
   if(nkmers_loaded) *nkmers_loaded = 0;
@@ -667,12 +694,31 @@ extern "C" int mcx_graph_load_records(mcx_graph *g, const void *records, uint64_
   unsigned long long c0[MCX_NCOUNTERS], c1[MCX_NCOUNTERS];
   CU(cudaMemcpyAsync(c0, g->d_counters, sizeof(c0), cudaMemcpyDeviceToHost, st));
   g->occ_bound = 0xF0000000ull; // file coverages can be anything: saturation-aware adds from here on
-  CU(mcx_launch_load_records(drecs, nrecords, file_ncols, d_from, d_into, nmap, flags, g->k, g->table, g->d_counters, st));
+  CU(mcx_launch_load_records(drecs, nrecords, file_ncols, d_from, d_into, nmap, flags, g->k, g->table, g->d_isec, g->d_counters, st));
   CU(cudaMemcpyAsync(c1, g->d_counters, sizeof(c1), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if(nkmers_loaded) *nkmers_loaded = c1[MCX_CNT_RECS_LOADED] - c0[MCX_CNT_RECS_LOADED];
   if(nkmers_novel) *nkmers_novel = c1[MCX_CNT_NOVEL] - c0[MCX_CNT_NOVEL];
   if(c1[MCX_CNT_FULL]) { snprintf(g_err, sizeof(g_err), "Hash table is full"); return MCX_ERR_TABLE_FULL; }
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_finish_intersect(mcx_graph *g, uint64_t *nkmers)
+{
+  if(!g) return MCX_ERR_BAD_ARG;
+  if(!g->d_isec) { snprintf(g_err, sizeof(g_err), "graph was not created with MCX_GRAPH_INTERSECT"); return MCX_ERR_BAD_ARG; }
+  int r = sync_all(g); if(r) return r;
+  if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
+  cudaStream_t st = primary(g);
+  unsigned long long *d_n = g->d_counters + MCX_CNT_INSERTED; // scratch counter (unused on this path)
+  CU(cudaMemsetAsync(d_n, 0, sizeof(*d_n), st));
+  CU(mcx_launch_finish_intersect(g->table, g->W, g->d_isec, d_n, st));
+  unsigned long long n = 0;
+  CU(cudaMemcpyAsync(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemsetAsync(d_n, 0, sizeof(*d_n), st));
+  CU(cudaStreamSynchronize(st));
+  g->nkmers = n;
+  if(nkmers) *nkmers = n;
   return MCX_OK;
 }
 

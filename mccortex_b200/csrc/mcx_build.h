@@ -13,6 +13,7 @@ enum {
   MCX_CNT_FULL,        // non-zero: table (or tuple bin) overflowed
   MCX_CNT_INSERTED,    // tuples inserted by kernel C
   MCX_CNT_RECS_LOADED, // graph-file records merged (mcx_ctxload.cu)
+  MCX_CNT_NOTFOUND,    // must-exist builds: windows of a contig whose k-mer is not in the graph
   MCX_NCOUNTERS = 8
 };
 
@@ -67,7 +68,13 @@ void mcx_set_inflight(int g);
 // graph files (mcx_ctxload.cu): from_col / into_col are device arrays of nmap colour pairs; flags bit 0 = must exist
 cudaError_t mcx_launch_load_records(const uint8_t *recs, uint64_t n, uint32_t file_ncols, const uint32_t *from_col,
                                     const uint32_t *into_col, uint32_t nmap, uint32_t flags, uint32_t k, const McxTable &t,
-                                    unsigned long long *counters, cudaStream_t st);
+                                    uint8_t *isec_edges, unsigned long long *counters, cudaStream_t st);
+// build --intersect (mcx_lookup.cu): reads update only k-mers that are already in the table; the final pass
+// removes k-mers without coverage and ANDs every colour's edges with isec_edges
+cudaError_t mcx_launch_build_lookup(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
+cudaError_t mcx_launch_finish_intersect(const McxTable &t, uint32_t W, const uint8_t *isec_edges, unsigned long long *nkept,
+                                        cudaStream_t st);
+#define MCX_KEY_TOMBSTONE (MCX_KEY_FLAG | (1ULL << 62))  /* slot of a removed k-mer: never equal to a key, never empty */
 
 // export (mcx_export.cu)
 struct McxExport {

@@ -10,45 +10,11 @@
 // with saturation and ORs their edges before touching the graph -- adding them one after the other
 // with a saturating add gives the same result).  A k-mer whose selected colours all have zero
 // coverage is skipped (graphs_load.c:121-124).  MCX_LOAD_MUST_EXIST: never insert, k-mers that are
-// not in the table are skipped (GraphLoadingPrefs.must_exist_in_graph).
+// not in the table are skipped (GraphLoadingPrefs.must_exist_in_graph).  Flag bit 1: the file is an
+// intersection graph (edges into isec_edges, no coverage); bit 2: edges are ANDed with isec_edges.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "mcx_build.h"
-
-// generic find / find-or-insert: returns the slot (u32 pointer) or nullptr (not found / table full).
-// Probe order is the one mcx_table_add uses, so both see the same slots.
-template <int W>
-__device__ __forceinline__ uint32_t *mcx_table_slot(const McxTable &t, const McxKmer<W> &key, bool insert, int *novel, int *full)
-{
-  uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
-  uint64_t idx = mcx_home_slot(hc, hb, t.nslots);
-  if(t.stride == 4u) idx &= ~1ull;
-  const uint64_t k0f = key.b[0] | MCX_KEY_FLAG;
-  for(uint64_t probes = 0; probes < t.nslots; probes++) {
-    uint32_t *s = t.slots + idx * (uint64_t)t.stride;
-    if(W == 1) {
-      uint64_t cur = *(volatile uint64_t *)s;
-      if(cur == 0) {
-        if(!insert) return nullptr;
-        cur = atomicCAS((unsigned long long *)s, 0ull, (unsigned long long)k0f);
-        if(cur == 0) { *novel = 1; return s; }
-      }
-      if(cur == k0f) return s;
-    } else {
-      uint64_t c0, c1;
-      mcx_ld128(s, c0, c1);
-      if(c0 == 0) {
-        if(!insert) return nullptr;
-        mcx_cas128(s, 0ull, 0ull, k0f, key.b[W - 1], c0, c1);
-        if(c0 == 0) { *novel = 1; return s; }
-      }
-      if(c0 == k0f && c1 == key.b[W - 1]) return s;
-    }
-    idx++; if(idx >= t.nslots) idx = 0;
-  }
-  *full = 1;
-  return nullptr;
-}
 
 __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t *p)
 {
@@ -62,7 +28,8 @@ __device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t *p)
 template <int W>
 __global__ void __launch_bounds__(256) mcx_load_records_kernel(const uint8_t *__restrict__ recs, uint64_t n, uint32_t file_ncols,
                                                                const uint32_t *__restrict__ from_col, const uint32_t *__restrict__ into_col,
-                                                               uint32_t nmap, uint32_t flags, McxTable t, unsigned long long *counters)
+                                                               uint32_t nmap, uint32_t flags, McxTable t, uint8_t *isec_edges,
+                                                               unsigned long long *counters)
 {
   const uint32_t rec_bytes = 8u * W + 5u * file_ncols;
   uint64_t n_loaded = 0, n_novel = 0; uint32_t full = 0;
@@ -80,8 +47,19 @@ __global__ void __launch_bounds__(256) mcx_load_records_kernel(const uint8_t *__
     full |= (uint32_t)isfull;
     if(!s) continue;
     n_novel += novel; n_loaded++;
+    const uint64_t slot_idx = (uint64_t)(s - t.slots) / t.stride;
+    if(flags & 2u) {
+      // intersection graph (ctx_build.c:348-361): no coverage, every selected colour's edges into the one
+      // edge set the build is intersected with at the end
+      uint32_t e = 0;
+      for(uint32_t m = 0; m < nmap; m++) e |= ed[from_col[m]];
+      uint32_t *w = reinterpret_cast<uint32_t *>(isec_edges + (slot_idx & ~3ull));
+      if(e) atomicOr(w, e << (8u * (uint32_t)(slot_idx & 3ull)));
+      continue;
+    }
+    const uint32_t emask = (flags & 4u) ? isec_edges[slot_idx] : 0xFFu;   // GraphLoadingPrefs.must_exist_in_edges
     for(uint32_t m = 0; m < nmap; m++) {
-      const uint32_t c = ld_u32_unaligned(cv + 4u * from_col[m]), e = ed[from_col[m]], into = into_col[m];
+      const uint32_t c = ld_u32_unaligned(cv + 4u * from_col[m]), e = ed[from_col[m]] & emask, into = into_col[m];
       mcx_covg_add(s + 2u * W + into, c, true);
       mcx_edges_or(s, W, t.ncols, into, e, 0, false);
     }
@@ -100,7 +78,7 @@ __global__ void __launch_bounds__(256) mcx_load_records_kernel(const uint8_t *__
 
 cudaError_t mcx_launch_load_records(const uint8_t *recs, uint64_t n, uint32_t file_ncols, const uint32_t *from_col,
                                     const uint32_t *into_col, uint32_t nmap, uint32_t flags, uint32_t k, const McxTable &t,
-                                    unsigned long long *counters, cudaStream_t st)
+                                    uint8_t *isec_edges, unsigned long long *counters, cudaStream_t st)
 {
   if(n == 0 || nmap == 0) return cudaSuccess;
   int dev = 0, sms = 148; cudaGetDevice(&dev);
@@ -108,7 +86,7 @@ cudaError_t mcx_launch_load_records(const uint8_t *recs, uint64_t n, uint32_t fi
   uint64_t want = (n + 255) / 256, cap = (uint64_t)sms * 8;
   unsigned grid = (unsigned)(want < cap ? want : cap);
   McxTable big = t; big.front = nullptr; big.front_cnt = nullptr; big.front_set_bits = 0;
-  if(k <= 31) mcx_load_records_kernel<1><<<grid, 256, 0, st>>>(recs, n, file_ncols, from_col, into_col, nmap, flags, big, counters);
-  else mcx_load_records_kernel<2><<<grid, 256, 0, st>>>(recs, n, file_ncols, from_col, into_col, nmap, flags, big, counters);
+  if(k <= 31) mcx_load_records_kernel<1><<<grid, 256, 0, st>>>(recs, n, file_ncols, from_col, into_col, nmap, flags, big, isec_edges, counters);
+  else mcx_load_records_kernel<2><<<grid, 256, 0, st>>>(recs, n, file_ncols, from_col, into_col, nmap, flags, big, isec_edges, counters);
   return cudaGetLastError();
 }

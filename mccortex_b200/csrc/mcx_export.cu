@@ -27,7 +27,7 @@ __global__ void mcx_compact_kernel(McxTable t, uint64_t *__restrict__ keys, uint
     uint64_t i = r * nthreads + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     uint64_t k0 = 0;
     if(i < t.nslots) k0 = *reinterpret_cast<const uint64_t *>(t.slots + i * (uint64_t)t.stride);
-    bool occ = k0 != 0;
+    bool occ = k0 != 0 && k0 != MCX_KEY_TOMBSTONE; // (a k-mer removed by an intersected build)
     uint32_t m = __ballot_sync(0xFFFFFFFFu, occ);
     if(!m) continue;
     unsigned long long base = 0;

@@ -237,6 +237,41 @@ __device__ __forceinline__ int mcx_table_add<2>(const McxTable &t, const McxKmer
   return 2;
 }
 
+// generic find / find-or-insert: returns the slot (u32 pointer) or nullptr (not found / table full).
+// Probe order is the one mcx_table_add uses, so both see the same slots.
+template <int W>
+__device__ __forceinline__ uint32_t *mcx_table_slot(const McxTable &t, const McxKmer<W> &key, bool insert, int *novel, int *full)
+{
+  uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
+  uint64_t idx = mcx_home_slot(hc, hb, t.nslots);
+  if(t.stride == 4u) idx &= ~1ull;
+  const uint64_t k0f = key.b[0] | MCX_KEY_FLAG;
+  for(uint64_t probes = 0; probes < t.nslots; probes++) {
+    uint32_t *s = t.slots + idx * (uint64_t)t.stride;
+    if(W == 1) {
+      uint64_t cur = *(volatile uint64_t *)s;
+      if(cur == 0) {
+        if(!insert) return nullptr;
+        cur = atomicCAS((unsigned long long *)s, 0ull, (unsigned long long)k0f);
+        if(cur == 0) { *novel = 1; return s; }
+      }
+      if(cur == k0f) return s;
+    } else {
+      uint64_t c0, c1;
+      mcx_ld128(s, c0, c1);
+      if(c0 == 0) {
+        if(!insert) return nullptr;
+        mcx_cas128(s, 0ull, 0ull, k0f, key.b[W - 1], c0, c1);
+        if(c0 == 0) { *novel = 1; return s; }
+      }
+      if(c0 == k0f && c1 == key.b[W - 1]) return s;
+    }
+    idx++; if(idx >= t.nslots) idx = 0;
+  }
+  *full = 1;
+  return nullptr;
+}
+
 // ---- front table ------------------------------------------------------------
 __device__ __forceinline__ McxFrontGeom mcx_front_geom(const McxTable &t) { return mcx_front_geom_bits(t.front_set_bits); }
 

@@ -7,7 +7,8 @@
  * what mccortex31 / mccortex63 write for their k ranges.
  *
  * Not (yet) supported, and rejected with an error rather than silently ignored:
- *   -p/--remove-pcr (order dependent in the reference), -I/--intersect, SAM/BAM/CRAM input.
+ *   -p/--remove-pcr (order dependent in the reference), SAM/BAM/CRAM input,
+ *   -I/--intersect together with -Q/--fq-cutoff on inputs that carry qualities.
  */
 #include "mcx_host.h"
 #include <ctype.h>
@@ -49,7 +50,7 @@ static const char build_usage[] =
 "  -P, --keep-pcr           Don't do PCR duplicate removal [default]\n"
 "  -M, --matepair <orient>  Mate pair orientation: FF,FR,RF,RR [default: FR]\n"
 "  -g, --graph <in.ctx>     Load samples from a graph file (.ctx)\n"
-"  -I, --intersect <i.ctx>  Only load kmers that appear in i.ctx [not supported]\n"
+"  -I, --intersect <i.ctx>  Only load kmers that appear in i.ctx. Multiple -I will merge\n"
 "  -S, --sort               Output a graph file ordered by kmer\n"
 "  -D, --device <id>        CUDA device [default: 0]\n"
 "\n"
@@ -80,6 +81,7 @@ typedef struct {
 static BuildTask *tasks = NULL; static size_t ntasks = 0, tasks_cap = 0;
 static char **sample_names = NULL; static size_t *sample_cols = NULL; static size_t nsamples = 0;
 static McxCtxFile **gfiles = NULL; static size_t ngfiles = 0;
+static McxCtxFile **ifiles = NULL; static size_t nifiles = 0;   /* --intersect graphs */
 static size_t nthreads = 0, kmer_size = 0, output_colours = 0;
 static bool mem_set = false, nkmers_set = false, force = false, sort_kmers = false;
 static size_t mem_to_use = MCX_DEFAULT_MEM, num_kmers = MCX_DEFAULT_NKMERS;
@@ -222,7 +224,14 @@ static void parse_args(int argc, char **argv)
         sample_named = false;
         break;
       }
-      case 'I': mcx_die("--intersect is not supported by "CMD" yet");
+      case 'I': { /* src/commands/ctx_build.c:197-204 */
+        McxCtxFile *gf = mcx_ctx_open(optarg, 0);
+        if(gf->into_ncols > 1) mcx_warn("Flattening intersection graph into colour 0: %s", optarg);
+        mcx_ctx_flatten(gf, 0);
+        ifiles = realloc(ifiles, (nifiles + 1) * sizeof(*ifiles));
+        ifiles[nifiles++] = gf;
+        break;
+      }
       case 'D': device = (int)parse_size(cmd, optarg, false); break;
       case ':': case '?':
         mcx_die("`"CMD" build -h` for help. Bad option: %s", argv[optind - 1]);
@@ -317,9 +326,17 @@ static int ctx_build(int argc, char **argv)
     max_kmers += (size_t)fsize * 5;
   }
 
+  /* src/commands/ctx_build.c:293-303: intersecting: every read only updates k-mers of the intersection
+   * graphs, and those bound the table */
+  if(nifiles > 0) {
+    for(t = 0; t < ntasks; t++) tasks[t].prefs.must_exist = true;
+    max_kmers = 0;
+    for(i = 0; i < nifiles; i++) max_kmers += ifiles[i]->num_of_kmers < 0 ? 0 : (size_t)ifiles[i]->num_of_kmers;
+  }
+
   /* src/commands/ctx_build.c:311-322 */
   size_t W = (kmer_size + 31) / 32, graph_mem;
-  size_t bits_per_kmer = W * 64 + (32 + 8) * output_colours + (sort_kmers ? 64 : 0);
+  size_t bits_per_kmer = W * 64 + (32 + 8) * output_colours + (nifiles > 0 ? 8 : 0) + (sort_kmers ? 64 : 0);
   size_t kmers_in_hash = mcx_get_kmers_in_hash(mem_to_use, mem_set, num_kmers, nkmers_set, bits_per_kmer, 0,
                                                (int64_t)max_kmers, true, &graph_mem);
   if(graph_mem > mem_to_use) { char m[64]; mcx_bytes_to_str(graph_mem, m); mcx_die("Need to set higher memory limit [ at least -m %s ]", m); }
@@ -329,7 +346,8 @@ static int ctx_build(int argc, char **argv)
 
   if(mcx_device_count() == 0) mcx_die("No CUDA device: "CMD" has no CPU fallback");
   mcx_graph *g = NULL;
-  int r = mcx_graph_create((uint32_t)kmer_size, (uint32_t)output_colours, kmers_in_hash, device, 0, &g);
+  int r = mcx_graph_create((uint32_t)kmer_size, (uint32_t)output_colours, kmers_in_hash, device,
+                           nifiles > 0 ? MCX_GRAPH_INTERSECT : 0, &g);
   if(r) die_mcx(r, "mcx_graph_create");
   { char a[64]; mcx_ulong_to_str(kmers_in_hash, a); mcx_status("[hasht] Allocating device table with %s entries on GPU %i", a, device); }
 
@@ -338,9 +356,22 @@ static int ctx_build(int argc, char **argv)
 
   /* src/commands/ctx_build.c:362-377: graph files first (their header metadata is merged into the
    * colours they load into), then the --sample names OVERWRITE the names of the colours they name */
+  /* src/commands/ctx_build.c:346-361: intersection graphs first -- k-mers and one flattened edge set, no
+   * coverage, no header metadata */
+  for(i = 0; i < nifiles; i++) {
+    if(ifiles[i]->kmer_size != kmer_size)
+      mcx_die("Graph has different kmer size [kmer_size: %u vs %zu; path: %s]", ifiles[i]->kmer_size, kmer_size, ifiles[i]->path);
+    r = mcx_ctx_load(g, ifiles[i], NULL, output_colours, MCX_LOAD_INTO_ISEC, NULL, NULL, NULL);
+    if(r) die_mcx(r, "loading intersection graph");
+    mcx_load_stats st;
+    r = mcx_graph_sync(g, &st);
+    if(r) die_mcx(r, "loading intersection graph");
+    mcx_ctx_close(ifiles[i]);
+  }
   for(i = 0; i < ngfiles; i++) {
     uint64_t nread = 0, nloaded = 0, nnovel = 0;
-    r = mcx_ctx_load(g, gfiles[i], ginfo, output_colours, false, &nread, &nloaded, &nnovel);
+    r = mcx_ctx_load(g, gfiles[i], ginfo, output_colours, nifiles > 0 ? (MCX_LOAD_MUST_EXIST | MCX_LOAD_MASK_ISEC) : 0u,
+                     &nread, &nloaded, &nnovel);
     if(r) die_mcx(r, "loading graph file");
     mcx_load_stats st; /* fold the novel k-mers of the file into the table occupancy */
     r = mcx_graph_sync(g, &st);
@@ -366,6 +397,12 @@ static int ctx_build(int argc, char **argv)
       credited.contigs_parsed += tasks[t].stats.contigs_parsed;
     }
     mcx_ginfo_update_contigs(&ginfo[tasks[start].prefs.colour], credited.total_bases_loaded, credited.contigs_parsed);
+  }
+
+  /* src/commands/ctx_build.c:409-413 */
+  if(nifiles > 0) {
+    r = mcx_graph_finish_intersect(g, NULL);
+    if(r) die_mcx(r, "mcx_graph_finish_intersect");
   }
 
   uint64_t nk = 0, cap = 0;

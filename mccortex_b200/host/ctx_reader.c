@@ -248,7 +248,13 @@ void mcx_ctx_close(McxCtxFile *f)
 }
 
 /* ---- graphs_load.c ------------------------------------------------------------------------ */
-int mcx_ctx_load(mcx_graph *g, McxCtxFile *f, McxGInfo *ginfo, size_t graph_ncols, bool must_exist,
+void mcx_ctx_flatten(McxCtxFile *f, uint32_t intocol)
+{
+  for(uint32_t i = 0; i < f->nfilter; i++) f->into_col[i] = intocol;
+  f->into_ncols = intocol + 1;
+}
+
+int mcx_ctx_load(mcx_graph *g, McxCtxFile *f, McxGInfo *ginfo, size_t graph_ncols, uint32_t load_flags,
                  uint64_t *nkmers_read, uint64_t *nkmers_loaded, uint64_t *nkmers_novel)
 {
   char a[64], b[64];
@@ -259,7 +265,7 @@ int mcx_ctx_load(mcx_graph *g, McxCtxFile *f, McxGInfo *ginfo, size_t graph_ncol
   /* graph_load_ginfo */
   if(f->into_ncols > graph_ncols)
     mcx_die("Program has not assigned enough colours! [colours in graph: %zu vs file: %zu; path: %s]", graph_ncols, (size_t)f->into_ncols, f->path);
-  for(uint32_t i = 0; i < f->nfilter; i++) mcx_ginfo_merge(&ginfo[f->into_col[i]], &f->ginfo[f->from_col[i]]);
+  if(ginfo) for(uint32_t i = 0; i < f->nfilter; i++) mcx_ginfo_merge(&ginfo[f->into_col[i]], &f->ginfo[f->from_col[i]]);
 
   if(f->fh != stdin && fseek(f->fh, (long)f->hdr_size, SEEK_SET) != 0) mcx_die("fseek failed: %s", strerror(errno));
   const size_t rec_bytes = 8u * f->num_of_bitfields + 5u * (size_t)f->num_of_cols;
@@ -273,7 +279,7 @@ int mcx_ctx_load(mcx_graph *g, McxCtxFile *f, McxGInfo *ginfo, size_t graph_ncol
     if(got % rec_bytes != 0) mcx_die("Unexpected end of file: %s", f->path);
     uint64_t l = 0, nv = 0;
     r = mcx_graph_load_records(g, buf, got / rec_bytes, f->num_of_cols, MCX_MEM_HOST, f->from_col, f->into_col, f->nfilter,
-                               must_exist ? MCX_LOAD_MUST_EXIST : 0u, &l, &nv);
+                               load_flags, &l, &nv);
     if(r) break;
     nread += got / rec_bytes; nloaded += l; nnovel += nv;
   }

@@ -75,9 +75,11 @@ typedef struct {
 McxCtxFile *mcx_ctx_open(const char *input, size_t into_offset);
 void mcx_ctx_close(McxCtxFile *f);
 /* graph_load(): merge the header's colours into ginfo[] (graph_load_ginfo) and the records into g.
- * must_exist: only k-mers already in g.  Returns 0 or an MCX_ERR_*. */
-int mcx_ctx_load(mcx_graph *g, McxCtxFile *f, McxGInfo *ginfo, size_t graph_ncols, bool must_exist,
+ * ginfo == NULL: the header metadata is not merged (intersection graphs: ctx_build.c:359-360 resets it).
+ * load_flags: MCX_LOAD_* of mcx_gpu.h.  Returns 0 or an MCX_ERR_*. */
+int mcx_ctx_load(mcx_graph *g, McxCtxFile *f, McxGInfo *ginfo, size_t graph_ncols, uint32_t load_flags,
                  uint64_t *nkmers_read, uint64_t *nkmers_loaded, uint64_t *nkmers_novel);
+void mcx_ctx_flatten(McxCtxFile *f, uint32_t intocol);   /* file_filter_flatten, src/basic/file_filter.c:218-226 */
 
 /* ---- sequence input: libs/seq_file/seq_file.h, src/basic/seq_reader.c -------- */
 typedef struct McxSeqFile McxSeqFile;
@@ -88,6 +90,7 @@ int64_t mcx_seq_file_size(const McxSeqFile *sf);       /* -1 if unknown (stdin) 
 
 typedef struct {
   uint8_t fq_cutoff, hp_cutoff, fq_offset;             /* fq_offset 0 = auto-detect */
+  bool must_exist;                                     /* SeqLoadingPrefs.must_exist_in_graph (--intersect) */
   uint32_t colour;
 } McxLoadPrefs;
 

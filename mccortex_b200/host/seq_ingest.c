@@ -139,7 +139,7 @@ static void flush_batch(Loader *L)
   mcx_read_batch b; memset(&b, 0, sizeof(b));
   b.seq = L->lines.b; b.nbytes = L->lines.len;
   b.layout = MCX_LAYOUT_LINES; b.mem = MCX_MEM_HOST;
-  b.colour = L->prefs->colour; b.hp_cutoff = L->prefs->hp_cutoff;
+  b.colour = L->prefs->colour; b.hp_cutoff = L->prefs->hp_cutoff; b.must_exist = L->prefs->must_exist;
   if(L->prefs->fq_cutoff && L->any_qual) {
     /* build_graph.c:202-207: the ASCII offset is added only when a cut-off is set */
     if(!L->offset_known) {

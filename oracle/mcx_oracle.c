@@ -243,6 +243,9 @@ typedef struct {
   uint8_t  *edges; /* cap * ncols   (db_graph.h:40) */
   OrcGInfo *ginfo;
   int full;
+  /* build --intersect (src/commands/ctx_build.c:293-303,341-361,409-413) */
+  int must_exist;        /* SeqLoadingPrefs.must_exist_in_graph for every read */
+  uint8_t *isec_edges;   /* cap bytes, or NULL */
 } OrcGraph;
 
 static void orc_ginfo_init(OrcGInfo *g) /* src/basic/graph_info.c:60-67 */
@@ -273,7 +276,7 @@ OrcGraph *orc_graph_new(size_t k, size_t ncols, uint64_t capacity)
 void orc_graph_free(OrcGraph *g)
 {
   if(!g) return;
-  free(g->keys); free(g->covgs); free(g->edges); free(g->ginfo); free(g);
+  free(g->keys); free(g->covgs); free(g->edges); free(g->ginfo); free(g->isec_edges); free(g);
 }
 
 uint64_t orc_graph_nkmers(const OrcGraph *g) { return g->nkmers; }
@@ -311,11 +314,31 @@ typedef struct { uint64_t slot; int orient; } OrcNode;
 
 /* src/tools/build_graph.c:99-117 (_find_or_insert, must_exist_in_graph=false)
  * + src/graph/db_graph.c:101-105,126-134 + src/graph/db_node.c:139-144 */
+#define ORC_NOT_FOUND UINT64_MAX
+/* hash_table_find */
+static uint64_t orc_find(const OrcGraph *g, const OrcKmer *key)
+{
+  size_t W = (size_t)g->W, w;
+  uint64_t h = orc_lookup3(key->b, (int)W, 0, NULL) & g->mask;
+  for(;; h = (h + 1) & g->mask) {
+    const uint64_t *sl = g->keys + h * W;
+    if(sl[0] == 0) return ORC_NOT_FOUND;
+    if(sl[0] == (key->b[0] | ORC_FLAG)) { for(w = 1; w < W && sl[w] == key->b[w]; w++) {} if(w == W) return h; }
+  }
+}
+
+/* _find_or_insert, src/tools/build_graph.c:99-118: with must_exist_in_graph the k-mer is only looked up
+ * (slot ORC_NOT_FOUND if absent) and coverage is added only when it is there */
 static OrcNode orc_add_kmer(OrcGraph *g, OrcKmer bk, size_t colour, int *found)
 {
-  OrcNode n;
-  OrcKmer key = orc_get_key(bk, g->k, &n.orient);
-  n.slot = orc_find_or_insert(g, &key, found);
+  OrcNode n; int o;
+  OrcKmer key = orc_get_key(bk, g->k, &o);
+  n.orient = o;
+  if(g->must_exist) {
+    n.slot = orc_find(g, &key);
+    *found = (n.slot != ORC_NOT_FOUND);
+    if(!*found) return n;
+  } else n.slot = orc_find_or_insert(g, &key, found);
   uint32_t *cv = &g->covgs[n.slot * g->ncols + colour];
   if(*cv < UINT32_MAX) (*cv)++; /* saturating */
   return n;
@@ -338,8 +361,10 @@ size_t orc_graph_add_contig(OrcGraph *g, size_t colour, const char *seq, size_t 
     /* lhs = first base of prev as read, rhs = last base of curr as read */
     uint8_t lhs = orc_char_to_nuc(seq[i - k]), rhs = nuc;
     uint8_t lhs_rev = (uint8_t)(~lhs & 3);
-    g->edges[prev.slot * g->ncols + colour] |= (uint8_t)(1u << (rhs + 4 * prev.orient));
-    g->edges[curr.slot * g->ncols + colour] |= (uint8_t)(1u << (lhs_rev + 4 * (!curr.orient)));
+    if(prev.slot != ORC_NOT_FOUND && curr.slot != ORC_NOT_FOUND) { /* build_graph.c:144-145 */
+      g->edges[prev.slot * g->ncols + colour] |= (uint8_t)(1u << (rhs + 4 * prev.orient));
+      g->edges[curr.slot * g->ncols + colour] |= (uint8_t)(1u << (lhs_rev + 4 * (!curr.orient)));
+    }
     nonnovel += (size_t)found;
   }
   return nonnovel;
@@ -362,8 +387,8 @@ void orc_graph_add_read(OrcGraph *g, const char *seq, size_t seqlen, const char 
     size_t nonnovel = orc_graph_add_contig(g, colour, seq + cs, clen);
     size_t ck = clen + 1 - k;
     st->total_bases_loaded += clen;
-    st->num_kmers_loaded += ck;
-    st->num_kmers_novel += ck - nonnovel;
+    if(g->must_exist) st->num_kmers_loaded += nonnovel;   /* build_graph.c:176-181 */
+    else { st->num_kmers_loaded += ck; st->num_kmers_novel += ck - nonnovel; }
     ncontigs++;
   }
   st->contigs_parsed += ncontigs;
@@ -510,8 +535,9 @@ size_t orc_graph_write_header(const OrcGraph *g, uint8_t *buf)
  * db_node_add_col_covg (saturating) and col_edges[into] |= edges (edge_mask = 0xff without --intersect). */
 static uint32_t orc_safe_add_covg(uint32_t a, uint32_t b) { uint64_t s = (uint64_t)a + b; return s > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)s; }
 uint64_t orc_graph_load_records(OrcGraph *g, const uint8_t *recs, uint64_t n, uint32_t file_ncols,
-                                const uint32_t *from, const uint32_t *into, uint32_t nmap, int must_exist, uint64_t *novel_out)
+                                const uint32_t *from, const uint32_t *into, uint32_t nmap, int flags, uint64_t *novel_out)
 {
+  const int must_exist = flags & 1;
   const size_t W = (size_t)g->W, C = g->ncols, rec = 8*W + 5*(size_t)file_ncols;
   uint32_t *cv = (uint32_t*)calloc(C, 4); uint8_t *ed = (uint8_t*)calloc(C, 1);
   uint64_t i, loaded = 0, novel = 0; uint32_t m; size_t c;
@@ -530,22 +556,21 @@ uint64_t orc_graph_load_records(OrcGraph *g, const uint8_t *recs, uint64_t n, ui
     if(!keep) continue;
     uint64_t slot; int found = 0;
     if(must_exist) {
-      /* hash_table_find */
-      uint64_t h = orc_lookup3(key.b, (int)W, 0, NULL) & g->mask; int hit = 0; size_t w;
-      for(;; h = (h + 1) & g->mask) {
-        uint64_t *sl = g->keys + h * W;
-        if(sl[0] == 0) break;
-        if(sl[0] == (key.b[0] | ORC_FLAG)) { for(w = 1; w < W && sl[w] == key.b[w]; w++) {} if(w == W) { hit = 1; break; } }
-      }
-      if(!hit) continue;
-      slot = h;
+      slot = orc_find(g, &key);
+      if(slot == ORC_NOT_FOUND) continue;
     } else {
       slot = orc_find_or_insert(g, &key, &found);
       novel += !found;
     }
-    for(c = 0; c < C; c++) {
-      g->covgs[slot*C + c] = orc_safe_add_covg(g->covgs[slot*C + c], cv[c]);
-      g->edges[slot*C + c] |= ed[c];
+    if(flags & 2) {
+      /* intersection graph: col_covgs is NULL and col_edges is the single isec edge set (ctx_build.c:350-358) */
+      for(c = 0; c < C; c++) g->isec_edges[slot] |= ed[c];
+    } else {
+      uint8_t edge_mask = (flags & 4) ? g->isec_edges[slot] : 0xff;   /* prefs.must_exist_in_edges */
+      for(c = 0; c < C; c++) {
+        g->covgs[slot*C + c] = orc_safe_add_covg(g->covgs[slot*C + c], cv[c]);
+        g->edges[slot*C + c] |= (uint8_t)(ed[c] & edge_mask);
+      }
     }
     loaded++;
   }
@@ -572,6 +597,29 @@ void orc_graph_merge_file_ginfo(OrcGraph *g, size_t into, uint32_t mean_read_len
   orc_ginfo_merge(&g->ginfo[into], &src);
 }
 
+/* build --intersect set-up and tear-down.
+ * orc_graph_set_intersect: allocate isec_edges (ctx_build.c:341-343); reads from now on must exist.
+ * orc_graph_finish_intersect: db_graph_remove_no_covg_kmers + db_graph_intersect_edges
+ * (src/graph/db_graph.c:632-673): a deleted k-mer simply is not dumped (hash_table_delete). */
+void orc_graph_set_intersect(OrcGraph *g, int must_exist_reads)
+{
+  if(!g->isec_edges) g->isec_edges = (uint8_t*)calloc(g->cap, 1);
+  g->must_exist = must_exist_reads;
+}
+#define ORC_TOMBSTONE (ORC_FLAG | (1ULL << 62))
+void orc_graph_finish_intersect(OrcGraph *g)
+{
+  uint64_t h; size_t c, C = g->ncols, W = (size_t)g->W;
+  for(h = 0; h < g->cap; h++) {
+    uint64_t *sl = g->keys + h * W;
+    if(sl[0] == 0 || sl[0] == ORC_TOMBSTONE) continue;
+    uint32_t any = 0;
+    for(c = 0; c < C; c++) any |= g->covgs[h*C + c];
+    if(!any) { sl[0] = ORC_TOMBSTONE; g->nkmers--; continue; }
+    for(c = 0; c < C; c++) g->edges[h*C + c] &= g->isec_edges[h];
+  }
+}
+
 static int orc_W_for_sort;
 static int orc_cmp_keys(const void *a, const void *b)
 {
@@ -591,7 +639,7 @@ size_t orc_graph_dump_sorted(const OrcGraph *g, uint8_t *buf)
   size_t off = orc_graph_write_header(g, buf), W = (size_t)g->W, C = g->ncols, i, n = 0;
   if(!buf) return off + g->nkmers * (8*W + 5*C);
   const uint64_t **ptrs = (const uint64_t**)malloc((g->nkmers + 1) * sizeof(*ptrs));
-  for(i = 0; i < g->cap; i++) if(g->keys[i*W]) ptrs[n++] = &g->keys[i*W];
+  for(i = 0; i < g->cap; i++) if(g->keys[i*W] && g->keys[i*W] != (ORC_FLAG | (1ULL << 62))) ptrs[n++] = &g->keys[i*W]; /* (not the removed ones) */
   orc_W_for_sort = g->W;
   qsort(ptrs, n, sizeof(*ptrs), orc_cmp_keys);
   for(i = 0; i < n; i++) {

@@ -79,6 +79,8 @@ def lib():
                                              C.POINTER(C.c_uint32), C.c_uint32, C.c_int, C.POINTER(C.c_uint64)]
         L.orc_graph_merge_file_ginfo.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint64, C.c_char_p, C.c_char_p,
                                                  C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p]
+        L.orc_graph_set_intersect.argtypes = [C.c_void_p, C.c_int]
+        L.orc_graph_finish_intersect.argtypes = [C.c_void_p]
         L.orc_guess_fq_offset.restype = C.c_int
         L.orc_guess_fq_offset.argtypes = [C.c_char_p, C.c_size_t]
         _lib = L
@@ -127,10 +129,21 @@ class Graph:
             raise IOError("cannot open " + path)
         return st
 
-    def load_ctx(self, spec, into_offset=0, must_exist=False):
-        """graph_load() of `[into:]path[:from]` (file_filter.c syntax); returns (ctx, loaded, novel)"""
+    def set_intersect(self, must_exist_reads=True):
+        lib().orc_graph_set_intersect(self.h, int(must_exist_reads))
+
+    def finish_intersect(self):
+        lib().orc_graph_finish_intersect(self.h)
+
+    def load_ctx(self, spec, into_offset=0, must_exist=False, isec=False, mask_isec=False):
+        """graph_load() of `[into:]path[:from]` (file_filter.c syntax); returns (ctx, loaded, novel).
+        isec: an intersection graph (flattened into colour 0, edges only, no header metadata);
+        mask_isec: edges ANDed with the intersection edge set (must_exist_in_edges)."""
         ctx = CtxFile(spec, into_offset)
-        for fr, into in ctx.filter:
+        if isec:
+            ctx.filter = [(f, 0) for f, _ in ctx.filter]
+            ctx.into_ncols = 1
+        for fr, into in ([] if isec else ctx.filter):
             h = ctx.ginfo[fr]
             lib().orc_graph_merge_file_ginfo(self.h, into, h["mean"], h["total"], h["name"], h["seq_err"], h["flags"],
                                              h["thr_unitigs"], h["thr_kmers"], h["isec_name"])
@@ -138,7 +151,8 @@ class Graph:
         fr = (C.c_uint32 * len(ctx.filter))(*[f for f, _ in ctx.filter])
         to = (C.c_uint32 * len(ctx.filter))(*[t for _, t in ctx.filter])
         novel = C.c_uint64(0)
-        loaded = lib().orc_graph_load_records(self.h, ctx.records, n, ctx.ncols, fr, to, len(ctx.filter), int(must_exist),
+        flags = (1 if must_exist else 0) | (2 if isec else 0) | (4 if mask_isec else 0)
+        loaded = lib().orc_graph_load_records(self.h, ctx.records, n, ctx.ncols, fr, to, len(ctx.filter), flags,
                                               C.byref(novel))
         return ctx, int(loaded), int(novel.value)
 
@@ -236,6 +250,7 @@ def build_ctx_args(k, args, capacity=1 << 20):
     overwrite the names of the colours they name (:379-382), stats credited per batch of <= 10 tasks (Q1)."""
     intocolour, sample_named = -1, False
     names, tasks, graphs = [], [], []
+    isecs = [args[i + 1] for i, a in enumerate(args) if a in ("-I", "--intersect")]
     fq_cutoff = fq_offset = hp_cutoff = 0
     it = iter(args)
     for a in it:
@@ -260,11 +275,16 @@ def build_ctx_args(k, args, capacity=1 << 20):
             intocolour = max(intocolour, ctx.into_ncols - 1)
             graphs.append((spec, ctx.filter[0][1] if False else None, intocolour, ctx))
             sample_named = False
+        elif a in ("-I", "--intersect"):
+            next(it)
         else:
             raise ValueError("unsupported build argument for the oracle: " + a)
     ncols = intocolour + (1 if sample_named else 0)
     g = Graph(k, ncols, capacity)
-    offs = []
+    if isecs:   # ctx_build.c:341-361
+        g.set_intersect(True)
+        for spec in isecs:
+            g.load_ctx(spec, 0, isec=True)
     # into_offset of each graph = intocolour at the time its -g was parsed
     intocolour = -1
     it = iter(args)
@@ -275,9 +295,9 @@ def build_ctx_args(k, args, capacity=1 << 20):
             if intocolour == -1:
                 intocolour = 0
             spec = next(it)
-            ctx, _, _ = g.load_ctx(spec, intocolour)
+            ctx, _, _ = g.load_ctx(spec, intocolour, must_exist=bool(isecs), mask_isec=bool(isecs))
             intocolour = max(intocolour, ctx.into_ncols - 1)
-        elif a in ("-1", "--seq", "-Q", "--fq-cutoff", "-O", "--fq-offset", "-H", "--cut-hp"):
+        elif a in ("-1", "--seq", "-Q", "--fq-cutoff", "-O", "--fq-offset", "-H", "--cut-hp", "-I", "--intersect"):
             next(it)
     for col, name in names:
         g.set_name(col, name)
@@ -286,6 +306,8 @@ def build_ctx_args(k, args, capacity=1 << 20):
         for col, t in tasks[start:start + MAX_IO_THREADS]:
             g.load_file(t["path"], col, t["fq_cutoff"], t["fq_offset"], t["hp_cutoff"], st)
         g.update_ginfo(tasks[start][0], st)
+    if isecs:   # ctx_build.c:409-413
+        g.finish_intersect()
     out = g.dump_sorted()
     full = g.full
     g.close()

@@ -100,6 +100,14 @@ def main():
     add_graph("graph_k63", 63, ["-g", "@/reads_k63.ctx", "-s", "t", "-1", "@/b.fa"])
     add_graph("sample_graph_sample_k21", 21, ["-s", "first", "-1", "@/b.fa", "-g", "@/two_colours_k21.ctx:1,0", "-s", "last", "-1", "@/g1.fa"])
 
+    # build --intersect: only k-mers of the intersection graph(s); reads and graphs are looked up, never inserted
+    add_graph("isec_reads_k21", 21, ["-I", "@/two_colours_k21.ctx", "-s", "z", "-1", "@/b.fa", "-1", "@/a.fa", "-s", "w", "-1", "@/g1.fa"])
+    add_graph("isec_filter_graph_k21", 21, ["-I", "@/two_colours_k21.ctx:1", "-g", "@/hp4_k21.ctx", "-s", "z", "-1", "@/b.fa"])
+    add_graph("isec_two_graphs_hp_k21", 21, ["-I", "@/hp4_k21.ctx", "-I", "@/fq10_k21.ctx", "-g", "@/two_colours_k21.ctx", "-s", "z",
+                                             "-H", "5", "-1", "@/a.fa", "-1", "@/q.fq"])
+    add_graph("isec_long_k31", 31, ["-I", "@/long_record_k31.ctx", "-s", "s2", "-1", "@/a.fa", "-1", "@/long.fa"])
+    add_graph("isec_k63", 63, ["-I", "@/reads_k63.ctx", "-s", "t", "-1", "@/b.fa", "-1", "@/a.fa"])
+
     with open(os.path.join(HERE, "cases.json"), "w") as f:
         json.dump(cases, f, indent=1)
     with open(os.path.join(HERE, "graph_cases.json"), "w") as f:

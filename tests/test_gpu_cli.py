@@ -163,3 +163,32 @@ def test_cli_graph_loading_matches_reference_binary(tmp_path, oracle, k):
         assert open(mine, "rb").read() == ref, args
         r = oracle.ref_run(k, ["check", "-q", mine], check=False)
         assert r.returncode == 0, r.stderr.decode()[-2000:]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "mccortex31")), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("k", [25, 45])
+def test_cli_intersect_matches_reference_binary(tmp_path, oracle, k):
+    """build --intersect on fresh inputs (reads that only partly overlap the intersection graph, so that
+    contigs contain runs of k-mers that are not found): bytes equal to the reference binary's"""
+    rng = random.Random(3000 + k)
+    fas = []
+    for i in range(3):
+        p = tmp_path / ("r%d.fa" % i)
+        p.write_text("".join(">r%d\n%s\n" % (j, r) for j, r in enumerate(rand_reads(rng, 500, (20, 260), 6000, perr=0.01))))
+        fas.append(str(p))
+    # the three files sample the same seeded genome? no: rand_reads draws a new genome per call -- share one
+    genome_reads = rand_reads(random.Random(5), 1500, (20, 260), 6000, perr=0.01)
+    for i in range(3):
+        with open(fas[i], "w") as f:
+            f.write("".join(">r%d\n%s\n" % (j, r) for j, r in enumerate(genome_reads[i * 500:(i + 1) * 500])))
+    isec = str(tmp_path / "isec.ctx")
+    oracle.ref_build(k, ["-s", "i", "-1", fas[0]], isec, threads=2, nkmers="2M")
+    other = str(tmp_path / "other.ctx")
+    oracle.ref_build(k, ["-s", "o", "-1", fas[1], "-s", "p", "-1", fas[2]], other, threads=2, nkmers="2M")
+    for n, args in enumerate((["-I", isec, "-s", "n", "-1", fas[1], "-1", fas[2]],
+                              ["-I", isec, "-g", other, "-s", "n", "-H", "6", "-1", fas[2]],
+                              ["-I", other + ":1", "-I", isec, "-g", other + ":0", "-s", "a", "-1", fas[0], "-s", "b", "-1", fas[1]])):
+        mine = str(tmp_path / ("mine%d.ctx" % n))
+        _run(["-q", "-f", "-m", "1G", "-n", "2M", "-k", str(k), "-S"] + args + [mine])
+        ref = oracle.ref_build(k, args, str(tmp_path / "ref.ctx"), threads=3, nkmers="2M")
+        assert open(mine, "rb").read() == ref, args
