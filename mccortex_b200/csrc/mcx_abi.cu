@@ -115,7 +115,7 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
   cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), g->own_primary);
   e = cudaStreamSynchronize(g->own_primary);
   if(e != cudaSuccess) { int r = fail_cuda(e, "memset(table)"); mcx_graph_destroy(g); return r; }
-  // front table (k <= 31, one colour): sized to sit in L2 (64 MB = 2^21 sets of four 8-byte
+  // front table (k <= 31; it counts one colour at a time and is flushed when the colour changes): sized to sit in L2 (64 MB = 2^21 sets of four 8-byte
   // slots); MCX_FRONT_BITS=0 disables it, other values are for experiments
   if(flags & MCX_GRAPH_INTERSECT) {
     e = cudaMalloc(&g->d_isec, (size_t)g->table.nslots + 8);
@@ -123,7 +123,7 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
     cudaMemset(g->d_isec, 0, (size_t)g->table.nslots + 8);
   }
   // (an intersected build only looks k-mers up: no front table)
-  if(g->table.stride == 4u && !(flags & MCX_GRAPH_INTERSECT)) {
+  if(g->W == 1u && !(flags & MCX_GRAPH_INTERSECT)) {
     uint32_t bits = 21;
     if(const char *m = getenv("MCX_FRONT_BITS")) bits = (uint32_t)atoi(m);
     if(bits) {
@@ -237,6 +237,17 @@ static McxBuildParams make_params(mcx_graph *g, const mcx_read_batch *b, const u
 // wrap, i.e. before 2^32 - 2^28 positions (an upper bound on the occurrences of any one k-mer)
 // have been queued since the last flush.
 #define MCX_FRONT_SPAN 0xEF000000ull  /* most positions one launch may cover */
+static int front_colour(mcx_graph *g, uint32_t colour)
+{
+  if(!g->table.front_set_bits || g->table.front_colour == colour) return MCX_OK;
+  if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must run before the colour changes"); return MCX_ERR_UNSUPPORTED; }
+  if(g->front_pending) {
+    CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+    g->front_pending = 0;
+  }
+  g->table.front_colour = colour;
+  return MCX_OK;
+}
 static int front_guard(mcx_graph *g, uint64_t positions)
 {
   if(!g->table.front_set_bits) return MCX_OK;
@@ -389,6 +400,7 @@ extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
   }
   CU(cudaSetDevice(g->device));
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
+  { int r = front_colour(g, b->colour); if(r) return r; }
   if((b->fq_cutoff && b->qual) || b->layout != MCX_LAYOUT_LINES) { int r = front_guard(g, b->nbytes + b->nreads); if(r) return r; }
   if(b->fq_cutoff && b->qual) return add_reads_qual(g, b);
 
@@ -573,6 +585,7 @@ static int add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t npa
   cudaStream_t st = primary(g);
   McxTupleBins bins;
   { int r = fill_bins(&bins, g->W, nparts, my_part, cap_per_part, keys_out, meta_out, keys_dst, meta_dst, counts_out); if(r) return r; }
+  { int r = front_colour(g, b->colour); if(r) return r; }
   g->sharded = true;
   { int r = front_guard(g, b->nbytes); if(r) return r; }
   CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));

@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t
         continue;
       }
     }
-    int r = mcx_table_add<1>(t, key, hc, hb, 0u, edges, count, may_saturate != 0);
+    int r = mcx_table_add<1>(t, key, hc, hb, t.front_colour, edges, count, may_saturate != 0);
     n_novel += (r == 1); full |= (r == 2);
   }
   for(int s = 16; s > 0; s >>= 1) {

@@ -22,7 +22,7 @@ struct McxTable {
   uint64_t nslots;      // always even
   uint32_t stride;      // u32 words per slot
   uint32_t ncols;
-  // L2-resident front table (k <= 31, one colour): a dense write-combining cache in front of
+  // L2-resident front table (k <= 31; one colour at a time): a dense write-combining cache in front of
   // the big table.  The big table is >> L2 and a hot k-mer there drags a whole 128-byte L2 line
   // for 16 useful bytes, so on high-coverage input the hot set does not fit L2 (ncu, first
   // kernel: 127 B of DRAM traffic per occurrence, L2 hit rate 30 %).  Layout, the bijective hash
@@ -36,6 +36,7 @@ struct McxTable {
   unsigned long long *front;   // tags: (4 << front_set_bits) slots, or nullptr
   unsigned int *front_cnt;     // counters: one per slot
   uint32_t front_set_bits;     // log2(number of sets); 0 = no front table
+  uint32_t front_colour;       // the ONE colour the front table is counting (it is flushed when the colour changes)
   // L2 eviction policies (createpolicy handles) applied by the kernels that set them; 0 = none
   uint64_t pol_front;          // front-table probe loads and counter REDs
   uint64_t pol_big;            // big-table probe loads
