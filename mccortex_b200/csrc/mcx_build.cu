@@ -28,7 +28,8 @@
 #include "mcx_table.cuh"
 #include "mcx_build.h"
 
-#define MCX_THREADS 256
+#define MCX_THREADS MCX_CTA_THREADS
+#define MCX_CTAS(n) ((n) * (256u / MCX_CTA_THREADS))   /* resident CTAs per SM, given for 256-thread CTAs */
 
 // Per-CTA staging of the chunk pipeline.  Three chunks are in flight per CTA (phase 1 of chunk
 // j+2, phase 2a of chunk j+1, phase 2b of chunk j run in the SAME barrier interval), hence the
@@ -114,6 +115,7 @@ __device__ __forceinline__ void mcx_apply_hints(McxTable &t)
   const uint32_t h = g_mcx_hints;
   t.pol_big = (h & 2u) ? mcx_policy_evict_first() : 0ull;
   t.pol_front = (h & 4u) ? mcx_policy_evict_last() : 0ull;
+  t.pol_cnt = (h & 64u) ? mcx_policy_evict_last() : ((h & 128u) ? mcx_policy_evict_first() : 0ull);
 }
 void mcx_set_hints(uint32_t h) { cudaMemcpyToSymbol(g_mcx_hints, &h, sizeof(h)); }
 
@@ -219,7 +221,7 @@ template <int W, int G> struct FusedSink { // G = probe loads kept in flight per
 #pragma unroll
         for(uint32_t i = 0; i < G; i++) {
           if((valid >> (h + i)) & 1u) {
-            if(!mcx_front_hit(g, t.front_cnt + ((uint64_t)(fk[i].y & g.setmask) << 2), t.pol_front, fk[i].x, (fk[i].y >> g.S) | g.occ,
+            if(!mcx_front_hit(g, t.front_cnt + ((uint64_t)(fk[i].y & g.setmask) << 2), t.pol_cnt, fk[i].x, (fk[i].y >> g.S) | g.occ,
                               emasks[h + i] << g.eshift, v[i][0], v[i][1], v[i][2], v[i][3]))
               park(keys[h + i], emasks[h + i]);
           }
@@ -459,7 +461,7 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
 }
 
 template <int W, int MINB, int G>
-__global__ void __launch_bounds__(MCX_THREADS, MINB) mcx_build_fused_kernel(McxBuildParams p, McxTable t)
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(MINB)) mcx_build_fused_kernel(McxBuildParams p, McxTable t)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
   if(threadIdx.x == 0) q->n = 0;
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(MCX_THREADS, MINB) mcx_build_fused_kernel(McxB
 // them (they are forwarded, aggregated, at flush); the parked pass inserts owned keys into the
 // local big table and bins the others for the exchange
 template <int W>
-__global__ void __launch_bounds__(MCX_THREADS, 3) mcx_build_sharded_kernel(McxBuildParams p, McxTable t, McxTupleBins b)
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(3)) mcx_build_sharded_kernel(McxBuildParams p, McxTable t, McxTupleBins b)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
   if(threadIdx.x == 0) q->n = 0;
@@ -488,13 +490,13 @@ struct NullSink {
   __device__ __forceinline__ void reset() {}
   __device__ __forceinline__ bool should_drain() const { return false; }
 };
-__global__ void __launch_bounds__(MCX_THREADS, 4) mcx_contig_summary_kernel(McxBuildParams p)
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_contig_summary_kernel(McxBuildParams p)
 {
   NullSink sink;
   mcx_front_end<1, MCX_MODE_QSUM>(p, sink);
 }
 template <int W>
-__global__ void __launch_bounds__(MCX_THREADS, 4) mcx_build_fused_qual_kernel(McxBuildParams p, McxTable t)
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_build_fused_qual_kernel(McxBuildParams p, McxTable t)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
   if(threadIdx.x == 0) q->n = 0;
@@ -503,7 +505,7 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_build_fused_qual_kernel(Mc
 }
 
 template <int W>
-__global__ void __launch_bounds__(MCX_THREADS, 4) mcx_kmer_tuples_kernel(McxBuildParams p, McxTupleBins b)
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_kmer_tuples_kernel(McxBuildParams p, McxTupleBins b)
 {
   TupleSink<W> sink{b};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
@@ -626,7 +628,7 @@ template <int W, class K> static size_t queue_smem(K kernel)
 static unsigned grid_for_chunks(const McxBuildParams &p, int ctas_per_sm)
 {
   uint64_t nch = (p.r_end + MCX_T - 1) / MCX_T - p.r_begin / MCX_T;
-  uint64_t g = (uint64_t)num_sms() * ctas_per_sm;
+  uint64_t g = (uint64_t)num_sms() * MCX_CTAS(ctas_per_sm);
   return (unsigned)(nch < g ? (nch ? nch : 1) : g);
 }
 

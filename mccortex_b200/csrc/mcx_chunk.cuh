@@ -12,7 +12,10 @@
 #pragma once
 #include "mcx_device.cuh"
 
-#define MCX_T     2048u                 /* window starts per chunk */
+#ifndef MCX_CTA_THREADS
+#define MCX_CTA_THREADS 256u             /* threads per CTA of the chunk kernels (128 was measured: see profiles/r1g_experiments.txt) */
+#endif
+#define MCX_T     (8u * MCX_CTA_THREADS) /* window starts per chunk: MCX_WPT per thread */
 #define MCX_LB    16u                   /* look-back bytes */
 #define MCX_TAIL  80u                   /* look-ahead bytes (>= 64 + 1, multiple of 16) */
 #define MCX_RAW   (MCX_LB + MCX_T + MCX_TAIL)   /* 2144 bytes, multiple of 16 */

@@ -38,7 +38,8 @@ struct McxTable {
   uint32_t front_set_bits;     // log2(number of sets); 0 = no front table
   uint32_t front_colour;       // the ONE colour the front table is counting (it is flushed when the colour changes)
   // L2 eviction policies (createpolicy handles) applied by the kernels that set them; 0 = none
-  uint64_t pol_front;          // front-table probe loads and counter REDs
+  uint64_t pol_front;          // front-table probe loads (tags)
+  uint64_t pol_cnt;            // front-table counter REDs
   uint64_t pol_big;            // big-table probe loads
 };
 
@@ -63,7 +64,7 @@ __device__ __forceinline__ void mcx_red_add_pol(unsigned int *p, uint32_t v, uin
   else atomicAdd(p, v);
 }
 // hint flags (experiments, MCX_L2_HINTS): 1 = input stream evict_first, 2 = big-table probes evict_first,
-// 4 = front table evict_last
+// 4 = front-table tags evict_last, 64 = counters evict_last, 128 = counters evict_first
 __device__ __forceinline__ uint64_t mcx_policy_evict_first()
 {
   uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); return pol;
@@ -312,7 +313,7 @@ __device__ __forceinline__ bool mcx_front_resolve_sector(const McxTable &t, cons
     }
     if(w < 0) return false;
   }
-  mcx_red_add_pol(t.front_cnt + s4 + (uint32_t)w, 1u, t.pol_front);
+  mcx_red_add_pol(t.front_cnt + s4 + (uint32_t)w, 1u, t.pol_cnt);
   if((seen_hi & eb) != eb) atomicOr(reinterpret_cast<unsigned int *>(&set[w]) + 1, eb);
   return true;
 }
