@@ -13,6 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 MCX_LAYOUT_LINES, MCX_LAYOUT_OFFSETS = 0, 1
 MCX_MEM_HOST, MCX_MEM_DEVICE = 0, 1
+MCX_GRAPH_INTERSECT = 1
+MCX_LOAD_MUST_EXIST, MCX_LOAD_INTO_ISEC, MCX_LOAD_MASK_ISEC = 1, 2, 4
 
 _STATUS = {0: "MCX_OK", 1: "MCX_ERR_BAD_ARG", 2: "MCX_ERR_CUDA", 3: "MCX_ERR_TABLE_FULL",
            4: "MCX_ERR_NOMEM", 5: "MCX_ERR_UNSUPPORTED", 6: "MCX_ERR_NO_DEVICE"}
@@ -160,11 +162,11 @@ def key_owner(key_words, k, nparts):
 class Graph:
     """Device-resident coloured de Bruijn graph shard (reference: dBGraph, src/graph/db_graph.h:23-56)."""
 
-    def __init__(self, kmer_size, ncols=1, capacity=1 << 20, device=0):
+    def __init__(self, kmer_size, ncols=1, capacity=1 << 20, device=0, flags=0):
         self.k, self.ncols, self.capacity, self.device = kmer_size, ncols, capacity, device
         self.W = (kmer_size + 31) // 32
         h = C.c_void_p()
-        _ck(lib().mcx_graph_create(kmer_size, ncols, capacity, device, 0, C.byref(h)), "mcx_graph_create")
+        _ck(lib().mcx_graph_create(kmer_size, ncols, capacity, device, flags, C.byref(h)), "mcx_graph_create")
         self.h = h
 
     def close(self):
@@ -194,18 +196,19 @@ class Graph:
         return b
 
     def add_reads_raw(self, seq_addr, nbytes, layout=MCX_LAYOUT_LINES, mem=MCX_MEM_HOST, colour=0, hp_cutoff=0,
-                      offsets_addr=None, nreads=0, qual_addr=None, fq_cutoff=0):
+                      offsets_addr=None, nreads=0, qual_addr=None, fq_cutoff=0, must_exist=False):
         b = self._batch(seq_addr, nbytes, layout, mem, colour, hp_cutoff, offsets_addr, nreads, qual_addr, fq_cutoff)
+        b.must_exist = 1 if must_exist else 0
         _ck(lib().mcx_graph_add_reads(self.h, C.byref(b)), "mcx_graph_add_reads")
 
-    def add_lines(self, data, colour=0, hp_cutoff=0, qual=None, fq_cutoff=0):
+    def add_lines(self, data, colour=0, hp_cutoff=0, qual=None, fq_cutoff=0, must_exist=False):
         """data: bytes in LINES layout (each read followed by one newline), host memory.
         qual: bytes parallel to data (0x7F where a read has no quality); fq_cutoff includes the ASCII offset."""
         buf = C.create_string_buffer(bytes(data), len(data))
         qbuf = C.create_string_buffer(bytes(qual), len(qual)) if qual is not None else None
         assert qbuf is None or len(qual) == len(data)
         self.add_reads_raw(C.addressof(buf), len(data), MCX_LAYOUT_LINES, MCX_MEM_HOST, colour, hp_cutoff,
-                           qual_addr=C.addressof(qbuf) if qbuf is not None else None, fq_cutoff=fq_cutoff)
+                           qual_addr=C.addressof(qbuf) if qbuf is not None else None, fq_cutoff=fq_cutoff, must_exist=must_exist)
 
     def add_reads(self, reads, colour=0, hp_cutoff=0, quals=None, fq_cutoff=0):
         """reads: list of bytes/str; shipped in OFFSETS layout (reads abut + offsets[n+1]).
@@ -235,6 +238,25 @@ class Graph:
         if isinstance(seq, str):
             seq = seq.encode()
         _ck(lib().mcx_graph_add_str(self.h, colour, seq, len(seq)), "mcx_graph_add_str")
+
+    # -- graph_load() ------------------------------------------------------------------
+    def load_records(self, records, file_ncols, from_cols, into_cols, flags=0):
+        """records: bytes of packed .ctx records (W x u64 key, file_ncols x u32 covg, file_ncols x u8 edges);
+        (from_cols[i], into_cols[i]) = the reference's FileFilter.  Returns (nkmers_loaded, nkmers_novel)."""
+        rb = 8 * self.W + 5 * file_ncols
+        assert len(records) % rb == 0 and len(from_cols) == len(into_cols)
+        buf = C.create_string_buffer(bytes(records), max(len(records), 1))
+        fr = (C.c_uint32 * len(from_cols))(*from_cols)
+        to = (C.c_uint32 * len(into_cols))(*into_cols)
+        nl, nn = C.c_uint64(), C.c_uint64()
+        _ck(lib().mcx_graph_load_records(self.h, buf, len(records) // rb, file_ncols, MCX_MEM_HOST, fr, to, len(from_cols),
+                                         flags, C.byref(nl), C.byref(nn)), "mcx_graph_load_records")
+        return int(nl.value), int(nn.value)
+
+    def finish_intersect(self):
+        n = C.c_uint64()
+        _ck(lib().mcx_graph_finish_intersect(self.h, C.byref(n)), "mcx_graph_finish_intersect")
+        return int(n.value)
 
     def sync(self):
         st = LoadStats()

@@ -428,3 +428,65 @@ def test_high_multiplicity_kmers_drain_the_front_table(M, oracle):
         assert got[i + 12] == recs[i + 12]
     assert max(int.from_bytes(got[i + 8:i + 12], "little") for i in range(0, len(got), rb)) >= 3 * 40000 * 120
     g.close()
+
+
+@pytest.mark.parametrize("k", [21, 47])
+def test_load_records_and_intersect_match_oracle(M, oracle, tmp_path, k):
+    """graph_load() through the C ABI (mcx_graph_load_records): a 3-colour graph file goes into a 2-colour
+    graph through the colour filter 2->1, 0->1 on top of reads; then the same file as an INTERSECTION
+    graph: must-exist graph load + must-exist reads + finish.  Both against the oracle's restatement
+    (pinned to the compiled reference in tests/test_oracle.py)."""
+    rng = random.Random(500 + k)
+    shared = rand_reads(rng, 900, (20, 240), 7000, perr=0.006)
+    parts = [shared[0:300], shared[300:600], shared[600:900]]
+    src = oracle.Graph(k, 3, 1 << 20)
+    for c, reads in enumerate(parts):
+        for r in reads:
+            src.add_read(r, colour=c)
+    path = tmp_path / "three.ctx"
+    path.write_bytes(src.dump_sorted())
+    src.close()
+    extra = shared[250:700]
+
+    # ---- build --graph 1,1:three.ctx:2,0 on top of reads in colour 0
+    og = oracle.Graph(k, 2, 1 << 20)
+    for r in extra:
+        og.add_read(r, colour=0)
+    ctx, oloaded, onovel = og.load_ctx("1,1:%s:2,0" % path)
+    want = og.dump_sorted()[len(og.header()):]
+    og.close()
+    g = M.Graph(k, 2, 1 << 20)
+    g.add_lines("".join(r + "\n" for r in extra).encode(), colour=0)
+    g.sync()
+    loaded, novel = g.load_records(ctx.records, ctx.ncols, [f for f, _ in ctx.filter], [t for _, t in ctx.filter])
+    assert (loaded, novel) == (oloaded, onovel)
+    g.sync()
+    got, n, _ = g.export_records()
+    assert got == want
+    g.close()
+
+    # ---- build --intersect three.ctx:1 --graph three.ctx:0,2 + reads
+    og = oracle.Graph(k, 3, 1 << 20)
+    og.set_intersect(True)
+    ictx, _, _ = og.load_ctx("%s:1" % path, 0, isec=True)
+    gctx, gl, _ = og.load_ctx("%s:0,2" % path, 0, must_exist=True, mask_isec=True)
+    ost = oracle.Stats()
+    for r in extra:
+        og.add_read(r, colour=2, stats=ost)
+    og.finish_intersect()
+    want = og.dump_sorted()[len(og.header()):]
+    og.close()
+    g = M.Graph(k, 3, 1 << 20, flags=M.MCX_GRAPH_INTERSECT)
+    g.load_records(ictx.records, ictx.ncols, [f for f, _ in ictx.filter], [0] * len(ictx.filter), M.MCX_LOAD_INTO_ISEC)
+    l2, n2 = g.load_records(gctx.records, gctx.ncols, [f for f, _ in gctx.filter], [t for _, t in gctx.filter],
+                            M.MCX_LOAD_MUST_EXIST | M.MCX_LOAD_MASK_ISEC)
+    assert (l2, n2) == (gl, 0)
+    g.sync()
+    g.add_lines("".join(r + "\n" for r in extra).encode(), colour=2, must_exist=True)
+    st = g.sync()
+    assert st.num_kmers_loaded == ost.num_kmers_loaded and st.num_kmers_novel == 0
+    assert st.contigs_parsed == ost.contigs_parsed and st.total_bases_loaded == ost.total_bases_loaded
+    kept = g.finish_intersect()
+    got, n, _ = g.export_records()
+    assert n == kept and got == want
+    g.close()
