@@ -157,6 +157,12 @@ int mcx_graph_export_begin(mcx_graph *g, int sorted, uint64_t *nrecords, uint32_
 int mcx_graph_export_read(mcx_graph *g, uint64_t first_record, uint64_t nrecords, void *host_dst);
 int mcx_graph_export_end(mcx_graph *g);
 
+/* replaces the body of `mccortex sort` (src/commands/ctx_sort.c:117-155: read every record, qsort pointers by
+ * key, write them back): nrecords packed .ctx records (W x u64 key, ncols x u32 covg, ncols x u8 edges) in
+ * host memory are ordered by ascending key on the GPU; records_out may be records_in. */
+int mcx_sort_records(int device, uint32_t kmer_size, uint32_t ncols, const void *records_in, uint64_t nrecords,
+                     void *records_out);
+
 /* ---- multi-GPU pieces (one graph shard per GPU, one process per GPU) ------------------------
  * Ownership: owner(key) = (c * nparts) >> 32 with c = Lookup3(key) (the hash the reference uses
  * for its bucket choice, src/graph/hash_table.c:259).  A tuple is

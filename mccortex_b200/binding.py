@@ -101,6 +101,7 @@ def lib():
     L.mcx_ipc_export.argtypes = [vp, C.c_char_p]
     L.mcx_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
     L.mcx_ipc_close.argtypes = [C.c_int, vp]
+    L.mcx_sort_records.argtypes = [C.c_int, u32, u32, vp, u64, vp]
     L.mcx_key_owner.restype = u32
     L.mcx_key_owner.argtypes = [C.POINTER(u64), u32, u32]
     _lib = L

@@ -735,6 +735,28 @@ extern "C" int mcx_graph_finish_intersect(mcx_graph *g, uint64_t *nkmers)
   return MCX_OK;
 }
 
+// replaces the body of ctx_sort (src/commands/ctx_sort.c:117-155): nrecords packed .ctx records in host
+// memory -> the same records in ascending key order (records_out may equal records_in)
+extern "C" int mcx_sort_records(int device, uint32_t kmer_size, uint32_t ncols, const void *records_in, uint64_t nrecords,
+                                void *records_out)
+{
+  if(kmer_size < 3 || kmer_size > 63 || !(kmer_size & 1u) || !ncols || (nrecords && (!records_in || !records_out))) return MCX_ERR_BAD_ARG;
+  if(mcx_device_count() == 0) { snprintf(g_err, sizeof(g_err), "no CUDA device: libmcxgpu has no CPU fallback"); return MCX_ERR_NO_DEVICE; }
+  if(nrecords == 0) return MCX_OK;
+  CU(cudaSetDevice(device));
+  const size_t bytes = (size_t)nrecords * (8u * ((kmer_size + 31u) / 32u) + 5u * (size_t)ncols);
+  uint8_t *d_in = NULL, *d_out = NULL;
+  cudaError_t e = cudaMalloc(&d_in, bytes + 16);
+  if(e == cudaSuccess) e = cudaMalloc(&d_out, bytes + 16);
+  if(e == cudaSuccess) e = cudaMemcpy(d_in, records_in, bytes, cudaMemcpyHostToDevice);
+  if(e == cudaSuccess) e = mcx_sort_records_device(d_in, nrecords, kmer_size, ncols, d_out, 0);
+  if(e == cudaSuccess) e = cudaMemcpy(records_out, d_out, bytes, cudaMemcpyDeviceToHost);
+  if(d_in) cudaFree(d_in);
+  if(d_out) cudaFree(d_out);
+  if(e != cudaSuccess) return fail_cuda(e, "mcx_sort_records");
+  return MCX_OK;
+}
+
 // ---- device buffers that peers can map (one process per GPU: CUDA IPC over NVLink) ----------
 extern "C" int mcx_device_alloc(int device, size_t bytes, void **dptr)
 {

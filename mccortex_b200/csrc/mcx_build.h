@@ -84,3 +84,4 @@ struct McxExport {
 };
 cudaError_t mcx_export_build(const McxTable &t, uint32_t kmer_size, bool sorted, McxExport *out, cudaStream_t st);
 void mcx_export_free(McxExport *e);
+cudaError_t mcx_sort_records_device(const uint8_t *d_in, uint64_t n, uint32_t k, uint32_t ncols, uint8_t *d_out, cudaStream_t st);

@@ -165,6 +165,72 @@ fail:
   return err;
 }
 
+// ---------------------------------------------------------------- sort of a graph FILE's records
+// Replaces ctx_sort (src/commands/ctx_sort.c:38-160): the records of a .ctx file (W x u64 key,
+// C x u32 covg, C x u8 edges, packed) are ordered by key.  The reference qsorts pointers with an
+// unaligned compare; here the keys are pulled out of the packed records, (key word, index) pairs
+// are radix sorted (stable; two passes for k > 31) and the records gathered in that order.
+__global__ void mcx_rec_keys_kernel(const uint8_t *__restrict__ recs, uint64_t n, uint32_t rec_bytes, uint32_t word,
+                                    const uint64_t *__restrict__ order, uint64_t *__restrict__ keys, uint64_t *__restrict__ idx)
+{
+  for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = order ? order[i] : i;
+    const uint8_t *p = recs + r * rec_bytes + 8u * word;
+    uint64_t v = 0;
+#pragma unroll
+    for(int b = 7; b >= 0; b--) v = (v << 8) | p[b];
+    keys[i] = v;
+    if(!order) idx[i] = i;
+  }
+}
+__global__ void mcx_rec_gather_kernel(const uint8_t *__restrict__ recs, const uint64_t *__restrict__ order, uint64_t n,
+                                      uint32_t rec_bytes, uint8_t *__restrict__ out)
+{
+  // one warp per record: lanes copy its bytes
+  const uint32_t lane = threadIdx.x & 31u;
+  uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for(uint64_t i = warp; i < n; i += nwarps) {
+    const uint8_t *s = recs + order[i] * rec_bytes;
+    uint8_t *d = out + i * rec_bytes;
+    for(uint32_t b = lane; b < rec_bytes; b += 32u) d[b] = s[b];
+  }
+}
+
+cudaError_t mcx_sort_records_device(const uint8_t *d_in, uint64_t n, uint32_t k, uint32_t ncols, uint8_t *d_out, cudaStream_t st)
+{
+  cudaError_t err = cudaSuccess;
+  const uint32_t W = (k + 31u) / 32u, rec_bytes = 8u * W + 5u * ncols;
+  uint64_t *keys = nullptr, *vals = nullptr, *keys_alt = nullptr, *vals_alt = nullptr;
+  void *tmp = nullptr; size_t tmp_bytes = 0;
+  int sms = 148, dev = 0;
+  if(n == 0) return cudaSuccess;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  CK(cudaMalloc(&keys, n * sizeof(uint64_t)));
+  CK(cudaMalloc(&vals, n * sizeof(uint64_t)));
+  CK(cudaMalloc(&keys_alt, n * sizeof(uint64_t)));
+  CK(cudaMalloc(&vals_alt, n * sizeof(uint64_t)));
+  // least significant key word first
+  mcx_rec_keys_kernel<<<sms * 8, 256, 0, st>>>(d_in, n, rec_bytes, W - 1u, nullptr, keys, vals);
+  CK(cudaGetLastError());
+  CK(radix_pass(&keys, &vals, &keys_alt, &vals_alt, n, W == 1 ? (int)(2u * k) : 64, &tmp, &tmp_bytes, st));
+  if(W == 2) {
+    mcx_rec_keys_kernel<<<sms * 8, 256, 0, st>>>(d_in, n, rec_bytes, 0u, vals, keys, nullptr);
+    CK(cudaGetLastError());
+    CK(radix_pass(&keys, &vals, &keys_alt, &vals_alt, n, (int)(2u * (k - 32u)), &tmp, &tmp_bytes, st));
+  }
+  mcx_rec_gather_kernel<<<sms * 16, 256, 0, st>>>(d_in, vals, n, rec_bytes, d_out);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+fail:
+  if(keys) cudaFree(keys);
+  if(vals) cudaFree(vals);
+  if(keys_alt) cudaFree(keys_alt);
+  if(vals_alt) cudaFree(vals_alt);
+  if(tmp) cudaFree(tmp);
+  return err;
+}
+
 void mcx_export_free(McxExport *e)
 {
   if(e && e->records) { cudaFree(e->records); e->records = nullptr; }

@@ -172,10 +172,10 @@ static size_t read_header(McxCtxFile *f)
       free(f->ginfo[i].sample_name);
       f->ginfo[i].sample_name = read_str(f, "sample name", i, &bytes_read);
     }
+    f->seq_err_raw = calloc(f->num_of_cols, 16);
     for(i = 0; i < f->num_of_cols; i++) {
-      unsigned char ld[sizeof(long double)];
-      gfread(f, ld, sizeof(ld), "seq error rates");
-      memcpy(&f->ginfo[i].seq_err, ld, sizeof(long double));
+      gfread(f, f->seq_err_raw[i], 16, "seq error rates");
+      memcpy(&f->ginfo[i].seq_err, f->seq_err_raw[i], 10);
     }
     bytes_read += sizeof(long double) * f->num_of_cols;
     for(i = 0; i < f->num_of_cols; i++) {
@@ -244,7 +244,39 @@ void mcx_ctx_close(McxCtxFile *f)
   if(!f) return;
   if(f->fh && f->fh != stdin) fclose(f->fh);
   if(f->ginfo) { for(uint32_t i = 0; i < f->num_of_cols; i++) mcx_ginfo_free(&f->ginfo[i]); free(f->ginfo); }
+  free(f->seq_err_raw);
   free(f->from_col); free(f->into_col); free(f->input); free(f->path); free(f);
+}
+
+bool mcx_ctx_filter_is_direct(const McxCtxFile *f)
+{
+  if(f->nfilter != f->num_of_cols) return false;
+  for(uint32_t i = 0; i < f->nfilter; i++) if(f->from_col[i] != i) return false;
+  return true;
+}
+
+size_t mcx_ctx_write_header_raw(FILE *fh, const McxCtxFile *f)
+{
+  size_t b = 0; uint32_t i, C = f->num_of_cols;
+#define PUT(p, n) do { if(fwrite((p), 1, (n), fh) != (size_t)(n)) mcx_die("Cannot write file"); b += (n); } while(0)
+  PUT("CORTEX", 6);
+  PUT(&f->version, 4); PUT(&f->kmer_size, 4); PUT(&f->num_of_bitfields, 4); PUT(&f->num_of_cols, 4);
+  for(i = 0; i < C; i++) PUT(&f->ginfo[i].mean_read_length, 4);
+  for(i = 0; i < C; i++) PUT(&f->ginfo[i].total_sequence, 8);
+  if(f->version >= 6) {
+    for(i = 0; i < C; i++) { uint32_t len = (uint32_t)strlen(f->ginfo[i].sample_name); PUT(&len, 4); PUT(f->ginfo[i].sample_name, len); }
+    for(i = 0; i < C; i++) PUT(f->seq_err_raw[i], 16);
+    for(i = 0; i < C; i++) {
+      const McxCleaning *c = &f->ginfo[i].cleaning;
+      unsigned char flags[4] = {c->cleaned_tips, c->cleaned_unitigs, c->cleaned_kmers, c->is_graph_intersection};
+      uint32_t tu = c->cleaned_unitigs ? c->clean_unitigs_thresh : 0, tk = c->cleaned_kmers ? c->clean_kmers_thresh : 0;
+      uint32_t len = (uint32_t)strlen(c->intersection_name);
+      PUT(flags, 4); PUT(&tu, 4); PUT(&tk, 4); PUT(&len, 4); PUT(c->intersection_name, len);
+    }
+  }
+  PUT("CORTEX", 6);
+#undef PUT
+  return b;
 }
 
 /* ---- graphs_load.c ------------------------------------------------------------------------ */

@@ -66,6 +66,7 @@ typedef struct {
   FILE *fh;
   uint32_t version, kmer_size, num_of_bitfields, num_of_cols;
   McxGInfo *ginfo;              /* num_of_cols entries */
+  unsigned char (*seq_err_raw)[16]; /* the 16 bytes of each colour's long double as stored (padding included) */
   size_t hdr_size;
   int64_t file_size, num_of_kmers;   /* -1 if unknown */
   uint32_t nfilter, *from_col, *into_col;   /* FileFilter, sorted by into */
@@ -79,7 +80,13 @@ void mcx_ctx_close(McxCtxFile *f);
  * load_flags: MCX_LOAD_* of mcx_gpu.h.  Returns 0 or an MCX_ERR_*. */
 int mcx_ctx_load(mcx_graph *g, McxCtxFile *f, McxGInfo *ginfo, size_t graph_ncols, uint32_t load_flags,
                  uint64_t *nkmers_read, uint64_t *nkmers_loaded, uint64_t *nkmers_novel);
-void mcx_ctx_flatten(McxCtxFile *f, uint32_t intocol);   /* file_filter_flatten, src/basic/file_filter.c:218-226 */
+void mcx_ctx_flatten(McxCtxFile *f, uint32_t intocol);
+/* graph_write_header(fh, &file->hdr) (src/graph/graph_writer.c:62-110): the header as parsed, not merged */
+size_t mcx_ctx_write_header_raw(FILE *fh, const McxCtxFile *f);
+bool mcx_ctx_filter_is_direct(const McxCtxFile *f);     /* file_filter_from_direct */
+
+/* `sort` command: src/commands/ctx_sort.c */
+int mcx_cmd_sort(int argc, char **argv);   /* file_filter_flatten, src/basic/file_filter.c:218-226 */
 
 /* ---- sequence input: libs/seq_file/seq_file.h, src/basic/seq_reader.c -------- */
 typedef struct McxSeqFile McxSeqFile;

@@ -192,3 +192,43 @@ def test_cli_intersect_matches_reference_binary(tmp_path, oracle, k):
         _run(["-q", "-f", "-m", "1G", "-n", "2M", "-k", str(k), "-S"] + args + [mine])
         ref = oracle.ref_build(k, args, str(tmp_path / "ref.ctx"), threads=3, nkmers="2M")
         assert open(mine, "rb").read() == ref, args
+
+
+def _run_cmd(cmd, args, check=True):
+    r = subprocess.run([_driver(), cmd] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    if check:
+        assert r.returncode == 0, r.stderr.decode()[-3000:]
+    return r
+
+
+@pytest.mark.parametrize("k", [31, 63])
+def test_cli_sort_command(tmp_path, oracle, k):
+    """`mccortex-b200 sort` (src/commands/ctx_sort.c): in place and with -o; sort(unsorted build) == build -S
+    (the reference asserts the same, tests/sort/Makefile:25-45), and == the reference's own `sort`"""
+    import shutil
+    rng = random.Random(4000 + k)
+    fa = tmp_path / "r.fa"
+    fa.write_text("".join(">r\n%s\n" % r for r in rand_reads(rng, 1500, (30, 200), 20000, perr=0.005)))
+    fb = tmp_path / "s.fa"
+    fb.write_text("".join(">r\n%s\n" % r for r in rand_reads(rng, 500, (30, 200), 20000, perr=0.005)))
+    base = ["-q", "-f", "-m", "1G", "-n", "4M", "-k", str(k), "-s", "a", "-1", str(fa), "-s", "b", "-1", str(fb)]
+    uns, srt = tmp_path / "uns.ctx", tmp_path / "sorted.ctx"
+    _run(base + [str(uns)])
+    _run(base[:2] + ["-S"] + base[2:] + [str(srt)])
+    want = open(srt, "rb").read()
+    assert open(uns, "rb").read() != want
+    out = tmp_path / "out.ctx"
+    _run_cmd("sort", ["-q", "-o", str(out), str(uns)])
+    assert open(out, "rb").read() == want
+    r = _run_cmd("sort", ["-q", "-o", str(out), str(uns)], check=False)
+    assert r.returncode == 1 and b"File already exists" in r.stderr
+    inplace = tmp_path / "inplace.ctx"
+    shutil.copy(uns, inplace)
+    _run_cmd("sort", ["-q", str(inplace)])
+    assert open(inplace, "rb").read() == want
+    assert _run_cmd("sort", ["-q", str(inplace) + ":0"], check=False).returncode == 1   # no filters
+    if oracle.ref_binary(k) is not None:
+        refcopy = tmp_path / "ref.ctx"
+        shutil.copy(uns, refcopy)
+        oracle.ref_run(k, ["sort", "-q", str(refcopy)])
+        assert open(refcopy, "rb").read() == want
