@@ -193,7 +193,8 @@ template <int W, int G> struct FusedSink { // G = probe loads kept in flight per
       // hot pass: G probe loads in flight per thread, one 32-bit RED per hit; no Lookup3, no
       // big-table access for k-mers that live in the L2-resident front table
       const McxFrontGeom g = mcx_front_geom(t);
-      const uint32_t abl = ablate; // experiments only (MCX_L2_HINTS bits 3..5): 0 in production
+#ifdef MCX_ABLATE  /* experiments only (profiles/r1g_experiments.txt, item 5): MCX_L2_HINTS bits 3..5 */
+      const uint32_t abl = ablate;
       if(abl) {
 #pragma unroll
         for(uint32_t h = 0; h < MCX_HALF; h++) {
@@ -210,6 +211,7 @@ template <int W, int G> struct FusedSink { // G = probe loads kept in flight per
         }
         return;
       }
+#endif
 #pragma unroll
       for(uint32_t h = 0; h < MCX_HALF; h += G) {
         uint64_t v[G][4]; McxFKey fk[G];
