@@ -61,7 +61,7 @@ typedef struct {
   uint8_t         hp_cutoff; /* 0 = off; else break contigs at homopolymer runs >= hp_cutoff (2 <= hp_cutoff <= k) */
   uint8_t         must_exist; /* SeqLoadingPrefs.must_exist_in_graph (build --intersect): k-mers are looked up, never
                                  inserted; coverage and edges only where the k-mers are in the graph
-                                 (src/tools/build_graph.c:99-150).  Not combinable with a quality cut-off yet. */
+                                 (src/tools/build_graph.c:99-150). */
   uint8_t         reserved;
 } mcx_read_batch;
 

@@ -376,7 +376,8 @@ static int add_reads_qual(mcx_graph *g, const mcx_read_batch *b)
   g->occ_bound += lines_bytes;
   McxBuildParams p = make_params(g, b, dseq, lines_bytes, 0, lines_bytes);
   p.qual = dqual; p.qcut = b->fq_cutoff; p.summary = g->d_tmp + sum_off;
-  CU(mcx_launch_build_fused_qual(p, g->table, st));
+  if(b->must_exist) { CU(mcx_launch_contig_summary(p, st)); CU(mcx_launch_build_lookup(p, g->table, st)); }
+  else CU(mcx_launch_build_fused_qual(p, g->table, st));
   g->pend_positions += lines_bytes;
   CU(cudaStreamSynchronize(st)); // d_tmp (and pageable host sources) are reused by the next batch
   return MCX_OK;
@@ -390,9 +391,6 @@ extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
     snprintf(g_err, sizeof(g_err), "hp_cutoff must be 0 or in [2, k]"); return MCX_ERR_UNSUPPORTED;
   }
   if(b->fq_cutoff >= 127) { snprintf(g_err, sizeof(g_err), "fq_cutoff (incl. offset) must be < 127"); return MCX_ERR_UNSUPPORTED; }
-  if(b->must_exist && b->fq_cutoff && b->qual) {
-    snprintf(g_err, sizeof(g_err), "must_exist (--intersect) cannot be combined with a quality cut-off yet"); return MCX_ERR_UNSUPPORTED;
-  }
   if(b->must_exist && g->table.front_set_bits) {
     // everything counted so far must be in the big table before k-mers are looked up there
     CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));

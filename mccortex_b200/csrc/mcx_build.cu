@@ -665,6 +665,14 @@ cudaError_t mcx_launch_build_fused_qual(const McxBuildParams &p, const McxTable 
   return cudaGetLastError();
 }
 
+// pass 1 of the quality cut-off alone (the must-exist kernel of mcx_lookup.cu runs its own pass 2)
+cudaError_t mcx_launch_contig_summary(const McxBuildParams &p, cudaStream_t st)
+{
+  if(p.r_end <= p.r_begin) return cudaSuccess;
+  mcx_contig_summary_kernel<<<grid_for_chunks(p, 4), MCX_THREADS, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
 cudaError_t mcx_launch_kmer_tuples(const McxBuildParams &p, const McxTupleBins &b, cudaStream_t st)
 {
   if(p.r_end <= p.r_begin) return cudaSuccess;

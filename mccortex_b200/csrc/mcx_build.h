@@ -72,6 +72,7 @@ cudaError_t mcx_launch_load_records(const uint8_t *recs, uint64_t n, uint32_t fi
 // build --intersect (mcx_lookup.cu): reads update only k-mers that are already in the table; the final pass
 // removes k-mers without coverage and ANDs every colour's edges with isec_edges
 cudaError_t mcx_launch_build_lookup(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
+cudaError_t mcx_launch_contig_summary(const McxBuildParams &p, cudaStream_t st);
 cudaError_t mcx_launch_finish_intersect(const McxTable &t, uint32_t W, const uint8_t *isec_edges, unsigned long long *nkept,
                                         cudaStream_t st);
 #define MCX_KEY_TOMBSTONE (MCX_KEY_FLAG | (1ULL << 62))  /* slot of a removed k-mer: never equal to a key, never empty */

@@ -21,15 +21,29 @@
 
 struct __align__(16) McxLookupSmem {
   uint8_t raw[MCX_RAW];
+  uint8_t qraw[MCX_RAW];      // quality bytes of the same positions (quality cut-off only)
   uint32_t pk[MCX_PKW];
   uint32_t bad[MCX_MSW];
+  uint32_t bads[MCX_MSW];     // base cannot be in a window that STARTS a contig (quality cut-off only)
   uint32_t eq[MCX_MSW];
   uint32_t vmask[MCX_VW];
+  uint32_t svm[MCX_VW];
   uint64_t slot[MCX_T + 2];   // window -1 .. T of the chunk: slot index | orientation << 63, or LK_NONE
   unsigned long long red[MCX_NCOUNTERS];
 };
 
-template <int W>
+// in_contig of the window just before `chunk` from the per-chunk carry summaries of pass 1 (same walk as mcx_build.cu)
+__device__ __forceinline__ uint32_t lk_carry_in(const uint8_t *summary, uint64_t chunk, uint64_t c_first)
+{
+  while(chunk > c_first) {
+    const uint32_t s = summary[--chunk - c_first];
+    if(s == 0u) return 0u;
+    if(s == 3u) return 1u;
+  }
+  return 0u;
+}
+
+template <int W, bool QUAL>
 __global__ void __launch_bounds__(LK_THREADS) mcx_build_lookup_kernel(McxBuildParams p, McxTable t)
 {
   extern __shared__ __align__(16) unsigned char lk_smem[];
@@ -37,7 +51,10 @@ __global__ void __launch_bounds__(LK_THREADS) mcx_build_lookup_kernel(McxBuildPa
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
   const uint64_t c_first = p.r_begin / MCX_T, c_last = (p.r_end + MCX_T - 1) / MCX_T;
   if(tid < MCX_NCOUNTERS) sm.red[tid] = 0;
-  if(tid < 4) { sm.pk[MCX_RAW / 16u + tid] = 0; sm.bad[MCX_RAW / 32u + tid] = 0xFFFFFFFFu; sm.eq[MCX_RAW / 32u + tid] = 0; }
+  if(tid < 4) {
+    sm.pk[MCX_RAW / 16u + tid] = 0; sm.bad[MCX_RAW / 32u + tid] = 0xFFFFFFFFu; sm.eq[MCX_RAW / 32u + tid] = 0;
+    sm.bads[MCX_RAW / 32u + tid] = 0xFFFFFFFFu;
+  }
   uint64_t n_found = 0, n_notfound = 0, n_contigs = 0, n_reads = 0;
   const uint64_t readable = (p.nbytes + 15ull) & ~15ull;
 
@@ -50,6 +67,11 @@ __global__ void __launch_bounds__(LK_THREADS) mcx_build_lookup_kernel(McxBuildPa
       uint4 v = make_uint4(0, 0, 0, 0);
       if(gpos < readable) v = *reinterpret_cast<const uint4 *>(p.seq + gpos);
       *reinterpret_cast<uint4 *>(&sm.raw[tid * 16u]) = v;
+      if(QUAL) {
+        uint4 qv = make_uint4(0, 0, 0, 0);
+        if(gpos < readable) qv = *reinterpret_cast<const uint4 *>(p.qual + gpos);
+        *reinterpret_cast<uint4 *>(&sm.qraw[tid * 16u]) = qv;
+      }
     }
     __syncthreads();
     if(tid < MCX_RAW / 16u) {
@@ -60,6 +82,14 @@ __global__ void __launch_bounds__(LK_THREADS) mcx_build_lookup_kernel(McxBuildPa
       uint32_t pk, b16, e16, n16;
       mcx_convert16(w, prev, gpos, p.nbytes, &pk, &b16, &e16, &n16);
       sm.pk[tid] = pk;
+      if(QUAL) {
+        const uint4 qv = *reinterpret_cast<const uint4 *>(&sm.qraw[tid * 16u]);
+        const uint32_t q[4] = {qv.x, qv.y, qv.z, qv.w};
+        uint32_t wk16, st16;
+        mcx_qual16(q, p.qcut, &wk16, &st16);
+        reinterpret_cast<uint16_t *>(sm.bads)[tid] = (uint16_t)(b16 | st16);
+        b16 |= wk16;
+      }
       reinterpret_cast<uint16_t *>(sm.bad)[tid] = (uint16_t)b16;
       reinterpret_cast<uint16_t *>(sm.eq)[tid] = (uint16_t)e16;
       if(n16 && tid >= MCX_LB / 16u && tid < (MCX_LB + MCX_T) / 16u)
@@ -71,8 +101,20 @@ __global__ void __launch_bounds__(LK_THREADS) mcx_build_lookup_kernel(McxBuildPa
     if(tid < MCX_VW) {
       const bool live = tid < (MCX_LB + MCX_T + 32u) / 32u;
       sm.vmask[tid] = live ? mcx_valid_word(sm.bad, sm.eq, tid, p.k, p.hp_cutoff) : 0u;
+      if(QUAL) sm.svm[tid] = live ? mcx_valid_word(sm.bads, sm.eq, tid, p.k, p.hp_cutoff) : 0u;
     }
     __syncthreads();
+    if(QUAL) {
+      // vmask holds ev, svm holds sv: in_contig = ev & (sv | in_contig(prev)), carry-in from the summaries of pass 1
+      if(tid == 0) {
+        const uint32_t cb = MCX_LB - 1u, keep = ~0u << cb;
+        const uint32_t cin = lk_carry_in(p.summary, chunk, c_first);
+        sm.vmask[0] = (sm.vmask[0] & keep & ~(1u << cb)) | (cin << cb);
+        sm.svm[0] = (sm.svm[0] & keep & ~(1u << cb)) | (cin << cb);
+        mcx_contig_chain(sm.vmask, sm.svm, MCX_VW, 0u, sm.vmask);
+      }
+      __syncthreads();
+    }
     // ---- pass A: look every window of the chunk, and the one on either side, up
     for(uint32_t idx = tid; idx < MCX_T + 2u; idx += LK_THREADS) {
       const uint32_t q = MCX_LB - 1u + idx;
@@ -131,13 +173,13 @@ cudaError_t mcx_launch_build_lookup(const McxBuildParams &p, const McxTable &t, 
   unsigned grid = (unsigned)(nch < cap ? (nch ? nch : 1) : cap);
   const size_t smem = sizeof(McxLookupSmem);
   McxTable big = t; big.front = nullptr; big.front_cnt = nullptr; big.front_set_bits = 0;
-  if(p.k <= 31) {
-    cudaFuncSetAttribute(mcx_build_lookup_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mcx_build_lookup_kernel<1><<<grid, LK_THREADS, smem, st>>>(p, big);
-  } else {
-    cudaFuncSetAttribute(mcx_build_lookup_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mcx_build_lookup_kernel<2><<<grid, LK_THREADS, smem, st>>>(p, big);
-  }
+#define LK_LAUNCH(WW, QQ) do { \
+    cudaFuncSetAttribute(mcx_build_lookup_kernel<WW, QQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    mcx_build_lookup_kernel<WW, QQ><<<grid, LK_THREADS, smem, st>>>(p, big); } while(0)
+  // p.qual set: quality cut-off; p.summary must then hold the carry summaries of mcx_launch_contig_summary
+  if(p.k <= 31) { if(p.qual) LK_LAUNCH(1, true); else LK_LAUNCH(1, false); }
+  else { if(p.qual) LK_LAUNCH(2, true); else LK_LAUNCH(2, false); }
+#undef LK_LAUNCH
   return cudaGetLastError();
 }
 

@@ -7,8 +7,7 @@
  * what mccortex31 / mccortex63 write for their k ranges.
  *
  * Not (yet) supported, and rejected with an error rather than silently ignored:
- *   -p/--remove-pcr (order dependent in the reference), SAM/BAM/CRAM input,
- *   -I/--intersect together with -Q/--fq-cutoff on inputs that carry qualities.
+ *   -p/--remove-pcr (order dependent in the reference), SAM/BAM/CRAM input.
  */
 #include "mcx_host.h"
 #include <ctype.h>

@@ -106,6 +106,8 @@ def main():
     add_graph("isec_two_graphs_hp_k21", 21, ["-I", "@/hp4_k21.ctx", "-I", "@/fq10_k21.ctx", "-g", "@/two_colours_k21.ctx", "-s", "z",
                                              "-H", "5", "-1", "@/a.fa", "-1", "@/q.fq"])
     add_graph("isec_long_k31", 31, ["-I", "@/long_record_k31.ctx", "-s", "s2", "-1", "@/a.fa", "-1", "@/long.fa"])
+    add_graph("isec_fq10_k15", 15, ["-I", "@/fq20_hp5_k15.ctx", "-s", "z", "-Q", "10", "-1", "@/q.fq"])
+    add_graph("isec_fq25_hp4_k15", 15, ["-I", "@/fq20_hp5_k15.ctx", "-s", "z", "-Q", "25", "-H", "4", "-1", "@/q.fq", "-1", "@/a.fa"])
     add_graph("isec_k63", 63, ["-I", "@/reads_k63.ctx", "-s", "t", "-1", "@/b.fa", "-1", "@/a.fa"])
 
     with open(os.path.join(HERE, "cases.json"), "w") as f:
