@@ -245,6 +245,8 @@ static int front_colour(mcx_graph *g, uint32_t colour)
     CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
     g->front_pending = 0;
   }
+  // the tags carry the old colour's edge bits: start the new colour with an empty front table
+  CU(cudaMemsetAsync(g->table.front, 0, (4ull << g->table.front_set_bits) * 12u, primary(g)));
   g->table.front_colour = colour;
   return MCX_OK;
 }

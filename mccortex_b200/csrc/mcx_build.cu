@@ -549,7 +549,8 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_insert_tuples_kernel(const
 }
 
 // ---------------------------------------------------------------- front-table flush
-// merge every front entry into the big table: key = phi^-1(set, tag), covg += count, edges |= edges
+// merge every front entry that has counted something since the last flush into the big table:
+// key = mcx_fhash_inv(set, tag), covg += count, edges |= edges; its counter restarts at 0
 __global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t, McxTupleBins bins, int may_saturate, unsigned long long *counters)
 {
   const McxFrontGeom g = mcx_front_geom(t);
@@ -562,6 +563,11 @@ __global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t
     McxKmer<1> key; key.b[0] = mcx_fhash_inv((uint32_t)v, ((hi & (g.occ - 1u)) << g.S) | ((uint32_t)(i >> 2) ^ (hi >> 31))); // displaced: home = the neighbouring set
     const uint32_t edges = (hi >> g.eshift) & 0xFFu;
     uint32_t count = t.front_cnt[i];
+    // The tags stay: the table is still warm after the flush (no second wave of claims for the ~4.6 M hot
+    // k-mers).  A record with no new occurrence has nothing new to merge -- its edge bits came with
+    // occurrences that an earlier flush merged.
+    if(count == 0) continue;
+    t.front_cnt[i] = 0;
     uint32_t hb, hc = mcx_lookup3<1>(key, 0u, &hb);
     if(bins.nparts > 1u) {
       // sharded build: an aggregated record of a key owned elsewhere travels as ONE tuple (a tuple
@@ -707,9 +713,7 @@ cudaError_t mcx_launch_front_flush(const McxTable &t, int may_saturate, unsigned
 {
   if(!t.front_set_bits) return cudaSuccess;
   mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, mcx_no_bins(), may_saturate, counters);
-  cudaError_t e = cudaGetLastError();
-  if(e != cudaSuccess) return e;
-  return cudaMemsetAsync(t.front, 0, (4ull << t.front_set_bits) * 12u, st); // tags + counters (one allocation)
+  return cudaGetLastError(); // (the kernel zeroes the counters it merges; the tags stay claimed)
 }
 
 cudaError_t mcx_launch_front_flush_sharded(const McxTable &t, const McxTupleBins &b, int may_saturate,
@@ -717,9 +721,7 @@ cudaError_t mcx_launch_front_flush_sharded(const McxTable &t, const McxTupleBins
 {
   if(!t.front_set_bits) return cudaSuccess;
   mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, b, may_saturate, counters);
-  cudaError_t e = cudaGetLastError();
-  if(e != cudaSuccess) return e;
-  return cudaMemsetAsync(t.front, 0, (4ull << t.front_set_bits) * 12u, st); // tags + counters (one allocation)
+  return cudaGetLastError();
 }
 
 cudaError_t mcx_launch_build_sharded(const McxBuildParams &p, const McxTable &t, const McxTupleBins &b, cudaStream_t st)
