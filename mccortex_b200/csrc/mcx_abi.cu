@@ -45,6 +45,7 @@ struct mcx_graph {
   uint64_t nkmers;         // slots claimed so far (updated at sync)
   McxExport exp; bool exp_valid;
   uint8_t *d_tmp; size_t d_tmp_bytes; // scratch for OFFSETS -> LINES repack
+  int ws_variant;          // MCX_WS=<variant>: experimental warp-specialised kernel (mcx_build_ws.cu), 0 = fused kernel
   uint8_t *d_isec;         // build --intersect: one edge byte per slot (Edges *isec_edges, ctx_build.c:341-343), else NULL
   size_t persist_bytes;    // experiment: L2 persisting window over the front table
   uint64_t front_pending;  // positions queued since the front table was last flushed (its counters are 32-bit)
@@ -140,6 +141,7 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
   // experiment knobs (see profiles/): probe-load flavour and L2 fetch granularity
   if(const char *m = getenv("MCX_MINB")) mcx_set_minb(atoi(m));
   if(const char *m = getenv("MCX_G")) mcx_set_inflight(atoi(m));
+  if(const char *m = getenv("MCX_WS")) g->ws_variant = atoi(m);
   if(const char *m = getenv("MCX_L2_HINTS")) mcx_set_hints((uint32_t)atoi(m));
   if(const char *m = getenv("MCX_L2_PERSIST_MB")) {
     // experiment: pin the front table with the L2 persistence controls
@@ -267,6 +269,7 @@ static int front_guard(mcx_graph *g, uint64_t positions)
 static cudaError_t launch_build(mcx_graph *g, const mcx_read_batch *b, const McxBuildParams &p, cudaStream_t st)
 {
   if(b->must_exist) return mcx_launch_build_lookup(p, g->table, st);
+  if(g->ws_variant && g->k <= 31 && g->table.front_set_bits) { mcx_set_ws_variant(g->ws_variant); return mcx_launch_build_ws(p, g->table, st); }
   return mcx_launch_build_fused(p, g->table, st);
 }
 

@@ -61,6 +61,9 @@ cudaError_t mcx_launch_front_flush_sharded(const McxTable &t, const McxTupleBins
 cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uint64_t nreads, uint8_t *dst, cudaStream_t st);
 
 cudaError_t mcx_launch_front_flush(const McxTable &t, int may_saturate, unsigned long long *counters, cudaStream_t st);
+// warp-specialised variant of the fused kernel (mcx_build_ws.cu): k <= 31, front table, no quality cut-off
+cudaError_t mcx_launch_build_ws(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
+void mcx_set_ws_variant(int v);
 void mcx_set_minb(int minb);
 void mcx_set_hints(uint32_t h);
 void mcx_set_inflight(int g);

@@ -174,19 +174,33 @@ template <int W> MCX_HD uint32_t mcx_first_base(const McxKmer<W> &f, uint32_t k)
 // A group is complete before any table access so that the sink can keep several probe loads in
 // flight (the kernel is L2-latency bound otherwise) without holding all eight keys in registers.
 #define MCX_HALF 4u
+// mcx_thread_occurrences2: `pre(j0)` is called before the keys of each group are computed, `fn` after it even
+// when the group has no window in a contig (valid == 0); returns false if the thread has no window in a
+// contig at all (then neither hook was called).  The warp-specialised kernel stages EVERY window.
+template <int W, class P, class F>
+MCX_HD bool mcx_thread_occurrences2(const uint32_t *pk, const uint32_t *vmask, uint32_t t, uint32_t k, P &&pre, F &&fn);
+
 template <int W, class F>
 MCX_HD void mcx_thread_occurrences(const uint32_t *pk, const uint32_t *vmask, uint32_t t, uint32_t k, F &&fn)
+{
+  mcx_thread_occurrences2<W>(pk, vmask, t, k, [](uint32_t) {}, [&](const McxKmer<W> *keys, const uint32_t *emasks, uint32_t valid,
+                                                                uint32_t starts, uint32_t j0) { if(valid) fn(keys, emasks, valid, starts, j0); });
+}
+
+template <int W, class P, class F>
+MCX_HD bool mcx_thread_occurrences2(const uint32_t *pk, const uint32_t *vmask, uint32_t t, uint32_t k, P &&pre, F &&fn)
 {
   const uint32_t p0 = MCX_LB + MCX_WPT * t;
   // in_contig bits of windows p0-1 .. p0+8 (bit 0 = the window before ours)
   const uint32_t vb = (uint32_t)(mcx_get64bits(vmask, p0 - 1u)) & 0x3FFu;
-  if(!(vb & 0x1FEu)) return;
+  if(!(vb & 0x1FEu)) return false;
   McxKmer<W> f = mcx_kmer_at<W>(pk, p0, k);
   McxKmer<W> r = mcx_kmer_revcomp<W>(f, k);
   const uint64_t nx = mcx_get32bases(pk, p0 + k);      // bases p0+k .. : the ones shifted in
   uint32_t prev = mcx_get_base(pk, p0 - 1u);           // base before the current window
 #pragma unroll
   for(uint32_t j0 = 0; j0 < MCX_WPT; j0 += MCX_HALF) {
+    pre(j0);
     McxKmer<W> keys[MCX_HALF]; uint32_t emasks[MCX_HALF];
 #pragma unroll
     for(uint32_t i = 0; i < MCX_HALF; i++) {
@@ -202,6 +216,7 @@ MCX_HD void mcx_thread_occurrences(const uint32_t *pk, const uint32_t *vmask, ui
     }
     const uint32_t valid = (vb >> (j0 + 1u)) & ((1u << MCX_HALF) - 1u);
     const uint32_t starts = valid & ~(vb >> j0);
-    if(valid) fn(keys, emasks, valid, starts, j0);
+    fn(keys, emasks, valid, starts, j0);
   }
+  return true;
 }

@@ -490,3 +490,26 @@ def test_load_records_and_intersect_match_oracle(M, oracle, tmp_path, k):
     got, n, _ = g.export_records()
     assert n == kept and got == want
     g.close()
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+def test_warp_specialised_kernel_matches_oracle(M, oracle, reads_small, variant, monkeypatch):
+    """the experimental warp-specialised build kernel (mcx_build_ws.cu, MCX_WS=<variant>: producer warps stage
+    hashed windows in shared memory, probe warps keep four tag loads in flight, variant 3 adds drain warps):
+    same records and counters as the oracle, including homopolymer cut-off, several batches and a k-mer
+    seen 240 000 times"""
+    monkeypatch.setenv("MCX_WS", str(variant))
+    rng = random.Random(600 + variant)
+    reads = reads_small + rand_reads(rng, 2500, 150, 12000, perr=0.004, pN=0.001) + ["A" * 150] * 2000
+    rng.shuffle(reads)
+    for k, hp in ((31, 0), (21, 4), (11, 0)):
+        recs, ost = oracle_records(oracle, reads, k, hp_cutoff=hp, capacity=1 << 22)
+        g = M.Graph(k, 1, 1 << 21)
+        half = len(reads) // 2
+        g.add_lines("".join(r + "\n" for r in reads[:half]).encode(), hp_cutoff=hp)
+        g.add_lines("".join(r + "\n" for r in reads[half:]).encode(), hp_cutoff=hp)
+        st = g.sync()
+        got, n, _ = g.export_records()
+        assert got == recs
+        _check_stats(st, ost, len(reads))
+        g.close()
