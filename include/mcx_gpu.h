@@ -77,6 +77,8 @@ typedef struct {
   uint64_t num_pe_reads;
   uint64_t num_good_reads;   /* UINT64_MAX when not computed */
   uint64_t num_bad_reads;    /* UINT64_MAX when not computed */
+  uint64_t num_dup_se_reads; /* mcx_graph_add_reads_pcr: single-end reads / read pairs dropped as duplicates */
+  uint64_t num_dup_pe_pairs;
 } mcx_load_stats;
 
 typedef struct mcx_graph mcx_graph;
@@ -96,6 +98,8 @@ int mcx_host_free(void *ptr);
  * (src/graph/hash_table.c:16-52).  capacity = number of k-mer slots (what
  * cmd_get_kmers_in_hash returns, src/graph/cmd_mem.c:38-130); 3 <= k <= 63, k odd. */
 #define MCX_GRAPH_INTERSECT 1u  /* flags: also allocate the intersection edge set (Edges *isec_edges, ctx_build.c:341-343) */
+#define MCX_GRAPH_READSTRT  2u  /* flags: also allocate the read-start marks of build --remove-pcr (DBG_ALLOC_READSTRT,
+                                   ctx_build.c:336; two u32 per k-mer slot here, two bits in the reference) */
 int mcx_graph_create(uint32_t kmer_size, uint32_t ncols, uint64_t capacity, int device, uint32_t flags, mcx_graph **out);
 /* replaces db_graph_dealloc (src/graph/db_graph.h:67) */
 int mcx_graph_destroy(mcx_graph *g);
@@ -144,6 +148,26 @@ int mcx_graph_load_records(mcx_graph *g, const void *records, uint64_t nrecords,
  * ctx_build.c:409-413) at the end of a build --intersect: k-mers without coverage in any colour leave the
  * graph, every colour's edges are ANDed with the intersection edge set.  *nkmers = k-mers left. */
 int mcx_graph_finish_intersect(mcx_graph *g, uint64_t *nkmers);
+
+/* ---- build --remove-pcr ---------------------------------------------------- */
+/* replaces build_graph_from_reads_mt with SeqLoadingPrefs.remove_pcr_dups (src/tools/build_graph.c:192-231), i.e.
+ * seq_reads_are_novel (:35-92) in front of load_read, for one batch.  batch: MCX_LAYOUT_LINES, host or device memory
+ * (device buffers are MODIFIED: reads re-oriented, duplicates overwritten with 'N'); read_off[nreads + 1] = byte offset
+ * of every read's first base (read_off[nreads] = nbytes), mate[nreads] = MCX_MATE_* per read, both in the same memory
+ * as the batch; the two reads of a pair are consecutive and in the same batch.  A read (pair) is dropped when each of its mates that has a k-mer starts, in the same orientation,
+ * on a k-mer where a mate of an EARLIER read (pair) of this colour started -- "earlier" in the order of the calls and
+ * of the reads inside a batch, which is what the reference does with one worker thread and one input task (with more
+ * threads its result depends on scheduling).  MCX_MATE_REVCOMP is seq_reader_orient_mp_FF (seq_reader.c:506-510): the
+ * caller sets it on read 1 when matedir & 2 and on read 2 when matedir & 1; the read is loaded in that orientation.
+ * Synchronous.  mcx_graph_sync reports the dropped reads / pairs in num_dup_se_reads / num_dup_pe_pairs. */
+#define MCX_MATE_SINGLE  0u
+#define MCX_MATE_FIRST   1u  /* first read of a pair: the next read is its mate */
+#define MCX_MATE_SECOND  2u
+#define MCX_MATE_REVCOMP 4u  /* OR-ed in: reverse-complement the read and reverse its qualities first */
+int mcx_graph_add_reads_pcr(mcx_graph *g, const mcx_read_batch *batch, const uint64_t *read_off, const uint8_t *mate,
+                            uint64_t nreads);
+/* forget all read starts: the memset of db_graph.readstrt when the colour changes (ctx_build.c:392-395) */
+int mcx_graph_pcr_reset(mcx_graph *g);
 
 /* replaces hash_table_print_stats inputs (src/graph/hash_table.h:73): occupancy */
 int mcx_graph_stats(mcx_graph *g, uint64_t *nkmers, uint64_t *capacity);

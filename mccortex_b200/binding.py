@@ -14,6 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 MCX_LAYOUT_LINES, MCX_LAYOUT_OFFSETS = 0, 1
 MCX_MEM_HOST, MCX_MEM_DEVICE = 0, 1
 MCX_GRAPH_INTERSECT = 1
+MCX_GRAPH_READSTRT = 2
+MCX_MATE_SINGLE, MCX_MATE_FIRST, MCX_MATE_SECOND, MCX_MATE_REVCOMP = 0, 1, 2, 4
 MCX_LOAD_MUST_EXIST, MCX_LOAD_INTO_ISEC, MCX_LOAD_MASK_ISEC = 1, 2, 4
 
 _STATUS = {0: "MCX_OK", 1: "MCX_ERR_BAD_ARG", 2: "MCX_ERR_CUDA", 3: "MCX_ERR_TABLE_FULL",
@@ -37,7 +39,8 @@ class ReadBatch(C.Structure):
 class LoadStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "total_bases_read", "total_bases_loaded", "contigs_parsed", "num_kmers_loaded",
-        "num_kmers_novel", "num_se_reads", "num_pe_reads", "num_good_reads", "num_bad_reads")]
+        "num_kmers_novel", "num_se_reads", "num_pe_reads", "num_good_reads", "num_bad_reads",
+        "num_dup_se_reads", "num_dup_pe_pairs")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -79,6 +82,8 @@ def lib():
     L.mcx_graph_clear.argtypes = [vp]
     L.mcx_graph_set_stream.argtypes = [vp, vp]
     L.mcx_graph_add_reads.argtypes = [vp, C.POINTER(ReadBatch)]
+    L.mcx_graph_add_reads_pcr.argtypes = [vp, C.POINTER(ReadBatch), vp, vp, C.c_uint64]
+    L.mcx_graph_pcr_reset.argtypes = [vp]
     L.mcx_graph_add_str.argtypes = [vp, u32, C.c_char_p, C.c_size_t]
     L.mcx_graph_sync.argtypes = [vp, C.POINTER(LoadStats)]
     L.mcx_graph_flush.argtypes = [vp]
@@ -234,6 +239,38 @@ class Graph:
         self.add_reads_raw(C.addressof(buf), len(blob), MCX_LAYOUT_OFFSETS, MCX_MEM_HOST, colour, hp_cutoff,
                            C.addressof(offs), len(reads),
                            qual_addr=C.addressof(qbuf) if qbuf is not None else None, fq_cutoff=fq_cutoff)
+
+    def add_units_pcr(self, units, quals=None, colour=0, fq_cutoff=0, hp_cutoff=0, matedir=1):
+        """build --remove-pcr for one batch (mcx_graph_add_reads_pcr): units = [(seq,) | (seq1, seq2), ...] in
+        reading order, quals parallel to it (strings, '' = none); matedir 0 FF, 1 FR, 2 RF, 3 RR.
+        fq_cutoff includes the ASCII offset.  The graph must have been created with MCX_GRAPH_READSTRT."""
+        lines, qlines, mates, offs, o = [], [], bytearray(), [], 0
+        for i, u in enumerate(units):
+            for m, r in enumerate(u):
+                r = r.encode() if isinstance(r, str) else bytes(r)
+                q = quals[i][m] if quals is not None else b""
+                q = (q.encode("latin1") if isinstance(q, str) else bytes(q or b""))[:len(r)]
+                flip = (matedir & 2) if m == 0 else (matedir & 1)
+                if q and len(q) < len(r) and flip:
+                    q = q + b"." * (len(r) - len(q))   # what seq_read_reverse_complement means to pad with
+                lines.append(r + b"\n")
+                qlines.append(q + b"\x7f" * (len(r) - len(q) + 1))
+                mates.append((0 if len(u) == 1 else 1 + m) | (MCX_MATE_REVCOMP if flip else 0))
+                offs.append(o)
+                o += len(r) + 1
+        offs.append(o)
+        blob, qblob = b"".join(lines), b"".join(qlines)
+        buf = C.create_string_buffer(blob, max(len(blob), 1))
+        qbuf = C.create_string_buffer(qblob, max(len(qblob), 1))
+        oarr = (C.c_uint64 * len(offs))(*offs)
+        marr = C.create_string_buffer(bytes(mates), max(len(mates), 1))
+        b = self._batch(C.addressof(buf), len(blob), MCX_LAYOUT_LINES, MCX_MEM_HOST, colour, hp_cutoff,
+                        qual_addr=C.addressof(qbuf) if fq_cutoff else None, fq_cutoff=fq_cutoff)
+        _ck(lib().mcx_graph_add_reads_pcr(self.h, C.byref(b), C.addressof(oarr), C.addressof(marr), len(mates)),
+            "mcx_graph_add_reads_pcr")
+
+    def pcr_reset(self):
+        _ck(lib().mcx_graph_pcr_reset(self.h), "mcx_graph_pcr_reset")
 
     def add_str(self, seq, colour=0):
         if isinstance(seq, str):

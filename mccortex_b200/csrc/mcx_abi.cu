@@ -49,6 +49,9 @@ struct mcx_graph {
   uint8_t *d_isec;         // build --intersect: one edge byte per slot (Edges *isec_edges, ctx_build.c:341-343), else NULL
   size_t persist_bytes;    // experiment: L2 persisting window over the front table
   uint64_t front_pending;  // positions queued since the front table was last flushed (its counters are 32-bit)
+  uint32_t *d_first;       // build --remove-pcr: first read ordinal per (slot, orientation) (mcx_pcr.cuh), else NULL
+  uint32_t pcr_ord;        // ordinal of the next read of this colour
+  uint8_t *d_pcr; size_t d_pcr_bytes; // --remove-pcr: device copy of the batch being filtered
   bool sharded;  // front table holds records of keys owned by other shards: only mcx_graph_flush_sharded may empty it
 };
 
@@ -104,7 +107,7 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
   size_t bytes = (size_t)g->table.nslots * g->table.stride * 4u;
   cudaError_t e = cudaMalloc(&g->table.slots, bytes);
   if(e != cudaSuccess) { free(g); return fail_cuda(e, "cudaMalloc(table)"); }
-  e = cudaMalloc(&g->d_counters, MCX_NCOUNTERS * sizeof(unsigned long long));
+  e = cudaMalloc(&g->d_counters, MCX_NCOUNTERS_ALL * sizeof(unsigned long long));
   if(e != cudaSuccess) { cudaFree(g->table.slots); free(g); return fail_cuda(e, "cudaMalloc(counters)"); }
   cudaStreamCreateWithFlags(&g->own_primary, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming);
@@ -113,7 +116,7 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
     cudaEventCreateWithFlags(&g->events[i], cudaEventDisableTiming);
   }
   cudaMemsetAsync(g->table.slots, 0, bytes, g->own_primary);
-  cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), g->own_primary);
+  cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS_ALL * sizeof(unsigned long long), g->own_primary);
   e = cudaStreamSynchronize(g->own_primary);
   if(e != cudaSuccess) { int r = fail_cuda(e, "memset(table)"); mcx_graph_destroy(g); return r; }
   // front table (k <= 31; it counts one colour at a time and is flushed when the colour changes): sized to sit in L2 (64 MB = 2^21 sets of four 8-byte
@@ -122,6 +125,11 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
     e = cudaMalloc(&g->d_isec, (size_t)g->table.nslots + 8);
     if(e != cudaSuccess) { int r = fail_cuda(e, "cudaMalloc(isec_edges)"); mcx_graph_destroy(g); return r; }
     cudaMemset(g->d_isec, 0, (size_t)g->table.nslots + 8);
+  }
+  if(flags & MCX_GRAPH_READSTRT) {
+    e = cudaMalloc(&g->d_first, (size_t)g->table.nslots * 8u);
+    if(e != cudaSuccess) { int r = fail_cuda(e, "cudaMalloc(read starts)"); mcx_graph_destroy(g); return r; }
+    cudaMemset(g->d_first, 0xFF, (size_t)g->table.nslots * 8u);
   }
   // (an intersected build only looks k-mers up: no front table)
   if(g->W == 1u && !(flags & MCX_GRAPH_INTERSECT)) {
@@ -172,6 +180,8 @@ extern "C" int mcx_graph_destroy(mcx_graph *g)
   if(g->ev_fork) cudaEventDestroy(g->ev_fork);
   if(g->d_tmp) cudaFree(g->d_tmp);
   if(g->d_isec) cudaFree(g->d_isec);
+  if(g->d_first) cudaFree(g->d_first);
+  if(g->d_pcr) cudaFree(g->d_pcr);
   if(g->table.front) cudaFree(g->table.front);
   if(g->d_counters) cudaFree(g->d_counters);
   if(g->table.slots) cudaFree(g->table.slots);
@@ -193,9 +203,11 @@ extern "C" int mcx_graph_clear(mcx_graph *g)
   CU(cudaSetDevice(g->device));
   cudaStream_t st = primary(g);
   CU(cudaMemsetAsync(g->table.slots, 0, (size_t)g->table.nslots * g->table.stride * 4u, st));
-  CU(cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS * sizeof(unsigned long long), st));
+  CU(cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS_ALL * sizeof(unsigned long long), st));
   if(g->table.front) CU(cudaMemsetAsync(g->table.front, 0, (4ull << g->table.front_set_bits) * 12u, st));
   if(g->d_isec) CU(cudaMemsetAsync(g->d_isec, 0, (size_t)g->table.nslots + 8, st));
+  if(g->d_first) CU(cudaMemsetAsync(g->d_first, 0xFF, (size_t)g->table.nslots * 8u, st));
+  g->pcr_ord = 0;
   g->front_pending = 0;
   g->sharded = false;
   g->occ_bound = 0; g->pend_positions = 0; g->pend_offsets_reads = g->pend_offsets_bases = 0; g->nkmers = 0;
@@ -445,6 +457,65 @@ extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
   return MCX_OK;
 }
 
+// ---- build --remove-pcr ---------------------------------------------------------------------
+extern "C" int mcx_graph_pcr_reset(mcx_graph *g)
+{
+  if(!g || !g->d_first) return MCX_ERR_BAD_ARG;
+  CU(cudaSetDevice(g->device));
+  CU(cudaMemsetAsync(g->d_first, 0xFF, (size_t)g->table.nslots * 8u, primary(g)));
+  g->pcr_ord = 0;
+  return MCX_OK;
+}
+
+extern "C" int mcx_graph_add_reads_pcr(mcx_graph *g, const mcx_read_batch *b, const uint64_t *read_off, const uint8_t *mate,
+                                       uint64_t nreads)
+{
+  if(!g || !b || b->colour >= g->ncols || b->layout != MCX_LAYOUT_LINES) return MCX_ERR_BAD_ARG;
+  if(!g->d_first) { snprintf(g_err, sizeof(g_err), "graph was not created with MCX_GRAPH_READSTRT"); return MCX_ERR_BAD_ARG; }
+  if(b->must_exist) { snprintf(g_err, sizeof(g_err), "remove-pcr and must-exist exclude each other (build_graph.c:197)"); return MCX_ERR_UNSUPPORTED; }
+  if(nreads == 0 || b->nbytes == 0) return MCX_OK;
+  if(!b->seq || !read_off || !mate || (b->mem != MCX_MEM_HOST && b->mem != MCX_MEM_DEVICE)) return MCX_ERR_BAD_ARG;
+  if(b->hp_cutoff == 1 || b->hp_cutoff > g->k) { snprintf(g_err, sizeof(g_err), "hp_cutoff must be 0 or in [2, k]"); return MCX_ERR_UNSUPPORTED; }
+  if(b->fq_cutoff >= 127) { snprintf(g_err, sizeof(g_err), "fq_cutoff (incl. offset) must be < 127"); return MCX_ERR_UNSUPPORTED; }
+  if((uint64_t)g->pcr_ord + nreads >= 0xFFFFFFFFull) { snprintf(g_err, sizeof(g_err), "remove-pcr: more than 4e9 reads in one colour"); return MCX_ERR_UNSUPPORTED; }
+  CU(cudaSetDevice(g->device));
+  cudaStream_t st = primary(g);
+  const bool useq = b->fq_cutoff && b->qual;
+  const bool host = b->mem == MCX_MEM_HOST;
+  const size_t A = 256, sb = ((size_t)b->nbytes + 16 + A - 1) / A * A;
+  const size_t seq_off = 0, qual_off = host ? sb : 0, off_off = qual_off + (host && useq ? sb : 0);
+  const size_t mate_off = off_off + (host ? ((size_t)(nreads + 1) * 8 + A - 1) / A * A : 0);
+  const size_t node_off = mate_off + (host ? ((size_t)nreads + A - 1) / A * A : 0);
+  const size_t need = node_off + (size_t)nreads * 8 + A;
+  if(g->d_pcr_bytes < need) {
+    int r = sync_all(g); if(r) return r;
+    if(g->d_pcr) cudaFree(g->d_pcr);
+    g->d_pcr = NULL; g->d_pcr_bytes = 0;
+    CU(cudaMalloc(&g->d_pcr, need + need / 4));
+    g->d_pcr_bytes = need + need / 4;
+  }
+  uint8_t *dseq = (uint8_t *)b->seq, *dqual = useq ? (uint8_t *)b->qual : nullptr;
+  const uint64_t *doff = read_off; const uint8_t *dmate = mate;
+  if(host) {
+    if(read_off[0] != 0 || read_off[nreads] != b->nbytes) return MCX_ERR_BAD_ARG;
+    dseq = g->d_pcr + seq_off;
+    CU(cudaMemcpyAsync(dseq, b->seq, b->nbytes, cudaMemcpyHostToDevice, st));
+    if(useq) { dqual = g->d_pcr + qual_off; CU(cudaMemcpyAsync(dqual, b->qual, b->nbytes, cudaMemcpyHostToDevice, st)); }
+    CU(cudaMemcpyAsync(g->d_pcr + off_off, read_off, (size_t)(nreads + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(g->d_pcr + mate_off, mate, (size_t)nreads, cudaMemcpyHostToDevice, st));
+    doff = (const uint64_t *)(g->d_pcr + off_off); dmate = g->d_pcr + mate_off;
+  }
+  CU(mcx_launch_pcr_filter(dseq, dqual, doff, dmate, nreads, g->k, useq ? b->fq_cutoff : 0u, b->hp_cutoff, g->table, g->d_first,
+                           (uint64_t *)(g->d_pcr + node_off), g->pcr_ord, g->d_counters, st));
+  g->pcr_ord += (uint32_t)nreads;
+  mcx_read_batch db = *b;
+  db.mem = MCX_MEM_DEVICE; db.seq = (const char *)dseq; db.qual = (const char *)dqual;
+  int r = mcx_graph_add_reads(g, &db);
+  if(r) return r;
+  CU(cudaStreamSynchronize(st)); // the device copy (and pageable host sources) are reused by the next batch
+  return MCX_OK;
+}
+
 extern "C" int mcx_graph_add_str(mcx_graph *g, uint32_t colour, const char *seq, size_t len)
 {
   if(!g || !seq) return MCX_ERR_BAD_ARG;
@@ -467,7 +538,7 @@ extern "C" int mcx_graph_sync(mcx_graph *g, mcx_load_stats *stats)
   CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
   g->front_pending = 0;
   CU(cudaStreamSynchronize(primary(g)));
-  unsigned long long c[MCX_NCOUNTERS];
+  unsigned long long c[MCX_NCOUNTERS_ALL];
   CU(cudaMemcpy(c, g->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
   CU(cudaMemset(g->d_counters, 0, sizeof(c)));
   g->nkmers += c[MCX_CNT_NOVEL];
@@ -483,6 +554,8 @@ extern "C" int mcx_graph_sync(mcx_graph *g, mcx_load_stats *stats)
     stats->total_bases_read = g->pend_positions - c[MCX_CNT_READS];
     stats->num_good_reads = UINT64_MAX;
     stats->num_bad_reads = UINT64_MAX;
+    stats->num_dup_se_reads = c[MCX_CNT_DUP_SE];
+    stats->num_dup_pe_pairs = c[MCX_CNT_DUP_PE];
   }
   g->pend_positions = 0;
   if(c[MCX_CNT_FULL]) { snprintf(g_err, sizeof(g_err), "Hash table is full"); return MCX_ERR_TABLE_FULL; }
@@ -707,7 +780,7 @@ extern "C" int mcx_graph_load_records(mcx_graph *g, const void *records, uint64_
   CU(cudaMemcpyAsync(d_from, from_col, 4u * (size_t)nmap, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(d_into, into_col, 4u * (size_t)nmap, cudaMemcpyHostToDevice, st));
   // counts of THIS call: read the running counters before and after
-  unsigned long long c0[MCX_NCOUNTERS], c1[MCX_NCOUNTERS];
+  unsigned long long c0[MCX_NCOUNTERS_ALL], c1[MCX_NCOUNTERS_ALL];
   CU(cudaMemcpyAsync(c0, g->d_counters, sizeof(c0), cudaMemcpyDeviceToHost, st));
   g->occ_bound = 0xF0000000ull; // file coverages can be anything: saturation-aware adds from here on
   CU(mcx_launch_load_records(drecs, nrecords, file_ncols, d_from, d_into, nmap, flags, g->k, g->table, g->d_isec, g->d_counters, st));

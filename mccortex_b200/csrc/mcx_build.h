@@ -14,7 +14,10 @@ enum {
   MCX_CNT_INSERTED,    // tuples inserted by kernel C
   MCX_CNT_RECS_LOADED, // graph-file records merged (mcx_ctxload.cu)
   MCX_CNT_NOTFOUND,    // must-exist builds: windows of a contig whose k-mer is not in the graph
-  MCX_NCOUNTERS = 8
+  MCX_NCOUNTERS = 8,   // counters the build kernels reduce in shared memory
+  MCX_CNT_DUP_SE = 8,  // --remove-pcr: single-end reads dropped       (num_dup_se_reads)
+  MCX_CNT_DUP_PE,      // --remove-pcr: read pairs dropped              (num_dup_pe_pairs)
+  MCX_NCOUNTERS_ALL = 10 // size of the device counter block
 };
 
 struct McxBuildParams {
@@ -78,6 +81,11 @@ cudaError_t mcx_launch_build_lookup(const McxBuildParams &p, const McxTable &t, 
 cudaError_t mcx_launch_contig_summary(const McxBuildParams &p, cudaStream_t st);
 cudaError_t mcx_launch_finish_intersect(const McxTable &t, uint32_t W, const uint8_t *isec_edges, unsigned long long *nkept,
                                         cudaStream_t st);
+// build --remove-pcr (mcx_pcr.cu): first = 2 * nslots u32 (MCX_PCR_UNSET when no read has started there), node = nreads
+// u64 scratch; seq / qual are modified in place (reads re-oriented, duplicates overwritten with 'N')
+cudaError_t mcx_launch_pcr_filter(uint8_t *seq, uint8_t *qual, const uint64_t *off, const uint8_t *mate, uint64_t nreads,
+                                  uint32_t k, uint32_t qcut, uint32_t hp, const McxTable &t, uint32_t *first, uint64_t *node,
+                                  uint32_t ord_base, unsigned long long *counters, cudaStream_t st);
 #define MCX_KEY_TOMBSTONE (MCX_KEY_FLAG | (1ULL << 62))  /* slot of a removed k-mer: never equal to a key, never empty */
 
 // export (mcx_export.cu)

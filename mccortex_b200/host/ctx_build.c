@@ -7,7 +7,7 @@
  * what mccortex31 / mccortex63 write for their k ranges.
  *
  * Not (yet) supported, and rejected with an error rather than silently ignored:
- *   -p/--remove-pcr (order dependent in the reference), SAM/BAM/CRAM input.
+ *   SAM/BAM/CRAM input.
  */
 #include "mcx_host.h"
 #include <ctype.h>
@@ -45,7 +45,7 @@ static const char build_usage[] =
 "  -Q, --fq-cutoff <Q>      Filter quality scores [default: 0 (off)]\n"
 "  -O, --fq-offset <N>      FASTQ ASCII offset    [default: 0 (auto-detect)]\n"
 "  -H, --cut-hp <bp>        Breaks reads at homopolymers >= <bp> [default: off]\n"
-"  -p, --remove-pcr         Remove (or keep) PCR duplicate reads [not supported]\n"
+"  -p, --remove-pcr         Remove (or keep) PCR duplicate reads\n"
 "  -P, --keep-pcr           Don't do PCR duplicate removal [default]\n"
 "  -M, --matepair <orient>  Mate pair orientation: FF,FR,RF,RR [default: FR]\n"
 "  -g, --graph <in.ctx>     Load samples from a graph file (.ctx)\n"
@@ -72,7 +72,8 @@ static struct option longopts[] = {
   {NULL, 0, NULL, 0}};
 
 typedef struct {
-  McxSeqFile *file;
+  McxSeqFile *file, *file2;   /* file2: the second file of a --seq2 pair kept together (--remove-pcr only) */
+  bool interleaved;           /* --seqi */
   McxLoadPrefs prefs;
   mcx_load_stats stats;
 } BuildTask;
@@ -132,12 +133,18 @@ static bool has_ext(const char *p, const char *ext)
   return n >= m && strcasecmp(p + n - m, ext) == 0;
 }
 
-static void push_task(const char *path, char opt, const McxLoadPrefs *prefs)
+static McxSeqFile *open_seq(const char *path, char opt)
 {
   if(has_ext(path, ".sam") || has_ext(path, ".bam") || has_ext(path, ".cram"))
     mcx_die("SAM/BAM/CRAM input is not supported by "CMD": %s", path);
   McxSeqFile *sf = mcx_seq_open(path);
   if(!sf) mcx_die("Cannot open -%c file: %s", opt, path);
+  return sf;
+}
+
+static void push_task(const char *path, char opt, const McxLoadPrefs *prefs)
+{
+  McxSeqFile *sf = open_seq(path, opt);
   if(ntasks == tasks_cap) { tasks_cap = tasks_cap ? tasks_cap * 2 : 16; tasks = realloc(tasks, tasks_cap * sizeof(*tasks)); }
   memset(&tasks[ntasks], 0, sizeof(tasks[ntasks]));
   tasks[ntasks].file = sf; tasks[ntasks].prefs = *prefs;
@@ -156,13 +163,18 @@ static void add_seq_arg(char opt, char *arg, const McxLoadPrefs *prefs)
     if(!sep || strchr(sep + 1, *sep)) mcx_die("Expected -%c <in1>:<in2>", opt);
     *sep = '\0';
     push_task(arg, opt, prefs);
-    push_task(sep + 1, opt, prefs);
-  } else push_task(arg, opt, prefs);
+    if(prefs->remove_pcr) tasks[ntasks - 1].file2 = open_seq(sep + 1, opt); /* submit paired end reads together */
+    else push_task(sep + 1, opt, prefs);
+  } else {
+    push_task(arg, opt, prefs);
+    tasks[ntasks - 1].interleaved = (opt == 'i');
+  }
 }
 
 static void parse_args(int argc, char **argv)
 {
   McxLoadPrefs prefs; memset(&prefs, 0, sizeof(prefs));
+  prefs.matedir = 1; /* SEQ_LOADING_PREFS_INIT: READPAIR_FR */
   int intocolour = -1, c;
   bool sample_named = false, pref_unused = false, kmer_given = false, threads_given = false;
   char cmd[100];
@@ -208,12 +220,13 @@ static void parse_args(int argc, char **argv)
       case 'M':
         if(strcmp(optarg, "FF") && strcmp(optarg, "FR") && strcmp(optarg, "RF") && strcmp(optarg, "RR"))
           mcx_die("-M,--matepair <orient> must be one of: FF,FR,RF,RR");
+        prefs.matedir = (uint8_t)((optarg[0] == 'R' ? 2 : 0) | (optarg[1] == 'R' ? 1 : 0)); /* cortex_types.h:17-25 */
         pref_unused = true; break; /* only matters with --remove-pcr */
       case 'O': prefs.fq_offset = parse_uint8(cmd, optarg); pref_unused = true; break;
       case 'Q': prefs.fq_cutoff = parse_uint8(cmd, optarg); pref_unused = true; break;
       case 'H': prefs.hp_cutoff = parse_uint8(cmd, optarg); pref_unused = true; break;
-      case 'p': mcx_die("--remove-pcr is not supported by "CMD" (order-dependent in the reference)");
-      case 'P': pref_unused = true; break;
+      case 'p': prefs.remove_pcr = true; pref_unused = true; break;
+      case 'P': prefs.remove_pcr = false; pref_unused = true; break;
       case 'g': { /* src/commands/ctx_build.c:189-196 */
         if(intocolour == -1) intocolour = 0;
         McxCtxFile *gf = mcx_ctx_open(optarg, (size_t)intocolour);
@@ -287,7 +300,8 @@ static void print_task_stats(const BuildTask *t)
     mcx_ulong_to_str(t->stats.num_good_reads, a); mcx_ulong_to_str(t->stats.num_bad_reads, b);
     mcx_status("  good reads: %s  bad reads: %s", a, b);
   }
-  mcx_status("  dup SE reads: 0  dup PE pairs: 0");
+  mcx_ulong_to_str(t->stats.num_dup_se_reads, a); mcx_ulong_to_str(t->stats.num_dup_pe_pairs, b);
+  mcx_status("  dup SE reads: %s  dup PE pairs: %s", a, b);
   mcx_ulong_to_str(t->stats.total_bases_read, a); mcx_ulong_to_str(t->stats.total_bases_loaded, b);
   mcx_status("  bases read: %s  bases loaded: %s", a, b);
   mcx_ulong_to_str(t->stats.contigs_parsed, a); mcx_ulong_to_str(t->stats.num_kmers_loaded, b);
@@ -312,22 +326,27 @@ static int ctx_build(int argc, char **argv)
       if(tasks[t].prefs.fq_offset) sprintf(off, "%u", tasks[t].prefs.fq_offset);
       if(tasks[t].prefs.fq_cutoff) sprintf(cut, "%u", tasks[t].prefs.fq_cutoff);
       if(tasks[t].prefs.hp_cutoff) sprintf(hp, "%u", tasks[t].prefs.hp_cutoff);
-      mcx_status("[task] %s; FASTQ offset: %s, threshold: %s; cut homopolymers: %s; remove PCR duplicates: no; colour: %u\n",
-                 mcx_seq_path(tasks[t].file), off, cut, hp, tasks[t].prefs.colour);
+      mcx_status("[task] %s%s%s; FASTQ offset: %s, threshold: %s; cut homopolymers: %s; remove PCR duplicates: %s; colour: %u\n",
+                 mcx_seq_path(tasks[t].file), tasks[t].file2 ? ", " : "", tasks[t].file2 ? mcx_seq_path(tasks[t].file2) : "",
+                 off, cut, hp, tasks[t].prefs.remove_pcr ? "yes" : "no", tasks[t].prefs.colour);
       t++;
     }
   }
 
   /* src/commands/ctx_build.c:285-289 + src/basic/async_read_io.c:313-334: 5 x file bytes */
   for(t = 0; t < ntasks; t++) {
-    int64_t fsize = mcx_seq_file_size(tasks[t].file);
-    if(fsize < 0) { max_kmers = SIZE_MAX; break; }
-    max_kmers += (size_t)fsize * 5;
+    int64_t fsize = mcx_seq_file_size(tasks[t].file), fsize2 = tasks[t].file2 ? mcx_seq_file_size(tasks[t].file2) : 0;
+    if(fsize < 0 || fsize2 < 0) { max_kmers = SIZE_MAX; break; }
+    max_kmers += (size_t)(fsize + fsize2) * 5;
   }
 
   /* src/commands/ctx_build.c:293-303: intersecting: every read only updates k-mers of the intersection
    * graphs, and those bound the table */
+  /* src/commands/ctx_build.c:259-261 */
+  bool remove_pcr_used = false;
+  for(t = 0; t < ntasks; t++) remove_pcr_used |= tasks[t].prefs.remove_pcr;
   if(nifiles > 0) {
+    if(remove_pcr_used) usage_err("Cannot use --remove-pcr and --intersect"); /* ctx_build.c:294-295 */
     for(t = 0; t < ntasks; t++) tasks[t].prefs.must_exist = true;
     max_kmers = 0;
     for(i = 0; i < nifiles; i++) max_kmers += ifiles[i]->num_of_kmers < 0 ? 0 : (size_t)ifiles[i]->num_of_kmers;
@@ -335,7 +354,9 @@ static int ctx_build(int argc, char **argv)
 
   /* src/commands/ctx_build.c:311-322 */
   size_t W = (kmer_size + 31) / 32, graph_mem;
-  size_t bits_per_kmer = W * 64 + (32 + 8) * output_colours + (nifiles > 0 ? 8 : 0) + (sort_kmers ? 64 : 0);
+  /* (the reference's arithmetic, so that -m gives the same number of k-mers: its read-start marks are two
+   * bits per k-mer; the device keeps two u32 per slot on top of that) */
+  size_t bits_per_kmer = W * 64 + (32 + 8) * output_colours + (nifiles > 0 ? 8 : 0) + (remove_pcr_used ? 2 : 0) + (sort_kmers ? 64 : 0);
   size_t kmers_in_hash = mcx_get_kmers_in_hash(mem_to_use, mem_set, num_kmers, nkmers_set, bits_per_kmer, 0,
                                                (int64_t)max_kmers, true, &graph_mem);
   if(graph_mem > mem_to_use) { char m[64]; mcx_bytes_to_str(graph_mem, m); mcx_die("Need to set higher memory limit [ at least -m %s ]", m); }
@@ -346,7 +367,7 @@ static int ctx_build(int argc, char **argv)
   if(mcx_device_count() == 0) mcx_die("No CUDA device: "CMD" has no CPU fallback");
   mcx_graph *g = NULL;
   int r = mcx_graph_create((uint32_t)kmer_size, (uint32_t)output_colours, kmers_in_hash, device,
-                           nifiles > 0 ? MCX_GRAPH_INTERSECT : 0, &g);
+                           (nifiles > 0 ? MCX_GRAPH_INTERSECT : 0) | (remove_pcr_used ? MCX_GRAPH_READSTRT : 0), &g);
   if(r) die_mcx(r, "mcx_graph_create");
   { char a[64]; mcx_ulong_to_str(kmers_in_hash, a); mcx_status("[hasht] Allocating device table with %s entries on GPU %i", a, device); }
 
@@ -385,11 +406,24 @@ static int ctx_build(int argc, char **argv)
   /* src/commands/ctx_build.c:389-407: build_graph() on batches of <= 10 tasks.  Quirk Q1
    * (src/tools/build_graph.c:242 vs :276,:285-300): within one call every task's header
    * statistics are credited to the batch's FIRST task, i.e. to that task's colour. */
-  size_t start, end;
+  /* With --remove-pcr anywhere (ctx_build.c:386-403): one call per run of <= 10 tasks of ONE colour, and the
+   * read-start marks are wiped when the colour changes.  The reference reads the files of one call
+   * concurrently; here they are read one after the other, in command-line order. */
+  size_t start, end; uint32_t prev_colour = 0;
   for(start = 0; start < ntasks; start = end) {
     end = start + MAX_IO_THREADS < ntasks ? start + MAX_IO_THREADS : ntasks;
+    if(remove_pcr_used) {
+      uint32_t colour = tasks[start].prefs.colour;
+      if(colour != prev_colour) { r = mcx_graph_pcr_reset(g); if(r) die_mcx(r, "mcx_graph_pcr_reset"); }
+      end = start + 1;
+      while(end < ntasks && end - start < MAX_IO_THREADS && tasks[end].prefs.colour == colour) end++;
+      prev_colour = colour;
+    }
     mcx_load_stats credited; memset(&credited, 0, sizeof(credited));
     for(t = start; t < end; t++) {
+      if(tasks[t].prefs.remove_pcr)
+        r = mcx_load_seq_pcr(g, tasks[t].file, tasks[t].file2, tasks[t].interleaved, &tasks[t].prefs, &tasks[t].stats);
+      else
       r = mcx_load_seq_file(g, tasks[t].file, &tasks[t].prefs, &tasks[t].stats);
       if(r) die_mcx(r, "loading sequence");
       credited.total_bases_loaded += tasks[t].stats.total_bases_loaded;
@@ -408,7 +442,7 @@ static int ctx_build(int argc, char **argv)
   mcx_graph_stats(g, &nk, &cap);
   { char a[64], b[64]; mcx_ulong_to_str(nk, a); mcx_ulong_to_str(cap, b);
     mcx_status("[hasht] table occupancy: %s / %s (%.2f%%)", a, b, cap ? 100.0 * nk / cap : 0.0); }
-  for(t = 0; t < ntasks; t++) { print_task_stats(&tasks[t]); mcx_seq_close(tasks[t].file); }
+  for(t = 0; t < ntasks; t++) { print_task_stats(&tasks[t]); mcx_seq_close(tasks[t].file); mcx_seq_close(tasks[t].file2); }
 
   mcx_status("Dumping graph...\n");
   FILE *fh = strcmp(out_path, "-") ? fopen(out_path, "w") : stdout;

@@ -98,6 +98,8 @@ int64_t mcx_seq_file_size(const McxSeqFile *sf);       /* -1 if unknown (stdin) 
 typedef struct {
   uint8_t fq_cutoff, hp_cutoff, fq_offset;             /* fq_offset 0 = auto-detect */
   bool must_exist;                                     /* SeqLoadingPrefs.must_exist_in_graph (--intersect) */
+  bool remove_pcr;                                     /* SeqLoadingPrefs.remove_pcr_dups */
+  uint8_t matedir;                                     /* ReadMateDir: 0 FF, 1 FR (default), 2 RF, 3 RR */
   uint32_t colour;
 } McxLoadPrefs;
 
@@ -105,5 +107,11 @@ typedef struct {
  * seq_file.h:311-323) and feed the graph in LINES batches.  Stats of this file are ADDED
  * to *stats.  Returns 0, or the MCX_ERR_* that stopped the load. */
 int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats);
+
+/* One task with --remove-pcr in force (build_graph_from_reads_mt with remove_pcr_dups): sf2 != NULL for a --seq2
+ * pair, interleaved for --seqi (consecutive reads whose names match are a pair), else single-end.  Reads and
+ * pairs go through mcx_graph_add_reads_pcr in file order. */
+int mcx_load_seq_pcr(mcx_graph *g, McxSeqFile *sf1, McxSeqFile *sf2, bool interleaved, const McxLoadPrefs *prefs,
+                     mcx_load_stats *stats);
 
 #endif /* MCX_HOST_H_ */

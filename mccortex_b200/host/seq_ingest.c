@@ -16,7 +16,15 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
-#define MCX_BATCH_BYTES (96u << 20)
+#define MCX_BATCH_BYTES_DEFAULT (96u << 20)
+/* bytes per batch; MCX_BATCH_BYTES=<n> in the environment overrides it (tests use tiny batches) */
+static size_t batch_bytes(void)
+{
+  static size_t v = 0;
+  if(!v) { const char *e = getenv("MCX_BATCH_BYTES"); v = e && atol(e) > 0 ? (size_t)atol(e) : MCX_BATCH_BYTES_DEFAULT; }
+  return v;
+}
+#define MCX_BATCH_BYTES batch_bytes()
 #define MCX_IN_BYTES (4u << 20)
 
 struct McxSeqFile {
@@ -105,6 +113,7 @@ static inline void chomp_from(Buf *b, size_t floor_len)
 static inline bool is_space(int c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
 /* ---- loader state ---------------------------------------------------------------- */
+typedef struct { int qmin, qmax; size_t qcount, bcount; } QStat;
 typedef struct {
   mcx_graph *g; const McxLoadPrefs *prefs; mcx_load_stats *stats;
   Buf lines;          /* LINES batch under construction */
@@ -112,14 +121,19 @@ typedef struct {
   Buf qual;           /* quality string of the current FASTQ record */
   uint64_t nreads_total;
   /* FASTQ offset auto-detection (seq_file.h:636-682): min/max of the first <= 1000 quals */
-  int qmin, qmax; size_t qcount, bcount; bool saw_qual;
+  QStat qs[2]; int cur;   /* per input file (two with --seq2 under --remove-pcr) */
   bool any_qual, offset_known; uint8_t fq_offset;
   int err;
+  /* --remove-pcr: one entry per read of the batch under construction */
+  bool pcr, want_names;
+  Buf name;           /* name line of the record just parsed (want_names) */
+  uint64_t *read_off; uint8_t *mate; size_t nreads, reads_cap;
+  uint8_t next_flip;  /* MCX_MATE_REVCOMP if the read being parsed will be reverse-complemented on the device */
 } Loader;
 
 /* FASTQ ASCII offset from the quality range of the first reads, exactly the decision list of
  * seq_guess_fastq_format (libs/seq_file/seq_file.h:666-682) + FASTQ_OFFSET (:127) */
-static uint8_t guess_fq_offset(const Loader *L)
+static uint8_t guess_fq_offset(const QStat *L)
 {
   static const int OFFS[6] = {33, 33, 64, 64, 64, 33};
   int fmt, mn = L->qmin, mx = L->qmax;
@@ -143,7 +157,7 @@ static void flush_batch(Loader *L)
   if(L->prefs->fq_cutoff && L->any_qual) {
     /* build_graph.c:202-207: the ASCII offset is added only when a cut-off is set */
     if(!L->offset_known) {
-      L->fq_offset = L->prefs->fq_offset ? L->prefs->fq_offset : guess_fq_offset(L);
+      L->fq_offset = L->prefs->fq_offset ? L->prefs->fq_offset : guess_fq_offset(&L->qs[0]);
       L->offset_known = true;
       if(L->fq_offset + L->prefs->fq_cutoff >= 127) { L->err = MCX_ERR_UNSUPPORTED; L->lines.len = L->qlines.len = 0; return; }
     }
@@ -160,26 +174,40 @@ static void flush_batch(Loader *L)
 static void end_read(Loader *L, size_t start)
 {
   size_t seqlen = L->lines.len - start;
-  if(L->qual.len && L->bcount < 1000) {
-    size_t lim = 1000 - L->qcount, n = L->qual.len < lim ? L->qual.len : lim, i;
+  QStat *qs = &L->qs[L->cur];
+  if(L->qual.len && qs->bcount < 1000) {
+    size_t lim = 1000 - qs->qcount, n = L->qual.len < lim ? L->qual.len : lim, i;
     for(i = 0; i < n; i++) {
       int q = (signed char)L->qual.b[i];
-      if(q > L->qmax) L->qmax = q;
-      if(q < L->qmin) L->qmin = q;
+      if(q > qs->qmax) qs->qmax = q;
+      if(q < qs->qmin) qs->qmin = q;
     }
-    L->bcount += seqlen; L->qcount += L->qual.len; L->saw_qual = true;
-  } else if(L->bcount < 1000) L->bcount += seqlen;
+    qs->bcount += seqlen; qs->qcount += L->qual.len;
+  } else if(qs->bcount < 1000) qs->bcount += seqlen;
   if(L->prefs->fq_cutoff) {
     /* quality bytes parallel to the sequence; 0x7F where the read has none (not filtered there) */
     size_t have = L->qual.len < seqlen ? L->qual.len : seqlen;
     buf_reserve(&L->qlines, seqlen + 1);
     memcpy(L->qlines.b + L->qlines.len, L->qual.b, have);
     memset(L->qlines.b + L->qlines.len + have, 0x7F, seqlen - have + 1);
+    /* a read that gets reverse-complemented has a too short quality string padded to the read's length
+     * first (seq_file.h:726-733,763; '.' is what that code means to pad with) */
+    if(L->next_flip && have > 0 && have < seqlen) memset(L->qlines.b + L->qlines.len + have, '.', seqlen - have);
     L->qlines.len += seqlen + 1;
     if(L->qual.len) L->any_qual = true;
   }
   buf_push(&L->lines, '\n');
   L->nreads_total++;
+  if(L->pcr) {
+    if(L->nreads + 2 > L->reads_cap) {
+      L->reads_cap = L->reads_cap ? L->reads_cap * 2 : 1u << 16;
+      L->read_off = realloc(L->read_off, L->reads_cap * sizeof(uint64_t));
+      L->mate = realloc(L->mate, L->reads_cap);
+      if(!L->read_off || !L->mate) mcx_die("Out of memory");
+    }
+    L->read_off[L->nreads] = start; L->mate[L->nreads] = L->next_flip; L->nreads++;
+    return; /* the pair logic decides when a batch is complete */
+  }
   if(L->lines.len >= MCX_BATCH_BYTES) flush_batch(L);
 }
 
@@ -188,7 +216,8 @@ static int read_fasta(McxSeqFile *sf, Loader *L)
 {
   int c = sgetc(sf);
   if(c == -1) return 0;
-  if(c != '>' || sreadline(sf, NULL) == 0) return -1;
+  L->name.len = 0;
+  if(c != '>' || sreadline(sf, L->want_names ? &L->name : NULL) == 0) return -1;
   size_t start = L->lines.len;
   L->qual.len = 0;
   while((c = speek(sf)) != '>') {
@@ -210,7 +239,8 @@ static int read_fastq(McxSeqFile *sf, Loader *L)
 {
   int c = sgetc(sf);
   if(c == -1) return 0;
-  if(c != '@' || sreadline(sf, NULL) == 0) return -1;
+  L->name.len = 0;
+  if(c != '@' || sreadline(sf, L->want_names ? &L->name : NULL) == 0) return -1;
   size_t start = L->lines.len;
   L->qual.len = 0;
   while((c = sgetc(sf)) != '+') {
@@ -243,7 +273,7 @@ static int read_plain(McxSeqFile *sf, Loader *L)
   while((c = sgetc(sf)) != -1 && is_space(c)) if(c != '\n') sreadline(sf, NULL);
   if(c == -1) return 0;
   size_t start = L->lines.len;
-  L->qual.len = 0;
+  L->qual.len = 0; L->name.len = 0;
   buf_push(&L->lines, (char)c);
   sreadline(sf, &L->lines);
   chomp_from(&L->lines, start);
@@ -254,7 +284,7 @@ static int read_plain(McxSeqFile *sf, Loader *L)
 int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats)
 {
   Loader L; memset(&L, 0, sizeof(L));
-  L.g = g; L.prefs = prefs; L.stats = stats; L.qmin = 0x7fffffff; L.qmax = 0;
+  L.g = g; L.prefs = prefs; L.stats = stats; L.qs[0].qmin = L.qs[1].qmin = 0x7fffffff;
   buf_reserve(&L.lines, MCX_BATCH_BYTES + (1u << 20));
   buf_reserve(&L.qual, 1u << 16);
 
@@ -287,5 +317,168 @@ int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, m
   char n1[64]; mcx_ulong_to_str(L.nreads_total, n1);
   mcx_status("[seq] Loaded %s reads and 0 reads pairs (file: %s)", n1, sf->path);
   free(L.lines.b); free(L.qual.b); free(L.qlines.b);
+  return r;
+}
+
+/* ---- --remove-pcr -------------------------------------------------------------------------
+ * The reads of one task go to the device together with their offsets and a mate byte each
+ * (mcx_graph_add_reads_pcr); which reads form a pair is decided here exactly like the reference's
+ * parse loops: --seq every read single (seq_reader.c:421-462), --seq2 read i of file 1 with read i of
+ * file 2 until either ends (:357-419), --seqi consecutive reads whose names match (:289-355,
+ * seq_file.h:783-800).  Re-orienting the mates (seq_reader.c:506-510) and the duplicate test itself
+ * run on the GPU. */
+static bool name_end(unsigned char c) { return !c || is_space(c); }
+static int names_cmp(const char *aa, const char *bb)
+{
+  const unsigned char *a = (const unsigned char *)aa, *b = (const unsigned char *)bb, *a0 = a, *b0 = b;
+  while(*a && *b && *a == *b && !is_space(*a)) { a++; b++; }
+  if(a > a0 && b > b0 && a[-1] == '/' && b[-1] == '/' && ((*a == '1' && *b == '2') || (*a == '2' && *b == '1')) &&
+     name_end(a[1]) && name_end(b[1])) return 0;
+  return name_end(*a) && name_end(*b) ? 0 : (int)*a - (int)*b;
+}
+
+/* ship the first n reads of the batch; later reads (at most one: a read still waiting for its mate) move to the front */
+static void flush_batch_pcr(Loader *L, size_t n)
+{
+  if(n == 0) return;
+  size_t cut = n < L->nreads ? L->read_off[n] : L->lines.len, i;
+  if(!L->err) {
+    mcx_read_batch b; memset(&b, 0, sizeof(b));
+    b.seq = L->lines.b; b.nbytes = cut;
+    b.layout = MCX_LAYOUT_LINES; b.mem = MCX_MEM_HOST;
+    b.colour = L->prefs->colour; b.hp_cutoff = L->prefs->hp_cutoff;
+    if(L->prefs->fq_cutoff && L->any_qual) {
+      if(!L->offset_known) {
+        uint8_t o1 = L->prefs->fq_offset ? L->prefs->fq_offset : guess_fq_offset(&L->qs[0]), o2 = o1;
+        if(!L->prefs->fq_offset && L->qs[1].bcount) o2 = guess_fq_offset(&L->qs[1]);
+        /* one threshold per batch: files of one pair with different ASCII offsets are not supported */
+        if(o1 != o2 && o1 && o2) mcx_die("Paired files with different FASTQ offsets (%u, %u) are not supported", o1, o2);
+        L->fq_offset = o1 ? o1 : o2;
+        L->offset_known = true;
+        if(L->fq_offset + L->prefs->fq_cutoff >= 127) L->err = MCX_ERR_UNSUPPORTED;
+      }
+      b.qual = L->qlines.b;
+      b.fq_cutoff = (uint8_t)(L->prefs->fq_cutoff + L->fq_offset);
+    }
+    if(!L->err) {
+      L->read_off[n] = cut; /* read_off[nreads] = nbytes for the call (already so when a read stays behind) */
+      int r = mcx_graph_add_reads_pcr(L->g, &b, L->read_off, L->mate, n);
+      if(r != MCX_OK) L->err = r;
+    }
+  }
+  memmove(L->lines.b, L->lines.b + cut, L->lines.len - cut);
+  L->lines.len -= cut;
+  if(L->prefs->fq_cutoff) { memmove(L->qlines.b, L->qlines.b + cut, L->qlines.len - cut); L->qlines.len -= cut; }
+  for(i = n; i < L->nreads; i++) { L->read_off[i - n] = L->read_off[i] - cut; L->mate[i - n] = L->mate[i]; }
+  L->nreads -= n;
+}
+
+typedef int (*ReaderFn)(McxSeqFile *, Loader *);
+static ReaderFn sniff_reader(McxSeqFile *sf)
+{
+  int c;
+  while((c = sgetc(sf)) != -1 && is_space(c)) if(c != '\n') sreadline(sf, NULL);
+  if(c == -1) return NULL;
+  sf->in_pos--;
+  return c == '@' ? read_fastq : (c == '>' ? read_fasta : read_plain);
+}
+
+int mcx_load_seq_pcr(mcx_graph *g, McxSeqFile *sf1, McxSeqFile *sf2, bool interleaved, const McxLoadPrefs *prefs,
+                     mcx_load_stats *stats)
+{
+  Loader L; memset(&L, 0, sizeof(L));
+  L.g = g; L.prefs = prefs; L.stats = stats; L.qs[0].qmin = L.qs[1].qmin = 0x7fffffff;
+  L.pcr = true; L.want_names = interleaved;
+  buf_reserve(&L.lines, MCX_BATCH_BYTES + (1u << 20));
+  buf_reserve(&L.qual, 1u << 16);
+  buf_reserve(&L.name, 1u << 10);
+  const uint8_t flip1 = (prefs->matedir & 2) ? MCX_MATE_REVCOMP : 0, flip2 = (prefs->matedir & 1) ? MCX_MATE_REVCOMP : 0;
+  uint64_t num_se = 0, num_pairs = 0;
+  int s1 = 0, s2 = 0;
+
+  if(sf2) mcx_status("[seq] Parsing sequence files %s %s\n", sf1->path, sf2->path);
+  else if(interleaved) mcx_status("[seq] Reading a (possibly) interleaved file (expect both S.E. & P.E. reads)");
+  else mcx_status("[seq] Parsing sequence file %s", sf1->path);
+
+  ReaderFn rd1 = sniff_reader(sf1), rd2 = sf2 ? sniff_reader(sf2) : NULL;
+  if(sf2) {
+    for(;;) {
+      const size_t n_before = L.nreads, len_before = L.lines.len, qlen_before = L.qlines.len;
+      const uint64_t total_before = L.nreads_total;
+      L.cur = 0; L.next_flip = flip1;
+      s1 = rd1 ? rd1(sf1, &L) : 0;
+      L.cur = 1; L.next_flip = flip2;
+      s2 = rd2 ? rd2(sf2, &L) : 0;
+      if(s1 < 0) mcx_warn("input error: %s", sf1->path);
+      if(s2 < 0) mcx_warn("input error: %s", sf2->path);
+      if((s1 > 0) != (s2 > 0) && !(s1 < 0 || s2 < 0)) mcx_warn("Different number of reads in pe files [%s; %s]\n", sf1->path, sf2->path);
+      if(s1 <= 0 || s2 <= 0) {
+        /* drop a read that has no mate (the reference never hands it to the graph) */
+        L.nreads = n_before; L.lines.len = len_before; L.qlines.len = qlen_before; L.nreads_total = total_before;
+        break;
+      }
+      L.mate[L.nreads - 2] |= MCX_MATE_FIRST; L.mate[L.nreads - 1] |= MCX_MATE_SECOND;
+      num_pairs++;
+      if(L.lines.len >= MCX_BATCH_BYTES) flush_batch_pcr(&L, L.nreads);
+      if(L.err) break;
+    }
+  } else if(interleaved) {
+    Buf prev_name = {0, 0, 0};
+    bool pending = false; /* the batch's last read is waiting to see whether the next one is its mate */
+    buf_reserve(&prev_name, 1u << 10);
+    L.cur = 0;
+    for(;;) {
+      L.next_flip = pending ? flip2 : flip1;
+      size_t before = L.nreads;
+      s1 = rd1 ? rd1(sf1, &L) : 0;
+      if(s1 <= 0) break;
+      buf_push(&L.name, '\0'); L.name.len--;
+      if(pending && names_cmp(prev_name.b, L.name.b) == 0) {
+        L.mate[before - 1] |= MCX_MATE_FIRST; L.mate[before] |= MCX_MATE_SECOND;
+        num_pairs++; pending = false;
+      } else {
+        if(pending) num_se++;
+        if(pending && flip1 != flip2) {
+          /* parsed as a possible second mate, it is a first one: its quality padding rule and flip flag follow read 1 */
+          L.mate[before] = flip1;
+        }
+        prev_name.len = 0; buf_reserve(&prev_name, L.name.len + 1);
+        memcpy(prev_name.b, L.name.b, L.name.len + 1); prev_name.len = L.name.len;
+        pending = true;
+      }
+      if(L.lines.len >= MCX_BATCH_BYTES) flush_batch_pcr(&L, L.nreads - (pending ? 1 : 0));
+      if(L.err) break;
+    }
+    if(pending) num_se++;
+    if(s1 < 0) mcx_warn("Input error: %s\n", sf1->path);
+    free(prev_name.b);
+  } else {
+    L.cur = 0; L.next_flip = flip1;
+    while((s1 = rd1 ? rd1(sf1, &L) : 0) > 0 && !L.err) {
+      num_se++;
+      if(L.lines.len >= MCX_BATCH_BYTES) flush_batch_pcr(&L, L.nreads);
+    }
+    if(s1 < 0) mcx_warn("Input error: %s\n", sf1->path);
+  }
+  flush_batch_pcr(&L, L.nreads);
+
+  mcx_load_stats st;
+  int r = mcx_graph_sync(g, &st);
+  if(L.err) r = L.err;
+  stats->total_bases_read += st.total_bases_read;
+  stats->total_bases_loaded += st.total_bases_loaded;
+  stats->contigs_parsed += st.contigs_parsed;
+  stats->num_kmers_loaded += st.num_kmers_loaded;
+  stats->num_kmers_novel += st.num_kmers_novel;
+  stats->num_se_reads += num_se;
+  stats->num_pe_reads += 2 * num_pairs;
+  stats->num_dup_se_reads += st.num_dup_se_reads;
+  stats->num_dup_pe_pairs += st.num_dup_pe_pairs;
+  stats->num_good_reads = stats->num_bad_reads = UINT64_MAX;
+
+  char n1[64], n2[64]; mcx_ulong_to_str(num_se, n1); mcx_ulong_to_str(num_pairs, n2);
+  if(sf2) mcx_status("[seq] Loaded %s read pairs (files: %s, %s)", n2, sf1->path, sf2->path);
+  else mcx_status("[seq] Loaded %s reads and %s reads pairs (file: %s)", n1, n2, sf1->path);
+  free(L.lines.b); free(L.qual.b); free(L.qlines.b); free(L.name.b); free(L.read_off); free(L.mate);
   return r;
 }

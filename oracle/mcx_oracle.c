@@ -222,6 +222,7 @@ typedef struct {
   uint64_t total_bases_read, total_bases_loaded, contigs_parsed;
   uint64_t num_kmers_loaded, num_kmers_novel;
   uint64_t num_se_reads, num_pe_reads, num_good_reads, num_bad_reads;
+  uint64_t num_dup_se_reads, num_dup_pe_pairs;
 } OrcStats; /* subset of src/basic/seq_loading_stats.h:5-14 */
 
 typedef struct {
@@ -246,6 +247,9 @@ typedef struct {
   /* build --intersect (src/commands/ctx_build.c:293-303,341-361,409-413) */
   int must_exist;        /* SeqLoadingPrefs.must_exist_in_graph for every read */
   uint8_t *isec_edges;   /* cap bytes, or NULL */
+  /* build --remove-pcr: "a read started here" per node and orientation (db_graph.h readstrt,
+   * src/tools/build_graph.c:29-32), one byte per bit here */
+  uint8_t *readstrt;     /* cap * 2 bytes, or NULL */
 } OrcGraph;
 
 static void orc_ginfo_init(OrcGInfo *g) /* src/basic/graph_info.c:60-67 */
@@ -276,7 +280,7 @@ OrcGraph *orc_graph_new(size_t k, size_t ncols, uint64_t capacity)
 void orc_graph_free(OrcGraph *g)
 {
   if(!g) return;
-  free(g->keys); free(g->covgs); free(g->edges); free(g->ginfo); free(g->isec_edges); free(g);
+  free(g->keys); free(g->covgs); free(g->edges); free(g->ginfo); free(g->isec_edges); free(g->readstrt); free(g);
 }
 
 uint64_t orc_graph_nkmers(const OrcGraph *g) { return g->nkmers; }
@@ -394,6 +398,89 @@ void orc_graph_add_read(OrcGraph *g, const char *seq, size_t seqlen, const char 
   st->contigs_parsed += ncontigs;
   st->num_good_reads += (ncontigs > 0);
   st->num_bad_reads += (ncontigs == 0);
+}
+
+/* ---- build --remove-pcr (row N3) ------------------------------------------------------------ */
+/* DBG_ALLOC_READSTRT (ctx_build.c:336) / the wipe between colours (ctx_build.c:392-395) */
+void orc_graph_wipe_readstrt(OrcGraph *g)
+{
+  if(!g->readstrt) g->readstrt = (uint8_t*)malloc(g->cap * 2);
+  memset(g->readstrt, 0, g->cap * 2);
+}
+
+/* seq_read_reverse_complement, libs/seq_file/seq_file.h:758-777 (complement of seq_file.h:715-723: only
+ * ACGTacgt change).  A quality string longer than the read is cut to the read's length first; for one
+ * that is SHORTER the reference calls cbuf_capacity with the length field in place of the capacity
+ * (seq_file.h:726-733), which leaves the missing qualities undefined -- the oracle pads with '.', the
+ * value that code was written to pad with, and the tests do not depend on it. */
+static char orc_complement(char c)
+{
+  switch(c) {
+    case 'a': return 't'; case 'A': return 'T'; case 'c': return 'g'; case 'C': return 'G';
+    case 'g': return 'c'; case 'G': return 'C'; case 't': return 'a'; case 'T': return 'A';
+    default: return c;
+  }
+}
+static void orc_read_revcomp(char *seq, size_t sl, char *qual, size_t *ql)
+{
+  size_t i, j;
+  if(*ql > 0) { for(i = *ql; i < sl; i++) qual[i] = '.'; *ql = sl; }
+  for(i = 0; i < sl / 2; i++) {
+    char a = seq[i], b = seq[sl - 1 - i];
+    seq[i] = orc_complement(b); seq[sl - 1 - i] = orc_complement(a);
+  }
+  if(sl & 1) seq[sl / 2] = orc_complement(seq[sl / 2]);
+  if(*ql > 0) for(i = 0, j = *ql - 1; i < j; i++, j--) { char t = qual[i]; qual[i] = qual[j]; qual[j] = t; }
+}
+
+/* build_graph_from_reads_mt (src/tools/build_graph.c:192-231) with prefs->remove_pcr_dups set, i.e.
+ * including seq_reads_are_novel (:35-92).  seq2 == NULL: a single-end read.  matedir: READPAIR_FF 0,
+ * FR 1, RF 2, RR 3 (cortex_types.h:17-25); read 1 is reverse-complemented when matedir & 2, read 2 when
+ * matedir & 1 (seq_reader.c:506-510) -- the reads stay that way when they are loaded.  fq_offset1/2: the
+ * ASCII offsets of the two files.  Reads are taken in the order of the calls (the reference with one
+ * worker thread and one input task). */
+void orc_graph_add_reads_pcr(OrcGraph *g, const char *seq1, size_t sl1, const char *qual1, size_t ql1,
+                             const char *seq2, size_t sl2, const char *qual2, size_t ql2,
+                             size_t colour, uint8_t fq_cutoff, uint8_t fq_offset1, uint8_t fq_offset2,
+                             uint8_t hp_cutoff, int matedir, OrcStats *st)
+{
+  size_t k = g->k;
+  uint8_t qc1 = fq_cutoff ? (uint8_t)(fq_cutoff + fq_offset1) : 0, qc2 = fq_cutoff ? (uint8_t)(fq_cutoff + fq_offset2) : 0;
+  char *s1 = (char*)malloc(sl1 + 1), *q1 = (char*)malloc((ql1 > sl1 ? ql1 : sl1) + 1), *s2 = NULL, *q2 = NULL;
+  memcpy(s1, seq1, sl1); if(ql1) memcpy(q1, qual1, ql1);
+  if(seq2) {
+    s2 = (char*)malloc(sl2 + 1); q2 = (char*)malloc((ql2 > sl2 ? ql2 : sl2) + 1);
+    memcpy(s2, seq2, sl2); if(ql2) memcpy(q2, qual2, ql2);
+  }
+  if(!g->readstrt) orc_graph_wipe_readstrt(g);
+  st->total_bases_read += sl1 + (seq2 ? sl2 : 0);
+  if(seq2) st->num_pe_reads += 2; else st->num_se_reads += 1;
+
+  /* seq_reads_are_novel */
+  if(matedir & 2) orc_read_revcomp(s1, sl1, q1, &ql1);
+  if(seq2 && (matedir & 1)) orc_read_revcomp(s2, sl2, q2, &ql2);
+  size_t start1 = orc_contig_start(s1, sl1, q1, ql1, 0, k, qc1, hp_cutoff), start2 = 0;
+  int got1 = start1 < sl1, got2 = 0, found1 = 0, found2 = 0, o1 = 0, o2 = 0;
+  uint64_t n1 = 0, n2 = 0;
+  if(seq2) { start2 = orc_contig_start(s2, sl2, q2, ql2, 0, k, qc2, hp_cutoff); got2 = start2 < sl2; }
+  if(got1) { OrcKmer key = orc_get_key(orc_bkmer_from_str(s1 + start1, k), k, &o1); n1 = orc_find_or_insert(g, &key, &found1); }
+  if(got2) { OrcKmer key = orc_get_key(orc_bkmer_from_str(s2 + start2, k), k, &o2); n2 = orc_find_or_insert(g, &key, &found2); }
+  st->num_kmers_novel += (uint64_t)(!found1 + !found2); /* build_graph.c:75-76: counts reads without a k-mer too */
+  int novel = !((!got1 || g->readstrt[2 * n1 + (uint64_t)o1]) && (!got2 || g->readstrt[2 * n2 + (uint64_t)o2]));
+  if(novel) {
+    if(got1) g->readstrt[2 * n1 + (uint64_t)o1] = 1;
+    if(got2) g->readstrt[2 * n2 + (uint64_t)o2] = 1;
+  }
+
+  if(!novel) { if(seq2) st->num_dup_pe_pairs++; else st->num_dup_se_reads++; }
+  else {
+    /* load_read of each mate; orc_graph_add_read also counts the read and its bases: undo that part */
+    OrcStats t = *st;
+    orc_graph_add_read(g, s1, sl1, ql1 ? q1 : NULL, ql1, colour, fq_cutoff, fq_offset1, hp_cutoff, st);
+    if(seq2) orc_graph_add_read(g, s2, sl2, ql2 ? q2 : NULL, ql2, colour, fq_cutoff, fq_offset2, hp_cutoff, st);
+    st->total_bases_read = t.total_bases_read; st->num_se_reads = t.num_se_reads;
+  }
+  free(s1); free(q1); free(s2); free(q2);
 }
 
 /* Per-window view of one read, for tuple-level checks of the GPU kernel:
@@ -691,6 +778,7 @@ uint64_t orc_hash_table_mem_limit(size_t memlimit, size_t entrybits, uint64_t *n
  * reads plain and gzip transparently).  Calls cb(seq,len,qual,qlen,ctx) per read. */
 typedef void (*orc_read_cb)(const char *seq, size_t seqlen, const char *qual, size_t quallen, void *ctx);
 
+static const char *orc_cur_name = ""; /* name line of the record being delivered (without '@' / '>') */
 typedef struct { const char *p, *end; } OrcCur;
 static int orc_getc(OrcCur *c) { return c->p < c->end ? (unsigned char)*c->p++ : -1; }
 /* append the rest of the current line (including '\n') to dst; returns bytes read */
@@ -774,6 +862,7 @@ long orc_parse_buffer(const char *buf, size_t n, orc_read_cb cb, void *ctx)
       orc_readline(&cur, &seq, &sl, &sc);
       orc_chomp(seq, &sl);
     }
+    orc_cur_name = name;
     cb(seq, sl, ql ? qual : NULL, ql, ctx);
     nreads++;
   }
@@ -847,4 +936,76 @@ long orc_graph_load_file(OrcGraph *g, const char *path, size_t colour,
   r = orc_parse_buffer(buf, n, orc_load_cb, &c);
   free(buf);
   return r;
+}
+
+/* ---- build --remove-pcr over files (row N3) ------------------------------------------------ */
+typedef struct { char *name, *seq, *qual; size_t sl, ql; } OrcRead;
+typedef struct { OrcRead *r; size_t n, cap; } OrcReadVec;
+static void orc_collect_cb(const char *seq, size_t sl, const char *qual, size_t ql, void *ctx)
+{
+  OrcReadVec *v = (OrcReadVec*)ctx;
+  if(v->n == v->cap) { v->cap = v->cap ? v->cap * 2 : 1024; v->r = (OrcRead*)realloc(v->r, v->cap * sizeof(OrcRead)); }
+  OrcRead *r = &v->r[v->n++];
+  r->name = (char*)malloc(strlen(orc_cur_name) + 1); strcpy(r->name, orc_cur_name);
+  r->seq = (char*)malloc(sl + 1); memcpy(r->seq, seq, sl); r->seq[sl] = 0; r->sl = sl;
+  r->qual = (char*)malloc(ql + 1); if(ql) memcpy(r->qual, qual, ql); r->qual[ql] = 0; r->ql = ql;
+}
+static void orc_readvec_free(OrcReadVec *v)
+{
+  size_t i;
+  for(i = 0; i < v->n; i++) { free(v->r[i].name); free(v->r[i].seq); free(v->r[i].qual); }
+  free(v->r);
+}
+static int orc_name_end(unsigned char c) { return !c || orc_isspace(c); }
+/* seq_read_names_cmp, libs/seq_file/seq_file.h:783-800: 0 when the names agree up to the first white
+ * space, or differ only in a trailing /1 vs /2 */
+static int orc_names_cmp(const char *aa, const char *bb)
+{
+  const unsigned char *a = (const unsigned char*)aa, *b = (const unsigned char*)bb, *a0 = a, *b0 = b;
+  while(*a && *b && *a == *b && !orc_isspace(*a)) { a++; b++; }
+  if(a > a0 && b > b0 && a[-1] == '/' && b[-1] == '/' && ((*a == '1' && *b == '2') || (*a == '2' && *b == '1')) &&
+     orc_name_end(a[1]) && orc_name_end(b[1])) return 0;
+  return orc_name_end(*a) && orc_name_end(*b) ? 0 : (int)*a - (int)*b;
+}
+
+/* One --seq / --seq2 / --seqi task with --remove-pcr in force: seq_parse_se_sf (seq_reader.c:421-462),
+ * seq_parse_pe_sf (:357-419: pairs until either file ends) or seq_parse_interleaved_sf (:289-355:
+ * consecutive reads whose names match are a pair, the rest single-end), every read / pair through
+ * orc_graph_add_reads_pcr in file order.  fq_offset 0 = auto-detect per file.  mode: 0 se, 1 pe (path2), 2 interleaved.
+ * Returns the number of reads consumed or -1000000000 if a file cannot be opened. */
+long orc_graph_load_pcr(OrcGraph *g, const char *path1, const char *path2, int mode, size_t colour,
+                        uint8_t fq_cutoff, uint8_t fq_offset, uint8_t hp_cutoff, int matedir, OrcStats *st)
+{
+  size_t n1 = 0, n2 = 0, i; long used = 0;
+  char *b1 = orc_slurp(path1, &n1), *b2 = NULL;
+  OrcReadVec v1 = {0, 0, 0}, v2 = {0, 0, 0};
+  uint8_t off1 = fq_offset, off2 = fq_offset;
+  if(!b1) return -1000000000L;
+  if(mode == 1) { b2 = orc_slurp(path2, &n2); if(!b2) { free(b1); return -1000000000L; } }
+  if(fq_offset == 0) { off1 = (uint8_t)orc_guess_fq_offset(b1, n1); if(b2) off2 = (uint8_t)orc_guess_fq_offset(b2, n2); }
+  orc_parse_buffer(b1, n1, orc_collect_cb, &v1);
+  if(b2) orc_parse_buffer(b2, n2, orc_collect_cb, &v2);
+  if(mode == 0) {
+    for(i = 0; i < v1.n; i++, used++)
+      orc_graph_add_reads_pcr(g, v1.r[i].seq, v1.r[i].sl, v1.r[i].qual, v1.r[i].ql, NULL, 0, NULL, 0,
+                              colour, fq_cutoff, off1, 0, hp_cutoff, matedir, st);
+  } else if(mode == 1) {
+    for(i = 0; i < v1.n && i < v2.n; i++, used += 2)
+      orc_graph_add_reads_pcr(g, v1.r[i].seq, v1.r[i].sl, v1.r[i].qual, v1.r[i].ql, v2.r[i].seq, v2.r[i].sl, v2.r[i].qual, v2.r[i].ql,
+                              colour, fq_cutoff, off1, off2, hp_cutoff, matedir, st);
+  } else {
+    for(i = 0; i < v1.n; ) {
+      OrcRead *a = &v1.r[i], *b = i + 1 < v1.n ? &v1.r[i + 1] : NULL;
+      if(b && orc_names_cmp(a->name, b->name) == 0) {
+        orc_graph_add_reads_pcr(g, a->seq, a->sl, a->qual, a->ql, b->seq, b->sl, b->qual, b->ql,
+                                colour, fq_cutoff, off1, off1, hp_cutoff, matedir, st);
+        i += 2; used += 2;
+      } else {
+        orc_graph_add_reads_pcr(g, a->seq, a->sl, a->qual, a->ql, NULL, 0, NULL, 0, colour, fq_cutoff, off1, 0, hp_cutoff, matedir, st);
+        i += 1; used += 1;
+      }
+    }
+  }
+  orc_readvec_free(&v1); orc_readvec_free(&v2); free(b1); free(b2);
+  return used;
 }

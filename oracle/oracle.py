@@ -27,7 +27,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "total_bases_read", "total_bases_loaded", "contigs_parsed",
         "num_kmers_loaded", "num_kmers_novel",
-        "num_se_reads", "num_pe_reads", "num_good_reads", "num_bad_reads")]
+        "num_se_reads", "num_pe_reads", "num_good_reads", "num_bad_reads",
+        "num_dup_se_reads", "num_dup_pe_pairs")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -81,6 +82,13 @@ def lib():
                                                  C.c_char_p, C.c_uint32, C.c_uint32, C.c_char_p]
         L.orc_graph_set_intersect.argtypes = [C.c_void_p, C.c_int]
         L.orc_graph_finish_intersect.argtypes = [C.c_void_p]
+        L.orc_graph_wipe_readstrt.argtypes = [C.c_void_p]
+        L.orc_graph_add_reads_pcr.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
+                                              C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_size_t,
+                                              C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint8, C.c_int, C.POINTER(Stats)]
+        L.orc_graph_load_pcr.restype = C.c_long
+        L.orc_graph_load_pcr.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_size_t, C.c_uint8, C.c_uint8,
+                                         C.c_uint8, C.c_int, C.POINTER(Stats)]
         L.orc_guess_fq_offset.restype = C.c_int
         L.orc_guess_fq_offset.argtypes = [C.c_char_p, C.c_size_t]
         _lib = L
@@ -127,6 +135,30 @@ class Graph:
         r = lib().orc_graph_load_file(self.h, path.encode(), colour, fq_cutoff, fq_offset, hp_cutoff, C.byref(st))
         if r == -1000000000:
             raise IOError("cannot open " + path)
+        return st
+
+    def wipe_readstrt(self):
+        lib().orc_graph_wipe_readstrt(self.h)
+
+    def add_reads_pcr(self, seq1, qual1=None, seq2=None, qual2=None, colour=0, fq_cutoff=0, fq_offset=0, hp_cutoff=0,
+                      matedir=1, stats=None):
+        """one read (seq2 None) or one pair through build_graph_from_reads_mt with --remove-pcr"""
+        st = stats if stats is not None else Stats()
+        enc = lambda x: x.encode("latin1") if isinstance(x, str) else x
+        seq1, qual1, seq2, qual2 = enc(seq1), enc(qual1), enc(seq2), enc(qual2)
+        lib().orc_graph_add_reads_pcr(self.h, seq1, len(seq1), qual1, len(qual1) if qual1 else 0,
+                                      seq2, len(seq2) if seq2 else 0, qual2, len(qual2) if qual2 else 0,
+                                      colour, fq_cutoff, fq_offset, fq_offset, hp_cutoff, matedir, C.byref(st))
+        return st
+
+    def load_pcr(self, path1, path2=None, interleaved=False, colour=0, fq_cutoff=0, fq_offset=0, hp_cutoff=0, matedir=1,
+                 stats=None):
+        st = stats if stats is not None else Stats()
+        mode = 1 if path2 else (2 if interleaved else 0)
+        r = lib().orc_graph_load_pcr(self.h, path1.encode(), path2.encode() if path2 else None, mode, colour, fq_cutoff,
+                                     fq_offset, hp_cutoff, matedir, C.byref(st))
+        if r == -1000000000:
+            raise IOError("cannot open " + path1)
         return st
 
     def set_intersect(self, must_exist_reads=True):
@@ -252,14 +284,28 @@ def build_ctx_args(k, args, capacity=1 << 20):
     names, tasks, graphs = [], [], []
     isecs = [args[i + 1] for i, a in enumerate(args) if a in ("-I", "--intersect")]
     fq_cutoff = fq_offset = hp_cutoff = 0
+    remove_pcr, matedir = False, 1   # SEQ_LOADING_PREFS_INIT: READPAIR_FR
     it = iter(args)
     for a in it:
         if a in ("-s", "--sample"):
             intocolour += 1
             names.append((intocolour, next(it)))
             sample_named = True
-        elif a in ("-1", "--seq"):
-            tasks.append((intocolour, dict(path=next(it), fq_cutoff=fq_cutoff, fq_offset=fq_offset, hp_cutoff=hp_cutoff)))
+        elif a in ("-1", "--seq", "-2", "--seq2", "-i", "--seqi"):
+            t = dict(path=next(it), path2=None, interleaved=a in ("-i", "--seqi"), fq_cutoff=fq_cutoff, fq_offset=fq_offset,
+                     hp_cutoff=hp_cutoff, remove_pcr=remove_pcr, matedir=matedir)
+            if a in ("-2", "--seq2"):
+                t["path"], t["path2"] = t["path"].split(":")
+                if not remove_pcr:   # add_task, ctx_build.c:99-118: two single-end tasks (quirk Q5)
+                    tasks.append((intocolour, dict(t, path2=None)))
+                    t = dict(t, path=t["path2"], path2=None)
+            tasks.append((intocolour, t))
+        elif a in ("-p", "--remove-pcr"):
+            remove_pcr = True
+        elif a in ("-P", "--keep-pcr"):
+            remove_pcr = False
+        elif a in ("-M", "--matepair"):
+            matedir = ["FF", "FR", "RF", "RR"].index(next(it))
         elif a in ("-Q", "--fq-cutoff"):
             fq_cutoff = int(next(it))
         elif a in ("-O", "--fq-offset"):
@@ -297,15 +343,34 @@ def build_ctx_args(k, args, capacity=1 << 20):
             spec = next(it)
             ctx, _, _ = g.load_ctx(spec, intocolour, must_exist=bool(isecs), mask_isec=bool(isecs))
             intocolour = max(intocolour, ctx.into_ncols - 1)
-        elif a in ("-1", "--seq", "-Q", "--fq-cutoff", "-O", "--fq-offset", "-H", "--cut-hp", "-I", "--intersect"):
+        elif a in ("-1", "--seq", "-2", "--seq2", "-i", "--seqi", "-Q", "--fq-cutoff", "-O", "--fq-offset", "-H", "--cut-hp",
+                   "-I", "--intersect", "-M", "--matepair"):
             next(it)
     for col, name in names:
         g.set_name(col, name)
-    for start in range(0, len(tasks), MAX_IO_THREADS):
+    # ctx_build.c:384-407: with --remove-pcr anywhere, one build_graph() call per run of <= 10 tasks of one
+    # colour and the read-start marks are wiped when the colour changes; the files of one call are read in
+    # command-line order here (the reference reads them concurrently)
+    remove_pcr_used = any(t["remove_pcr"] for _, t in tasks)
+    start, prev_col = 0, 0
+    while start < len(tasks):
+        col0 = tasks[start][0]
+        end = min(start + MAX_IO_THREADS, len(tasks))
+        if remove_pcr_used:
+            if col0 != prev_col:
+                g.wipe_readstrt()
+            end = start + 1
+            while end < len(tasks) and end - start < MAX_IO_THREADS and tasks[end][0] == col0:
+                end += 1
         st = Stats()
-        for col, t in tasks[start:start + MAX_IO_THREADS]:
-            g.load_file(t["path"], col, t["fq_cutoff"], t["fq_offset"], t["hp_cutoff"], st)
-        g.update_ginfo(tasks[start][0], st)
+        for col, t in tasks[start:end]:
+            if t["remove_pcr"]:
+                g.load_pcr(t["path"], t["path2"], t["interleaved"], col, t["fq_cutoff"], t["fq_offset"], t["hp_cutoff"],
+                           t["matedir"], st)
+            else:
+                g.load_file(t["path"], col, t["fq_cutoff"], t["fq_offset"], t["hp_cutoff"], st)
+        g.update_ginfo(col0, st)
+        start, prev_col = end, col0
     if isecs:   # ctx_build.c:409-413
         g.finish_intersect()
     out = g.dump_sorted()

@@ -20,6 +20,7 @@
 #include <vector>
 #include <array>
 #include "../../mccortex_b200/csrc/mcx_chunk.cuh"
+#include "../../mccortex_b200/csrc/mcx_pcr.cuh"
 
 struct Rec { uint32_t covg; uint8_t edges; };
 typedef std::map<std::array<uint64_t, 2>, Rec> Table;
@@ -109,8 +110,87 @@ static void run_launch(const uint8_t *seq, uint64_t nbytes, uint64_t r_begin, ui
   }
 }
 
+static std::vector<uint8_t> slurp(const char *path)
+{
+  std::vector<uint8_t> data; uint8_t buf[1 << 16]; size_t n;
+  FILE *f = fopen(path, "rb"); if(!f) { perror(path); exit(2); }
+  while((n = fread(buf, 1, sizeof(buf), f)) > 0) data.insert(data.end(), buf, buf + n);
+  fclose(f);
+  return data;
+}
+
+// --pcr <lines-file> <k> <hp> <qual-lines-file|-> <qcut> <mate-file> <batch_reads>
+// the three passes of mcx_pcr.cu (orient / mark / mask) batch by batch with the MCX_HD math of mcx_pcr.cuh,
+// a std::map standing in for the table's slot numbers, then the normal front end over the filtered lines
+static int main_pcr(int argc, char **argv)
+{
+  if(argc < 9) { fprintf(stderr, "usage: %s --pcr <lines> <k> <hp> <qual|-> <qcut> <mates> <batch_reads>\n", argv[0]); return 2; }
+  std::vector<uint8_t> data = slurp(argv[2]), qdata, mate = slurp(argv[7]);
+  uint32_t k = (uint32_t)atoi(argv[3]), hp = (uint32_t)atoi(argv[4]), qcut = (uint32_t)atoi(argv[6]);
+  if(strcmp(argv[5], "-") != 0) qdata = slurp(argv[5]);
+  uint64_t batch = strtoull(argv[8], NULL, 10);
+  uint8_t *qp = qdata.empty() ? nullptr : qdata.data();
+  std::vector<uint64_t> off(1, 0);
+  for(uint64_t i = 0; i < data.size(); i++) if(data[i] == '\n') off.push_back(i + 1);
+  uint64_t nreads = off.size() - 1;
+  if(mate.size() != nreads || (qp && qdata.size() != data.size())) { fprintf(stderr, "mate/qual files do not match the lines\n"); return 2; }
+  if(batch == 0) batch = nreads ? nreads : 1;
+  std::map<std::array<uint64_t, 3>, uint64_t> ids;   // (key words, orient) -> node number
+  std::vector<uint32_t> first;
+  std::vector<uint64_t> node(nreads);
+  uint64_t dup_se = 0, dup_pe = 0; uint32_t ord_base = 0;
+  for(uint64_t b0 = 0, n; b0 < nreads; b0 += n) {
+    n = nreads - b0 < batch ? nreads - b0 : batch;
+    if((mate[b0 + n - 1] & MCX_MATE_KIND) == MCX_MATE_FIRST) n++;   // a pair never straddles two batches
+    const uint64_t *boff = off.data() + b0; const uint8_t *bmate = mate.data() + b0; uint64_t *bnode = node.data() + b0;
+    for(uint64_t r = 0; r < n; r++) if(bmate[r] & MCX_MATE_REVCOMP)
+      for(uint32_t lane = 0; lane < 32; lane++)
+        mcx_pcr_revcomp_lanes(data.data() + boff[r], qp ? qp + boff[r] : nullptr, boff[r + 1] - boff[r] - 1, lane, 32);
+    for(uint64_t r = 0; r < n; r++) {
+      uint64_t lo = boff[r], len = boff[r + 1] - lo - 1;
+      uint64_t start = mcx_first_contig_start(data.data() + lo, qp ? qp + lo : nullptr, len, k, qp ? qcut : 0, hp);
+      bnode[r] = MCX_PCR_NONE;
+      if(start >= len) continue;
+      uint32_t orient; std::array<uint64_t, 3> id = {0, 0, 0};
+      if(k <= 31) { McxKmer<1> key = mcx_kmer_key<1>(mcx_kmer_from_ascii<1>(data.data() + lo + start, k), k, &orient); id[0] = key.b[0]; }
+      else { McxKmer<2> key = mcx_kmer_key<2>(mcx_kmer_from_ascii<2>(data.data() + lo + start, k), k, &orient); id[0] = key.b[0]; id[1] = key.b[1]; }
+      id[2] = orient;
+      auto it = ids.find(id);
+      if(it == ids.end()) { it = ids.emplace(id, (uint64_t)first.size()).first; first.push_back(MCX_PCR_UNSET); }
+      bnode[r] = it->second;
+      uint32_t ord = ord_base + (uint32_t)mcx_pcr_leader(r, bmate[r]);
+      if(ord < first[it->second]) first[it->second] = ord;
+    }
+    for(uint64_t r = 0; r < n; r++) {
+      if(!mcx_pcr_is_dup(r, bmate, bnode, first.data(), ord_base)) continue;
+      for(uint64_t i = boff[r]; i + 1 < boff[r + 1]; i++) data[i] = 'N';
+      uint32_t kind = bmate[r] & MCX_MATE_KIND;
+      if(kind == MCX_MATE_FIRST) dup_pe++; else if(kind == MCX_MATE_SINGLE) dup_se++;
+    }
+    ord_base += (uint32_t)n;
+  }
+  Table tab; Counters cnt;
+  uint64_t nbytes = data.size();
+  if(nbytes) {
+    if(k <= 31) run_launch<1>(data.data(), nbytes, 0, nbytes, k, hp, tab, cnt, qp, qcut);
+    else run_launch<2>(data.data(), nbytes, 0, nbytes, k, hp, tab, cnt, qp, qcut);
+  }
+  int W = k <= 31 ? 1 : 2;
+  for(auto &kv : tab) {
+    fwrite(&kv.first[0], 8, 1, stdout);
+    if(W == 2) fwrite(&kv.first[1], 8, 1, stdout);
+    fwrite(&kv.second.covg, 4, 1, stdout);
+    fwrite(&kv.second.edges, 1, 1, stdout);
+  }
+  fprintf(stderr, "kmers=%llu novel=%llu contigs=%llu reads=%llu dupse=%llu duppe=%llu\n", (unsigned long long)cnt.kmers,
+          (unsigned long long)cnt.novel, (unsigned long long)cnt.contigs, (unsigned long long)cnt.reads,
+          (unsigned long long)dup_se, (unsigned long long)dup_pe);
+  return 0;
+}
+
 int main(int argc, char **argv)
 {
+  if(argc > 1 && strcmp(argv[1], "--pcr") == 0) return main_pcr(argc, argv);
   if(argc < 5) { fprintf(stderr, "usage: %s <lines-file> <k> <hp> <r_piece>\n", argv[0]); return 2; }
   FILE *f = fopen(argv[1], "rb"); if(!f) { perror(argv[1]); return 2; }
   std::vector<uint8_t> data; uint8_t buf[1 << 16]; size_t n;

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import oracle as O  # noqa: E402
-from conftest import rand_reads, EDGE_READS  # noqa: E402
+from conftest import rand_reads, EDGE_READS, write_pcr_files  # noqa: E402
 
 
 def write_fa(path, reads, wrap=None):
@@ -86,10 +86,10 @@ def main():
     # given raw; "@/" stands for this directory.
     graph_cases = []
 
-    def add_graph(name, k, raw):
+    def add_graph(name, k, raw, threads=3):
         args = [a.replace("@/", HERE + "/") for a in raw]
         ctx = name + ".ctx"
-        data = O.ref_build(k, args, os.path.join(HERE, ctx), threads=3)
+        data = O.ref_build(k, args, os.path.join(HERE, ctx), threads=threads)
         graph_cases.append(dict(name=name, k=k, ctx=ctx, md5=hashlib.md5(data).hexdigest(), ref_args=raw))
         print(name, len(data), graph_cases[-1]["md5"])
 
@@ -109,6 +109,24 @@ def main():
     add_graph("isec_fq10_k15", 15, ["-I", "@/fq20_hp5_k15.ctx", "-s", "z", "-Q", "10", "-1", "@/q.fq"])
     add_graph("isec_fq25_hp4_k15", 15, ["-I", "@/fq20_hp5_k15.ctx", "-s", "z", "-Q", "25", "-H", "4", "-1", "@/q.fq", "-1", "@/a.fa"])
     add_graph("isec_k63", 63, ["-I", "@/reads_k63.ctx", "-s", "t", "-1", "@/b.fa", "-1", "@/a.fa"])
+
+    # build --remove-pcr: the reference with ONE worker thread and one input task per colour is
+    # deterministic (reads are tested in file order); that run is the golden.  se.fa / p1.fq + p2.fq / il.fq come
+    # from their own seed so the files above keep their bytes.
+    pdir = os.path.join(HERE, "pcr")
+    os.makedirs(pdir, exist_ok=True)
+    write_pcr_files(random.Random(31337), pdir, n=250)
+    add_graph("pcr_se_k21", 21, ["-p", "-s", "a", "-1", "@/pcr/se.fa"], threads=1)
+    add_graph("pcr_se_rr_k31", 31, ["-p", "-M", "RR", "-s", "a", "-1", "@/pcr/se.fa"], threads=1)
+    add_graph("pcr_pe_k21", 21, ["-p", "-s", "a", "-2", "@/pcr/p1.fq:@/pcr/p2.fq"], threads=1)
+    add_graph("pcr_pe_fq10_hp4_k21", 21, ["-p", "-Q", "10", "-H", "4", "-s", "a", "-2", "@/pcr/p1.fq:@/pcr/p2.fq"], threads=1)
+    add_graph("pcr_pe_ff_k33", 33, ["-p", "-M", "FF", "-s", "a", "-2", "@/pcr/p1.fq:@/pcr/p2.fq"], threads=1)
+    add_graph("pcr_pe_rf_fq12_k21", 21, ["-p", "-M", "RF", "-Q", "12", "-s", "a", "-2", "@/pcr/p1.fq:@/pcr/p2.fq"], threads=1)
+    add_graph("pcr_il_k21", 21, ["-p", "-s", "a", "-i", "@/pcr/il.fq"], threads=1)
+    add_graph("pcr_il_fq10_rr_k63", 63, ["-p", "-Q", "10", "-M", "RR", "-s", "a", "-i", "@/pcr/il.fq"], threads=1)
+    add_graph("pcr_three_colours_k21", 21, ["-p", "-s", "a", "-1", "@/pcr/se.fa", "-P", "-s", "b", "-2", "@/pcr/p1.fq:@/pcr/p2.fq",
+                                            "-p", "-s", "c", "-i", "@/pcr/il.fq"], threads=1)
+    add_graph("pcr_same_file_two_colours_k21", 21, ["-p", "-s", "a", "-1", "@/pcr/se.fa", "-s", "b", "-1", "@/pcr/se.fa"], threads=1)
 
     with open(os.path.join(HERE, "cases.json"), "w") as f:
         json.dump(cases, f, indent=1)

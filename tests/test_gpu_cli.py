@@ -23,8 +23,9 @@ def _driver():
     return M.driver_path()
 
 
-def _run(args, cwd=None, check=True):
-    r = subprocess.run([_driver(), "build"] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+def _run(args, cwd=None, check=True, env=None):
+    r = subprocess.run([_driver(), "build"] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       env=dict(os.environ, **env) if env else None)
     if check:
         assert r.returncode == 0, r.stderr.decode()[-3000:]
     return r
@@ -59,6 +60,33 @@ def test_cli_graph_loading_matches_golden_ctx(case, tmp_path):
     ref = open(os.path.join(GOLD, c["ctx"]), "rb").read()
     assert hashlib.md5(ref).hexdigest() == c["md5"]
     assert got == ref
+
+
+@pytest.mark.parametrize("case", [c["name"] for c in GRAPH_CASES if c["name"].startswith("pcr_")])
+def test_cli_remove_pcr_small_batches(case, tmp_path):
+    """build --remove-pcr with the host cutting the input into many tiny batches: the read-start
+    marks carry over from batch to batch, pairs stay whole, a read waiting for its mate moves to the next batch"""
+    c = next(x for x in GRAPH_CASES if x["name"] == case)
+    out = str(tmp_path / "out.ctx")
+    args = ["-q", "-f", "-m", "1G", "-n", "1M", "-k", str(c["k"]), "-S"]
+    args += [a.replace("@/", GOLD + "/") for a in c["ref_args"]] + [out]
+    _run(args, env={"MCX_BATCH_BYTES": "3000"})
+    assert open(out, "rb").read() == open(os.path.join(GOLD, c["ctx"]), "rb").read()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "mccortex31")), reason="oracle/_ref not built")
+def test_cli_remove_pcr_matches_reference_binary(tmp_path, oracle):
+    """fresh seeded inputs, the compiled reference run with one worker thread (its deterministic mode)"""
+    from conftest import write_pcr_files
+    write_pcr_files(random.Random(2024), str(tmp_path), n=600, k=27)
+    d = str(tmp_path)
+    # (one input task per colour: with two tasks in a colour the reference interleaves their reads as they arrive)
+    for k, args in ((27, ["-p", "-s", "a", "-2", d + "/p1.fq:" + d + "/p2.fq", "-s", "b", "-1", d + "/se.fa"]),
+                    (41, ["-p", "-H", "6", "-M", "RF", "-s", "a", "-i", d + "/il.fq", "-s", "b", "-Q", "15", "-2", d + "/p1.fq:" + d + "/p2.fq"])):
+        ref = oracle.ref_build(k, args, str(tmp_path / "ref.ctx"), threads=1)
+        out = str(tmp_path / "out.ctx")
+        _run(["-q", "-f", "-m", "1G", "-n", "1M", "-k", str(k), "-S"] + args + [out])
+        assert open(out, "rb").read() == ref, args
 
 
 def test_cli_many_tasks_header_quirks(tmp_path, oracle):

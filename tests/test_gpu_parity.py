@@ -513,3 +513,57 @@ def test_warp_specialised_kernel_matches_oracle(M, oracle, reads_small, variant,
         assert got == recs
         _check_stats(st, ost, len(reads))
         g.close()
+
+
+# ---- build --remove-pcr (row N3) -------------------------------------------------------------
+@pytest.mark.parametrize("k,hp,cut,matedir,nbatch", [(21, 0, 0, 1, 1), (31, 0, 0, 3, 4), (21, 4, 45, 1, 3), (33, 0, 50, 2, 2),
+                                                   (63, 5, 0, 0, 5), (11, 0, 40, 1, 7)])
+def test_remove_pcr_matches_oracle(M, oracle, k, hp, cut, matedir, nbatch):
+    """mcx_graph_add_reads_pcr (orient / mark / mask kernels + the normal build) against seq_reads_are_novel restated
+    read by read in the oracle (itself byte-identical to the reference run with one thread)"""
+    from conftest import pcr_reads
+    rng = random.Random(1000 * k + cut + matedir)
+    units = pcr_reads(rng, 3000, k, G=20000, sites=300)
+    quals = [tuple("".join(chr(cut) if rng.random() < 0.03 else chr(rng.randint(max(cut - 3, 35), 74)) for _ in r) if cut else ""
+                   for r in u) for u in units]
+    og = oracle.Graph(k, 1, 1 << 20)
+    ost = oracle.Stats()
+    for u, q in zip(units, quals):
+        og.add_reads_pcr(u[0], q[0] or None, u[1] if len(u) > 1 else None, (q[1] or None) if len(u) > 1 else None,
+                         fq_cutoff=cut, hp_cutoff=hp, matedir=matedir, stats=ost)
+    recs = og.dump_sorted()[len(og.header()):]
+    g = M.Graph(k, 1, 1 << 20, flags=M.MCX_GRAPH_READSTRT)
+    step = (len(units) + nbatch - 1) // nbatch
+    for i in range(0, len(units), step):
+        g.add_units_pcr(units[i:i + step], quals[i:i + step], fq_cutoff=cut, hp_cutoff=hp, matedir=matedir)
+    st = g.sync()
+    got, n, _ = g.export_records()
+    assert got == recs
+    assert (st.num_dup_se_reads, st.num_dup_pe_pairs) == (ost.num_dup_se_reads, ost.num_dup_pe_pairs)
+    assert ost.num_dup_se_reads + ost.num_dup_pe_pairs > 300
+    assert st.num_kmers_loaded == ost.num_kmers_loaded and st.contigs_parsed == ost.contigs_parsed
+    # (the reference's num_kmers_novel also counts one per mate WITHOUT a k-mer, build_graph.c:75-76 -- a log-only
+    # statistic; the library reports the slots claimed)
+    assert st.num_kmers_novel == n
+    assert st.total_bases_read == ost.total_bases_read and st.total_bases_loaded == ost.total_bases_loaded
+    g.close()
+
+
+def test_remove_pcr_reset_between_colours(M, oracle):
+    """the read-start marks are wiped when the colour changes (ctx_build.c:392-395)"""
+    from conftest import pcr_reads
+    rng = random.Random(77)
+    units = pcr_reads(rng, 1500, 31, paired=0.3)
+    og = oracle.Graph(31, 2, 1 << 20)
+    g = M.Graph(31, 2, 1 << 20, flags=M.MCX_GRAPH_READSTRT)
+    for col in (0, 1):
+        if col:
+            og.wipe_readstrt()
+            g.pcr_reset()
+        for u in units:
+            og.add_reads_pcr(u[0], None, u[1] if len(u) > 1 else None, None, colour=col)
+        g.add_units_pcr(units, colour=col)
+    g.sync()
+    got, _, _ = g.export_records()
+    assert got == og.dump_sorted()[len(og.header()):]
+    g.close()

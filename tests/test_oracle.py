@@ -194,3 +194,76 @@ def test_device_math_quality_cutoff(oracle, emul, tmp_path, k, hp, cut, eqp):
     got, cnt = _emul_q(emul, tmp_path, reads, quals, k, cut, hp)
     assert got == recs
     assert cnt["kmers"] == st.num_kmers_loaded and cnt["contigs"] == st.contigs_parsed
+
+
+# ---- build --remove-pcr (row N3) -------------------------------------------------------------
+def _pcr_lines(units, quals, matedir):
+    """LINES + parallel quality bytes + mate bytes as the host driver hands them to mcx_graph_add_reads_pcr"""
+    lines, qlines, mates = [], [], bytearray()
+    for u, q in zip(units, quals):
+        for m, (r, qs) in enumerate(zip(u, q)):
+            lines.append(r)
+            qb = qs[:len(r)]
+            qlines.append(qb + "\x7f" * (len(r) - len(qb)))
+            kind = 0 if len(u) == 1 else 1 + m
+            flip = (matedir & 2) if m == 0 else (matedir & 1)
+            mates.append(kind | (4 if flip else 0))
+    return lines, qlines, bytes(mates)
+
+
+@pytest.mark.parametrize("k,hp,cut,matedir,batch", [(21, 0, 0, 1, 0), (31, 0, 0, 3, 37), (21, 4, 45, 1, 0), (33, 0, 50, 2, 64),
+                                                  (63, 5, 0, 0, 101), (11, 0, 40, 1, 2)])
+def test_device_math_remove_pcr(oracle, emul, tmp_path, k, hp, cut, matedir, batch):
+    """orient / mark (atomicMin of read ordinals) / mask as in mcx_pcr.cu against the read-by-read bit test
+    of seq_reads_are_novel restated in the oracle"""
+    from conftest import pcr_reads
+    rng = random.Random(1000 * k + cut + matedir)
+    units = pcr_reads(rng, 500, k)
+    quals = [tuple("".join(chr(cut) if rng.random() < 0.03 else chr(rng.randint(max(cut - 3, 35), 74)) for _ in r) if cut else ""
+                   for r in u) for u in units]
+    g = oracle.Graph(k, 1, 1 << 20)
+    st = oracle.Stats()
+    for u, q in zip(units, quals):
+        g.add_reads_pcr(u[0], q[0] or None, u[1] if len(u) > 1 else None, (q[1] or None) if len(u) > 1 else None,
+                        fq_cutoff=cut, hp_cutoff=hp, matedir=matedir, stats=st)
+    recs = g.dump_sorted()[len(g.header()):]
+    lines, qlines, mates = _pcr_lines(units, quals, matedir)
+    (tmp_path / "l.txt").write_text("".join(r + "\n" for r in lines))
+    (tmp_path / "q.txt").write_bytes("".join(q + "!" for q in qlines).encode("latin1"))
+    (tmp_path / "m.bin").write_bytes(mates)
+    r = subprocess.run([emul, "--pcr", str(tmp_path / "l.txt"), str(k), str(hp), str(tmp_path / "q.txt") if cut else "-",
+                        str(cut), str(tmp_path / "m.bin"), str(batch)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    cnt = {a: int(b) for a, b in (x.split("=") for x in r.stderr.decode().split())}
+    assert r.stdout == recs
+    assert cnt["dupse"] == st.num_dup_se_reads and cnt["duppe"] == st.num_dup_pe_pairs
+    assert st.num_dup_se_reads + st.num_dup_pe_pairs > 50
+    assert cnt["kmers"] == st.num_kmers_loaded and cnt["contigs"] == st.contigs_parsed
+
+
+@pytest.mark.parametrize("mode,k,cut,hp,matedir,batch_bytes", [("se", 21, 0, 0, 1, 0), ("se", 31, 0, 0, 3, 3000), ("pe", 21, 10, 4, 1, 0),
+                                                            ("pe", 33, 0, 0, 2, 5000), ("il", 21, 0, 0, 1, 2000), ("il", 21, 12, 0, 3, 0)])
+def test_host_ingest_remove_pcr(oracle, emul, ingest_dump, tmp_path, mode, k, cut, hp, matedir, batch_bytes):
+    """host driver's pairing (file pairs, interleaved names), mate bytes and batch cuts + the device math
+    == the oracle's restatement of seq_parse_*_sf + build_graph_from_reads_mt with --remove-pcr"""
+    from conftest import write_pcr_files
+    write_pcr_files(random.Random(k + cut), str(tmp_path))
+    f1 = str(tmp_path / {"se": "se.fa", "pe": "p1.fq", "il": "il.fq"}[mode])
+    f2 = str(tmp_path / "p2.fq") if mode == "pe" else None
+    g = oracle.Graph(k, 1, 1 << 20)
+    st = g.load_pcr(f1, f2, mode == "il", fq_cutoff=cut, hp_cutoff=hp, matedir=matedir)
+    recs = g.dump_sorted()[len(g.header()):]
+    env = dict(os.environ)
+    if batch_bytes:
+        env["MCX_BATCH_BYTES"] = str(batch_bytes)
+    pre = str(tmp_path / "d")
+    out = subprocess.run([ingest_dump, pre, mode, str(cut), "0", str(hp), str(matedir), f1] + ([f2] if f2 else []),
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True, env=env).stdout.decode()
+    info = dict(x.split("=") for x in out.split())
+    assert int(info["nbatches"]) > (3 if batch_bytes else 0)
+    assert (int(info["se"]), int(info["pe"])) == (st.num_se_reads, st.num_pe_reads)
+    r = subprocess.run([emul, "--pcr", pre + ".lines", str(k), str(hp), pre + ".qual" if cut else "-", info["fq_cutoff"],
+                        pre + ".mate", "0"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    cnt = {a: int(b) for a, b in (x.split("=") for x in r.stderr.decode().split())}
+    assert r.stdout == recs
+    assert (cnt["dupse"], cnt["duppe"]) == (st.num_dup_se_reads, st.num_dup_pe_pairs)
+    assert st.num_dup_se_reads + st.num_dup_pe_pairs > 20
