@@ -115,6 +115,10 @@ int mcx_graph_set_stream(mcx_graph *g, void *cuda_stream);
  * queued (host buffers may be reused after return unless they are pinned, in which
  * case they must stay valid until mcx_graph_sync). */
 int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *batch);
+/* optional: allocate now the staging ring that host batches go through (3 x 32 MB of pinned host memory and as much
+ * device memory; otherwise the first mcx_graph_add_reads with MCX_MEM_HOST does it).  The reference has no
+ * counterpart: its workers read the hosts's read_t buffers in place (src/basic/async_read_io.c:118-141). */
+int mcx_graph_prepare_host(mcx_graph *g);
 /* replaces build_graph_from_str_mt(&g, colour, seq, len, false) (src/tools/build_graph.h:77-79):
  * one contig-to-be, synchronous. */
 int mcx_graph_add_str(mcx_graph *g, uint32_t colour, const char *seq, size_t len);

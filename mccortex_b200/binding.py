@@ -85,6 +85,7 @@ def lib():
     L.mcx_graph_add_reads_pcr.argtypes = [vp, C.POINTER(ReadBatch), vp, vp, C.c_uint64]
     L.mcx_graph_pcr_reset.argtypes = [vp]
     L.mcx_graph_add_str.argtypes = [vp, u32, C.c_char_p, C.c_size_t]
+    L.mcx_graph_prepare_host.argtypes = [vp]
     L.mcx_graph_sync.argtypes = [vp, C.POINTER(LoadStats)]
     L.mcx_graph_flush.argtypes = [vp]
     L.mcx_graph_finish_intersect.argtypes = [vp, C.POINTER(u64)]
@@ -271,6 +272,10 @@ class Graph:
 
     def pcr_reset(self):
         _ck(lib().mcx_graph_pcr_reset(self.h), "mcx_graph_pcr_reset")
+
+    def prepare_host(self):
+        """allocate the pinned staging ring for host batches now (otherwise the first host batch does it)"""
+        _ck(lib().mcx_graph_prepare_host(self.h), "mcx_graph_prepare_host")
 
     def add_str(self, seq, colour=0):
         if isinstance(seq, str):

@@ -53,6 +53,13 @@ struct mcx_graph {
   uint32_t pcr_ord;        // ordinal of the next read of this colour
   uint8_t *d_pcr; size_t d_pcr_bytes; // --remove-pcr: device copy of the batch being filtered
   bool sharded;  // front table holds records of keys owned by other shards: only mcx_graph_flush_sharded may empty it
+  // MCX_SPILL=1 (k <= 31, front table on): the fused kernel's parked pass appends big-table work to a tuple bin
+  // and kernel C inserts it right after the launch (mcx_spill_push, mcx_build.cu).  One bin per staging slot
+  // plus one (index MCX_NSTAGE) for launches on the primary stream.
+  bool spill_on;
+  uint64_t spill_span;                  // positions per launch on the primary stream when spilling
+  uint64_t spill_cap[MCX_NSTAGE + 1];   // tuples
+  uint64_t *spill_keys[MCX_NSTAGE + 1]; uint32_t *spill_meta[MCX_NSTAGE + 1]; unsigned long long *spill_cursor[MCX_NSTAGE + 1];
 };
 
 extern "C" int mcx_device_count(void)
@@ -90,13 +97,30 @@ static void apply_persist(mcx_graph *g, cudaStream_t st)
   cudaGetLastError();
 }
 
+// MCX_TIMING=1: wall clock of the steps of mcx_graph_create on stderr
+#include <time.h>
+static void abi_phase(const char *what)
+{
+  static int on = -1; static struct timespec last;
+  struct timespec now;
+  if(on < 0) { on = getenv("MCX_TIMING") != NULL; clock_gettime(CLOCK_MONOTONIC, &last); }
+  if(!on) return;
+  clock_gettime(CLOCK_MONOTONIC, &now);
+  fprintf(stderr, "[phase]     %-24s +%.3f s\n", what, (double)(now.tv_sec - last.tv_sec) + 1e-9 * (double)(now.tv_nsec - last.tv_nsec));
+  last = now;
+}
+
 extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, int device, uint32_t flags, mcx_graph **out)
 {
   if(!out || k < 3 || k > 63 || !(k & 1u) || ncols == 0 || ncols > 4096 || capacity == 0) return MCX_ERR_BAD_ARG;
+  abi_phase("create: enter");
   int ndev = mcx_device_count();
+  abi_phase("create: device count");
   if(ndev == 0) { snprintf(g_err, sizeof(g_err), "no CUDA device: libmcxgpu has no CPU fallback"); return MCX_ERR_NO_DEVICE; }
   if(device < 0 || device >= ndev) return MCX_ERR_BAD_ARG;
   CU(cudaSetDevice(device));
+  CU(cudaFree(0));
+  abi_phase("create: context");
   mcx_graph *g = (mcx_graph *)calloc(1, sizeof(*g));
   if(!g) return MCX_ERR_NOMEM;
   g->device = device; g->k = k; g->W = (k + 31u) / 32u; g->ncols = ncols;
@@ -107,6 +131,7 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
   size_t bytes = (size_t)g->table.nslots * g->table.stride * 4u;
   cudaError_t e = cudaMalloc(&g->table.slots, bytes);
   if(e != cudaSuccess) { free(g); return fail_cuda(e, "cudaMalloc(table)"); }
+  abi_phase("create: table malloc");
   e = cudaMalloc(&g->d_counters, MCX_NCOUNTERS_ALL * sizeof(unsigned long long));
   if(e != cudaSuccess) { cudaFree(g->table.slots); free(g); return fail_cuda(e, "cudaMalloc(counters)"); }
   cudaStreamCreateWithFlags(&g->own_primary, cudaStreamNonBlocking);
@@ -119,6 +144,7 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
   cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS_ALL * sizeof(unsigned long long), g->own_primary);
   e = cudaStreamSynchronize(g->own_primary);
   if(e != cudaSuccess) { int r = fail_cuda(e, "memset(table)"); mcx_graph_destroy(g); return r; }
+  abi_phase("create: streams + memset");
   // front table (k <= 31; it counts one colour at a time and is flushed when the colour changes): sized to sit in L2 (64 MB = 2^21 sets of four 8-byte
   // slots); MCX_FRONT_BITS=0 disables it, other values are for experiments
   if(flags & MCX_GRAPH_INTERSECT) {
@@ -151,6 +177,9 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
   if(const char *m = getenv("MCX_G")) mcx_set_inflight(atoi(m));
   if(const char *m = getenv("MCX_WS")) g->ws_variant = atoi(m);
   if(const char *m = getenv("MCX_L2_HINTS")) mcx_set_hints((uint32_t)atoi(m));
+  g->spill_span = 1ull << 30;
+  if(const char *m = getenv("MCX_SPILL")) g->spill_on = atoi(m) != 0 && g->table.front_set_bits != 0;
+  if(const char *m = getenv("MCX_SPILL_SPAN_MB")) { long v = atol(m); if(v >= 1 && v <= 3584) g->spill_span = (uint64_t)v << 20; }
   if(const char *m = getenv("MCX_L2_PERSIST_MB")) {
     // experiment: pin the front table with the L2 persistence controls
     size_t want = (size_t)atoi(m) << 20;
@@ -160,6 +189,7 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
   if(const char *m = getenv("MCX_L2FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(m));
   apply_persist(g, g->own_primary);
   for(int i = 0; i < MCX_NSTAGE; i++) apply_persist(g, g->streams[i]);
+  abi_phase("create: front table");
   *out = g;
   return MCX_OK;
 }
@@ -182,6 +212,11 @@ extern "C" int mcx_graph_destroy(mcx_graph *g)
   if(g->d_isec) cudaFree(g->d_isec);
   if(g->d_first) cudaFree(g->d_first);
   if(g->d_pcr) cudaFree(g->d_pcr);
+  for(int i = 0; i <= MCX_NSTAGE; i++) {
+    if(g->spill_keys[i]) cudaFree(g->spill_keys[i]);
+    if(g->spill_meta[i]) cudaFree(g->spill_meta[i]);
+    if(g->spill_cursor[i]) cudaFree(g->spill_cursor[i]);
+  }
   if(g->table.front) cudaFree(g->table.front);
   if(g->d_counters) cudaFree(g->d_counters);
   if(g->table.slots) cudaFree(g->table.slots);
@@ -227,12 +262,21 @@ extern "C" int mcx_graph_set_stream(mcx_graph *g, void *cuda_stream)
 static int ensure_stage(mcx_graph *g)
 {
   if(g->stage_ready) return MCX_OK;
+  abi_phase("stage: enter");
   for(int i = 0; i < MCX_NSTAGE; i++) {
     CU(cudaMalloc(&g->d_stage[i], MCX_STAGE_BYTES));
     CU(cudaHostAlloc(&g->h_stage[i], MCX_STAGE_BYTES, cudaHostAllocDefault));
   }
+  abi_phase("stage: 3 x 32 MB pinned");
   g->stage_ready = true;
   return MCX_OK;
+}
+
+extern "C" int mcx_graph_prepare_host(mcx_graph *g)
+{
+  if(!g) return MCX_ERR_BAD_ARG;
+  CU(cudaSetDevice(g->device));
+  return ensure_stage(g);
 }
 
 static McxBuildParams make_params(mcx_graph *g, const mcx_read_batch *b, const uint8_t *dseq, uint64_t nbytes,
@@ -277,11 +321,40 @@ static int front_guard(mcx_graph *g, uint64_t positions)
   return MCX_OK;
 }
 
+// spill bin `slot` (a staging slot, or MCX_NSTAGE for the primary stream), allocated on first use: room for
+// one tuple per 8 positions of the largest launch it serves (the bench workload parks 3.5 % of its
+// occurrences; what does not fit is inserted inline by the kernel), MCX_SPILL_CAP=<tuples> overrides
+static cudaError_t ensure_spill(mcx_graph *g, int slot)
+{
+  if(g->spill_keys[slot]) return cudaSuccess;
+  uint64_t cap = (slot == MCX_NSTAGE ? g->spill_span : MCX_STAGE_POS) / 8u;
+  if(const char *m = getenv("MCX_SPILL_CAP")) { long long v = atoll(m); if(v >= 1 && v <= (4096ll << 20)) cap = (uint64_t)v; }
+  cudaError_t e;
+  if((e = cudaMalloc(&g->spill_keys[slot], cap * g->W * sizeof(uint64_t))) != cudaSuccess) return e;
+  if((e = cudaMalloc(&g->spill_meta[slot], cap * sizeof(uint32_t))) != cudaSuccess) return e;
+  if((e = cudaMalloc(&g->spill_cursor[slot], sizeof(unsigned long long))) != cudaSuccess) return e;
+  if((e = cudaMemset(g->spill_cursor[slot], 0, sizeof(unsigned long long))) != cudaSuccess) return e;
+  g->spill_cap[slot] = cap;
+  return cudaSuccess;
+}
+
 // one launch over [r_begin, r_end) of a LINES buffer: the fused insert kernel, or (must_exist) the lookup kernel
-static cudaError_t launch_build(mcx_graph *g, const mcx_read_batch *b, const McxBuildParams &p, cudaStream_t st)
+static cudaError_t launch_build(mcx_graph *g, const mcx_read_batch *b, const McxBuildParams &p, cudaStream_t st, int slot = MCX_NSTAGE)
 {
   if(b->must_exist) return mcx_launch_build_lookup(p, g->table, st);
   if(g->ws_variant && g->k <= 31 && g->table.front_set_bits) { mcx_set_ws_variant(g->ws_variant); return mcx_launch_build_ws(p, g->table, st); }
+  if(g->spill_on && g->W == 1u && g->table.front_set_bits) {
+    cudaError_t e = ensure_spill(g, slot);
+    if(e != cudaSuccess) return e;
+    McxTupleBins bins; memset(&bins, 0, sizeof(bins));
+    bins.keys[0] = g->spill_keys[slot]; bins.meta[0] = g->spill_meta[slot]; bins.cursor = g->spill_cursor[slot];
+    bins.cap = g->spill_cap[slot]; bins.nparts = 1; bins.my_part = 0; bins.spill = 1;
+    if((e = mcx_launch_build_spill(p, g->table, bins, st)) != cudaSuccess) return e;
+    // kernel C reads the tuple count from the cursor (at most cap tuples were stored); then the bin is empty again
+    if((e = mcx_launch_insert_tuples(bins.keys[0], bins.meta[0], bins.cap, (const uint64_t *)bins.cursor, g->k, g->table, p.colour,
+                                     p.may_saturate, g->d_counters, st)) != cudaSuccess) return e;
+    return cudaMemsetAsync(bins.cursor, 0, sizeof(unsigned long long), st);
+  }
   return mcx_launch_build_fused(p, g->table, st);
 }
 
@@ -292,8 +365,9 @@ static int add_lines_device(mcx_graph *g, const mcx_read_batch *b, const uint8_t
   g->occ_bound += nbytes;
   // one launch per span of <= MCX_FRONT_SPAN positions (the whole buffer stays visible to every
   // launch, so windows and edges across a cut see their neighbours)
-  for(uint64_t lo = 0; lo < nbytes; lo += MCX_FRONT_SPAN) {
-    const uint64_t hi = lo + MCX_FRONT_SPAN < nbytes ? lo + MCX_FRONT_SPAN : nbytes;
+  const uint64_t span = (g->spill_on && !b->must_exist) ? g->spill_span : MCX_FRONT_SPAN;
+  for(uint64_t lo = 0; lo < nbytes; lo += span) {
+    const uint64_t hi = lo + span < nbytes ? lo + span : nbytes;
     int r = front_guard(g, hi - lo); if(r) return r;
     McxBuildParams p = make_params(g, b, dseq, nbytes, lo, hi);
     CU(launch_build(g, b, p, primary(g)));
@@ -329,7 +403,7 @@ static int add_lines_host(mcx_graph *g, const mcx_read_batch *b, const uint8_t *
     if(!pinned) { memcpy(g->h_stage[s], src, b1 - b0); src = g->h_stage[s]; }
     CU(cudaMemcpyAsync(g->d_stage[s], src, b1 - b0, cudaMemcpyHostToDevice, st));
     McxBuildParams p = make_params(g, b, g->d_stage[s], b1 - b0, pos - b0, pend - b0);
-    CU(launch_build(g, b, p, st));
+    CU(launch_build(g, b, p, st, s));
     CU(cudaEventRecord(g->events[s], st));
   }
   for(int s = 0; s < MCX_NSTAGE; s++) if(used[s]) CU(cudaStreamWaitEvent(primary(g), g->events[s], 0));
@@ -624,7 +698,7 @@ static int fill_bins(McxTupleBins *bins, uint32_t W, uint32_t nparts, uint32_t m
     bins->meta[d] = meta_dst ? meta_dst[d] : meta_out + (uint64_t)d * cap;
     if(d != my_part && (!bins->keys[d] || !bins->meta[d])) return MCX_ERR_BAD_ARG;
   }
-  bins->cursor = (unsigned long long *)counts_out; bins->cap = cap; bins->nparts = nparts; bins->my_part = my_part;
+  bins->cursor = (unsigned long long *)counts_out; bins->cap = cap; bins->nparts = nparts; bins->my_part = my_part; bins->spill = 0;
   return MCX_OK;
 }
 

@@ -168,8 +168,31 @@ static __host__ __device__ __forceinline__ McxTupleBins mcx_no_bins()
 {
   McxTupleBins b;
   for(int i = 0; i < MCX_MAX_PARTS; i++) { b.keys[i] = nullptr; b.meta[i] = nullptr; }
-  b.cursor = nullptr; b.cap = 0; b.nparts = 1; b.my_part = 0;
+  b.cursor = nullptr; b.cap = 0; b.nparts = 1; b.my_part = 0; b.spill = 0;
   return b;
+}
+
+// Single-GPU spill.  A parked occurrence the front table cannot absorb (an error k-mer, mostly: seen once or
+// twice) needs Lookup3 + a random DRAM sector of the big table + CAS + RED: three dependent round trips, one
+// item per thread, while the CTA's hot pass waits (ablation, profiles/r1g_experiments.txt: ~45 % of the fused
+// kernel's time for 3.5 % of the occurrences).  With a spill bin the occurrence leaves as a (key, meta) tuple --
+// one coalesced 12-byte store -- and kernel C inserts the bin right after the launch with every thread of the
+// chip holding one probe in flight.  Returns false when the bin is full: the caller then inserts inline, so a
+// bin of any size is correct.
+template <int W>
+__device__ __forceinline__ bool mcx_spill_push(const McxTupleBins &b, const McxKmer<W> &key, uint32_t meta)
+{
+  const uint32_t act = __activemask(), lane = threadIdx.x & 31u, leader = __ffs(act) - 1u;
+  unsigned long long base = 0;
+  if(lane == leader) base = atomicAdd(&b.cursor[0], (unsigned long long)__popc(act));
+  base = __shfl_sync(act, base, leader);
+  const uint64_t at = base + __popc(act & ((1u << lane) - 1u));
+  if(at >= b.cap) return false;
+  uint64_t *kd = b.keys[0] + at * W;
+#pragma unroll
+  for(int w = 0; w < W; w++) kd[w] = key.b[w];
+  b.meta[0][at] = meta;
+  return true;
 }
 
 template <int W, int G> struct FusedSink { // G = probe loads kept in flight per thread
@@ -244,6 +267,7 @@ template <int W, int G> struct FusedSink { // G = probe loads kept in flight per
     if(W == 1 && t.front_set_bits) {
       if(mcx_front_add_slow(t, key.b[0], emask)) return; // absorbed by the front table
     }
+    if(bins.spill && mcx_spill_push<W>(bins, key, (1u << 8) | emask)) return; // kernel C inserts it after the launch
     uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
     if(bins.nparts > 1u) {
       const uint32_t d = mcx_owner(hc, bins.nparts);
@@ -731,6 +755,12 @@ cudaError_t mcx_launch_build_sharded(const McxBuildParams &p, const McxTable &t,
   if(p.k <= 31) mcx_build_sharded_kernel<1><<<grid, MCX_THREADS, queue_smem<1>(mcx_build_sharded_kernel<1>), st>>>(p, t, b);
   else mcx_build_sharded_kernel<2><<<grid, MCX_THREADS, queue_smem<2>(mcx_build_sharded_kernel<2>), st>>>(p, t, b);
   return cudaGetLastError();
+}
+
+cudaError_t mcx_launch_build_spill(const McxBuildParams &p, const McxTable &t, const McxTupleBins &b, cudaStream_t st)
+{
+  // the sharded kernel with one shard: nothing is owned elsewhere, b.spill routes the big-table work into bin 0
+  return mcx_launch_build_sharded(p, t, b, st);
 }
 
 // ---------------------------------------------------------------- tuning knobs (experiments)

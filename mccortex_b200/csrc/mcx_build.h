@@ -48,6 +48,9 @@ struct McxTupleBins {
   uint64_t cap;                  // tuples per destination
   uint32_t nparts;
   uint32_t my_part;              // sharded kernels: tuples owned by my_part are inserted locally instead
+  uint32_t spill;                // single-GPU spill (nparts 1): parked occurrences the front table cannot absorb are
+                                 // appended to bin 0 while it has room (cursor[0] keeps counting beyond cap: the
+                                 // excess was inserted inline) and inserted by kernel C right after the launch
 };
 
 cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
@@ -59,6 +62,8 @@ cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint32_t *meta,
                                      cudaStream_t st);
 // sharded build: fused local front table, big-table inserts for owned keys, tuples for the rest
 cudaError_t mcx_launch_build_sharded(const McxBuildParams &p, const McxTable &t, const McxTupleBins &b, cudaStream_t st);
+// fused build whose parked pass spills big-table work into b (b.spill = 1, nparts = 1) instead of doing it inline
+cudaError_t mcx_launch_build_spill(const McxBuildParams &p, const McxTable &t, const McxTupleBins &b, cudaStream_t st);
 cudaError_t mcx_launch_front_flush_sharded(const McxTable &t, const McxTupleBins &b, int may_saturate,
                                            unsigned long long *counters, cudaStream_t st);
 cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uint64_t nreads, uint8_t *dst, cudaStream_t st);

@@ -14,6 +14,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <getopt.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <strings.h>
@@ -309,9 +310,46 @@ static void print_task_stats(const BuildTask *t)
   mcx_status("  num contigs: %s  num kmers: %s novel kmers: %s", a, b, c);
 }
 
+/* the device graph, created on its own thread (see ctx_build) */
+static struct {
+  pthread_t thread; bool joined;
+  uint32_t k, ncols, flags; uint64_t capacity; int device; bool host_batches;
+  mcx_graph *g; int rc; const char *what;
+  volatile int done;
+} ginit;
+
+static void *graph_init_main(void *arg)
+{
+  (void)arg;
+  if(mcx_device_count() == 0) { ginit.rc = MCX_ERR_NO_DEVICE; ginit.what = "device"; }
+  else {
+    ginit.rc = mcx_graph_create(ginit.k, ginit.ncols, ginit.capacity, ginit.device, ginit.flags, &ginit.g);
+    ginit.what = "mcx_graph_create";
+    if(!ginit.rc && ginit.host_batches) { ginit.rc = mcx_graph_prepare_host(ginit.g); ginit.what = "mcx_graph_prepare_host"; }
+  }
+  __sync_synchronize();
+  ginit.done = 1;
+  return NULL;
+}
+static bool graph_ready(void *ctx) { (void)ctx; return ginit.done != 0; }
+static mcx_graph *graph_wait(void *ctx)
+{
+  (void)ctx;
+  if(!ginit.joined) {
+    pthread_join(ginit.thread, NULL); ginit.joined = true;
+    if(ginit.rc == MCX_ERR_NO_DEVICE && !ginit.g && !strcmp(ginit.what, "device")) mcx_die("No CUDA device: "CMD" has no CPU fallback");
+    if(ginit.rc) die_mcx(ginit.rc, ginit.what);
+    char a[64]; mcx_ulong_to_str(ginit.capacity, a);
+    mcx_status("[hasht] Allocating device table with %s entries on GPU %i", a, ginit.device);
+    mcx_phase("cuda init + table (joined)");
+  }
+  return ginit.g;
+}
+
 static int ctx_build(int argc, char **argv)
 {
   size_t i, s, t;
+  mcx_phase("start");
   parse_args(argc, argv);
 
   size_t max_kmers = 0;
@@ -364,12 +402,16 @@ static int ctx_build(int argc, char **argv)
   create_output(out_path);
   mcx_status("Writing %zu colour graph to %s\n", output_colours, strcmp(out_path, "-") ? out_path : "STDOUT");
 
-  if(mcx_device_count() == 0) mcx_die("No CUDA device: "CMD" has no CPU fallback");
+  /* CUDA start-up, the context and the table take 0.5-1.5 s: they run on a second thread while this one
+   * starts parsing the first sequence file (seq_ingest.c keeps the parsed batches until the graph exists) */
+  ginit.k = (uint32_t)kmer_size; ginit.ncols = (uint32_t)output_colours; ginit.capacity = kmers_in_hash; ginit.device = device;
+  ginit.flags = (nifiles > 0 ? MCX_GRAPH_INTERSECT : 0) | (remove_pcr_used ? MCX_GRAPH_READSTRT : 0);
+  ginit.host_batches = ntasks > 0;
+  if(pthread_create(&ginit.thread, NULL, graph_init_main, NULL) != 0) mcx_die("Cannot start a thread");
+  mcx_graph_source.wait = graph_wait; mcx_graph_source.ready = graph_ready; mcx_graph_source.ctx = NULL;
   mcx_graph *g = NULL;
-  int r = mcx_graph_create((uint32_t)kmer_size, (uint32_t)output_colours, kmers_in_hash, device,
-                           (nifiles > 0 ? MCX_GRAPH_INTERSECT : 0) | (remove_pcr_used ? MCX_GRAPH_READSTRT : 0), &g);
-  if(r) die_mcx(r, "mcx_graph_create");
-  { char a[64]; mcx_ulong_to_str(kmers_in_hash, a); mcx_status("[hasht] Allocating device table with %s entries on GPU %i", a, device); }
+  int r = 0;
+  if(nifiles > 0 || ngfiles > 0 || remove_pcr_used) g = graph_wait(NULL); /* these need the device right away */
 
   McxGInfo *ginfo = calloc(output_colours, sizeof(McxGInfo));
   for(i = 0; i < output_colours; i++) mcx_ginfo_init(&ginfo[i]);
@@ -424,14 +466,16 @@ static int ctx_build(int argc, char **argv)
       if(tasks[t].prefs.remove_pcr)
         r = mcx_load_seq_pcr(g, tasks[t].file, tasks[t].file2, tasks[t].interleaved, &tasks[t].prefs, &tasks[t].stats);
       else
-      r = mcx_load_seq_file(g, tasks[t].file, &tasks[t].prefs, &tasks[t].stats);
+      r = mcx_load_seq_file(g, tasks[t].file, &tasks[t].prefs, &tasks[t].stats); /* g may still be NULL: see mcx_graph_source */
       if(r) die_mcx(r, "loading sequence");
+      mcx_phase("sequence file loaded");
       credited.total_bases_loaded += tasks[t].stats.total_bases_loaded;
       credited.contigs_parsed += tasks[t].stats.contigs_parsed;
     }
     mcx_ginfo_update_contigs(&ginfo[tasks[start].prefs.colour], credited.total_bases_loaded, credited.contigs_parsed);
   }
 
+  g = graph_wait(NULL);
   /* src/commands/ctx_build.c:409-413 */
   if(nifiles > 0) {
     r = mcx_graph_finish_intersect(g, NULL);
@@ -453,6 +497,7 @@ static int ctx_build(int argc, char **argv)
   uint64_t nrec = 0; uint32_t rec_bytes = 0;
   r = mcx_graph_export_begin(g, sort_kmers ? 1 : 0, &nrec, &rec_bytes);
   if(r) die_mcx(r, "mcx_graph_export_begin");
+  mcx_phase("export: compact + sort");
   size_t chunk_recs = (64u << 20) / rec_bytes;
   char *buf = malloc(chunk_recs * rec_bytes);
   for(uint64_t at = 0; at < nrec; at += chunk_recs) {
@@ -464,6 +509,7 @@ static int ctx_build(int argc, char **argv)
   free(buf);
   mcx_graph_export_end(g);
   if(fh != stdout) fclose(fh); else fflush(fh);
+  mcx_phase("export: D2H + write");
   { char a[64]; mcx_ulong_to_str(nrec, a);
     mcx_status("[graphwriter] Dumped %s kmers in %zu colour%s into: %s (format version: 6)", a, output_colours,
                output_colours == 1 ? "" : "s", strcmp(out_path, "-") ? out_path : "STDOUT"); }
@@ -471,6 +517,7 @@ static int ctx_build(int argc, char **argv)
   for(i = 0; i < output_colours; i++) mcx_ginfo_free(&ginfo[i]);
   free(ginfo); free(tasks); free(sample_names);
   mcx_graph_destroy(g);
+  mcx_phase("destroy");
   return EXIT_SUCCESS;
 }
 
@@ -518,5 +565,8 @@ int main(int argc, char **argv)
   int ret = is_sort ? mcx_cmd_sort(argc - 1, argv + 1) : ctx_build(argc - 1, argv + 1);
   mcx_status(ret == 0 ? "Done." : "Fail.");
   mcx_status("[time] %.2lf seconds\n", difftime(time(NULL), t0));
-  return ret;
+  /* every output file is closed: leave without the CUDA runtime's exit handlers (tearing the context down in user
+   * space takes 0.3-0.7 s; the kernel driver reclaims the device memory either way) */
+  fflush(stdout); fflush(stderr);
+  _exit(ret);
 }

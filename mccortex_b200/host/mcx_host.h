@@ -17,6 +17,7 @@
 extern FILE *mcx_msg_out;                 /* NULL when -q/--quiet */
 void mcx_status(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
 void mcx_warn(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+void mcx_phase(const char *what); /* MCX_TIMING=1: phase wall clock on stderr */
 void mcx_die(const char *fmt, ...) __attribute__((noreturn)) __attribute__((format(printf, 1, 2)));
 void mcx_print_usage(const char *usage, const char *errfmt, ...) __attribute__((noreturn))
     __attribute__((format(printf, 2, 3)));
@@ -103,10 +104,24 @@ typedef struct {
   uint32_t colour;
 } McxLoadPrefs;
 
+/* The loaders below accept g == NULL when mcx_graph_source is set: they parse ahead while the graph is being
+ * created elsewhere (ready() polls, wait() blocks and returns it) -- see seq_ingest.c */
+typedef struct {
+  mcx_graph *(*wait)(void *ctx);
+  bool (*ready)(void *ctx);
+  void *ctx;
+} McxGraphSource;
+extern McxGraphSource mcx_graph_source;
+
 /* Parse every read of sf (FASTA / FASTQ / plain, sniffed from the first byte like
  * seq_file.h:311-323) and feed the graph in LINES batches.  Stats of this file are ADDED
  * to *stats.  Returns 0, or the MCX_ERR_* that stopped the load. */
 int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats);
+
+/* seq_ingest_par.c: the same for a regular, uncompressed FASTA / one-read-per-line file of >= 32 MB, parsed by
+ * several threads (MCX_PARSE_THREADS, default min(cores, 16); 1 = off).  Returns false when the file is not
+ * eligible (then nothing was done); else *rc is what mcx_load_seq_file would have returned. */
+bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats, int *rc);
 
 /* One task with --remove-pcr in force (build_graph_from_reads_mt with remove_pcr_dups): sf2 != NULL for a --seq2
  * pair, interleaved for --seqi (consecutive reads whose names match are a pair), else single-end.  Reads and

@@ -16,6 +16,12 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
+/* Where the graph comes from when a loader is called with g == NULL: the driver creates the device table on a
+ * second thread (CUDA start-up + context take 0.5-1.5 s, as long as parsing a GB of FASTA) and the loader parses
+ * ahead meanwhile, keeping up to MCX_RUNAHEAD_BYTES of finished batches until wait() hands the graph over. */
+McxGraphSource mcx_graph_source = {NULL, NULL, NULL};
+#define MCX_RUNAHEAD_BYTES (2048ull << 20)
+
 #define MCX_BATCH_BYTES_DEFAULT (96u << 20)
 /* bytes per batch; MCX_BATCH_BYTES=<n> in the environment overrides it (tests use tiny batches) */
 static size_t batch_bytes(void)
@@ -114,8 +120,10 @@ static inline bool is_space(int c) { return c == ' ' || (c >= '\t' && c <= '\r')
 
 /* ---- loader state ---------------------------------------------------------------- */
 typedef struct { int qmin, qmax; size_t qcount, bcount; } QStat;
+typedef struct { mcx_read_batch b; char *seq, *qual; } PendingBatch; /* parsed before the graph existed */
 typedef struct {
   mcx_graph *g; const McxLoadPrefs *prefs; mcx_load_stats *stats;
+  PendingBatch *pend; size_t npend, pend_cap; uint64_t pend_bytes;
   Buf lines;          /* LINES batch under construction */
   Buf qlines;         /* quality bytes parallel to `lines` (only when a quality cut-off is set) */
   Buf qual;           /* quality string of the current FASTQ record */
@@ -147,27 +155,61 @@ static uint8_t guess_fq_offset(const QStat *L)
   return (uint8_t)OFFS[fmt];
 }
 
-static void flush_batch(Loader *L)
+/* the call for the batch under construction; false: nothing to send */
+static bool prepare_batch(Loader *L, mcx_read_batch *b)
 {
-  if(L->lines.len == 0 || L->err) { L->lines.len = 0; L->qlines.len = 0; return; }
-  mcx_read_batch b; memset(&b, 0, sizeof(b));
-  b.seq = L->lines.b; b.nbytes = L->lines.len;
-  b.layout = MCX_LAYOUT_LINES; b.mem = MCX_MEM_HOST;
-  b.colour = L->prefs->colour; b.hp_cutoff = L->prefs->hp_cutoff; b.must_exist = L->prefs->must_exist;
+  if(L->lines.len == 0 || L->err) { L->lines.len = 0; L->qlines.len = 0; return false; }
+  memset(b, 0, sizeof(*b));
+  b->seq = L->lines.b; b->nbytes = L->lines.len;
+  b->layout = MCX_LAYOUT_LINES; b->mem = MCX_MEM_HOST;
+  b->colour = L->prefs->colour; b->hp_cutoff = L->prefs->hp_cutoff; b->must_exist = L->prefs->must_exist;
   if(L->prefs->fq_cutoff && L->any_qual) {
     /* build_graph.c:202-207: the ASCII offset is added only when a cut-off is set */
     if(!L->offset_known) {
       L->fq_offset = L->prefs->fq_offset ? L->prefs->fq_offset : guess_fq_offset(&L->qs[0]);
       L->offset_known = true;
-      if(L->fq_offset + L->prefs->fq_cutoff >= 127) { L->err = MCX_ERR_UNSUPPORTED; L->lines.len = L->qlines.len = 0; return; }
+      if(L->fq_offset + L->prefs->fq_cutoff >= 127) { L->err = MCX_ERR_UNSUPPORTED; L->lines.len = L->qlines.len = 0; return false; }
     }
-    b.qual = L->qlines.b;
-    b.fq_cutoff = (uint8_t)(L->prefs->fq_cutoff + L->fq_offset);
+    b->qual = L->qlines.b;
+    b->fq_cutoff = (uint8_t)(L->prefs->fq_cutoff + L->fq_offset);
   }
-  L->qlines.len = 0;
-  int r = mcx_graph_add_reads(L->g, &b);
-  if(r != MCX_OK) L->err = r;
-  L->lines.len = 0;
+  return true;
+}
+
+/* block until the graph exists, then send, in order, the batches parsed meanwhile */
+static void loader_need_graph(Loader *L)
+{
+  if(L->g || !mcx_graph_source.wait) return; /* (g == NULL without a source: the CPU-only test harness) */
+  L->g = mcx_graph_source.wait(mcx_graph_source.ctx);
+  for(size_t i = 0; i < L->npend; i++) {
+    if(!L->err) { int r = mcx_graph_add_reads(L->g, &L->pend[i].b); if(r != MCX_OK) L->err = r; }
+    free(L->pend[i].seq); free(L->pend[i].qual);
+  }
+  free(L->pend); L->pend = NULL; L->npend = L->pend_cap = 0; L->pend_bytes = 0;
+}
+
+static void flush_batch(Loader *L)
+{
+  mcx_read_batch b;
+  if(!prepare_batch(L, &b)) return;
+  if(!L->g && mcx_graph_source.wait && mcx_graph_source.ready && !mcx_graph_source.ready(mcx_graph_source.ctx) &&
+     L->pend_bytes + b.nbytes < MCX_RUNAHEAD_BYTES) {
+    /* the device is still starting up: keep the batch, go on parsing into fresh buffers */
+    if(L->npend == L->pend_cap) {
+      L->pend_cap = L->pend_cap ? 2 * L->pend_cap : 16;
+      L->pend = realloc(L->pend, L->pend_cap * sizeof(*L->pend));
+      if(!L->pend) mcx_die("Out of memory");
+    }
+    PendingBatch *pb = &L->pend[L->npend++];
+    pb->b = b; pb->seq = L->lines.b; pb->qual = L->qlines.b;
+    L->pend_bytes += b.nbytes;
+    memset(&L->lines, 0, sizeof(L->lines)); memset(&L->qlines, 0, sizeof(L->qlines));
+    buf_reserve(&L->lines, MCX_BATCH_BYTES + (1u << 20));
+    return;
+  }
+  loader_need_graph(L);
+  if(!L->err) { int r = mcx_graph_add_reads(L->g, &b); if(r != MCX_OK) L->err = r; }
+  L->lines.len = 0; L->qlines.len = 0;
 }
 
 /* a record's sequence now sits at lines[start .. len): terminate it, maybe ship the batch */
@@ -283,6 +325,7 @@ static int read_plain(McxSeqFile *sf, Loader *L)
 
 int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats)
 {
+  { int rc = 0; if(mcx_load_seq_file_par(g, sf, prefs, stats, &rc)) return rc; } /* big uncompressed FASTA / plain files */
   Loader L; memset(&L, 0, sizeof(L));
   L.g = g; L.prefs = prefs; L.stats = stats; L.qs[0].qmin = L.qs[1].qmin = 0x7fffffff;
   buf_reserve(&L.lines, MCX_BATCH_BYTES + (1u << 20));
@@ -301,9 +344,12 @@ int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, m
   }
   flush_batch(&L);
   if(s < 0 && !L.err) mcx_warn("Input error: %s\n", sf->path);
+  mcx_phase("  parsed");
+  loader_need_graph(&L);
+  mcx_phase("  submitted");
 
   mcx_load_stats st;
-  int r = mcx_graph_sync(g, &st);
+  int r = mcx_graph_sync(L.g, &st);
   if(L.err) r = L.err;
   stats->total_bases_read += st.total_bases_read;
   stats->total_bases_loaded += st.total_bases_loaded;
@@ -341,6 +387,7 @@ static int names_cmp(const char *aa, const char *bb)
 static void flush_batch_pcr(Loader *L, size_t n)
 {
   if(n == 0) return;
+  loader_need_graph(L);
   size_t cut = n < L->nreads ? L->read_off[n] : L->lines.len, i;
   if(!L->err) {
     mcx_read_batch b; memset(&b, 0, sizeof(b));
@@ -461,9 +508,10 @@ int mcx_load_seq_pcr(mcx_graph *g, McxSeqFile *sf1, McxSeqFile *sf2, bool interl
     if(s1 < 0) mcx_warn("Input error: %s\n", sf1->path);
   }
   flush_batch_pcr(&L, L.nreads);
+  loader_need_graph(&L);
 
   mcx_load_stats st;
-  int r = mcx_graph_sync(g, &st);
+  int r = mcx_graph_sync(L.g, &st);
   if(L.err) r = L.err;
   stats->total_bases_read += st.total_bases_read;
   stats->total_bases_loaded += st.total_bases_loaded;

@@ -1,0 +1,242 @@
+/* seq_ingest_par.c -- uncompressed FASTA / plain files parsed by several host threads.
+ *
+ * The GPU side of `build` takes host batches at tens of GB/s (PCIe-bound); one thread running the record
+ * reader of seq_ingest.c delivers ~2 GB/s.  A file that is a regular, uncompressed FASTA or one-read-per-line
+ * file is therefore mapped and cut into segments at record starts; worker threads turn segments into LINES
+ * buffers (same rules as read_fasta / read_plain of seq_ingest.c, i.e. libs/seq_file/seq_file.h:274-309) and the
+ * calling thread hands the buffers to mcx_graph_add_reads in file order.  The reference reads one file per
+ * thread (src/basic/async_read_io.c:118-141, one async_io_reader each); a build's table updates commute, so the
+ * order in which reads arrive does not change the graph.
+ *
+ * Where a cut may be made:
+ *   FASTA  at a '>' that follows a '\n'.  The sequential reader only ever looks for '>' at the start of a line,
+ *          header lines are consumed whole, so such a byte is a record start whatever precedes it.
+ *   plain  after any '\n' (every line is a record or is skipped on its own).
+ * FASTQ ('@' also starts quality lines), gzip, stdin, --remove-pcr (order matters) and small files keep the
+ * sequential reader.
+ */
+#include "mcx_host.h"
+#include <fcntl.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#define PAR_MIN_BYTES (32u << 20)          /* smaller files: not worth the threads */
+#define PAR_SEG_BYTES_DEFAULT (16u << 20)  /* raw bytes per segment (MCX_PARSE_SEG_BYTES overrides; tests use tiny ones) */
+#define PAR_MAX_THREADS 32
+
+typedef struct {
+  char *b; size_t len, cap;   /* LINES bytes of one segment */
+  uint64_t nreads;
+  int state;                  /* 0 free, 1 being filled, 2 full */
+  size_t seg;                 /* which segment it holds */
+} SegBuf;
+
+typedef struct {
+  const unsigned char *data; size_t size;
+  bool fasta;
+  size_t nseg; size_t *cut;   /* segment i = [cut[i], cut[i+1]) */
+  size_t next_seg;            /* next segment to hand to a worker */
+  SegBuf *bufs; size_t nbufs;
+  pthread_mutex_t mu; pthread_cond_t cv;
+} ParState;
+
+static inline bool par_is_space(int c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+/* read_fasta of seq_ingest.c over memory [p, end): end is the end of the file or a record start */
+static void parse_fasta_range(const unsigned char *d, size_t p, size_t end, SegBuf *o)
+{
+  while(p < end) {
+    /* d[p] == '>' : header line, dropped */
+    const unsigned char *e = memchr(d + p + 1, '\n', end - p - 1);
+    if(!e) {
+      if(end - p - 1 == 0) return; /* '>' then EOF: the sequential reader reports an input error and stops */
+      p = end;
+    } else p = (size_t)(e - d) + 1;
+    const size_t start = o->len;
+    while(p < end && d[p] != '>') {
+      const unsigned char c = d[p++];
+      if(c != '\r' && c != '\n') {
+        const unsigned char *nl = memchr(d + p, '\n', end - p);
+        const size_t n = nl ? (size_t)(nl - (d + p)) : end - p;
+        o->b[o->len++] = (char)c;
+        memcpy(o->b + o->len, d + p, n); o->len += n;
+        p += n + (nl ? 1 : 0);
+        while(o->len > start && (o->b[o->len - 1] == '\n' || o->b[o->len - 1] == '\r')) o->len--;
+        if(!nl && n == 0) break;
+      }
+    }
+    o->b[o->len++] = '\n';
+    o->nreads++;
+  }
+}
+
+/* read_plain of seq_ingest.c over memory [p, end): both are line starts (or the end of the file) */
+static void parse_plain_range(const unsigned char *d, size_t p, size_t end, SegBuf *o)
+{
+  while(p < end) {
+    const unsigned char c = d[p++];
+    if(par_is_space(c)) {
+      if(c != '\n') { const unsigned char *nl = memchr(d + p, '\n', end - p); p = nl ? (size_t)(nl - d) + 1 : end; }
+      continue;
+    }
+    const size_t start = o->len;
+    const unsigned char *nl = memchr(d + p, '\n', end - p);
+    const size_t n = nl ? (size_t)(nl - (d + p)) : end - p;
+    o->b[o->len++] = (char)c;
+    memcpy(o->b + o->len, d + p, n); o->len += n;
+    p += n + (nl ? 1 : 0);
+    while(o->len > start && (o->b[o->len - 1] == '\n' || o->b[o->len - 1] == '\r')) o->len--;
+    o->b[o->len++] = '\n';
+    o->nreads++;
+  }
+}
+
+static void *par_worker(void *arg)
+{
+  ParState *ps = arg;
+  for(;;) {
+    pthread_mutex_lock(&ps->mu);
+    SegBuf *o = NULL;
+    while(ps->next_seg < ps->nseg) {
+      /* segments are consumed in order: take one only if a buffer is free */
+      for(size_t i = 0; i < ps->nbufs; i++) if(ps->bufs[i].state == 0) { o = &ps->bufs[i]; break; }
+      if(o) break;
+      pthread_cond_wait(&ps->cv, &ps->mu);
+    }
+    if(!o) { pthread_mutex_unlock(&ps->mu); return NULL; }
+    const size_t seg = ps->next_seg++;
+    o->state = 1; o->seg = seg; o->len = 0; o->nreads = 0;
+    pthread_mutex_unlock(&ps->mu);
+
+    const size_t a = ps->cut[seg], b = ps->cut[seg + 1];
+    if(o->cap < b - a + 2) {
+      free(o->b);
+      o->cap = b - a + 2 + (1u << 16);
+      o->b = malloc(o->cap);
+      if(!o->b) mcx_die("Out of memory");
+    }
+    if(ps->fasta) parse_fasta_range(ps->data, a, b, o); else parse_plain_range(ps->data, a, b, o);
+
+    pthread_mutex_lock(&ps->mu);
+    o->state = 2;
+    pthread_cond_broadcast(&ps->cv);
+    pthread_mutex_unlock(&ps->mu);
+  }
+}
+
+bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats, int *rc)
+{
+  const char *path = mcx_seq_path(sf);
+  long nthreads = sysconf(_SC_NPROCESSORS_ONLN);
+  if(nthreads > 16) nthreads = 16;
+  if(getenv("MCX_PARSE_THREADS")) nthreads = atol(getenv("MCX_PARSE_THREADS"));
+  if(nthreads > PAR_MAX_THREADS) nthreads = PAR_MAX_THREADS;
+  size_t seg_bytes = PAR_SEG_BYTES_DEFAULT, min_bytes = PAR_MIN_BYTES;
+  if(getenv("MCX_PARSE_SEG_BYTES") && atol(getenv("MCX_PARSE_SEG_BYTES")) > 0) { seg_bytes = (size_t)atol(getenv("MCX_PARSE_SEG_BYTES")); min_bytes = 0; }
+  if(nthreads < 2 || prefs->remove_pcr || strcmp(path, "-") == 0) return false;
+
+  struct stat st;
+  int fd = open(path, O_RDONLY);
+  if(fd < 0) return false;
+  if(fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || (size_t)st.st_size < min_bytes || st.st_size < 2) { close(fd); return false; }
+  const size_t size = (size_t)st.st_size;
+  const unsigned char *d = mmap(NULL, size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if(d == MAP_FAILED) return false;
+  /* gzip goes through zlib; the format is the first byte that is not white space (seq_file.h:311-323) */
+  size_t p0 = 0;
+  bool ok = !(d[0] == 0x1f && d[1] == 0x8b);
+  if(ok) {
+    /* the sequential sniff skips the REST OF THE LINE after a leading white-space byte other than '\n' */
+    while(p0 < size && par_is_space(d[p0])) {
+      if(d[p0] != '\n') { const unsigned char *nl = memchr(d + p0, '\n', size - p0); p0 = nl ? (size_t)(nl - d) + 1 : size; }
+      else p0++;
+    }
+    ok = p0 < size && d[p0] != '@';
+  }
+  if(!ok) { munmap((void *)d, size); return false; }
+
+  ParState ps; memset(&ps, 0, sizeof(ps));
+  ps.data = d; ps.size = size; ps.fasta = d[p0] == '>';
+  /* cuts */
+  size_t max_seg = (size - p0) / seg_bytes + 2;
+  ps.cut = malloc((max_seg + 1) * sizeof(size_t));
+  if(!ps.cut) mcx_die("Out of memory");
+  ps.cut[0] = p0; ps.nseg = 0;
+  for(size_t at = p0;;) {
+    size_t q = at + seg_bytes;
+    if(q >= size) { ps.cut[++ps.nseg] = size; break; }
+    /* first legal cut at or after q */
+    for(;;) {
+      const unsigned char *nl = memchr(d + q - 1, '\n', size - (q - 1));
+      if(!nl) { q = size; break; }
+      q = (size_t)(nl - d) + 1;
+      if(q >= size || !ps.fasta || d[q] == '>') break;
+      q++; /* a sequence line: keep looking */
+    }
+    ps.cut[++ps.nseg] = q;
+    if(q >= size) break;
+    at = q;
+  }
+
+  mcx_status("[seq] Parsing sequence file %s", path);
+  ps.nbufs = (size_t)nthreads * 2 < ps.nseg ? (size_t)nthreads * 2 : ps.nseg;
+  ps.bufs = calloc(ps.nbufs, sizeof(SegBuf));
+  pthread_mutex_init(&ps.mu, NULL); pthread_cond_init(&ps.cv, NULL);
+  pthread_t th[PAR_MAX_THREADS];
+  size_t nth = (size_t)nthreads < ps.nseg ? (size_t)nthreads : ps.nseg;
+  for(size_t i = 0; i < nth; i++) if(pthread_create(&th[i], NULL, par_worker, &ps) != 0) mcx_die("Cannot start a thread");
+
+  int err = 0; uint64_t nreads_total = 0;
+  for(size_t seg = 0; seg < ps.nseg; seg++) {
+    SegBuf *o = NULL;
+    pthread_mutex_lock(&ps.mu);
+    for(;;) {
+      for(size_t i = 0; i < ps.nbufs; i++) if(ps.bufs[i].state == 2 && ps.bufs[i].seg == seg) { o = &ps.bufs[i]; break; }
+      if(o) break;
+      pthread_cond_wait(&ps.cv, &ps.mu);
+    }
+    pthread_mutex_unlock(&ps.mu);
+    if(seg == 0) mcx_phase("  first segment parsed");
+    if(!g && mcx_graph_source.wait) g = mcx_graph_source.wait(mcx_graph_source.ctx);
+    if(!err && o->len) {
+      mcx_read_batch b; memset(&b, 0, sizeof(b));
+      b.seq = o->b; b.nbytes = o->len; b.layout = MCX_LAYOUT_LINES; b.mem = MCX_MEM_HOST;
+      b.colour = prefs->colour; b.hp_cutoff = prefs->hp_cutoff; b.must_exist = prefs->must_exist;
+      int r = mcx_graph_add_reads(g, &b);
+      if(r != MCX_OK) err = r;
+    }
+    nreads_total += o->nreads;
+    pthread_mutex_lock(&ps.mu);
+    o->state = 0;
+    pthread_cond_broadcast(&ps.cv);
+    pthread_mutex_unlock(&ps.mu);
+  }
+  for(size_t i = 0; i < nth; i++) pthread_join(th[i], NULL);
+  for(size_t i = 0; i < ps.nbufs; i++) free(ps.bufs[i].b);
+  free(ps.bufs); free(ps.cut);
+  pthread_mutex_destroy(&ps.mu); pthread_cond_destroy(&ps.cv);
+  munmap((void *)d, size);
+  mcx_phase("  parsed + submitted");
+  if(!g && mcx_graph_source.wait) g = mcx_graph_source.wait(mcx_graph_source.ctx);
+
+  mcx_load_stats s;
+  int r = mcx_graph_sync(g, &s);
+  if(err) r = err;
+  stats->total_bases_read += s.total_bases_read;
+  stats->total_bases_loaded += s.total_bases_loaded;
+  stats->contigs_parsed += s.contigs_parsed;
+  stats->num_kmers_loaded += s.num_kmers_loaded;
+  stats->num_kmers_novel += s.num_kmers_novel;
+  stats->num_se_reads += s.num_se_reads;
+  if(s.num_good_reads != UINT64_MAX) { stats->num_good_reads += s.num_good_reads; stats->num_bad_reads += s.num_bad_reads; }
+  else { stats->num_good_reads = stats->num_bad_reads = UINT64_MAX; }
+  char n1[64]; mcx_ulong_to_str(nreads_total, n1);
+  mcx_status("[seq] Loaded %s reads and 0 reads pairs (file: %s)", n1, path);
+  *rc = r;
+  return true;
+}

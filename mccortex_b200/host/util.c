@@ -71,6 +71,19 @@ void mcx_print_usage(const char *usage, const char *errfmt, ...)
   exit(EXIT_FAILURE);
 }
 
+/* MCX_TIMING=1: wall clock of the driver's phases on stderr (not part of the reference's log) */
+void mcx_phase(const char *what)
+{
+  static int on = -1; static struct timespec t0, last;
+  struct timespec now;
+  if(on < 0) { on = getenv("MCX_TIMING") != NULL; clock_gettime(CLOCK_MONOTONIC, &t0); last = t0; }
+  if(!on) return;
+  clock_gettime(CLOCK_MONOTONIC, &now);
+  fprintf(stderr, "[phase] %-28s +%.3f s  (at %.3f s)\n", what, (double)(now.tv_sec - last.tv_sec) + 1e-9 * (double)(now.tv_nsec - last.tv_nsec),
+          (double)(now.tv_sec - t0.tv_sec) + 1e-9 * (double)(now.tv_nsec - t0.tv_nsec));
+  last = now;
+}
+
 void mcx_ulong_to_str(uint64_t num, char *out)
 {
   char tmp[32]; int n = snprintf(tmp, sizeof(tmp), "%llu", (unsigned long long)num), i, j = 0;

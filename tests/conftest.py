@@ -103,11 +103,12 @@ def ingest_dump():
     src = os.path.join(ROOT, "tests", "emul", "ingest_dump.c")
     exe = os.path.join(ROOT, "tests", "emul", "ingest_dump")
     host = os.path.join(ROOT, "mccortex_b200", "host")
-    deps = [src, os.path.join(host, "seq_ingest.c"), os.path.join(host, "util.c"), os.path.join(host, "mcx_host.h"),
-            os.path.join(ROOT, "include", "mcx_gpu.h")]
+    deps = [src, os.path.join(host, "seq_ingest.c"), os.path.join(host, "seq_ingest_par.c"), os.path.join(host, "util.c"),
+            os.path.join(host, "mcx_host.h"), os.path.join(ROOT, "include", "mcx_gpu.h")]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
         subprocess.check_call(["gcc", "-O2", "-std=c99", "-D_GNU_SOURCE", "-I", os.path.join(ROOT, "include"), "-o", exe, src,
-                               os.path.join(host, "seq_ingest.c"), os.path.join(host, "util.c"), "-lz", "-lm"])
+                               os.path.join(host, "seq_ingest.c"), os.path.join(host, "seq_ingest_par.c"), os.path.join(host, "util.c"),
+                               "-lz", "-lm", "-lpthread"])
     return exe
 
 

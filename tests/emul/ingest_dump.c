@@ -7,6 +7,8 @@
  *
  * usage: ingest_dump <out-prefix> <mode se|pe|il> <fq_cutoff> <fq_offset> <hp> <matedir 0..3> <file1> [<file2>]
  *   writes <out-prefix>.lines .qual .mate and prints "fq_cutoff=<with offset> nreads=<n> nbatches=<n>"
+ * mode `file`: the plain build ingest (mcx_load_seq_file: sequential reader, or the multi-threaded one of
+ *   seq_ingest_par.c when the file is eligible); .lines / .qual are what mcx_graph_add_reads would receive, in call order
  */
 #include "../../mccortex_b200/host/mcx_host.h"
 #include <stdlib.h>
@@ -29,7 +31,20 @@ int mcx_graph_add_reads_pcr(mcx_graph *g, const mcx_read_batch *b, const uint64_
   nreads_seen += nreads; nbatches++;
   return MCX_OK;
 }
-int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b) { (void)g; (void)b; fprintf(stderr, "unexpected mcx_graph_add_reads\n"); exit(3); }
+static int file_mode;
+int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
+{
+  (void)g;
+  if(!file_mode) { fprintf(stderr, "unexpected mcx_graph_add_reads\n"); exit(3); }
+  if(b->layout != MCX_LAYOUT_LINES || b->mem != MCX_MEM_HOST || !b->nbytes || b->seq[b->nbytes - 1] != '\n') { fprintf(stderr, "bad batch\n"); exit(3); }
+  fwrite(b->seq, 1, b->nbytes, f_lines);
+  if(b->qual) fwrite(b->qual, 1, b->nbytes, f_qual);
+  else for(uint64_t i = 0; i < b->nbytes; i++) fputc(0x7F, f_qual);
+  for(uint64_t i = 0; i < b->nbytes; i++) nreads_seen += b->seq[i] == '\n';
+  if(b->fq_cutoff) last_cut = b->fq_cutoff;
+  nbatches++;
+  return MCX_OK;
+}
 int mcx_graph_sync(mcx_graph *g, mcx_load_stats *st) { (void)g; memset(st, 0, sizeof(*st)); return MCX_OK; }
 
 int main(int argc, char **argv)
@@ -46,7 +61,9 @@ int main(int argc, char **argv)
   McxSeqFile *a = mcx_seq_open(argv[7]), *b = !strcmp(argv[2], "pe") ? mcx_seq_open(argv[8]) : NULL;
   if(!a || (!strcmp(argv[2], "pe") && !b)) { fprintf(stderr, "cannot open input\n"); return 2; }
   mcx_load_stats st; memset(&st, 0, sizeof(st));
-  int r = mcx_load_seq_pcr(NULL, a, b, !strcmp(argv[2], "il"), &prefs, &st);
+  int r;
+  if(!strcmp(argv[2], "file")) { file_mode = 1; prefs.remove_pcr = false; r = mcx_load_seq_file(NULL, a, &prefs, &st); }
+  else r = mcx_load_seq_pcr(NULL, a, b, !strcmp(argv[2], "il"), &prefs, &st);
   fclose(f_lines); fclose(f_qual); fclose(f_mate);
   printf("fq_cutoff=%u nreads=%llu nbatches=%llu se=%llu pe=%llu\n", last_cut, nreads_seen, nbatches,
          (unsigned long long)st.num_se_reads, (unsigned long long)st.num_pe_reads);

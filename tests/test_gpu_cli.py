@@ -260,3 +260,25 @@ def test_cli_sort_command(tmp_path, oracle, k):
         shutil.copy(uns, refcopy)
         oracle.ref_run(k, ["sort", "-q", str(refcopy)])
         assert open(refcopy, "rb").read() == want
+
+
+def test_cli_parallel_ingest_and_background_device_start(tmp_path, oracle):
+    """uncompressed FASTA / plain files cut at record starts and parsed by several host threads
+    (seq_ingest_par.c; tiny segments so that a small file is cut hundreds of times), the device table created on
+    a second thread meanwhile: same bytes as the oracle's build, and as the sequential reader's"""
+    rng = random.Random(77)
+    reads = rand_reads(rng, 3000, (20, 300), 40000, perr=0.004) + EDGE_READS
+    fa = tmp_path / "a.fa"
+    with open(fa, "w") as f:
+        for i, r in enumerate(reads):
+            f.write(">r%d >x @y\n" % i)
+            for j in range(0, len(r), 60):
+                f.write(r[j:j + 60] + ("\r\n" if i % 7 == 0 else "\n"))
+    plain = tmp_path / "b.txt"
+    plain.write_text("\n".join(r for r in reads if r) + "\n")
+    want, _ = oracle.build_ctx(31, [("fa", [str(fa)]), ("plain", [str(plain)])])
+    args = ["-q", "-f", "-m", "1G", "-n", "2M", "-k", "31", "-S", "-s", "fa", "-1", str(fa), "-s", "plain", "-1", str(plain)]
+    for env in ({"MCX_PARSE_THREADS": "4", "MCX_PARSE_SEG_BYTES": "5000"}, {"MCX_PARSE_THREADS": "1"}):
+        out = tmp_path / "out.ctx"
+        _run(args + [str(out)], env=env)
+        assert open(out, "rb").read() == want, env

@@ -567,3 +567,46 @@ def test_remove_pcr_reset_between_colours(M, oracle):
     got, _, _ = g.export_records()
     assert got == og.dump_sorted()[len(og.header()):]
     g.close()
+
+
+# ---- MCX_SPILL: parked big-table work leaves the fused kernel as tuples, kernel C inserts it ---------------
+@pytest.mark.parametrize("cap,span_mb", [(0, 0), (1000, 1), (7, 0)])
+def test_spill_variant_matches_oracle(M, oracle, reads_small, cap, span_mb, monkeypatch):
+    """MCX_SPILL=1 with a front table too small for the input (MCX_FRONT_BITS=16: 262 144 ways for ~600 000
+    distinct k-mers), so that most new k-mers are spilled; cap = 1000 / 7 tuples makes nearly all of them
+    overflow the bin and take the inline insert instead; span 1 MB cuts the device-resident batch into several
+    launch + insert pairs.  Host batch (staging slots) and device batch (primary stream), two colours (the
+    front table is flushed and restarted in between), a k-mer seen 300 000 times, homopolymer cut-off."""
+    import torch
+    monkeypatch.setenv("MCX_SPILL", "1")
+    monkeypatch.setenv("MCX_FRONT_BITS", "16")
+    if cap:
+        monkeypatch.setenv("MCX_SPILL_CAP", str(cap))
+    if span_mb:
+        monkeypatch.setenv("MCX_SPILL_SPAN_MB", str(span_mb))
+    rng = random.Random(900 + cap)
+    reads = reads_small + rand_reads(rng, 9000, 150, 3_000_000, perr=0.002, pN=0.0005) + ["A" * 150] * 2500
+    rng.shuffle(reads)
+    third = len(reads) // 3
+    parts = [reads[:third], reads[third:2 * third], reads[2 * third:]]
+    dev = torch.device("cuda:0")
+    for k, hp in ((31, 0), (21, 4)):
+        og = oracle.Graph(k, 2, 1 << 22)
+        ost = oracle.Stats()
+        for i, part in enumerate(parts):
+            for r in part:
+                og.add_read(r, colour=i & 1, hp_cutoff=hp, stats=ost)
+        want = og.dump_sorted()[len(og.header()):]
+        og.close()
+        g = M.Graph(k, 2, 1 << 21)
+        g.add_lines("".join(r + "\n" for r in parts[0]).encode(), colour=0, hp_cutoff=hp)          # host: staging slots
+        seq = _to_dev(torch, "".join(r + "\n" for r in parts[1]).encode(), dev)                      # device: primary stream
+        g.add_reads_raw(seq.data_ptr(), sum(len(r) + 1 for r in parts[1]), mem=M.MCX_MEM_DEVICE, colour=1, hp_cutoff=hp)
+        g.add_lines("".join(r + "\n" for r in parts[2]).encode(), colour=0, hp_cutoff=hp)
+        st = g.sync()
+        got, n, _ = g.export_records()
+        assert n == ost.num_kmers_novel
+        assert got == want
+        _check_stats(st, ost, len(reads))
+        g.close()
+        del seq

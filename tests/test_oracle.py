@@ -267,3 +267,54 @@ def test_host_ingest_remove_pcr(oracle, emul, ingest_dump, tmp_path, mode, k, cu
     assert r.stdout == recs
     assert (cnt["dupse"], cnt["duppe"]) == (st.num_dup_se_reads, st.num_dup_pe_pairs)
     assert st.num_dup_se_reads + st.num_dup_pe_pairs > 20
+
+
+# ---- multi-threaded ingest (seq_ingest_par.c) == the sequential reader ----------------------------------------
+def _tricky_fasta(rng, nrec):
+    out = []
+    for i in range(nrec):
+        hdr = ">" + "".join(rng.choice("ACGTxyz >@|_") for _ in range(rng.randint(0, 30)))
+        eol = rng.choice(["\n", "\n", "\n", "\r\n"])
+        out.append(hdr + eol)
+        nlines = rng.choice([0, 1, 1, 1, 2, 5])
+        for _ in range(nlines):
+            line = "".join(rng.choice("ACGTacgtNn") for _ in range(rng.randint(1, 90)))
+            if rng.random() < 0.03:
+                line = line[:len(line) // 2] + "\r" + line[len(line) // 2:]      # a CR inside a line stays in the read
+            out.append(line + rng.choice(["\n", "\n", "\r\n", "\r\r\n"]))
+            if rng.random() < 0.05:
+                out.append(rng.choice(["\n", "\r\n", "\r"]))                      # empty lines / a bare CR at a line start
+    return "".join(out)
+
+
+@pytest.mark.parametrize("kind,seg,tail", [("fasta", 700, "\n"), ("fasta", 5000, ""), ("fasta", 64, ">last"), ("fasta", 300, ">"),
+                                           ("plain", 500, "\n"), ("plain", 90, "ACGT")])
+def test_parallel_ingest_matches_sequential_reader(ingest_dump, tmp_path, kind, seg, tail):
+    """the LINES bytes handed to mcx_graph_add_reads are identical whether the file goes through the sequential
+    reader (MCX_PARSE_THREADS=1) or is cut at record starts and parsed by 4 threads (tiny segments: hundreds of cuts);
+    multi-line records, CR LF, empty lines, '>' and '@' inside headers, leading white-space lines, odd file ends"""
+    rng = random.Random(seg)
+    if kind == "fasta":
+        txt = " skipped line\n\n" + _tricky_fasta(rng, 600) + tail
+    else:
+        lines = []
+        for _ in range(3000):
+            r = rng.random()
+            if r < 0.05:
+                lines.append(rng.choice(["", " ignored ACGT", "\tACGT", "\r"]))
+            else:
+                lines.append("".join(rng.choice("ACGTacgtN") for _ in range(rng.randint(1, 160))) + rng.choice(["", "", "\r"]))
+        txt = "\n".join(lines) + "\n" + tail
+    path = tmp_path / ("in." + kind)
+    path.write_bytes(txt.encode())
+    outs = []
+    for threads in (1, 4):
+        env = dict(os.environ, MCX_PARSE_THREADS=str(threads), MCX_PARSE_SEG_BYTES=str(seg), MCX_BATCH_BYTES="4000")
+        pre = str(tmp_path / ("d%d" % threads))
+        info = subprocess.run([ingest_dump, pre, "file", "0", "0", "0", "1", str(path)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, check=True, env=env).stdout.decode()
+        info = dict(x.split("=") for x in info.split())
+        outs.append((open(pre + ".lines", "rb").read(), int(info["nreads"]), int(info["nbatches"])))
+    assert outs[0][0] == outs[1][0]
+    assert outs[0][1] == outs[1][1] > 500
+    assert outs[1][2] > 10     # the threaded run really was cut into many segments
