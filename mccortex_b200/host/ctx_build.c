@@ -346,6 +346,82 @@ static mcx_graph *graph_wait(void *ctx)
   return ginit.g;
 }
 
+/* Large outputs: the records come off the device in 32 MB chunks into pinned buffers (DMA at PCIe speed) and
+ * writer threads put each chunk at its place in the file with pwrite -- the reference's dump is one thread calling
+ * fwrite per field (src/graph/graph_writer.c:116-127).  Returns false (nothing written) if the file is not seekable. */
+#define OUT_NBUF 4
+#define OUT_CHUNK (32u << 20)
+typedef struct {
+  int fd; char *buf[OUT_NBUF]; size_t nbytes[OUT_NBUF]; off_t off[OUT_NBUF]; int state[OUT_NBUF]; /* 0 free, 1 full, 2 being written */
+  bool done; int err;
+  pthread_mutex_t mu; pthread_cond_t cv;
+} OutPipe;
+static void *out_writer(void *arg)
+{
+  OutPipe *op = arg;
+  for(;;) {
+    int s = -1;
+    pthread_mutex_lock(&op->mu);
+    for(;;) {
+      for(int i = 0; i < OUT_NBUF; i++) if(op->state[i] == 1) { s = i; break; }
+      if(s >= 0 || op->done) break;
+      pthread_cond_wait(&op->cv, &op->mu);
+    }
+    if(s < 0) { pthread_mutex_unlock(&op->mu); return NULL; }
+    op->state[s] = 2;
+    pthread_mutex_unlock(&op->mu);
+    size_t at = 0; int err = 0;
+    while(at < op->nbytes[s]) {
+      ssize_t w = pwrite(op->fd, op->buf[s] + at, op->nbytes[s] - at, op->off[s] + (off_t)at);
+      if(w <= 0) { if(w < 0 && errno == EINTR) continue; err = 1; break; }
+      at += (size_t)w;
+    }
+    pthread_mutex_lock(&op->mu);
+    if(err) op->err = 1;
+    op->state[s] = 0;
+    pthread_cond_broadcast(&op->cv);
+    pthread_mutex_unlock(&op->mu);
+  }
+}
+static bool write_records_parallel(mcx_graph *g, FILE *fh, uint64_t nrec, uint32_t rec_bytes)
+{
+  if(fflush(fh) != 0) return false;
+  const off_t base = ftello(fh);
+  if(base < 0) return false;
+  OutPipe op; memset(&op, 0, sizeof(op));
+  op.fd = fileno(fh);
+  for(int i = 0; i < OUT_NBUF; i++)
+    if(mcx_host_alloc((void **)&op.buf[i], OUT_CHUNK) != MCX_OK) { while(i-- > 0) mcx_host_free(op.buf[i]); return false; }
+  pthread_mutex_init(&op.mu, NULL); pthread_cond_init(&op.cv, NULL);
+  pthread_t th[OUT_NBUF];
+  for(int i = 0; i < OUT_NBUF; i++) if(pthread_create(&th[i], NULL, out_writer, &op) != 0) mcx_die("Cannot start a thread");
+  const uint64_t chunk_recs = OUT_CHUNK / rec_bytes;
+  for(uint64_t at = 0; at < nrec; at += chunk_recs) {
+    const uint64_t n = nrec - at < chunk_recs ? nrec - at : chunk_recs;
+    int s = -1;
+    pthread_mutex_lock(&op.mu);
+    for(;;) {
+      for(int i = 0; i < OUT_NBUF; i++) if(op.state[i] == 0) { s = i; break; }
+      if(s >= 0) break;
+      pthread_cond_wait(&op.cv, &op.mu);
+    }
+    pthread_mutex_unlock(&op.mu);
+    int r = mcx_graph_export_read(g, at, n, op.buf[s]);
+    if(r) die_mcx(r, "mcx_graph_export_read");
+    pthread_mutex_lock(&op.mu);
+    op.nbytes[s] = (size_t)(n * rec_bytes); op.off[s] = base + (off_t)(at * rec_bytes); op.state[s] = 1;
+    pthread_cond_broadcast(&op.cv);
+    pthread_mutex_unlock(&op.mu);
+  }
+  pthread_mutex_lock(&op.mu); op.done = true; pthread_cond_broadcast(&op.cv); pthread_mutex_unlock(&op.mu);
+  for(int i = 0; i < OUT_NBUF; i++) pthread_join(th[i], NULL);
+  for(int i = 0; i < OUT_NBUF; i++) mcx_host_free(op.buf[i]);
+  pthread_mutex_destroy(&op.mu); pthread_cond_destroy(&op.cv);
+  if(op.err) mcx_die("Cannot write to file");
+  if(fseeko(fh, base + (off_t)(nrec * rec_bytes), SEEK_SET) != 0) mcx_die("Cannot write to file");
+  return true;
+}
+
 static int ctx_build(int argc, char **argv)
 {
   size_t i, s, t;
@@ -498,15 +574,18 @@ static int ctx_build(int argc, char **argv)
   r = mcx_graph_export_begin(g, sort_kmers ? 1 : 0, &nrec, &rec_bytes);
   if(r) die_mcx(r, "mcx_graph_export_begin");
   mcx_phase("export: compact + sort");
-  size_t chunk_recs = (64u << 20) / rec_bytes;
-  char *buf = malloc(chunk_recs * rec_bytes);
-  for(uint64_t at = 0; at < nrec; at += chunk_recs) {
-    uint64_t n = nrec - at < chunk_recs ? nrec - at : chunk_recs;
-    r = mcx_graph_export_read(g, at, n, buf);
-    if(r) die_mcx(r, "mcx_graph_export_read");
-    if(fwrite(buf, rec_bytes, n, fh) != n) mcx_die("Cannot write to file");
+  const bool big_regular = fh != stdout && (uint64_t)nrec * rec_bytes >= (256u << 20);
+  if(!big_regular || !write_records_parallel(g, fh, nrec, rec_bytes)) {
+    size_t chunk_recs = (64u << 20) / rec_bytes;
+    char *buf = malloc(chunk_recs * rec_bytes);
+    for(uint64_t at = 0; at < nrec; at += chunk_recs) {
+      uint64_t n = nrec - at < chunk_recs ? nrec - at : chunk_recs;
+      r = mcx_graph_export_read(g, at, n, buf);
+      if(r) die_mcx(r, "mcx_graph_export_read");
+      if(fwrite(buf, rec_bytes, n, fh) != n) mcx_die("Cannot write to file");
+    }
+    free(buf);
   }
-  free(buf);
   mcx_graph_export_end(g);
   if(fh != stdout) fclose(fh); else fflush(fh);
   mcx_phase("export: D2H + write");
