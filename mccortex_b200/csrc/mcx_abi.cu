@@ -54,7 +54,7 @@ struct mcx_graph {
   uint8_t *d_pcr; size_t d_pcr_bytes; // --remove-pcr: device copy of the batch being filtered
   bool sharded;  // front table holds records of keys owned by other shards: only mcx_graph_flush_sharded may empty it
   // MCX_SPILL=1 (k <= 31, front table on): the fused kernel's parked pass appends big-table work to a tuple bin
-  // and kernel C inserts it right after the launch (mcx_spill_push, mcx_build.cu).  One bin per staging slot
+  // and kernel C inserts it right after the launch (FusedSink::drain, mcx_build.cu).  One bin per staging slot
   // plus one (index MCX_NSTAGE) for launches on the primary stream.
   bool spill_on;
   uint64_t spill_span;                  // positions per launch on the primary stream when spilling
@@ -322,7 +322,7 @@ static int front_guard(mcx_graph *g, uint64_t positions)
 }
 
 // spill bin `slot` (a staging slot, or MCX_NSTAGE for the primary stream), allocated on first use: room for
-// one tuple per 8 positions of the largest launch it serves (the bench workload parks 3.5 % of its
+// one slot per 8 positions of the largest launch it serves (every PARKED item gets a slot; the bench workload parks ~10 % of its
 // occurrences; what does not fit is inserted inline by the kernel), MCX_SPILL_CAP=<tuples> overrides
 static cudaError_t ensure_spill(mcx_graph *g, int slot)
 {

@@ -64,6 +64,8 @@ template <int W> struct McxSlowQueue {
   uint64_t key[MCX_QCAP(W) * W];
   uint8_t emask[MCX_QCAP(W)];
   uint32_t n;
+  uint32_t spill_ok;                 // this drain's reservation fits the spill bin
+  unsigned long long spill_base;     // first bin slot of this drain's reservation (one slot per parked item)
 };
 // the queue lives in dynamic shared memory (static + dynamic exceeds the 48 KB static limit)
 extern __shared__ __align__(16) unsigned char mcx_dyn_smem[];
@@ -172,28 +174,15 @@ static __host__ __device__ __forceinline__ McxTupleBins mcx_no_bins()
   return b;
 }
 
-// Single-GPU spill.  A parked occurrence the front table cannot absorb (an error k-mer, mostly: seen once or
-// twice) needs Lookup3 + a random DRAM sector of the big table + CAS + RED: three dependent round trips, one
-// item per thread, while the CTA's hot pass waits (ablation, profiles/r1g_experiments.txt: ~45 % of the fused
-// kernel's time for 3.5 % of the occurrences).  With a spill bin the occurrence leaves as a (key, meta) tuple --
-// one coalesced 12-byte store -- and kernel C inserts the bin right after the launch with every thread of the
-// chip holding one probe in flight.  Returns false when the bin is full: the caller then inserts inline, so a
-// bin of any size is correct.
-template <int W>
-__device__ __forceinline__ bool mcx_spill_push(const McxTupleBins &b, const McxKmer<W> &key, uint32_t meta)
-{
-  const uint32_t act = __activemask(), lane = threadIdx.x & 31u, leader = __ffs(act) - 1u;
-  unsigned long long base = 0;
-  if(lane == leader) base = atomicAdd(&b.cursor[0], (unsigned long long)__popc(act));
-  base = __shfl_sync(act, base, leader);
-  const uint64_t at = base + __popc(act & ((1u << lane) - 1u));
-  if(at >= b.cap) return false;
-  uint64_t *kd = b.keys[0] + at * W;
-#pragma unroll
-  for(int w = 0; w < W; w++) kd[w] = key.b[w];
-  b.meta[0][at] = meta;
-  return true;
-}
+// Single-GPU spill (experiment, MCX_SPILL=1).  A parked occurrence the front table cannot absorb (an error k-mer,
+// mostly: seen once or twice) needs Lookup3 + a random DRAM sector of the big table + CAS + RED: dependent round
+// trips, one item per thread, while the CTA's hot pass waits.  With a spill bin it leaves as a (key, meta) tuple and
+// kernel C inserts the bin right after the launch with every thread of the chip holding one probe in flight.
+// One reservation per drain: thread 0 takes n slots (one per parked item, item i -> slot base + i) with ONE atomic
+// on the bin's cursor -- a cursor bumped per tuple serialises on one L2 address (first version: 153 ms per step
+// against 120, profiles/r1k_exp_spill.txt).  Items the front table absorbs leave meta = 0 in their slot, which
+// kernel C skips.  A reservation that does not fit the bin makes the whole drain insert inline, so a bin of any
+// size is correct.
 
 template <int W, int G> struct FusedSink { // G = probe loads kept in flight per thread
   McxTable t; uint32_t colour; bool may_saturate;
@@ -262,12 +251,21 @@ template <int W, int G> struct FusedSink { // G = probe loads kept in flight per
   // the next chunk may not fit (evaluated per thread just before the step barrier, OR-reduced there)
   __device__ __forceinline__ bool should_drain() const { return q->n > MCX_QCAP(W) - MCX_T; }
   // one parked occurrence: front table (claim / edge bit), else the big table
-  __device__ __forceinline__ void slow(McxKmer<W> key, uint32_t emask, uint64_t &novel, uint32_t &full)
+  // spill_at: slot of the spill bin reserved for this item, or ~0 (insert inline)
+  __device__ __forceinline__ void slow(McxKmer<W> key, uint32_t emask, uint64_t &novel, uint32_t &full, uint64_t spill_at = ~0ull)
   {
     if(W == 1 && t.front_set_bits) {
-      if(mcx_front_add_slow(t, key.b[0], emask)) return; // absorbed by the front table
+      if(mcx_front_add_slow(t, key.b[0], emask)) { // absorbed by the front table
+        if(spill_at != ~0ull) bins.meta[0][spill_at] = 0u;
+        return;
+      }
     }
-    if(bins.spill && mcx_spill_push<W>(bins, key, (1u << 8) | emask)) return; // kernel C inserts it after the launch
+    if(spill_at != ~0ull) { // kernel C inserts it after the launch
+#pragma unroll
+      for(int w = 0; w < W; w++) bins.keys[0][spill_at * W + w] = key.b[w];
+      bins.meta[0][spill_at] = (1u << 8) | emask;
+      return;
+    }
     uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
     if(bins.nparts > 1u) {
       const uint32_t d = mcx_owner(hc, bins.nparts);
@@ -281,11 +279,25 @@ template <int W, int G> struct FusedSink { // G = probe loads kept in flight per
   __device__ __forceinline__ void drain(uint64_t &novel, uint32_t &full)
   {
     const uint32_t n = q->n;
+    uint64_t sbase = ~0ull;
+    if(bins.spill) { // (launch-uniform)
+      if(threadIdx.x == 0) {
+        const unsigned long long base = n ? atomicAdd(&bins.cursor[0], (unsigned long long)n) : 0ull;
+        q->spill_base = base; q->spill_ok = (n && base + n <= bins.cap) ? 1u : 0u;
+      }
+      __syncthreads();
+      if(q->spill_ok) sbase = q->spill_base;
+      else if(n) {
+        // the part of a reservation that does not fit still lies below the count kernel C will read: empty it
+        const unsigned long long base = q->spill_base;
+        for(uint32_t i = threadIdx.x; i < n && base + i < bins.cap; i += blockDim.x) bins.meta[0][base + i] = 0u;
+      }
+    }
     for(uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
       McxKmer<W> key;
 #pragma unroll
       for(int w = 0; w < W; w++) key.b[w] = q->key[i * W + w];
-      slow(key, q->emask[i], novel, full);
+      slow(key, q->emask[i], novel, full, sbase == ~0ull ? ~0ull : sbase + i);
     }
   }
 };
@@ -556,6 +568,7 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_insert_tuples_kernel(const
 #pragma unroll
     for(int w = 0; w < W; w++) key.b[w] = keys[i * W + w];
     const uint32_t m = meta[i];
+    if(m == 0u) continue; // nothing to add (an empty slot of a spill reservation; no sender emits such a tuple)
     uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
     int r = mcx_table_add<W>(big, key, hc, hb, colour, m & 0xFFu, m >> 8, may_saturate != 0);
     n_novel += (r == 1); full |= (r == 2); n_kmers += m >> 8;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# MCX_SPILL experiment: parity test of the spill path, then the N=1 bench with and without it
+# MCX_SPILL experiment: parity test of the spill path, then the N=1 bench with it (baseline: profiles/r1j_bench_n1.json)
 set -u
 mkdir -p gpurun_out
 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "spill" > gpurun_out/pytest_spill.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_spill.log
@@ -16,6 +16,10 @@ except Exception as e:
     print("$name: no result", e)
 PY
 }
-run spill_1024 MCX_SPILL=1
-run spill_256 MCX_SPILL=1 MCX_SPILL_SPAN_MB=256
-run spill_one MCX_SPILL=1 MCX_SPILL_SPAN_MB=3584 MCX_SPILL_CAP=300000000
+for v in "$@"; do
+  case $v in
+    s1024) run spill2_1024 MCX_SPILL=1 ;;
+    s3584) run spill2_3584 MCX_SPILL=1 MCX_SPILL_SPAN_MB=3584 ;;
+    base) run base MCX_SPILL=0 ;;
+  esac
+done
