@@ -118,10 +118,19 @@ extern McxGraphSource mcx_graph_source;
  * to *stats.  Returns 0, or the MCX_ERR_* that stopped the load. */
 int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats);
 
-/* seq_ingest_par.c: the same for a regular, uncompressed FASTA / one-read-per-line file of >= 32 MB, parsed by
+/* seq_ingest_par.c: the same for a regular, uncompressed FASTA / FASTQ / one-read-per-line file of >= 32 MB, parsed by
  * several threads (MCX_PARSE_THREADS, default min(cores, 16); 1 = off).  Returns false when the file is not
  * eligible (then nothing was done); else *rc is what mcx_load_seq_file would have returned. */
-bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats, int *rc);
+typedef struct { int qmin, qmax; size_t qcount, bcount; } McxQStat; /* quality range of the first reads (seq_file.h:636-682) */
+uint8_t mcx_guess_fq_offset(const McxQStat *qs);                    /* seq_guess_fastq_format + FASTQ_OFFSET */
+typedef struct {
+  bool resume; size_t offset;   /* FASTQ that stops being strict: the sequential reader continues at this file offset */
+  mcx_graph *g;                 /* the graph, if it was obtained from mcx_graph_source meanwhile */
+  McxQStat qs; bool any_qual, offset_known; uint8_t fq_offset;
+  uint64_t nreads;
+} McxParResume;
+bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats, int *rc,
+                           McxParResume *resume);
 
 /* One task with --remove-pcr in force (build_graph_from_reads_mt with remove_pcr_dups): sf2 != NULL for a --seq2
  * pair, interleaved for --seqi (consecutive reads whose names match are a pair), else single-end.  Reads and

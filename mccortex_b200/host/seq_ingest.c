@@ -119,7 +119,7 @@ static inline void chomp_from(Buf *b, size_t floor_len)
 static inline bool is_space(int c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
 /* ---- loader state ---------------------------------------------------------------- */
-typedef struct { int qmin, qmax; size_t qcount, bcount; } QStat;
+typedef McxQStat QStat;
 typedef struct { mcx_read_batch b; char *seq, *qual; } PendingBatch; /* parsed before the graph existed */
 typedef struct {
   mcx_graph *g; const McxLoadPrefs *prefs; mcx_load_stats *stats;
@@ -141,7 +141,7 @@ typedef struct {
 
 /* FASTQ ASCII offset from the quality range of the first reads, exactly the decision list of
  * seq_guess_fastq_format (libs/seq_file/seq_file.h:666-682) + FASTQ_OFFSET (:127) */
-static uint8_t guess_fq_offset(const QStat *L)
+uint8_t mcx_guess_fq_offset(const McxQStat *L)
 {
   static const int OFFS[6] = {33, 33, 64, 64, 64, 33};
   int fmt, mn = L->qmin, mx = L->qmax;
@@ -166,7 +166,7 @@ static bool prepare_batch(Loader *L, mcx_read_batch *b)
   if(L->prefs->fq_cutoff && L->any_qual) {
     /* build_graph.c:202-207: the ASCII offset is added only when a cut-off is set */
     if(!L->offset_known) {
-      L->fq_offset = L->prefs->fq_offset ? L->prefs->fq_offset : guess_fq_offset(&L->qs[0]);
+      L->fq_offset = L->prefs->fq_offset ? L->prefs->fq_offset : mcx_guess_fq_offset(&L->qs[0]);
       L->offset_known = true;
       if(L->fq_offset + L->prefs->fq_cutoff >= 127) { L->err = MCX_ERR_UNSUPPORTED; L->lines.len = L->qlines.len = 0; return false; }
     }
@@ -325,18 +325,30 @@ static int read_plain(McxSeqFile *sf, Loader *L)
 
 int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats)
 {
-  { int rc = 0; if(mcx_load_seq_file_par(g, sf, prefs, stats, &rc)) return rc; } /* big uncompressed FASTA / plain files */
+  /* big uncompressed files: several threads (seq_ingest_par.c); a FASTQ file that stops being strictly
+   * four lines per record comes back with `resume` set: the rest of it is read here */
+  McxParResume pr;
+  { int rc = 0; if(mcx_load_seq_file_par(g, sf, prefs, stats, &rc, &pr)) return rc; }
   Loader L; memset(&L, 0, sizeof(L));
   L.g = g; L.prefs = prefs; L.stats = stats; L.qs[0].qmin = L.qs[1].qmin = 0x7fffffff;
   buf_reserve(&L.lines, MCX_BATCH_BYTES + (1u << 20));
   buf_reserve(&L.qual, 1u << 16);
 
-  mcx_status("[seq] Parsing sequence file %s", sf->path);
+  if(!pr.resume) mcx_status("[seq] Parsing sequence file %s", sf->path);
 
   /* format sniff, seq_file.h:311-323 */
   int c, s = 0;
   int (*reader)(McxSeqFile *, Loader *) = NULL;
-  while((c = sgetc(sf)) != -1 && is_space(c)) if(c != '\n') sreadline(sf, NULL);
+  if(pr.resume) {
+    if(pr.g) L.g = pr.g;
+    L.qs[0] = pr.qs; L.any_qual = pr.any_qual; L.offset_known = pr.offset_known; L.fq_offset = pr.fq_offset;
+    L.nreads_total = pr.nreads;
+    if(gzseek(sf->gz, (z_off_t)pr.offset, SEEK_SET) < 0) mcx_die("Cannot seek in %s", sf->path);
+    sf->in_len = sf->in_pos = 0; sf->eof = false;
+    while((s = read_fastq(sf, &L)) > 0 && !L.err) {}
+    c = -1;
+  }
+  else while((c = sgetc(sf)) != -1 && is_space(c)) if(c != '\n') sreadline(sf, NULL);
   if(c != -1) {
     reader = c == '@' ? read_fastq : (c == '>' ? read_fasta : read_plain);
     sf->in_pos--; /* ungetc: the byte came from the current buffer */
@@ -396,8 +408,8 @@ static void flush_batch_pcr(Loader *L, size_t n)
     b.colour = L->prefs->colour; b.hp_cutoff = L->prefs->hp_cutoff;
     if(L->prefs->fq_cutoff && L->any_qual) {
       if(!L->offset_known) {
-        uint8_t o1 = L->prefs->fq_offset ? L->prefs->fq_offset : guess_fq_offset(&L->qs[0]), o2 = o1;
-        if(!L->prefs->fq_offset && L->qs[1].bcount) o2 = guess_fq_offset(&L->qs[1]);
+        uint8_t o1 = L->prefs->fq_offset ? L->prefs->fq_offset : mcx_guess_fq_offset(&L->qs[0]), o2 = o1;
+        if(!L->prefs->fq_offset && L->qs[1].bcount) o2 = mcx_guess_fq_offset(&L->qs[1]);
         /* one threshold per batch: files of one pair with different ASCII offsets are not supported */
         if(o1 != o2 && o1 && o2) mcx_die("Paired files with different FASTQ offsets (%u, %u) are not supported", o1, o2);
         L->fq_offset = o1 ? o1 : o2;

@@ -12,8 +12,15 @@
  *   FASTA  at a '>' that follows a '\n'.  The sequential reader only ever looks for '>' at the start of a line,
  *          header lines are consumed whole, so such a byte is a record start whatever precedes it.
  *   plain  after any '\n' (every line is a record or is skipped on its own).
- * FASTQ ('@' also starts quality lines), gzip, stdin, --remove-pcr (order matters) and small files keep the
- * sequential reader.
+ *   FASTQ  candidates are '@' lines whose next-but-one line starts with '+', but '@' may also start a quality line
+ *          and the sequential reader accepts multi-line records, so a candidate is only a guess.  It is made
+ *          certain by induction: workers parse STRICT records only ('@' line, one sequence line, '+' line, one
+ *          quality line at least as long as the sequence, next byte '@' or the end) -- on those the sequential reader
+ *          (read_fastq, seq_file.h:245-272) does exactly the same -- and the calling thread accepts segment s only
+ *          if every earlier segment ended on its cut with a complete record.  The first record that is not strict
+ *          (or a segment that does not end on its cut) hands the REST OF THE FILE, from that record on, to the
+ *          sequential reader.
+ * gzip, stdin, --remove-pcr (order matters) and small files keep the sequential reader.
  */
 #include "mcx_host.h"
 #include <fcntl.h>
@@ -30,14 +37,17 @@
 
 typedef struct {
   char *b; size_t len, cap;   /* LINES bytes of one segment */
+  char *q;                    /* FASTQ with a quality cut-off: quality bytes parallel to b (cap bytes too) */
   uint64_t nreads;
+  size_t dev_at;              /* FASTQ: file offset of the first record that is not strict, or SIZE_MAX */
   int state;                  /* 0 free, 1 being filled, 2 full */
   size_t seg;                 /* which segment it holds */
 } SegBuf;
 
+enum { FMT_FASTA, FMT_PLAIN, FMT_FASTQ };
 typedef struct {
   const unsigned char *data; size_t size;
-  bool fasta;
+  int fmt; bool want_qual;
   size_t nseg; size_t *cut;   /* segment i = [cut[i], cut[i+1]) */
   size_t next_seg;            /* next segment to hand to a worker */
   SegBuf *bufs; size_t nbufs;
@@ -95,6 +105,52 @@ static void parse_plain_range(const unsigned char *d, size_t p, size_t end, SegB
   }
 }
 
+/* one STRICT FASTQ record at *p (see the header of this file); end = the segment's cut (or the file's end, then
+ * at_eof).  Returns false, leaving *p alone, if the record is not strict or does not end at or before `end`. */
+typedef struct { const unsigned char *seq, *qual; size_t seqlen, quallen; } FqRec;
+static bool fq_next(const unsigned char *d, size_t *pp, size_t end, bool at_eof, FqRec *r)
+{
+  size_t p = *pp;
+  if(d[p] != '@') return false;
+  const unsigned char *nl = memchr(d + p + 1, '\n', end - p - 1);
+  if(!nl) return false;
+  p = (size_t)(nl - d) + 1;
+  if(p >= end || d[p] == '+' || d[p] == '\r' || d[p] == '\n') return false; /* empty line / no sequence: not strict */
+  nl = memchr(d + p, '\n', end - p);
+  if(!nl) return false;
+  r->seq = d + p; r->seqlen = (size_t)(nl - (d + p));
+  while(r->seqlen && r->seq[r->seqlen - 1] == '\r') r->seqlen--; /* (the first byte is not a CR: seqlen >= 1) */
+  p = (size_t)(nl - d) + 1;
+  if(p >= end || d[p] != '+') return false;
+  nl = memchr(d + p, '\n', end - p);
+  if(!nl) return false;
+  p = (size_t)(nl - d) + 1;
+  if(p >= end) return false;             /* no quality line */
+  nl = memchr(d + p, '\n', end - p);
+  if(!nl && !at_eof) return false;       /* the quality line crosses the cut: the cut was not a record start */
+  r->qual = d + p; r->quallen = nl ? (size_t)(nl - (d + p)) : end - p;
+  while(r->quallen && (r->qual[r->quallen - 1] == '\r')) r->quallen--;
+  if(r->quallen < r->seqlen) return false; /* the sequential reader would go on reading quality lines */
+  p = nl ? (size_t)(nl - d) + 1 : end;
+  if(p < end && d[p] != '@') return false; /* junk between records */
+  *pp = p;
+  return true;
+}
+
+static void parse_fastq_range(const unsigned char *d, size_t p, size_t end, bool at_eof, bool want_qual, SegBuf *o)
+{
+  FqRec r;
+  while(p < end) {
+    const size_t rec_at = p;
+    if(!fq_next(d, &p, end, at_eof, &r)) { o->dev_at = rec_at; return; }
+    memcpy(o->b + o->len, r.seq, r.seqlen);
+    if(want_qual) { memcpy(o->q + o->len, r.qual, r.seqlen); o->q[o->len + r.seqlen] = 0x7F; }
+    o->len += r.seqlen;
+    o->b[o->len++] = '\n';
+    o->nreads++;
+  }
+}
+
 static void *par_worker(void *arg)
 {
   ParState *ps = arg;
@@ -109,17 +165,20 @@ static void *par_worker(void *arg)
     }
     if(!o) { pthread_mutex_unlock(&ps->mu); return NULL; }
     const size_t seg = ps->next_seg++;
-    o->state = 1; o->seg = seg; o->len = 0; o->nreads = 0;
+    o->state = 1; o->seg = seg; o->len = 0; o->nreads = 0; o->dev_at = SIZE_MAX;
     pthread_mutex_unlock(&ps->mu);
 
     const size_t a = ps->cut[seg], b = ps->cut[seg + 1];
     if(o->cap < b - a + 2) {
-      free(o->b);
+      free(o->b); free(o->q); o->q = NULL;
       o->cap = b - a + 2 + (1u << 16);
       o->b = malloc(o->cap);
-      if(!o->b) mcx_die("Out of memory");
+      if(ps->want_qual) o->q = malloc(o->cap);
+      if(!o->b || (ps->want_qual && !o->q)) mcx_die("Out of memory");
     }
-    if(ps->fasta) parse_fasta_range(ps->data, a, b, o); else parse_plain_range(ps->data, a, b, o);
+    if(ps->fmt == FMT_FASTA) parse_fasta_range(ps->data, a, b, o);
+    else if(ps->fmt == FMT_PLAIN) parse_plain_range(ps->data, a, b, o);
+    else parse_fastq_range(ps->data, a, b, b == ps->size, ps->want_qual, o);
 
     pthread_mutex_lock(&ps->mu);
     o->state = 2;
@@ -128,8 +187,11 @@ static void *par_worker(void *arg)
   }
 }
 
-bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats, int *rc)
+bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats, int *rc,
+                           McxParResume *resume)
 {
+  memset(resume, 0, sizeof(*resume));
+  resume->qs.qmin = 0x7fffffff;
   const char *path = mcx_seq_path(sf);
   long nthreads = sysconf(_SC_NPROCESSORS_ONLN);
   if(nthreads > 16) nthreads = 16;
@@ -156,12 +218,28 @@ bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *pre
       if(d[p0] != '\n') { const unsigned char *nl = memchr(d + p0, '\n', size - p0); p0 = nl ? (size_t)(nl - d) + 1 : size; }
       else p0++;
     }
-    ok = p0 < size && d[p0] != '@';
+    ok = p0 < size;
   }
   if(!ok) { munmap((void *)d, size); return false; }
 
   ParState ps; memset(&ps, 0, sizeof(ps));
-  ps.data = d; ps.size = size; ps.fasta = d[p0] == '>';
+  ps.data = d; ps.size = size; ps.fmt = d[p0] == '>' ? FMT_FASTA : (d[p0] == '@' ? FMT_FASTQ : FMT_PLAIN);
+  ps.want_qual = ps.fmt == FMT_FASTQ && prefs->fq_cutoff != 0;
+  McxQStat qs = resume->qs;
+  if(ps.fmt == FMT_FASTQ) {
+    /* quality range of the first reads (until 1000 bases have been seen), exactly as the sequential reader collects
+     * it (end_read, seq_ingest.c) -- it decides the ASCII offset at the first batch.  If the file stops being strict
+     * before that, it is not for this path at all. */
+    size_t p = p0; FqRec r;
+    while(p < size && qs.bcount < 1000) {
+      if(!fq_next(d, &p, size, true, &r)) { munmap((void *)d, size); return false; }
+      if(r.quallen) {
+        size_t lim = 1000 - qs.qcount, n = r.quallen < lim ? r.quallen : lim;
+        for(size_t i = 0; i < n; i++) { int q = (signed char)r.qual[i]; if(q > qs.qmax) qs.qmax = q; if(q < qs.qmin) qs.qmin = q; }
+        qs.bcount += r.seqlen; qs.qcount += r.quallen;
+      } else qs.bcount += r.seqlen;
+    }
+  }
   /* cuts */
   size_t max_seg = (size - p0) / seg_bytes + 2;
   ps.cut = malloc((max_seg + 1) * sizeof(size_t));
@@ -175,8 +253,13 @@ bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *pre
       const unsigned char *nl = memchr(d + q - 1, '\n', size - (q - 1));
       if(!nl) { q = size; break; }
       q = (size_t)(nl - d) + 1;
-      if(q >= size || !ps.fasta || d[q] == '>') break;
-      q++; /* a sequence line: keep looking */
+      if(q >= size || ps.fmt == FMT_PLAIN || (ps.fmt == FMT_FASTA && d[q] == '>')) break;
+      if(ps.fmt == FMT_FASTQ && d[q] == '@') {
+        /* a record start if the next-but-one line starts with '+' (a guess: verified when the segments are consumed) */
+        const unsigned char *l1 = memchr(d + q, '\n', size - q), *l2 = l1 ? memchr(l1 + 1, '\n', size - (size_t)(l1 + 1 - d)) : NULL;
+        if(l2 && (size_t)(l2 + 1 - d) < size && l2[1] == '+') break;
+      }
+      q++; /* not a place to cut: keep looking */
     }
     ps.cut[++ps.nseg] = q;
     if(q >= size) break;
@@ -192,6 +275,8 @@ bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *pre
   for(size_t i = 0; i < nth; i++) if(pthread_create(&th[i], NULL, par_worker, &ps) != 0) mcx_die("Cannot start a thread");
 
   int err = 0; uint64_t nreads_total = 0;
+  bool any_qual = false, offset_known = false; uint8_t fq_offset = 0;
+  size_t resume_at = SIZE_MAX;
   for(size_t seg = 0; seg < ps.nseg; seg++) {
     SegBuf *o = NULL;
     pthread_mutex_lock(&ps.mu);
@@ -207,20 +292,38 @@ bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *pre
       mcx_read_batch b; memset(&b, 0, sizeof(b));
       b.seq = o->b; b.nbytes = o->len; b.layout = MCX_LAYOUT_LINES; b.mem = MCX_MEM_HOST;
       b.colour = prefs->colour; b.hp_cutoff = prefs->hp_cutoff; b.must_exist = prefs->must_exist;
-      int r = mcx_graph_add_reads(g, &b);
-      if(r != MCX_OK) err = r;
+      if(ps.fmt == FMT_FASTQ) any_qual = true; /* a strict record has a quality string */
+      if(ps.want_qual) {
+        /* build_graph.c:202-207 + seq_file.h:636-682, as prepare_batch of seq_ingest.c */
+        if(!offset_known) {
+          fq_offset = prefs->fq_offset ? prefs->fq_offset : mcx_guess_fq_offset(&qs);
+          offset_known = true;
+          if(fq_offset + prefs->fq_cutoff >= 127) err = MCX_ERR_UNSUPPORTED;
+        }
+        b.qual = o->q; b.fq_cutoff = (uint8_t)(prefs->fq_cutoff + fq_offset);
+      }
+      if(!err) { int r = mcx_graph_add_reads(g, &b); if(r != MCX_OK) err = r; }
     }
     nreads_total += o->nreads;
+    const size_t dev_at = o->dev_at;
     pthread_mutex_lock(&ps.mu);
     o->state = 0;
+    if(dev_at != SIZE_MAX) ps.next_seg = ps.nseg; /* no more segments: the sequential reader takes over */
     pthread_cond_broadcast(&ps.cv);
     pthread_mutex_unlock(&ps.mu);
+    if(dev_at != SIZE_MAX) { resume_at = dev_at; break; }
   }
   for(size_t i = 0; i < nth; i++) pthread_join(th[i], NULL);
-  for(size_t i = 0; i < ps.nbufs; i++) free(ps.bufs[i].b);
+  for(size_t i = 0; i < ps.nbufs; i++) { free(ps.bufs[i].b); free(ps.bufs[i].q); }
   free(ps.bufs); free(ps.cut);
   pthread_mutex_destroy(&ps.mu); pthread_cond_destroy(&ps.cv);
   munmap((void *)d, size);
+  if(resume_at != SIZE_MAX && !err) {
+    resume->resume = true; resume->offset = resume_at; resume->g = g;
+    resume->qs = qs; resume->any_qual = any_qual; resume->offset_known = offset_known; resume->fq_offset = fq_offset;
+    resume->nreads = nreads_total;
+    return false;
+  }
   mcx_phase("  parsed + submitted");
   if(!g && mcx_graph_source.wait) g = mcx_graph_source.wait(mcx_graph_source.ctx);
 

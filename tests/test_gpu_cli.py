@@ -276,8 +276,19 @@ def test_cli_parallel_ingest_and_background_device_start(tmp_path, oracle):
                 f.write(r[j:j + 60] + ("\r\n" if i % 7 == 0 else "\n"))
     plain = tmp_path / "b.txt"
     plain.write_text("\n".join(r for r in reads if r) + "\n")
-    want, _ = oracle.build_ctx(31, [("fa", [str(fa)]), ("plain", [str(plain)])])
-    args = ["-q", "-f", "-m", "1G", "-n", "2M", "-k", "31", "-S", "-s", "fa", "-1", str(fa), "-s", "plain", "-1", str(plain)]
+    # FASTQ with a quality cut-off: strict records go to the worker threads, the multi-line record near the end
+    # hands the rest of the file back to the sequential reader
+    fq = tmp_path / "c.fq"
+    with open(fq, "w") as f:
+        for i, r in enumerate(x for x in reads if x):
+            q = "".join(rng.choice("!#+5@IIIIII") for _ in r)
+            if i == 2500 and len(r) > 10:
+                f.write("@r%d\n%s\n%s\n+\n%s\n%s\n" % (i, r[:7], r[7:], q[:7], q[7:]))
+            else:
+                f.write("@r%d\n%s\n+\n%s\n" % (i, r, q))
+    want, _ = oracle.build_ctx(31, [("fa", [str(fa)]), ("plain", [str(plain)]), ("fq", [dict(path=str(fq), fq_cutoff=12)])])
+    args = ["-q", "-f", "-m", "1G", "-n", "2M", "-k", "31", "-S", "-s", "fa", "-1", str(fa), "-s", "plain", "-1", str(plain),
+            "-s", "fq", "-Q", "12", "-1", str(fq)]
     for env in ({"MCX_PARSE_THREADS": "4", "MCX_PARSE_SEG_BYTES": "5000"}, {"MCX_PARSE_THREADS": "1"}):
         out = tmp_path / "out.ctx"
         _run(args + [str(out)], env=env)

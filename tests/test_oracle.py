@@ -318,3 +318,50 @@ def test_parallel_ingest_matches_sequential_reader(ingest_dump, tmp_path, kind, 
     assert outs[0][0] == outs[1][0]
     assert outs[0][1] == outs[1][1] > 500
     assert outs[1][2] > 10     # the threaded run really was cut into many segments
+
+
+def _fastq(rng, nrec, deviations):
+    """4-line FASTQ with quality lines that often start with '@' or '+', CR LF here and there; `deviations` places
+    records the strict parser must hand back to the sequential reader (multi-line, junk, short / missing quality)"""
+    out = []
+    for i in range(nrec):
+        n = rng.randint(1, 120)
+        seq = "".join(rng.choice("ACGTacgtN") for _ in range(n))
+        qual = "".join(rng.choice("@+IIIIFFF#5<") for _ in range(n + rng.choice([0, 0, 0, 3])))
+        eol = "\r\n" if rng.random() < 0.1 else "\n"
+        kind = deviations.get(i)
+        if kind == "multi" and n > 4:
+            h = n // 2
+            out.append("@r%d\n%s\n%s\n+r%d\n%s\n%s\n" % (i, seq[:h], seq[h:], i, qual[:h], qual[h:]))
+        elif kind == "junk":
+            out.append("@r%d\n%s\n+\n%s\nthis line is skipped\n\n" % (i, seq, qual))
+        elif kind == "short":
+            out.append("@r%d\n%s\n+\n%s\n%s\n" % (i, seq, qual[:n // 2], qual))   # a second quality line is read
+        elif kind == "empty":
+            out.append("@r%d\n\n%s\n+\n%s\n" % (i, seq, qual))
+        else:
+            out.append("@r%d some text%s%s%s+%s%s%s" % (i, eol, seq, eol, eol, qual, eol))
+    return "".join(out)
+
+
+@pytest.mark.parametrize("seg,cut,devs,tail", [(600, 0, {}, ""), (600, 10, {}, ""), (250, 12, {700: "multi"}, ""), (1000, 0, {300: "junk", 900: "multi"}, ""),
+                                               (400, 10, {1500: "short"}, ""), (700, 0, {1100: "empty"}, ""), (500, 10, {}, "@last\nACGTACGT\n+\nIIIIIIII"),
+                                               (500, 0, {}, "@last\nACGTACGT\n+"), (300, 10, {2: "multi"}, "")])
+def test_parallel_fastq_ingest_matches_sequential_reader(ingest_dump, tmp_path, seg, cut, devs, tail):
+    """FASTQ through the multi-threaded ingest: strict 4-line records are parsed by the workers, the first record that is
+    not strict sends the rest of the file to the sequential reader -- sequence bytes, quality bytes, the cut-off
+    (ASCII offset auto-detected) and the read count are those of the sequential reader alone"""
+    rng = random.Random(seg + cut)
+    path = tmp_path / "in.fq"
+    path.write_bytes((_fastq(rng, 2000, devs) + tail).encode())
+    outs = []
+    for threads in (1, 4):
+        env = dict(os.environ, MCX_PARSE_THREADS=str(threads), MCX_PARSE_SEG_BYTES=str(seg), MCX_BATCH_BYTES="3000")
+        pre = str(tmp_path / ("d%d" % threads))
+        r = subprocess.run([ingest_dump, pre, "file", str(cut), "0", "0", "1", str(path)], stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, env=env)
+        info = dict(x.split("=") for x in r.stdout.decode().split())
+        outs.append((open(pre + ".lines", "rb").read(), open(pre + ".qual", "rb").read(), info["fq_cutoff"], info["nreads"],
+                     b"Input error" in r.stderr))
+    assert outs[0] == outs[1]
+    assert int(outs[0][3]) >= 2000
