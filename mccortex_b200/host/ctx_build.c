@@ -310,6 +310,15 @@ static void print_task_stats(const BuildTask *t)
   mcx_status("  num contigs: %s  num kmers: %s novel kmers: %s", a, b, c);
 }
 
+/* one of several files of one colour that are read at the same time */
+typedef struct { pthread_t thread; BuildTask *task; mcx_graph *g; int rc; } FileLoad;
+static void *file_load_main(void *arg)
+{
+  FileLoad *fl = arg;
+  fl->rc = mcx_load_seq_file(fl->g, fl->task->file, &fl->task->prefs, &fl->task->stats);
+  return NULL;
+}
+
 /* the device graph, created on its own thread (see ctx_build) */
 static struct {
   pthread_t thread; bool joined;
@@ -335,6 +344,8 @@ static bool graph_ready(void *ctx) { (void)ctx; return ginit.done != 0; }
 static mcx_graph *graph_wait(void *ctx)
 {
   (void)ctx;
+  static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+  pthread_mutex_lock(&mu); /* several file threads may ask */
   if(!ginit.joined) {
     pthread_join(ginit.thread, NULL); ginit.joined = true;
     if(ginit.rc == MCX_ERR_NO_DEVICE && !ginit.g && !strcmp(ginit.what, "device")) mcx_die("No CUDA device: "CMD" has no CPU fallback");
@@ -343,6 +354,7 @@ static mcx_graph *graph_wait(void *ctx)
     mcx_status("[hasht] Allocating device table with %s entries on GPU %i", a, ginit.device);
     mcx_phase("cuda init + table (joined)");
   }
+  pthread_mutex_unlock(&mu);
   return ginit.g;
 }
 
@@ -526,7 +538,7 @@ static int ctx_build(int argc, char **argv)
    * statistics are credited to the batch's FIRST task, i.e. to that task's colour. */
   /* With --remove-pcr anywhere (ctx_build.c:386-403): one call per run of <= 10 tasks of ONE colour, and the
    * read-start marks are wiped when the colour changes.  The reference reads the files of one call
-   * concurrently; here they are read one after the other, in command-line order. */
+   * concurrently; so does this driver for consecutive files of one colour (not with --remove-pcr: order matters). */
   size_t start, end; uint32_t prev_colour = 0;
   for(start = 0; start < ntasks; start = end) {
     end = start + MAX_IO_THREADS < ntasks ? start + MAX_IO_THREADS : ntasks;
@@ -539,6 +551,32 @@ static int ctx_build(int argc, char **argv)
     }
     mcx_load_stats credited; memset(&credited, 0, sizeof(credited));
     for(t = start; t < end; t++) {
+      /* consecutive files of one colour are read at the same time, like the reader threads of one build_graph() call
+       * (src/basic/async_read_io.c); their counters cannot be told apart, so the totals go to the first of them --
+       * where the reference's own bookkeeping puts them anyway (quirk Q1) */
+      size_t run_end = t + 1;
+      while(!tasks[t].prefs.remove_pcr && run_end < end && !tasks[run_end].prefs.remove_pcr &&
+            tasks[run_end].prefs.colour == tasks[t].prefs.colour) run_end++;
+      if(run_end - t > 1 && !(getenv("MCX_FILE_THREADS") && atoi(getenv("MCX_FILE_THREADS")) == 1)) {
+        FileLoad fl[MAX_IO_THREADS];
+        mcx_ingest.concurrent = true; mcx_ingest.nfiles = (int)(run_end - t);
+        for(size_t i = t; i < run_end; i++) {
+          fl[i - t].task = &tasks[i]; fl[i - t].g = g; fl[i - t].rc = 0;
+          if(pthread_create(&fl[i - t].thread, NULL, file_load_main, &fl[i - t]) != 0) mcx_die("Cannot start a thread");
+        }
+        for(size_t i = t; i < run_end; i++) { pthread_join(fl[i - t].thread, NULL); if(fl[i - t].rc) die_mcx(fl[i - t].rc, "loading sequence"); }
+        mcx_ingest.concurrent = false; mcx_ingest.nfiles = 0;
+        g = graph_wait(NULL);
+        mcx_load_stats st;
+        r = mcx_graph_sync(g, &st);
+        if(r) die_mcx(r, "loading sequence");
+        mcx_add_load_stats(&tasks[t].stats, &st);
+        mcx_phase("sequence files loaded");
+        credited.total_bases_loaded += tasks[t].stats.total_bases_loaded;
+        credited.contigs_parsed += tasks[t].stats.contigs_parsed;
+        t = run_end - 1;
+        continue;
+      }
       if(tasks[t].prefs.remove_pcr)
         r = mcx_load_seq_pcr(g, tasks[t].file, tasks[t].file2, tasks[t].interleaved, &tasks[t].prefs, &tasks[t].stats);
       else

@@ -113,6 +113,13 @@ typedef struct {
 } McxGraphSource;
 extern McxGraphSource mcx_graph_source;
 
+/* several files loaded at once (see seq_ingest.c): submissions are serialised, the caller syncs after the last file */
+#include <pthread.h>
+typedef struct { bool concurrent; pthread_mutex_t lock; int nfiles; } McxIngestShared;
+extern McxIngestShared mcx_ingest;
+int mcx_submit_reads(mcx_graph *g, const mcx_read_batch *b);
+void mcx_add_load_stats(mcx_load_stats *stats, const mcx_load_stats *st);
+
 /* Parse every read of sf (FASTA / FASTQ / plain, sniffed from the first byte like
  * seq_file.h:311-323) and feed the graph in LINES batches.  Stats of this file are ADDED
  * to *stats.  Returns 0, or the MCX_ERR_* that stopped the load. */

@@ -11,6 +11,7 @@
  * SAM/BAM/CRAM input is out of scope (needs htslib).
  */
 #include "mcx_host.h"
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
@@ -20,6 +21,20 @@
  * second thread (CUDA start-up + context take 0.5-1.5 s, as long as parsing a GB of FASTA) and the loader parses
  * ahead meanwhile, keeping up to MCX_RUNAHEAD_BYTES of finished batches until wait() hands the graph over. */
 McxGraphSource mcx_graph_source = {NULL, NULL, NULL};
+
+/* Several files of one colour loaded at the same time (the reference runs one reader thread per file of a
+ * build_graph() call, src/basic/async_read_io.c): the library wants one host thread per graph at a time, so
+ * every submission takes mcx_ingest.lock; the loaders do not sync (the counters are the graph's, not a file's) --
+ * the caller syncs once after the last file and gets the totals of the whole call. */
+McxIngestShared mcx_ingest = {false, PTHREAD_MUTEX_INITIALIZER, 0};
+int mcx_submit_reads(mcx_graph *g, const mcx_read_batch *b)
+{
+  if(!mcx_ingest.concurrent) return mcx_graph_add_reads(g, b);
+  pthread_mutex_lock(&mcx_ingest.lock);
+  int r = mcx_graph_add_reads(g, b);
+  pthread_mutex_unlock(&mcx_ingest.lock);
+  return r;
+}
 #define MCX_RUNAHEAD_BYTES (2048ull << 20)
 
 #define MCX_BATCH_BYTES_DEFAULT (96u << 20)
@@ -182,7 +197,7 @@ static void loader_need_graph(Loader *L)
   if(L->g || !mcx_graph_source.wait) return; /* (g == NULL without a source: the CPU-only test harness) */
   L->g = mcx_graph_source.wait(mcx_graph_source.ctx);
   for(size_t i = 0; i < L->npend; i++) {
-    if(!L->err) { int r = mcx_graph_add_reads(L->g, &L->pend[i].b); if(r != MCX_OK) L->err = r; }
+    if(!L->err) { int r = mcx_submit_reads(L->g, &L->pend[i].b); if(r != MCX_OK) L->err = r; }
     free(L->pend[i].seq); free(L->pend[i].qual);
   }
   free(L->pend); L->pend = NULL; L->npend = L->pend_cap = 0; L->pend_bytes = 0;
@@ -208,7 +223,7 @@ static void flush_batch(Loader *L)
     return;
   }
   loader_need_graph(L);
-  if(!L->err) { int r = mcx_graph_add_reads(L->g, &b); if(r != MCX_OK) L->err = r; }
+  if(!L->err) { int r = mcx_submit_reads(L->g, &b); if(r != MCX_OK) L->err = r; }
   L->lines.len = 0; L->qlines.len = 0;
 }
 
@@ -323,6 +338,18 @@ static int read_plain(McxSeqFile *sf, Loader *L)
   return 1;
 }
 
+void mcx_add_load_stats(mcx_load_stats *stats, const mcx_load_stats *st)
+{
+  stats->total_bases_read += st->total_bases_read;
+  stats->total_bases_loaded += st->total_bases_loaded;
+  stats->contigs_parsed += st->contigs_parsed;
+  stats->num_kmers_loaded += st->num_kmers_loaded;
+  stats->num_kmers_novel += st->num_kmers_novel;
+  stats->num_se_reads += st->num_se_reads;
+  if(st->num_good_reads != UINT64_MAX && stats->num_good_reads != UINT64_MAX) { stats->num_good_reads += st->num_good_reads; stats->num_bad_reads += st->num_bad_reads; }
+  else { stats->num_good_reads = stats->num_bad_reads = UINT64_MAX; }
+}
+
 int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, mcx_load_stats *stats)
 {
   /* big uncompressed files: several threads (seq_ingest_par.c); a FASTQ file that stops being strictly
@@ -360,18 +387,13 @@ int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, m
   loader_need_graph(&L);
   mcx_phase("  submitted");
 
-  mcx_load_stats st;
-  int r = mcx_graph_sync(L.g, &st);
-  if(L.err) r = L.err;
-  stats->total_bases_read += st.total_bases_read;
-  stats->total_bases_loaded += st.total_bases_loaded;
-  stats->contigs_parsed += st.contigs_parsed;
-  stats->num_kmers_loaded += st.num_kmers_loaded;
-  stats->num_kmers_novel += st.num_kmers_novel;
-  stats->num_se_reads += st.num_se_reads;
-  if(st.num_good_reads != UINT64_MAX) { stats->num_good_reads += st.num_good_reads; stats->num_bad_reads += st.num_bad_reads; }
-  else { stats->num_good_reads = stats->num_bad_reads = UINT64_MAX; }
-
+  int r = L.err;
+  if(!mcx_ingest.concurrent) {
+    mcx_load_stats st;
+    r = mcx_graph_sync(L.g, &st);
+    if(L.err) r = L.err;
+    mcx_add_load_stats(stats, &st);
+  }
   char n1[64]; mcx_ulong_to_str(L.nreads_total, n1);
   mcx_status("[seq] Loaded %s reads and 0 reads pairs (file: %s)", n1, sf->path);
   free(L.lines.b); free(L.qual.b); free(L.qlines.b);

@@ -195,6 +195,7 @@ bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *pre
   const char *path = mcx_seq_path(sf);
   long nthreads = sysconf(_SC_NPROCESSORS_ONLN);
   if(nthreads > 16) nthreads = 16;
+  if(mcx_ingest.concurrent && mcx_ingest.nfiles > 1) { nthreads /= mcx_ingest.nfiles; if(nthreads < 2) nthreads = 2; } /* files share the cores */
   if(getenv("MCX_PARSE_THREADS")) nthreads = atol(getenv("MCX_PARSE_THREADS"));
   if(nthreads > PAR_MAX_THREADS) nthreads = PAR_MAX_THREADS;
   size_t seg_bytes = PAR_SEG_BYTES_DEFAULT, min_bytes = PAR_MIN_BYTES;
@@ -302,7 +303,7 @@ bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *pre
         }
         b.qual = o->q; b.fq_cutoff = (uint8_t)(prefs->fq_cutoff + fq_offset);
       }
-      if(!err) { int r = mcx_graph_add_reads(g, &b); if(r != MCX_OK) err = r; }
+      if(!err) { int r = mcx_submit_reads(g, &b); if(r != MCX_OK) err = r; }
     }
     nreads_total += o->nreads;
     const size_t dev_at = o->dev_at;
@@ -327,17 +328,13 @@ bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *pre
   mcx_phase("  parsed + submitted");
   if(!g && mcx_graph_source.wait) g = mcx_graph_source.wait(mcx_graph_source.ctx);
 
-  mcx_load_stats s;
-  int r = mcx_graph_sync(g, &s);
-  if(err) r = err;
-  stats->total_bases_read += s.total_bases_read;
-  stats->total_bases_loaded += s.total_bases_loaded;
-  stats->contigs_parsed += s.contigs_parsed;
-  stats->num_kmers_loaded += s.num_kmers_loaded;
-  stats->num_kmers_novel += s.num_kmers_novel;
-  stats->num_se_reads += s.num_se_reads;
-  if(s.num_good_reads != UINT64_MAX) { stats->num_good_reads += s.num_good_reads; stats->num_bad_reads += s.num_bad_reads; }
-  else { stats->num_good_reads = stats->num_bad_reads = UINT64_MAX; }
+  int r = err;
+  if(!mcx_ingest.concurrent) {
+    mcx_load_stats s;
+    r = mcx_graph_sync(g, &s);
+    if(err) r = err;
+    mcx_add_load_stats(stats, &s);
+  }
   char n1[64]; mcx_ulong_to_str(nreads_total, n1);
   mcx_status("[seq] Loaded %s reads and 0 reads pairs (file: %s)", n1, path);
   *rc = r;

@@ -293,3 +293,39 @@ def test_cli_parallel_ingest_and_background_device_start(tmp_path, oracle):
         out = tmp_path / "out.ctx"
         _run(args + [str(out)], env=env)
         assert open(out, "rb").read() == want, env
+
+
+def test_cli_files_of_one_colour_loaded_concurrently(tmp_path, oracle):
+    """consecutive --seq files of one colour are read by one thread each (gz, FASTQ with a cut-off, FASTA, plain mixed);
+    the table updates commute and the header credits the batch (quirk Q1), so the bytes are those of the oracle's
+    build -- and of the same command with MCX_FILE_THREADS=1 (one file after the other)"""
+    import gzip
+    rng = random.Random(31)
+    genome_reads = rand_reads(rng, 2400, (20, 250), 20000, perr=0.004)
+    files = []
+    for i in range(6):
+        part = genome_reads[i * 400:(i + 1) * 400]
+        if i % 3 == 0:
+            p = tmp_path / ("f%d.fa.gz" % i)
+            with gzip.open(p, "wt") as f:
+                f.write("".join(">r%d\n%s\n" % (j, r) for j, r in enumerate(part)))
+        elif i % 3 == 1:
+            p = tmp_path / ("f%d.fq" % i)
+            p.write_text("".join("@r%d\n%s\n+\n%s\n" % (j, r, "".join(rng.choice("#5III") for _ in r)) for j, r in enumerate(part)))
+        else:
+            p = tmp_path / ("f%d.txt" % i)
+            p.write_text("\n".join(part) + "\n")
+        files.append(str(p))
+    tasks0 = [dict(path=f, fq_cutoff=10) for f in files[:4]]
+    tasks1 = [dict(path=f, fq_cutoff=10) for f in files[4:]]
+    want, _ = oracle.build_ctx(25, [("a", tasks0), ("b", tasks1)])
+    args = ["-q", "-f", "-m", "1G", "-n", "2M", "-k", "25", "-S", "-Q", "10", "-s", "a"]
+    for f in files[:4]:
+        args += ["-1", f]
+    args += ["-s", "b"]
+    for f in files[4:]:
+        args += ["-1", f]
+    for env in ({}, {"MCX_FILE_THREADS": "1"}):
+        out = tmp_path / "out.ctx"
+        _run(args + [str(out)], env=env)
+        assert open(out, "rb").read() == want, env

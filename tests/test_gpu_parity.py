@@ -44,6 +44,7 @@ def test_lines_batch_matches_oracle(M, oracle, reads_small, k):
 def test_offsets_batch_matches_oracle(M, oracle, reads_small, k):
     recs, ost = oracle_records(oracle, reads_small, k)
     g = M.Graph(k, 1, 1 << 20)
+    g.prepare_host()   # mcx_graph_prepare_host: the staging ring up front (optional)
     g.add_reads(reads_small)
     st = g.sync()
     got, n, _ = g.export_records()
