@@ -407,7 +407,9 @@ static bool write_records_parallel(mcx_graph *g, FILE *fh, uint64_t nrec, uint32
   pthread_mutex_init(&op.mu, NULL); pthread_cond_init(&op.cv, NULL);
   pthread_t th[OUT_NBUF];
   for(int i = 0; i < OUT_NBUF; i++) if(pthread_create(&th[i], NULL, out_writer, &op) != 0) mcx_die("Cannot start a thread");
-  const uint64_t chunk_recs = OUT_CHUNK / rec_bytes;
+  uint64_t chunk_recs = OUT_CHUNK / rec_bytes;
+  if(getenv("MCX_OUT_CHUNK_RECS") && atol(getenv("MCX_OUT_CHUNK_RECS")) > 0 && (uint64_t)atol(getenv("MCX_OUT_CHUNK_RECS")) < chunk_recs)
+    chunk_recs = (uint64_t)atol(getenv("MCX_OUT_CHUNK_RECS")); /* tests: many small chunks */
   for(uint64_t at = 0; at < nrec; at += chunk_recs) {
     const uint64_t n = nrec - at < chunk_recs ? nrec - at : chunk_recs;
     int s = -1;
@@ -612,7 +614,9 @@ static int ctx_build(int argc, char **argv)
   r = mcx_graph_export_begin(g, sort_kmers ? 1 : 0, &nrec, &rec_bytes);
   if(r) die_mcx(r, "mcx_graph_export_begin");
   mcx_phase("export: compact + sort");
-  const bool big_regular = fh != stdout && (uint64_t)nrec * rec_bytes >= (256u << 20);
+  uint64_t pipe_min = 256u << 20; /* MCX_OUT_PIPE_MIN=<bytes> overrides (tests) */
+  if(getenv("MCX_OUT_PIPE_MIN")) pipe_min = (uint64_t)atoll(getenv("MCX_OUT_PIPE_MIN"));
+  const bool big_regular = fh != stdout && (uint64_t)nrec * rec_bytes >= pipe_min;
   if(!big_regular || !write_records_parallel(g, fh, nrec, rec_bytes)) {
     size_t chunk_recs = (64u << 20) / rec_bytes;
     char *buf = malloc(chunk_recs * rec_bytes);

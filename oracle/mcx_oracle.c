@@ -297,6 +297,8 @@ static uint64_t orc_find_or_insert(OrcGraph *g, const OrcKmer *key, int *found)
 {
   int W = g->W, i;
   uint64_t h = orc_lookup3(key->b, W, 0, NULL) & g->mask;
+  /* (a graph already flagged full is discarded by every caller: stop before the array itself has no empty slot left) */
+  if(g->full && g->nkmers + 2 >= g->cap) { *found = 1; return h; }
   for(;; h = (h + 1) & g->mask) {
     uint64_t *s = g->keys + h * (uint64_t)W;
     if(s[0] == 0) {

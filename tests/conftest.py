@@ -112,6 +112,25 @@ def ingest_dump():
     return exe
 
 
+def build_hostcheck():
+    """the host driver's C sources linked against tests/emul/abi_shim.c (the C ABI implemented by the oracle) instead
+    of libmcxgpu.so: test infrastructure for the CPU-only run, never part of the product"""
+    import glob
+    exe = os.path.join(ROOT, "tests", "emul", "hostcheck")
+    host = sorted(glob.glob(os.path.join(ROOT, "mccortex_b200", "host", "*.c")))
+    srcs = host + [os.path.join(ROOT, "tests", "emul", "abi_shim.c"), os.path.join(ROOT, "oracle", "mcx_oracle.c")]
+    deps = srcs + [os.path.join(ROOT, "mccortex_b200", "host", "mcx_host.h"), os.path.join(ROOT, "include", "mcx_gpu.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["gcc", "-O2", "-std=c99", "-D_GNU_SOURCE", "-w", "-I", os.path.join(ROOT, "include"), "-o", exe] + srcs +
+                              ["-lz", "-lpthread", "-lm"])
+    return exe
+
+
+@pytest.fixture(scope="session")
+def hostcheck():
+    return build_hostcheck()
+
+
 def write_pcr_files(rng, d, n=400, k=21):
     """se.fa, p1.fq / p2.fq (p2 one read longer), il.fq (pairs by name, /1 /2 names, singles) for --remove-pcr tests"""
     def q(L, lowp=0.05):

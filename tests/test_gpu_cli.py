@@ -329,3 +329,24 @@ def test_cli_files_of_one_colour_loaded_concurrently(tmp_path, oracle):
         out = tmp_path / "out.ctx"
         _run(args + [str(out)], env=env)
         assert open(out, "rb").read() == want, env
+
+
+def test_cli_pipelined_writer(tmp_path):
+    """outputs >= 256 MB are written by four pwrite threads from pinned chunks (write_records_parallel, ctx_build.c);
+    forced here on a small graph with 100-record chunks: same file as the plain fwrite loop, header included"""
+    rng = random.Random(91)
+    fa = tmp_path / "r.fa"
+    fa.write_text("".join(">r\n%s\n" % r for r in rand_reads(rng, 1500, 150, 30000, perr=0.005)))
+    outs = []
+    for env in ({"MCX_OUT_PIPE_MIN": "1", "MCX_OUT_CHUNK_RECS": "100"}, {}):
+        for k, sort in ((31, True), (63, False)):
+            out = tmp_path / "o.ctx"
+            _run(["-q", "-f", "-m", "1G", "-n", "4M", "-k", str(k), "-s", "s", "-1", str(fa)] + (["-S"] if sort else []) + [str(out)], env=env)
+            outs.append(open(out, "rb").read())
+    assert outs[0] == outs[2] and len(outs[0]) > 100000
+
+    def recs(ctx, rb):   # unsorted dumps: same header, same records in some order
+        h = ctx.index(b"CORTEX", 6) + 6
+        assert (len(ctx) - h) % rb == 0
+        return ctx[:h], sorted(ctx[i:i + rb] for i in range(h, len(ctx), rb))
+    assert recs(outs[1], 21) == recs(outs[3], 21)
