@@ -663,14 +663,15 @@ int main(int argc, char **argv)
 {
   time_t t0 = time(NULL);
   mcx_msg_out = stderr;
-  bool is_sort = argc >= 2 && strcasecmp(argv[1], "sort") == 0;
-  if(argc < 2 || (strcasecmp(argv[1], "build") != 0 && !is_sort)) {
-    fprintf(stderr, "\nusage: "CMD" <build|sort> [options] <out.ctx>\n"
+  bool is_sort = argc >= 2 && strcasecmp(argv[1], "sort") == 0, is_join = argc >= 2 && strcasecmp(argv[1], "join") == 0;
+  if(argc < 2 || (strcasecmp(argv[1], "build") != 0 && !is_sort && !is_join)) {
+    fprintf(stderr, "\nusage: "CMD" <build|sort|join> [options] <out.ctx>\n"
                     "  build   construct a CORTEX v6 graph file on a B200 for the rest of McCortex\n"
-                    "  sort    sort the k-mers of a graph file\n\n");
+                    "  sort    sort the k-mers of a graph file\n"
+                    "  join    merge graph files\n\n");
     return EXIT_FAILURE;
   }
-  if(argc == 2 && !is_sort) mcx_print_usage(build_usage, NULL);
+  if(argc == 2 && !is_sort && !is_join) mcx_print_usage(build_usage, NULL);
   /* command line for the log, before -q is stripped */
   size_t len = 0; int i;
   for(i = 0; i < argc; i++) len += strlen(argv[i]) + 1;
@@ -683,7 +684,7 @@ int main(int argc, char **argv)
   free(line);
 
   char *tmp = argv[1]; argv[1] = argv[0]; argv[0] = tmp;
-  int ret = is_sort ? mcx_cmd_sort(argc - 1, argv + 1) : ctx_build(argc - 1, argv + 1);
+  int ret = is_sort ? mcx_cmd_sort(argc - 1, argv + 1) : (is_join ? mcx_cmd_join(argc - 1, argv + 1) : ctx_build(argc - 1, argv + 1));
   mcx_status(ret == 0 ? "Done." : "Fail.");
   mcx_status("[time] %.2lf seconds\n", difftime(time(NULL), t0));
   /* every output file is closed: leave without the CUDA runtime's exit handlers (tearing the context down in user

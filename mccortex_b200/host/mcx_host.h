@@ -59,6 +59,8 @@ void mcx_ginfo_merge(McxGInfo *dst, const McxGInfo *src);
 /* writes the .ctx v6 header for ncols colours after merging every colour into a fresh
  * header entry, exactly as graph_writer_mkhdr does; returns bytes written */
 size_t mcx_write_ctx_header(FILE *fh, uint32_t kmer_size, uint32_t ncols, const McxGInfo *ginfo);
+/* graph_write_header of the colours as they stand (no merge into a fresh header): `join` */
+size_t mcx_write_ctx_header_as_is(FILE *fh, uint32_t kmer_size, uint32_t ncols, const McxGInfo *ginfo);
 
 /* ---- graph files: src/graph/graph_file_reader.{c,h}, src/basic/file_filter.{c,h}, src/basic/range.c,
  *      src/graph/graphs_load.c ------------------------------------------------------------- */
@@ -86,6 +88,8 @@ void mcx_ctx_flatten(McxCtxFile *f, uint32_t intocol);
 size_t mcx_ctx_write_header_raw(FILE *fh, const McxCtxFile *f);
 bool mcx_ctx_filter_is_direct(const McxCtxFile *f);     /* file_filter_from_direct */
 
+/* `join` command: src/commands/ctx_join.c (without --intersect) */
+int mcx_cmd_join(int argc, char **argv);
 /* `sort` command: src/commands/ctx_sort.c */
 int mcx_cmd_sort(int argc, char **argv);   /* file_filter_flatten, src/basic/file_filter.c:218-226 */
 

@@ -3,7 +3,7 @@
  *
  * Dispatch shim (written for this repo) that links the UNMODIFIED reference
  * sources under /root/reference into a small binary exposing only the
- * sub-commands the parity tests need:  build, sort, view, check, hashtest.
+ * sub-commands the parity tests need:  build, sort, join, view, check, hashtest.
  * It replaces src/main/mccortex.c:279-332 (whose command table pulls in all
  * 30 sub-commands and, through them, htslib/VCF and seq-align), and follows
  * the same start-up sequence: cortex_init -> cmd_init -> cmd_set_usage ->
@@ -20,6 +20,7 @@ typedef struct { const char *cmd; int (*func)(int, char **); const char *usage; 
 static const RefCmd cmds[] = {
   {"build",    ctx_build,        build_usage},
   {"sort",     ctx_sort,         sort_usage},
+  {"join",     ctx_join,         join_usage},
   {"view",     ctx_view,         view_usage},
   {"check",    ctx_health_check, health_usage},
   {"hashtest", ctx_exp_hashtest, exp_hashtest_usage},
@@ -48,7 +49,7 @@ int main(int argc, char **argv)
   ctx_msg_out = stderr;
   cortex_init();
   cmd_init(argc, argv);
-  if(argc < 2) { fprintf(stderr, "usage: %s <build|sort|view|check|hashtest> ...\n", argv[0]); return 1; }
+  if(argc < 2) { fprintf(stderr, "usage: %s <build|sort|join|view|check|hashtest> ...\n", argv[0]); return 1; }
   for(i = 0; i < n; i++) if(!strcasecmp(cmds[i].cmd, argv[1])) cmd = &cmds[i];
   if(cmd == NULL) { fprintf(stderr, "unknown command: %s\n", argv[1]); return 1; }
   cmd_set_usage(cmd->usage);

@@ -350,3 +350,49 @@ def test_cli_pipelined_writer(tmp_path):
         assert (len(ctx) - h) % rb == 0
         return ctx[:h], sorted(ctx[i:i + rb] for i in range(h, len(ctx), rb))
     assert recs(outs[1], 21) == recs(outs[3], 21)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "mccortex31")), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("k", [21, 39])
+def test_cli_join_matches_reference_binary(tmp_path, oracle, k):
+    """`mccortex-b200 join` (src/commands/ctx_join.c without --intersect): colours side by side, on top of each other,
+    picked by filter, with offsets; the merged header; -S output byte-identical to the reference's join, unsorted
+    multi-file output identical after the reference's `sort`, single-file stream filter identical as it is"""
+    r = oracle.ref_run(k, ["join"], check=False)
+    if b"usage" not in r.stderr + r.stdout or b"unknown command" in r.stderr:
+        pytest.skip("oracle/_ref was built without join")
+    rng = random.Random(5000 + k)
+    reads = rand_reads(rng, 1800, (20, 220), 12000, perr=0.004)
+    fas = []
+    for i in range(3):
+        p = tmp_path / ("r%d.fa" % i)
+        p.write_text("".join(">r%d\n%s\n" % (j, x) for j, x in enumerate(reads[i * 600:(i + 1) * 600])))
+        fas.append(str(p))
+    a, b = str(tmp_path / "a.ctx"), str(tmp_path / "b.ctx")
+    oracle.ref_build(k, ["-s", "sa0", "-1", fas[0], "-s", "sa1", "-1", fas[1]], a, nkmers="2M", sort=False)   # 2 colours, unsorted
+    oracle.ref_build(k, ["-s", "sb", "-1", fas[2], "-1", fas[0]], b, nkmers="2M")                             # 1 colour
+    cases = [[a, b], [b + ":0", "0:" + a + ":1"], ["1:" + b, a + ":1,0"], [a + ":0-1", "0:" + b, "3:" + a + ":0"], [a]]
+    for n, files in enumerate(cases):
+        mine, ref = str(tmp_path / ("mine%d.ctx" % n)), str(tmp_path / ("ref%d.ctx" % n))
+        _run_cmd("join", ["-q", "-f", "-m", "1G", "-n", "2M", "-S", "-o", mine] + files)
+        oracle.ref_run(k, ["join", "-q", "-f", "-m", "1G", "-n", "2M", "-S", "-o", ref] + files)
+        assert open(mine, "rb").read() == open(ref, "rb").read(), files
+        assert oracle.ref_run(k, ["check", "-q", mine], check=False).returncode == 0
+    # unsorted: several files -> same after `sort`; one file through a filter -> the stream keeps the input order
+    mine, ref = str(tmp_path / "mu.ctx"), str(tmp_path / "ru.ctx")
+    _run_cmd("join", ["-q", "-f", "-m", "1G", "-n", "2M", "-o", mine, a, b])
+    oracle.ref_run(k, ["join", "-q", "-f", "-m", "1G", "-n", "2M", "-o", ref, a, b])
+    oracle.ref_run(k, ["sort", "-q", mine]); oracle.ref_run(k, ["sort", "-q", ref])
+    assert open(mine, "rb").read() == open(ref, "rb").read()
+    for flt in (a + ":1", a + ":1,0", "2:" + a + ":0"):
+        _run_cmd("join", ["-q", "-f", "-o", mine, flt])
+        oracle.ref_run(k, ["join", "-q", "-f", "-o", ref, flt])
+        assert open(mine, "rb").read() == open(ref, "rb").read(), flt
+    # errors: no output, existing output, mixed kmer sizes, --intersect
+    assert _run_cmd("join", ["-q", a], check=False).returncode == 1
+    r = _run_cmd("join", ["-q", "-o", mine, a], check=False)
+    assert r.returncode == 1 and b"File already exists" in r.stderr
+    other = str(tmp_path / "k.ctx")
+    oracle.ref_build(k + 2, ["-s", "x", "-1", fas[0]], other, nkmers="2M")
+    assert _run_cmd("join", ["-q", "-f", "-o", mine, a, other], check=False).returncode == 1
+    assert _run_cmd("join", ["-q", "-f", "-o", mine, "-i", b, a], check=False).returncode == 1
