@@ -324,7 +324,7 @@ static struct {
   pthread_t thread; bool joined;
   uint32_t k, ncols, flags; uint64_t capacity; int device; bool host_batches;
   mcx_graph *g; int rc; const char *what;
-  volatile int done;
+  int done; /* set (release) by the thread when rc / g are final; polled (acquire) by graph_ready */
 } ginit;
 
 static void *graph_init_main(void *arg)
@@ -336,11 +336,10 @@ static void *graph_init_main(void *arg)
     ginit.what = "mcx_graph_create";
     if(!ginit.rc && ginit.host_batches) { ginit.rc = mcx_graph_prepare_host(ginit.g); ginit.what = "mcx_graph_prepare_host"; }
   }
-  __sync_synchronize();
-  ginit.done = 1;
+  __atomic_store_n(&ginit.done, 1, __ATOMIC_RELEASE);
   return NULL;
 }
-static bool graph_ready(void *ctx) { (void)ctx; return ginit.done != 0; }
+static bool graph_ready(void *ctx) { (void)ctx; return __atomic_load_n(&ginit.done, __ATOMIC_ACQUIRE) != 0; }
 static mcx_graph *graph_wait(void *ctx)
 {
   (void)ctx;

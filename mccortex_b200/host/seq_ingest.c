@@ -39,11 +39,17 @@ int mcx_submit_reads(mcx_graph *g, const mcx_read_batch *b)
 
 #define MCX_BATCH_BYTES_DEFAULT (96u << 20)
 /* bytes per batch; MCX_BATCH_BYTES=<n> in the environment overrides it (tests use tiny batches) */
+static size_t batch_bytes_v;
+static void batch_bytes_init(void)
+{
+  const char *e = getenv("MCX_BATCH_BYTES");
+  batch_bytes_v = e && atol(e) > 0 ? (size_t)atol(e) : MCX_BATCH_BYTES_DEFAULT;
+}
 static size_t batch_bytes(void)
 {
-  static size_t v = 0;
-  if(!v) { const char *e = getenv("MCX_BATCH_BYTES"); v = e && atol(e) > 0 ? (size_t)atol(e) : MCX_BATCH_BYTES_DEFAULT; }
-  return v;
+  static pthread_once_t once = PTHREAD_ONCE_INIT; /* several files may be loading at once */
+  pthread_once(&once, batch_bytes_init);
+  return batch_bytes_v;
 }
 #define MCX_BATCH_BYTES batch_bytes()
 #define MCX_IN_BYTES (4u << 20)

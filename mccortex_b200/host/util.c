@@ -3,6 +3,7 @@
  * status lines are time-stamped and carry a per-run 3-letter code, -q silences status),
  * src/global/util.c:206-222 (memory suffixes), :251-264 (thousands separators). */
 #include "mcx_host.h"
+#include <pthread.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -13,18 +14,23 @@
 FILE *mcx_msg_out = NULL;
 static char run_code[4] = "";
 
+static void run_code_init(void)
+{
+  static const char cons[] = "bcdfghjklmnpqrstvwxyzBCDFGHJKLMNPQRSTVWXYZ", vow[] = "aeiouAEIOU";
+  unsigned s = (unsigned)time(NULL) * 2654435761u + (unsigned)getpid();
+  run_code[0] = cons[s % (sizeof(cons) - 1)]; s /= 41;
+  run_code[1] = vow[s % (sizeof(vow) - 1)]; s /= 11;
+  run_code[2] = cons[s % (sizeof(cons) - 1)]; run_code[3] = 0;
+}
+/* status lines come from several threads (one per file being loaded): one line at a time */
+static pthread_mutex_t msg_lock = PTHREAD_MUTEX_INITIALIZER;
 static void timestamp(FILE *fh)
 {
-  if(!run_code[0]) {
-    static const char cons[] = "bcdfghjklmnpqrstvwxyzBCDFGHJKLMNPQRSTVWXYZ", vow[] = "aeiouAEIOU";
-    unsigned s = (unsigned)time(NULL) * 2654435761u + (unsigned)getpid();
-    run_code[0] = cons[s % (sizeof(cons) - 1)]; s /= 41;
-    run_code[1] = vow[s % (sizeof(vow) - 1)]; s /= 11;
-    run_code[2] = cons[s % (sizeof(cons) - 1)]; run_code[3] = 0;
-  }
-  time_t t; char ts[100];
+  static pthread_once_t once = PTHREAD_ONCE_INIT;
+  pthread_once(&once, run_code_init);
+  time_t t; char ts[100]; struct tm tmv;
   time(&t);
-  strftime(ts, sizeof(ts), "[%d %b %Y %H:%M:%S", localtime(&t));
+  strftime(ts, sizeof(ts), "[%d %b %Y %H:%M:%S", localtime_r(&t, &tmv));
   fprintf(fh, "%s-%s]", ts, run_code);
 }
 
@@ -32,20 +38,24 @@ void mcx_status(const char *fmt, ...)
 {
   if(!mcx_msg_out) return;
   va_list ap;
+  pthread_mutex_lock(&msg_lock);
   timestamp(mcx_msg_out);
   if(fmt[0] != ' ' && fmt[0] != '[') fputc(' ', mcx_msg_out);
   va_start(ap, fmt); vfprintf(mcx_msg_out, fmt, ap); va_end(ap);
   if(fmt[strlen(fmt) - 1] != '\n') fputc('\n', mcx_msg_out);
   fflush(mcx_msg_out);
+  pthread_mutex_unlock(&msg_lock);
 }
 
 static void err_msg(const char *type, const char *fmt, va_list ap)
 {
   fflush(stdout);
+  pthread_mutex_lock(&msg_lock);
   timestamp(stderr);
   fprintf(stderr, "[mccortex-b200] %s: ", type);
   vfprintf(stderr, fmt, ap);
   if(fmt[strlen(fmt) - 1] != '\n') fputc('\n', stderr);
+  pthread_mutex_unlock(&msg_lock);
 }
 
 void mcx_warn(const char *fmt, ...)
@@ -76,12 +86,14 @@ void mcx_phase(const char *what)
 {
   static int on = -1; static struct timespec t0, last;
   struct timespec now;
+  pthread_mutex_lock(&msg_lock);
   if(on < 0) { on = getenv("MCX_TIMING") != NULL; clock_gettime(CLOCK_MONOTONIC, &t0); last = t0; }
-  if(!on) return;
+  if(!on) { pthread_mutex_unlock(&msg_lock); return; }
   clock_gettime(CLOCK_MONOTONIC, &now);
   fprintf(stderr, "[phase] %-28s +%.3f s  (at %.3f s)\n", what, (double)(now.tv_sec - last.tv_sec) + 1e-9 * (double)(now.tv_nsec - last.tv_nsec),
           (double)(now.tv_sec - t0.tv_sec) + 1e-9 * (double)(now.tv_nsec - t0.tv_nsec));
   last = now;
+  pthread_mutex_unlock(&msg_lock);
 }
 
 void mcx_ulong_to_str(uint64_t num, char *out)

@@ -116,6 +116,8 @@ def build_hostcheck():
     """the host driver's C sources linked against tests/emul/abi_shim.c (the C ABI implemented by the oracle) instead
     of libmcxgpu.so: test infrastructure for the CPU-only run, never part of the product"""
     import glob
+    if os.environ.get("MCX_HOSTCHECK_EXE"):   # e.g. the same sources built with -fsanitize=address,undefined / thread
+        return os.environ["MCX_HOSTCHECK_EXE"]
     exe = os.path.join(ROOT, "tests", "emul", "hostcheck")
     host = sorted(glob.glob(os.path.join(ROOT, "mccortex_b200", "host", "*.c")))
     srcs = host + [os.path.join(ROOT, "tests", "emul", "abi_shim.c"), os.path.join(ROOT, "oracle", "mcx_oracle.c")]
