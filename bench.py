@@ -343,6 +343,8 @@ def own_arm(args):
         "config": workload_config(args, 1),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
+                     # physical DRAM utilisation next to the logical (algorithmic) fraction
+                     "dram_util": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None,
                      "kernel": "mcx_build_fused_kernel<1,3,2>", "kernel_ms": kernel_ms,
                      "alg_bytes_per_kmer": B_ALG, "kmers_per_launch": occ_per_step,
                      "traffic_note": (tr or {}).get("note")},
