@@ -18,6 +18,77 @@ import os
 import time
 
 
+# ---------------------------------------------------------------------------------------------
+# One sorted .ctx from P shards (output).  Every shard exports its records in ascending
+# key order (mcx_graph_export_begin(sorted=1)); ownership is by hash, so each shard's keys cover the
+# whole key range and the file order -- ascending (b[0], b[1]), what HASH_ITERATE_SORTED gives the
+# reference (src/graph/hash_table.c:362-374) -- needs a P-way merge of disjoint sorted runs.  The merge
+# streams: per round it takes a chunk from every run, everything up to the smallest "last key of a
+# chunk" is final, is merged (sort of the concatenation) and emitted.  Memory = P chunks.
+def _rec_keys(recs, W):
+    """recs: uint8 array [n, rec_bytes] -> (w0, w1 or None) as uint64 arrays"""
+    import numpy as np
+    k = np.ascontiguousarray(recs[:, :8 * W]).view("<u8").reshape(len(recs), W)
+    return k[:, 0], (k[:, 1] if W == 2 else None)
+
+
+def merge_sorted_runs(runs, rec_bytes, W, chunk_recs=1 << 20):
+    """runs: list of objects supporting len() in bytes via .nbytes / len and slicing to bytes-like (bytes,
+    bytearray, numpy uint8 arrays, numpy.memmap): each a whole number of records sorted by key, keys
+    disjoint between runs.  Yields uint8 arrays [m, rec_bytes] whose concatenation is the merged run."""
+    import numpy as np
+    arrs = []
+    for r in runs:
+        a = np.frombuffer(r, dtype=np.uint8) if isinstance(r, (bytes, bytearray, memoryview)) else np.asarray(r, dtype=np.uint8).reshape(-1)
+        if a.size % rec_bytes:
+            raise ValueError("run is not a whole number of records")
+        arrs.append(a.reshape(-1, rec_bytes))
+    pos = [0] * len(arrs)
+    while True:
+        live = [i for i, a in enumerate(arrs) if pos[i] < len(a)]
+        if not live:
+            return
+        if len(live) == 1:
+            i = live[0]
+            while pos[i] < len(arrs[i]):
+                yield np.array(arrs[i][pos[i]:pos[i] + chunk_recs])
+                pos[i] += chunk_recs
+            return
+        chunks = {i: np.array(arrs[i][pos[i]:pos[i] + chunk_recs]) for i in live}
+        keys = {i: _rec_keys(c, W) for i, c in chunks.items()}
+        # everything <= the smallest last key is final: later records of any run are larger
+        bound = min((int(keys[i][0][-1]), int(keys[i][1][-1]) if W == 2 else 0) for i in live)
+        take, tk0, tk1 = [], [], []
+        for i in live:
+            w0, w1 = keys[i]
+            if W == 1:
+                n = int(np.searchsorted(w0, np.uint64(bound[0]), side="right"))
+            else:
+                n = int(np.count_nonzero((w0 < np.uint64(bound[0])) | ((w0 == np.uint64(bound[0])) & (w1 <= np.uint64(bound[1])))))
+            if n:
+                take.append(chunks[i][:n]); tk0.append(w0[:n])
+                if W == 2:
+                    tk1.append(w1[:n])
+                pos[i] += n
+        cat = np.concatenate(take)
+        k0 = np.concatenate(tk0)
+        order = np.argsort(k0, kind="stable") if W == 1 else np.lexsort((np.concatenate(tk1), k0))
+        yield cat[order]
+
+
+def write_ctx_from_shards(out_fh, header_bytes, shard_paths, rec_bytes, W, chunk_recs=1 << 20):
+    """rank 0 of a sharded build: header + the merge of the shards' sorted record files (each rank has written
+    its `export_records(sorted=True)` to shard_paths[rank]).  Returns the number of records written."""
+    import numpy as np
+    out_fh.write(header_bytes)
+    runs = [np.memmap(p, dtype=np.uint8, mode="r") if os.path.getsize(p) else np.zeros(0, dtype=np.uint8) for p in shard_paths]
+    n = 0
+    for piece in merge_sorted_runs(runs, rec_bytes, W, chunk_recs):
+        out_fh.write(piece.tobytes())
+        n += len(piece)
+    return n
+
+
 FRONT_SPAN = 0xE0000000  # positions between two flushes of a sharded graph's front table (library limit: 0xF0000000)
 
 

@@ -257,12 +257,13 @@ def test_sharded_build_on_one_device(M, oracle, k, nparts):
                 shards[d].insert_tuples(keys[d * cap * W:].data_ptr(), meta[d * cap:].data_ptr(), cnt[d])
         torch.cuda.synchronize()
     rb = 8 * W + 5
-    allrecs, loaded, novel = [], 0, 0
+    allrecs, loaded, novel, runs = [], 0, 0, []
     for p in range(nparts):
         st = shards[p].sync()
         loaded += st.num_kmers_loaded
         novel += st.num_kmers_novel
         got, n, _ = shards[p].export_records()
+        runs.append(bytes(got))
         for i in range(0, len(got), rb):
             key = [int.from_bytes(got[i + 8 * w:i + 8 * w + 8], "little") for w in range(W)]
             assert M.key_owner(key, k, nparts) == p
@@ -273,6 +274,9 @@ def test_sharded_build_on_one_device(M, oracle, k, nparts):
     def sort_key(r):
         return tuple(int.from_bytes(r[8 * w:8 * w + 8], "little") for w in range(W))
     assert b"".join(sorted(allrecs, key=sort_key)) == recs
+    # the file a sharded build writes: streaming P-way merge of the shards' sorted exports (multi.merge_sorted_runs)
+    from mccortex_b200.multi import merge_sorted_runs
+    assert b"".join(x.tobytes() for x in merge_sorted_runs(runs, rb, W, chunk_recs=777)) == recs
 
 
 @pytest.mark.parametrize("k,nparts", [(31, 2), (31, 4), (63, 3)])

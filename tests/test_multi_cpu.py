@@ -164,3 +164,50 @@ def test_routed_builder_host_logic_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+# ---- one sorted .ctx from P shards: the streaming P-way merge of mccortex_b200/multi.py -------------------------
+import random as _random
+
+import pytest as _pytest
+
+
+@_pytest.mark.parametrize("W,ncols,nshards,n,chunk", [(1, 1, 2, 5000, 64), (1, 4, 8, 20000, 1000), (2, 1, 3, 7000, 50), (2, 2, 5, 3000, 1 << 20),
+                                                      (1, 1, 4, 0, 16), (2, 1, 1, 1000, 7)])
+def test_merge_of_sorted_shard_runs(tmp_path, W, ncols, nshards, n, chunk):
+    """records with distinct random keys are dealt to shards by a hash of the key (as the build does), every shard sorts its
+    own: the merge must reproduce the globally sorted file, through memory and through shard files; empty shards, one
+    shard, chunks far smaller than the runs"""
+    import numpy as np
+    from mccortex_b200.multi import merge_sorted_runs, write_ctx_from_shards
+    rng = _random.Random(W * 1000 + nshards)
+    rb = 8 * W + 5 * ncols
+    keys = set()
+    while len(keys) < n:
+        # few distinct high words so that the second word decides often (W = 2)
+        keys.add((rng.getrandbits(62) if W == 1 else rng.randrange(40), rng.getrandbits(64) if W == 2 else 0))
+    recs = []
+    for k0, k1 in keys:
+        r = k0.to_bytes(8, "little") + (k1.to_bytes(8, "little") if W == 2 else b"") + rng.randbytes(5 * ncols)
+        recs.append(((k0, k1), r))
+    want = b"".join(r for _, r in sorted(recs))
+    shards = [[] for _ in range(nshards)]
+    for key, r in recs:
+        shards[hash(key) % nshards].append((key, r))
+    if nshards > 2:
+        shards[1] = []   # an empty shard
+        want = b"".join(r for _, r in sorted(x for s in shards for x in s))
+    runs = [b"".join(r for _, r in sorted(s)) for s in shards]
+    got = b"".join(p.tobytes() for p in merge_sorted_runs(runs, rb, W, chunk))
+    assert got == want
+    paths = []
+    for i, run in enumerate(runs):
+        p = tmp_path / ("shard%d.bin" % i)
+        p.write_bytes(run)
+        paths.append(str(p))
+    out = tmp_path / "out.ctx"
+    with open(out, "wb") as fh:
+        nrec = write_ctx_from_shards(fh, b"HEADER", paths, rb, W, chunk)
+    assert nrec == len(want) // rb and out.read_bytes() == b"HEADER" + want
+    with _pytest.raises(ValueError):
+        list(merge_sorted_runs([b"x" * (rb + 1)], rb, W))
