@@ -52,7 +52,8 @@ static const char build_usage[] =
 "  -g, --graph <in.ctx>     Load samples from a graph file (.ctx)\n"
 "  -I, --intersect <i.ctx>  Only load kmers that appear in i.ctx. Multiple -I will merge\n"
 "  -S, --sort               Output a graph file ordered by kmer\n"
-"  -D, --device <id>        CUDA device [default: 0]\n"
+"  -D, --device <id[,id..]> CUDA device [default: 0]; several: one replica of the graph per device, every\n"
+"                           batch of reads goes to one of them, the replicas are merged before the dump\n"
 "\n"
 "  Note: Argument must come before input file\n"
 "  --sample <name> is required before sequence input can be loaded.\n"
@@ -87,6 +88,8 @@ static size_t nthreads = 0, kmer_size = 0, output_colours = 0;
 static bool mem_set = false, nkmers_set = false, force = false, sort_kmers = false;
 static size_t mem_to_use = MCX_DEFAULT_MEM, num_kmers = MCX_DEFAULT_NKMERS;
 static int device = 0;
+#define MAX_DEVICES 16
+static int devices[MAX_DEVICES] = {0}, ndevices = 1;
 static char *out_path = NULL;
 
 #define usage_err(...) mcx_print_usage(build_usage, __VA_ARGS__)
@@ -245,7 +248,19 @@ static void parse_args(int argc, char **argv)
         ifiles[nifiles++] = gf;
         break;
       }
-      case 'D': device = (int)parse_size(cmd, optarg, false); break;
+      case 'D': {
+        /* -D 2 or -D 0,1,2,3 */
+        char *list = strdup(optarg), *tok, *save = NULL;
+        ndevices = 0;
+        for(tok = strtok_r(list, ",", &save); tok; tok = strtok_r(NULL, ",", &save)) {
+          if(ndevices == MAX_DEVICES) mcx_die("%s: at most %d devices", cmd, MAX_DEVICES);
+          devices[ndevices++] = (int)parse_size(cmd, tok, false);
+        }
+        if(ndevices == 0) mcx_die("%s <id[,id..]> requires an argument", cmd);
+        device = devices[0];
+        free(list);
+        break;
+      }
       case ':': case '?':
         mcx_die("`"CMD" build -h` for help. Bad option: %s", argv[optind - 1]);
       default: mcx_die("Bad option: %s", cmd);
@@ -324,6 +339,8 @@ static struct {
   pthread_t thread; bool joined;
   uint32_t k, ncols, flags; uint64_t capacity; int device; bool host_batches;
   mcx_graph *g; int rc; const char *what;
+  mcx_graph *gs[MAX_DEVICES]; /* gs[0] == g; more with -D a,b,..: replicas on the other devices */
+  unsigned next;              /* round robin over the replicas (under mcx_ingest.lock when files load concurrently) */
   int done; /* set (release) by the thread when rc / g are final; polled (acquire) by graph_ready */
 } ginit;
 
@@ -332,13 +349,55 @@ static void *graph_init_main(void *arg)
   (void)arg;
   if(mcx_device_count() == 0) { ginit.rc = MCX_ERR_NO_DEVICE; ginit.what = "device"; }
   else {
-    ginit.rc = mcx_graph_create(ginit.k, ginit.ncols, ginit.capacity, ginit.device, ginit.flags, &ginit.g);
-    ginit.what = "mcx_graph_create";
-    if(!ginit.rc && ginit.host_batches) { ginit.rc = mcx_graph_prepare_host(ginit.g); ginit.what = "mcx_graph_prepare_host"; }
+    for(int d = 0; d < ndevices && !ginit.rc; d++) {
+      ginit.rc = mcx_graph_create(ginit.k, ginit.ncols, ginit.capacity, devices[d], ginit.flags, &ginit.gs[d]);
+      ginit.what = "mcx_graph_create";
+      if(!ginit.rc && ginit.host_batches) { ginit.rc = mcx_graph_prepare_host(ginit.gs[d]); ginit.what = "mcx_graph_prepare_host"; }
+    }
+    ginit.g = ginit.gs[0];
   }
   __atomic_store_n(&ginit.done, 1, __ATOMIC_RELEASE);
   return NULL;
 }
+/* -D a,b,..: which replica takes the next batch; joining all of them */
+static mcx_graph *route_replica(mcx_graph *g) { (void)g; return ginit.gs[ginit.next++ % (unsigned)ndevices]; }
+static int sync_replicas(mcx_graph *g, mcx_load_stats *st)
+{
+  (void)g;
+  memset(st, 0, sizeof(*st));
+  int rc = MCX_OK;
+  for(int d = 0; d < ndevices; d++) {
+    mcx_load_stats s;
+    int r = mcx_graph_sync(ginit.gs[d], &s);
+    if(r && !rc) rc = r;
+    mcx_add_load_stats(st, &s);
+  }
+  return rc;
+}
+/* fold replica d into replica 0: its records (coverage adds saturating, edges OR -- mcx_graph_load_records) */
+static void merge_replica(int d, uint32_t ncols)
+{
+  uint64_t nrec = 0; uint32_t rec_bytes = 0;
+  int r = mcx_graph_export_begin(ginit.gs[d], 0, &nrec, &rec_bytes);
+  if(r) die_mcx(r, "mcx_graph_export_begin");
+  uint32_t *cols = malloc(4 * (size_t)ncols);
+  for(uint32_t c = 0; c < ncols; c++) cols[c] = c;
+  const size_t chunk_recs = (64u << 20) / rec_bytes;
+  char *buf = malloc(chunk_recs * rec_bytes);
+  if(!cols || !buf) mcx_die("Out of memory");
+  for(uint64_t at = 0; at < nrec; at += chunk_recs) {
+    const uint64_t n = nrec - at < chunk_recs ? nrec - at : chunk_recs;
+    r = mcx_graph_export_read(ginit.gs[d], at, n, buf);
+    if(r) die_mcx(r, "mcx_graph_export_read");
+    r = mcx_graph_load_records(ginit.gs[0], buf, n, ncols, MCX_MEM_HOST, cols, cols, ncols, 0, NULL, NULL);
+    if(r) die_mcx(r, "merging replicas");
+  }
+  free(buf); free(cols);
+  mcx_graph_export_end(ginit.gs[d]);
+  mcx_graph_destroy(ginit.gs[d]); ginit.gs[d] = NULL;
+  { char a[64]; mcx_ulong_to_str(nrec, a); mcx_status("[replica] merged %s kmers of the graph on GPU %i into GPU %i", a, devices[d], devices[0]); }
+}
+
 static bool graph_ready(void *ctx) { (void)ctx; return __atomic_load_n(&ginit.done, __ATOMIC_ACQUIRE) != 0; }
 static mcx_graph *graph_wait(void *ctx)
 {
@@ -350,7 +409,7 @@ static mcx_graph *graph_wait(void *ctx)
     if(ginit.rc == MCX_ERR_NO_DEVICE && !ginit.g && !strcmp(ginit.what, "device")) mcx_die("No CUDA device: "CMD" has no CPU fallback");
     if(ginit.rc) die_mcx(ginit.rc, ginit.what);
     char a[64]; mcx_ulong_to_str(ginit.capacity, a);
-    mcx_status("[hasht] Allocating device table with %s entries on GPU %i", a, ginit.device);
+    for(int d = 0; d < ndevices; d++) mcx_status("[hasht] Allocating device table with %s entries on GPU %i", a, devices[d]);
     mcx_phase("cuda init + table (joined)");
   }
   pthread_mutex_unlock(&mu);
@@ -493,11 +552,13 @@ static int ctx_build(int argc, char **argv)
 
   /* CUDA start-up, the context and the table take 0.5-1.5 s: they run on a second thread while this one
    * starts parsing the first sequence file (seq_ingest.c keeps the parsed batches until the graph exists) */
+  if(ndevices > 1 && remove_pcr_used) mcx_die("--remove-pcr needs the reads in order on one table: use one device");
   ginit.k = (uint32_t)kmer_size; ginit.ncols = (uint32_t)output_colours; ginit.capacity = kmers_in_hash; ginit.device = device;
   ginit.flags = (nifiles > 0 ? MCX_GRAPH_INTERSECT : 0) | (remove_pcr_used ? MCX_GRAPH_READSTRT : 0);
   ginit.host_batches = ntasks > 0;
   if(pthread_create(&ginit.thread, NULL, graph_init_main, NULL) != 0) mcx_die("Cannot start a thread");
   mcx_graph_source.wait = graph_wait; mcx_graph_source.ready = graph_ready; mcx_graph_source.ctx = NULL;
+  if(ndevices > 1) { mcx_ingest.route = route_replica; mcx_ingest.sync = sync_replicas; }
   mcx_graph *g = NULL;
   int r = 0;
   if(nifiles > 0 || ngfiles > 0 || remove_pcr_used) g = graph_wait(NULL); /* these need the device right away */
@@ -512,11 +573,13 @@ static int ctx_build(int argc, char **argv)
   for(i = 0; i < nifiles; i++) {
     if(ifiles[i]->kmer_size != kmer_size)
       mcx_die("Graph has different kmer size [kmer_size: %u vs %zu; path: %s]", ifiles[i]->kmer_size, kmer_size, ifiles[i]->path);
-    r = mcx_ctx_load(g, ifiles[i], NULL, output_colours, MCX_LOAD_INTO_ISEC, NULL, NULL, NULL);
-    if(r) die_mcx(r, "loading intersection graph");
-    mcx_load_stats st;
-    r = mcx_graph_sync(g, &st);
-    if(r) die_mcx(r, "loading intersection graph");
+    for(int d = 0; d < ndevices; d++) { /* every replica looks its reads up in the intersection graph */
+      r = mcx_ctx_load(ginit.gs[d], ifiles[i], NULL, output_colours, MCX_LOAD_INTO_ISEC, NULL, NULL, NULL);
+      if(r) die_mcx(r, "loading intersection graph");
+      mcx_load_stats st;
+      r = mcx_graph_sync(ginit.gs[d], &st);
+      if(r) die_mcx(r, "loading intersection graph");
+    }
     mcx_ctx_close(ifiles[i]);
   }
   for(i = 0; i < ngfiles; i++) {
@@ -569,7 +632,7 @@ static int ctx_build(int argc, char **argv)
         mcx_ingest.concurrent = false; mcx_ingest.nfiles = 0;
         g = graph_wait(NULL);
         mcx_load_stats st;
-        r = mcx_graph_sync(g, &st);
+        r = mcx_sync_reads(g, &st);
         if(r) die_mcx(r, "loading sequence");
         mcx_add_load_stats(&tasks[t].stats, &st);
         mcx_phase("sequence files loaded");
@@ -591,6 +654,9 @@ static int ctx_build(int argc, char **argv)
   }
 
   g = graph_wait(NULL);
+  /* several devices: the replicas' tables are folded into the first one (graph files went there alone) */
+  for(int d = 1; d < ndevices; d++) merge_replica(d, (uint32_t)output_colours);
+  if(ndevices > 1) { mcx_load_stats st; r = mcx_graph_sync(g, &st); if(r) die_mcx(r, "merging replicas"); mcx_phase("replicas merged"); }
   /* src/commands/ctx_build.c:409-413 */
   if(nifiles > 0) {
     r = mcx_graph_finish_intersect(g, NULL);

@@ -119,9 +119,15 @@ extern McxGraphSource mcx_graph_source;
 
 /* several files loaded at once (see seq_ingest.c): submissions are serialised, the caller syncs after the last file */
 #include <pthread.h>
-typedef struct { bool concurrent; pthread_mutex_t lock; int nfiles; } McxIngestShared;
+typedef struct {
+  bool concurrent; pthread_mutex_t lock; int nfiles;
+  /* several devices (build -D 0,1,...): every batch goes to the replica route() picks, sync() joins all of them */
+  mcx_graph *(*route)(mcx_graph *g);
+  int (*sync)(mcx_graph *g, mcx_load_stats *st);
+} McxIngestShared;
 extern McxIngestShared mcx_ingest;
 int mcx_submit_reads(mcx_graph *g, const mcx_read_batch *b);
+int mcx_sync_reads(mcx_graph *g, mcx_load_stats *st);
 void mcx_add_load_stats(mcx_load_stats *stats, const mcx_load_stats *st);
 
 /* Parse every read of sf (FASTA / FASTQ / plain, sniffed from the first byte like

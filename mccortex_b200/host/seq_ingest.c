@@ -26,15 +26,16 @@ McxGraphSource mcx_graph_source = {NULL, NULL, NULL};
  * build_graph() call, src/basic/async_read_io.c): the library wants one host thread per graph at a time, so
  * every submission takes mcx_ingest.lock; the loaders do not sync (the counters are the graph's, not a file's) --
  * the caller syncs once after the last file and gets the totals of the whole call. */
-McxIngestShared mcx_ingest = {false, PTHREAD_MUTEX_INITIALIZER, 0};
+McxIngestShared mcx_ingest = {false, PTHREAD_MUTEX_INITIALIZER, 0, NULL, NULL};
 int mcx_submit_reads(mcx_graph *g, const mcx_read_batch *b)
 {
-  if(!mcx_ingest.concurrent) return mcx_graph_add_reads(g, b);
+  if(!mcx_ingest.concurrent) return mcx_graph_add_reads(mcx_ingest.route ? mcx_ingest.route(g) : g, b);
   pthread_mutex_lock(&mcx_ingest.lock);
-  int r = mcx_graph_add_reads(g, b);
+  int r = mcx_graph_add_reads(mcx_ingest.route ? mcx_ingest.route(g) : g, b);
   pthread_mutex_unlock(&mcx_ingest.lock);
   return r;
 }
+int mcx_sync_reads(mcx_graph *g, mcx_load_stats *st) { return mcx_ingest.sync ? mcx_ingest.sync(g, st) : mcx_graph_sync(g, st); }
 #define MCX_RUNAHEAD_BYTES (2048ull << 20)
 
 #define MCX_BATCH_BYTES_DEFAULT (96u << 20)
@@ -396,7 +397,7 @@ int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, m
   int r = L.err;
   if(!mcx_ingest.concurrent) {
     mcx_load_stats st;
-    r = mcx_graph_sync(L.g, &st);
+    r = mcx_sync_reads(L.g, &st);
     if(L.err) r = L.err;
     mcx_add_load_stats(stats, &st);
   }

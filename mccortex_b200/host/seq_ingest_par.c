@@ -331,7 +331,7 @@ bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *pre
   int r = err;
   if(!mcx_ingest.concurrent) {
     mcx_load_stats s;
-    r = mcx_graph_sync(g, &s);
+    r = mcx_sync_reads(g, &s);
     if(err) r = err;
     mcx_add_load_stats(stats, &s);
   }

@@ -396,3 +396,34 @@ def test_cli_join_matches_reference_binary(tmp_path, oracle, k):
     oracle.ref_build(k + 2, ["-s", "x", "-1", fas[0]], other, nkmers="2M")
     assert _run_cmd("join", ["-q", "-f", "-o", mine, a, other], check=False).returncode == 1
     assert _run_cmd("join", ["-q", "-f", "-o", mine, "-i", b, a], check=False).returncode == 1
+
+
+def test_cli_replicas_on_several_devices(tmp_path, oracle):
+    """build -D a,b,c: one replica of the graph per listed device (here three on device 0), batches of reads dealt round
+    robin, replicas folded into the first before the dump (coverage adds, edges OR): same bytes as the oracle's build and as
+    the one-device run, also with --graph (loaded into the first replica only) and --intersect (looked up in every replica)"""
+    rng = random.Random(123)
+    reads = rand_reads(rng, 3000, (20, 250), 15000, perr=0.004)
+    fas = []
+    for i in range(3):
+        p = tmp_path / ("r%d.fa" % i)
+        p.write_text("".join(">r%d\n%s\n" % (j, x) for j, x in enumerate(reads[i * 1000:(i + 1) * 1000])))
+        fas.append(str(p))
+    env = {"MCX_BATCH_BYTES": "20000"}    # many batches, so that every replica gets reads of every file
+    base = ["-q", "-f", "-m", "1G", "-n", "2M", "-k", "27", "-S"]
+    args = ["-s", "a", "-1", fas[0], "-1", fas[1], "-s", "b", "-H", "5", "-1", fas[2]]
+    want, _ = oracle.build_ctx(27, [("a", fas[:2]), ("b", [dict(path=fas[2], hp_cutoff=5)])])
+    one, many = str(tmp_path / "one.ctx"), str(tmp_path / "many.ctx")
+    _run(base + args + [one], env=env)
+    _run(base + ["-D", "0,0,0"] + args + [many], env=env)
+    assert open(one, "rb").read() == want and open(many, "rb").read() == want
+    # --graph + --intersect
+    g0, isec = str(tmp_path / "g0.ctx"), str(tmp_path / "isec.ctx")
+    _run(base + ["-s", "g", "-1", fas[0], g0], env=env)
+    _run(base + ["-s", "i", "-1", fas[1], isec], env=env)
+    args2 = ["-I", isec, "-g", g0, "-s", "n", "-1", fas[2], "-1", fas[0]]
+    _run(base + args2 + [one], env=env)
+    _run(base + ["-D", "0,0"] + args2 + [many], env=env)
+    assert open(one, "rb").read() == open(many, "rb").read() and len(open(one, "rb").read()) > 1000
+    r = _run(base + ["-D", "0,0", "-p", "-s", "x", "-1", fas[0], many], check=False)
+    assert r.returncode == 1 and b"--remove-pcr" in r.stderr
