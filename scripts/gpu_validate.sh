@@ -1,5 +1,6 @@
 #!/bin/bash
-# one gpurun call: GPU parity tests, smoke, N=1 bench, ncu launch list, one ncu --set full capture
+# one gpurun call: GPU parity tests, smoke, N=1 bench + reference arm, ncu launch list, one ncu --set full capture,
+# command line at scale (phases, configs[1])
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
@@ -16,4 +17,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
   python bench.py --reads 10000000 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:mcx_build_fused_kernel -s 1 -c 1 -f -o gpurun_out/fused_full \
   python bench.py --reads 10000000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_bench.log 2>&1
+bash scripts/gpu_cli_phases.sh > gpurun_out/cli_phases.txt 2>&1; tail -12 gpurun_out/cli_phases.txt
+bash scripts/gpu_cli_config2.sh > gpurun_out/cli_config2.txt 2>&1; tail -4 gpurun_out/cli_config2.txt
 ls -la gpurun_out
