@@ -427,3 +427,19 @@ def test_cli_replicas_on_several_devices(tmp_path, oracle):
     assert open(one, "rb").read() == open(many, "rb").read() and len(open(one, "rb").read()) > 1000
     r = _run(base + ["-D", "0,0", "-p", "-s", "x", "-1", fas[0], many], check=False)
     assert r.returncode == 1 and b"--remove-pcr" in r.stderr
+
+
+JOIN_CASES = json.load(open(os.path.join(GOLD, "join_cases.json")))
+
+
+@pytest.mark.parametrize("case", [c["name"] for c in JOIN_CASES])
+def test_cli_join_matches_golden_ctx(case, tmp_path):
+    """`mccortex-b200 join` on committed graph files: bytes == what the compiled reference's join wrote
+    (tests/golden/make_golden_join.py) -- sorted merges and the unsorted single-file stream filter"""
+    c = next(x for x in JOIN_CASES if x["name"] == case)
+    out = str(tmp_path / "out.ctx")
+    _run_cmd("join", ["-q", "-f", "-m", "1G", "-n", "1M"] + (["-S"] if c["sort"] else []) + ["-o", out] +
+             [a.replace("@/", GOLD + "/") for a in c["args"]])
+    ref = open(os.path.join(GOLD, c["ctx"]), "rb").read()
+    assert hashlib.md5(ref).hexdigest() == c["md5"]
+    assert open(out, "rb").read() == ref
