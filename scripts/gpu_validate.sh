@@ -19,4 +19,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:mcx_
   python bench.py --reads 10000000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_bench.log 2>&1
 bash scripts/gpu_cli_phases.sh > gpurun_out/cli_phases.txt 2>&1; tail -12 gpurun_out/cli_phases.txt
 bash scripts/gpu_cli_config2.sh > gpurun_out/cli_config2.txt 2>&1; tail -4 gpurun_out/cli_config2.txt
+# two-pass design probe
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/part_bench scripts/part_bench.cu && timeout 120 /tmp/part_bench 1200 > gpurun_out/part_bench.txt 2>&1; cat gpurun_out/part_bench.txt
 ls -la gpurun_out
