@@ -256,7 +256,7 @@ static void flush_batch(Loader *L)
   mcx_read_batch b;
   if(!prepare_batch(L, &b)) return;
   if(!L->g && mcx_graph_source.wait && mcx_graph_source.ready && !mcx_graph_source.ready(mcx_graph_source.ctx) &&
-     L->pend_bytes + b.nbytes < MCX_RUNAHEAD_BYTES) {
+     L->pend_bytes + b.nbytes < MCX_RUNAHEAD_BYTES / (uint64_t)(mcx_ingest.nfiles > 1 ? mcx_ingest.nfiles : 1)) {
     /* the device is still starting up: keep the batch, go on parsing into fresh buffers */
     if(L->npend == L->pend_cap) {
       L->pend_cap = L->pend_cap ? 2 * L->pend_cap : 16;
