@@ -57,12 +57,21 @@ static size_t batch_bytes(void)
 
 /* The stream is read (and, for .gz, inflated: ~0.3 GB/s, the slowest stage of a gzip'd build) by a thread of its own
  * into two buffers that the parser and the reader swap: inflate and parse overlap instead of alternating. */
+struct Loader;
 struct McxSeqFile {
   char *path;
   gzFile gz;
   unsigned char *in; size_t in_len, in_pos; bool eof;   /* the buffer the parser is consuming */
+  size_t in_raw;                                        /* bytes the reader put there (in_len shrinks when Q9 deletes) */
   unsigned char *buf[2]; int nread[2]; int full[2];     /* full[i]: buf[i] holds nread[i] bytes (<= 0: end / error) for the parser */
   int cur;                                              /* index of the parser's buffer, -1 before the first refill */
+  /* quirk Q9 (see q9_apply): lines to delete from the stream at q9_at */
+  uint64_t pd_off;                                      /* offset of in[0] in the stream AFTER deletions (what the parser has been given so far) */
+  uint64_t q9_at;                                       /* where (same coordinates) the pending deletions start */
+  uint32_t q9_lines; bool q9_mid;                       /* lines still to delete; the deletion continues at in[0] of the next buffer */
+  /* how the next record is read (see next_record) */
+  bool unknown, lookahead; uint64_t la_bases;
+  int (*rec_fn)(McxSeqFile *, struct Loader *);
   bool started, stop;
   pthread_t thread; pthread_mutex_t mu; pthread_cond_t cv;
 };
@@ -92,7 +101,7 @@ McxSeqFile *mcx_seq_open(const char *path)
   sf->gz = strcmp(path, "-") == 0 ? gzdopen(0, "r") : gzopen(path, "r");
   if(!sf->gz) { free(sf->path); free(sf); return NULL; }
   gzbuffer(sf->gz, 1u << 20);
-  sf->cur = -1;
+  sf->cur = -1; sf->unknown = true; sf->lookahead = true;
   pthread_mutex_init(&sf->mu, NULL); pthread_cond_init(&sf->cv, NULL);
   return sf;
 }
@@ -119,6 +128,37 @@ int64_t mcx_seq_file_size(const McxSeqFile *sf)
 }
 
 /* ---- byte stream with getc / ungetc / "rest of line" ------------------------- */
+/* Quirk Q9 [probed against the compiled reference, found by tests/test_host_fuzz.py].  The reference reads a record
+ * through _read_unknown (libs/seq_file/seq_file.h:311-323) -- white space in front of the record is skipped, the first
+ * other byte picks the format -- not only for the first record: seq_get_qual_limits buffers reads worth 1000 bases with
+ * it before anything is parsed (seq_file.h:359-377,636-660; src/basic/seq_reader.c:436), and with an explicit
+ * --fq-offset nothing ever replaces it (seq_file.h:97,337,437).  In that function a white-space byte other than '\n' is
+ * meant to skip the rest of its line, but the buffered readers are instantiated with the UNBUFFERED skipline
+ * (seq_file.h:426-427), which reads from the file behind the 1 MB stream buffer (DEFAULT_BUFSIZE, :129,:580).  So the
+ * current line is NOT skipped (only the byte is), and the stream loses, per such byte, the bytes from the end of the
+ * buffered megabyte through the next '\n' -- nothing, if the file ends inside that megabyte.  Every fill reads exactly
+ * 2^20 bytes of what is left of the stream, so in the coordinates of the stream after deletions the place is the next
+ * multiple of 2^20 behind the byte just read.  Deleted here in place, in the part of the buffer the parser has not
+ * seen yet, or when the buffer that holds the place arrives. */
+static void q9_apply(McxSeqFile *sf)
+{
+  size_t at;
+  if(sf->q9_mid) at = 0;
+  else if(sf->pd_off + sf->in_len <= sf->q9_at) return;         /* the place is not in this buffer yet */
+  else at = sf->q9_at <= sf->pd_off ? 0 : (size_t)(sf->q9_at - sf->pd_off);
+  if(at < sf->in_pos) at = sf->in_pos;
+  while((sf->q9_lines || sf->q9_mid) && at < sf->in_len) {
+    if(!sf->q9_mid) { sf->q9_lines--; sf->q9_mid = true; }      /* start deleting one more line */
+    unsigned char *nl = memchr(sf->in + at, '\n', sf->in_len - at);
+    const size_t end = nl ? (size_t)(nl - sf->in) + 1 : sf->in_len;
+    memmove(sf->in + at, sf->in + end, sf->in_len - end);
+    sf->in_len -= end - at;
+    if(nl) sf->q9_mid = false;
+  }
+}
+/* the white space in front of the first record (seq_file.h:316), with quirk Q9 */
+static int sniff_skip_space(McxSeqFile *sf);
+
 static bool refill(McxSeqFile *sf)
 {
   if(sf->eof) return false;
@@ -135,7 +175,10 @@ static bool refill(McxSeqFile *sf)
   const int n = sf->nread[sf->cur];
   pthread_mutex_unlock(&sf->mu);
   if(n <= 0) { sf->eof = true; sf->in_len = sf->in_pos = 0; return false; }
-  sf->in = sf->buf[sf->cur]; sf->in_len = (size_t)n; sf->in_pos = 0;
+  sf->pd_off += sf->in_len;
+  sf->in = sf->buf[sf->cur]; sf->in_len = sf->in_raw = (size_t)n; sf->in_pos = 0;
+  if(sf->q9_lines || sf->q9_mid) q9_apply(sf);
+  if(sf->in_len == 0) return refill(sf); /* (everything of this buffer was deleted) */
   return true;
 }
 static inline int sgetc(McxSeqFile *sf)
@@ -180,12 +223,25 @@ static inline void chomp_from(Buf *b, size_t floor_len)
   while(b->len > floor_len && (b->b[b->len - 1] == '\n' || b->b[b->len - 1] == '\r')) b->len--;
 }
 static inline bool is_space(int c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+static int sniff_skip_space(McxSeqFile *sf)
+{
+  int c;
+  while((c = sgetc(sf)) != -1 && is_space(c))
+    if(c != '\n') { /* not the rest of this line: a line at the end of the reference's stream buffer (Q9) */
+      const uint64_t p = sf->pd_off + sf->in_pos;   /* bytes given to the parser so far, this one included */
+      if(!sf->q9_lines && !sf->q9_mid) sf->q9_at = (((p - 1) >> 20) + 1) << 20;
+      sf->q9_lines++;
+      q9_apply(sf);
+    }
+  return c;
+}
 
 /* ---- loader state ---------------------------------------------------------------- */
 typedef McxQStat QStat;
 typedef struct { mcx_read_batch b; char *seq, *qual; } PendingBatch; /* parsed before the graph existed */
-typedef struct {
+typedef struct Loader {
   mcx_graph *g; const McxLoadPrefs *prefs; mcx_load_stats *stats;
+  size_t last_seqlen;  /* length of the record just read (look-ahead accounting of next_record) */
   PendingBatch *pend; size_t npend, pend_cap; uint64_t pend_bytes;
   Buf lines;          /* LINES batch under construction */
   Buf qlines;         /* quality bytes parallel to `lines` (only when a quality cut-off is set) */
@@ -279,6 +335,7 @@ static void flush_batch(Loader *L)
 static void end_read(Loader *L, size_t start)
 {
   size_t seqlen = L->lines.len - start;
+  L->last_seqlen = seqlen;
   QStat *qs = &L->qs[L->cur];
   if(L->qual.len && qs->bcount < 1000) {
     size_t lim = 1000 - qs->qcount, n = L->qual.len < lim ? L->qual.len : lim, i;
@@ -386,6 +443,26 @@ static int read_plain(McxSeqFile *sf, Loader *L)
   return 1;
 }
 
+/* One record, the way the reference gets it (quirk Q9 above): while the file is in `unknown` mode -- the reads worth
+ * the first 1000 bases, or every read when --fq-offset was given -- white space in front of the record is skipped byte
+ * by byte and the record's own first byte picks the reader; afterwards the reader of the last such record serves the
+ * rest of the file.  Returns what the readers return: 1, 0 at the end, -1 on a truncated record. */
+static int next_record(McxSeqFile *sf, Loader *L)
+{
+  if(sf->unknown) {
+    const int c = sniff_skip_space(sf);
+    if(c == -1) return 0;
+    sf->in_pos--; /* ungetc: the byte came from the current buffer */
+    sf->rec_fn = c == '@' ? read_fastq : (c == '>' ? read_fasta : read_plain);
+  }
+  const int s = sf->rec_fn(sf, L);
+  if(s > 0 && sf->unknown && sf->lookahead) {
+    sf->la_bases += L->last_seqlen;
+    if(sf->la_bases >= 1000) sf->unknown = false; /* _seq_buffer_reads stops here; the format reader takes over */
+  }
+  return s;
+}
+
 void mcx_add_load_stats(mcx_load_stats *stats, const mcx_load_stats *st)
 {
   stats->total_bases_read += st->total_bases_read;
@@ -411,24 +488,18 @@ int mcx_load_seq_file(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *prefs, m
 
   if(!pr.resume) mcx_status("[seq] Parsing sequence file %s", sf->path);
 
-  /* format sniff, seq_file.h:311-323 */
-  int c, s = 0;
-  int (*reader)(McxSeqFile *, Loader *) = NULL;
+  int s = 0;
+  sf->lookahead = prefs->fq_offset == 0; /* seq_reader.c:436: the look-ahead only runs when the offset is to be guessed */
   if(pr.resume) {
+    /* the multi-threaded reader has taken the strict FASTQ records up to pr.offset (>= 1000 bases: format known) */
     if(pr.g) L.g = pr.g;
     L.qs[0] = pr.qs; L.any_qual = pr.any_qual; L.offset_known = pr.offset_known; L.fq_offset = pr.fq_offset;
     L.nreads_total = pr.nreads;
     if(gzseek(sf->gz, (z_off_t)pr.offset, SEEK_SET) < 0) mcx_die("Cannot seek in %s", sf->path);
     sf->in_len = sf->in_pos = 0; sf->eof = false;
-    while((s = read_fastq(sf, &L)) > 0 && !L.err) {}
-    c = -1;
+    if(sf->lookahead) { sf->unknown = false; sf->rec_fn = read_fastq; }
   }
-  else while((c = sgetc(sf)) != -1 && is_space(c)) if(c != '\n') sreadline(sf, NULL);
-  if(c != -1) {
-    reader = c == '@' ? read_fastq : (c == '>' ? read_fasta : read_plain);
-    sf->in_pos--; /* ungetc: the byte came from the current buffer */
-    while((s = reader(sf, &L)) > 0 && !L.err) {}
-  }
+  while((s = next_record(sf, &L)) > 0 && !L.err) {}
   flush_batch(&L);
   if(s < 0 && !L.err) mcx_warn("Input error: %s\n", sf->path);
   mcx_phase("  parsed");
@@ -502,15 +573,6 @@ static void flush_batch_pcr(Loader *L, size_t n)
   L->nreads -= n;
 }
 
-typedef int (*ReaderFn)(McxSeqFile *, Loader *);
-static ReaderFn sniff_reader(McxSeqFile *sf)
-{
-  int c;
-  while((c = sgetc(sf)) != -1 && is_space(c)) if(c != '\n') sreadline(sf, NULL);
-  if(c == -1) return NULL;
-  sf->in_pos--;
-  return c == '@' ? read_fastq : (c == '>' ? read_fasta : read_plain);
-}
 
 int mcx_load_seq_pcr(mcx_graph *g, McxSeqFile *sf1, McxSeqFile *sf2, bool interleaved, const McxLoadPrefs *prefs,
                      mcx_load_stats *stats)
@@ -529,15 +591,16 @@ int mcx_load_seq_pcr(mcx_graph *g, McxSeqFile *sf1, McxSeqFile *sf2, bool interl
   else if(interleaved) mcx_status("[seq] Reading a (possibly) interleaved file (expect both S.E. & P.E. reads)");
   else mcx_status("[seq] Parsing sequence file %s", sf1->path);
 
-  ReaderFn rd1 = sniff_reader(sf1), rd2 = sf2 ? sniff_reader(sf2) : NULL;
+  sf1->lookahead = prefs->fq_offset == 0;
+  if(sf2) sf2->lookahead = prefs->fq_offset == 0;
   if(sf2) {
     for(;;) {
       const size_t n_before = L.nreads, len_before = L.lines.len, qlen_before = L.qlines.len;
       const uint64_t total_before = L.nreads_total;
       L.cur = 0; L.next_flip = flip1;
-      s1 = rd1 ? rd1(sf1, &L) : 0;
+      s1 = next_record(sf1, &L);
       L.cur = 1; L.next_flip = flip2;
-      s2 = rd2 ? rd2(sf2, &L) : 0;
+      s2 = next_record(sf2, &L);
       if(s1 < 0) mcx_warn("input error: %s", sf1->path);
       if(s2 < 0) mcx_warn("input error: %s", sf2->path);
       if((s1 > 0) != (s2 > 0) && !(s1 < 0 || s2 < 0)) mcx_warn("Different number of reads in pe files [%s; %s]\n", sf1->path, sf2->path);
@@ -559,7 +622,7 @@ int mcx_load_seq_pcr(mcx_graph *g, McxSeqFile *sf1, McxSeqFile *sf2, bool interl
     for(;;) {
       L.next_flip = pending ? flip2 : flip1;
       size_t before = L.nreads;
-      s1 = rd1 ? rd1(sf1, &L) : 0;
+      s1 = next_record(sf1, &L);
       if(s1 <= 0) break;
       buf_push(&L.name, '\0'); L.name.len--;
       if(pending && names_cmp(prev_name.b, L.name.b) == 0) {
@@ -583,7 +646,7 @@ int mcx_load_seq_pcr(mcx_graph *g, McxSeqFile *sf1, McxSeqFile *sf2, bool interl
     free(prev_name.b);
   } else {
     L.cur = 0; L.next_flip = flip1;
-    while((s1 = rd1 ? rd1(sf1, &L) : 0) > 0 && !L.err) {
+    while((s1 = next_record(sf1, &L)) > 0 && !L.err) {
       num_se++;
       if(L.lines.len >= MCX_BATCH_BYTES) flush_batch_pcr(&L, L.nreads);
     }

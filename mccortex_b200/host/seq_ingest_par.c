@@ -214,12 +214,10 @@ bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *pre
   size_t p0 = 0;
   bool ok = !(d[0] == 0x1f && d[1] == 0x8b);
   if(ok) {
-    /* the sequential sniff skips the REST OF THE LINE after a leading white-space byte other than '\n' */
-    while(p0 < size && par_is_space(d[p0])) {
-      if(d[p0] != '\n') { const unsigned char *nl = memchr(d + p0, '\n', size - p0); p0 = nl ? (size_t)(nl - d) + 1 : size; }
-      else p0++;
-    }
-    ok = p0 < size;
+    /* leading blank lines are skipped; a file that begins with other white space is left to the sequential reader
+     * (quirk Q9 of seq_ingest.c: the reference then drops lines at file offset 2^20) */
+    while(p0 < size && d[p0] == '\n') p0++;
+    ok = p0 < size && !par_is_space(d[p0]);
   }
   if(!ok) { munmap((void *)d, size); return false; }
 
@@ -227,6 +225,25 @@ bool mcx_load_seq_file_par(mcx_graph *g, McxSeqFile *sf, const McxLoadPrefs *pre
   ps.data = d; ps.size = size; ps.fmt = d[p0] == '>' ? FMT_FASTA : (d[p0] == '@' ? FMT_FASTQ : FMT_PLAIN);
   ps.want_qual = ps.fmt == FMT_FASTQ && prefs->fq_cutoff != 0;
   McxQStat qs = resume->qs;
+  if(ps.fmt == FMT_PLAIN) {
+    /* The reference picks the reader per record while it is in its look-ahead (the reads worth the first 1000 bases;
+     * every read when --fq-offset is given): see next_record / quirk Q9 in seq_ingest.c.  For FASTA and FASTQ that is the
+     * same thing -- their readers stop on the next record's '>' / '@' -- but a line of a plain file that starts with
+     * '>', '@' or white space is read differently there.  Such files are left to the sequential reader. */
+    bool plain_ok = prefs->fq_offset == 0;
+    size_t p = p0, bases = 0;
+    while(plain_ok && p < size && bases < 1000) {
+      const unsigned char c = d[p];
+      const unsigned char *nl = memchr(d + p, '\n', size - p);
+      size_t end = nl ? (size_t)(nl - d) : size, len;
+      if(c == '\n') { p++; continue; }
+      if(c == '>' || c == '@' || par_is_space(c)) plain_ok = false;
+      for(len = end - p; len && (d[p + len - 1] == '\r'); len--) {}
+      bases += len;
+      p = nl ? end + 1 : size;
+    }
+    if(!plain_ok) { munmap((void *)d, size); return false; }
+  }
   if(ps.fmt == FMT_FASTQ) {
     /* quality range of the first reads (until 1000 bases have been seen), exactly as the sequential reader collects
      * it (end_read, seq_ingest.c) -- it decides the ASCII offset at the first batch.  If the file stops being strict

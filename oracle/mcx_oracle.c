@@ -803,23 +803,44 @@ static void orc_pushc(char **dst, size_t *len, size_t *cap, char ch)
 static int orc_isspace(int c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
 /* returns number of reads, or -(reads+1) on a malformed record (the reference
- * stops at the first malformed record, seq_reader.c:445-452) */
-long orc_parse_buffer(const char *buf, size_t n, orc_read_cb cb, void *ctx)
+ * stops at the first malformed record, seq_reader.c:445-452).
+ *
+ * How the reference really reads records [probed against the compiled reference]: through _read_unknown
+ * (seq_file.h:311-323) -- skip white space, let the first other byte pick FASTQ / FASTA / plain for THIS record -- as
+ * long as sf->readfunc is that function: for the reads worth the first 1000 bases that seq_get_qual_limits buffers when
+ * the FASTQ offset is to be guessed (seq_file.h:359-377,636-660, seq_reader.c:436; afterwards _seq_read_pop installs the
+ * reader of the last record's format, :337), and for every read when an offset was given (`lookahead` = 0).  And in
+ * _read_unknown the buffered readers are instantiated with the UNBUFFERED skipline (seq_file.h:426-427): after a
+ * white-space byte other than '\n' it is not the rest of the current line that goes but a line of the FILE, at the
+ * position the 1 MB stream buffer (DEFAULT_BUFSIZE) has read up to -- in the coordinates of the stream after such
+ * deletions, the next multiple of 2^20 behind the byte; nothing if the stream ends before that. */
+long orc_parse_buffer_la(const char *buf, size_t n, int lookahead, orc_read_cb cb, void *ctx)
 {
-  OrcCur cur = { buf, buf + n };
+  char *w = (char*)malloc(n + 1);
+  size_t wn = n, la_bases = 0;
+  memcpy(w, buf, n);
+  OrcCur cur = { w, w + wn };
   char *name = NULL, *seq = NULL, *qual = NULL;
   size_t nl = 0, nc = 0, sl = 0, sc = 0, ql = 0, qc = 0;
-  long nreads = 0; int c, fmt = 0, bad = 0; /* fmt: 1 fastq 2 fasta 3 plain */
+  long nreads = 0; int c, fmt = 0, bad = 0, unknown = 1; /* fmt: 1 fastq 2 fasta 3 plain */
   orc_pushc(&name, &nl, &nc, 0); orc_pushc(&seq, &sl, &sc, 0); orc_pushc(&qual, &ql, &qc, 0);
-
-  /* _read_unknown, seq_file.h:311-323 */
-  while((c = orc_getc(&cur)) != -1 && orc_isspace(c)) if(c != '\n') { while((c = orc_getc(&cur)) != -1 && c != '\n') {} }
-  if(c == -1) goto done;
-  fmt = c == '@' ? 1 : (c == '>' ? 2 : 3);
-  cur.p--;
 
   for(;;) {
     nl = sl = ql = 0; name[0] = seq[0] = qual[0] = 0;
+    if(unknown) {
+      while((c = orc_getc(&cur)) != -1 && orc_isspace(c)) if(c != '\n') {
+        size_t p = (size_t)(cur.p - w), at = (((p - 1) >> 20) + 1) << 20;
+        if(at < wn) {
+          const char *e = (const char*)memchr(w + at, '\n', wn - at);
+          size_t to = e ? (size_t)(e - w) + 1 : wn;
+          memmove(w + at, w + to, wn - to);
+          wn -= to - at; cur.end = w + wn;
+        }
+      }
+      if(c == -1) break;
+      fmt = c == '@' ? 1 : (c == '>' ? 2 : 3);
+      cur.p--;
+    }
     if(fmt == 1) { /* seq_file.h:245-272 */
       c = orc_getc(&cur);
       if(c == -1) break;
@@ -867,11 +888,12 @@ long orc_parse_buffer(const char *buf, size_t n, orc_read_cb cb, void *ctx)
     orc_cur_name = name;
     cb(seq, sl, ql ? qual : NULL, ql, ctx);
     nreads++;
+    if(unknown && lookahead) { la_bases += sl; if(la_bases >= 1000) unknown = 0; }
   }
-done:
-  free(name); free(seq); free(qual);
+  free(name); free(seq); free(qual); free(w);
   return bad ? -(nreads + 1) : nreads;
 }
+long orc_parse_buffer(const char *buf, size_t n, orc_read_cb cb, void *ctx) { return orc_parse_buffer_la(buf, n, 1, cb, ctx); }
 
 typedef struct { OrcGraph *g; size_t colour; uint8_t fq_cutoff, fq_offset, hp_cutoff; OrcStats *st; } OrcLoadCtx;
 static void orc_load_cb(const char *seq, size_t sl, const char *qual, size_t ql, void *ctx)
@@ -933,9 +955,10 @@ long orc_graph_load_file(OrcGraph *g, const char *path, size_t colour,
   size_t n; long r;
   char *buf = orc_slurp(path, &n);
   if(!buf) return -1000000000L;
+  const int lookahead = fq_offset == 0; /* reads are only buffered for the offset guess when none was given */
   if(fq_offset == 0) fq_offset = (uint8_t)orc_guess_fq_offset(buf, n);
   OrcLoadCtx c = { g, colour, fq_cutoff, fq_offset, hp_cutoff, st };
-  r = orc_parse_buffer(buf, n, orc_load_cb, &c);
+  r = orc_parse_buffer_la(buf, n, lookahead, orc_load_cb, &c);
   free(buf);
   return r;
 }
@@ -985,8 +1008,8 @@ long orc_graph_load_pcr(OrcGraph *g, const char *path1, const char *path2, int m
   if(!b1) return -1000000000L;
   if(mode == 1) { b2 = orc_slurp(path2, &n2); if(!b2) { free(b1); return -1000000000L; } }
   if(fq_offset == 0) { off1 = (uint8_t)orc_guess_fq_offset(b1, n1); if(b2) off2 = (uint8_t)orc_guess_fq_offset(b2, n2); }
-  orc_parse_buffer(b1, n1, orc_collect_cb, &v1);
-  if(b2) orc_parse_buffer(b2, n2, orc_collect_cb, &v2);
+  orc_parse_buffer_la(b1, n1, fq_offset == 0, orc_collect_cb, &v1);
+  if(b2) orc_parse_buffer_la(b2, n2, fq_offset == 0, orc_collect_cb, &v2);
   if(mode == 0) {
     for(i = 0; i < v1.n; i++, used++)
       orc_graph_add_reads_pcr(g, v1.r[i].seq, v1.r[i].sl, v1.r[i].qual, v1.r[i].ql, NULL, 0, NULL, 0,

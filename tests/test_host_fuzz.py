@@ -1,0 +1,130 @@
+"""Seeded fuzz of the sequence ingest against the COMPILED REFERENCE: small FASTA / FASTQ / plain files
+with the oddities real files have and a few they should not (CR LF, blank lines, multi-line records, '>' '@' '+' where they
+do not belong, missing final newline, truncated records, leading white space, lower case, N) go through
+`mccortex31 build -S` and through the host driver linked against the oracle-backed ABI stand-in (tests/emul/hostcheck):
+same exit status and, when both succeed, the same bytes.  Sequential reader and the multi-threaded one (tiny segments)."""
+import os
+import random
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+REF = os.path.join(ROOT, "oracle", "_ref", "mccortex31")
+pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref not built")
+
+
+def _seq(rng, lo=0, hi=60):
+    return "".join(rng.choice("ACGTACGTACGTacgtN") for _ in range(rng.randint(lo, hi)))
+
+
+def _eol(rng):
+    return rng.choice(["\n", "\n", "\n", "\n", "\r\n"])
+
+
+def _fasta(rng):
+    out = []
+    for _ in range(rng.randint(1, 25)):
+        out.append(">" + rng.choice(["", "r", "r 1 >x", "@weird +", "\tname"]) + _eol(rng))
+        for _ in range(rng.choice([0, 1, 1, 1, 2, 3])):
+            line = _seq(rng, 1)
+            if rng.random() < 0.05:
+                line = rng.choice([">", "@", "+", " ", "\t"]) + line          # odd first bytes inside a record
+            out.append(line + _eol(rng))
+            if rng.random() < 0.08:
+                out.append(rng.choice(["\n", "\r\n", "\r", " \n"]))
+    return "".join(out)
+
+
+def _fastq(rng):
+    out = []
+    for _ in range(rng.randint(1, 25)):
+        s = _seq(rng, 0, 50)
+        q = "".join(rng.choice("!#+5@>IIIIII") for _ in s)
+        kind = rng.random()
+        if kind < 0.75:
+            out.append("@r" + _eol(rng) + s + _eol(rng) + "+" + rng.choice(["", "r"]) + _eol(rng) + q + _eol(rng))
+        elif kind < 0.85 and len(s) > 3:      # multi-line
+            h = len(s) // 2
+            out.append("@r\n%s\n%s\n+\n%s\n%s\n" % (s[:h], s[h:], q[:h], q[h:]))
+        elif kind < 0.92:                     # quality shorter / longer than the sequence
+            out.append("@r\n%s\n+\n%s\n" % (s, (q + "III")[:rng.randint(0, len(q) + 3)]))
+        else:                                 # junk between records
+            out.append("@r\n%s\n+\n%s\n%s\n" % (s, q, rng.choice(["junk", "", " x", "+"])))
+    return "".join(out)
+
+
+def _plain(rng):
+    out = []
+    for _ in range(rng.randint(1, 40)):
+        r = rng.random()
+        if r < 0.8:
+            out.append(_seq(rng, 1) + _eol(rng))
+        elif r < 0.9:
+            out.append(rng.choice(["", " skipped", "\tskipped ACGTACGTACGTACGT", "\r"]) + "\n")
+        else:
+            out.append(_seq(rng, 1) + rng.choice(["\r\r\n", " trailing\n", "\t\n"]))
+    return "".join(out)
+
+
+def _run(exe, args, env=None):
+    return subprocess.run([exe, "build", "-q", "-f", "-m", "1G", "-n", "100K"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                          env=dict(os.environ, **env) if env else None)
+
+
+@pytest.mark.parametrize("block", range(10))
+def test_ingest_fuzz_against_the_reference_binary(hostcheck, tmp_path, block):
+    for case in range(40):
+        rng = random.Random(1000 * block + case)
+        text = rng.choice([_fasta, _fasta, _fastq, _fastq, _plain])(rng)
+        if rng.random() < 0.3 and text.endswith("\n"):
+            text = text[:-1]                                      # no final newline
+        if rng.random() < 0.1:
+            text = rng.choice(["\n", " lead\n", "\r\n\n"]) + text   # leading white space / skipped first line
+        if rng.random() < 0.1:
+            text = text[:rng.randint(0, len(text))]               # truncated anywhere
+        path = tmp_path / ("in%d.txt" % case)
+        path.write_bytes(text.encode())
+        k = rng.choice([5, 11, 21])
+        extra = rng.choice([[], [], ["-Q", "10"], ["-H", "3"], ["-Q", "20", "-H", "4"], ["-O", "33"], ["-O", "64", "-Q", "5"]])
+        args = ["-k", str(k), "-S"] + extra + ["-s", "s", "-1", str(path)]
+        ref_out, out = str(tmp_path / "ref.ctx"), str(tmp_path / "mine.ctx")
+        r = _run(REF, ["-t", "1"] + args + [ref_out])
+        want = open(ref_out, "rb").read() if r.returncode == 0 else None
+        for env in ({"MCX_PARSE_THREADS": "1"}, {"MCX_PARSE_THREADS": "3", "MCX_PARSE_SEG_BYTES": str(rng.choice([16, 64, 300]))}):
+            m = _run(hostcheck, args + [out], env=env)
+            assert (m.returncode == 0) == (r.returncode == 0), (block, case, env, text[:200], m.stderr[-300:], r.stderr[-300:])
+            if want is not None:
+                assert open(out, "rb").read() == want, (block, case, env, text[:300])
+
+
+@pytest.mark.parametrize("lead,kind,extra", [(" x", "plain", []), ("\t\t", "plain", []), (" ", "fasta", []), ("\r\n \n", "fastq", ["-Q", "10"]),
+                                             ("", "plain_ws_inside", []), ("", "plain_ws_inside", ["-O", "33"])])
+def test_ingest_quirk_q9_beyond_one_megabyte(hostcheck, tmp_path, lead, kind, extra):
+    """files of ~2.5 MB: white space in front of a record that the reference reads through _read_unknown makes it drop
+    lines at the end of its 1 MB stream buffer (quirk Q9, seq_ingest.c) -- same bytes here, sequential and threaded"""
+    rng = random.Random(len(lead) * 7 + len(kind))
+    recs = []
+    for i in range(30000):
+        s = "".join(rng.choice("ACGT") for _ in range(rng.randint(40, 100)))
+        if kind == "fasta":
+            recs.append(">r%d\n%s\n" % (i, s))
+        elif kind == "fastq":
+            recs.append("@r%d\n%s\n+\n%s\n" % (i, s, "I" * len(s)))
+        elif kind == "plain_ws_inside":
+            recs.append(("\t" if i in (3, 5, 20000) else "") + s + "\n")   # two inside the look-ahead, one far behind it
+        else:
+            recs.append(s + "\n")
+    path = tmp_path / "big.txt"
+    path.write_bytes((lead + "".join(recs)).encode())
+    args = ["-k", "21", "-S"] + extra + ["-s", "s", "-1", str(path)]
+    ref_out, out = str(tmp_path / "ref.ctx"), str(tmp_path / "mine.ctx")
+    r = subprocess.run([REF, "build", "-q", "-f", "-m", "1G", "-n", "4M", "-t", "1"] + args + [ref_out], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0
+    want = open(ref_out, "rb").read()
+    for env in ({"MCX_PARSE_THREADS": "1"}, {"MCX_PARSE_THREADS": "4", "MCX_PARSE_SEG_BYTES": "200000"}):
+        m = subprocess.run([hostcheck, "build", "-q", "-f", "-m", "1G", "-n", "4M"] + args + [out], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           env=dict(os.environ, **env))
+        assert m.returncode == 0, m.stderr[-500:]
+        assert open(out, "rb").read() == want, env

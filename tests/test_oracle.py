@@ -295,7 +295,7 @@ def test_parallel_ingest_matches_sequential_reader(ingest_dump, tmp_path, kind, 
     multi-line records, CR LF, empty lines, '>' and '@' inside headers, leading white-space lines, odd file ends"""
     rng = random.Random(seg)
     if kind == "fasta":
-        txt = " skipped line\n\n" + _tricky_fasta(rng, 600) + tail
+        txt = "\n\n" + _tricky_fasta(rng, 600) + tail
     else:
         lines = []
         for _ in range(3000):
