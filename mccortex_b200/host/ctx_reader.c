@@ -39,6 +39,22 @@ static int range_get_num(const char *str, size_t range_max)
   }
   return n == 0 ? (int)(range_max + 1) : (int)n;
 }
+/* A backward range a-b (a > b) does not stop at b in the reference: its loop is `for(j = start; j <= start; j--)`
+ * (src/basic/range.c:67-68), so it emits a, a-1, ..., 0 -- more entries than range_get_num counted, which shifts what
+ * follows (a colour filter uses the first range_get_num() entries, file_filter.c:119-122; an `into` list of the wrong
+ * length is an error, range.c:107-109) and overruns the reference's scratch array.  Same entries here, in an array
+ * that is large enough (range_emitted).  [found by tests/test_host_fuzz.py against the compiled reference] */
+static size_t range_emitted(const char *str, size_t range_max)
+{
+  const char *ptr = str; size_t n = 0, start, end; int bytes;
+  while(*ptr != '\0') {
+    if((bytes = range_parse(ptr, &start, &end, range_max)) == -1) return n;
+    ptr += bytes;
+    if(*ptr == ',') ptr++;
+    n += start <= end ? end - start + 1 : start + 1;
+  }
+  return n;
+}
 static int range_parse_array(const char *str, size_t *arr, size_t range_max)
 {
   const char *ptr = str; size_t n = 0, j, start, end; int bytes;
@@ -47,7 +63,7 @@ static int range_parse_array(const char *str, size_t *arr, size_t range_max)
     ptr += bytes;
     if(*ptr == ',') ptr++;
     if(start <= end) for(j = start; j <= end; j++) arr[n++] = j;
-    else for(j = start; j <= start; j--) { arr[n++] = j; if(j == end) break; }
+    else for(j = start; j <= start; j--) arr[n++] = j;
   }
   if(ptr > str && *(ptr - 1) == ',') return -1;
   if(n == 0) for(n = 0; n <= range_max; n++) arr[n] = n;
@@ -100,7 +116,12 @@ static void filter_set_cols(McxCtxFile *f, size_t srcncols, size_t into_offset)
     int s = range_get_num(into_fltr, SIZE_MAX);
     if(s < 0 || (s != 1 && (size_t)s != ncols)) mcx_die("Invalid filter path: %s (s:%i ncols:%zu)", f->input, s, ncols);
   }
-  size_t *tmp = calloc(ncols > srcncols ? ncols : srcncols, sizeof(size_t));
+  size_t tmp_n = ncols > srcncols ? ncols : srcncols, e;
+  if(from_fltr && (e = range_emitted(from_fltr, srcncols - 1)) > tmp_n) tmp_n = e;
+  if(into_fltr && (e = range_emitted(into_fltr, SIZE_MAX)) > tmp_n) tmp_n = e;
+  if(tmp_n > ((size_t)1 << 28)) mcx_die("Invalid filter path: %s", f->input);
+  size_t *tmp = calloc(tmp_n + 1, sizeof(size_t));
+  if(!tmp) mcx_die("Out of memory");
   uint32_t *pairs = calloc(ncols, 2 * sizeof(uint32_t));
   if(from_fltr) {
     if(range_parse_array(from_fltr, tmp, srcncols - 1) == -1) mcx_die("Invalid filter path: %s", f->input);

@@ -213,8 +213,10 @@ class Graph:
         return buf.raw[:n]
 
 
-def _parse_range(s, range_max):
-    """src/basic/range.c: '1,3-5' -> [1,3,4,5]; '' -> 0..range_max; descending ranges stop at their end"""
+def _parse_range(s, range_max, count_only=False):
+    """src/basic/range.c: '1,3-5' -> [1,3,4,5]; '' -> 0..range_max.  A descending range a-b does NOT stop at b in the
+    reference (range.c:67-68: `for(j = start; j <= start; j--)`): it emits a, a-1, ..., 0 -- while range_get_num
+    (:39-55) counts |a-b|+1 entries; count_only returns that count.  [probed against the compiled reference]"""
     out = []
     for part in [p for p in s.split(",") if p != ""]:
         if part == "*":
@@ -225,7 +227,10 @@ def _parse_range(s, range_max):
         b = int(b) if b != "" else a
         if a > range_max or b > range_max:
             raise ValueError("Invalid filter path")
-        out += list(range(a, b + 1)) if a <= b else list(range(a, b - 1, -1))
+        if count_only:
+            out += [0] * (abs(a - b) + 1)
+        else:
+            out += list(range(a, b + 1)) if a <= b else list(range(a, -1, -1))
     return out if out else list(range(0, range_max + 1))
 
 
@@ -260,7 +265,8 @@ class CtxFile:
         self.hdr_size = off
         self.rec_bytes = 8 * self.W + 5 * self.ncols
         self.records = data[off:off + (len(data) - off) // self.rec_bytes * self.rec_bytes]
-        frm = _parse_range(from_f or "", self.ncols - 1)
+        # file_filter_set_cols (file_filter.c:94-138): the FIRST range_get_num() entries of the parsed `from` list are used
+        frm = _parse_range(from_f or "", self.ncols - 1)[:len(_parse_range(from_f or "", self.ncols - 1, count_only=True))]
         if into_f is not None:
             into = _parse_range(into_f, 1 << 30)
             if len(into) == 1:

@@ -128,3 +128,102 @@ def test_ingest_quirk_q9_beyond_one_megabyte(hostcheck, tmp_path, lead, kind, ex
                            env=dict(os.environ, **env))
         assert m.returncode == 0, m.stderr[-500:]
         assert open(out, "rb").read() == want, env
+
+
+def _names(rng, i):
+    base = rng.choice(["r%d" % i, "read%d" % (i // 2), "x"])
+    return base + rng.choice(["", "/1", "/2", " extra", "\textra", "/1 more", "/3"])
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_remove_pcr_ingest_fuzz_against_the_reference_binary(hostcheck, tmp_path, block):
+    """--remove-pcr with --seq, --seq2 (files of different lengths and formats) and --seqi (names that do and do not
+    pair), --matepair, cut-offs: the pairing, the order and the duplicate test are those of `mccortex31 build -t 1`"""
+    for case in range(12):
+        rng = random.Random(7000 + 100 * block + case)
+        sites = [_seq(rng, 25, 60).upper().replace("N", "A") for _ in range(6)]
+
+        def read():
+            s = rng.choice(sites)[rng.randint(0, 3):]
+            if rng.random() < 0.3:
+                s = s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+            return s[:rng.randint(5, len(s))]
+
+        def write(path, n, fq):
+            with open(path, "w") as f:
+                for i in range(n):
+                    s = read()
+                    if fq:
+                        f.write("@%s\n%s\n+\n%s\n" % (_names(rng, i), s, "".join(rng.choice("#5III") for _ in s)))
+                    else:
+                        f.write(">%s\n%s\n" % (_names(rng, i), s))
+        a, b = str(tmp_path / ("a%d" % case)), str(tmp_path / ("b%d" % case))
+        write(a, rng.randint(0, 40), rng.random() < 0.5)
+        write(b, rng.randint(0, 40), rng.random() < 0.5)
+        mode = rng.choice(["se", "pe", "il"])
+        src = {"se": ["-1", a], "pe": ["-2", a + ":" + b], "il": ["-i", a]}[mode]
+        extra = rng.choice([[], ["-M", "FF"], ["-M", "RF"], ["-M", "RR"], ["-Q", "10"], ["-H", "4"]])
+        args = ["-k", str(rng.choice([11, 15, 21])), "-S", "-p"] + extra + ["-s", "s"] + src
+        if rng.random() < 0.3:
+            args += ["-s", "t", "-1", b]
+        ref_out, out = str(tmp_path / "ref.ctx"), str(tmp_path / "mine.ctx")
+        r = _run(REF, ["-t", "1"] + args + [ref_out])
+        m = _run(hostcheck, args + [out], env={"MCX_BATCH_BYTES": str(rng.choice([300, 5000, 1 << 20]))})
+        assert (m.returncode == 0) == (r.returncode == 0), (block, case, args, m.stderr[-300:], r.stderr[-300:])
+        if r.returncode == 0:
+            assert open(out, "rb").read() == open(ref_out, "rb").read(), (block, case, args)
+
+
+def _spec(rng, path, ncols):
+    """[into:]path[:from] with valid and invalid pieces"""
+    s = path
+    r = rng.random()
+    if r < 0.6:
+        parts = []
+        for _ in range(rng.randint(1, 3)):
+            a, b = rng.randint(0, ncols), rng.randint(0, ncols)      # ncols itself is out of range
+            parts.append(rng.choice(["%d" % a, "%d-%d" % (a, b), "%d-%d" % (min(a, b), max(a, b)), "%d-" % a, "-%d" % b, "*"][:5]))
+        s += ":" + ",".join(parts)
+    elif r < 0.65:
+        s += rng.choice([":", ":x", ":1,,2", ":0-1-2"])
+    r = rng.random()
+    if r < 0.4:
+        s = rng.choice(["%d" % rng.randint(0, 4), "%d,%d" % (rng.randint(0, 3), rng.randint(0, 3)), "%d-%d" % (rng.randint(0, 2), rng.randint(2, 5))]) + ":" + s
+    elif r < 0.45:
+        s = rng.choice(["x:", "-1:", "1-:"]) + s
+    return s
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_colour_filter_fuzz_against_the_reference_binary(hostcheck, tmp_path, block, oracle):
+    """[into:]in.ctx[:from] arguments of `build --graph` and `join`, valid and malformed: same exit status as the reference
+    and, when it succeeds, the same bytes (-S)"""
+    rng = random.Random(9000 + block)
+    fa = []
+    for i in range(3):
+        p = tmp_path / ("r%d.fa" % i)
+        p.write_text("".join(">r\n%s\n" % _seq(rng, 30, 80) for _ in range(60)))
+        fa.append(str(p))
+    g3, g1 = str(tmp_path / "g3.ctx"), str(tmp_path / "g1.ctx")
+    oracle.ref_build(15, ["-s", "a", "-1", fa[0], "-s", "b", "-1", fa[1], "-s", "c", "-1", fa[2]], g3, nkmers="100K")
+    oracle.ref_build(15, ["-s", "d", "-1", fa[1], "-1", fa[2]], g1, nkmers="100K", sort=False)
+    ref_out, out = str(tmp_path / "ref.ctx"), str(tmp_path / "mine.ctx")
+    for case in range(40):
+        specs = [_spec(rng, rng.choice([g3, g1]), 3) for _ in range(rng.randint(1, 3))]
+        if rng.random() < 0.5:
+            cmd = "join"
+            args = ["-q", "-f", "-m", "1G", "-n", "100K", "-S", "-o"]
+            r = subprocess.run([REF, cmd] + args + [ref_out] + specs, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            m = subprocess.run([hostcheck, cmd] + args + [out] + specs, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        else:
+            cmd = "build"
+            args = ["-q", "-f", "-m", "1G", "-n", "100K", "-k", "15", "-S"]
+            for sp in specs:
+                args += ["-g", sp]
+            if rng.random() < 0.5:
+                args += ["-s", "z", "-1", fa[0]]
+            r = subprocess.run([REF, cmd, "-t", "1"] + args + [ref_out], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            m = subprocess.run([hostcheck, cmd] + args + [out], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert (m.returncode == 0) == (r.returncode == 0), (cmd, specs, m.stderr[-300:], r.stderr[-300:])
+        if r.returncode == 0:
+            assert open(out, "rb").read() == open(ref_out, "rb").read(), (cmd, specs)

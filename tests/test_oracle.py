@@ -365,3 +365,27 @@ def test_parallel_fastq_ingest_matches_sequential_reader(ingest_dump, tmp_path, 
                      b"Input error" in r.stderr))
     assert outs[0] == outs[1]
     assert int(outs[0][3]) >= 2000
+
+
+def test_backward_colour_ranges_are_the_reference_s(oracle, tmp_path):
+    """a descending range a-b in a colour filter runs down to 0 in the reference (src/basic/range.c:67-68) and only the
+    first range_get_num() entries are used: 'g.ctx:2-1,0,0-2' selects colours 2,1,0,0,0,1.  Oracle (CtxFile) == the compiled
+    reference's `join` on exactly that"""
+    if oracle.ref_binary(15) is None:
+        pytest.skip("oracle/_ref not built")
+    rng = random.Random(3)
+    fas = []
+    for i in range(3):
+        p = tmp_path / ("r%d.fa" % i)
+        p.write_text("".join(">r\n%s\n" % "".join(rng.choice("ACGT") for _ in range(60)) for _ in range(30)))
+        fas.append(str(p))
+    g3 = str(tmp_path / "g3.ctx")
+    oracle.ref_build(15, ["-s", "a", "-1", fas[0], "-s", "b", "-1", fas[1], "-s", "c", "-1", fas[2]], g3, nkmers="100K")
+    f = oracle.CtxFile(g3 + ":2-1,0,0-2")
+    assert [a for a, _ in f.filter] == [2, 1, 0, 0, 0, 1] and [b for _, b in f.filter] == [0, 1, 2, 3, 4, 5]
+    out = str(tmp_path / "j.ctx")
+    oracle.ref_run(15, ["join", "-q", "-f", "-o", out, g3 + ":2-1,0,0-2"])
+    j = oracle.CtxFile(out)
+    assert j.ncols == 6
+    src = oracle.CtxFile(g3)
+    assert [g["total"] for g in j.ginfo] == [src.ginfo[c]["total"] for c in (2, 1, 0, 0, 0, 1)]
