@@ -227,3 +227,78 @@ def test_colour_filter_fuzz_against_the_reference_binary(hostcheck, tmp_path, bl
         assert (m.returncode == 0) == (r.returncode == 0), (cmd, specs, m.stderr[-300:], r.stderr[-300:])
         if r.returncode == 0:
             assert open(out, "rb").read() == open(ref_out, "rb").read(), (cmd, specs)
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_build_command_line_fuzz_against_the_reference_binary(hostcheck, tmp_path, block):
+    """whole `build` command lines: samples with and without sequence, many tasks (header credit per batch of ten, quirks Q1 /
+    Q4 / Q6), -Q / -O / -H switched between inputs, --seq2 without --remove-pcr, memory / size arguments that do and do not
+    fit: same exit status as `mccortex31 build -t 1`, same bytes when it succeeds"""
+    rng = random.Random(11000 + block)
+    files = []
+    for i in range(8):
+        p = tmp_path / ("f%d" % i)
+        text = rng.choice([_fasta, _fastq, _plain])(rng)
+        p.write_bytes(text.encode())
+        files.append(str(p))
+    for case in range(25):
+        args = ["-k", str(rng.choice([5, 9, 15])), "-S"]
+        r0 = rng.random()
+        if r0 < 0.2:
+            # (sizes that do not fit the memory given: an error before anything is loaded.  Tables that are merely tight are
+            # not compared: the reference gives up when 20 rehashes hit full buckets, which depends on its random seed)
+            args += ["-m", rng.choice(["1K", "100K", "2M", "20M"]), "-n", rng.choice(["64K", "1M", "3M"])]
+        else:
+            args += ["-m", "1G", "-n", "100K"]
+        for s in range(rng.randint(1, 3)):
+            args += ["-s", "s%d" % s]
+            for _ in range(rng.choice([0, 1, 1, 2, 3, 6])):
+                if rng.random() < 0.3:
+                    args += rng.choice([["-Q", "10"], ["-Q", "0"], ["-O", "33"], ["-O", "0"], ["-H", "3"], ["-H", "0"], ["-P"]])
+                if rng.random() < 0.15:
+                    args += ["-2", rng.choice(files) + ":" + rng.choice(files)]
+                else:
+                    args += ["-1", rng.choice(files)]
+        ref_out, out = str(tmp_path / "ref.ctx"), str(tmp_path / "mine.ctx")
+        r = subprocess.run([REF, "build", "-q", "-f", "-t", "1"] + args + [ref_out], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        m = subprocess.run([hostcheck, "build", "-q", "-f"] + args + [out], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert (m.returncode == 0) == (r.returncode == 0), (block, case, args, m.stderr[-300:], r.stderr[-300:])
+        if r.returncode == 0:
+            assert open(out, "rb").read() == open(ref_out, "rb").read(), (block, case, args)
+
+
+@pytest.mark.parametrize("block", range(2))
+def test_intersect_and_sort_fuzz_against_the_reference_binary(hostcheck, tmp_path, block, oracle):
+    """build --intersect with one or two (filtered) intersection graphs, graph files and reads in random combinations, then
+    `sort` of an unsorted multi-colour result: same exit status and bytes as the reference"""
+    rng = random.Random(13000 + block)
+    fa = []
+    genome = _seq(rng, 600, 600).upper().replace("N", "C")
+    for i in range(4):
+        p = tmp_path / ("r%d.fa" % i)
+        p.write_text("".join(">r\n%s\n" % genome[s:s + rng.randint(20, 90)] for s in (rng.randrange(0, 520) for _ in range(50))))
+        fa.append(str(p))
+    g2, g1 = str(tmp_path / "g2.ctx"), str(tmp_path / "g1.ctx")
+    oracle.ref_build(13, ["-s", "a", "-1", fa[0], "-s", "b", "-1", fa[1]], g2, nkmers="100K")
+    oracle.ref_build(13, ["-s", "c", "-1", fa[2]], g1, nkmers="100K", sort=False)
+    ref_out, out = str(tmp_path / "ref.ctx"), str(tmp_path / "mine.ctx")
+    for case in range(20):
+        args = ["-q", "-f", "-m", "1G", "-n", "100K", "-k", "13"]
+        sort = rng.random() < 0.7
+        if sort:
+            args.append("-S")
+        for _ in range(rng.randint(1, 2)):
+            args += ["-I", rng.choice([g2, g1, g2 + ":1", g2 + ":0,1", "0:" + g2 + ":1"])]
+        for _ in range(rng.randint(0, 2)):
+            args += ["-g", rng.choice([g2, g1, g2 + ":1", "1:" + g1, g2 + ":1-0"])]
+        if rng.random() < 0.8:
+            args += ["-s", "n"] + rng.choice([[], ["-H", "4"]]) + ["-1", rng.choice(fa)] + (["-1", rng.choice(fa)] if rng.random() < 0.4 else [])
+        r = subprocess.run([REF, "build", "-t", "1"] + args + [ref_out], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        m = subprocess.run([hostcheck, "build"] + args + [out], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert (m.returncode == 0) == (r.returncode == 0), (args, m.stderr[-300:], r.stderr[-300:])
+        if r.returncode != 0:
+            continue
+        if not sort:   # unsorted dumps have no defined order: canonicalise both, ours with our own `sort`
+            assert subprocess.run([REF, "sort", "-q", ref_out]).returncode == 0
+            assert subprocess.run([hostcheck, "sort", "-q", out]).returncode == 0
+        assert open(out, "rb").read() == open(ref_out, "rb").read(), args
