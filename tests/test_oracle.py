@@ -389,3 +389,46 @@ def test_backward_colour_ranges_are_the_reference_s(oracle, tmp_path):
     assert j.ncols == 6
     src = oracle.CtxFile(g3)
     assert [g["total"] for g in j.ginfo] == [src.ginfo[c]["total"] for c in (2, 1, 0, 0, 0, 1)]
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_device_math_fuzz(oracle, emul, tmp_path, block):
+    """the kernels' host/device math (tests/emul) against the oracle on seeded adversarial reads: random odd k in 3..63,
+    homopolymer cut-offs from 2 to k, quality cut-offs with many values exactly at the threshold, runs of one base around
+    the cut-off length, N runs, reads shorter than / equal to / just over k, reads long enough to cross chunk (2048) and
+    staging-piece boundaries; records and counters must be identical"""
+    rng = random.Random(500 + block)
+    for case in range(8):
+        k = rng.choice(range(3, 64, 2))
+        hp = rng.choice([0, 0, 2, 3, rng.randint(2, k), k])
+        cut = rng.choice([0, 0, rng.randint(36, 73)])
+        piece = rng.choice([0, 0, 16, 160, 2048, 4112])
+        reads = []
+        for _ in range(rng.randint(20, 120)):
+            n = rng.choice([rng.randint(1, k + 3), rng.randint(k, 3 * k + 5), rng.randint(100, 400), rng.randint(2000, 5000)])
+            s = []
+            while len(s) < n:
+                r = rng.random()
+                if r < 0.08:
+                    s += [rng.choice("ACGT")] * rng.choice([max(1, hp - 1), hp or 3, (hp or 3) + 1, rng.randint(1, 2 * k)])
+                elif r < 0.11:
+                    s += ["N"] * rng.randint(1, 3)
+                else:
+                    s += [rng.choice("ACGTacgt") for _ in range(rng.randint(1, 2 * k))]
+            reads.append("".join(s[:n]))
+        if cut:
+            quals = ["".join(chr(rng.choice([cut - 1, cut, cut, cut + 1, rng.randint(35, 74)])) for _ in r) for r in reads]
+            for i in range(0, len(reads), 5):
+                quals[i] = quals[i][:rng.randint(0, len(quals[i]))]
+        g = oracle.Graph(k, 1, 1 << 21)
+        st = oracle.Stats()
+        for i, r in enumerate(reads):
+            g.add_read(r, qual=(quals[i].encode("latin1") or None) if cut else None, fq_cutoff=cut, hp_cutoff=hp, stats=st)
+        recs = g.dump_sorted()[len(g.header()):]
+        g.close()
+        if cut:
+            got, cnt = _emul_q(emul, tmp_path, reads, quals, k, cut, hp)
+        else:
+            got, cnt = _emul(emul, tmp_path, reads, k, hp=hp, piece=piece)
+        assert got == recs, (block, case, k, hp, cut, piece)
+        assert cnt["kmers"] == st.num_kmers_loaded and cnt["contigs"] == st.contigs_parsed, (block, case, k, hp, cut)
