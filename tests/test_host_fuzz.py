@@ -85,7 +85,13 @@ def test_ingest_fuzz_against_the_reference_binary(hostcheck, tmp_path, block):
         if rng.random() < 0.1:
             text = text[:rng.randint(0, len(text))]               # truncated anywhere
         path = tmp_path / ("in%d.txt" % case)
-        path.write_bytes(text.encode())
+        if rng.random() < 0.2:
+            import gzip
+            path = tmp_path / ("in%d.txt.gz" % case)
+            with gzip.open(path, "wb") as f:
+                f.write(text.encode())
+        else:
+            path.write_bytes(text.encode())
         k = rng.choice([5, 11, 21])
         extra = rng.choice([[], [], ["-Q", "10"], ["-H", "3"], ["-Q", "20", "-H", "4"], ["-O", "33"], ["-O", "64", "-Q", "5"]])
         args = ["-k", str(k), "-S"] + extra + ["-s", "s", "-1", str(path)]
