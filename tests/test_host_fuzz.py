@@ -70,7 +70,7 @@ def _plain(rng):
 
 def _run(exe, args, env=None):
     return subprocess.run([exe, "build", "-q", "-f", "-m", "1G", "-n", "100K"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
-                          env=dict(os.environ, **env) if env else None)
+                          env=dict(os.environ, **env) if env else None, timeout=20)
 
 
 @pytest.mark.parametrize("block", range(10))
@@ -96,7 +96,10 @@ def test_ingest_fuzz_against_the_reference_binary(hostcheck, tmp_path, block):
         extra = rng.choice([[], [], ["-Q", "10"], ["-H", "3"], ["-Q", "20", "-H", "4"], ["-O", "33"], ["-O", "64", "-Q", "5"]])
         args = ["-k", str(k), "-S"] + extra + ["-s", "s", "-1", str(path)]
         ref_out, out = str(tmp_path / "ref.ctx"), str(tmp_path / "mine.ctx")
-        r = _run(REF, ["-t", "1"] + args + [ref_out])
+        try:
+            r = _run(REF, ["-t", "1"] + args + [ref_out])
+        except subprocess.TimeoutExpired:
+            continue   # (the reference loops for ever on some malformed FASTQ with -O 64: nothing to compare with)
         want = open(ref_out, "rb").read() if r.returncode == 0 else None
         for env in ({"MCX_PARSE_THREADS": "1"}, {"MCX_PARSE_THREADS": "3", "MCX_PARSE_SEG_BYTES": str(rng.choice([16, 64, 300]))}):
             m = _run(hostcheck, args + [out], env=env)
