@@ -311,3 +311,40 @@ def test_intersect_and_sort_fuzz_against_the_reference_binary(hostcheck, tmp_pat
             assert subprocess.run([REF, "sort", "-q", ref_out]).returncode == 0
             assert subprocess.run([hostcheck, "sort", "-q", out]).returncode == 0
         assert open(out, "rb").read() == open(ref_out, "rb").read(), args
+
+
+REF63 = os.path.join(ROOT, "oracle", "_ref", "mccortex63")
+
+
+@pytest.mark.skipif(not os.path.exists(REF63), reason="oracle/_ref/mccortex63 not built")
+@pytest.mark.parametrize("block", range(3))
+def test_two_word_kmers_fuzz_against_the_reference_binary(hostcheck, tmp_path, block):
+    """k = 33 ... 63 (two 64-bit words per k-mer, mccortex63): reads from a small genome with errors, N, lower case, both
+    strands, homopolymer and quality cut-offs, two colours: same bytes as `mccortex63 build -S`"""
+    rng = random.Random(15000 + block)
+    genome = "".join(rng.choice("ACGT") for _ in range(1500)) + "A" * 70 + "".join(rng.choice("ACGT") for _ in range(300))
+    tr = str.maketrans("ACGTacgt", "TGCAtgca")
+    for case in range(10):
+        paths = []
+        for f in range(2):
+            recs = []
+            for i in range(rng.randint(5, 60)):
+                st = rng.randrange(0, len(genome) - 40)
+                s = genome[st:st + rng.randint(30, 200)]
+                if rng.random() < 0.5:
+                    s = s[::-1].translate(tr)
+                s = "".join((rng.choice("ACGTN") if rng.random() < 0.01 else c) for c in s)
+                if rng.random() < 0.1:
+                    s = s.lower()
+                recs.append(s)
+            p = tmp_path / ("w%d_%d.fq" % (case, f))
+            p.write_text("".join("@r\n%s\n+\n%s\n" % (s, "".join(rng.choice("#+5IIIII") for _ in s)) for s in recs))
+            paths.append(str(p))
+        k = rng.choice([33, 35, 41, 47, 55, 63])
+        extra = rng.choice([[], ["-Q", "10"], ["-H", "8"], ["-Q", "20", "-H", "33"]])
+        args = ["-k", str(k), "-S"] + extra + ["-s", "a", "-1", paths[0], "-s", "b", "-1", paths[1], "-1", paths[0]]
+        ref_out, out = str(tmp_path / "ref.ctx"), str(tmp_path / "mine.ctx")
+        r = _run(REF63, ["-t", "1"] + args + [ref_out])
+        m = _run(hostcheck, args + [out])
+        assert r.returncode == 0 and m.returncode == 0, (args, m.stderr[-300:], r.stderr[-300:])
+        assert open(out, "rb").read() == open(ref_out, "rb").read(), (block, case, args)
