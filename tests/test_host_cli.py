@@ -6,6 +6,7 @@ This says nothing about the CUDA path."""
 import pytest
 
 import test_gpu_cli as G
+import test_zy_gpu_cli_new as G2
 
 
 @pytest.fixture(autouse=True)
@@ -14,7 +15,8 @@ def _use_hostcheck(monkeypatch, hostcheck):
 
 
 # (function objects carry their own parametrize / skipif marks; the module-level gpu mark of test_gpu_cli stays there)
-for _name in dir(G):
-    if _name.startswith("test_cli_"):
-        globals()[_name.replace("test_cli_", "test_host_")] = getattr(G, _name)
-del _name
+for _mod in (G, G2):
+    for _name in dir(_mod):
+        if _name.startswith("test_cli_"):
+            globals()[_name.replace("test_cli_", "test_host_")] = getattr(_mod, _name)
+del _name, _mod
