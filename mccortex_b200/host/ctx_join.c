@@ -62,7 +62,7 @@ static inline uint32_t safe_add_covg(uint32_t a, uint32_t b) { uint64_t s = (uin
 /* graph_writer_stream: one file through its colour filter, record order kept */
 static uint64_t stream_filter(McxCtxFile *f, FILE *out, uint32_t out_ncols)
 {
-  const size_t W = f->num_of_bitfields, in_rec = 8 * W + 5 * (size_t)f->num_of_cols, out_rec = 8 * W + 5 * (size_t)out_ncols;
+  const size_t W = MCX_CTX_W(f), in_rec = 8 * W + 5 * (size_t)f->num_of_cols, out_rec = 8 * W + 5 * (size_t)out_ncols;
   if(f->fh != stdin && fseek(f->fh, (long)f->hdr_size, SEEK_SET) != 0) mcx_die("fseek failed: %s", strerror(errno));
   const size_t chunk = 1u << 16;
   unsigned char *in = malloc(chunk * in_rec), *ob = malloc(chunk * out_rec);
@@ -74,6 +74,7 @@ static uint64_t stream_filter(McxCtxFile *f, FILE *out, uint32_t out_ncols)
     if(got == 0) break;
     if(got % in_rec != 0) mcx_die("Unexpected end of file: %s", f->path);
     size_t n = got / in_rec, w = 0;
+    mcx_ctx_check_records(f, in, n);
     for(size_t r = 0; r < n; r++) {
       const unsigned char *rec = in + r * in_rec;
       memset(cv, 0, 4 * (size_t)out_ncols); memset(ed, 0, out_ncols);
@@ -174,7 +175,7 @@ int mcx_cmd_join(int argc, char **argv)
     McxCtxFile *f = files[0];
     for(uint32_t j = 0; j < f->nfilter; j++) mcx_ginfo_merge(&ginfo[f->into_col[j]], &f->ginfo[f->from_col[j]]);
     mcx_status("Filtering %s to %s with stream filter", f->path, to_stdout ? "STDOUT" : out_path);
-    mcx_write_ctx_header_as_is(out, kmer_size, (uint32_t)ctx_max_cols, ginfo);
+    mcx_write_ctx_header_as_is(out, kmer_size, (uint32_t)ctx_max_cols, ginfo, files[nfiles - 1]->num_of_bitfields);
     nrec = stream_filter(f, out, (uint32_t)ctx_max_cols);
   } else {
     /* ctx_join.c:212-226: the reference sizes its table for ONE colour in memory (then takes as many as fit) */
@@ -195,7 +196,7 @@ int mcx_cmd_join(int argc, char **argv)
     mcx_load_stats st;
     r = mcx_graph_sync(g, &st);
     if(r) die_lib(r, "loading graph file");
-    mcx_write_ctx_header_as_is(out, kmer_size, (uint32_t)ctx_max_cols, ginfo);
+    mcx_write_ctx_header_as_is(out, kmer_size, (uint32_t)ctx_max_cols, ginfo, files[nfiles - 1]->num_of_bitfields);
     uint32_t rec_bytes = 0;
     r = mcx_graph_export_begin(g, sort_kmers ? 1 : 0, &nrec, &rec_bytes);
     if(r) die_lib(r, "mcx_graph_export_begin");

@@ -194,6 +194,7 @@ static size_t read_header(McxCtxFile *f)
       f->ginfo[i].sample_name = read_str(f, "sample name", i, &bytes_read);
     }
     f->seq_err_raw = calloc(f->num_of_cols, 16);
+    f->clean_flags_raw = calloc(f->num_of_cols, 4);
     for(i = 0; i < f->num_of_cols; i++) {
       gfread(f, f->seq_err_raw[i], 16, "seq error rates");
       memcpy(&f->ginfo[i].seq_err, f->seq_err_raw[i], 10);
@@ -203,6 +204,7 @@ static size_t read_header(McxCtxFile *f)
       McxCleaning *c = &f->ginfo[i].cleaning;
       uint8_t fl[4]; uint32_t thr_unitigs = 0, thr_kmers = 0;
       gfread(f, fl, 4, "cleaning flags");
+      memcpy(f->clean_flags_raw[i], fl, 4); /* the header goes back out byte for byte (`sort`), even a flag that is not 0 / 1 */
       c->cleaned_tips = fl[0]; c->cleaned_unitigs = fl[1]; c->cleaned_kmers = fl[2]; c->is_graph_intersection = fl[3];
       gfread(f, &thr_unitigs, 4, "remove low covg unitig threshold");
       gfread(f, &thr_kmers, 4, "remove low covg kmer threshold");
@@ -250,7 +252,7 @@ McxCtxFile *mcx_ctx_open(const char *input, size_t into_offset)
   f->hdr_size = read_header(f);
   filter_set_cols(f, f->num_of_cols, into_offset);
   if(f->file_size != -1) {
-    size_t bytes_per_kmer = 8u * f->num_of_bitfields + 5u * (size_t)f->num_of_cols;
+    size_t bytes_per_kmer = 8u * MCX_CTX_W(f) + 5u * (size_t)f->num_of_cols;
     size_t remaining = (size_t)f->file_size - f->hdr_size;
     f->num_of_kmers = (int64_t)(remaining / bytes_per_kmer);
     if(remaining % bytes_per_kmer != 0)
@@ -265,7 +267,7 @@ void mcx_ctx_close(McxCtxFile *f)
   if(!f) return;
   if(f->fh && f->fh != stdin) fclose(f->fh);
   if(f->ginfo) { for(uint32_t i = 0; i < f->num_of_cols; i++) mcx_ginfo_free(&f->ginfo[i]); free(f->ginfo); }
-  free(f->seq_err_raw);
+  free(f->seq_err_raw); free(f->clean_flags_raw);
   free(f->from_col); free(f->into_col); free(f->input); free(f->path); free(f);
 }
 
@@ -289,10 +291,9 @@ size_t mcx_ctx_write_header_raw(FILE *fh, const McxCtxFile *f)
     for(i = 0; i < C; i++) PUT(f->seq_err_raw[i], 16);
     for(i = 0; i < C; i++) {
       const McxCleaning *c = &f->ginfo[i].cleaning;
-      unsigned char flags[4] = {c->cleaned_tips, c->cleaned_unitigs, c->cleaned_kmers, c->is_graph_intersection};
       uint32_t tu = c->cleaned_unitigs ? c->clean_unitigs_thresh : 0, tk = c->cleaned_kmers ? c->clean_kmers_thresh : 0;
       uint32_t len = (uint32_t)strlen(c->intersection_name);
-      PUT(flags, 4); PUT(&tu, 4); PUT(&tk, 4); PUT(&len, 4); PUT(c->intersection_name, len);
+      PUT(f->clean_flags_raw[i], 4); PUT(&tu, 4); PUT(&tk, 4); PUT(&len, 4); PUT(c->intersection_name, len);
     }
   }
   PUT("CORTEX", 6);
@@ -305,6 +306,19 @@ void mcx_ctx_flatten(McxCtxFile *f, uint32_t intocol)
 {
   for(uint32_t i = 0; i < f->nfilter; i++) f->into_col[i] = intocol;
   f->into_ncols = intocol + 1;
+}
+
+/* graph_file_read_raw (src/graph/graph_file_reader.c:368-370): a record whose top key word has bits above 2k set */
+void mcx_ctx_check_records(const McxCtxFile *f, const unsigned char *recs, size_t n)
+{
+  const size_t rec_bytes = 8u * MCX_CTX_W(f) + 5u * (size_t)f->num_of_cols;
+  const unsigned top_bits = 2u * (f->kmer_size & 31u); /* k is odd: 2..62 */
+  /* :360-361: the bytes of the key just read (sizeof(BinaryKmer)) against the header's bitfield count, as an int */
+  if(n && (int)(sizeof(uint64_t) * (size_t)f->num_of_bitfields) != (int)(8u * MCX_CTX_W(f))) mcx_die("Unexpected end of file: %s", f->path);
+  for(size_t i = 0; i < n; i++) {
+    uint64_t w0; memcpy(&w0, recs + i * rec_bytes, 8);
+    if(w0 >> top_bits) mcx_die("Oversized kmer in path [kmer: %u]: %s", f->kmer_size, f->path);
+  }
 }
 
 int mcx_ctx_load(mcx_graph *g, McxCtxFile *f, McxGInfo *ginfo, size_t graph_ncols, uint32_t load_flags,
@@ -321,7 +335,7 @@ int mcx_ctx_load(mcx_graph *g, McxCtxFile *f, McxGInfo *ginfo, size_t graph_ncol
   if(ginfo) for(uint32_t i = 0; i < f->nfilter; i++) mcx_ginfo_merge(&ginfo[f->into_col[i]], &f->ginfo[f->from_col[i]]);
 
   if(f->fh != stdin && fseek(f->fh, (long)f->hdr_size, SEEK_SET) != 0) mcx_die("fseek failed: %s", strerror(errno));
-  const size_t rec_bytes = 8u * f->num_of_bitfields + 5u * (size_t)f->num_of_cols;
+  const size_t rec_bytes = 8u * MCX_CTX_W(f) + 5u * (size_t)f->num_of_cols;
   size_t chunk_recs = LOAD_CHUNK_BYTES / rec_bytes; if(chunk_recs == 0) chunk_recs = 1;
   unsigned char *buf = malloc(chunk_recs * rec_bytes);
   uint64_t nread = 0, nloaded = 0, nnovel = 0;
@@ -330,6 +344,7 @@ int mcx_ctx_load(mcx_graph *g, McxCtxFile *f, McxGInfo *ginfo, size_t graph_ncol
     size_t got = fread(buf, 1, chunk_recs * rec_bytes, f->fh);
     if(got == 0) break;
     if(got % rec_bytes != 0) mcx_die("Unexpected end of file: %s", f->path);
+    mcx_ctx_check_records(f, buf, got / rec_bytes);
     uint64_t l = 0, nv = 0;
     r = mcx_graph_load_records(g, buf, got / rec_bytes, f->num_of_cols, MCX_MEM_HOST, f->from_col, f->into_col, f->nfilter,
                                load_flags, &l, &nv);

@@ -84,7 +84,7 @@ int mcx_cmd_sort(int argc, char **argv)
     fout = fd < 0 ? stdout : fdopen(fd, "w");
   }
 
-  const size_t ncols = f->num_of_cols, kmer_mem = 8u * f->num_of_bitfields + 5u * ncols;
+  const size_t ncols = f->num_of_cols, kmer_mem = 8u * MCX_CTX_W(f) + 5u * ncols;
   const size_t memory = (sizeof(char *) + kmer_mem) * num_kmers;
   char mem_str[64]; mcx_bytes_to_str(memory, mem_str);
   if(memory > mem_to_use) mcx_die("Require at least %s memory", mem_str);

@@ -92,17 +92,17 @@ size_t mcx_write_ctx_header(FILE *fh, uint32_t kmer_size, uint32_t ncols, const 
   uint32_t i;
   McxGInfo *h = calloc(ncols, sizeof(McxGInfo));
   for(i = 0; i < ncols; i++) { mcx_ginfo_init(&h[i]); mcx_ginfo_merge(&h[i], &ginfo[i]); }
-  size_t b = mcx_write_ctx_header_as_is(fh, kmer_size, ncols, h);
+  size_t b = mcx_write_ctx_header_as_is(fh, kmer_size, ncols, h, 0);
   for(i = 0; i < ncols; i++) mcx_ginfo_free(&h[i]);
   free(h);
   return b;
 }
 
 /* graph_write_header (src/graph/graph_writer.c:62-110) of a header whose colours are h[] as they stand */
-size_t mcx_write_ctx_header_as_is(FILE *fh, uint32_t kmer_size, uint32_t ncols, const McxGInfo *h)
+size_t mcx_write_ctx_header_as_is(FILE *fh, uint32_t kmer_size, uint32_t ncols, const McxGInfo *h, uint32_t nbitfields)
 {
   size_t b = 0; uint32_t i;
-  uint32_t version = 6, W = (kmer_size + 31) / 32;
+  uint32_t version = 6, W = nbitfields ? nbitfields : (kmer_size + 31) / 32;
   b += put(fh, "CORTEX", 6);
   b += put(fh, &version, 4); b += put(fh, &kmer_size, 4); b += put(fh, &W, 4); b += put(fh, &ncols, 4);
   for(i = 0; i < ncols; i++) b += put(fh, &h[i].mean_read_length, 4);

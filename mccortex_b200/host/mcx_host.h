@@ -40,7 +40,7 @@ size_t mcx_get_kmers_in_hash(size_t mem_to_use, bool mem_to_use_set, size_t num_
 
 /* ---- header metadata: src/basic/graph_info.{c,h}, src/graph/graph_writer.c -- */
 typedef struct {              /* ErrorCleaning, src/basic/graph_info.h */
-  bool cleaned_tips, cleaned_unitigs, cleaned_kmers, is_graph_intersection;
+  uint8_t cleaned_tips, cleaned_unitigs, cleaned_kmers, is_graph_intersection; /* the bytes as stored in a header: merges OR them as they are, like the reference's `bool |= bool` on bytes that are not 0 / 1 */
   uint32_t clean_unitigs_thresh, clean_kmers_thresh;
   char *intersection_name;    /* malloc'd, "undefined" by default */
 } McxCleaning;
@@ -60,7 +60,7 @@ void mcx_ginfo_merge(McxGInfo *dst, const McxGInfo *src);
  * header entry, exactly as graph_writer_mkhdr does; returns bytes written */
 size_t mcx_write_ctx_header(FILE *fh, uint32_t kmer_size, uint32_t ncols, const McxGInfo *ginfo);
 /* graph_write_header of the colours as they stand (no merge into a fresh header): `join` */
-size_t mcx_write_ctx_header_as_is(FILE *fh, uint32_t kmer_size, uint32_t ncols, const McxGInfo *ginfo);
+size_t mcx_write_ctx_header_as_is(FILE *fh, uint32_t kmer_size, uint32_t ncols, const McxGInfo *ginfo, uint32_t nbitfields /* 0: the minimum for k */);
 
 /* ---- graph files: src/graph/graph_file_reader.{c,h}, src/basic/file_filter.{c,h}, src/basic/range.c,
  *      src/graph/graphs_load.c ------------------------------------------------------------- */
@@ -70,11 +70,15 @@ typedef struct {
   uint32_t version, kmer_size, num_of_bitfields, num_of_cols;
   McxGInfo *ginfo;              /* num_of_cols entries */
   unsigned char (*seq_err_raw)[16]; /* the 16 bytes of each colour's long double as stored (padding included) */
+  unsigned char (*clean_flags_raw)[4]; /* the four cleaning flag bytes of each colour as stored */
   size_t hdr_size;
   int64_t file_size, num_of_kmers;   /* -1 if unknown */
   uint32_t nfilter, *from_col, *into_col;   /* FileFilter, sorted by into */
   uint32_t into_ncols;          /* max into + 1 */
 } McxCtxFile;
+/* words per k-mer in the records: what the reference binary for this k is compiled with (sizeof(BinaryKmer)), whatever a
+ * damaged header's bitfield count says (its checks, graph_file_reader.c:118-129, wrap at 2^32) */
+#define MCX_CTX_W(f) (((f)->kmer_size + 31u) / 32u)
 /* graph_file_open2(file, input, "r", true, into_offset): dies on a malformed file like the reference */
 McxCtxFile *mcx_ctx_open(const char *input, size_t into_offset);
 void mcx_ctx_close(McxCtxFile *f);
@@ -84,6 +88,7 @@ void mcx_ctx_close(McxCtxFile *f);
 int mcx_ctx_load(mcx_graph *g, McxCtxFile *f, McxGInfo *ginfo, size_t graph_ncols, uint32_t load_flags,
                  uint64_t *nkmers_read, uint64_t *nkmers_loaded, uint64_t *nkmers_novel);
 void mcx_ctx_flatten(McxCtxFile *f, uint32_t intocol);
+void mcx_ctx_check_records(const McxCtxFile *f, const unsigned char *recs, size_t n); /* dies on an oversized k-mer */
 /* graph_write_header(fh, &file->hdr) (src/graph/graph_writer.c:62-110): the header as parsed, not merged */
 size_t mcx_ctx_write_header_raw(FILE *fh, const McxCtxFile *f);
 bool mcx_ctx_filter_is_direct(const McxCtxFile *f);     /* file_filter_from_direct */

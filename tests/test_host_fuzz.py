@@ -348,3 +348,40 @@ def test_two_word_kmers_fuzz_against_the_reference_binary(hostcheck, tmp_path, b
         m = _run(hostcheck, args + [out])
         assert r.returncode == 0 and m.returncode == 0, (args, m.stderr[-300:], r.stderr[-300:])
         assert open(out, "rb").read() == open(ref_out, "rb").read(), (block, case, args)
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_damaged_graph_files_fuzz_against_the_reference_binary(hostcheck, tmp_path, block):
+    """golden .ctx files with header bytes overwritten, truncated anywhere, or with bytes appended, through `sort -o` and
+    `join`: the driver never crashes, fails where the reference fails, and where both succeed writes the same bytes (even a
+    cleaning flag byte that is neither 0 nor 1 goes through as it is)"""
+    gold = os.path.join(ROOT, "tests", "golden")
+    srcs = [os.path.join(gold, f) for f in ("two_colours_k21.ctx", "tiny_k11_c2.ctx", "fq10_k21.ctx")]
+    rng = random.Random(17000 + block)
+    p = str(tmp_path / "m.ctx")
+    for it in range(60):
+        data = bytearray(open(rng.choice(srcs), "rb").read())
+        hdr_end = data.index(b"CORTEX", 6) + 6
+        mode = rng.random()
+        if mode < 0.5:
+            for _ in range(rng.randint(1, 3)):
+                data[rng.randrange(0, hdr_end)] = rng.randrange(256)
+        elif mode < 0.8:
+            data = data[:rng.randrange(0, len(data))]
+        else:
+            data += bytes(rng.randrange(256) for _ in range(rng.randint(1, 30)))
+        open(p, "wb").write(data)
+        for cmd in ("sort", "join"):
+            res = {}
+            for exe, tag in ((REF, "r"), (hostcheck, "m")):
+                o = str(tmp_path / ("o_%s.ctx" % tag))
+                if os.path.exists(o):
+                    os.remove(o)
+                c = [exe, "sort", "-q", "-f", "-o", o, p] if cmd == "sort" else [exe, "join", "-q", "-f", "-S", "-m", "1G", "-n", "100K", "-o", o, p, p + ":0"]
+                r = subprocess.run(c, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=30)
+                res[tag] = (r.returncode, open(o, "rb").read() if r.returncode == 0 and os.path.exists(o) else None, r.stderr[-300:])
+            assert res["m"][0] in (0, 1), (it, cmd, res["m"][0])
+            if res["r"][0] in (0, 1):       # (a reference that dies of a signal on a damaged file is nothing to compare with)
+                assert (res["m"][0] == 0) == (res["r"][0] == 0), (it, cmd, mode, len(data), res["r"][2], res["m"][2])
+                if res["r"][0] == 0:
+                    assert res["m"][1] == res["r"][1], (it, cmd)
