@@ -9,7 +9,7 @@ using it without a CUDA device, raises.
 """
 from .binding import (  # noqa: F401
     Graph, LoadStats, McxError, lib, lib_path, driver_path, device_count, build_native,
-    host_alloc, host_free, key_owner, device_alloc, device_free, ipc_export, ipc_open, ipc_close,
+    host_alloc, host_free, key_owner, sort_records, device_alloc, device_free, ipc_export, ipc_open, ipc_close,
     MCX_LAYOUT_LINES, MCX_LAYOUT_OFFSETS, MCX_MEM_HOST, MCX_MEM_DEVICE,
     MCX_GRAPH_INTERSECT, MCX_GRAPH_READSTRT, MCX_LOAD_MUST_EXIST, MCX_LOAD_INTO_ISEC, MCX_LOAD_MASK_ISEC,
 )

@@ -161,6 +161,16 @@ def ipc_close(device, addr):
     _ck(lib().mcx_ipc_close(device, C.c_void_p(addr)), "mcx_ipc_close")
 
 
+def sort_records(kmer_size, ncols, records, device=0):
+    """mcx_sort_records: packed .ctx records (bytes) -> the same records in ascending key order (bytes)"""
+    rb = 8 * ((kmer_size + 31) // 32) + 5 * ncols
+    assert len(records) % rb == 0
+    src = C.create_string_buffer(bytes(records), max(len(records), 1))
+    dst = C.create_string_buffer(max(len(records), 1))
+    _ck(lib().mcx_sort_records(device, kmer_size, ncols, src, len(records) // rb, dst), "mcx_sort_records")
+    return dst.raw[:len(records)]
+
+
 def key_owner(key_words, k, nparts):
     arr = (C.c_uint64 * len(key_words))(*key_words)
     return int(lib().mcx_key_owner(arr, k, nparts))

@@ -45,22 +45,39 @@ struct mcx_graph {
   uint64_t nkmers;         // slots claimed so far (updated at sync)
   McxExport exp; bool exp_valid;
   uint8_t *d_tmp; size_t d_tmp_bytes; // scratch for OFFSETS -> LINES repack
-  int ws_variant;          // MCX_WS=<variant>: experimental warp-specialised kernel (mcx_build_ws.cu), 0 = fused kernel
   uint8_t *d_isec;         // build --intersect: one edge byte per slot (Edges *isec_edges, ctx_build.c:341-343), else NULL
-  size_t persist_bytes;    // experiment: L2 persisting window over the front table
   uint64_t front_pending;  // positions queued since the front table was last flushed (its counters are 32-bit)
   uint32_t *d_first;       // build --remove-pcr: first read ordinal per (slot, orientation) (mcx_pcr.cuh), else NULL
   uint32_t pcr_ord;        // ordinal of the next read of this colour
   uint8_t *d_pcr; size_t d_pcr_bytes; // --remove-pcr: device copy of the batch being filtered
   bool sharded;  // front table holds records of keys owned by other shards: only mcx_graph_flush_sharded may empty it
-  // MCX_SPILL=1 (k <= 31, front table on): the fused kernel's parked pass appends big-table work to a tuple bin
-  // and kernel C inserts it right after the launch (FusedSink::drain, mcx_build.cu).  One bin per staging slot
-  // plus one (index MCX_NSTAGE) for launches on the primary stream.
-  bool spill_on;
-  uint64_t spill_span;                  // positions per launch on the primary stream when spilling
-  uint64_t spill_cap[MCX_NSTAGE + 1];   // tuples
-  uint64_t *spill_keys[MCX_NSTAGE + 1]; uint32_t *spill_meta[MCX_NSTAGE + 1]; unsigned long long *spill_cursor[MCX_NSTAGE + 1];
+  // `make EXPERIMENTS=1` builds only: MCX_KERNEL=warp selects kernel A2 (mcx_build_warp.cu) for inserting builds with
+  // k <= 31 and no quality / homopolymer cut-off; MCX_CLASSES=2|4: one front table per key class, one launch per class
+  bool warp_kernel;
+  uint32_t ncls_log2;
 };
+
+// front table geometry: ncls class tables of (4 << bits) slots each; all tags first, then all counters
+static size_t front_slots(const mcx_graph *g) { return (size_t)4u << g->table.front_set_bits; }
+static size_t front_bytes(const mcx_graph *g) { return (front_slots(g) << g->ncls_log2) * 12u; }
+static McxTable class_table(const mcx_graph *g, uint32_t c)
+{
+  McxTable t = g->table;
+  if(t.front) { t.front = g->table.front + c * front_slots(g); t.front_cnt = g->table.front_cnt + c * front_slots(g); }
+  return t;
+}
+// merge every class's front table into the big table (or, sharded, into the owners' bins)
+static cudaError_t flush_front(mcx_graph *g, cudaStream_t st, const McxTupleBins *bins = nullptr)
+{
+  if(!g->table.front_set_bits) return cudaSuccess;
+  for(uint32_t c = 0; c < (1u << g->ncls_log2); c++) {
+    const McxTable t = class_table(g, c);
+    cudaError_t e = bins ? mcx_launch_front_flush_sharded(t, *bins, g->occ_bound >= 0xF0000000ull, g->d_counters, st)
+                         : mcx_launch_front_flush(t, g->occ_bound >= 0xF0000000ull, g->d_counters, st);
+    if(e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
 
 extern "C" int mcx_device_count(void)
 {
@@ -83,20 +100,6 @@ extern "C" int mcx_host_free(void *ptr) { if(ptr) CU(cudaFreeHost(ptr)); return 
 // host-staging path fans out to the ring streams and joins back (event fork/join), so
 // events recorded on the primary stream bracket everything a call enqueued.
 static cudaStream_t primary(mcx_graph *g) { return g->use_user_stream ? g->user_stream : g->own_primary; }
-static void apply_persist(mcx_graph *g, cudaStream_t st)
-{
-  if(!g->persist_bytes || !g->table.front) return;
-  cudaStreamAttrValue a; memset(&a, 0, sizeof(a));
-  a.accessPolicyWindow.base_ptr = g->table.front;
-  size_t bytes = (4ull << g->table.front_set_bits) * 12u;
-  a.accessPolicyWindow.num_bytes = bytes;
-  a.accessPolicyWindow.hitRatio = g->persist_bytes >= bytes ? 1.0f : (float)g->persist_bytes / (float)bytes;
-  a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &a);
-  cudaGetLastError();
-}
-
 // MCX_TIMING=1: wall clock of the steps of mcx_graph_create on stderr
 #include <time.h>
 static void abi_phase(const char *what)
@@ -165,30 +168,19 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
       if(bits < 16) bits = 16;
       if(bits > 24) bits = 24;
       g->table.front_set_bits = bits;
-      // one allocation: (4 << bits) 8-byte tags, then (4 << bits) 4-byte counters
-      e = cudaMalloc(&g->table.front, (4ull << bits) * 12u);
+#ifdef MCX_EXPERIMENTS
+      if(const char *m = getenv("MCX_CLASSES")) { int v = atoi(m); g->ncls_log2 = v >= 4 ? 2u : (v >= 2 ? 1u : 0u); }
+#endif
+      // one allocation: per class (4 << bits) 8-byte tags -- all classes' tags first --, then the 4-byte counters
+      e = cudaMalloc(&g->table.front, front_bytes(g));
       if(e != cudaSuccess) { g->table.front_set_bits = 0; int r = fail_cuda(e, "cudaMalloc(front)"); mcx_graph_destroy(g); return r; }
-      g->table.front_cnt = reinterpret_cast<unsigned int *>(g->table.front + (4ull << bits));
-      cudaMemset(g->table.front, 0, (4ull << bits) * 12u);
+      g->table.front_cnt = reinterpret_cast<unsigned int *>(g->table.front + (front_slots(g) << g->ncls_log2));
+      cudaMemset(g->table.front, 0, front_bytes(g));
     }
   }
-  // experiment knobs (see profiles/): probe-load flavour and L2 fetch granularity
-  if(const char *m = getenv("MCX_MINB")) mcx_set_minb(atoi(m));
-  if(const char *m = getenv("MCX_G")) mcx_set_inflight(atoi(m));
-  if(const char *m = getenv("MCX_WS")) g->ws_variant = atoi(m);
-  if(const char *m = getenv("MCX_L2_HINTS")) mcx_set_hints((uint32_t)atoi(m));
-  g->spill_span = 1ull << 30;
-  if(const char *m = getenv("MCX_SPILL")) g->spill_on = atoi(m) != 0 && g->table.front_set_bits != 0;
-  if(const char *m = getenv("MCX_SPILL_SPAN_MB")) { long v = atol(m); if(v >= 1 && v <= 3584) g->spill_span = (uint64_t)v << 20; }
-  if(const char *m = getenv("MCX_L2_PERSIST_MB")) {
-    // experiment: pin the front table with the L2 persistence controls
-    size_t want = (size_t)atoi(m) << 20;
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-    g->persist_bytes = want;
-  }
-  if(const char *m = getenv("MCX_L2FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(m));
-  apply_persist(g, g->own_primary);
-  for(int i = 0; i < MCX_NSTAGE; i++) apply_persist(g, g->streams[i]);
+#ifdef MCX_EXPERIMENTS
+  if(const char *m = getenv("MCX_KERNEL")) g->warp_kernel = strcmp(m, "warp") == 0;
+#endif
   abi_phase("create: front table");
   *out = g;
   return MCX_OK;
@@ -212,11 +204,6 @@ extern "C" int mcx_graph_destroy(mcx_graph *g)
   if(g->d_isec) cudaFree(g->d_isec);
   if(g->d_first) cudaFree(g->d_first);
   if(g->d_pcr) cudaFree(g->d_pcr);
-  for(int i = 0; i <= MCX_NSTAGE; i++) {
-    if(g->spill_keys[i]) cudaFree(g->spill_keys[i]);
-    if(g->spill_meta[i]) cudaFree(g->spill_meta[i]);
-    if(g->spill_cursor[i]) cudaFree(g->spill_cursor[i]);
-  }
   if(g->table.front) cudaFree(g->table.front);
   if(g->d_counters) cudaFree(g->d_counters);
   if(g->table.slots) cudaFree(g->table.slots);
@@ -239,7 +226,7 @@ extern "C" int mcx_graph_clear(mcx_graph *g)
   cudaStream_t st = primary(g);
   CU(cudaMemsetAsync(g->table.slots, 0, (size_t)g->table.nslots * g->table.stride * 4u, st));
   CU(cudaMemsetAsync(g->d_counters, 0, MCX_NCOUNTERS_ALL * sizeof(unsigned long long), st));
-  if(g->table.front) CU(cudaMemsetAsync(g->table.front, 0, (4ull << g->table.front_set_bits) * 12u, st));
+  if(g->table.front) CU(cudaMemsetAsync(g->table.front, 0, front_bytes(g), st));
   if(g->d_isec) CU(cudaMemsetAsync(g->d_isec, 0, (size_t)g->table.nslots + 8, st));
   if(g->d_first) CU(cudaMemsetAsync(g->d_first, 0xFF, (size_t)g->table.nslots * 8u, st));
   g->pcr_ord = 0;
@@ -255,7 +242,6 @@ extern "C" int mcx_graph_set_stream(mcx_graph *g, void *cuda_stream)
   int r = sync_all(g); if(r) return r;
   g->use_user_stream = cuda_stream != NULL;
   g->user_stream = (cudaStream_t)cuda_stream;
-  apply_persist(g, primary(g));
   return MCX_OK;
 }
 
@@ -288,6 +274,8 @@ static McxBuildParams make_params(mcx_graph *g, const mcx_read_batch *b, const u
   p.may_saturate = g->occ_bound >= 0xF0000000ull;
   p.counters = g->d_counters;
   p.qual = nullptr; p.qcut = 0; p.summary = nullptr;
+  p.cls = 0; p.ncls_log2 = 0;
+  p.run_tiles = 0; if(const char *m = getenv("MCX_W_RUN")) p.run_tiles = (uint32_t)atoi(m);
   return p;
 }
 
@@ -300,11 +288,11 @@ static int front_colour(mcx_graph *g, uint32_t colour)
   if(!g->table.front_set_bits || g->table.front_colour == colour) return MCX_OK;
   if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must run before the colour changes"); return MCX_ERR_UNSUPPORTED; }
   if(g->front_pending) {
-    CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+    CU(flush_front(g, primary(g)));
     g->front_pending = 0;
   }
   // the tags carry the old colour's edge bits: start the new colour with an empty front table
-  CU(cudaMemsetAsync(g->table.front, 0, (4ull << g->table.front_set_bits) * 12u, primary(g)));
+  CU(cudaMemsetAsync(g->table.front, 0, front_bytes(g), primary(g)));
   g->table.front_colour = colour;
   return MCX_OK;
 }
@@ -314,47 +302,28 @@ static int front_guard(mcx_graph *g, uint64_t positions)
   if(positions > MCX_FRONT_SPAN) { snprintf(g_err, sizeof(g_err), "batch too large: split it into pieces of < 3.7e9 bytes"); return MCX_ERR_UNSUPPORTED; }
   if(g->front_pending + positions >= 0xF0000000ull) {
     if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must run at least every 4e9 positions"); return MCX_ERR_UNSUPPORTED; }
-    CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+    CU(flush_front(g, primary(g)));
     g->front_pending = 0;
   }
   g->front_pending += positions;
   return MCX_OK;
 }
 
-// spill bin `slot` (a staging slot, or MCX_NSTAGE for the primary stream), allocated on first use: room for
-// one slot per 8 positions of the largest launch it serves (every PARKED item gets a slot; the bench workload parks ~10 % of its
-// occurrences; what does not fit is inserted inline by the kernel), MCX_SPILL_CAP=<tuples> overrides
-static cudaError_t ensure_spill(mcx_graph *g, int slot)
-{
-  if(g->spill_keys[slot]) return cudaSuccess;
-  uint64_t cap = (slot == MCX_NSTAGE ? g->spill_span : MCX_STAGE_POS) / 8u;
-  if(const char *m = getenv("MCX_SPILL_CAP")) { long long v = atoll(m); if(v >= 1 && v <= (4096ll << 20)) cap = (uint64_t)v; }
-  cudaError_t e;
-  if((e = cudaMalloc(&g->spill_keys[slot], cap * g->W * sizeof(uint64_t))) != cudaSuccess) return e;
-  if((e = cudaMalloc(&g->spill_meta[slot], cap * sizeof(uint32_t))) != cudaSuccess) return e;
-  if((e = cudaMalloc(&g->spill_cursor[slot], sizeof(unsigned long long))) != cudaSuccess) return e;
-  if((e = cudaMemset(g->spill_cursor[slot], 0, sizeof(unsigned long long))) != cudaSuccess) return e;
-  g->spill_cap[slot] = cap;
-  return cudaSuccess;
-}
-
 // one launch over [r_begin, r_end) of a LINES buffer: the fused insert kernel, or (must_exist) the lookup kernel
-static cudaError_t launch_build(mcx_graph *g, const mcx_read_batch *b, const McxBuildParams &p, cudaStream_t st, int slot = MCX_NSTAGE)
+static cudaError_t launch_build(mcx_graph *g, const mcx_read_batch *b, const McxBuildParams &p, cudaStream_t st)
 {
   if(b->must_exist) return mcx_launch_build_lookup(p, g->table, st);
-  if(g->ws_variant && g->k <= 31 && g->table.front_set_bits) { mcx_set_ws_variant(g->ws_variant); return mcx_launch_build_ws(p, g->table, st); }
-  if(g->spill_on && g->W == 1u && g->table.front_set_bits) {
-    cudaError_t e = ensure_spill(g, slot);
-    if(e != cudaSuccess) return e;
-    McxTupleBins bins; memset(&bins, 0, sizeof(bins));
-    bins.keys[0] = g->spill_keys[slot]; bins.meta[0] = g->spill_meta[slot]; bins.cursor = g->spill_cursor[slot];
-    bins.cap = g->spill_cap[slot]; bins.nparts = 1; bins.my_part = 0; bins.spill = 1;
-    if((e = mcx_launch_build_spill(p, g->table, bins, st)) != cudaSuccess) return e;
-    // kernel C reads the tuple count from the cursor (at most cap tuples were stored); then the bin is empty again
-    if((e = mcx_launch_insert_tuples(bins.keys[0], bins.meta[0], bins.cap, (const uint64_t *)bins.cursor, g->k, g->table, p.colour,
-                                     p.may_saturate, g->d_counters, st)) != cudaSuccess) return e;
-    return cudaMemsetAsync(bins.cursor, 0, sizeof(unsigned long long), st);
+#ifdef MCX_EXPERIMENTS
+  if(g->warp_kernel && mcx_warp_kernel_supports(p)) {
+    // one launch per key class over the same reads, each with the class's own front table
+    for(uint32_t c = 0; c < (1u << g->ncls_log2); c++) {
+      McxBuildParams pc = p; pc.cls = c; pc.ncls_log2 = g->table.front_set_bits ? g->ncls_log2 : 0u;
+      cudaError_t e = mcx_launch_build_warp(pc, class_table(g, c), st);
+      if(e != cudaSuccess || !pc.ncls_log2) return e;
+    }
+    return cudaSuccess;
   }
+#endif
   return mcx_launch_build_fused(p, g->table, st);
 }
 
@@ -365,7 +334,7 @@ static int add_lines_device(mcx_graph *g, const mcx_read_batch *b, const uint8_t
   g->occ_bound += nbytes;
   // one launch per span of <= MCX_FRONT_SPAN positions (the whole buffer stays visible to every
   // launch, so windows and edges across a cut see their neighbours)
-  const uint64_t span = (g->spill_on && !b->must_exist) ? g->spill_span : MCX_FRONT_SPAN;
+  const uint64_t span = MCX_FRONT_SPAN;
   for(uint64_t lo = 0; lo < nbytes; lo += span) {
     const uint64_t hi = lo + span < nbytes ? lo + span : nbytes;
     int r = front_guard(g, hi - lo); if(r) return r;
@@ -403,7 +372,7 @@ static int add_lines_host(mcx_graph *g, const mcx_read_batch *b, const uint8_t *
     if(!pinned) { memcpy(g->h_stage[s], src, b1 - b0); src = g->h_stage[s]; }
     CU(cudaMemcpyAsync(g->d_stage[s], src, b1 - b0, cudaMemcpyHostToDevice, st));
     McxBuildParams p = make_params(g, b, g->d_stage[s], b1 - b0, pos - b0, pend - b0);
-    CU(launch_build(g, b, p, st, s));
+    CU(launch_build(g, b, p, st));
     CU(cudaEventRecord(g->events[s], st));
   }
   for(int s = 0; s < MCX_NSTAGE; s++) if(used[s]) CU(cudaStreamWaitEvent(primary(g), g->events[s], 0));
@@ -482,12 +451,12 @@ extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
     snprintf(g_err, sizeof(g_err), "hp_cutoff must be 0 or in [2, k]"); return MCX_ERR_UNSUPPORTED;
   }
   if(b->fq_cutoff >= 127) { snprintf(g_err, sizeof(g_err), "fq_cutoff (incl. offset) must be < 127"); return MCX_ERR_UNSUPPORTED; }
+  CU(cudaSetDevice(g->device));
   if(b->must_exist && g->table.front_set_bits) {
     // everything counted so far must be in the big table before k-mers are looked up there
-    CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+    CU(flush_front(g, primary(g)));
     g->front_pending = 0;
   }
-  CU(cudaSetDevice(g->device));
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
   { int r = front_colour(g, b->colour); if(r) return r; }
   if((b->fq_cutoff && b->qual) || b->layout != MCX_LAYOUT_LINES) { int r = front_guard(g, b->nbytes + b->nreads); if(r) return r; }
@@ -609,7 +578,7 @@ extern "C" int mcx_graph_sync(mcx_graph *g, mcx_load_stats *stats)
   if(!g) return MCX_ERR_BAD_ARG;
   int r = sync_all(g); if(r) return r;
   if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must run before sync"); return MCX_ERR_BAD_ARG; }
-  CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+  CU(flush_front(g, primary(g)));
   g->front_pending = 0;
   CU(cudaStreamSynchronize(primary(g)));
   unsigned long long c[MCX_NCOUNTERS_ALL];
@@ -641,7 +610,7 @@ extern "C" int mcx_graph_flush(mcx_graph *g)
   if(!g) return MCX_ERR_BAD_ARG;
   if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must be used on a sharded graph"); return MCX_ERR_BAD_ARG; }
   CU(cudaSetDevice(g->device));
-  CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+  CU(flush_front(g, primary(g)));
   g->front_pending = 0;
   return MCX_OK;
 }
@@ -659,7 +628,7 @@ extern "C" int mcx_graph_export_begin(mcx_graph *g, int sorted, uint64_t *nrecor
   if(!g) return MCX_ERR_BAD_ARG;
   int r = sync_all(g); if(r) return r;
   if(g->sharded) { snprintf(g_err, sizeof(g_err), "mcx_graph_flush_sharded must run before export"); return MCX_ERR_BAD_ARG; }
-  CU(mcx_launch_front_flush(g->table, g->occ_bound >= 0xF0000000ull, g->d_counters, primary(g)));
+  CU(flush_front(g, primary(g)));
   g->front_pending = 0;
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
   cudaError_t e = mcx_export_build(g->table, g->k, sorted != 0, &g->exp, primary(g));
@@ -698,7 +667,7 @@ static int fill_bins(McxTupleBins *bins, uint32_t W, uint32_t nparts, uint32_t m
     bins->meta[d] = meta_dst ? meta_dst[d] : meta_out + (uint64_t)d * cap;
     if(d != my_part && (!bins->keys[d] || !bins->meta[d])) return MCX_ERR_BAD_ARG;
   }
-  bins->cursor = (unsigned long long *)counts_out; bins->cap = cap; bins->nparts = nparts; bins->my_part = my_part; bins->spill = 0;
+  bins->cursor = (unsigned long long *)counts_out; bins->cap = cap; bins->nparts = nparts; bins->my_part = my_part;
   return MCX_OK;
 }
 
@@ -741,6 +710,15 @@ static int add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t npa
   CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
   g->occ_bound += b->nbytes;
   McxBuildParams p = make_params(g, b, (const uint8_t *)b->seq, b->nbytes, 0, b->nbytes);
+#ifdef MCX_EXPERIMENTS
+  if(g->warp_kernel && mcx_warp_kernel_supports(p)) {
+    for(uint32_t c = 0; c < (1u << g->ncls_log2); c++) {
+      McxBuildParams pc = p; pc.cls = c; pc.ncls_log2 = g->table.front_set_bits ? g->ncls_log2 : 0u;
+      CU(mcx_launch_build_warp_sharded(pc, class_table(g, c), bins, st));
+      if(!pc.ncls_log2) break;
+    }
+  } else
+#endif
   CU(mcx_launch_build_sharded(p, g->table, bins, st));
   g->pend_positions += b->nbytes;
   g->sharded = true;
@@ -772,7 +750,7 @@ static int flush_sharded(mcx_graph *g, uint32_t nparts, uint32_t my_part, uint64
   McxTupleBins bins;
   { int r = fill_bins(&bins, g->W, nparts, my_part, cap_per_part, keys_out, meta_out, keys_dst, meta_dst, counts_out); if(r) return r; }
   CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
-  CU(mcx_launch_front_flush_sharded(g->table, bins, g->occ_bound >= 0xF0000000ull, g->d_counters, st));
+  CU(flush_front(g, st, &bins));
   g->sharded = false; g->front_pending = 0;
   return MCX_OK;
 }

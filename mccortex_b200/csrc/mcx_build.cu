@@ -64,8 +64,6 @@ template <int W> struct McxSlowQueue {
   uint64_t key[MCX_QCAP(W) * W];
   uint8_t emask[MCX_QCAP(W)];
   uint32_t n;
-  uint32_t spill_ok;                 // this drain's reservation fits the spill bin
-  unsigned long long spill_base;     // first bin slot of this drain's reservation (one slot per parked item)
 };
 // the queue lives in dynamic shared memory (static + dynamic exceeds the 48 KB static limit)
 extern __shared__ __align__(16) unsigned char mcx_dyn_smem[];
@@ -100,26 +98,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
   } while(!done);
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ uint32_t g_mcx_hints = 0;  // MCX_L2_HINTS (see mcx_table.cuh)
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
 {
-  if(g_mcx_hints & 1u) {
-    // the read stream is touched once: let it leave L2 first, the front table lives there
-    const uint64_t pol = mcx_policy_evict_first();
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-  } else
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mcx_apply_hints(McxTable &t)
-{
-  const uint32_t h = g_mcx_hints;
-  t.pol_big = (h & 2u) ? mcx_policy_evict_first() : 0ull;
-  t.pol_front = (h & 4u) ? mcx_policy_evict_last() : 0ull;
-  t.pol_cnt = (h & 64u) ? mcx_policy_evict_last() : ((h & 128u) ? mcx_policy_evict_first() : 0ull);
-}
-void mcx_set_hints(uint32_t h) { cudaMemcpyToSymbol(g_mcx_hints, &h, sizeof(h)); }
 
 template <bool QUAL>
 __device__ __forceinline__ void issue_chunk_load(McxChunkSmem<QUAL> &sm, const McxBuildParams &p, uint64_t chunk, uint32_t buf)
@@ -148,47 +131,22 @@ __device__ __forceinline__ uint32_t chunk_carry_in(const uint8_t *summary, uint6
 }
 
 // ---------------------------------------------------------------- sinks
-// what to do with one occurrence
-// append one tuple to the bin of shard d (warp-aggregated cursor bump)
-template <int W>
-__device__ __forceinline__ void mcx_bin_push(const McxTupleBins &b, uint32_t d, const McxKmer<W> &key, uint32_t meta, uint32_t &full)
-{
-  uint32_t peers = __match_any_sync(__activemask(), d);
-  uint32_t leader = __ffs(peers) - 1u, lane = threadIdx.x & 31u;
-  unsigned long long base = 0;
-  if(lane == leader) base = atomicAdd(&b.cursor[d], (unsigned long long)__popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  uint64_t at = base + __popc(peers & ((1u << lane) - 1u));
-  if(at >= b.cap) { full = 1; return; }
-  uint64_t *kd = b.keys[d] + at * W;
-#pragma unroll
-  for(int w = 0; w < W; w++) kd[w] = key.b[w];
-  b.meta[d][at] = meta;
-}
-
 static __host__ __device__ __forceinline__ McxTupleBins mcx_no_bins()
 {
   McxTupleBins b;
   for(int i = 0; i < MCX_MAX_PARTS; i++) { b.keys[i] = nullptr; b.meta[i] = nullptr; }
-  b.cursor = nullptr; b.cap = 0; b.nparts = 1; b.my_part = 0; b.spill = 0;
+  b.cursor = nullptr; b.cap = 0; b.nparts = 1; b.my_part = 0;
   return b;
 }
 
-// Single-GPU spill (experiment, MCX_SPILL=1).  A parked occurrence the front table cannot absorb (an error k-mer,
-// mostly: seen once or twice) needs Lookup3 + a random DRAM sector of the big table + CAS + RED: dependent round
-// trips, one item per thread, while the CTA's hot pass waits.  With a spill bin it leaves as a (key, meta) tuple and
-// kernel C inserts the bin right after the launch with every thread of the chip holding one probe in flight.
-// One reservation per drain: thread 0 takes n slots (one per parked item, item i -> slot base + i) with ONE atomic
-// on the bin's cursor -- a cursor bumped per tuple serialises on one L2 address (first version: 153 ms per step
-// against 120, profiles/r1k_exp_spill.txt).  Items the front table absorbs leave meta = 0 in their slot, which
-// kernel C skips.  A reservation that does not fit the bin makes the whole drain insert inline, so a bin of any
-// size is correct.
-
-template <int W, int G> struct FusedSink { // G = probe loads kept in flight per thread
-  McxTable t; uint32_t colour; bool may_saturate;
+// what to do with one occurrence.  The table and the bins are the kernel's __grid_constant__ parameters, referenced
+// in place (constant bank): the sink itself is a handful of registers.  (The first version carried copies of both and
+// lived in local memory: 432 bytes of stack, LDL / STL in the hot loop -- DESIGN.md 8.3 of round 1.)
+template <int W, int G, bool SHARDED> struct FusedSink { // G = probe loads kept in flight per thread
+  const McxTable &t; const McxTupleBins &bins; // SHARDED: keys owned by another shard leave as tuples
+  uint32_t colour; bool may_saturate;
   McxSlowQueue<W> *q;
-  uint32_t ablate;
-  McxTupleBins bins; // bins.nparts > 1: sharded build, keys owned by another shard leave as tuples
+  unsigned long long *counters;
 
   __device__ __forceinline__ void park(const McxKmer<W> &key, uint32_t emask)
   {
@@ -198,44 +156,25 @@ template <int W, int G> struct FusedSink { // G = probe loads kept in flight per
     q->emask[at] = (uint8_t)emask;
   }
   __device__ __forceinline__ void consume(const McxKmer<W> keys[MCX_HALF], const uint32_t emasks[MCX_HALF], uint32_t valid,
-                                          uint64_t &novel, uint32_t &full)
+                                          uint32_t &novel, uint32_t &full)
   {
     (void)novel; (void)full;
     if(W == 1 && t.front_set_bits) {
       // hot pass: G probe loads in flight per thread, one 32-bit RED per hit; no Lookup3, no
       // big-table access for k-mers that live in the L2-resident front table
       const McxFrontGeom g = mcx_front_geom(t);
-#ifdef MCX_ABLATE  /* experiments only (profiles/r1g_experiments.txt, item 5): MCX_L2_HINTS bits 3..5 */
-      const uint32_t abl = ablate;
-      if(abl) {
-#pragma unroll
-        for(uint32_t h = 0; h < MCX_HALF; h++) {
-          if(!((valid >> h) & 1u)) continue;
-          const McxFKey fk = mcx_fhash(keys[h].b[0]);
-          const uint64_t s4 = (uint64_t)(fk.y & g.setmask) << 2;
-          if(abl & 1u) { novel += (fk.x == 0x12345u && fk.y == 77u && emasks[h] == 3u); continue; }   // no table access at all
-          if(abl & 2u) {                                                                              // load + compare only
-            uint64_t v0, v1, v2, v3; mcx_ld256(t.front + s4, v0, v1, v2, v3);
-            novel += ((uint32_t)v0 == fk.x) + ((uint32_t)v1 == fk.x) + ((uint32_t)v2 == fk.x) + ((uint32_t)v3 == fk.x + emasks[h]);
-            continue;
-          }
-          atomicAdd(t.front_cnt + s4 + (fk.x & 3u), 1u);                                              // RED only
-        }
-        return;
-      }
-#endif
 #pragma unroll
       for(uint32_t h = 0; h < MCX_HALF; h += G) {
         uint64_t v[G][4]; McxFKey fk[G];
 #pragma unroll
         for(uint32_t i = 0; i < G; i++) {
           fk[i] = mcx_fhash(keys[h + i].b[0]);
-          if((valid >> (h + i)) & 1u) mcx_ld256_pol(t.front + ((uint64_t)(fk[i].y & g.setmask) << 2), t.pol_front, v[i][0], v[i][1], v[i][2], v[i][3]);
+          if((valid >> (h + i)) & 1u) mcx_ld256(t.front + ((uint64_t)(fk[i].y & g.setmask) << 2), v[i][0], v[i][1], v[i][2], v[i][3]);
         }
 #pragma unroll
         for(uint32_t i = 0; i < G; i++) {
           if((valid >> (h + i)) & 1u) {
-            if(!mcx_front_hit(g, t.front_cnt + ((uint64_t)(fk[i].y & g.setmask) << 2), t.pol_cnt, fk[i].x, (fk[i].y >> g.S) | g.occ,
+            if(!mcx_front_hit(g, t.front_cnt + ((uint64_t)(fk[i].y & g.setmask) << 2), fk[i].x, (fk[i].y >> g.S) | g.occ,
                               emasks[h + i] << g.eshift, v[i][0], v[i][1], v[i][2], v[i][3]))
               park(keys[h + i], emasks[h + i]);
           }
@@ -251,74 +190,48 @@ template <int W, int G> struct FusedSink { // G = probe loads kept in flight per
   // the next chunk may not fit (evaluated per thread just before the step barrier, OR-reduced there)
   __device__ __forceinline__ bool should_drain() const { return q->n > MCX_QCAP(W) - MCX_T; }
   // one parked occurrence: front table (claim / edge bit), else the big table
-  // spill_at: slot of the spill bin reserved for this item, or ~0 (insert inline)
-  __device__ __forceinline__ void slow(McxKmer<W> key, uint32_t emask, uint64_t &novel, uint32_t &full, uint64_t spill_at = ~0ull)
+  __device__ __forceinline__ void slow(McxKmer<W> key, uint32_t emask, uint32_t &novel, uint32_t &full)
   {
-    if(W == 1 && t.front_set_bits) {
-      if(mcx_front_add_slow(t, key.b[0], emask)) { // absorbed by the front table
-        if(spill_at != ~0ull) bins.meta[0][spill_at] = 0u;
-        return;
-      }
-    }
-    if(spill_at != ~0ull) { // kernel C inserts it after the launch
-#pragma unroll
-      for(int w = 0; w < W; w++) bins.keys[0][spill_at * W + w] = key.b[w];
-      bins.meta[0][spill_at] = (1u << 8) | emask;
-      return;
-    }
+    if(W == 1 && t.front_set_bits && mcx_front_add_slow(t, key.b[0], emask)) return; // absorbed by the front table
     uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
-    if(bins.nparts > 1u) {
+    if(SHARDED) {
       const uint32_t d = mcx_owner(hc, bins.nparts);
       if(d != bins.my_part) { mcx_bin_push<W>(bins, d, key, (1u << 8) | emask, full); return; }
     }
     int r = mcx_table_add<W>(t, key, hc, hb, colour, emask, 1u, may_saturate);
     novel += (r == 1);
-    full |= (r == 2);
+    if(r == 2) { full = 1; atomicOr(&counters[MCX_CNT_FULL], 1ull); } // seen at once by every CTA (mcx_front_end stops inserting)
   }
   // all threads of the CTA, between two __syncthreads
-  __device__ __forceinline__ void drain(uint64_t &novel, uint32_t &full)
+  __device__ __forceinline__ void drain(uint32_t &novel, uint32_t &full)
   {
     const uint32_t n = q->n;
-    uint64_t sbase = ~0ull;
-    if(bins.spill) { // (launch-uniform)
-      if(threadIdx.x == 0) {
-        const unsigned long long base = n ? atomicAdd(&bins.cursor[0], (unsigned long long)n) : 0ull;
-        q->spill_base = base; q->spill_ok = (n && base + n <= bins.cap) ? 1u : 0u;
-      }
-      __syncthreads();
-      if(q->spill_ok) sbase = q->spill_base;
-      else if(n) {
-        // the part of a reservation that does not fit still lies below the count kernel C will read: empty it
-        const unsigned long long base = q->spill_base;
-        for(uint32_t i = threadIdx.x; i < n && base + i < bins.cap; i += blockDim.x) bins.meta[0][base + i] = 0u;
-      }
-    }
     for(uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
       McxKmer<W> key;
 #pragma unroll
       for(int w = 0; w < W; w++) key.b[w] = q->key[i * W + w];
-      slow(key, q->emask[i], novel, full, sbase == ~0ull ? ~0ull : sbase + i);
+      slow(key, q->emask[i], novel, full);
     }
   }
 };
 
 // tuples binned by owner (kernel B): every occurrence leaves as a tuple
 template <int W> struct TupleSink {
-  McxTupleBins b;
+  const McxTupleBins &b;
   __device__ __noinline__ void one(McxKmer<W> key, uint32_t emask, uint32_t &full)
   {
     uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
     mcx_bin_push<W>(b, mcx_owner(hc, b.nparts), key, (1u << 8) | emask, full);
   }
   __device__ __forceinline__ void consume(const McxKmer<W> keys[MCX_HALF], const uint32_t emasks[MCX_HALF], uint32_t valid,
-                                          uint64_t &novel, uint32_t &full)
+                                          uint32_t &novel, uint32_t &full)
   {
     (void)novel;
 #pragma unroll
     for(uint32_t j = 0; j < MCX_HALF; j++)
       if((valid >> j) & 1u) one(keys[j], emasks[j], full);
   }
-  __device__ __forceinline__ void drain(uint64_t &, uint32_t &) {}
+  __device__ __forceinline__ void drain(uint32_t &, uint32_t &) {}
   __device__ __forceinline__ void reset() {}
   __device__ __forceinline__ bool should_drain() const { return false; }
 };
@@ -361,8 +274,11 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
     if(chunk0 + cstride < c_last) issue_chunk_load<QUAL>(sm, p, chunk0 + cstride, 1);
   }
 
-  uint64_t n_kmers = 0, n_novel = 0, n_contigs = 0, n_reads = 0;
+  // per-thread counters: a launch covers < 2^32 positions, so 32 bits are plenty (64-bit ones were spilled: six LDL + six
+  // STL per group of eight windows in the first version's hot loop)
+  uint32_t n_kmers = 0, n_novel = 0, n_contigs = 0, n_reads = 0;
   uint32_t full = 0;
+  bool stopped = false; // the table is full (any CTA found out): nothing more is inserted, the launch just runs out
 
   for(int64_t s = -2;; s++) {
     const uint64_t ch2 = chunk0 + (uint64_t)(s + 2) * cstride;                      // phase 1
@@ -422,7 +338,7 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
       mcx_thread_occurrences<W>(sm.pk[j % 3u], sm.vmask[j & 1u], tid, p.k,
         [&](const McxKmer<W> *keys, const uint32_t *emasks, uint32_t valid, uint32_t starts, uint32_t j0) {
           valid &= own >> j0;
-          if(valid) {
+          if(valid && !stopped) {
             n_kmers += __popc(valid);
             n_contigs += __popc(starts & valid);
             sink.consume(keys, emasks, valid, n_novel, full);
@@ -431,7 +347,11 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
     }
     // the step's only barrier.  It also decides, CTA-uniformly, whether the parked occurrences must
     // be drained now: the last thread to arrive evaluates its predicate after every park of the step
-    const int drain_now = __syncthreads_or(sink.should_drain() ? 1 : 0);
+    // (bit 1: some insert has found the table full -- an undersized -n must not turn into hours of full-table scans)
+    const int bar_flags = __syncthreads_or((sink.should_drain() ? 1 : 0) |
+                                           ((tid == 0 && MODE != MCX_MODE_QSUM && *(volatile unsigned long long *)&p.counters[MCX_CNT_FULL]) ? 2 : 0));
+    const int drain_now = bar_flags & 1;
+    if(bar_flags & 2) stopped = true;
     // raw[(s+2)&1] has been consumed by phase 1: refill it with chunk s+4
     if(tid == 0) {
       const uint64_t ch4 = chunk0 + (uint64_t)(s + 4) * cstride;
@@ -467,14 +387,14 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
 
     // ---- parked (slow) occurrences: only when the queue could overflow during the next chunk
     if(drain_now) {
-      sink.drain(n_novel, full);
+      if(!stopped) sink.drain(n_novel, full);
       __syncthreads();
       sink.reset();
       __syncthreads();
     }
   }
   __syncthreads();
-  sink.drain(n_novel, full);
+  if(!stopped) sink.drain(n_novel, full);
 
   // ---- counters: warp shuffle -> shared -> one global atomic per CTA per counter
   for(int sh = 16; sh > 0; sh >>= 1) {
@@ -498,13 +418,15 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
   }
 }
 
-template <int W, int MINB, int G>
-__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(MINB)) mcx_build_fused_kernel(McxBuildParams p, McxTable t)
+// k <= 31: 3 CTAs x 256 threads per SM, two probe loads in flight per thread (other occupancies / depths were measured in
+// round 1: profiles/r1_exp_occupancy.txt).  k > 31 (no front table: every occurrence parks): 4 CTAs.
+template <int W>
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(W == 1 ? 3 : 4))
+mcx_build_fused_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTable t, const __grid_constant__ McxTupleBins nobins)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
   if(threadIdx.x == 0) q->n = 0;
-  mcx_apply_hints(t);
-  FusedSink<W, G> sink{t, p.colour, p.may_saturate != 0, q, (g_mcx_hints >> 3) & 7u, mcx_no_bins()};
+  FusedSink<W, W == 1 ? 2 : 1, false> sink{t, nobins, p.colour, p.may_saturate != 0, q, p.counters};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
 
@@ -512,38 +434,39 @@ __global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(MINB)) mcx_build_fused_k
 // them (they are forwarded, aggregated, at flush); the parked pass inserts owned keys into the
 // local big table and bins the others for the exchange
 template <int W>
-__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(3)) mcx_build_sharded_kernel(McxBuildParams p, McxTable t, McxTupleBins b)
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(3))
+mcx_build_sharded_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTable t, const __grid_constant__ McxTupleBins b)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
   if(threadIdx.x == 0) q->n = 0;
-  mcx_apply_hints(t);
-  FusedSink<W, 2> sink{t, p.colour, p.may_saturate != 0, q, 0u, b};
+  FusedSink<W, 2, true> sink{t, b, p.colour, p.may_saturate != 0, q, p.counters};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
 
 // quality cut-off variants: pass 1 writes the per-chunk carry summaries, pass 2 inserts
 struct NullSink {
-  __device__ __forceinline__ void consume(const McxKmer<1> *, const uint32_t *, uint32_t, uint64_t &, uint32_t &) {}
-  __device__ __forceinline__ void drain(uint64_t &, uint32_t &) {}
+  __device__ __forceinline__ void consume(const McxKmer<1> *, const uint32_t *, uint32_t, uint32_t &, uint32_t &) {}
+  __device__ __forceinline__ void drain(uint32_t &, uint32_t &) {}
   __device__ __forceinline__ void reset() {}
   __device__ __forceinline__ bool should_drain() const { return false; }
 };
-__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_contig_summary_kernel(McxBuildParams p)
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_contig_summary_kernel(const __grid_constant__ McxBuildParams p)
 {
   NullSink sink;
   mcx_front_end<1, MCX_MODE_QSUM>(p, sink);
 }
 template <int W>
-__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_build_fused_qual_kernel(McxBuildParams p, McxTable t)
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4))
+mcx_build_fused_qual_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTable t, const __grid_constant__ McxTupleBins nobins)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
   if(threadIdx.x == 0) q->n = 0;
-  FusedSink<W, 2> sink{t, p.colour, p.may_saturate != 0, q, 0u, mcx_no_bins()};
+  FusedSink<W, 2, false> sink{t, nobins, p.colour, p.may_saturate != 0, q, p.counters};
   mcx_front_end<W, MCX_MODE_QUAL>(p, sink);
 }
 
 template <int W>
-__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_kmer_tuples_kernel(McxBuildParams p, McxTupleBins b)
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_kmer_tuples_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTupleBins b)
 {
   TupleSink<W> sink{b};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
@@ -568,7 +491,8 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_insert_tuples_kernel(const
 #pragma unroll
     for(int w = 0; w < W; w++) key.b[w] = keys[i * W + w];
     const uint32_t m = meta[i];
-    if(m == 0u) continue; // nothing to add (an empty slot of a spill reservation; no sender emits such a tuple)
+    if(m == 0u) continue; // nothing to add (no sender emits such a tuple)
+    if(full) break;       // this thread has found the table full: the build has failed, stop probing
     uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
     int r = mcx_table_add<W>(big, key, hc, hb, colour, m & 0xFFu, m >> 8, may_saturate != 0);
     n_novel += (r == 1); full |= (r == 2); n_kmers += m >> 8;
@@ -622,6 +546,7 @@ __global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t
     }
     int r = mcx_table_add<1>(t, key, hc, hb, t.front_colour, edges, count, may_saturate != 0);
     n_novel += (r == 1); full |= (r == 2);
+    if(full) break; // the build has failed: stop probing
   }
   for(int s = 16; s > 0; s >>= 1) {
     n_novel += __shfl_xor_sync(0xFFFFFFFFu, n_novel, s);
@@ -650,8 +575,6 @@ __global__ void mcx_repack_lines_kernel(const uint8_t *__restrict__ src, const u
 
 // ---------------------------------------------------------------- launchers
 static int g_num_sms = 0;
-static int g_minb = 3;     // resident CTAs per SM the fused kernel is compiled / launched for (experiment knob; 3 x 80 registers measured best)
-static int g_inflight = 2; // front-table probe loads in flight per thread (experiment knob)
 static int num_sms()
 {
   if(!g_num_sms) {
@@ -680,20 +603,8 @@ static unsigned grid_for_chunks(const McxBuildParams &p, int ctas_per_sm)
 cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, cudaStream_t st)
 {
   if(p.r_end <= p.r_begin) return cudaSuccess;
-  const int minb = g_minb;
-  unsigned grid = grid_for_chunks(p, minb);
-#define MCX_LAUNCH_A(MB, GG) mcx_build_fused_kernel<1, MB, GG><<<grid, MCX_THREADS, queue_smem<1>(mcx_build_fused_kernel<1, MB, GG>), st>>>(p, t)
-  if(p.k <= 31) {
-    switch(minb * 10 + g_inflight) {
-      case 21: MCX_LAUNCH_A(2, 1); break; case 22: MCX_LAUNCH_A(2, 2); break; case 24: MCX_LAUNCH_A(2, 4); break;
-      case 31: MCX_LAUNCH_A(3, 1); break; case 32: MCX_LAUNCH_A(3, 2); break; case 34: MCX_LAUNCH_A(3, 4); break;
-      case 41: MCX_LAUNCH_A(4, 1); break; case 42: MCX_LAUNCH_A(4, 2); break; case 44: MCX_LAUNCH_A(4, 4); break;
-      case 51: MCX_LAUNCH_A(5, 1); break; case 52: MCX_LAUNCH_A(5, 2); break; case 54: MCX_LAUNCH_A(5, 4); break;
-      case 61: MCX_LAUNCH_A(6, 1); break; case 62: MCX_LAUNCH_A(6, 2); break;
-      default: MCX_LAUNCH_A(3, 2); break;
-    }
-  } else mcx_build_fused_kernel<2, 4, 1><<<grid, MCX_THREADS, queue_smem<2>(mcx_build_fused_kernel<2, 4, 1>), st>>>(p, t);
-#undef MCX_LAUNCH_A
+  if(p.k <= 31) mcx_build_fused_kernel<1><<<grid_for_chunks(p, 3), MCX_THREADS, queue_smem<1>(mcx_build_fused_kernel<1>), st>>>(p, t, mcx_no_bins());
+  else mcx_build_fused_kernel<2><<<grid_for_chunks(p, 4), MCX_THREADS, queue_smem<2>(mcx_build_fused_kernel<2>), st>>>(p, t, mcx_no_bins());
   return cudaGetLastError();
 }
 
@@ -703,8 +614,8 @@ cudaError_t mcx_launch_build_fused_qual(const McxBuildParams &p, const McxTable 
   if(p.r_end <= p.r_begin) return cudaSuccess;
   unsigned grid = grid_for_chunks(p, 4);
   mcx_contig_summary_kernel<<<grid, MCX_THREADS, 0, st>>>(p);
-  if(p.k <= 31) mcx_build_fused_qual_kernel<1><<<grid, MCX_THREADS, queue_smem<1>(mcx_build_fused_qual_kernel<1>), st>>>(p, t);
-  else mcx_build_fused_qual_kernel<2><<<grid, MCX_THREADS, queue_smem<2>(mcx_build_fused_qual_kernel<2>), st>>>(p, t);
+  if(p.k <= 31) mcx_build_fused_qual_kernel<1><<<grid, MCX_THREADS, queue_smem<1>(mcx_build_fused_qual_kernel<1>), st>>>(p, t, mcx_no_bins());
+  else mcx_build_fused_qual_kernel<2><<<grid, MCX_THREADS, queue_smem<2>(mcx_build_fused_qual_kernel<2>), st>>>(p, t, mcx_no_bins());
   return cudaGetLastError();
 }
 
@@ -770,12 +681,3 @@ cudaError_t mcx_launch_build_sharded(const McxBuildParams &p, const McxTable &t,
   return cudaGetLastError();
 }
 
-cudaError_t mcx_launch_build_spill(const McxBuildParams &p, const McxTable &t, const McxTupleBins &b, cudaStream_t st)
-{
-  // the sharded kernel with one shard: nothing is owned elsewhere, b.spill routes the big-table work into bin 0
-  return mcx_launch_build_sharded(p, t, b, st);
-}
-
-// ---------------------------------------------------------------- tuning knobs (experiments)
-void mcx_set_minb(int minb) { g_minb = (minb >= 2 && minb <= 6) ? minb : 3; }
-void mcx_set_inflight(int g) { g_inflight = (g == 1 || g == 2 || g == 4) ? g : 2; }

@@ -34,6 +34,9 @@ struct McxBuildParams {
   const uint8_t *qual;  // quality bytes parallel to seq (same layout; terminator bytes ignored)
   uint32_t qcut;        // cut-off including the FASTQ ASCII offset
   uint8_t *summary;     // one byte per chunk of [r_begin, r_end): carry summaries (pass 1 -> pass 2)
+  // key classes (kernel A2 only): this launch handles the keys whose front hash has its top ncls_log2 bits == cls
+  uint32_t cls, ncls_log2;
+  uint32_t run_tiles;   // kernel A2: consecutive tiles a warp takes at a time (0 = default)
 };
 
 // tuples for other shards: bin d holds up to cap tuples for shard d
@@ -48,12 +51,33 @@ struct McxTupleBins {
   uint64_t cap;                  // tuples per destination
   uint32_t nparts;
   uint32_t my_part;              // sharded kernels: tuples owned by my_part are inserted locally instead
-  uint32_t spill;                // single-GPU spill (nparts 1): parked occurrences the front table cannot absorb are
-                                 // appended to bin 0 while it has room (cursor[0] keeps counting beyond cap: the
-                                 // excess was inserted inline) and inserted by kernel C right after the launch
 };
 
+#if defined(__CUDACC__)
+// append one tuple to the bin of shard d (warp-aggregated cursor bump)
+template <int W>
+__device__ __forceinline__ void mcx_bin_push(const McxTupleBins &b, uint32_t d, const McxKmer<W> &key, uint32_t meta, uint32_t &full)
+{
+  uint32_t peers = __match_any_sync(__activemask(), d);
+  uint32_t leader = __ffs(peers) - 1u, lane = threadIdx.x & 31u;
+  unsigned long long base = 0;
+  if(lane == leader) base = atomicAdd(&b.cursor[d], (unsigned long long)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  uint64_t at = base + __popc(peers & ((1u << lane) - 1u));
+  if(at >= b.cap) { full = 1; return; }
+  uint64_t *kd = b.keys[d] + at * W;
+#pragma unroll
+  for(int w = 0; w < W; w++) kd[w] = key.b[w];
+  b.meta[d][at] = meta;
+}
+#endif
+
 cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
+// kernel A2 (mcx_build_warp.cu, only in `make EXPERIMENTS=1` builds: it is slower than kernel A on the bench workload,
+// DESIGN.md 4): warp-autonomous front end; k <= 31, no quality / homopolymer cut-off
+bool mcx_warp_kernel_supports(const McxBuildParams &p);
+cudaError_t mcx_launch_build_warp(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
+cudaError_t mcx_launch_build_warp_sharded(const McxBuildParams &p, const McxTable &t, const McxTupleBins &b, cudaStream_t st);
 cudaError_t mcx_launch_build_fused_qual(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
 cudaError_t mcx_launch_kmer_tuples(const McxBuildParams &p, const McxTupleBins &b, cudaStream_t st);
 // n_dev (may be NULL): device word holding the tuple count, read by the kernel (min(*n_dev, n) tuples)
@@ -62,19 +86,11 @@ cudaError_t mcx_launch_insert_tuples(const uint64_t *keys, const uint32_t *meta,
                                      cudaStream_t st);
 // sharded build: fused local front table, big-table inserts for owned keys, tuples for the rest
 cudaError_t mcx_launch_build_sharded(const McxBuildParams &p, const McxTable &t, const McxTupleBins &b, cudaStream_t st);
-// fused build whose parked pass spills big-table work into b (b.spill = 1, nparts = 1) instead of doing it inline
-cudaError_t mcx_launch_build_spill(const McxBuildParams &p, const McxTable &t, const McxTupleBins &b, cudaStream_t st);
 cudaError_t mcx_launch_front_flush_sharded(const McxTable &t, const McxTupleBins &b, int may_saturate,
                                            unsigned long long *counters, cudaStream_t st);
 cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uint64_t nreads, uint8_t *dst, cudaStream_t st);
 
 cudaError_t mcx_launch_front_flush(const McxTable &t, int may_saturate, unsigned long long *counters, cudaStream_t st);
-// warp-specialised variant of the fused kernel (mcx_build_ws.cu): k <= 31, front table, no quality cut-off
-cudaError_t mcx_launch_build_ws(const McxBuildParams &p, const McxTable &t, cudaStream_t st);
-void mcx_set_ws_variant(int v);
-void mcx_set_minb(int minb);
-void mcx_set_hints(uint32_t h);
-void mcx_set_inflight(int g);
 
 // graph files (mcx_ctxload.cu): from_col / into_col are device arrays of nmap colour pairs; flags bit 0 = must exist
 cudaError_t mcx_launch_load_records(const uint8_t *recs, uint64_t n, uint32_t file_ncols, const uint32_t *from_col,

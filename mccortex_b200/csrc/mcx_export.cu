@@ -51,30 +51,34 @@ __global__ void mcx_gather_hi_kernel(McxTable t, const uint64_t *__restrict__ sl
 }
 
 // record i <- slot order[i] : W x u64 key (flag cleared), C x u32 covg, C x u8 edges
-#define MCX_EXP_RPB 128
-__global__ void __launch_bounds__(MCX_EXP_RPB) mcx_format_kernel(McxTable t, uint32_t W, const uint64_t *__restrict__ order,
-                                                                 uint64_t n, uint32_t rec_bytes, uint8_t *__restrict__ out)
+// A block formats rpb records at a time in shared memory (rpb = as many as fit the shared-memory budget, at most
+// MCX_EXP_THREADS: a 4096-colour record is 20 KB), word by word across the block's threads, then writes them out
+// with coalesced stores.
+#define MCX_EXP_THREADS 128
+#define MCX_EXP_SMEM (96u * 1024u)
+__global__ void __launch_bounds__(MCX_EXP_THREADS) mcx_format_kernel(McxTable t, uint32_t W, const uint64_t *__restrict__ order,
+                                                                     uint64_t n, uint32_t rec_bytes, uint32_t rpb, uint8_t *__restrict__ out)
 {
   extern __shared__ __align__(16) uint8_t tile[];
-  for(uint64_t blk = blockIdx.x; blk * MCX_EXP_RPB < n; blk += gridDim.x) {
-    uint64_t first = blk * MCX_EXP_RPB;
-    uint32_t cnt = (uint32_t)((n - first < MCX_EXP_RPB) ? (n - first) : MCX_EXP_RPB);
-    if(threadIdx.x < cnt) {
-      const uint32_t *s = t.slots + order[first + threadIdx.x] * (uint64_t)t.stride;
-      uint8_t *d = tile + threadIdx.x * rec_bytes;
-      uint32_t C = t.ncols;
-      for(uint32_t w = 0; w < 2u * W + C; w++) {
-        uint32_t v = s[w];
-        if(w == 1u) v &= 0x7FFFFFFFu; // MCX_KEY_FLAG lives in the top bit of key word b[0]
-        d[4 * w + 0] = (uint8_t)v; d[4 * w + 1] = (uint8_t)(v >> 8);
-        d[4 * w + 2] = (uint8_t)(v >> 16); d[4 * w + 3] = (uint8_t)(v >> 24);
-      }
-      for(uint32_t c = 0; c < C; c++) d[8u * W + 4u * C + c] = (uint8_t)(s[2u * W + C + (c >> 2)] >> (8u * (c & 3u)));
+  const uint32_t C = t.ncols, nw = 2u * W + C;
+  for(uint64_t blk = blockIdx.x; blk * rpb < n; blk += gridDim.x) {
+    const uint64_t first = blk * rpb;
+    const uint32_t cnt = (uint32_t)((n - first < rpb) ? (n - first) : rpb);
+    for(uint32_t idx = threadIdx.x; idx < cnt * nw; idx += blockDim.x) {
+      const uint32_t r = idx / nw, w = idx - r * nw;
+      uint32_t v = t.slots[order[first + r] * (uint64_t)t.stride + w];
+      if(w == 1u) v &= 0x7FFFFFFFu; // MCX_KEY_FLAG lives in the top bit of key word b[0]
+      uint8_t *d = tile + r * rec_bytes + 4u * w;
+      d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
+    }
+    for(uint32_t idx = threadIdx.x; idx < cnt * C; idx += blockDim.x) {
+      const uint32_t r = idx / C, c = idx - r * C;
+      tile[r * rec_bytes + 4u * nw + c] = (uint8_t)(t.slots[order[first + r] * (uint64_t)t.stride + nw + (c >> 2)] >> (8u * (c & 3u)));
     }
     __syncthreads();
-    uint64_t obase = first * rec_bytes; // multiple of 128*rec_bytes => 16-byte aligned
-    uint32_t nbytes = cnt * rec_bytes;
-    if((nbytes & 3u) == 0) {
+    const uint64_t obase = first * rec_bytes;
+    const uint32_t nbytes = cnt * rec_bytes;
+    if(((obase | nbytes) & 3u) == 0) {
       uint32_t *o32 = reinterpret_cast<uint32_t *>(out + obase);
       const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tile);
       for(uint32_t i = threadIdx.x; i < nbytes / 4u; i += blockDim.x) o32[i] = t32[i];
@@ -146,10 +150,15 @@ cudaError_t mcx_export_build(const McxTable &t, uint32_t k, bool sorted, McxExpo
   }
   if(n) {
     CK(cudaMalloc(&out->records, n * (uint64_t)out->rec_bytes + 16));
-    uint64_t nblk = (n + MCX_EXP_RPB - 1) / MCX_EXP_RPB, cap = (uint64_t)sms * 16;
-    size_t smem = (size_t)MCX_EXP_RPB * out->rec_bytes;
+    // records per block: what fits the shared-memory budget (a multiple of 4 keeps the vector stores aligned)
+    uint32_t rpb = MCX_EXP_SMEM / out->rec_bytes;
+    if(rpb > MCX_EXP_THREADS) rpb = MCX_EXP_THREADS;
+    if(rpb >= 4u) rpb &= ~3u;
+    if(rpb == 0u) rpb = 1u; // (rec_bytes <= 8 * 2 + 5 * 4096 < MCX_EXP_SMEM: never)
+    uint64_t nblk = (n + rpb - 1) / rpb, cap = (uint64_t)sms * 16;
+    size_t smem = (size_t)rpb * out->rec_bytes;
     if(smem > 48 * 1024) CK(cudaFuncSetAttribute(mcx_format_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mcx_format_kernel<<<(unsigned)(nblk < cap ? nblk : cap), MCX_EXP_RPB, smem, st>>>(t, W, vals, n, out->rec_bytes, out->records);
+    mcx_format_kernel<<<(unsigned)(nblk < cap ? nblk : cap), MCX_EXP_THREADS, smem, st>>>(t, W, vals, n, out->rec_bytes, rpb, out->records);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
   }
@@ -213,11 +222,13 @@ cudaError_t mcx_sort_records_device(const uint8_t *d_in, uint64_t n, uint32_t k,
   // least significant key word first
   mcx_rec_keys_kernel<<<sms * 8, 256, 0, st>>>(d_in, n, rec_bytes, W - 1u, nullptr, keys, vals);
   CK(cudaGetLastError());
-  CK(radix_pass(&keys, &vals, &keys_alt, &vals_alt, n, W == 1 ? (int)(2u * k) : 64, &tmp, &tmp_bytes, st));
+  // all 64 bits of every word: the reference's `sort` compares whole words whatever k the header claims
+  // (ctx_sort.c:117-155, binary_kmer.h:79-94), so a file with bits above 2k comes out in the same order
+  CK(radix_pass(&keys, &vals, &keys_alt, &vals_alt, n, 64, &tmp, &tmp_bytes, st));
   if(W == 2) {
     mcx_rec_keys_kernel<<<sms * 8, 256, 0, st>>>(d_in, n, rec_bytes, 0u, vals, keys, nullptr);
     CK(cudaGetLastError());
-    CK(radix_pass(&keys, &vals, &keys_alt, &vals_alt, n, (int)(2u * (k - 32u)), &tmp, &tmp_bytes, st));
+    CK(radix_pass(&keys, &vals, &keys_alt, &vals_alt, n, 64, &tmp, &tmp_bytes, st));
   }
   mcx_rec_gather_kernel<<<sms * 16, 256, 0, st>>>(d_in, vals, n, rec_bytes, d_out);
   CK(cudaGetLastError());

@@ -37,41 +37,16 @@ struct McxTable {
   unsigned int *front_cnt;     // counters: one per slot
   uint32_t front_set_bits;     // log2(number of sets); 0 = no front table
   uint32_t front_colour;       // the ONE colour the front table is counting (it is flushed when the colour changes)
-  // L2 eviction policies (createpolicy handles) applied by the kernels that set them; 0 = none
-  uint64_t pol_front;          // front-table probe loads (tags)
-  uint64_t pol_cnt;            // front-table counter REDs
-  uint64_t pol_big;            // big-table probe loads
 };
 
 #if defined(__CUDACC__)
 
-// 32-byte probe load (SASS: LDG.E.256).  .ca / .cg / volatile / L1::no_allocate flavours and
-// two 16-byte loads were measured (profiles/r1_exp_ld_modes.txt): no difference except that two
-// 16-byte loads are 45 % slower, so the plain form stays.
+// 32-byte probe load (SASS: LDG.E.256).  .ca / .cg / volatile / L1::no_allocate flavours, L2 eviction-policy
+// hints and two 16-byte loads were measured (profiles/r1_exp_ld_modes.txt, r1g_experiments.txt 5, 13): no
+// difference except that two 16-byte loads are 45 % slower, so the plain form stays.
 __device__ __forceinline__ void mcx_ld256(const void *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d)
 {
   asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
-}
-
-__device__ __forceinline__ void mcx_ld256_pol(const void *p, uint64_t pol, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d)
-{
-  if(pol) asm volatile("ld.global.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol));
-  else mcx_ld256(p, a, b, c, d);
-}
-__device__ __forceinline__ void mcx_red_add_pol(unsigned int *p, uint32_t v, uint64_t pol)
-{
-  if(pol) asm volatile("red.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
-  else atomicAdd(p, v);
-}
-// hint flags (experiments, MCX_L2_HINTS): 1 = input stream evict_first, 2 = big-table probes evict_first,
-// 4 = front-table tags evict_last, 64 = counters evict_last, 128 = counters evict_first
-__device__ __forceinline__ uint64_t mcx_policy_evict_first()
-{
-  uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); return pol;
-}
-__device__ __forceinline__ uint64_t mcx_policy_evict_last()
-{
-  uint64_t pol; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol)); return pol;
 }
 
 __device__ __forceinline__ void mcx_ld128(const void *p, uint64_t &a, uint64_t &b)
@@ -103,9 +78,10 @@ __device__ __forceinline__ void mcx_covg_add(uint32_t *cv, uint32_t n, bool may_
                                              uint32_t snap = 0)
 {
   if(n == 0) return;
-  if(!may_saturate || (have_snap && snap < 0xF0000000u - n)) { atomicAdd(cv, n); return; }
+  // (n itself may be anything up to 2^32-1 when it comes from a graph file: 0xF0000000u - n must not wrap)
+  if(!may_saturate || (have_snap && n < 0xF0000000u && snap < 0xF0000000u - n)) { atomicAdd(cv, n); return; }
   uint32_t v = *(volatile uint32_t *)cv;
-  if(v < 0xF0000000u - n) { atomicAdd(cv, n); return; }
+  if(n < 0xF0000000u && v < 0xF0000000u - n) { atomicAdd(cv, n); return; }
   while(v != 0xFFFFFFFFu) {
     uint32_t nv = (v + n < v) ? 0xFFFFFFFFu : v + n;
     uint32_t old = atomicCAS(cv, v, nv);
@@ -123,6 +99,14 @@ __device__ __forceinline__ void mcx_edges_or(uint32_t *slot, uint32_t W, uint32_
   uint32_t cur = known ? known_word : *(volatile uint32_t *)e; // possibly stale: only ever misses bits => extra OR
   if((cur & bits) != bits) atomicOr(e, bits);
 }
+
+// Probing stops after MCX_PROBE_CAP slots: the table then counts as full.  Linear probing over a table sized
+// by the reference's rule (distinct / 0.75, src/graph/cmd_mem.c) has runs of a few hundred slots; runs of 2^16 need a
+// load above 0.98.  Without the cap every missing k-mer of an undersized table would scan the whole table
+// (the reference gives up after 20 full buckets: "Hash table is full", src/graph/hash_table.c:119-123,280).
+// Insert and find use the same cap, so a key is always found where it was put.
+#define MCX_PROBE_CAP 65536ull
+__device__ __forceinline__ uint64_t mcx_probe_limit(const McxTable &t) { return t.nslots < MCX_PROBE_CAP ? t.nslots : MCX_PROBE_CAP; }
 
 // find-or-insert in the big table, then covg[colour] += n (saturating) and edges |= emask.
 // Returns 0 = found, 1 = novel, 2 = table full.
@@ -153,11 +137,11 @@ __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer
   if(t.stride == 4u) {
     // 16-byte slots {key, covg, edges}: probe one 32-byte sector (= 2 slots) per load
     idx &= ~1ull;
-    for(uint64_t probes = 0; probes < t.nslots; probes += 2) {
+    for(uint64_t probes = 0, lim = mcx_probe_limit(t); probes < lim; probes += 2) {
       uint32_t *s = t.slots + idx * 4u;
       uint64_t k0, m0, k1, m1;
       if(probes == 0 && pre) { k0 = pre[0]; m0 = pre[1]; k1 = pre[2]; m1 = pre[3]; }
-      else mcx_ld256_pol(s, t.pol_big, k0, m0, k1, m1);
+      else mcx_ld256(s, k0, m0, k1, m1);
       uint32_t *hit = nullptr; uint64_t meta = 0;
       if(k0 == keyf) { hit = s; meta = m0; }
       else if(k1 == keyf) { hit = s + 4; meta = m1; }
@@ -185,7 +169,7 @@ __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer
     return 2;
   }
   // generic stride (C > 1)
-  for(uint64_t probes = 0; probes < t.nslots; probes++) {
+  for(uint64_t probes = 0, lim = mcx_probe_limit(t); probes < lim; probes++) {
     uint32_t *s = t.slots + idx * (uint64_t)t.stride;
     uint64_t cur = (probes == 0 && pre) ? pre[0] : *(volatile uint64_t *)s;
     if(cur == 0) {
@@ -211,12 +195,12 @@ __device__ __forceinline__ int mcx_table_add<2>(const McxTable &t, const McxKmer
   const uint64_t k0f = key.b[0] | MCX_KEY_FLAG, k1 = key.b[1];
   uint64_t idx = mcx_home_slot(hc, hb, t.nslots);
   int novel = 0;
-  for(uint64_t probes = 0; probes < t.nslots; probes++) {
+  for(uint64_t probes = 0, lim = mcx_probe_limit(t); probes < lim; probes++) {
     uint32_t *s = t.slots + idx * (uint64_t)t.stride;
     uint64_t c0, c1, m0 = 0, m1 = 0;
     bool have_meta = (t.stride == 8u);
     if(probes == 0 && pre) { c0 = pre[0]; c1 = pre[1]; m0 = pre[2]; m1 = pre[3]; }
-    else if(have_meta) mcx_ld256_pol(s, t.pol_big, c0, c1, m0, m1); // 32-byte slot: key + covg + edges in one sector
+    else if(have_meta) mcx_ld256(s, c0, c1, m0, m1); // 32-byte slot: key + covg + edges in one sector
     else mcx_ld128(s, c0, c1); // one 16-byte transaction: never a torn view of a 128-bit CAS
     if(c0 == 0) {
       mcx_cas128(s, 0ull, 0ull, k0f, k1, c0, c1);
@@ -248,7 +232,7 @@ __device__ __forceinline__ uint32_t *mcx_table_slot(const McxTable &t, const Mcx
   uint64_t idx = mcx_home_slot(hc, hb, t.nslots);
   if(t.stride == 4u) idx &= ~1ull;
   const uint64_t k0f = key.b[0] | MCX_KEY_FLAG;
-  for(uint64_t probes = 0; probes < t.nslots; probes++) {
+  for(uint64_t probes = 0, lim = mcx_probe_limit(t); probes < lim; probes++) {
     uint32_t *s = t.slots + idx * (uint64_t)t.stride;
     if(W == 1) {
       uint64_t cur = *(volatile uint64_t *)s;
@@ -293,7 +277,7 @@ __device__ __forceinline__ bool mcx_front_resolve_sector(const McxTable &t, cons
   const uint32_t mask = g.tagmask | MCX_FRONT_DISPLACED;
   unsigned long long *set = t.front + s4;
   uint64_t v[4];
-  mcx_ld256_pol(set, t.pol_front, v[0], v[1], v[2], v[3]);
+  mcx_ld256(set, v[0], v[1], v[2], v[3]);
   int w = -1; uint32_t seen_hi = 0;
 #pragma unroll
   for(int i = 3; i >= 0; i--) {
@@ -313,7 +297,7 @@ __device__ __forceinline__ bool mcx_front_resolve_sector(const McxTable &t, cons
     }
     if(w < 0) return false;
   }
-  mcx_red_add_pol(t.front_cnt + s4 + (uint32_t)w, 1u, t.pol_cnt);
+  atomicAdd(t.front_cnt + s4 + (uint32_t)w, 1u);
   if((seen_hi & eb) != eb) atomicOr(reinterpret_cast<unsigned int *>(&set[w]) + 1, eb);
   return true;
 }
@@ -330,7 +314,7 @@ static __device__ __noinline__ bool mcx_front_add_slow(McxTable t, uint64_t key,
 // Fast side: the set has already been loaded (v0..v3).  Handles the overwhelmingly common case --
 // the key sits in the set and its edge bits are already there -- with ONE 32-bit RED into the
 // counter region and returns true; anything else returns false (-> parked, mcx_front_add_slow).
-__device__ __forceinline__ bool mcx_front_hit(const McxFrontGeom &g, unsigned int *cnt_set, uint64_t pol, uint32_t x, uint32_t th, uint32_t eb,
+__device__ __forceinline__ bool mcx_front_hit(const McxFrontGeom &g, unsigned int *cnt_set, uint32_t x, uint32_t th, uint32_t eb,
                                               uint64_t v0, uint64_t v1, uint64_t v2, uint64_t v3)
 {
   const uint32_t mask = g.tagmask | MCX_FRONT_DISPLACED; // a displaced entry belongs to the neighbouring set: never a match here
@@ -342,7 +326,7 @@ __device__ __forceinline__ bool mcx_front_hit(const McxFrontGeom &g, unsigned in
   const uint32_t hi = m0 ? h0 : (m1 ? h1 : (m2 ? h2 : h3));
   const uint32_t way = m0 ? 0u : (m1 ? 1u : (m2 ? 2u : 3u));
   if(!(m0 | m1 | m2 | m3) || (hi & eb) != eb) return false;
-  mcx_red_add_pol(cnt_set + way, 1u, pol);
+  atomicAdd(cnt_set + way, 1u);
   return true;
 }
 

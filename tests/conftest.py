@@ -27,7 +27,7 @@ def emul():
     """CPU executable that runs the MCX_HD device math (tests/emul)."""
     src = os.path.join(ROOT, "tests", "emul", "emul_frontend.cpp")
     exe = os.path.join(ROOT, "tests", "emul", "emul_frontend")
-    deps = [src] + [os.path.join(ROOT, "mccortex_b200", "csrc", f) for f in ("mcx_device.cuh", "mcx_chunk.cuh", "mcx_pcr.cuh")]
+    deps = [src] + [os.path.join(ROOT, "mccortex_b200", "csrc", f) for f in ("mcx_device.cuh", "mcx_chunk.cuh", "mcx_pcr.cuh", "mcx_lane.cuh")]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-o", exe, src])
     return exe

@@ -21,6 +21,7 @@
 #include <array>
 #include "../../mccortex_b200/csrc/mcx_chunk.cuh"
 #include "../../mccortex_b200/csrc/mcx_pcr.cuh"
+#include "../../mccortex_b200/csrc/mcx_lane.cuh"
 
 struct Rec { uint32_t covg; uint8_t edges; };
 typedef std::map<std::array<uint64_t, 2>, Rec> Table;
@@ -119,6 +120,78 @@ static std::vector<uint8_t> slurp(const char *path)
   return data;
 }
 
+
+// --lane: the warp-autonomous front end (mcx_lane.cuh) walked tile by tile, lane by lane, like
+// mcx_build_warp_kernel does (pieces of 16 bytes; a lane sees its piece, the two after it and the last
+// base of the one before); what the GPU gets from neighbouring lanes by shuffle is read from the buffer here.
+static void lane_piece(const uint8_t *seq, uint64_t nbytes, uint64_t g, uint32_t *pk, uint32_t *bad, uint32_t *nl)
+{
+  const uint64_t npieces = (nbytes + 15) >> 4;
+  uint32_t w[4] = {0, 0, 0, 0};
+  if(g < npieces) {
+    uint8_t raw[16];
+    for(uint32_t i = 0; i < 16; i++) raw[i] = (g * 16 + i < nbytes) ? seq[g * 16 + i] : (uint8_t)('A' + (i & 1)); // garbage that looks like data
+    memcpy(w, raw, 16);
+  }
+  mcx_piece_convert(w, g * 16, nbytes, pk, bad, nl);
+}
+static void run_launch_lane(const uint8_t *seq, uint64_t nbytes, uint64_t r_begin, uint64_t r_end, uint32_t k, Table &tab, Counters &cnt)
+{
+  const uint64_t T0 = r_begin / MCX_TILE, T1 = (r_end + MCX_TILE - 1) / MCX_TILE;
+  for(uint64_t t = T0; t < T1; t++)
+    for(uint32_t lane = 0; lane < 32; lane++) {
+      const uint64_t g = 32 * t + lane;
+      uint32_t pk[3], bad[3], nl[3];
+      for(int i = 0; i < 3; i++) lane_piece(seq, nbytes, g + i, &pk[i], &bad[i], &nl[i]);
+      uint32_t prev_base = 0, prev_bad = 1;
+      if(g > 0) { uint32_t ppk, pbad, pnl; lane_piece(seq, nbytes, g - 1, &ppk, &pbad, &pnl); prev_base = ppk & 3u; prev_bad = (pbad >> 15) & 1u; }
+      const uint32_t own = mcx_piece_own(g * 16, r_begin, r_end);
+      cnt.reads += __builtin_popcount(nl[0] & own);
+      const uint64_t bad48 = (uint64_t)bad[0] | ((uint64_t)bad[1] << 16) | ((uint64_t)bad[2] << 32);
+      const uint32_t vb = mcx_lane_valid(bad48, prev_bad, k);
+      uint32_t calls = 0;
+      mcx_lane_windows(pk[0], pk[1], pk[2], vb, prev_base, k,
+        [&](const McxKmer<1> *keys, const uint32_t *emasks, uint32_t valid, uint32_t starts, uint32_t j0) {
+          calls++;
+          valid &= own >> j0;
+          for(uint32_t i = 0; i < MCX_HALF; i++) {
+            if(!((valid >> i) & 1u)) continue;
+            cnt.kmers++;
+            cnt.contigs += (starts >> i) & 1u;
+            std::array<uint64_t, 2> key = {keys[i].b[0], 0};
+            auto it = tab.find(key);
+            if(it == tab.end()) { tab[key] = Rec{1, (uint8_t)emasks[i]}; cnt.novel++; }
+            else { if(it->second.covg != 0xFFFFFFFFu) it->second.covg++; it->second.edges |= (uint8_t)emasks[i]; }
+          }
+        });
+      if(calls != MCX_LW / MCX_HALF) { fprintf(stderr, "lane front end must call its sink for every group\n"); exit(3); }
+    }
+}
+static int main_lane(int argc, char **argv)
+{
+  if(argc < 5) { fprintf(stderr, "usage: %s --lane <lines-file> <k> <r_piece>\n", argv[0]); return 2; }
+  std::vector<uint8_t> data = slurp(argv[2]);
+  uint32_t k = (uint32_t)atoi(argv[3]);
+  uint64_t piece = strtoull(argv[4], NULL, 10), nbytes = data.size();
+  if(k > 31) { fprintf(stderr, "--lane: k <= 31\n"); return 2; }
+  if(piece == 0) piece = nbytes ? nbytes : 1;
+  Table tab; Counters cnt;
+  for(uint64_t pos = 0; pos < nbytes; pos += piece) {
+    uint64_t pend = pos + piece < nbytes ? pos + piece : nbytes;
+    uint64_t b0 = pos ? pos - MCX_LB : 0, b1 = pend + MCX_TAIL < nbytes ? pend + MCX_TAIL : nbytes;
+    if(b0 % 16) { fprintf(stderr, "piece must be a multiple of 16\n"); return 2; }
+    run_launch_lane(data.data() + b0, b1 - b0, pos - b0, pend - b0, k, tab, cnt);
+  }
+  for(auto &kv : tab) {
+    fwrite(&kv.first[0], 8, 1, stdout);
+    fwrite(&kv.second.covg, 4, 1, stdout);
+    fwrite(&kv.second.edges, 1, 1, stdout);
+  }
+  fprintf(stderr, "kmers=%llu novel=%llu contigs=%llu reads=%llu\n", (unsigned long long)cnt.kmers,
+          (unsigned long long)cnt.novel, (unsigned long long)cnt.contigs, (unsigned long long)cnt.reads);
+  return 0;
+}
+
 // --pcr <lines-file> <k> <hp> <qual-lines-file|-> <qcut> <mate-file> <batch_reads>
 // the three passes of mcx_pcr.cu (orient / mark / mask) batch by batch with the MCX_HD math of mcx_pcr.cuh,
 // a std::map standing in for the table's slot numbers, then the normal front end over the filtered lines
@@ -191,6 +264,7 @@ static int main_pcr(int argc, char **argv)
 int main(int argc, char **argv)
 {
   if(argc > 1 && strcmp(argv[1], "--pcr") == 0) return main_pcr(argc, argv);
+  if(argc > 1 && strcmp(argv[1], "--lane") == 0) return main_lane(argc, argv);
   if(argc < 5) { fprintf(stderr, "usage: %s <lines-file> <k> <hp> <r_piece>\n", argv[0]); return 2; }
   FILE *f = fopen(argv[1], "rb"); if(!f) { perror(argv[1]); return 2; }
   std::vector<uint8_t> data; uint8_t buf[1 << 16]; size_t n;

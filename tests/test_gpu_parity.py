@@ -497,29 +497,6 @@ def test_load_records_and_intersect_match_oracle(M, oracle, tmp_path, k):
     g.close()
 
 
-@pytest.mark.parametrize("variant", [2, 3])
-def test_warp_specialised_kernel_matches_oracle(M, oracle, reads_small, variant, monkeypatch):
-    """the experimental warp-specialised build kernel (mcx_build_ws.cu, MCX_WS=<variant>: producer warps stage
-    hashed windows in shared memory, probe warps keep four tag loads in flight, variant 3 adds drain warps):
-    same records and counters as the oracle, including homopolymer cut-off, several batches and a k-mer
-    seen 240 000 times"""
-    monkeypatch.setenv("MCX_WS", str(variant))
-    rng = random.Random(600 + variant)
-    reads = reads_small + rand_reads(rng, 2500, 150, 12000, perr=0.004, pN=0.001) + ["A" * 150] * 2000
-    rng.shuffle(reads)
-    for k, hp in ((31, 0), (21, 4), (11, 0)):
-        recs, ost = oracle_records(oracle, reads, k, hp_cutoff=hp, capacity=1 << 22)
-        g = M.Graph(k, 1, 1 << 21)
-        half = len(reads) // 2
-        g.add_lines("".join(r + "\n" for r in reads[:half]).encode(), hp_cutoff=hp)
-        g.add_lines("".join(r + "\n" for r in reads[half:]).encode(), hp_cutoff=hp)
-        st = g.sync()
-        got, n, _ = g.export_records()
-        assert got == recs
-        _check_stats(st, ost, len(reads))
-        g.close()
-
-
 # ---- build --remove-pcr (row N3) -------------------------------------------------------------
 @pytest.mark.parametrize("k,hp,cut,matedir,nbatch", [(21, 0, 0, 1, 1), (31, 0, 0, 3, 4), (21, 4, 45, 1, 3), (33, 0, 50, 2, 2),
                                                    (63, 5, 0, 0, 5), (11, 0, 40, 1, 7)])
@@ -574,44 +551,83 @@ def test_remove_pcr_reset_between_colours(M, oracle):
     g.close()
 
 
-# ---- MCX_SPILL: parked big-table work leaves the fused kernel as tuples, kernel C inserts it ---------------
-@pytest.mark.parametrize("cap,span_mb", [(0, 0), (1000, 1), (7, 0)])
-def test_spill_variant_matches_oracle(M, oracle, reads_small, cap, span_mb, monkeypatch):
-    """MCX_SPILL=1 with a front table too small for the input (MCX_FRONT_BITS=16: 262 144 ways for ~600 000
-    distinct k-mers), so that most new k-mers are spilled; cap = 1000 / 7 tuples makes nearly all of them
-    overflow the bin and take the inline insert instead; span 1 MB cuts the device-resident batch into several
-    launch + insert pairs.  Host batch (staging slots) and device batch (primary stream), two colours (the
-    front table is flushed and restarted in between), a k-mer seen 300 000 times, homopolymer cut-off."""
-    import torch
-    monkeypatch.setenv("MCX_SPILL", "1")
-    monkeypatch.setenv("MCX_FRONT_BITS", "16")
-    if cap:
-        monkeypatch.setenv("MCX_SPILL_CAP", str(cap))
-    if span_mb:
-        monkeypatch.setenv("MCX_SPILL_SPAN_MB", str(span_mb))
-    rng = random.Random(900 + cap)
-    reads = reads_small + rand_reads(rng, 9000, 150, 3_000_000, perr=0.002, pN=0.0005) + ["A" * 150] * 2500
-    rng.shuffle(reads)
-    third = len(reads) // 3
-    parts = [reads[:third], reads[third:2 * third], reads[2 * third:]]
-    dev = torch.device("cuda:0")
-    for k, hp in ((31, 0), (21, 4)):
-        og = oracle.Graph(k, 2, 1 << 22)
-        ost = oracle.Stats()
-        for i, part in enumerate(parts):
-            for r in part:
-                og.add_read(r, colour=i & 1, hp_cutoff=hp, stats=ost)
-        want = og.dump_sorted()[len(og.header()):]
-        og.close()
-        g = M.Graph(k, 2, 1 << 21)
-        g.add_lines("".join(r + "\n" for r in parts[0]).encode(), colour=0, hp_cutoff=hp)          # host: staging slots
-        seq = _to_dev(torch, "".join(r + "\n" for r in parts[1]).encode(), dev)                      # device: primary stream
-        g.add_reads_raw(seq.data_ptr(), sum(len(r) + 1 for r in parts[1]), mem=M.MCX_MEM_DEVICE, colour=1, hp_cutoff=hp)
-        g.add_lines("".join(r + "\n" for r in parts[2]).encode(), colour=0, hp_cutoff=hp)
-        st = g.sync()
-        got, n, _ = g.export_records()
-        assert n == ost.num_kmers_novel
-        assert got == want
-        _check_stats(st, ost, len(reads))
+# ---- round-1 advisor findings ------------------------------------------------------------------------------------
+def test_wide_records_export(M, oracle):
+    """hundreds of colours (a `join` of many samples): the export formats records of any width (the first version
+    needed 128 x record bytes of shared memory and failed above ~360 colours)"""
+    rng = random.Random(41)
+    ncols, k = 600, 31
+    base = rand_reads(rng, 60, 150, 2000)
+    og = oracle.Graph(k, ncols, 1 << 16)
+    g = M.Graph(k, ncols, 1 << 16)
+    for c in (0, 1, 255, 256, 361, 598, 599):
+        reads = base[:20] + rand_reads(rng, 20, 150, 2000)
+        for r in reads:
+            og.add_read(r, colour=c)
+        g.add_lines("".join(r + "\n" for r in reads).encode(), colour=c)
+    g.sync()
+    want = og.dump_sorted()[len(og.header()):]
+    og.close()
+    for srt in (True, False):
+        got, n, rb = g.export_records(sorted=srt)
+        assert rb == 8 + 5 * ncols and n * rb == len(want)
+        if srt:
+            assert got == want
+        else:
+            assert sorted(got[i:i + rb] for i in range(0, len(got), rb)) == sorted(want[i:i + rb] for i in range(0, len(want), rb))
+    g.close()
+
+
+def test_loaded_coverage_saturates(M):
+    """graph_load adds FILE coverages (db_node.c:139-144 saturates at UINT32_MAX): 0xFFFFFFFF on top of 5 must stay
+    0xFFFFFFFF, in either order, and 0xF0000000 + 0x20000000 must saturate too"""
+    import struct
+    k = 31
+    key = 0x0123456789ABCDE  # any canonical-looking 62-bit value: the table does not care
+    def rec(covg, edges=0x11, kk=key):
+        return struct.pack("<QIB", kk, covg, edges)
+    for first, second, want in ((5, 0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 5, 0xFFFFFFFF), (0xF0000000, 0x20000000, 0xFFFFFFFF),
+                                (0x7FFFFFFF, 0x7FFFFFFF, 0xFFFFFFFE), (7, 9, 16)):
+        g = M.Graph(k, 1, 1 << 10)
+        g.load_records(rec(first) + rec(3, 0x02, key + 1), 1, [0], [0])
+        g.load_records(rec(second), 1, [0], [0])
+        got, n, rb = g.export_records()
+        assert n == 2 and rb == 13
+        assert struct.unpack("<QIB", got[:13]) == (key, want, 0x11)
+        assert struct.unpack("<QIB", got[13:]) == (key + 1, 3, 0x02)
         g.close()
-        del seq
+
+
+def test_undersized_table_fails_fast(M):
+    """an -n far too small for the input must report "Hash table is full" quickly (the reference dies at once,
+    hash_table.c:119-123,280), not scan the whole table for every missing k-mer"""
+    import time
+    rng = random.Random(5)
+    reads = rand_reads(rng, 60000, 150, 5_000_000, perr=0.0, pN=0.0, lower=0.0)   # ~4.5 M distinct k-mers
+    blob = "".join(r + "\n" for r in reads).encode()
+    for k in (31, 63):
+        g = M.Graph(k, 1, 1 << 18)
+        t0 = time.time()
+        g.add_lines(blob)
+        with pytest.raises(M.McxError) as e:
+            g.sync()
+        assert e.value.status == "MCX_ERR_TABLE_FULL"
+        assert time.time() - t0 < 20.0
+        g.close()
+
+
+def test_sort_records_compares_whole_words(M):
+    """`sort` orders records by their whole 64-bit key words whatever k says (ctx_sort.c:117-155): keys with bits
+    above 2k (a damaged header k) must come out where the reference's compare puts them"""
+    import struct
+    rng = random.Random(17)
+    for k, W in ((11, 1), (31, 1), (41, 2)):
+        recs = []
+        for _ in range(3000):
+            words = [rng.getrandbits(64) for _ in range(W)]
+            recs.append(b"".join(struct.pack("<Q", w) for w in words) + struct.pack("<IB", rng.getrandbits(32), rng.getrandbits(8)))
+        blob = b"".join(recs)
+        got = M.sort_records(k, 1, blob)
+        rb = 8 * W + 5
+        want = sorted(recs, key=lambda r: struct.unpack("<%dQ" % W, r[:8 * W]))
+        assert [got[i:i + rb] for i in range(0, len(got), rb)] == want

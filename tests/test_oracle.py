@@ -143,6 +143,48 @@ def test_device_math_matches_oracle(oracle, emul, tmp_path, reads_small, k):
                        reads=len(reads_small))
 
 
+def _emul_lane(emul, tmp_path, reads, k, piece=0):
+    p = tmp_path / "lines.txt"
+    p.write_text("".join(r + "\n" for r in reads))
+    r = subprocess.run([emul, "--lane", str(p), str(k), str(piece)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    cnt = dict(x.split("=") for x in r.stderr.decode().split())
+    return r.stdout, {a: int(b) for a, b in cnt.items()}
+
+
+@pytest.mark.parametrize("k", [3, 5, 11, 15, 17, 21, 29, 31])
+def test_lane_front_end_matches_oracle(oracle, emul, tmp_path, reads_small, k):
+    """the warp-autonomous front end (mcx_lane.cuh: 16 windows per lane, pieces of 16 bytes) against the oracle"""
+    recs, st = oracle_records(oracle, reads_small, k)
+    got, cnt = _emul_lane(emul, tmp_path, reads_small, k)
+    assert got == recs
+    assert cnt == dict(kmers=st.num_kmers_loaded, novel=st.num_kmers_novel, contigs=st.contigs_parsed,
+                       reads=len(reads_small))
+
+
+@pytest.mark.parametrize("piece", [16, 160, 512, 2048, 4112])
+def test_lane_front_end_staging_cuts(oracle, emul, tmp_path, reads_small, piece):
+    for k in (31, 19):
+        recs, st = oracle_records(oracle, reads_small, k)
+        got, cnt = _emul_lane(emul, tmp_path, reads_small, k, piece=piece)
+        assert got == recs
+        assert cnt["kmers"] == st.num_kmers_loaded and cnt["reads"] == len(reads_small) and cnt["contigs"] == st.contigs_parsed
+
+
+def test_lane_front_end_odd_reads(oracle, emul, tmp_path):
+    """reads shorter than k, empty reads, one very long read, reads that end exactly on piece / tile boundaries"""
+    import random
+    rng = random.Random(77)
+    long_read = "".join(rng.choice("ACGT") for _ in range(20000))
+    reads = ["", "A", "ACGT" * 7 + "AC", "ACGT" * 8, long_read, "", "N" * 40, "acgtn" * 30, long_read[100:100 + 511], long_read[7:7 + 15],
+             long_read[50:50 + 527], "ACGTACGTACGTACGTACGTACGTACGTACGTACGTACG" + "-" + "TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT"]
+    for k in (31, 15, 3):
+        recs, st = oracle_records(oracle, reads, k)
+        for piece in (0, 48):
+            got, cnt = _emul_lane(emul, tmp_path, reads, k, piece=piece)
+            assert got == recs
+            assert cnt == dict(kmers=st.num_kmers_loaded, novel=st.num_kmers_novel, contigs=st.contigs_parsed, reads=len(reads))
+
+
 @pytest.mark.parametrize("k,hp", [(11, 2), (21, 5), (31, 4), (31, 31), (63, 6)])
 def test_device_math_homopolymer_cutoff(oracle, emul, tmp_path, reads_small, k, hp):
     recs, st = oracle_records(oracle, reads_small, k, hp_cutoff=hp)
