@@ -420,13 +420,19 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
 
 // k <= 31: 3 CTAs x 256 threads per SM, two probe loads in flight per thread (other occupancies / depths were measured in
 // round 1: profiles/r1_exp_occupancy.txt).  k > 31 (no front table: every occurrence parks): 4 CTAs.
+#ifndef MCX_FUSED_MINB
+#define MCX_FUSED_MINB 3
+#endif
 template <int W>
-__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(W == 1 ? 3 : 4))
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(W == 1 ? MCX_FUSED_MINB : 4))
 mcx_build_fused_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTable t, const __grid_constant__ McxTupleBins nobins)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
   if(threadIdx.x == 0) q->n = 0;
-  FusedSink<W, W == 1 ? 2 : 1, false> sink{t, nobins, p.colour, p.may_saturate != 0, q, p.counters};
+#ifndef MCX_FUSED_G
+#define MCX_FUSED_G 2
+#endif
+  FusedSink<W, W == 1 ? MCX_FUSED_G : 1, false> sink{t, nobins, p.colour, p.may_saturate != 0, q, p.counters};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
 
@@ -603,7 +609,7 @@ static unsigned grid_for_chunks(const McxBuildParams &p, int ctas_per_sm)
 cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, cudaStream_t st)
 {
   if(p.r_end <= p.r_begin) return cudaSuccess;
-  if(p.k <= 31) mcx_build_fused_kernel<1><<<grid_for_chunks(p, 3), MCX_THREADS, queue_smem<1>(mcx_build_fused_kernel<1>), st>>>(p, t, mcx_no_bins());
+  if(p.k <= 31) mcx_build_fused_kernel<1><<<grid_for_chunks(p, MCX_FUSED_MINB), MCX_THREADS, queue_smem<1>(mcx_build_fused_kernel<1>), st>>>(p, t, mcx_no_bins());
   else mcx_build_fused_kernel<2><<<grid_for_chunks(p, 4), MCX_THREADS, queue_smem<2>(mcx_build_fused_kernel<2>), st>>>(p, t, mcx_no_bins());
   return cudaGetLastError();
 }

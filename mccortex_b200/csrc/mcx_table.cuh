@@ -271,13 +271,13 @@ __device__ __forceinline__ McxFrontGeom mcx_front_geom(const McxTable &t) { retu
 // sharded build, no tuple.  Returns false if the front table cannot absorb the occurrence (both
 // sectors are full of other keys): then it belongs to the big table.
 #define MCX_FRONT_DISPLACED 0x80000000u
+// v[4]: the sector as the caller loaded it (possibly a little stale: a way that has been claimed since makes the CAS
+// fail, and the value the CAS returns says whether the same key took it)
 __device__ __forceinline__ bool mcx_front_resolve_sector(const McxTable &t, const McxFrontGeom &g, uint64_t s4, uint32_t x,
-                                                         uint32_t th, uint32_t eb)
+                                                         uint32_t th, uint32_t eb, const uint64_t v[4])
 {
   const uint32_t mask = g.tagmask | MCX_FRONT_DISPLACED;
   unsigned long long *set = t.front + s4;
-  uint64_t v[4];
-  mcx_ld256(set, v[0], v[1], v[2], v[3]);
   int w = -1; uint32_t seen_hi = 0;
 #pragma unroll
   for(int i = 3; i >= 0; i--) {
@@ -307,10 +307,13 @@ static __device__ __noinline__ bool mcx_front_add_slow(McxTable t, uint64_t key,
   const McxFKey fk = mcx_fhash(key);
   const uint32_t th = (fk.y >> g.S) | g.occ, eb = emask << g.eshift;
   const uint64_t s4 = (uint64_t)(fk.y & g.setmask) << 2;
-  if(mcx_front_resolve_sector(t, g, s4, fk.x, th, eb)) return true;
-  return mcx_front_resolve_sector(t, g, s4 ^ 4ull, fk.x, th | MCX_FRONT_DISPLACED, eb);
+  // both sectors are loaded at once: a displaced key (half of what is parked) costs one L2 round trip, not two
+  uint64_t a[4], b[4];
+  mcx_ld256(t.front + s4, a[0], a[1], a[2], a[3]);
+  mcx_ld256(t.front + (s4 ^ 4ull), b[0], b[1], b[2], b[3]);
+  if(mcx_front_resolve_sector(t, g, s4, fk.x, th, eb, a)) return true;
+  return mcx_front_resolve_sector(t, g, s4 ^ 4ull, fk.x, th | MCX_FRONT_DISPLACED, eb, b);
 }
-
 // Fast side: the set has already been loaded (v0..v3).  Handles the overwhelmingly common case --
 // the key sits in the set and its edge bits are already there -- with ONE 32-bit RED into the
 // counter region and returns true; anything else returns false (-> parked, mcx_front_add_slow).
