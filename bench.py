@@ -3,14 +3,18 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--reads R]
 
-Own arm (default): one "step" = one whole `build` load phase of the workload
-(BASELINE.json configs[1]: 50M x 150 bp synthetic reads of a 4.6 Mbp genome, 0.1 %
-substitutions, k=31, 1 colour): zero the table, insert every k-mer occurrence.
-  value : inputs resident in HBM (LINES layout), CUDA events on the launching stream.
-  e2e   : the same step through the C ABI with a pinned HOST buffer: H2D copies inside the
-          timed region, counters read back to the host every step.
+Own arm (default): one "step" = one whole `build` of the workload (BASELINE.json configs[1]:
+50M x 150 bp synthetic reads of a 4.6 Mbp genome, 0.1 % substitutions, k=31, 1 colour).
+  value : zero the table, insert every k-mer occurrence; inputs resident in HBM (LINES layout),
+          CUDA events on the launching stream.
+  e2e   : the whole job through the C ABI from a pinned HOST buffer: H2D of the reads, insert,
+          sorted export (mcx_graph_export_begin(sorted=1)) and D2H of every .ctx record into host
+          memory, all inside the timed region.
+  extra : cli (one `mccortex-b200 build -S` process, FASTA on tmpfs -> sorted .ctx), config5 (the cold-table
+          regime of configs[4]: a 1/32 slice of 600M reads of a 3 Gbp genome on this GPU, and the insert kernel
+          alone on a table >> L2), other_configs (configs[2] k=63, configs[3] four colours; kernel only).
 Reference arm (--impl reference): the compiled, unmodified reference (oracle/_ref/mccortex31
-build) on the box's host cores, each step a bounded sample of the same workload.
+build) on the box's host cores, each step a bounded sample (2M reads) of the same workload.
 
 Prints ONE JSON line (rank 0).
 """
@@ -148,8 +152,7 @@ def run_reference_build(fasta, nreads, threads, tmpdir):
     return dt, nk
 
 
-def sample_reads_for(k_plus_w):
-    return int(max(200_000, min(2_000_000, 8_000_000 // max(1, k_plus_w))))
+REF_SAMPLE_READS = 2_000_000   # reads per reference step: 240 M k-mer occurrences at 87x coverage, ~10 s on 16 cores
 
 
 def reference_arm(args):
@@ -162,7 +165,7 @@ def reference_arm(args):
     SL = synth_lib()
     genome = C.create_string_buffer(GENOME)
     SL.mcx_synth_genome(genome, GENOME, 0)
-    nreads = sample_reads_for(args.steps + args.warmup)
+    nreads = min(REF_SAMPLE_READS, args.reads)
     threads = min(os.cpu_count() or 1, 32)
     tmpdir = tempfile.mkdtemp(prefix="mcxref", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     fasta = os.path.join(tmpdir, "sample.fa")
@@ -181,7 +184,9 @@ def reference_arm(args):
         "impl": "reference", "metric": "kmers_per_sec_build_k31", "value": val, "unit": "k-mers/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": dict(workload_config(args, 1), reads_per_step=nreads,
+                       note="each reference step builds the first %d reads of the workload (a bounded sample); "
+                            "the own arm builds all %d" % (nreads, args.reads)),
         "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -250,11 +255,6 @@ def own_arm(args):
         g.add_reads_raw(dseq.data_ptr(), nbytes, M.MCX_LAYOUT_LINES, M.MCX_MEM_DEVICE)
         g.flush()
 
-    def step_host():
-        g.clear()
-        g.add_reads_raw(host, nbytes, M.MCX_LAYOUT_LINES, M.MCX_MEM_HOST)
-        return g.sync()  # counters D2H: the host-visible result of a step
-
     # ---- warm-up
     for _ in range(args.warmup):
         step_device()
@@ -283,30 +283,46 @@ def own_arm(args):
     assert st.num_kmers_loaded == occ_per_step, (st.as_dict(), occ_per_step)
     value = occ_per_step * args.steps / (ms_total * 1e-3)
 
-    # ---- e2e: pinned host buffer through the C ABI, H2D inside, counters read back every step
-    e_steps = max(1, min(args.steps, 5))
-    step_host()  # warm the staging ring
+    # ---- e2e: the whole job through the C ABI.  Pinned host reads -> insert -> sorted export -> every .ctx record back
+    #      in (pinned) host memory, all inside the timed region; wall clock and CUDA events, the larger one counts.
+    def step_e2e(dst, dst_bytes):
+        g.clear()
+        g.add_reads_raw(host, nbytes, M.MCX_LAYOUT_LINES, M.MCX_MEM_HOST)
+        nrec, rb = C.c_uint64(), C.c_uint32()
+        M.binding._ck(M.lib().mcx_graph_export_begin(g.h, 1, C.byref(nrec), C.byref(rb)), "export_begin")
+        nb_out = int(nrec.value) * int(rb.value)
+        assert nb_out <= dst_bytes, (nb_out, dst_bytes)
+        M.binding._ck(M.lib().mcx_graph_export_read(g.h, 0, nrec.value, C.c_void_p(dst)), "export_read")
+        M.lib().mcx_graph_export_end(g.h)
+        return int(nrec.value), int(rb.value)
+
+    distinct = g.stats()[0]
+    out_bytes = (distinct + (distinct >> 6) + 1024) * 13
+    hout = M.host_alloc(out_bytes)
+    e_steps = max(1, min(args.steps, 3))
+    nrec_e, rb_e = step_e2e(hout, out_bytes)  # warm the staging ring and the allocator
     torch.cuda.synchronize()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record(stream)
     t0 = time.perf_counter()
     for _ in range(e_steps):
-        st_h = step_host()
-        assert st_h.num_kmers_loaded == occ_per_step
+        nrec_e, rb_e = step_e2e(hout, out_bytes)
     ee1.record(stream)
     torch.cuda.synchronize()
     e2e_wall = time.perf_counter() - t0
     e2e_ms = ee0.elapsed_time(ee1)
     e2e_val = occ_per_step * e_steps / (max(e2e_ms * 1e-3, e2e_wall))
-    distinct = st_h.num_kmers_novel
+    st_h = g.sync()
+    assert st_h.num_kmers_loaded == occ_per_step and nrec_e == distinct, (st_h.as_dict(), nrec_e, distinct)
+    # the records that came back are a sorted .ctx body: strictly ascending keys (cheap check on a sample), md5 for the record
+    import hashlib
+    rec_view = (C.c_uint8 * (nrec_e * rb_e)).from_address(hout)
+    md5_records = hashlib.md5(rec_view).hexdigest() if not args.no_extras else None
+    import struct
+    probe = [struct.unpack_from("<Q", rec_view, i * rb_e)[0] for i in range(0, nrec_e, max(1, nrec_e // 4096))]
+    assert all(x < y for x, y in zip(probe, probe[1:])), "export is not in ascending key order"
     clocks = sampler.stop()
-
-    # ---- export (not in the metric; reported for the whole-job picture)
-    t0 = time.perf_counter()
-    nrec = C.c_uint64(); rb = C.c_uint32()
-    M.binding._ck(M.lib().mcx_graph_export_begin(g.h, 1, C.byref(nrec), C.byref(rb)), "export")
-    t_export = time.perf_counter() - t0
-    M.lib().mcx_graph_export_end(g.h)
+    M.host_free(hout)
 
     # ---- CPU baseline: the compiled reference on a bounded sample, host cores of this box
     cpu = None
@@ -314,7 +330,7 @@ def own_arm(args):
         try:
             from oracle import oracle as O
             if O.ref_binary(K) is not None:
-                n_s = 2_000_000 if R >= 2_000_000 else R
+                n_s = REF_SAMPLE_READS if R >= REF_SAMPLE_READS else R
                 threads = min(os.cpu_count() or 1, 32)
                 tmpdir = tempfile.mkdtemp(prefix="mcxref", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
                 fasta = os.path.join(tmpdir, "sample.fa")
@@ -326,6 +342,22 @@ def own_arm(args):
                            n_s, nk, threads, dt)}
         except Exception as ex:  # the baseline is informative; never lose the GPU numbers over it
             cpu = {"value": None, "unit": "k-mers/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % ex}
+
+    g.close()
+    extra = {"distinct_kmers": distinct, "table_slots": capacity, "host_gen_s": t_gen,
+             "export_records": nrec_e, "export_md5": md5_records,
+             "e2e_breakdown": "H2D %.2f GB + insert + sorted export + D2H %.2f GB per step" % (nbytes / 1e9, nrec_e * rb_e / 1e9)}
+    if not args.no_extras:
+        for name, fn in (("cli", lambda: extra_cli(args, SL, genome, occ_per_step)),
+                         ("other_configs", lambda: extra_other_configs(M, torch, dseq, nbytes, R, stream)),
+                         ("config5", lambda: extra_config5(args, M, torch, SL, dev, stream))):
+            try:
+                if name == "config5":
+                    del dseq
+                    torch.cuda.empty_cache()
+                extra[name] = fn()
+            except Exception as ex:  # extras never cost the headline numbers
+                extra[name] = {"failed": "%s: %s" % (type(ex).__name__, ex)}
 
     peak, peak_src = measured_peaks()
     achieved = occ_per_step * B_ALG / (kernel_ms * 1e-3) / 1e9
@@ -345,22 +377,137 @@ def own_arm(args):
                      "traffic": traffic, "peak_source": peak_src,
                      # physical DRAM utilisation next to the logical (algorithmic) fraction
                      "dram_util": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None,
-                     "kernel": "mcx_build_fused_kernel<1,3,2>", "kernel_ms": kernel_ms,
+                     "kernel": "mcx_build_fused_kernel<1>", "kernel_ms": kernel_ms,
                      "alg_bytes_per_kmer": B_ALG, "kmers_per_launch": occ_per_step,
                      "traffic_note": (tr or {}).get("note")},
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_val, "unit": "k-mers/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 64 + 72,
+        "e2e": {"value": e2e_val, "unit": "k-mers/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nrec_e * rb_e + 64 + 72,
                 "steps": e_steps, "ms_per_step": 1e3 * max(e2e_ms * 1e-3, e2e_wall) / e_steps},
         # per step in the `value` region: one mcx_build_fused_kernel per span of <= 0xEF000000 positions (the front
         # table's 32-bit counters are merged into the big table between spans) + as many mcx_front_flush_kernel
         "gpu_launches": 2 * args.steps * (-(-nbytes // 0xEF000000)),
         "clocks": clocks,
-        "extra": {"distinct_kmers": distinct, "table_slots": capacity, "host_gen_s": t_gen,
-                  "sorted_export_s": t_export, "export_records": int(nrec.value)},
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
-    g.close()
     M.host_free(host)
+
+
+def _time_build(M, torch, g, stream, batches, iters=3):
+    """best of `iters`: clear, add the device-resident batches [(addr, nbytes, colour)], flush; returns (ms, stats)"""
+    best = 1e30
+    for _ in range(iters):
+        g.clear(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for addr, nb, col in batches:
+            g.add_reads_raw(addr, nb, M.MCX_LAYOUT_LINES, M.MCX_MEM_DEVICE, colour=col)
+        g.flush()
+        e1.record(stream); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best, g.sync()
+
+
+def extra_other_configs(M, torch, dseq, nbytes, R, stream):
+    """configs[2] (k=63) and configs[3] (four colours) on the same reads, kernel only: parity cases (tests/) whose speed
+    is worth knowing, not bench lines"""
+    peak, _ = measured_peaks()
+    stride = READ_LEN + 1
+    out = {}
+    for label, k, ncols, balg in (("configs[2] k=63, 1 colour", 63, 1, 27.70), ("configs[3] k=31, 4 colours (4 samples x R/4 reads)", 31, 4, 19.25)):
+        occ = R * (READ_LEN - k + 1)
+        cap = int((GENOME + R * READ_LEN * P_ERR * k * 1.05) / 0.75)
+        g = M.Graph(k, ncols, cap); g.set_stream(stream.cuda_stream)
+        per = R // ncols * stride
+        batches = [(dseq.data_ptr() + c * per, per if c + 1 < ncols else nbytes - c * per, c) for c in range(ncols)]
+        ms, st = _time_build(M, torch, g, stream, batches)
+        assert st.num_kmers_loaded == occ, (label, st.num_kmers_loaded, occ)
+        out[label] = {"value": occ / (ms * 1e-3), "unit": "k-mers/s", "ms_per_step": ms, "reads": R, "distinct_kmers": g.stats()[0],
+                      "roofline_frac": occ * balg / (ms * 1e-3) / 1e9 / peak, "alg_bytes_per_kmer": balg}
+        g.close()
+    return out
+
+
+def extra_cli(args, SL, genome, occ):
+    """the whole `mccortex-b200 build -S` process on the workload: FASTA on tmpfs -> sorted .ctx on tmpfs"""
+    import shutil
+    import mccortex_b200 as M
+    R = args.reads
+    need = R * (READ_LEN + 4) + R * 40   # FASTA + output
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need * 1.2 else None
+    tmpdir = tempfile.mkdtemp(prefix="mcxcli", dir=base)
+    try:
+        fasta, out = os.path.join(tmpdir, "reads.fa"), os.path.join(tmpdir, "out.ctx")
+        write_fasta_sample(fasta, 0, R, genome, SL)
+        est = int((GENOME + R * READ_LEN * P_ERR * K * 1.05) / 0.75)
+        cmd = [M.driver_path(), "build", "-f", "-q", "-S", "-m", "100G", "-n", str(est), "-k", str(K), "--sample", "s", "--seq", fasta, out]
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"failed": r.stderr[-500:]}
+        return {"wall_s": wall, "kmers_per_s": occ / wall, "fasta_bytes": os.path.getsize(fasta), "ctx_bytes": os.path.getsize(out),
+                "command": "mccortex-b200 build -S -k 31 -n %d --sample s --seq reads.fa out.ctx (tmpfs: %s)" % (est, bool(base))}
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
+
+
+def extra_config5(args, M, torch, SL, dev, stream):
+    """the cold-table regime of configs[4] (600M x 150 bp reads of a 3 Gbp genome over 8 GPUs) on ONE GPU: a 1/32 slice of
+    the reads into a local table (every k-mer is seen about once: the front table absorbs nothing, every occurrence is a
+    random DRAM sector of a table >> L2), and the insert kernel (kernel C) alone on distinct random keys"""
+    peak, _ = measured_peaks()
+    G5, R5 = int(os.environ.get("MCX_BENCH_G5", 3_000_000_000)), args.config5_reads
+    stride = READ_LEN + 1
+    nb5 = R5 * stride
+    t0 = time.perf_counter()
+    genome5 = C.create_string_buffer(G5)
+    SL.mcx_synth_genome(genome5, G5, 5)
+    host5 = M.host_alloc(nb5 + 4096)
+    SL.mcx_synth_reads(host5, 0, R5, READ_LEN, genome5, G5, P_ERR, 0, 5)
+    del genome5
+    t_gen = time.perf_counter() - t0
+    d5 = torch.empty(nb5 + 4096, dtype=torch.uint8, device=dev)
+    d5[:nb5].copy_(torch.frombuffer((C.c_uint8 * nb5).from_address(host5), dtype=torch.uint8))
+    torch.cuda.synchronize()
+    M.host_free(host5)
+    occ = R5 * (READ_LEN - K + 1)
+    cap = int(occ * 1.02 / 0.75)           # (nearly) every occurrence is a distinct k-mer at 0.9x coverage
+    g = M.Graph(K, 1, cap); g.set_stream(stream.cuda_stream)
+    ms, st = _time_build(M, torch, g, stream, [(d5.data_ptr(), nb5, 0)], iters=2)
+    assert st.num_kmers_loaded == occ, (st.num_kmers_loaded, occ)
+    distinct = g.stats()[0]
+    out = {"workload": "1/32 slice of configs[4]: %d x %d bp reads of a %d bp genome, p_err %g, k=%d, local table of %d slots (%.0f GB)" % (
+               R5, READ_LEN, G5, P_ERR, K, cap, cap * 16 / 1e9),
+           "value": occ / (ms * 1e-3), "unit": "k-mers/s", "ms_per_step": ms, "distinct_kmers": distinct,
+           "occurrences_per_distinct": occ / max(1, distinct), "tuples_per_step": 0, "nvlink_bytes": 0,
+           "frac": occ * B_ALG / (ms * 1e-3) / 1e9 / peak, "alg_bytes_per_kmer": B_ALG,
+           "dram_bytes_per_occurrence": (ncu_traffic() or {}).get("config5_dram_bytes_per_kmer"), "host_gen_s": t_gen}
+    g.close(); del d5
+    torch.cuda.empty_cache()
+    # the insert kernel alone: distinct random keys -> a 2^30-slot (17 GB) table, then the same keys again (all found)
+    n = 128_000_000
+    g = M.Graph(K, 1, 1 << 30); g.set_stream(stream.cuda_stream)
+    gen = torch.Generator(device=dev); gen.manual_seed(1)
+    keys = torch.randint(0, 1 << 62, (n,), dtype=torch.int64, device=dev, generator=gen)
+    meta = torch.full((n,), (1 << 8) | 0x21, dtype=torch.int32, device=dev)
+    alg = 8 + 8 + 2 + 12   # key compare + covg RMW + edge RMW + the 12-byte tuple read
+    res = {}
+    for label in ("novel", "found"):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record(stream)
+        g.insert_tuples(keys.data_ptr(), meta.data_ptr(), n)
+        e1.record(stream); torch.cuda.synchronize()
+        t = e0.elapsed_time(e1)
+        res[label] = {"inserts_per_s": n / (t * 1e-3), "ms": t, "logical_gb_s": n * alg / (t * 1e-3) / 1e9,
+                      "frac_logical": n * alg / (t * 1e-3) / 1e9 / peak,
+                      "frac_physical_64B": n * 64 / (t * 1e-3) / 1e9 / peak}
+    stn = g.sync()
+    assert stn.num_kmers_novel >= n * 0.999
+    g.close()
+    out["insert_kernel_cold"] = dict(res, tuples=n, table_slots=1 << 30, alg_bytes_per_insert=alg,
+                                     note="mcx_insert_tuples_kernel<1> alone; physical floor = one 32-byte sector each way per insert")
+    return out
 
 
 def main():
@@ -371,6 +518,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--reads", type=int, default=DEFAULT_READS, help="reads per GPU (default: configs[1] = 50M)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra.cli / extra.other_configs / extra.config5")
+    ap.add_argument("--config5-reads", type=int, default=18_750_000, help="reads of the configs[4] slice (default: 600M / 32)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

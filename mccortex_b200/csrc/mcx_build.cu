@@ -64,6 +64,10 @@ template <int W> struct McxSlowQueue {
   uint64_t key[MCX_QCAP(W) * W];
   uint8_t emask[MCX_QCAP(W)];
   uint32_t n;
+  // sharded builds: the drain reserves bin space once per CTA and destination (see FusedSink::drain)
+  uint8_t dest[MCX_QCAP(W)];
+  uint32_t dcnt[MCX_MAX_PARTS], dfill[MCX_MAX_PARTS];
+  unsigned long long dbase[MCX_MAX_PARTS];
 };
 // the queue lives in dynamic shared memory (static + dynamic exceeds the 48 KB static limit)
 extern __shared__ __align__(16) unsigned char mcx_dyn_smem[];
@@ -189,28 +193,65 @@ template <int W, int G, bool SHARDED> struct FusedSink { // G = probe loads kept
   __device__ __forceinline__ void reset() { if(threadIdx.x == 0) q->n = 0; }
   // the next chunk may not fit (evaluated per thread just before the step barrier, OR-reduced there)
   __device__ __forceinline__ bool should_drain() const { return q->n > MCX_QCAP(W) - MCX_T; }
-  // one parked occurrence: front table (claim / edge bit), else the big table
-  __device__ __forceinline__ void slow(McxKmer<W> key, uint32_t emask, uint32_t &novel, uint32_t &full)
+  // one parked occurrence: front table (claim / edge bit), else the big table.  Returns the shard that owns the key if
+  // the occurrence has to travel there as a tuple (sharded builds), else MCX_NO_DEST (it has been dealt with).
+#define MCX_NO_DEST 0xFFu
+  __device__ __forceinline__ uint32_t slow(McxKmer<W> key, uint32_t emask, uint32_t &novel, uint32_t &full)
   {
-    if(W == 1 && t.front_set_bits && mcx_front_add_slow(t, key.b[0], emask)) return; // absorbed by the front table
+    if(W == 1 && t.front_set_bits && mcx_front_add_slow(t, key.b[0], emask)) return MCX_NO_DEST; // absorbed by the front table
     uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
     if(SHARDED) {
       const uint32_t d = mcx_owner(hc, bins.nparts);
-      if(d != bins.my_part) { mcx_bin_push<W>(bins, d, key, (1u << 8) | emask, full); return; }
+      if(d != bins.my_part) return d;
     }
     int r = mcx_table_add<W>(t, key, hc, hb, colour, emask, 1u, may_saturate);
     novel += (r == 1);
     if(r == 2) { full = 1; atomicOr(&counters[MCX_CNT_FULL], 1ull); } // seen at once by every CTA (mcx_front_end stops inserting)
+    return MCX_NO_DEST;
   }
   // all threads of the CTA, between two __syncthreads
   __device__ __forceinline__ void drain(uint32_t &novel, uint32_t &full)
   {
     const uint32_t n = q->n;
+    if(SHARDED) {
+      if(threadIdx.x < MCX_MAX_PARTS) { q->dcnt[threadIdx.x] = 0; q->dfill[threadIdx.x] = 0; }
+      __syncthreads();
+    }
     for(uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
       McxKmer<W> key;
 #pragma unroll
       for(int w = 0; w < W; w++) key.b[w] = q->key[i * W + w];
-      slow(key, q->emask[i], novel, full);
+      const uint32_t d = slow(key, q->emask[i], novel, full);
+      if(SHARDED) {
+        q->dest[i] = (uint8_t)d;
+        if(d != MCX_NO_DEST) atomicAdd(&q->dcnt[d], 1u);
+      }
+    }
+    if(SHARDED) {
+      // Tuples for other shards.  One reservation per CTA, drain and destination: a cursor bumped once per warp round
+      // (the first version) is one L2 address hammered by every warp of the grid -- with two shards the sharded kernel
+      // ran 26 % slower than the single-GPU one although it inserts half as many cold k-mers (profiles/r2o_*, r2p_*).
+      __syncthreads();
+      if(threadIdx.x < bins.nparts && q->dcnt[threadIdx.x])
+        q->dbase[threadIdx.x] = atomicAdd(&bins.cursor[threadIdx.x], (unsigned long long)q->dcnt[threadIdx.x]);
+      __syncthreads();
+      const uint32_t lane = threadIdx.x & 31u;
+      for(uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t d = q->dest[i];
+        if(d == MCX_NO_DEST) continue;
+        // the lanes of a warp that go to the same shard take consecutive slots: their stores coalesce on the wire
+        const uint32_t peers = __match_any_sync(__activemask(), d);
+        const uint32_t leader = __ffs(peers) - 1u;
+        uint32_t first = 0;
+        if(lane == leader) first = atomicAdd(&q->dfill[d], (uint32_t)__popc(peers));
+        first = __shfl_sync(peers, first, leader);
+        const uint64_t at = q->dbase[d] + first + __popc(peers & ((1u << lane) - 1u));
+        if(at >= bins.cap) { full = 1; continue; }
+        uint64_t *kd = bins.keys[d] + at * W;
+#pragma unroll
+        for(int w = 0; w < W; w++) kd[w] = q->key[i * W + w];
+        bins.meta[d][at] = (1u << 8) | q->emask[i];
+      }
     }
   }
 };

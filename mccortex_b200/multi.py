@@ -224,6 +224,7 @@ class RoutedBuilder:
         self.sent = []
         self.pending = 0
         self.insert_stream = None
+        self.sent_total = torch.zeros((), dtype=torch.int64, device=device)
 
     def set_stream(self, stream):
         self.g.set_stream(stream.cuda_stream)
@@ -271,6 +272,7 @@ class RoutedBuilder:
 
     def exchange_counts(self):
         j = self.batch % self.NRING
+        self.sent_total += self.counts[j].sum()   # device-side: tuples this rank shipped (for the roofline accounting)
         if self.insert_stream is not None and self.batch >= 1:
             # completing this exchange tells the peers that the ring of the PREVIOUS batch is free again
             import torch
@@ -364,6 +366,93 @@ class RoutedBuilder:
         for a in self.ring_k + self.ring_m:
             M.device_free(self.dev.index, a)
         self.ring_k = self.ring_m = []
+
+
+def routed_parity_check(M, dist, rank, world, dev, stream, k, reads_per_rank, first_read_of, synth, batches=5, check=None):
+    """Hardware parity of the sharded build: the routed build -- IPC rings over NVLink, two-ring
+    reuse, insert stream, front-table flush -- of reads_per_rank reads on every rank, in `batches` batches so that every
+    ring is reused, must give byte for byte the sorted records of ONE single-GPU fused build of the same reads.
+    Every shard is exported sorted, gathered on rank 0 and merged (merge_sorted_runs); rank 0 builds the union of the
+    reads on its own GPU with the single-GPU kernel and compares md5s.  `check(records_bytes)` (tests: the oracle) may
+    add a third opinion.  Returns a dict (rank 0) / None; raises on every rank if the records differ."""
+    import hashlib
+    import numpy as np
+    import torch
+    SL, genome, G, read_len, p_err = synth
+    stride = read_len + 1
+    nb = reads_per_rank * stride
+    host = M.host_alloc(nb + 4096)
+    SL.mcx_synth_reads(host, first_read_of(rank), reads_per_rank, read_len, genome, G, p_err, 0, 0)
+    dseq = torch.empty(nb + 4096, dtype=torch.uint8, device=dev)
+    dseq[:nb].copy_(torch.frombuffer((C.c_uint8 * nb).from_address(host), dtype=torch.uint8))
+    torch.cuda.synchronize()
+    M.host_free(host)
+    distinct_est = int(G + world * reads_per_rank * read_len * p_err * k * 1.05) if G < 1e9 else int(world * reads_per_rank * (read_len - k + 1) * 1.05)
+    cap_shard = int(distinct_est / world / 0.75 * 1.1) + 4096
+    per_batch = ((reads_per_rank + batches - 1) // batches + 15) // 16 * 16   # device batches must start 16-byte aligned
+    cap_part = int(per_batch * (read_len - k + 1) * (0.5 if G < 1e9 else 1.3) / max(1, world - 1)) + (4 << 20)
+    sb = RoutedBuilder(M, dist, rank, world, dev, k, cap_shard, cap_part)
+    sb.connect_ipc()
+    sb.set_stream(stream)
+    sb.use_insert_stream(torch.cuda.Stream(device=dev))
+    for b in range(batches):   # (every rank runs every batch: the counter exchange is a collective)
+        lo = min(b * per_batch, reads_per_rank)
+        n = min(per_batch, reads_per_rank - lo)
+        sb.add_batch(dseq.data_ptr() + lo * stride, n * stride)
+    sb.flush()
+    st = sb.g.sync()
+    recs, nrec, rb = sb.g.export_records(sorted=True)
+    sb.close()
+    # gather the shards' sorted runs on rank 0
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    sizes[rank] = len(recs)
+    dist.all_reduce(sizes)
+    sizes = sizes.tolist()
+    mx = max(max(sizes), 1)
+    mine = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    if recs:
+        mine[:len(recs)] = torch.frombuffer(bytearray(recs), dtype=torch.uint8).to(dev)
+    gathered = [torch.empty(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, gathered, dst=0)
+    tot = torch.tensor([st.num_kmers_loaded], dtype=torch.int64, device=dev)
+    dist.all_reduce(tot)
+    verdict = torch.zeros(1, dtype=torch.int64, device=dev)
+    out = None
+    if rank == 0:
+        W = (k + 31) // 32
+        runs = [gathered[r][:sizes[r]].cpu().numpy() for r in range(world)]
+        h = hashlib.md5(); merged_n = 0; pieces = []
+        for piece in merge_sorted_runs(runs, rb, W):
+            b = piece.tobytes(); h.update(b); merged_n += len(piece)
+            if check is not None:
+                pieces.append(b)
+        # the same reads, one GPU, single-GPU kernel
+        allb = world * nb
+        hall = M.host_alloc(allb + 4096)
+        for r in range(world):
+            SL.mcx_synth_reads(hall + r * nb, first_read_of(r), reads_per_rank, read_len, genome, G, p_err, 0, 0)
+        dall = torch.empty(allb + 4096, dtype=torch.uint8, device=dev)
+        dall[:allb].copy_(torch.frombuffer((C.c_uint8 * allb).from_address(hall), dtype=torch.uint8))
+        torch.cuda.synchronize()
+        M.host_free(hall)
+        g1 = M.Graph(k, 1, int(distinct_est / 0.75 * 1.1) + 4096, device=dev.index)
+        g1.set_stream(stream.cuda_stream)
+        g1.add_reads_raw(dall.data_ptr(), allb, M.MCX_LAYOUT_LINES, M.MCX_MEM_DEVICE)
+        st1 = g1.sync()
+        recs1, n1, _ = g1.export_records(sorted=True)
+        g1.close()
+        md5_1 = hashlib.md5(recs1).hexdigest()
+        ok = (md5_1 == h.hexdigest()) and n1 == merged_n and st1.num_kmers_loaded == int(tot[0])
+        if ok and check is not None:
+            ok = bool(check(b"".join(pieces)))
+        out = {"ok": ok, "reads": world * reads_per_rank, "batches_per_rank": batches, "records": merged_n,
+               "md5_sharded_merged": h.hexdigest(), "md5_single_gpu": md5_1, "kmers_loaded": int(tot[0]),
+               "what": "routed %d-shard build (IPC rings over NVLink) vs one single-GPU fused build of the same reads: sorted .ctx records" % world}
+        verdict[0] = 1 if ok else 2
+    dist.broadcast(verdict, src=0)
+    if int(verdict[0]) != 1:
+        raise RuntimeError("sharded build parity FAILED on %d GPUs: %s" % (world, out))
+    return out
 
 
 def bench_multi(args, rank, world, local, dist):
@@ -469,6 +558,8 @@ def bench_multi(args, rank, world, local, dist):
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sb.launches = 0
+    if routed:
+        sb.sent_total.zero_()
     ev0.record(stream)
     for _ in range(args.steps):
         step()
@@ -487,8 +578,17 @@ def bench_multi(args, rank, world, local, dist):
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     st = sb.g.sync()
-    tot = torch.tensor([st.num_kmers_loaded, st.num_kmers_novel, sb.launches], dtype=torch.int64, device=dev)
+    tot = torch.tensor([st.num_kmers_loaded, st.num_kmers_novel, sb.launches, int(sb.sent_total) if routed else 0], dtype=torch.int64, device=dev)
     dist.all_reduce(tot)
+    # hardware parity of the routed build on a bounded sample of the same workload (1M reads per rank), every run
+    parity = None
+    if routed and os.environ.get("MCX_MULTI_PARITY", "1") != "0":
+        parity = routed_parity_check(M, dist, rank, world, dev, stream, B.K, min(R, 1_000_000), lambda r: r * R,
+                                     (SL, genome, B.GENOME, B.READ_LEN, B.P_ERR))
+        if rank == 0:
+            import sys
+            print("parity: ok (%d GPUs, %d reads, %d records, md5 %s == single-GPU build)" % (
+                world, parity["reads"], parity["records"], parity["md5_sharded_merged"]), file=sys.stderr, flush=True)
 
     e_steps = max(1, min(args.steps, 3))
     step_host()
@@ -515,7 +615,10 @@ def bench_multi(args, rank, world, local, dist):
     value = occ_per_rank * world * args.steps / (ms_total * 1e-3)
     peak, peak_src = B.measured_peaks()
     if rank == 0:
-        ach = value * B.B_ALG_MULTI / 1e9 / world
+        # algorithmic bytes: every occurrence 19.25 B; only what became a tuple pays the tuple's write, send
+        # and re-read (+24 B) -- on this workload the local front tables absorb almost everything
+        tuples_per_step = int(tot[3]) / max(1, args.steps)
+        ach = (value * B.B_ALG + tuples_per_step / (ms_total / args.steps * 1e-3) * (B.B_ALG_MULTI - B.B_ALG)) / 1e9 / world
         line = {
             "metric": "kmers_per_sec_build_k31", "value": value, "unit": "k-mers/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -524,13 +627,15 @@ def bench_multi(args, rank, world, local, dist):
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": None, "peak_source": peak_src,
                          "kernel": "mcx_build_sharded_kernel + mcx_insert_tuples_kernel (per GPU)",
-                         "note": "achieved = value x 43.25 B / n_gpus; almost all occurrences are absorbed by the local front table and never become tuples",
-                         "alg_bytes_per_kmer": B.B_ALG_MULTI},
+                         "note": "per GPU: (occurrences x 19.25 B + tuples x 24 B) / time; tuples = what the local front tables did not absorb",
+                         "alg_bytes_per_kmer": B.B_ALG, "alg_bytes_per_tuple": B.B_ALG_MULTI - B.B_ALG,
+                         "tuples_per_step": tuples_per_step, "nvlink_bytes_per_step": tuples_per_step * 12 * (world - 1) / world},
             "cpu_baseline": None,
             "e2e": {"value": e2e_val, "unit": "k-mers/s", "h2d_bytes_per_step": nbytes * world,
                     "d2h_bytes_per_step": (64 + 72) * world, "steps": e_steps, "ms_per_step": float(e_ms[0]) / e_steps},
             "gpu_launches": int(tot[2]),
             "clocks": clocks,
+            "parity": parity,
             "extra": {"distinct_kmers_total": int(tot[1]), "shard_slots": cap_shard, "batches_per_step": nb,
                       "exchange": ("fused into the kernel: peer stores over NVLink (CUDA IPC rings), counters all_to_all"
                                    if routed else "NCCL send/recv of local bins") +

@@ -10,6 +10,15 @@ LS = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 N = (int(sys.argv[2]) if len(sys.argv) > 2 else 256) * 1_000_000
 K = int(os.environ.get("KBENCH_K", 31))
 dev = torch.device("cuda:0")
+torch.cuda.init(); torch.zeros(1, device=dev)
+if os.environ.get("L2FETCH"):
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    cur = ctypes.c_size_t()
+    rt.cudaDeviceGetLimit(ctypes.byref(cur), 5)
+    r = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["L2FETCH"])))
+    new = ctypes.c_size_t(); rt.cudaDeviceGetLimit(ctypes.byref(new), 5)
+    print("cudaLimitMaxL2FetchGranularity: was %d, set rc=%d, now %d" % (cur.value, r, new.value), flush=True)
 stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
 g = M.Graph(K, 1, 1 << LS); g.set_stream(stream.cuda_stream)
 W = 1 if K <= 31 else 2
