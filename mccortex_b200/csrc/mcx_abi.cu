@@ -133,6 +133,7 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
   g->table.ncols = ncols;
   size_t bytes = (size_t)g->table.nslots * g->table.stride * 4u;
   cudaError_t e = cudaMalloc(&g->table.slots, bytes);
+  if(e == cudaErrorMemoryAllocation) { cudaGetLastError(); mcx_pool_trim(device); e = cudaMalloc(&g->table.slots, bytes); } // (export scratch cached by the pool)
   if(e != cudaSuccess) { free(g); return fail_cuda(e, "cudaMalloc(table)"); }
   abi_phase("create: table malloc");
   e = cudaMalloc(&g->d_counters, MCX_NCOUNTERS_ALL * sizeof(unsigned long long));

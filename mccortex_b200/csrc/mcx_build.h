@@ -114,7 +114,9 @@ struct McxExport {
   uint8_t *records;   // nrec * rec_bytes, .ctx record layout, ascending key order if sorted
   uint64_t nrec;
   uint32_t rec_bytes;
+  cudaStream_t stream; // the records come from the stream-ordered pool: freed on this stream
 };
+void mcx_pool_trim(int dev); // give the pool's cached blocks back to the device (before a large cudaMalloc is retried)
 cudaError_t mcx_export_build(const McxTable &t, uint32_t kmer_size, bool sorted, McxExport *out, cudaStream_t st);
 void mcx_export_free(McxExport *e);
 cudaError_t mcx_sort_records_device(const uint8_t *d_in, uint64_t n, uint32_t k, uint32_t ncols, uint8_t *d_out, cudaStream_t st);
