@@ -241,6 +241,24 @@ int mcx_device_free(int device, void *dptr);
 int mcx_ipc_export(const void *dptr, unsigned char handle[64]);
 int mcx_ipc_open(int device, const unsigned char handle[64], void **dptr);
 int mcx_ipc_close(int device, void *dptr);
+/* ---- the sharded build from ONE process (the C driver's `build -D 0,1,.. --shard`) ----------------------------
+ * One table shard per device; what ctx_build.c:389-425 does with one shared-memory table -- build_graph() over all
+ * inputs, hash_table_print_stats, graph_writer_save_mkhdr -- over P device shards: host batches are dealt to the
+ * devices piece by piece, every device runs the sharded kernel (tuples for keys it does not own are stored straight
+ * into the owner's ring over NVLink: cudaDeviceEnablePeerAccess), owners insert what arrives, the dump is the P-way
+ * merge of the shards' sorted runs.  capacity = total k-mer slots (what cmd_get_kmers_in_hash returns); batches are
+ * MCX_MEM_HOST / MCX_LAYOUT_LINES without quality / homopolymer cut-off.  One host thread per shard set. */
+typedef struct mcx_shardset mcx_shardset;
+int mcx_shardset_create(uint32_t kmer_size, uint32_t ncols, uint64_t capacity, const int *devices, uint32_t ndevices, mcx_shardset **out);
+int mcx_shardset_destroy(mcx_shardset *s);
+int mcx_shardset_add_reads(mcx_shardset *s, const mcx_read_batch *batch);  /* asynchronous; pinned buffers must stay valid until sync */
+int mcx_shardset_sync(mcx_shardset *s, mcx_load_stats *stats);
+int mcx_shardset_stats(mcx_shardset *s, uint64_t *nkmers, uint64_t *capacity);
+int mcx_shardset_export_begin(mcx_shardset *s, int sorted, uint64_t *nrecords, uint32_t *record_bytes);
+/* the next (at most max_records) records of the dump, in file order, into host_dst; *got == 0 at the end */
+int mcx_shardset_export_next(mcx_shardset *s, void *host_dst, uint64_t max_records, uint64_t *got);
+int mcx_shardset_export_end(mcx_shardset *s);
+
 /* Kernel B alone: reads -> one tuple per occurrence (count 1), binned by owner; nothing is
  * inserted locally.  Kept as the unaggregated baseline of the exchange and for tests. */
 int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *batch, uint32_t nparts, uint64_t cap_per_part,

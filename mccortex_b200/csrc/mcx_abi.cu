@@ -44,7 +44,8 @@ struct mcx_graph {
   uint64_t pend_offsets_reads, pend_offsets_bases; // OFFSETS batches: counted on the host
   uint64_t nkmers;         // slots claimed so far (updated at sync)
   McxExport exp; bool exp_valid;
-  uint8_t *d_tmp; size_t d_tmp_bytes; // scratch for OFFSETS -> LINES repack
+  uint8_t *d_tmp; size_t d_tmp_bytes; // scratch of the batch being queued (OFFSETS -> LINES repack, quality batches, graph records):
+  uint8_t *d_tmpv[2]; size_t d_tmp_bytesv[2]; cudaEvent_t ev_tmp[2]; int tmp_cur; // one of two, so that batch b+1 is queued while b runs
   uint8_t *d_isec;         // build --intersect: one edge byte per slot (Edges *isec_edges, ctx_build.c:341-343), else NULL
   uint64_t front_pending;  // positions queued since the front table was last flushed (its counters are 32-bit)
   uint32_t *d_first;       // build --remove-pcr: first read ordinal per (slot, orientation) (mcx_pcr.cuh), else NULL
@@ -201,7 +202,8 @@ extern "C" int mcx_graph_destroy(mcx_graph *g)
   }
   if(g->own_primary) cudaStreamDestroy(g->own_primary);
   if(g->ev_fork) cudaEventDestroy(g->ev_fork);
-  if(g->d_tmp) cudaFree(g->d_tmp);
+  g->d_tmpv[g->tmp_cur] = g->d_tmp;
+  for(int i = 0; i < 2; i++) { if(g->d_tmpv[i]) cudaFree(g->d_tmpv[i]); if(g->ev_tmp[i]) cudaEventDestroy(g->ev_tmp[i]); }
   if(g->d_isec) cudaFree(g->d_isec);
   if(g->d_first) cudaFree(g->d_first);
   if(g->d_pcr) cudaFree(g->d_pcr);
@@ -382,6 +384,24 @@ static int add_lines_host(mcx_graph *g, const mcx_read_batch *b, const uint8_t *
   return MCX_OK;
 }
 
+// Side paths (quality batches, OFFSETS batches) stage through device scratch.  Two scratch buffers alternate: the one a
+// batch takes is free once the batch queued two calls earlier has run (its event), so the host queues batch b+1 while
+// batch b's copies and kernels run -- no cudaStreamSynchronize per batch (round 1 had one: the production pipeline's
+// --fq-cutoff builds ran without any overlap).
+static int tmp_rotate(mcx_graph *g)
+{
+  g->d_tmpv[g->tmp_cur] = g->d_tmp; g->d_tmp_bytesv[g->tmp_cur] = g->d_tmp_bytes;
+  g->tmp_cur ^= 1;
+  if(!g->ev_tmp[g->tmp_cur]) CU(cudaEventCreateWithFlags(&g->ev_tmp[g->tmp_cur], cudaEventDisableTiming));
+  else CU(cudaEventSynchronize(g->ev_tmp[g->tmp_cur]));
+  g->d_tmp = g->d_tmpv[g->tmp_cur]; g->d_tmp_bytes = g->d_tmp_bytesv[g->tmp_cur];
+  return MCX_OK;
+}
+static int tmp_release(mcx_graph *g, cudaStream_t st)
+{
+  CU(cudaEventRecord(g->ev_tmp[g->tmp_cur], st));
+  return MCX_OK;
+}
 static int ensure_tmp(mcx_graph *g, size_t bytes)
 {
   if(g->d_tmp_bytes >= bytes) return MCX_OK;
@@ -413,7 +433,8 @@ static int add_reads_qual(mcx_graph *g, const mcx_read_batch *b)
   size_t off_off = raw_qual_off + (b->nbytes + A - 1) / A * A;
   size_t need = off_off + (offsets ? (size_t)(b->nreads + 1) * 8 : 0) + A;
   bool direct = !offsets && b->mem == MCX_MEM_DEVICE && (((uintptr_t)b->seq | (uintptr_t)b->qual) & 15u) == 0;
-  int r = ensure_tmp(g, direct ? sum_off + sum_bytes + A : need); if(r) return r;
+  int r = tmp_rotate(g); if(r) return r;
+  r = ensure_tmp(g, direct ? sum_off + sum_bytes + A : need); if(r) return r;
   const uint8_t *dseq, *dqual;
   if(direct) { dseq = (const uint8_t *)b->seq; dqual = (const uint8_t *)b->qual; }
   else if(!offsets) {
@@ -440,8 +461,7 @@ static int add_reads_qual(mcx_graph *g, const mcx_read_batch *b)
   if(b->must_exist) { CU(mcx_launch_contig_summary(p, st)); CU(mcx_launch_build_lookup(p, g->table, st)); }
   else CU(mcx_launch_build_fused_qual(p, g->table, st));
   g->pend_positions += lines_bytes;
-  CU(cudaStreamSynchronize(st)); // d_tmp (and pageable host sources) are reused by the next batch
-  return MCX_OK;
+  return tmp_release(g, st); // (pageable host sources were staged by cudaMemcpyAsync before it returned; pinned ones stay the caller's until sync)
 }
 
 extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
@@ -478,7 +498,8 @@ extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
   const size_t lines_off = 0, offs_off = (lines_bytes + 255) & ~(size_t)255;
   size_t raw_off = (offs_off + off_bytes + 255) & ~(size_t)255;
   size_t need = raw_off + (b->mem == MCX_MEM_HOST ? ((b->nbytes + 255) & ~(size_t)255) : 0);
-  int r = ensure_tmp(g, need + 256); if(r) return r;
+  int r = tmp_rotate(g); if(r) return r;
+  r = ensure_tmp(g, need + 256); if(r) return r;
   cudaStream_t st = primary(g);
   uint64_t *d_off = (uint64_t *)(g->d_tmp + offs_off);
   const uint8_t *d_raw = (const uint8_t *)b->seq;
@@ -486,7 +507,6 @@ extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
     if(b->offsets[0] != 0 || b->offsets[b->nreads] != b->nbytes) return MCX_ERR_BAD_ARG;
     CU(cudaMemcpyAsync(g->d_tmp + raw_off, b->seq, b->nbytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_off, b->offsets, off_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st)); // pageable sources: make "host buffers reusable on return" true
     d_raw = g->d_tmp + raw_off;
   } else if(b->mem == MCX_MEM_DEVICE) {
     CU(cudaMemcpyAsync(d_off, b->offsets, off_bytes, cudaMemcpyDeviceToDevice, st));
@@ -496,9 +516,7 @@ extern "C" int mcx_graph_add_reads(mcx_graph *g, const mcx_read_batch *b)
   McxBuildParams p = make_params(g, b, g->d_tmp + lines_off, lines_bytes, 0, lines_bytes);
   CU(launch_build(g, b, p, st));
   g->pend_positions += lines_bytes;
-  // d_tmp is reused by the next OFFSETS batch: order it behind this one
-  CU(cudaStreamSynchronize(st));
-  return MCX_OK;
+  return tmp_release(g, st);
 }
 
 // ---- build --remove-pcr ---------------------------------------------------------------------
@@ -691,9 +709,10 @@ extern "C" int mcx_kmer_tuples(mcx_graph *g, const mcx_read_batch *b, uint32_t n
 }
 
 // sharded build, per batch: local front table + local big table for owned keys + tuples for the rest
+// [r_begin, r_end): the positions of the (device) buffer this launch owns; r_end == 0 means the whole buffer
 static int add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t nparts, uint32_t my_part, uint64_t cap_per_part,
                              uint64_t *keys_out, uint32_t *meta_out, uint64_t *const *keys_dst, uint32_t *const *meta_dst,
-                             uint64_t *counts_out)
+                             uint64_t *counts_out, uint64_t r_begin = 0, uint64_t r_end = 0)
 {
   if(!g || !b || nparts < 2 || my_part >= nparts || !cap_per_part || !counts_out) return MCX_ERR_BAD_ARG;
   if(!(keys_out && meta_out) && !(keys_dst && meta_dst)) return MCX_ERR_BAD_ARG;
@@ -707,10 +726,12 @@ static int add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t npa
   { int r = fill_bins(&bins, g->W, nparts, my_part, cap_per_part, keys_out, meta_out, keys_dst, meta_dst, counts_out); if(r) return r; }
   { int r = front_colour(g, b->colour); if(r) return r; }
   g->sharded = true;
-  { int r = front_guard(g, b->nbytes); if(r) return r; }
+  if(r_end == 0) r_end = b->nbytes;
+  if(r_begin > r_end || r_end > b->nbytes) return MCX_ERR_BAD_ARG;
+  { int r = front_guard(g, r_end - r_begin); if(r) return r; }
   CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
-  g->occ_bound += b->nbytes;
-  McxBuildParams p = make_params(g, b, (const uint8_t *)b->seq, b->nbytes, 0, b->nbytes);
+  g->occ_bound += r_end - r_begin;
+  McxBuildParams p = make_params(g, b, (const uint8_t *)b->seq, b->nbytes, r_begin, r_end);
 #ifdef MCX_EXPERIMENTS
   if(g->warp_kernel && mcx_warp_kernel_supports(p)) {
     for(uint32_t c = 0; c < (1u << g->ncls_log2); c++) {
@@ -721,7 +742,7 @@ static int add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t npa
   } else
 #endif
   CU(mcx_launch_build_sharded(p, g->table, bins, st));
-  g->pend_positions += b->nbytes;
+  g->pend_positions += r_end - r_begin;
   g->sharded = true;
   return MCX_OK;
 }
@@ -935,4 +956,312 @@ extern "C" uint32_t mcx_key_owner(const uint64_t *key_words, uint32_t k, uint32_
   if(k <= 31) { McxKmer<1> key; key.b[0] = key_words[0]; hc = mcx_lookup3<1>(key, 0u, &hb); }
   else { McxKmer<2> key; key.b[0] = key_words[0]; key.b[1] = key_words[1]; hc = mcx_lookup3<2>(key, 0u, &hb); }
   return mcx_owner(hc, nparts);
+}
+
+
+// =====================================================================================================================
+// Shard set: the sharded build driven from ONE process (the C driver's `build -D 0,1,.. --shard`).
+// One table shard per device, owner(key) = top bits of Lookup3.  Host batches are cut into pieces of
+// MCX_STAGE_POS positions, piece i goes to device i mod P: H2D on the device's copy stream, then the sharded kernel
+// (mcx_build_sharded_kernel: local front table, local inserts for owned keys, tuples for the others stored straight
+// into the owner's receive ring -- peer memory over NVLink, cudaDeviceEnablePeerAccess), then kernel C on every owner.
+// Ordering is events only (the host never waits inside a batch except for a free staging slot):
+//   produced[d]     d's kernel, hence its stores into the owners' rings and its counters, has completed
+//   inserted[o][d]  owner o has inserted region d of its ring: d may overwrite it (and its counters) with its next piece
+// Replaces what ctx_build.c:389-425 does with one shared-memory table: build_graph() + graph_writer_save_mkhdr().
+#define MCX_SS_NSLOT 2
+struct mcx_shardset {
+  uint32_t k, W, ncols, P;
+  int dev[MCX_MAX_PARTS];
+  mcx_graph *g[MCX_MAX_PARTS];
+  uint64_t cap;                                  // tuples per (owner, sender) ring region
+  uint64_t *ring_k[MCX_MAX_PARTS]; uint32_t *ring_m[MCX_MAX_PARTS];   // on the OWNER: P regions
+  uint64_t *counts[MCX_MAX_PARTS];               // on the SENDER: tuples it produced for each owner
+  cudaStream_t copy[MCX_MAX_PARTS];
+  uint8_t *d_stage[MCX_MAX_PARTS][MCX_SS_NSLOT], *h_stage[MCX_MAX_PARTS][MCX_SS_NSLOT];
+  cudaEvent_t staged[MCX_MAX_PARTS][MCX_SS_NSLOT], stage_free[MCX_MAX_PARTS][MCX_SS_NSLOT];
+  int slot[MCX_MAX_PARTS];
+  cudaEvent_t produced[MCX_MAX_PARTS], inserted[MCX_MAX_PARTS][MCX_MAX_PARTS];
+  bool region_busy[MCX_MAX_PARTS][MCX_MAX_PARTS];
+  uint32_t next, colour; bool dirty;             // round robin; colour of the pieces since the last flush
+  uint64_t pending[MCX_MAX_PARTS];               // positions since the last front-table flush, per device
+  uint64_t bytes_submitted;
+  // export: one sorted run per shard, merged on the host while reading
+  bool exp_on, exp_sorted; uint32_t rec_bytes;
+  uint64_t exp_n[MCX_MAX_PARTS], exp_at[MCX_MAX_PARTS];   // records of shard d / records already fetched
+  uint8_t *exp_buf[MCX_MAX_PARTS]; uint64_t exp_have[MCX_MAX_PARTS], exp_pos[MCX_MAX_PARTS];  // host chunk: records in it / consumed
+  uint32_t exp_cur;
+};
+#define MCX_SS_CHUNK_RECS (1u << 20)
+
+static void ss_peer_pointers(mcx_shardset *s, uint32_t d, uint64_t **kd, uint32_t **md)
+{
+  for(uint32_t o = 0; o < s->P; o++) { kd[o] = s->ring_k[o] + (uint64_t)d * s->cap * s->W; md[o] = s->ring_m[o] + (uint64_t)d * s->cap; }
+}
+// after d has produced (kernel or flush): every owner inserts region d of its ring
+static int ss_insert_all(mcx_shardset *s, uint32_t d, uint32_t colour)
+{
+  CU(cudaSetDevice(s->dev[d]));
+  CU(cudaEventRecord(s->produced[d], primary(s->g[d])));
+  for(uint32_t o = 0; o < s->P; o++) {
+    if(o == d) continue;
+    mcx_graph *go = s->g[o];
+    CU(cudaSetDevice(s->dev[o]));
+    CU(cudaStreamWaitEvent(primary(go), s->produced[d], 0));
+    go->occ_bound += s->cap;
+    CU(mcx_launch_insert_tuples(s->ring_k[o] + (uint64_t)d * s->cap * s->W, s->ring_m[o] + (uint64_t)d * s->cap, s->cap,
+                                s->counts[d] + o, s->k, go->table, colour, go->occ_bound >= 0xF0000000ull, go->d_counters, primary(go)));
+    CU(cudaEventRecord(s->inserted[o][d], primary(go)));
+    s->region_busy[o][d] = true;
+  }
+  return MCX_OK;
+}
+// d may write its regions (and counters) again only after the owners have read them
+static int ss_wait_regions(mcx_shardset *s, uint32_t d)
+{
+  CU(cudaSetDevice(s->dev[d]));
+  for(uint32_t o = 0; o < s->P; o++)
+    if(o != d && s->region_busy[o][d]) { CU(cudaStreamWaitEvent(primary(s->g[d]), s->inserted[o][d], 0)); s->region_busy[o][d] = false; }
+  return MCX_OK;
+}
+static int ss_flush(mcx_shardset *s)
+{
+  if(!s->dirty) return MCX_OK;
+  for(uint32_t d = 0; d < s->P; d++) {
+    uint64_t *kd[MCX_MAX_PARTS]; uint32_t *md[MCX_MAX_PARTS];
+    ss_peer_pointers(s, d, kd, md);
+    { int r = ss_wait_regions(s, d); if(r) return r; }
+    { int r = flush_sharded(s->g[d], s->P, d, s->cap, NULL, NULL, kd, md, s->counts[d]); if(r) return r; }
+    { int r = ss_insert_all(s, d, s->colour); if(r) return r; }
+    s->pending[d] = 0;
+  }
+  s->dirty = false;
+  return MCX_OK;
+}
+
+extern "C" int mcx_shardset_destroy(mcx_shardset *s)
+{
+  if(!s) return MCX_OK;
+  for(uint32_t d = 0; d < s->P; d++) { cudaSetDevice(s->dev[d]); cudaDeviceSynchronize(); }
+  for(uint32_t d = 0; d < s->P; d++) {
+    cudaSetDevice(s->dev[d]);
+    if(s->exp_buf[d]) cudaFreeHost(s->exp_buf[d]);
+    for(int i = 0; i < MCX_SS_NSLOT; i++) {
+      if(s->d_stage[d][i]) cudaFree(s->d_stage[d][i]);
+      if(s->h_stage[d][i]) cudaFreeHost(s->h_stage[d][i]);
+      if(s->staged[d][i]) cudaEventDestroy(s->staged[d][i]);
+      if(s->stage_free[d][i]) cudaEventDestroy(s->stage_free[d][i]);
+    }
+    if(s->copy[d]) cudaStreamDestroy(s->copy[d]);
+    if(s->produced[d]) cudaEventDestroy(s->produced[d]);
+    for(uint32_t o = 0; o < s->P; o++) if(s->inserted[d][o]) cudaEventDestroy(s->inserted[d][o]);
+    if(s->ring_k[d]) cudaFree(s->ring_k[d]);
+    if(s->ring_m[d]) cudaFree(s->ring_m[d]);
+    if(s->counts[d]) cudaFree(s->counts[d]);
+    if(s->g[d]) mcx_graph_destroy(s->g[d]);
+  }
+  free(s);
+  return MCX_OK;
+}
+
+extern "C" int mcx_shardset_create(uint32_t k, uint32_t ncols, uint64_t capacity, const int *devices, uint32_t ndevices, mcx_shardset **out)
+{
+  if(!out || !devices || ndevices < 2 || ndevices > MCX_MAX_PARTS || capacity == 0) return MCX_ERR_BAD_ARG;
+  const int ndev = mcx_device_count();
+  if(ndev == 0) { snprintf(g_err, sizeof(g_err), "no CUDA device: libmcxgpu has no CPU fallback"); return MCX_ERR_NO_DEVICE; }
+  for(uint32_t d = 0; d < ndevices; d++) {
+    if(devices[d] < 0 || devices[d] >= ndev) return MCX_ERR_BAD_ARG;
+    for(uint32_t e = 0; e < d; e++) if(devices[e] == devices[d]) { snprintf(g_err, sizeof(g_err), "a device may hold one shard only"); return MCX_ERR_BAD_ARG; }
+  }
+  mcx_shardset *s = (mcx_shardset *)calloc(1, sizeof(*s));
+  if(!s) return MCX_ERR_NOMEM;
+  s->k = k; s->W = (k + 31u) / 32u; s->ncols = ncols; s->P = ndevices;
+  // a piece is MCX_STAGE_POS positions; in the worst case (nothing absorbed by the front table) its occurrences
+  // spread evenly over the owners: 1.5 x that + the front table's flush (at most one tuple per slot, spread likewise)
+  s->cap = (MCX_STAGE_POS / ndevices) * 3u / 2u + (1u << 20);
+  // a shard holds 1/P of the k-mers (+ 10 % for the spread of a hash partition)
+  const uint64_t cap_shard = capacity / ndevices + capacity / ndevices / 10u + 1024u;
+  int rc = MCX_OK;
+  for(uint32_t d = 0; d < ndevices && rc == MCX_OK; d++) {
+    s->dev[d] = devices[d];
+    rc = mcx_graph_create(k, ncols, cap_shard, devices[d], 0, &s->g[d]);
+  }
+#define SS_CU(x) do { if(rc == MCX_OK) { cudaError_t e_ = (x); if(e_ != cudaSuccess) rc = fail_cuda(e_, #x); } } while(0)
+  for(uint32_t d = 0; d < ndevices && rc == MCX_OK; d++) {
+    SS_CU(cudaSetDevice(devices[d]));
+    for(uint32_t o = 0; o < ndevices && rc == MCX_OK; o++) {
+      if(o == d) continue;
+      int can = 0;
+      SS_CU(cudaDeviceCanAccessPeer(&can, devices[d], devices[o]));
+      if(rc == MCX_OK && !can) { snprintf(g_err, sizeof(g_err), "GPU %d cannot access GPU %d (no peer access)", devices[d], devices[o]); rc = MCX_ERR_UNSUPPORTED; }
+      if(rc == MCX_OK) { cudaError_t e = cudaDeviceEnablePeerAccess(devices[o], 0); if(e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = fail_cuda(e, "cudaDeviceEnablePeerAccess"); cudaGetLastError(); }
+    }
+    SS_CU(cudaMalloc(&s->ring_k[d], (size_t)ndevices * s->cap * s->W * sizeof(uint64_t)));
+    SS_CU(cudaMalloc(&s->ring_m[d], (size_t)ndevices * s->cap * sizeof(uint32_t)));
+    SS_CU(cudaMalloc(&s->counts[d], MCX_MAX_PARTS * sizeof(uint64_t)));
+    SS_CU(cudaMemset(s->counts[d], 0, MCX_MAX_PARTS * sizeof(uint64_t)));
+    SS_CU(cudaStreamCreateWithFlags(&s->copy[d], cudaStreamNonBlocking));
+    SS_CU(cudaEventCreateWithFlags(&s->produced[d], cudaEventDisableTiming));
+    for(uint32_t o = 0; o < ndevices; o++) SS_CU(cudaEventCreateWithFlags(&s->inserted[d][o], cudaEventDisableTiming));
+    for(int i = 0; i < MCX_SS_NSLOT; i++) {
+      SS_CU(cudaMalloc(&s->d_stage[d][i], MCX_STAGE_BYTES));
+      SS_CU(cudaHostAlloc(&s->h_stage[d][i], MCX_STAGE_BYTES, cudaHostAllocDefault));
+      SS_CU(cudaEventCreateWithFlags(&s->staged[d][i], cudaEventDisableTiming));
+      SS_CU(cudaEventCreateWithFlags(&s->stage_free[d][i], cudaEventDisableTiming));
+    }
+  }
+#undef SS_CU
+  if(rc != MCX_OK) { mcx_shardset_destroy(s); return rc; }
+  *out = s;
+  return MCX_OK;
+}
+
+// replaces build_graph() over one shared table (src/tools/build_graph.c:192-301) for a host batch in LINES layout
+extern "C" int mcx_shardset_add_reads(mcx_shardset *s, const mcx_read_batch *b)
+{
+  if(!s || !b || b->colour >= s->ncols) return MCX_ERR_BAD_ARG;
+  if(b->layout != MCX_LAYOUT_LINES || b->mem != MCX_MEM_HOST || (b->nbytes && !b->seq)) return MCX_ERR_BAD_ARG;
+  if((b->fq_cutoff && b->qual) || b->hp_cutoff || b->must_exist) {
+    snprintf(g_err, sizeof(g_err), "sharded builds take plain reads only (no quality / homopolymer cut-off, no --intersect)"); return MCX_ERR_UNSUPPORTED;
+  }
+  if(b->nbytes == 0) return MCX_OK;
+  if(s->exp_on) return MCX_ERR_BAD_ARG;
+  if(s->dirty && b->colour != s->colour) { int r = ss_flush(s); if(r) return r; }   // the front tables count one colour at a time
+  s->colour = b->colour;
+  const uint8_t *hseq = (const uint8_t *)b->seq;
+  const uint64_t nbytes = b->nbytes;
+  cudaPointerAttributes attr;
+  const bool pinned = (cudaPointerGetAttributes(&attr, hseq) == cudaSuccess) && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  for(uint64_t pos = 0; pos < nbytes; pos += MCX_STAGE_POS) {
+    const uint64_t pend = pos + MCX_STAGE_POS < nbytes ? pos + MCX_STAGE_POS : nbytes;
+    const uint64_t b0 = pos ? pos - MCX_LB : 0, b1 = pend + MCX_TAIL < nbytes ? pend + MCX_TAIL : nbytes;
+    // every device's front table counts in 32 bits: flush them all before any could wrap
+    for(uint32_t d = 0; d < s->P; d++) if(s->pending[d] + MCX_STAGE_POS >= 0xE0000000ull) { int r = ss_flush(s); if(r) return r; break; }
+    const uint32_t d = s->next++ % s->P;
+    mcx_graph *g = s->g[d];
+    CU(cudaSetDevice(s->dev[d]));
+    const int sl = s->slot[d]; s->slot[d] = (sl + 1) % MCX_SS_NSLOT;
+    CU(cudaEventSynchronize(s->stage_free[d][sl]));       // the kernel that last read this staging slot is done
+    const uint8_t *src = hseq + b0;
+    if(!pinned) { memcpy(s->h_stage[d][sl], src, b1 - b0); src = s->h_stage[d][sl]; }
+    CU(cudaMemcpyAsync(s->d_stage[d][sl], src, b1 - b0, cudaMemcpyHostToDevice, s->copy[d]));
+    CU(cudaEventRecord(s->staged[d][sl], s->copy[d]));
+    CU(cudaStreamWaitEvent(primary(g), s->staged[d][sl], 0));
+    { int r = ss_wait_regions(s, d); if(r) return r; }
+    uint64_t *kd[MCX_MAX_PARTS]; uint32_t *md[MCX_MAX_PARTS];
+    ss_peer_pointers(s, d, kd, md);
+    mcx_read_batch db = *b;
+    db.mem = MCX_MEM_DEVICE; db.seq = (const char *)s->d_stage[d][sl]; db.nbytes = b1 - b0; db.qual = NULL;
+    { int r = add_reads_sharded(g, &db, s->P, d, s->cap, NULL, NULL, kd, md, s->counts[d], pos - b0, pend - b0); if(r) return r; }
+    CU(cudaEventRecord(s->stage_free[d][sl], primary(g)));
+    { int r = ss_insert_all(s, d, b->colour); if(r) return r; }
+    s->pending[d] += pend - pos;
+    s->dirty = true;
+  }
+  s->bytes_submitted += nbytes;
+  return MCX_OK;
+}
+
+// join everything; stats = the counters of all shards since the previous sync
+extern "C" int mcx_shardset_sync(mcx_shardset *s, mcx_load_stats *stats)
+{
+  if(!s) return MCX_ERR_BAD_ARG;
+  { int r = ss_flush(s); if(r) return r; }
+  for(uint32_t d = 0; d < s->P; d++) { CU(cudaSetDevice(s->dev[d])); CU(cudaStreamSynchronize(s->copy[d])); CU(cudaStreamSynchronize(primary(s->g[d]))); }
+  mcx_load_stats tot; memset(&tot, 0, sizeof(tot));
+  int rc = MCX_OK;
+  for(uint32_t d = 0; d < s->P; d++) {
+    mcx_load_stats st;
+    const int r = mcx_graph_sync(s->g[d], &st);
+    if(r && rc == MCX_OK) rc = r;
+    tot.total_bases_read += st.total_bases_read; tot.total_bases_loaded += st.total_bases_loaded;
+    tot.contigs_parsed += st.contigs_parsed; tot.num_kmers_loaded += st.num_kmers_loaded; tot.num_kmers_novel += st.num_kmers_novel;
+    tot.num_se_reads += st.num_se_reads;
+  }
+  tot.num_good_reads = tot.num_bad_reads = UINT64_MAX;
+  if(stats) *stats = tot;
+  return rc;
+}
+
+extern "C" int mcx_shardset_stats(mcx_shardset *s, uint64_t *nkmers, uint64_t *capacity)
+{
+  if(!s) return MCX_ERR_BAD_ARG;
+  uint64_t n = 0, c = 0;
+  for(uint32_t d = 0; d < s->P; d++) { n += s->g[d]->nkmers; c += s->g[d]->capacity; }
+  if(nkmers) *nkmers = n;
+  if(capacity) *capacity = c;
+  return MCX_OK;
+}
+
+// replaces graph_writer_save_mkhdr's record stream (src/graph/graph_writer.c:182-193): every shard exports its records
+// (sorted: ascending keys); ownership is by hash, so the file order is the P-way merge of the shards' runs
+extern "C" int mcx_shardset_export_begin(mcx_shardset *s, int sorted, uint64_t *nrecords, uint32_t *record_bytes)
+{
+  if(!s) return MCX_ERR_BAD_ARG;
+  { int r = mcx_shardset_sync(s, NULL); if(r) return r; }
+  uint64_t tot = 0;
+  for(uint32_t d = 0; d < s->P; d++) {
+    uint32_t rb = 0;
+    int r = mcx_graph_export_begin(s->g[d], sorted, &s->exp_n[d], &rb);
+    if(r) return r;
+    s->rec_bytes = rb; s->exp_at[d] = s->exp_have[d] = s->exp_pos[d] = 0;
+    tot += s->exp_n[d];
+    if(!s->exp_buf[d]) { CU(cudaSetDevice(s->dev[d])); CU(cudaHostAlloc(&s->exp_buf[d], (size_t)MCX_SS_CHUNK_RECS * rb, cudaHostAllocDefault)); }
+  }
+  s->exp_on = true; s->exp_sorted = sorted != 0; s->exp_cur = 0;
+  if(nrecords) *nrecords = tot;
+  if(record_bytes) *record_bytes = s->rec_bytes;
+  return MCX_OK;
+}
+static int ss_refill(mcx_shardset *s, uint32_t d)
+{
+  const uint64_t left = s->exp_n[d] - s->exp_at[d];
+  const uint64_t n = left < MCX_SS_CHUNK_RECS ? left : MCX_SS_CHUNK_RECS;
+  s->exp_have[d] = n; s->exp_pos[d] = 0;
+  if(n == 0) return MCX_OK;
+  int r = mcx_graph_export_read(s->g[d], s->exp_at[d], n, s->exp_buf[d]);
+  s->exp_at[d] += n;
+  return r;
+}
+// the next (at most max_records) records of the merged stream -> host_dst; *got = 0 at the end
+extern "C" int mcx_shardset_export_next(mcx_shardset *s, void *host_dst, uint64_t max_records, uint64_t *got)
+{
+  if(!s || !s->exp_on || !got || (!host_dst && max_records)) return MCX_ERR_BAD_ARG;
+  const uint32_t rb = s->rec_bytes, W = s->W;
+  uint8_t *out = (uint8_t *)host_dst;
+  uint64_t n = 0;
+  while(n < max_records) {
+    uint32_t best = UINT32_MAX; uint64_t b0 = 0, b1 = 0;
+    for(uint32_t d = s->exp_sorted ? 0 : s->exp_cur; d < s->P; d++) {
+      if(s->exp_pos[d] == s->exp_have[d]) {
+        if(s->exp_at[d] == s->exp_n[d]) { if(!s->exp_sorted) { s->exp_cur = d + 1; } continue; }
+        int r = ss_refill(s, d); if(r) return r;
+      }
+      const uint8_t *rec = s->exp_buf[d] + s->exp_pos[d] * rb;
+      uint64_t k0, k1 = 0;
+      memcpy(&k0, rec, 8); if(W == 2) memcpy(&k1, rec + 8, 8);
+      if(!s->exp_sorted) { best = d; break; }
+      if(best == UINT32_MAX || k0 < b0 || (k0 == b0 && k1 < b1)) { best = d; b0 = k0; b1 = k1; }
+    }
+    if(best == UINT32_MAX) break;
+    if(!s->exp_sorted) { // concatenation: copy what is left of this shard's chunk at once
+      uint64_t m = s->exp_have[best] - s->exp_pos[best];
+      if(m > max_records - n) m = max_records - n;
+      memcpy(out + n * rb, s->exp_buf[best] + s->exp_pos[best] * rb, m * rb);
+      s->exp_pos[best] += m; n += m;
+      continue;
+    }
+    memcpy(out + n * rb, s->exp_buf[best] + s->exp_pos[best] * rb, rb);
+    s->exp_pos[best]++; n++;
+  }
+  *got = n;
+  return MCX_OK;
+}
+extern "C" int mcx_shardset_export_end(mcx_shardset *s)
+{
+  if(!s) return MCX_ERR_BAD_ARG;
+  for(uint32_t d = 0; d < s->P; d++) mcx_graph_export_end(s->g[d]);
+  s->exp_on = false;
+  return MCX_OK;
 }

@@ -5,13 +5,13 @@
 //   graph_write_kmer                          src/graph/graph_writer.c:116-127
 // The reference qsorts an array of pointers with an indirect compare and fwrites three
 // fields per k-mer.  Here: compact occupied slots -> LSD radix sort of (key word, slot
-// index) pairs (cub::DeviceRadixSort, the one library call on this path; it only touches
-// 2k key bits) -> one kernel that gathers key/covg/edges of each slot and writes the
-// packed 8W+5C byte records through shared memory so global stores stay coalesced.
+// index) pairs (mcx_radix.cu, in-tree; it only touches the 2k key bits) -> one kernel that
+// gathers key/covg/edges of each slot and writes the packed 8W+5C byte records through
+// shared memory so global stores stay coalesced.
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 #include <stdint.h>
 #include "mcx_build.h"
+#include "mcx_radix.cuh"
 
 #define CK(x) do { cudaError_t e_ = (x); if(e_ != cudaSuccess) { err = e_; goto fail; } } while(0)
 
@@ -124,13 +124,13 @@ __global__ void __launch_bounds__(MCX_EXP_THREADS) mcx_format_kernel(McxTable t,
   }
 }
 
+// one sort of the (key word, index) pairs by bits [0, end_bit): the in-tree radix sort (mcx_radix.cu); leaves the sorted
+// data in (*keys, *vals)
 static cudaError_t radix_pass(uint64_t **keys, uint64_t **vals, uint64_t **keys_alt, uint64_t **vals_alt, uint64_t n,
                               int end_bit, void **tmp, size_t *tmp_bytes, cudaStream_t st)
 {
-  cub::DoubleBuffer<uint64_t> dk(*keys, *keys_alt), dv(*vals, *vals_alt);
-  size_t need = 0;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, need, dk, dv, n, 0, end_bit, st);
-  if(e != cudaSuccess) return e;
+  const size_t need = mcx_radix_scratch_bytes(n);
+  cudaError_t e;
   if(need > *tmp_bytes) {
     if(*tmp) cudaFreeAsync(*tmp, st);
     *tmp = nullptr; *tmp_bytes = 0;
@@ -138,11 +138,11 @@ static cudaError_t radix_pass(uint64_t **keys, uint64_t **vals, uint64_t **keys_
     if(e != cudaSuccess) return e;
     *tmp_bytes = need;
   }
-  e = cub::DeviceRadixSort::SortPairs(*tmp, need, dk, dv, n, 0, end_bit, st);
+  uint64_t *ok, *ov;
+  e = mcx_radix_sort_pairs(*keys, *vals, *keys_alt, *vals_alt, n, end_bit, *tmp, &ok, &ov, st);
   if(e != cudaSuccess) return e;
-  // leave the sorted data in (*keys,*vals)
-  if(dk.Current() != *keys) { uint64_t *x = *keys; *keys = *keys_alt; *keys_alt = x; }
-  if(dv.Current() != *vals) { uint64_t *x = *vals; *vals = *vals_alt; *vals_alt = x; }
+  if(ok != *keys) { uint64_t *x = *keys; *keys = *keys_alt; *keys_alt = x; }
+  if(ov != *vals) { uint64_t *x = *vals; *vals = *vals_alt; *vals_alt = x; }
   return cudaSuccess;
 }
 

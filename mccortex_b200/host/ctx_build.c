@@ -54,6 +54,8 @@ static const char build_usage[] =
 "  -S, --sort               Output a graph file ordered by kmer\n"
 "  -D, --device <id[,id..]> CUDA device [default: 0]; several: one replica of the graph per device, every\n"
 "                           batch of reads goes to one of them, the replicas are merged before the dump\n"
+"      --shard              with several devices: ONE graph, hash-partitioned over the devices (each holds 1/N of\n"
+"                           the k-mers; k-mers travel to their owner over NVLink); plain --seq inputs only\n"
 "\n"
 "  Note: Argument must come before input file\n"
 "  --sample <name> is required before sequence input can be loaded.\n"
@@ -71,6 +73,7 @@ static struct option longopts[] = {
   {"cut-hp", required_argument, NULL, 'H'}, {"remove-pcr", no_argument, NULL, 'p'},
   {"keep-pcr", no_argument, NULL, 'P'},   {"graph", required_argument, NULL, 'g'},
   {"intersect", required_argument, NULL, 'I'}, {"device", required_argument, NULL, 'D'},
+  {"shard", no_argument, NULL, 1000},
   {NULL, 0, NULL, 0}};
 
 typedef struct {
@@ -90,6 +93,7 @@ static size_t mem_to_use = MCX_DEFAULT_MEM, num_kmers = MCX_DEFAULT_NKMERS;
 static int device = 0;
 #define MAX_DEVICES 16
 static int devices[MAX_DEVICES] = {0}, ndevices = 1;
+static bool shard_mode = false;    /* --shard: one graph partitioned over the devices (mcx_shardset_*) instead of replicas */
 static char *out_path = NULL;
 
 #define usage_err(...) mcx_print_usage(build_usage, __VA_ARGS__)
@@ -261,6 +265,7 @@ static void parse_args(int argc, char **argv)
         free(list);
         break;
       }
+      case 1000: shard_mode = true; break;
       case ':': case '?':
         mcx_die("`"CMD" build -h` for help. Bad option: %s", argv[optind - 1]);
       default: mcx_die("Bad option: %s", cmd);
@@ -340,6 +345,7 @@ static struct {
   uint32_t k, ncols, flags; uint64_t capacity; int device; bool host_batches;
   mcx_graph *g; int rc; const char *what;
   mcx_graph *gs[MAX_DEVICES]; /* gs[0] == g; more with -D a,b,..: replicas on the other devices */
+  mcx_shardset *ss;           /* --shard: the partitioned graph (then g is only a non-NULL token for the ingest) */
   unsigned next;              /* round robin over the replicas (under mcx_ingest.lock when files load concurrently) */
   int done; /* set (release) by the thread when rc / g are final; polled (acquire) by graph_ready */
 } ginit;
@@ -348,6 +354,11 @@ static void *graph_init_main(void *arg)
 {
   (void)arg;
   if(mcx_device_count() == 0) { ginit.rc = MCX_ERR_NO_DEVICE; ginit.what = "device"; }
+  else if(shard_mode) {
+    ginit.rc = mcx_shardset_create(ginit.k, ginit.ncols, ginit.capacity, devices, (uint32_t)ndevices, &ginit.ss);
+    ginit.what = "mcx_shardset_create";
+    ginit.g = (mcx_graph *)ginit.ss;
+  }
   else {
     for(int d = 0; d < ndevices && !ginit.rc; d++) {
       ginit.rc = mcx_graph_create(ginit.k, ginit.ncols, ginit.capacity, devices[d], ginit.flags, &ginit.gs[d]);
@@ -374,6 +385,9 @@ static int sync_replicas(mcx_graph *g, mcx_load_stats *st)
   }
   return rc;
 }
+/* --shard: the ingest's batches go to the shard set */
+static int submit_shard(mcx_graph *g, const mcx_read_batch *b) { (void)g; return mcx_shardset_add_reads(ginit.ss, b); }
+static int sync_shards(mcx_graph *g, mcx_load_stats *st) { (void)g; return mcx_shardset_sync(ginit.ss, st); }
 /* fold replica d into replica 0: its records (coverage adds saturating, edges OR -- mcx_graph_load_records) */
 static void merge_replica(int d, uint32_t ncols)
 {
@@ -409,7 +423,10 @@ static mcx_graph *graph_wait(void *ctx)
     if(ginit.rc == MCX_ERR_NO_DEVICE && !ginit.g && !strcmp(ginit.what, "device")) mcx_die("No CUDA device: "CMD" has no CPU fallback");
     if(ginit.rc) die_mcx(ginit.rc, ginit.what);
     char a[64]; mcx_ulong_to_str(ginit.capacity, a);
-    for(int d = 0; d < ndevices; d++) mcx_status("[hasht] Allocating device table with %s entries on GPU %i", a, devices[d]);
+    for(int d = 0; d < ndevices; d++) {
+      if(shard_mode) mcx_status("[hasht] Allocating shard %i of a device table with %s entries on GPU %i", d, a, devices[d]);
+      else mcx_status("[hasht] Allocating device table with %s entries on GPU %i", a, devices[d]);
+    }
     mcx_phase("cuda init + table (joined)");
   }
   pthread_mutex_unlock(&mu);
@@ -553,12 +570,19 @@ static int ctx_build(int argc, char **argv)
   /* CUDA start-up, the context and the table take 0.5-1.5 s: they run on a second thread while this one
    * starts parsing the first sequence file (seq_ingest.c keeps the parsed batches until the graph exists) */
   if(ndevices > 1 && remove_pcr_used) mcx_die("--remove-pcr needs the reads in order on one table: use one device");
+  if(shard_mode) {
+    if(ndevices < 2) mcx_die("--shard needs several devices: -D 0,1[,..]");
+    if(nifiles > 0 || ngfiles > 0) mcx_die("--shard builds from sequence only (no --graph / --intersect)");
+    for(t = 0; t < ntasks; t++)
+      if(tasks[t].prefs.fq_cutoff || tasks[t].prefs.hp_cutoff) mcx_die("--shard takes plain reads only (no --fq-cutoff / --cut-hp)");
+  }
   ginit.k = (uint32_t)kmer_size; ginit.ncols = (uint32_t)output_colours; ginit.capacity = kmers_in_hash; ginit.device = device;
   ginit.flags = (nifiles > 0 ? MCX_GRAPH_INTERSECT : 0) | (remove_pcr_used ? MCX_GRAPH_READSTRT : 0);
   ginit.host_batches = ntasks > 0;
   if(pthread_create(&ginit.thread, NULL, graph_init_main, NULL) != 0) mcx_die("Cannot start a thread");
   mcx_graph_source.wait = graph_wait; mcx_graph_source.ready = graph_ready; mcx_graph_source.ctx = NULL;
-  if(ndevices > 1) { mcx_ingest.route = route_replica; mcx_ingest.sync = sync_replicas; }
+  if(shard_mode) { mcx_ingest.submit = submit_shard; mcx_ingest.sync = sync_shards; }
+  else if(ndevices > 1) { mcx_ingest.route = route_replica; mcx_ingest.sync = sync_replicas; }
   mcx_graph *g = NULL;
   int r = 0;
   if(nifiles > 0 || ngfiles > 0 || remove_pcr_used) g = graph_wait(NULL); /* these need the device right away */
@@ -655,8 +679,8 @@ static int ctx_build(int argc, char **argv)
 
   g = graph_wait(NULL);
   /* several devices: the replicas' tables are folded into the first one (graph files went there alone) */
-  for(int d = 1; d < ndevices; d++) merge_replica(d, (uint32_t)output_colours);
-  if(ndevices > 1) { mcx_load_stats st; r = mcx_graph_sync(g, &st); if(r) die_mcx(r, "merging replicas"); mcx_phase("replicas merged"); }
+  for(int d = 1; d < ndevices && !shard_mode; d++) merge_replica(d, (uint32_t)output_colours);
+  if(ndevices > 1 && !shard_mode) { mcx_load_stats st; r = mcx_graph_sync(g, &st); if(r) die_mcx(r, "merging replicas"); mcx_phase("replicas merged"); }
   /* src/commands/ctx_build.c:409-413 */
   if(nifiles > 0) {
     r = mcx_graph_finish_intersect(g, NULL);
@@ -664,7 +688,7 @@ static int ctx_build(int argc, char **argv)
   }
 
   uint64_t nk = 0, cap = 0;
-  mcx_graph_stats(g, &nk, &cap);
+  if(shard_mode) mcx_shardset_stats(ginit.ss, &nk, &cap); else mcx_graph_stats(g, &nk, &cap);
   { char a[64], b[64]; mcx_ulong_to_str(nk, a); mcx_ulong_to_str(cap, b);
     mcx_status("[hasht] table occupancy: %s / %s (%.2f%%)", a, b, cap ? 100.0 * nk / cap : 0.0); }
   for(t = 0; t < ntasks; t++) { print_task_stats(&tasks[t]); mcx_seq_close(tasks[t].file); mcx_seq_close(tasks[t].file2); }
@@ -676,6 +700,36 @@ static int ctx_build(int argc, char **argv)
   mcx_write_ctx_header(fh, (uint32_t)kmer_size, (uint32_t)output_colours, ginfo);
 
   uint64_t nrec = 0; uint32_t rec_bytes = 0;
+  if(shard_mode) {
+    /* every shard dumps its records (sorted: ascending keys); the file is the merge of the P runs, made while writing
+     * (the reference iterates ONE table: HASH_ITERATE_SORTED, src/graph/hash_table.c:362-374) */
+    r = mcx_shardset_export_begin(ginit.ss, sort_kmers ? 1 : 0, &nrec, &rec_bytes);
+    if(r) die_mcx(r, "mcx_shardset_export_begin");
+    mcx_phase("export: compact + sort (per shard)");
+    const uint64_t chunk_recs = (64u << 20) / rec_bytes;
+    char *buf = malloc(chunk_recs * rec_bytes);
+    if(!buf) mcx_die("Out of memory");
+    uint64_t written = 0, got = 0;
+    do {
+      r = mcx_shardset_export_next(ginit.ss, buf, chunk_recs, &got);
+      if(r) die_mcx(r, "mcx_shardset_export_next");
+      if(got && fwrite(buf, rec_bytes, got, fh) != got) mcx_die("Cannot write to file");
+      written += got;
+    } while(got);
+    free(buf);
+    if(written != nrec) mcx_die("sharded dump: %llu of %llu records", (unsigned long long)written, (unsigned long long)nrec);
+    mcx_shardset_export_end(ginit.ss);
+    if(fh != stdout) fclose(fh); else fflush(fh);
+    mcx_phase("export: merge + write");
+    { char a[64]; mcx_ulong_to_str(nrec, a);
+      mcx_status("[graphwriter] Dumped %s kmers in %zu colour%s into: %s (format version: 6)", a, output_colours,
+                 output_colours == 1 ? "" : "s", strcmp(out_path, "-") ? out_path : "STDOUT"); }
+    for(i = 0; i < output_colours; i++) mcx_ginfo_free(&ginfo[i]);
+    free(ginfo); free(tasks); free(sample_names);
+    mcx_shardset_destroy(ginit.ss);
+    mcx_phase("destroy");
+    return EXIT_SUCCESS;
+  }
   r = mcx_graph_export_begin(g, sort_kmers ? 1 : 0, &nrec, &rec_bytes);
   if(r) die_mcx(r, "mcx_graph_export_begin");
   mcx_phase("export: compact + sort");

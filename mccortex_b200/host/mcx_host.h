@@ -129,6 +129,8 @@ typedef struct {
   /* several devices (build -D 0,1,...): every batch goes to the replica route() picks, sync() joins all of them */
   mcx_graph *(*route)(mcx_graph *g);
   int (*sync)(mcx_graph *g, mcx_load_stats *st);
+  /* sharded build (build -D 0,1,... --shard): batches go to the shard set instead of a graph */
+  int (*submit)(mcx_graph *g, const mcx_read_batch *b);
 } McxIngestShared;
 extern McxIngestShared mcx_ingest;
 int mcx_submit_reads(mcx_graph *g, const mcx_read_batch *b);

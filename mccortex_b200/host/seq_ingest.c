@@ -26,12 +26,12 @@ McxGraphSource mcx_graph_source = {NULL, NULL, NULL};
  * build_graph() call, src/basic/async_read_io.c): the library wants one host thread per graph at a time, so
  * every submission takes mcx_ingest.lock; the loaders do not sync (the counters are the graph's, not a file's) --
  * the caller syncs once after the last file and gets the totals of the whole call. */
-McxIngestShared mcx_ingest = {false, PTHREAD_MUTEX_INITIALIZER, 0, NULL, NULL};
+McxIngestShared mcx_ingest = {false, PTHREAD_MUTEX_INITIALIZER, 0, NULL, NULL, NULL};
 int mcx_submit_reads(mcx_graph *g, const mcx_read_batch *b)
 {
-  if(!mcx_ingest.concurrent) return mcx_graph_add_reads(mcx_ingest.route ? mcx_ingest.route(g) : g, b);
+  if(!mcx_ingest.concurrent) return mcx_ingest.submit ? mcx_ingest.submit(g, b) : mcx_graph_add_reads(mcx_ingest.route ? mcx_ingest.route(g) : g, b);
   pthread_mutex_lock(&mcx_ingest.lock);
-  int r = mcx_graph_add_reads(mcx_ingest.route ? mcx_ingest.route(g) : g, b);
+  int r = mcx_ingest.submit ? mcx_ingest.submit(g, b) : mcx_graph_add_reads(mcx_ingest.route ? mcx_ingest.route(g) : g, b);
   pthread_mutex_unlock(&mcx_ingest.lock);
   return r;
 }

@@ -206,3 +206,44 @@ int mcx_sort_records(int device, uint32_t k, uint32_t ncols, const void *in, uin
   qsort(out, n, sort_rb, cmp_rec);
   return MCX_OK;
 }
+
+/* the shard set: a sharded build gives the graph one table gives, so the stand-in is ONE oracle graph behind the same
+ * entry points (what the host driver's --shard mode needs on a box without GPUs: arguments, refusals, the dump loop) */
+struct mcx_shardset { mcx_graph *g; uint64_t at, n; uint32_t rb; };
+int mcx_shardset_create(uint32_t k, uint32_t ncols, uint64_t capacity, const int *devices, uint32_t ndevices, mcx_shardset **out)
+{
+  if(!out || !devices || ndevices < 2 || ndevices > 16) return MCX_ERR_BAD_ARG;
+  mcx_shardset *s = calloc(1, sizeof(*s));
+  if(!s) return MCX_ERR_NOMEM;
+  int r = mcx_graph_create(k, ncols, capacity + capacity / 10 + 1024 * ndevices, 0, 0, &s->g);
+  if(r) { free(s); return r; }
+  *out = s;
+  return MCX_OK;
+}
+int mcx_shardset_destroy(mcx_shardset *s) { if(s) { mcx_graph_destroy(s->g); free(s); } return MCX_OK; }
+int mcx_shardset_add_reads(mcx_shardset *s, const mcx_read_batch *b)
+{
+  if(!s || !b) return MCX_ERR_BAD_ARG;
+  if((b->fq_cutoff && b->qual) || b->hp_cutoff || b->must_exist) return MCX_ERR_UNSUPPORTED;
+  return mcx_graph_add_reads(s->g, b);
+}
+int mcx_shardset_sync(mcx_shardset *s, mcx_load_stats *st) { mcx_load_stats tmp; return s ? mcx_graph_sync(s->g, st ? st : &tmp) : MCX_ERR_BAD_ARG; }
+int mcx_shardset_stats(mcx_shardset *s, uint64_t *nkmers, uint64_t *capacity) { return s ? mcx_graph_stats(s->g, nkmers, capacity) : MCX_ERR_BAD_ARG; }
+int mcx_shardset_export_begin(mcx_shardset *s, int sorted, uint64_t *nrecords, uint32_t *record_bytes)
+{
+  if(!s) return MCX_ERR_BAD_ARG;
+  int r = mcx_graph_export_begin(s->g, sorted, &s->n, &s->rb);
+  s->at = 0;
+  if(nrecords) *nrecords = s->n;
+  if(record_bytes) *record_bytes = s->rb;
+  return r;
+}
+int mcx_shardset_export_next(mcx_shardset *s, void *dst, uint64_t max_records, uint64_t *got)
+{
+  if(!s || !got) return MCX_ERR_BAD_ARG;
+  uint64_t n = s->n - s->at < max_records ? s->n - s->at : max_records;
+  int r = n ? mcx_graph_export_read(s->g, s->at, n, dst) : MCX_OK;
+  s->at += n; *got = n;
+  return r;
+}
+int mcx_shardset_export_end(mcx_shardset *s) { return s ? mcx_graph_export_end(s->g) : MCX_ERR_BAD_ARG; }

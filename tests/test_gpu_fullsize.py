@@ -239,3 +239,64 @@ def test_config4_four_colours(M, synth):
     assert one["nrec"] == int(four["present"][c]) == st.num_kmers_novel
     assert one["col_ck"][0] == four["col_ck"][c]
     g1.close()
+
+
+# ---- byte parity with the reference at the stated sizes (`cmp` on configs 1-4) -------------------------
+# tests/golden/fullsize_md5.json holds md5 / size of `oracle/_ref/mccortex31|63 build -S` outputs on the stated inputs,
+# made ONCE on a GPU box by scripts/gpu_fullsize_golden.sh (which also `cmp`s them with this driver's files there; the
+# reference needs 3-7 minutes of 16 cores per config).  Here the driver's `build -S` output must have the same md5.
+def _golden_fullsize():
+    import json
+    p = os.path.join(ROOT, "tests", "golden", "fullsize_md5.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+@pytest.mark.parametrize("name", ["config1a_1Mbase_record_80col", "config1b_6536_reads", "config2_50M_reads_k31",
+                                  "config3_50M_reads_k63", "config4_4x25M_reads_4_colours"])
+def test_cli_output_md5_equals_reference_at_full_size(name, tmp_path):
+    import hashlib
+    import shutil
+    import subprocess
+    gold = _golden_fullsize().get(name)
+    if not gold or gold.get("cmp") != "identical":
+        pytest.skip("no reference md5 recorded for %s" % name)
+    import mccortex_b200 as M
+    synth_bin = os.path.join(ROOT, "mccortex_b200", "bin", "mcx-synth")
+    need = {"config2_50M_reads_k31": 10e9, "config3_50M_reads_k63": 14e9, "config4_4x25M_reads_4_colours": 20e9}.get(name, 1e8)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need * 1.2 else str(tmp_path)
+    d = os.path.join(base, "mcx_full_%d" % os.getpid())
+    os.makedirs(d, exist_ok=True)
+    try:
+        def synth(path, G, first, n):
+            with open(path, "wb") as f:
+                subprocess.run([synth_bin, str(G), str(first), str(n), "150", "0.001", "1"], stdout=f, check=True)
+        if name.startswith("config1a"):
+            SL = C.CDLL(os.path.join(ROOT, "mccortex_b200", "lib", "libmcxsynth.so"))
+            SL.mcx_synth_genome.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+            g = C.create_string_buffer(1000000); SL.mcx_synth_genome(g, 1000000, 0x1A)
+            s = "".join("ACGT"[b] for b in g.raw[:1000000])
+            open(os.path.join(d, "c1a.fa"), "w").write(">one\n" + "\n".join(s[i:i + 80] for i in range(0, len(s), 80)) + "\n")
+            inputs = ["--sample", "s", "--seq", os.path.join(d, "c1a.fa")]
+        elif name.startswith("config1b"):
+            synth(os.path.join(d, "c1b.fa"), 100000, 0, 6536)
+            inputs = ["--sample", "s", "--seq", os.path.join(d, "c1b.fa")]
+        elif name.startswith("config4"):
+            inputs = []
+            for c in range(4):
+                synth(os.path.join(d, "s%d.fa" % c), GENOME, c * 25_000_000, 25_000_000)
+                inputs += ["--sample", "s%d" % c, "--seq", os.path.join(d, "s%d.fa" % c)]
+        else:
+            synth(os.path.join(d, "r.fa"), GENOME, 0, 50_000_000)
+            inputs = ["--sample", "s", "--seq", os.path.join(d, "r.fa")]
+        out = os.path.join(d, "out.ctx")
+        r = subprocess.run([M.driver_path(), "build", "-f", "-q", "-m", "100G", "-n", str(gold["nslots"]), "-k", str(gold["k"]), "-S"] + inputs + [out],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert os.path.getsize(out) == gold["bytes"]
+        h = hashlib.md5()
+        with open(out, "rb") as f:
+            for blk in iter(lambda: f.read(1 << 24), b""):
+                h.update(blk)
+        assert h.hexdigest() == gold["md5"], "the .ctx differs from the reference's (%s)" % gold["args"]
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

@@ -136,3 +136,45 @@ def test_cli_join_matches_golden_ctx(case, tmp_path):
     ref = open(os.path.join(GOLD, c["ctx"]), "rb").read()
     assert hashlib.md5(ref).hexdigest() == c["md5"]
     assert open(out, "rb").read() == ref
+
+
+def _devices_for_shard():
+    """two device ids for `-D a,b --shard`: the CPU stand-in takes any; the real driver needs two GPUs"""
+    if "hostcheck" in os.path.basename(G._driver()):
+        return "0,1"
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("--shard needs two GPUs")
+    return "0,1"
+
+
+@pytest.mark.parametrize("k", [31, 63])
+def test_cli_shard_mode(tmp_path, oracle, k):
+    """`build -D 0,1 --shard`: ONE graph hash-partitioned over the devices (mcx_shardset_*), dump = merge of the shards'
+    sorted runs: the bytes of the single-device build (and of the reference binary); several colours, several files, a batch
+    size that cuts the input into many pieces; refusals"""
+    devs = _devices_for_shard()
+    rng = random.Random(300 + k)
+    fas = []
+    for i in range(3):
+        fa = tmp_path / ("s%d.fa" % i)
+        fa.write_text("".join(">r\n%s\n" % r for r in rand_reads(rng, 2500, (60, 200), 40000, perr=0.004) + EDGE_READS))
+        fas.append(str(fa))
+    args = ["-q", "-f", "-m", "1G", "-n", "4M", "-k", str(k), "-S", "-s", "a", "-1", fas[0], "-1", fas[1], "-s", "b", "-1", fas[2]]
+    one, two = str(tmp_path / "one.ctx"), str(tmp_path / "two.ctx")
+    _run(args + [one])
+    _run(args[:2] + ["-D", devs, "--shard"] + args[2:] + [two], env={"MCX_BATCH_BYTES": "200000"})
+    assert open(one, "rb").read() == open(two, "rb").read()
+    if oracle.ref_binary(k):
+        ref = str(tmp_path / "ref.ctx")
+        oracle.ref_run(k, ["build", "-q", "-f", "-m", "1G", "-n", "4M", "-k", str(k), "-S", "-s", "a", "-1", fas[0], "-1", fas[1], "-s", "b", "-1", fas[2], ref])
+        assert open(ref, "rb").read() == open(two, "rb").read()
+    # unsorted dump: the same records in shard order; `sort` brings it to the same file
+    uns = str(tmp_path / "uns.ctx")
+    _run(["-q", "-f", "-D", devs, "--shard", "-m", "1G", "-n", "4M", "-k", str(k), "-s", "a", "-1", fas[0], "-1", fas[1], "-s", "b", "-1", fas[2], uns])
+    _run_cmd("sort", ["-q", uns])
+    assert open(uns, "rb").read() == open(one, "rb").read()
+    # refusals: one device, quality cut-off, graph files
+    assert _run(["-q", "-f", "--shard", "-m", "1G", "-n", "1M", "-k", str(k), "-s", "a", "-1", fas[0], two], check=False).returncode == 1
+    assert _run(["-q", "-f", "-D", devs, "--shard", "-m", "1G", "-n", "1M", "-k", str(k), "-s", "a", "-Q", "10", "-1", fas[0], two], check=False).returncode == 1
+    assert _run(["-q", "-f", "-D", devs, "--shard", "-m", "1G", "-n", "1M", "-k", str(k), "-s", "a", "-1", fas[0], "-g", one, two], check=False).returncode == 1
