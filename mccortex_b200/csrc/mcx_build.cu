@@ -64,6 +64,10 @@ template <int W> struct McxSlowQueue {
   uint64_t key[MCX_QCAP(W) * W];
   uint8_t emask[MCX_QCAP(W)];
   uint32_t n;
+  // front-table bypass (k <= 31): queue length at the last chunk barrier, chunks done, and the decision -- on data the
+  // front table cannot absorb (a genome much larger than its 8.4 M ways: every k-mer is seen about once per batch) the
+  // tag probe, the claim attempt and the re-probe in the parked pass are pure overhead
+  uint32_t last_n, epoch, bypass;
   // sharded builds: the drain reserves bin space once per CTA and destination (see FusedSink::drain)
   uint8_t dest[MCX_QCAP(W)];
   uint32_t dcnt[MCX_MAX_PARTS], dfill[MCX_MAX_PARTS];
@@ -151,6 +155,8 @@ template <int W, int G, bool SHARDED> struct FusedSink { // G = probe loads kept
   uint32_t colour; bool may_saturate;
   McxSlowQueue<W> *q;
   unsigned long long *counters;
+  bool byp; // this chunk skips the front table (read once per chunk: begin_chunk)
+  __device__ __forceinline__ void begin_chunk() { byp = W == 1 && t.front_set_bits && *(volatile uint32_t *)&q->bypass; }
 
   __device__ __forceinline__ void park(const McxKmer<W> &key, uint32_t emask)
   {
@@ -163,7 +169,12 @@ template <int W, int G, bool SHARDED> struct FusedSink { // G = probe loads kept
                                           uint32_t &novel, uint32_t &full)
   {
     (void)novel; (void)full;
-    if(W == 1 && t.front_set_bits) {
+    if(W == 1 && byp) {
+      // the front table is not absorbing this data: straight to the parked pass, marked so that it skips the front table too
+#pragma unroll
+      for(uint32_t j = 0; j < MCX_HALF; j++)
+        if((valid >> j) & 1u) { McxKmer<W> kk = keys[j]; kk.b[0] |= MCX_KEY_FLAG; park(kk, emasks[j]); }
+    } else if(W == 1 && t.front_set_bits) {
       // hot pass: G probe loads in flight per thread, one 32-bit RED per hit; no Lookup3, no
       // big-table access for k-mers that live in the L2-resident front table
       const McxFrontGeom g = mcx_front_geom(t);
@@ -190,15 +201,30 @@ template <int W, int G, bool SHARDED> struct FusedSink { // G = probe loads kept
         if((valid >> j) & 1u) park(keys[j], emasks[j]);
     }
   }
-  __device__ __forceinline__ void reset() { if(threadIdx.x == 0) q->n = 0; }
+  __device__ __forceinline__ void reset() { if(threadIdx.x == 0) { q->n = 0; q->last_n = 0; } }
   // the next chunk may not fit (evaluated per thread just before the step barrier, OR-reduced there)
   __device__ __forceinline__ bool should_drain() const { return q->n > MCX_QCAP(W) - MCX_T; }
+  // Thread 0, after the chunk barrier: keep probing the front table, or bypass it for the next chunks?  The signal costs
+  // the hot pass nothing: how much the queue grew during the chunk.  Probed, the bench workload parks 8.5 % of a chunk's
+  // windows; data the front table cannot absorb parks all of them (~0.8 T on 150 bp reads).  Above 0.6 T the next fifteen
+  // chunks skip the probe, the sixteenth probes again.  (Other threads may act on the old decision for the first groups of
+  // the next chunk: every parked item carries its own mark, so that is harmless.)
+  __device__ __forceinline__ void decide()
+  {
+    if(W != 1 || !t.front_set_bits) return;
+    const uint32_t n = q->n, parks = n - q->last_n, e = ++q->epoch;
+    q->last_n = n;
+    if(q->bypass) { if((e & 15u) == 0u) q->bypass = 0; }
+    else q->bypass = (parks * 5u > MCX_T * 3u) ? 1u : 0u;
+  }
   // one parked occurrence: front table (claim / edge bit), else the big table.  Returns the shard that owns the key if
   // the occurrence has to travel there as a tuple (sharded builds), else MCX_NO_DEST (it has been dealt with).
 #define MCX_NO_DEST 0xFFu
   __device__ __forceinline__ uint32_t slow(McxKmer<W> key, uint32_t emask, uint32_t &novel, uint32_t &full)
   {
-    if(W == 1 && t.front_set_bits && mcx_front_add_slow(t, key.b[0], emask)) return MCX_NO_DEST; // absorbed by the front table
+    bool try_front = W == 1 && t.front_set_bits;
+    if(W == 1 && (key.b[0] & MCX_KEY_FLAG)) { key.b[0] &= ~MCX_KEY_FLAG; try_front = false; } // parked while the front table was bypassed
+    if(try_front && mcx_front_add_slow(t, key.b[0], emask)) return MCX_NO_DEST; // absorbed by the front table
     uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
     if(SHARDED) {
       const uint32_t d = mcx_owner(hc, bins.nparts);
@@ -249,7 +275,7 @@ template <int W, int G, bool SHARDED> struct FusedSink { // G = probe loads kept
         if(at >= bins.cap) { full = 1; continue; }
         uint64_t *kd = bins.keys[d] + at * W;
 #pragma unroll
-        for(int w = 0; w < W; w++) kd[w] = q->key[i * W + w];
+        for(int w = 0; w < W; w++) kd[w] = (W == 1) ? (q->key[i * W + w] & ~MCX_KEY_FLAG) : q->key[i * W + w];
         bins.meta[d][at] = (1u << 8) | q->emask[i];
       }
     }
@@ -275,6 +301,8 @@ template <int W> struct TupleSink {
   __device__ __forceinline__ void drain(uint32_t &, uint32_t &) {}
   __device__ __forceinline__ void reset() {}
   __device__ __forceinline__ bool should_drain() const { return false; }
+  __device__ __forceinline__ void decide() {}
+  __device__ __forceinline__ void begin_chunk() {}
 };
 
 // ---------------------------------------------------------------- front end
@@ -376,6 +404,7 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
       const uint32_t lo = p.r_begin > g0 ? (p.r_begin - g0 < MCX_WPT ? (uint32_t)(p.r_begin - g0) : MCX_WPT) : 0u;
       const uint32_t hi = p.r_end > g0 ? (p.r_end - g0 < MCX_WPT ? (uint32_t)(p.r_end - g0) : MCX_WPT) : 0u;
       const uint32_t own = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+      sink.begin_chunk();
       mcx_thread_occurrences<W>(sm.pk[j % 3u], sm.vmask[j & 1u], tid, p.k,
         [&](const McxKmer<W> *keys, const uint32_t *emasks, uint32_t valid, uint32_t starts, uint32_t j0) {
           valid &= own >> j0;
@@ -397,6 +426,7 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
     if(tid == 0) {
       const uint64_t ch4 = chunk0 + (uint64_t)(s + 4) * cstride;
       if(ch4 < c_last) issue_chunk_load<QUAL>(sm, p, ch4, (uint32_t)(s + 4) & 1u);
+      sink.decide();
     }
 
     if(QUAL && s >= -1 && ch1 < c_last) {
@@ -469,11 +499,11 @@ __global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(W == 1 ? MCX_FUSED_MINB 
 mcx_build_fused_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTable t, const __grid_constant__ McxTupleBins nobins)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
-  if(threadIdx.x == 0) q->n = 0;
+  if(threadIdx.x == 0) { q->n = 0; q->last_n = q->epoch = q->bypass = 0; }
 #ifndef MCX_FUSED_G
 #define MCX_FUSED_G 2
 #endif
-  FusedSink<W, W == 1 ? MCX_FUSED_G : 1, false> sink{t, nobins, p.colour, p.may_saturate != 0, q, p.counters};
+  FusedSink<W, W == 1 ? MCX_FUSED_G : 1, false> sink{t, nobins, p.colour, p.may_saturate != 0, q, p.counters, false};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
 
@@ -485,8 +515,8 @@ __global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(3))
 mcx_build_sharded_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTable t, const __grid_constant__ McxTupleBins b)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
-  if(threadIdx.x == 0) q->n = 0;
-  FusedSink<W, 2, true> sink{t, b, p.colour, p.may_saturate != 0, q, p.counters};
+  if(threadIdx.x == 0) { q->n = 0; q->last_n = q->epoch = q->bypass = 0; }
+  FusedSink<W, 2, true> sink{t, b, p.colour, p.may_saturate != 0, q, p.counters, false};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
 
@@ -496,6 +526,8 @@ struct NullSink {
   __device__ __forceinline__ void drain(uint32_t &, uint32_t &) {}
   __device__ __forceinline__ void reset() {}
   __device__ __forceinline__ bool should_drain() const { return false; }
+  __device__ __forceinline__ void decide() {}
+  __device__ __forceinline__ void begin_chunk() {}
 };
 __global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_contig_summary_kernel(const __grid_constant__ McxBuildParams p)
 {
@@ -507,8 +539,8 @@ __global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4))
 mcx_build_fused_qual_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTable t, const __grid_constant__ McxTupleBins nobins)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
-  if(threadIdx.x == 0) q->n = 0;
-  FusedSink<W, 2, false> sink{t, nobins, p.colour, p.may_saturate != 0, q, p.counters};
+  if(threadIdx.x == 0) { q->n = 0; q->last_n = q->epoch = q->bypass = 0; }
+  FusedSink<W, 2, false> sink{t, nobins, p.colour, p.may_saturate != 0, q, p.counters, false};
   mcx_front_end<W, MCX_MODE_QUAL>(p, sink);
 }
 

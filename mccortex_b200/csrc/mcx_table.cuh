@@ -146,18 +146,25 @@ __device__ __forceinline__ int mcx_table_add<1>(const McxTable &t, const McxKmer
       if(k0 == keyf) { hit = s; meta = m0; }
       else if(k1 == keyf) { hit = s + 4; meta = m1; }
       else if(k0 == 0 || k1 == 0) {
-        // first empty slot of the sector (slot 0 before slot 1 keeps the probe order total)
+        // first empty slot of the sector (slot 0 before slot 1 keeps the probe order total).  A novel k-mer takes the
+        // WHOLE 16-byte slot with one 128-bit compare-and-swap -- key, coverage and edges at once -- instead of a 64-bit
+        // CAS on the key followed by a RED on the coverage and a RED on the edges: one L2 atomic instead of three for what
+        // is most of the work on cold data (error k-mers; all of configs[4]).  An empty slot is all zero: nothing ever
+        // writes coverage or edges before the key.
+        const uint64_t val = (uint64_t)n | ((uint64_t)emask << 32);
         uint32_t *cand = (k0 == 0) ? s : s + 4;
-        uint64_t old = atomicCAS((unsigned long long *)cand, 0ull, (unsigned long long)keyf);
-        if(old == 0) { hit = cand; novel = 1; }
-        else if(old == keyf) { hit = cand; }
+        uint64_t olo, ohi;
+        mcx_cas128(cand, 0ull, 0ull, keyf, val, olo, ohi);
+        if(olo == 0) return 1;
+        if(olo == keyf) { hit = cand; meta = ohi; }
         else if(cand == s) {
           // lost slot 0 to another key: slot 1 of the same sector is next in probe order
-          uint64_t o1 = (k1 == 0) ? atomicCAS((unsigned long long *)(s + 4), 0ull, (unsigned long long)keyf) : k1;
-          if(o1 == 0) { hit = s + 4; novel = 1; }
-          else if(o1 == keyf) { hit = s + 4; }
+          if(k1 == 0) {
+            mcx_cas128(s + 4, 0ull, 0ull, keyf, val, olo, ohi);
+            if(olo == 0) return 1;
+            if(olo == keyf) { hit = s + 4; meta = ohi; }
+          }
         }
-        meta = 0; // freshly claimed or raced: treat edges as unknown-empty => OR is issued
       }
       if(hit) {
         mcx_covg_add(hit + 2, n, may_saturate, true, (uint32_t)meta);

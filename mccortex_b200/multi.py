@@ -455,6 +455,36 @@ def routed_parity_check(M, dist, rank, world, dev, stream, k, reads_per_rank, fi
     return out
 
 
+def bind_to_gpu_numa_node(local):
+    """run this rank on the cores of the NUMA node its GPU hangs off, so that the pinned read buffer it is about to
+    allocate and fill (first touch) is local to the GPU's PCIe root: eight ranks copying 7.5 GB each from one host share
+    the inter-socket links otherwise.  Returns the node number or None (information missing: nothing changed)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        if hasattr(pr, "pci_bus_id") and hasattr(pr, "pci_device_id"):
+            bus = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        else:
+            import subprocess
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                                 stdout=subprocess.PIPE, text=True, timeout=10).stdout.strip()
+            bus = out[-12:] if out else None     # 0000:19:00.0
+        if not bus:
+            return None
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus.lower()).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def bench_multi(args, rank, world, local, dist):
     """bench.py body for N > 1 (weak scaling: args.reads reads per GPU, disjoint read index ranges
     of the same genome)."""
@@ -463,6 +493,7 @@ def bench_multi(args, rank, world, local, dist):
     import bench as B
 
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     SL = B.synth_lib()
     R, stride = args.reads, B.READ_LEN + 1
     genome = C.create_string_buffer(B.GENOME)
@@ -546,8 +577,22 @@ def bench_multi(args, rank, world, local, dist):
             n = n_next
         if aggregate:
             sb.flush()
-        return sb.g.sync()
+        st_ = sb.g.sync()
+        # the job's result: this shard's records, sorted, in host memory (the sorted runs the P-way merge writes out)
+        nrec, rb = C.c_uint64(), C.c_uint32()
+        M.binding._ck(M.lib().mcx_graph_export_begin(sb.g.h, 1, C.byref(nrec), C.byref(rb)), "export_begin")
+        nb_out = int(nrec.value) * int(rb.value)
+        if nb_out > hout_bytes[0]:
+            if hout[0]:
+                M.host_free(hout[0])
+            hout_bytes[0] = nb_out + nb_out // 8 + 4096
+            hout[0] = M.host_alloc(hout_bytes[0])
+        M.binding._ck(M.lib().mcx_graph_export_read(sb.g.h, 0, nrec.value, C.c_void_p(hout[0])), "export_read")
+        M.lib().mcx_graph_export_end(sb.g.h)
+        d2h[0] = nb_out
+        return st_
 
+    hout, hout_bytes, d2h = [0], [0], [0]
     for _ in range(args.warmup):
         step()
     st = sb.g.sync()
@@ -566,6 +611,7 @@ def bench_multi(args, rank, world, local, dist):
     ev1.record(stream)
     torch.cuda.synchronize()
     dist.barrier()
+    sent_timed = int(sb.sent_total) if routed else 0   # (before the optional profiling step adds its own)
     if routed and os.environ.get("MCX_MULTI_PROFILE"):
         import sys
         sb.prof = []
@@ -578,7 +624,7 @@ def bench_multi(args, rank, world, local, dist):
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     st = sb.g.sync()
-    tot = torch.tensor([st.num_kmers_loaded, st.num_kmers_novel, sb.launches, int(sb.sent_total) if routed else 0], dtype=torch.int64, device=dev)
+    tot = torch.tensor([st.num_kmers_loaded, st.num_kmers_novel, sb.launches, sent_timed], dtype=torch.int64, device=dev)
     dist.all_reduce(tot)
     # hardware parity of the routed build on a bounded sample of the same workload (1M reads per rank), every run
     parity = None
@@ -607,6 +653,8 @@ def bench_multi(args, rank, world, local, dist):
     dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
     e_tot = torch.tensor([st_h.num_kmers_loaded], dtype=torch.int64, device=dev)
     dist.all_reduce(e_tot)
+    d2h_tot = torch.tensor([d2h[0]], dtype=torch.int64, device=dev)
+    dist.all_reduce(d2h_tot)
     assert int(e_tot[0]) == occ_per_rank * world
     e2e_val = occ_per_rank * world * e_steps / (float(e_ms[0]) * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
@@ -632,11 +680,12 @@ def bench_multi(args, rank, world, local, dist):
                          "tuples_per_step": tuples_per_step, "nvlink_bytes_per_step": tuples_per_step * 12 * (world - 1) / world},
             "cpu_baseline": None,
             "e2e": {"value": e2e_val, "unit": "k-mers/s", "h2d_bytes_per_step": nbytes * world,
-                    "d2h_bytes_per_step": (64 + 72) * world, "steps": e_steps, "ms_per_step": float(e_ms[0]) / e_steps},
+                    "d2h_bytes_per_step": int(d2h_tot[0]) + (64 + 72) * world, "steps": e_steps, "ms_per_step": float(e_ms[0]) / e_steps,
+                    "what": "per rank: pinned host reads -> H2D -> sharded build -> this shard's sorted records back in host memory"},
             "gpu_launches": int(tot[2]),
             "clocks": clocks,
             "parity": parity,
-            "extra": {"distinct_kmers_total": int(tot[1]), "shard_slots": cap_shard, "batches_per_step": nb,
+            "extra": {"distinct_kmers_total": int(tot[1]), "shard_slots": cap_shard, "batches_per_step": nb, "numa_node_rank0": numa,
                       "exchange": ("fused into the kernel: peer stores over NVLink (CUDA IPC rings), counters all_to_all"
                                    if routed else "NCCL send/recv of local bins") +
                                   (", front-table aggregated" if aggregate else ", every occurrence (baseline)")},
