@@ -342,8 +342,8 @@ class Graph:
             "mcx_kmer_tuples")
 
     def add_reads_sharded(self, seq_dev_addr, nbytes, nparts, my_part, cap_per_part, keys_addr, meta_addr, counts_addr,
-                          hp_cutoff=0, colour=0):
-        b = self._batch(seq_dev_addr, nbytes, MCX_LAYOUT_LINES, MCX_MEM_DEVICE, colour, hp_cutoff)
+                          hp_cutoff=0, colour=0, qual_dev_addr=None, fq_cutoff=0):
+        b = self._batch(seq_dev_addr, nbytes, MCX_LAYOUT_LINES, MCX_MEM_DEVICE, colour, hp_cutoff, qual_addr=qual_dev_addr, fq_cutoff=fq_cutoff)
         _ck(lib().mcx_graph_add_reads_sharded(self.h, C.byref(b), nparts, my_part, cap_per_part, keys_addr, meta_addr,
                                               counts_addr), "mcx_graph_add_reads_sharded")
 

@@ -717,7 +717,12 @@ static int add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t npa
   if(!g || !b || nparts < 2 || my_part >= nparts || !cap_per_part || !counts_out) return MCX_ERR_BAD_ARG;
   if(!(keys_out && meta_out) && !(keys_dst && meta_dst)) return MCX_ERR_BAD_ARG;
   if(b->layout != MCX_LAYOUT_LINES || b->mem != MCX_MEM_DEVICE || ((uintptr_t)b->seq & 15u)) return MCX_ERR_BAD_ARG;
-  if(b->hp_cutoff == 1 || b->hp_cutoff > g->k || (b->fq_cutoff && b->qual) || b->must_exist) return MCX_ERR_UNSUPPORTED;
+  if(b->hp_cutoff == 1 || b->hp_cutoff > g->k || b->must_exist) return MCX_ERR_UNSUPPORTED;
+  const bool useq = b->fq_cutoff && b->qual;
+  if(useq && (b->fq_cutoff >= 127 || ((uintptr_t)b->qual & 15u))) return MCX_ERR_BAD_ARG;
+  if(useq && (r_begin != 0 || (r_end != 0 && r_end != b->nbytes))) {
+    snprintf(g_err, sizeof(g_err), "a quality cut-off launch must cover whole reads"); return MCX_ERR_BAD_ARG;
+  }
   if(b->colour >= g->ncols) return MCX_ERR_BAD_ARG;
   CU(cudaSetDevice(g->device));
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
@@ -732,6 +737,11 @@ static int add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t npa
   CU(cudaMemsetAsync(counts_out, 0, nparts * sizeof(uint64_t), st));
   g->occ_bound += r_end - r_begin;
   McxBuildParams p = make_params(g, b, (const uint8_t *)b->seq, b->nbytes, r_begin, r_end);
+  if(useq) { // the carry summaries of the quality pass (one byte per chunk) live in the rotating scratch
+    int r = tmp_rotate(g); if(r) return r;
+    r = ensure_tmp(g, b->nbytes / MCX_T + 260); if(r) return r;
+    p.qual = (const uint8_t *)b->qual; p.qcut = b->fq_cutoff; p.summary = g->d_tmp;
+  }
 #ifdef MCX_EXPERIMENTS
   if(g->warp_kernel && mcx_warp_kernel_supports(p)) {
     for(uint32_t c = 0; c < (1u << g->ncls_log2); c++) {
@@ -742,6 +752,7 @@ static int add_reads_sharded(mcx_graph *g, const mcx_read_batch *b, uint32_t npa
   } else
 #endif
   CU(mcx_launch_build_sharded(p, g->table, bins, st));
+  if(useq) { int r = tmp_release(g, st); if(r) return r; }
   g->pend_positions += r_end - r_begin;
   g->sharded = true;
   return MCX_OK;
@@ -979,6 +990,7 @@ struct mcx_shardset {
   uint64_t *counts[MCX_MAX_PARTS];               // on the SENDER: tuples it produced for each owner
   cudaStream_t copy[MCX_MAX_PARTS];
   uint8_t *d_stage[MCX_MAX_PARTS][MCX_SS_NSLOT], *h_stage[MCX_MAX_PARTS][MCX_SS_NSLOT];
+  uint8_t *d_qstage[MCX_MAX_PARTS][MCX_SS_NSLOT], *h_qstage[MCX_MAX_PARTS][MCX_SS_NSLOT];   // quality bytes (allocated on first use)
   cudaEvent_t staged[MCX_MAX_PARTS][MCX_SS_NSLOT], stage_free[MCX_MAX_PARTS][MCX_SS_NSLOT];
   int slot[MCX_MAX_PARTS];
   cudaEvent_t produced[MCX_MAX_PARTS], inserted[MCX_MAX_PARTS][MCX_MAX_PARTS];
@@ -1049,6 +1061,8 @@ extern "C" int mcx_shardset_destroy(mcx_shardset *s)
     for(int i = 0; i < MCX_SS_NSLOT; i++) {
       if(s->d_stage[d][i]) cudaFree(s->d_stage[d][i]);
       if(s->h_stage[d][i]) cudaFreeHost(s->h_stage[d][i]);
+      if(s->d_qstage[d][i]) cudaFree(s->d_qstage[d][i]);
+      if(s->h_qstage[d][i]) cudaFreeHost(s->h_qstage[d][i]);
       if(s->staged[d][i]) cudaEventDestroy(s->staged[d][i]);
       if(s->stage_free[d][i]) cudaEventDestroy(s->stage_free[d][i]);
     }
@@ -1121,21 +1135,31 @@ extern "C" int mcx_shardset_add_reads(mcx_shardset *s, const mcx_read_batch *b)
 {
   if(!s || !b || b->colour >= s->ncols) return MCX_ERR_BAD_ARG;
   if(b->layout != MCX_LAYOUT_LINES || b->mem != MCX_MEM_HOST || (b->nbytes && !b->seq)) return MCX_ERR_BAD_ARG;
-  if((b->fq_cutoff && b->qual) || b->hp_cutoff || b->must_exist) {
-    snprintf(g_err, sizeof(g_err), "sharded builds take plain reads only (no quality / homopolymer cut-off, no --intersect)"); return MCX_ERR_UNSUPPORTED;
-  }
+  if(b->must_exist) { snprintf(g_err, sizeof(g_err), "sharded builds cannot intersect (must_exist)"); return MCX_ERR_UNSUPPORTED; }
+  if(b->hp_cutoff == 1 || b->hp_cutoff > s->k) { snprintf(g_err, sizeof(g_err), "hp_cutoff must be 0 or in [2, k]"); return MCX_ERR_UNSUPPORTED; }
+  if(b->fq_cutoff >= 127) { snprintf(g_err, sizeof(g_err), "fq_cutoff (incl. offset) must be < 127"); return MCX_ERR_UNSUPPORTED; }
   if(b->nbytes == 0) return MCX_OK;
   if(s->exp_on) return MCX_ERR_BAD_ARG;
   if(s->dirty && b->colour != s->colour) { int r = ss_flush(s); if(r) return r; }   // the front tables count one colour at a time
   s->colour = b->colour;
-  const uint8_t *hseq = (const uint8_t *)b->seq;
+  const bool useq = b->fq_cutoff && b->qual;
+  const uint8_t *hseq = (const uint8_t *)b->seq, *hqual = (const uint8_t *)b->qual;
   const uint64_t nbytes = b->nbytes;
   cudaPointerAttributes attr;
   const bool pinned = (cudaPointerGetAttributes(&attr, hseq) == cudaSuccess) && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
-  for(uint64_t pos = 0; pos < nbytes; pos += MCX_STAGE_POS) {
-    const uint64_t pend = pos + MCX_STAGE_POS < nbytes ? pos + MCX_STAGE_POS : nbytes;
-    const uint64_t b0 = pos ? pos - MCX_LB : 0, b1 = pend + MCX_TAIL < nbytes ? pend + MCX_TAIL : nbytes;
+  for(uint64_t pos = 0; pos < nbytes;) {
+    uint64_t pend = pos + MCX_STAGE_POS < nbytes ? pos + MCX_STAGE_POS : nbytes;
+    uint64_t b0 = pos ? pos - MCX_LB : 0, b1 = pend + MCX_TAIL < nbytes ? pend + MCX_TAIL : nbytes;
+    if(useq) {
+      // contig membership under a quality cut-off carries across chunks: a launch covers whole reads (cut after a terminator)
+      if(pend < nbytes) {
+        const void *nl = memrchr(hseq + pos, '\n', pend - pos);
+        if(!nl) { snprintf(g_err, sizeof(g_err), "a read longer than %llu bases cannot be quality-filtered in a sharded build", (unsigned long long)MCX_STAGE_POS); return MCX_ERR_UNSUPPORTED; }
+        pend = (uint64_t)((const uint8_t *)nl - hseq) + 1u;
+      }
+      b0 = pos; b1 = pend;   // (pos is 16-byte aligned in the source only by chance: the staging copy realigns it)
+    }
     // every device's front table counts in 32 bits: flush them all before any could wrap
     for(uint32_t d = 0; d < s->P; d++) if(s->pending[d] + MCX_STAGE_POS >= 0xE0000000ull) { int r = ss_flush(s); if(r) return r; break; }
     const uint32_t d = s->next++ % s->P;
@@ -1146,18 +1170,26 @@ extern "C" int mcx_shardset_add_reads(mcx_shardset *s, const mcx_read_batch *b)
     const uint8_t *src = hseq + b0;
     if(!pinned) { memcpy(s->h_stage[d][sl], src, b1 - b0); src = s->h_stage[d][sl]; }
     CU(cudaMemcpyAsync(s->d_stage[d][sl], src, b1 - b0, cudaMemcpyHostToDevice, s->copy[d]));
+    if(useq) {
+      if(!s->d_qstage[d][sl]) { CU(cudaMalloc(&s->d_qstage[d][sl], MCX_STAGE_BYTES)); CU(cudaHostAlloc(&s->h_qstage[d][sl], MCX_STAGE_BYTES, cudaHostAllocDefault)); }
+      const uint8_t *qsrc = hqual + b0;
+      if(!pinned) { memcpy(s->h_qstage[d][sl], qsrc, b1 - b0); qsrc = s->h_qstage[d][sl]; }
+      CU(cudaMemcpyAsync(s->d_qstage[d][sl], qsrc, b1 - b0, cudaMemcpyHostToDevice, s->copy[d]));
+    }
     CU(cudaEventRecord(s->staged[d][sl], s->copy[d]));
     CU(cudaStreamWaitEvent(primary(g), s->staged[d][sl], 0));
     { int r = ss_wait_regions(s, d); if(r) return r; }
     uint64_t *kd[MCX_MAX_PARTS]; uint32_t *md[MCX_MAX_PARTS];
     ss_peer_pointers(s, d, kd, md);
     mcx_read_batch db = *b;
-    db.mem = MCX_MEM_DEVICE; db.seq = (const char *)s->d_stage[d][sl]; db.nbytes = b1 - b0; db.qual = NULL;
-    { int r = add_reads_sharded(g, &db, s->P, d, s->cap, NULL, NULL, kd, md, s->counts[d], pos - b0, pend - b0); if(r) return r; }
+    db.mem = MCX_MEM_DEVICE; db.seq = (const char *)s->d_stage[d][sl]; db.nbytes = b1 - b0;
+    db.qual = useq ? (const char *)s->d_qstage[d][sl] : NULL;
+    { int r = add_reads_sharded(g, &db, s->P, d, s->cap, NULL, NULL, kd, md, s->counts[d], useq ? 0 : pos - b0, useq ? 0 : pend - b0); if(r) return r; }
     CU(cudaEventRecord(s->stage_free[d][sl], primary(g)));
     { int r = ss_insert_all(s, d, b->colour); if(r) return r; }
     s->pending[d] += pend - pos;
     s->dirty = true;
+    pos = pend;
   }
   s->bytes_submitted += nbytes;
   return MCX_OK;

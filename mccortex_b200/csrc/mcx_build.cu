@@ -544,6 +544,17 @@ mcx_build_fused_qual_kernel(const __grid_constant__ McxBuildParams p, const __gr
   mcx_front_end<W, MCX_MODE_QUAL>(p, sink);
 }
 
+// the same with the sharded sink (multi-GPU builds with --fq-cutoff: what the production pipeline runs)
+template <int W>
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(3))
+mcx_build_sharded_qual_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTable t, const __grid_constant__ McxTupleBins b)
+{
+  McxSlowQueue<W> *q = mcx_queue<W>();
+  if(threadIdx.x == 0) { q->n = 0; q->last_n = q->epoch = q->bypass = 0; }
+  FusedSink<W, 2, true> sink{t, b, p.colour, p.may_saturate != 0, q, p.counters, false};
+  mcx_front_end<W, MCX_MODE_QUAL>(p, sink);
+}
+
 template <int W>
 __global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_kmer_tuples_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTupleBins b)
 {
@@ -755,6 +766,12 @@ cudaError_t mcx_launch_build_sharded(const McxBuildParams &p, const McxTable &t,
 {
   if(p.r_end <= p.r_begin) return cudaSuccess;
   unsigned grid = grid_for_chunks(p, 3);
+  if(p.qual) { // quality cut-off: summary pass, then the sharded insert pass (the launch starts at a read boundary)
+    mcx_contig_summary_kernel<<<grid_for_chunks(p, 4), MCX_THREADS, 0, st>>>(p);
+    if(p.k <= 31) mcx_build_sharded_qual_kernel<1><<<grid, MCX_THREADS, queue_smem<1>(mcx_build_sharded_qual_kernel<1>), st>>>(p, t, b);
+    else mcx_build_sharded_qual_kernel<2><<<grid, MCX_THREADS, queue_smem<2>(mcx_build_sharded_qual_kernel<2>), st>>>(p, t, b);
+    return cudaGetLastError();
+  }
   if(p.k <= 31) mcx_build_sharded_kernel<1><<<grid, MCX_THREADS, queue_smem<1>(mcx_build_sharded_kernel<1>), st>>>(p, t, b);
   else mcx_build_sharded_kernel<2><<<grid, MCX_THREADS, queue_smem<2>(mcx_build_sharded_kernel<2>), st>>>(p, t, b);
   return cudaGetLastError();

@@ -55,7 +55,7 @@ static const char build_usage[] =
 "  -D, --device <id[,id..]> CUDA device [default: 0]; several: one replica of the graph per device, every\n"
 "                           batch of reads goes to one of them, the replicas are merged before the dump\n"
 "      --shard              with several devices: ONE graph, hash-partitioned over the devices (each holds 1/N of\n"
-"                           the k-mers; k-mers travel to their owner over NVLink); plain --seq inputs only\n"
+"                           the k-mers; k-mers travel to their owner over NVLink); sequence inputs only\n"
 "\n"
 "  Note: Argument must come before input file\n"
 "  --sample <name> is required before sequence input can be loaded.\n"
@@ -573,8 +573,6 @@ static int ctx_build(int argc, char **argv)
   if(shard_mode) {
     if(ndevices < 2) mcx_die("--shard needs several devices: -D 0,1[,..]");
     if(nifiles > 0 || ngfiles > 0) mcx_die("--shard builds from sequence only (no --graph / --intersect)");
-    for(t = 0; t < ntasks; t++)
-      if(tasks[t].prefs.fq_cutoff || tasks[t].prefs.hp_cutoff) mcx_die("--shard takes plain reads only (no --fq-cutoff / --cut-hp)");
   }
   ginit.k = (uint32_t)kmer_size; ginit.ncols = (uint32_t)output_colours; ginit.capacity = kmers_in_hash; ginit.device = device;
   ginit.flags = (nifiles > 0 ? MCX_GRAPH_INTERSECT : 0) | (remove_pcr_used ? MCX_GRAPH_READSTRT : 0);

@@ -224,7 +224,7 @@ int mcx_shardset_destroy(mcx_shardset *s) { if(s) { mcx_graph_destroy(s->g); fre
 int mcx_shardset_add_reads(mcx_shardset *s, const mcx_read_batch *b)
 {
   if(!s || !b) return MCX_ERR_BAD_ARG;
-  if((b->fq_cutoff && b->qual) || b->hp_cutoff || b->must_exist) return MCX_ERR_UNSUPPORTED;
+  if(b->must_exist) return MCX_ERR_UNSUPPORTED;
   return mcx_graph_add_reads(s->g, b);
 }
 int mcx_shardset_sync(mcx_shardset *s, mcx_load_stats *st) { mcx_load_stats tmp; return s ? mcx_graph_sync(s->g, st ? st : &tmp) : MCX_ERR_BAD_ARG; }

@@ -279,6 +279,62 @@ def test_sharded_build_on_one_device(M, oracle, k, nparts):
     assert b"".join(x.tobytes() for x in merge_sorted_runs(runs, rb, W, chunk_recs=777)) == recs
 
 
+@pytest.mark.parametrize("k,hp,cut,nparts", [(31, 0, 43, 2), (21, 4, 45, 3), (63, 6, 40, 2)])
+def test_sharded_build_with_quality_and_homopolymer_cutoffs(M, oracle, k, hp, cut, nparts):
+    """the production pipeline's flags (--fq-cutoff, also --cut-hp) through the sharded kernels: every shard filters its
+    own reads with the quality carry chain (summary pass + sharded insert pass), tuples travel, the union of the shards
+    equals the oracle's graph of the same reads and qualities"""
+    import torch
+    rng = random.Random(17 * nparts + k + cut)
+    reads = [r for r in rand_reads(rng, 1200, (30, 260), 9000, perr=0.004, pN=0.002, lower=0.05) if r] + ["A" * 150] * 100
+    rng.shuffle(reads)
+    quals = ["".join(chr(rng.choice((cut - 1, cut, cut + 1, cut + 20, cut + 20, cut + 20, cut + 20, cut + 20))) for _ in r) for r in reads]
+    og = oracle.Graph(k, 1, 1 << 22)
+    ost = oracle.Stats()
+    for r, q in zip(reads, quals):
+        og.add_read(r, qual=q, fq_cutoff=cut, hp_cutoff=hp, stats=ost)
+    want = og.dump_sorted()[len(og.header()):]
+    og.close()
+    dev = torch.device("cuda:0")
+    W = (k + 31) // 32
+    shards = [M.Graph(k, 1, 1 << 20) for _ in range(nparts)]
+    cap = ost.num_kmers_loaded + 1024
+    keep = []
+    for p in range(nparts):
+        seq = _to_dev(torch, "".join(r + "\n" for r in reads[p::nparts]).encode(), dev)
+        qual = _to_dev(torch, "".join(q + "\n" for q in quals[p::nparts]).encode(), dev)
+        nb = sum(len(r) + 1 for r in reads[p::nparts])
+        keys = torch.zeros(nparts * cap * W, dtype=torch.int64, device=dev)
+        meta = torch.zeros(nparts * cap, dtype=torch.int32, device=dev)
+        counts = torch.zeros(nparts, dtype=torch.int64, device=dev)
+        shards[p].add_reads_sharded(seq.data_ptr(), nb, nparts, p, cap, keys.data_ptr(), meta.data_ptr(), counts.data_ptr(),
+                                    hp_cutoff=hp, qual_dev_addr=qual.data_ptr(), fq_cutoff=cut)
+        torch.cuda.synchronize()
+        cnt = counts.cpu().tolist()
+        for d in range(nparts):
+            if cnt[d]:
+                shards[d].insert_tuples(keys[d * cap * W:].data_ptr(), meta[d * cap:].data_ptr(), cnt[d])
+        torch.cuda.synchronize()
+        shards[p].flush_sharded(nparts, p, cap, keys.data_ptr(), meta.data_ptr(), counts.data_ptr())
+        torch.cuda.synchronize()
+        cnt = counts.cpu().tolist()
+        for d in range(nparts):
+            if cnt[d]:
+                shards[d].insert_tuples(keys[d * cap * W:].data_ptr(), meta[d * cap:].data_ptr(), cnt[d])
+        torch.cuda.synchronize()
+        keep.append((seq, qual, keys, meta, counts))
+    runs, loaded = [], 0
+    for p in range(nparts):
+        st = shards[p].sync()
+        loaded += st.num_kmers_loaded
+        got, n, _ = shards[p].export_records()
+        runs.append(bytes(got))
+        shards[p].close()
+    assert loaded == ost.num_kmers_loaded
+    from mccortex_b200.multi import merge_sorted_runs
+    assert b"".join(x.tobytes() for x in merge_sorted_runs(runs, 8 * W + 5, W, chunk_recs=500)) == want
+
+
 @pytest.mark.parametrize("k,nparts", [(31, 2), (31, 4), (63, 3)])
 def test_routed_build_on_one_device(M, oracle, k, nparts):
     """the fused compute+exchange path (RoutedBuilder: the sharded kernel appends tuples straight into

@@ -174,7 +174,17 @@ def test_cli_shard_mode(tmp_path, oracle, k):
     _run(["-q", "-f", "-D", devs, "--shard", "-m", "1G", "-n", "4M", "-k", str(k), "-s", "a", "-1", fas[0], "-1", fas[1], "-s", "b", "-1", fas[2], uns])
     _run_cmd("sort", ["-q", uns])
     assert open(uns, "rb").read() == open(one, "rb").read()
-    # refusals: one device, quality cut-off, graph files
+    # what the production pipeline passes (scripts/make-pipeline.pl:342-346): FASTQ with --fq-cutoff, plus a homopolymer cut-off
+    fq = tmp_path / "q.fq"
+    reads = rand_reads(rng, 3000, (40, 220), 30000, perr=0.004)
+    with open(fq, "w") as f:
+        for i, r in enumerate(reads):
+            if r:
+                f.write("@r%d\n%s\n+\n%s\n" % (i, r, "".join(chr(33 + rng.choice((40,) * 40 + (2, 9, 10, 11, 30))) for _ in r)))
+    qargs = ["-q", "-f", "-m", "1G", "-n", "4M", "-k", str(k), "-S", "-s", "q", "-Q", "10", "-H", "5", "-1", str(fq)]
+    _run(qargs + [one])
+    _run(qargs[:2] + ["-D", devs, "--shard"] + qargs[2:] + [two], env={"MCX_BATCH_BYTES": "150000"})
+    assert open(one, "rb").read() == open(two, "rb").read() and os.path.getsize(one) > 10000
+    # refusals: one device, graph files
     assert _run(["-q", "-f", "--shard", "-m", "1G", "-n", "1M", "-k", str(k), "-s", "a", "-1", fas[0], two], check=False).returncode == 1
-    assert _run(["-q", "-f", "-D", devs, "--shard", "-m", "1G", "-n", "1M", "-k", str(k), "-s", "a", "-Q", "10", "-1", fas[0], two], check=False).returncode == 1
     assert _run(["-q", "-f", "-D", devs, "--shard", "-m", "1G", "-n", "1M", "-k", str(k), "-s", "a", "-1", fas[0], "-g", one, two], check=False).returncode == 1
