@@ -1,24 +1,26 @@
 #!/bin/bash
-# one gpurun call: GPU parity tests, smoke, N=1 bench + reference arm, ncu launch list, one ncu --set full capture,
-# command line at scale (phases, configs[1])
+# one gpurun call: the whole GPU suite (incl. full-size md5 parity), smoke, N=1 bench + reference arm, ncu launch list
 set -u
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-nproc >> gpurun_out/gpu.txt
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
-tail -3 gpurun_out/smoke.log
-timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
-cat gpurun_out/bench_n1.json
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-cat gpurun_out/bench_ref.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
-  python bench.py --reads 10000000 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:mcx_build_fused_kernel -s 1 -c 1 -f -o gpurun_out/fused_full \
-  python bench.py --reads 10000000 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_bench.log 2>&1
-bash scripts/gpu_cli_phases.sh > gpurun_out/cli_phases.txt 2>&1; tail -12 gpurun_out/cli_phases.txt
-bash scripts/gpu_cli_config2.sh > gpurun_out/cli_config2.txt 2>&1; tail -4 gpurun_out/cli_config2.txt
-# two-pass design probe
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o /tmp/part_bench scripts/part_bench.cu && timeout 120 /tmp/part_bench 1200 > gpurun_out/part_bench.txt 2>&1; cat gpurun_out/part_bench.txt
-ls -la gpurun_out
+TAG=${1:-r2}
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1; nproc >> gpurun_out/${TAG}_gpu.txt
+timeout 2400 python -m pytest tests -x -q -m gpu > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_gpu.log
+tail -5 gpurun_out/${TAG}_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${TAG}_smoke.log
+tail -3 gpurun_out/${TAG}_smoke.log
+timeout 900 python bench.py > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
+python3 - <<PY
+import json
+d=[json.loads(l) for l in open("gpurun_out/${TAG}_bench_n1.json") if l.startswith("{")][-1]
+r=[json.loads(l) for l in open("gpurun_out/${TAG}_bench_ref.json") if l.startswith("{")][-1]
+print("value %.2f G/s  ms/step %.1f  frac %.3f  e2e %.2f G/s (%.1f ms)  reference %.1f M/s  e2e ratio %.0fx" % (d["value"]/1e9, d["ms_per_step"], d["roofline"]["frac"], d["e2e"]["value"]/1e9, d["e2e"]["ms_per_step"], r["value"]/1e6, d["e2e"]["value"]/r["value"]))
+x=d["extra"]
+print("cli", x.get("cli")); 
+for k,v in (x.get("other_configs") or {}).items(): print(k, {a:(round(b/1e9,2) if a in ("value","positions_per_s") else b) for a,b in v.items() if a in ("value","ms_per_step","roofline_frac","failed")})
+c=x.get("config5") or {}
+print("config5", {a:c.get(a) for a in ("value","ms_per_step","frac","failed")}, (c.get("insert_kernel_cold") or {}).get("novel",{}).get("inserts_per_s"), (c.get("insert_kernel_cold") or {}).get("found",{}).get("inserts_per_s"))
+PY
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${TAG}_launches.csv \
+  python bench.py --reads 10000000 --steps 2 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/${TAG}_ncu_launch_bench.log 2>&1
+grep -c "mcx_" gpurun_out/${TAG}_launches.csv
