@@ -150,7 +150,7 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
   e = cudaStreamSynchronize(g->own_primary);
   if(e != cudaSuccess) { int r = fail_cuda(e, "memset(table)"); mcx_graph_destroy(g); return r; }
   abi_phase("create: streams + memset");
-  // front table (k <= 31; it counts one colour at a time and is flushed when the colour changes): sized to sit in L2 (64 MB = 2^21 sets of four 8-byte
+  // front table (it counts one colour at a time and is flushed when the colour changes): sized to sit in L2 (64 MB = 2^21 sets of four 8-byte
   // slots); MCX_FRONT_BITS=0 disables it, other values are for experiments
   if(flags & MCX_GRAPH_INTERSECT) {
     e = cudaMalloc(&g->d_isec, (size_t)g->table.nslots + 8);
@@ -163,15 +163,20 @@ extern "C" int mcx_graph_create(uint32_t k, uint32_t ncols, uint64_t capacity, i
     cudaMemset(g->d_first, 0xFF, (size_t)g->table.nslots * 8u);
   }
   // (an intersected build only looks k-mers up: no front table)
-  if(g->W == 1u && !(flags & MCX_GRAPH_INTERSECT)) {
-    uint32_t bits = 21;
+  if(!(flags & MCX_GRAPH_INTERSECT)) {
+    // k <= 31: 2^21 sets of four 8-byte ways = 64 MB of tags + 32 MB of counters, L2-resident.  k > 31: two 16-byte ways
+    // per set, so the same bytes hold half as many keys -- fewer than the 4.6 M hot k-mers of the bench genome; 2^22 sets
+    // (128 MB + 32 MB, no longer L2-resident) measured faster on configs[2]: 27.2 against 22.7 G k-mers/s
+    // (profiles/r2al_k63_grid.txt) -- a hot-pass hit that misses L2 is still cheaper than a parked big-table update
+    uint32_t bits = g->W == 1u ? 21 : 22;
     if(const char *m = getenv("MCX_FRONT_BITS")) bits = (uint32_t)atoi(m);
     if(bits) {
       if(bits < 16) bits = 16;
       if(bits > 24) bits = 24;
       g->table.front_set_bits = bits;
+      g->table.front_words = g->W; // k > 31: the same bytes hold two 16-byte ways per set (and half the counters are unused)
 #ifdef MCX_EXPERIMENTS
-      if(const char *m = getenv("MCX_CLASSES")) { int v = atoi(m); g->ncls_log2 = v >= 4 ? 2u : (v >= 2 ? 1u : 0u); }
+      if(const char *m = getenv("MCX_CLASSES")) if(g->W == 1u) { int v = atoi(m); g->ncls_log2 = v >= 4 ? 2u : (v >= 2 ? 1u : 0u); }
 #endif
       // one allocation: per class (4 << bits) 8-byte tags -- all classes' tags first --, then the 4-byte counters
       e = cudaMalloc(&g->table.front, front_bytes(g));

@@ -58,8 +58,12 @@ template <bool QUAL> struct __align__(128) McxChunkSmem {
 // drained only when the next chunk might not fit (about every tenth chunk on the bench
 // workload): draining after every chunk left most warps idle at the barrier (ncu: 27 % of all
 // stall samples).
-// k > 31 has no front table: everything parks and the queue is drained after every chunk.
-#define MCX_QCAP(W) ((W) == 1 ? 2u * MCX_T : MCX_T)
+// k > 31: 16-byte keys, so the queue holds one and a half chunks (three CTAs per SM still fit); with its front table it is
+// drained every fourth chunk or so, without one (or bypassed) after every chunk.
+#ifndef MCX_QCAP2
+#define MCX_QCAP2 (MCX_T + MCX_T / 2u)
+#endif
+#define MCX_QCAP(W) ((W) == 1 ? 2u * MCX_T : MCX_QCAP2)
 template <int W> struct McxSlowQueue {
   uint64_t key[MCX_QCAP(W) * W];
   uint8_t emask[MCX_QCAP(W)];
@@ -156,7 +160,7 @@ template <int W, int G, bool SHARDED> struct FusedSink { // G = probe loads kept
   McxSlowQueue<W> *q;
   unsigned long long *counters;
   bool byp; // this chunk skips the front table (read once per chunk: begin_chunk)
-  __device__ __forceinline__ void begin_chunk() { byp = W == 1 && t.front_set_bits && *(volatile uint32_t *)&q->bypass; }
+  __device__ __forceinline__ void begin_chunk() { byp = t.front_set_bits && *(volatile uint32_t *)&q->bypass; }
 
   __device__ __forceinline__ void park(const McxKmer<W> &key, uint32_t emask)
   {
@@ -169,7 +173,7 @@ template <int W, int G, bool SHARDED> struct FusedSink { // G = probe loads kept
                                           uint32_t &novel, uint32_t &full)
   {
     (void)novel; (void)full;
-    if(W == 1 && byp) {
+    if(byp) {
       // the front table is not absorbing this data: straight to the parked pass, marked so that it skips the front table too
 #pragma unroll
       for(uint32_t j = 0; j < MCX_HALF; j++)
@@ -195,6 +199,26 @@ template <int W, int G, bool SHARDED> struct FusedSink { // G = probe loads kept
           }
         }
       }
+    } else if(W == 2 && t.front_set_bits) {
+      // the same hot pass over 16-byte tags, two ways per set
+      const McxFrontGeom2 g = mcx_front_geom2_bits(t.front_set_bits);
+#pragma unroll
+      for(uint32_t h = 0; h < MCX_HALF; h += G) {
+        uint64_t v[G][4]; McxFKey2 fk[G];
+#pragma unroll
+        for(uint32_t i = 0; i < G; i++) {
+          fk[i] = mcx_fhash2(keys[h + i].b[0], keys[h + i].b[W - 1]);
+          if((valid >> (h + i)) & 1u) mcx_ld256(t.front + ((fk[i].y >> g.tshift) << 2), v[i][0], v[i][1], v[i][2], v[i][3]);
+        }
+#pragma unroll
+        for(uint32_t i = 0; i < G; i++) {
+          if((valid >> (h + i)) & 1u) {
+            if(!mcx_front2_hit(g, t.front_cnt + ((fk[i].y >> g.tshift) << 1), fk[i].x, (fk[i].y & (g.occ - 1ull)) | g.occ,
+                               (uint64_t)emasks[h + i] << g.eshift, v[i][0], v[i][1], v[i][2], v[i][3]))
+              park(keys[h + i], emasks[h + i]);
+          }
+        }
+      }
     } else {
 #pragma unroll
       for(uint32_t j = 0; j < MCX_HALF; j++)
@@ -205,26 +229,28 @@ template <int W, int G, bool SHARDED> struct FusedSink { // G = probe loads kept
   // the next chunk may not fit (evaluated per thread just before the step barrier, OR-reduced there)
   __device__ __forceinline__ bool should_drain() const { return q->n > MCX_QCAP(W) - MCX_T; }
   // Thread 0, after the chunk barrier: keep probing the front table, or bypass it for the next chunks?  The signal costs
-  // the hot pass nothing: how much the queue grew during the chunk.  Probed, the bench workload parks 8.5 % of a chunk's
-  // windows; data the front table cannot absorb parks all of them (~0.8 T on 150 bp reads).  Above 0.6 T the next fifteen
-  // chunks skip the probe, the sixteenth probes again.  (Other threads may act on the old decision for the first groups of
-  // the next chunk: every parked item carries its own mark, so that is harmless.)
-  __device__ __forceinline__ void decide()
+  // the hot pass nothing: how much the queue grew during the chunk, against the chunk's windows (nwin: in-contig bits of
+  // the chunk, counted by warp 0 before the barrier).  Probed, the bench workload parks a tenth of a chunk's windows; data
+  // the front table cannot absorb parks all of them.  Above three quarters the next fifteen chunks skip the probe, the
+  // sixteenth probes again.  (Other threads may act on the old decision for the first groups of the next chunk: every
+  // parked item carries its own mark, so that is harmless.)
+  __device__ __forceinline__ void decide(uint32_t nwin)
   {
-    if(W != 1 || !t.front_set_bits) return;
+    if(!t.front_set_bits) return;
     const uint32_t n = q->n, parks = n - q->last_n, e = ++q->epoch;
     q->last_n = n;
     if(q->bypass) { if((e & 15u) == 0u) q->bypass = 0; }
-    else q->bypass = (parks * 5u > MCX_T * 3u) ? 1u : 0u;
+    else q->bypass = (parks * 4u > nwin * 3u && parks > MCX_T / 8u) ? 1u : 0u;
   }
   // one parked occurrence: front table (claim / edge bit), else the big table.  Returns the shard that owns the key if
   // the occurrence has to travel there as a tuple (sharded builds), else MCX_NO_DEST (it has been dealt with).
 #define MCX_NO_DEST 0xFFu
   __device__ __forceinline__ uint32_t slow(McxKmer<W> key, uint32_t emask, uint32_t &novel, uint32_t &full)
   {
-    bool try_front = W == 1 && t.front_set_bits;
-    if(W == 1 && (key.b[0] & MCX_KEY_FLAG)) { key.b[0] &= ~MCX_KEY_FLAG; try_front = false; } // parked while the front table was bypassed
-    if(try_front && mcx_front_add_slow(t, key.b[0], emask)) return MCX_NO_DEST; // absorbed by the front table
+    bool try_front = t.front_set_bits != 0u;
+    if(key.b[0] & MCX_KEY_FLAG) { key.b[0] &= ~MCX_KEY_FLAG; try_front = false; } // parked while the front table was bypassed
+    if(try_front && (W == 1 ? mcx_front_add_slow(t, key.b[0], emask) : mcx_front2_add_slow(t, key.b[0], key.b[W - 1], emask)))
+      return MCX_NO_DEST; // absorbed by the front table
     uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
     if(SHARDED) {
       const uint32_t d = mcx_owner(hc, bins.nparts);
@@ -275,7 +301,7 @@ template <int W, int G, bool SHARDED> struct FusedSink { // G = probe loads kept
         if(at >= bins.cap) { full = 1; continue; }
         uint64_t *kd = bins.keys[d] + at * W;
 #pragma unroll
-        for(int w = 0; w < W; w++) kd[w] = (W == 1) ? (q->key[i * W + w] & ~MCX_KEY_FLAG) : q->key[i * W + w];
+        for(int w = 0; w < W; w++) kd[w] = (w == 0) ? (q->key[i * W + w] & ~MCX_KEY_FLAG) : q->key[i * W + w];
         bins.meta[d][at] = (1u << 8) | q->emask[i];
       }
     }
@@ -301,7 +327,7 @@ template <int W> struct TupleSink {
   __device__ __forceinline__ void drain(uint32_t &, uint32_t &) {}
   __device__ __forceinline__ void reset() {}
   __device__ __forceinline__ bool should_drain() const { return false; }
-  __device__ __forceinline__ void decide() {}
+  __device__ __forceinline__ void decide(uint32_t) {}
   __device__ __forceinline__ void begin_chunk() {}
 };
 
@@ -347,6 +373,7 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
   // STL per group of eight windows in the first version's hot loop)
   uint32_t n_kmers = 0, n_novel = 0, n_contigs = 0, n_reads = 0;
   uint32_t full = 0;
+  uint32_t nwin = 0;    // warp 0: in-contig windows of the chunk just processed
   bool stopped = false; // the table is full (any CTA found out): nothing more is inserted, the launch just runs out
 
   for(int64_t s = -2;; s++) {
@@ -405,6 +432,11 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
       const uint32_t hi = p.r_end > g0 ? (p.r_end - g0 < MCX_WPT ? (uint32_t)(p.r_end - g0) : MCX_WPT) : 0u;
       const uint32_t own = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
       sink.begin_chunk();
+      if(tid < 32u) { // in-contig windows of the chunk (its look-back positions included: close enough), for sink.decide
+        uint32_t c = 0;
+        for(uint32_t w = tid; w < MCX_VW; w += 32u) c += __popc(sm.vmask[j & 1u][w]);
+        nwin = __reduce_add_sync(0xFFFFFFFFu, c);
+      }
       mcx_thread_occurrences<W>(sm.pk[j % 3u], sm.vmask[j & 1u], tid, p.k,
         [&](const McxKmer<W> *keys, const uint32_t *emasks, uint32_t valid, uint32_t starts, uint32_t j0) {
           valid &= own >> j0;
@@ -426,7 +458,7 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
     if(tid == 0) {
       const uint64_t ch4 = chunk0 + (uint64_t)(s + 4) * cstride;
       if(ch4 < c_last) issue_chunk_load<QUAL>(sm, p, ch4, (uint32_t)(s + 4) & 1u);
-      sink.decide();
+      sink.decide(nwin);
     }
 
     if(QUAL && s >= -1 && ch1 < c_last) {
@@ -490,12 +522,15 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
 }
 
 // k <= 31: 3 CTAs x 256 threads per SM, two probe loads in flight per thread (other occupancies / depths were measured in
-// round 1: profiles/r1_exp_occupancy.txt).  k > 31 (no front table: every occurrence parks): 4 CTAs.
+// round 1: profiles/r1_exp_occupancy.txt).  k > 31: the same, with the 16-byte-tag front table and a queue of 1.5 chunks.
 #ifndef MCX_FUSED_MINB
 #define MCX_FUSED_MINB 3
 #endif
+#ifndef MCX_FUSED_MINB2
+#define MCX_FUSED_MINB2 3
+#endif
 template <int W>
-__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(W == 1 ? MCX_FUSED_MINB : 4))
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(W == 1 ? MCX_FUSED_MINB : MCX_FUSED_MINB2))
 mcx_build_fused_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTable t, const __grid_constant__ McxTupleBins nobins)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
@@ -503,7 +538,10 @@ mcx_build_fused_kernel(const __grid_constant__ McxBuildParams p, const __grid_co
 #ifndef MCX_FUSED_G
 #define MCX_FUSED_G 2
 #endif
-  FusedSink<W, W == 1 ? MCX_FUSED_G : 1, false> sink{t, nobins, p.colour, p.may_saturate != 0, q, p.counters, false};
+#ifndef MCX_FUSED_G2
+#define MCX_FUSED_G2 2
+#endif
+  FusedSink<W, W == 1 ? MCX_FUSED_G : MCX_FUSED_G2, false> sink{t, nobins, p.colour, p.may_saturate != 0, q, p.counters, false};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
 
@@ -526,7 +564,7 @@ struct NullSink {
   __device__ __forceinline__ void drain(uint32_t &, uint32_t &) {}
   __device__ __forceinline__ void reset() {}
   __device__ __forceinline__ bool should_drain() const { return false; }
-  __device__ __forceinline__ void decide() {}
+  __device__ __forceinline__ void decide(uint32_t) {}
   __device__ __forceinline__ void begin_chunk() {}
 };
 __global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_contig_summary_kernel(const __grid_constant__ McxBuildParams p)
@@ -601,25 +639,39 @@ __global__ void __launch_bounds__(MCX_THREADS, 4) mcx_insert_tuples_kernel(const
 
 // ---------------------------------------------------------------- front-table flush
 // merge every front entry that has counted something since the last flush into the big table:
-// key = mcx_fhash_inv(set, tag), covg += count, edges |= edges; its counter restarts at 0
+// key = inverse hash of (set, tag), covg += count, edges |= edges; its counter restarts at 0
+template <int W>
 __global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t, McxTupleBins bins, int may_saturate, unsigned long long *counters)
 {
   const McxFrontGeom g = mcx_front_geom(t);
-  const uint64_t nslots = 4ull << t.front_set_bits;
+  const McxFrontGeom2 g2 = mcx_front_geom2_bits(t.front_set_bits);
+  const uint64_t nways = (W == 1 ? 4ull : 2ull) << t.front_set_bits;
   uint64_t n_novel = 0; uint32_t full = 0;
-  for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nslots; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t v = t.front[i];
-    if(v == 0) continue;
-    const uint32_t hi = (uint32_t)(v >> 32);
-    McxKmer<1> key; key.b[0] = mcx_fhash_inv((uint32_t)v, ((hi & (g.occ - 1u)) << g.S) | ((uint32_t)(i >> 2) ^ (hi >> 31))); // displaced: home = the neighbouring set
-    const uint32_t edges = (hi >> g.eshift) & 0xFFu;
+  for(uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nways; i += (uint64_t)gridDim.x * blockDim.x) {
+    McxKmer<W> key; uint32_t edges;
+    if(W == 1) {
+      const uint64_t v = t.front[i];
+      if(v == 0) continue;
+      const uint32_t hi = (uint32_t)(v >> 32);
+      key.b[0] = mcx_fhash_inv((uint32_t)v, ((hi & (g.occ - 1u)) << g.S) | ((uint32_t)(i >> 2) ^ (hi >> 31))); // displaced: home = the neighbouring set
+      edges = (hi >> g.eshift) & 0xFFu;
+    } else {
+      uint64_t lo, hi;
+      mcx_ld128(t.front + 2u * i, lo, hi);
+      if(!(hi & g2.occ)) continue;
+      const uint64_t set = (i >> 1) ^ (hi >> 63);
+      uint64_t kh, kl;
+      mcx_fhash2_inv(lo, (set << g2.tshift) | (hi & (g2.occ - 1ull)), &kh, &kl);
+      key.b[0] = kh; key.b[W - 1] = kl;
+      edges = (uint32_t)(hi >> g2.eshift) & 0xFFu;
+    }
     uint32_t count = t.front_cnt[i];
     // The tags stay: the table is still warm after the flush (no second wave of claims for the ~4.6 M hot
     // k-mers).  A record with no new occurrence has nothing new to merge -- its edge bits came with
     // occurrences that an earlier flush merged.
     if(count == 0) continue;
     t.front_cnt[i] = 0;
-    uint32_t hb, hc = mcx_lookup3<1>(key, 0u, &hb);
+    uint32_t hb, hc = mcx_lookup3<W>(key, 0u, &hb);
     if(bins.nparts > 1u) {
       // sharded build: an aggregated record of a key owned elsewhere travels as ONE tuple (a tuple
       // carries a 24-bit count: more than that, which takes a k-mer seen > 16 M times, is split)
@@ -628,13 +680,13 @@ __global__ void __launch_bounds__(MCX_THREADS) mcx_front_flush_kernel(McxTable t
         uint32_t e = edges;
         while(count | e) {
           const uint32_t c = count < 0xFFFFFFu ? count : 0xFFFFFFu;
-          mcx_bin_push<1>(bins, d, key, (c << 8) | e, full);
+          mcx_bin_push<W>(bins, d, key, (c << 8) | e, full);
           count -= c; e = 0;
         }
         continue;
       }
     }
-    int r = mcx_table_add<1>(t, key, hc, hb, t.front_colour, edges, count, may_saturate != 0);
+    int r = mcx_table_add<W>(t, key, hc, hb, t.front_colour, edges, count, may_saturate != 0);
     n_novel += (r == 1); full |= (r == 2);
     if(full) break; // the build has failed: stop probing
   }
@@ -683,6 +735,16 @@ template <int W, class K> static size_t queue_smem(K kernel)
   return bytes;
 }
 
+// CTAs of `kernel` that are resident per SM with `smem` bytes of dynamic shared memory.  The
+// build kernels are persistent -- CTA b takes chunks b, b + grid, ... -- so a grid of more CTAs than fit runs a second,
+// mostly empty wave (k > 31 was launched 4 per SM when 3 fit: a third of the run at a third of the occupancy).
+template <class K> static int resident_ctas(K kernel, size_t smem)
+{
+  int n = 0;
+  if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, (int)MCX_THREADS, smem) != cudaSuccess || n < 1) n = 1;
+  return n;
+}
+
 static unsigned grid_for_chunks(const McxBuildParams &p, int ctas_per_sm)
 {
   uint64_t nch = (p.r_end + MCX_T - 1) / MCX_T - p.r_begin / MCX_T;
@@ -694,7 +756,10 @@ cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, c
 {
   if(p.r_end <= p.r_begin) return cudaSuccess;
   if(p.k <= 31) mcx_build_fused_kernel<1><<<grid_for_chunks(p, MCX_FUSED_MINB), MCX_THREADS, queue_smem<1>(mcx_build_fused_kernel<1>), st>>>(p, t, mcx_no_bins());
-  else mcx_build_fused_kernel<2><<<grid_for_chunks(p, 4), MCX_THREADS, queue_smem<2>(mcx_build_fused_kernel<2>), st>>>(p, t, mcx_no_bins());
+  else {
+    const size_t smem = queue_smem<2>(mcx_build_fused_kernel<2>);
+    mcx_build_fused_kernel<2><<<grid_for_chunks(p, resident_ctas(mcx_build_fused_kernel<2>, smem)), MCX_THREADS, smem, st>>>(p, t, mcx_no_bins());
+  }
   return cudaGetLastError();
 }
 
@@ -702,10 +767,14 @@ cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, c
 cudaError_t mcx_launch_build_fused_qual(const McxBuildParams &p, const McxTable &t, cudaStream_t st)
 {
   if(p.r_end <= p.r_begin) return cudaSuccess;
-  unsigned grid = grid_for_chunks(p, 4);
-  mcx_contig_summary_kernel<<<grid, MCX_THREADS, 0, st>>>(p);
-  if(p.k <= 31) mcx_build_fused_qual_kernel<1><<<grid, MCX_THREADS, queue_smem<1>(mcx_build_fused_qual_kernel<1>), st>>>(p, t, mcx_no_bins());
-  else mcx_build_fused_qual_kernel<2><<<grid, MCX_THREADS, queue_smem<2>(mcx_build_fused_qual_kernel<2>), st>>>(p, t, mcx_no_bins());
+  mcx_contig_summary_kernel<<<grid_for_chunks(p, 4), MCX_THREADS, 0, st>>>(p);
+  if(p.k <= 31) {
+    const size_t smem = queue_smem<1>(mcx_build_fused_qual_kernel<1>);
+    mcx_build_fused_qual_kernel<1><<<grid_for_chunks(p, resident_ctas(mcx_build_fused_qual_kernel<1>, smem)), MCX_THREADS, smem, st>>>(p, t, mcx_no_bins());
+  } else {
+    const size_t smem = queue_smem<2>(mcx_build_fused_qual_kernel<2>);
+    mcx_build_fused_qual_kernel<2><<<grid_for_chunks(p, resident_ctas(mcx_build_fused_qual_kernel<2>, smem)), MCX_THREADS, smem, st>>>(p, t, mcx_no_bins());
+  }
   return cudaGetLastError();
 }
 
@@ -750,7 +819,8 @@ cudaError_t mcx_launch_repack_lines(const uint8_t *src, const uint64_t *off, uin
 cudaError_t mcx_launch_front_flush(const McxTable &t, int may_saturate, unsigned long long *counters, cudaStream_t st)
 {
   if(!t.front_set_bits) return cudaSuccess;
-  mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, mcx_no_bins(), may_saturate, counters);
+  if(t.front_words == 2u) mcx_front_flush_kernel<2><<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, mcx_no_bins(), may_saturate, counters);
+  else mcx_front_flush_kernel<1><<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, mcx_no_bins(), may_saturate, counters);
   return cudaGetLastError(); // (the kernel zeroes the counters it merges; the tags stay claimed)
 }
 
@@ -758,7 +828,8 @@ cudaError_t mcx_launch_front_flush_sharded(const McxTable &t, const McxTupleBins
                                            unsigned long long *counters, cudaStream_t st)
 {
   if(!t.front_set_bits) return cudaSuccess;
-  mcx_front_flush_kernel<<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, b, may_saturate, counters);
+  if(t.front_words == 2u) mcx_front_flush_kernel<2><<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, b, may_saturate, counters);
+  else mcx_front_flush_kernel<1><<<num_sms() * 8, MCX_THREADS, 0, st>>>(t, b, may_saturate, counters);
   return cudaGetLastError();
 }
 
@@ -768,12 +839,20 @@ cudaError_t mcx_launch_build_sharded(const McxBuildParams &p, const McxTable &t,
   unsigned grid = grid_for_chunks(p, 3);
   if(p.qual) { // quality cut-off: summary pass, then the sharded insert pass (the launch starts at a read boundary)
     mcx_contig_summary_kernel<<<grid_for_chunks(p, 4), MCX_THREADS, 0, st>>>(p);
-    if(p.k <= 31) mcx_build_sharded_qual_kernel<1><<<grid, MCX_THREADS, queue_smem<1>(mcx_build_sharded_qual_kernel<1>), st>>>(p, t, b);
-    else mcx_build_sharded_qual_kernel<2><<<grid, MCX_THREADS, queue_smem<2>(mcx_build_sharded_qual_kernel<2>), st>>>(p, t, b);
+    if(p.k <= 31) {
+      const size_t smem = queue_smem<1>(mcx_build_sharded_qual_kernel<1>);
+      mcx_build_sharded_qual_kernel<1><<<grid_for_chunks(p, resident_ctas(mcx_build_sharded_qual_kernel<1>, smem)), MCX_THREADS, smem, st>>>(p, t, b);
+    } else {
+      const size_t smem = queue_smem<2>(mcx_build_sharded_qual_kernel<2>);
+      mcx_build_sharded_qual_kernel<2><<<grid_for_chunks(p, resident_ctas(mcx_build_sharded_qual_kernel<2>, smem)), MCX_THREADS, smem, st>>>(p, t, b);
+    }
     return cudaGetLastError();
   }
   if(p.k <= 31) mcx_build_sharded_kernel<1><<<grid, MCX_THREADS, queue_smem<1>(mcx_build_sharded_kernel<1>), st>>>(p, t, b);
-  else mcx_build_sharded_kernel<2><<<grid, MCX_THREADS, queue_smem<2>(mcx_build_sharded_kernel<2>), st>>>(p, t, b);
+  else {
+    const size_t smem = queue_smem<2>(mcx_build_sharded_kernel<2>);
+    mcx_build_sharded_kernel<2><<<grid_for_chunks(p, resident_ctas(mcx_build_sharded_kernel<2>, smem)), MCX_THREADS, smem, st>>>(p, t, b);
+  }
   return cudaGetLastError();
 }
 

@@ -316,6 +316,45 @@ MCX_HD uint64_t mcx_fhash_inv(uint32_t x, uint32_t y)
   const uint32_t kh = y1 ^ ((kl * MCX_FH_C1) >> 2);
   return ((uint64_t)kh << 32) | kl;
 }
+// ---- 33 <= k <= 63: the same table with 16-byte tags, two ways per 32-byte set -------------------------------------
+// A key is a high word kh (<= 62 bits) and a low word kl (64 bits).  The same three Feistel steps, 64 bits wide, with
+// m(v, C) = (v ^ (v >> 31)) * C as the round function:
+//     y1 = kh ^ (m(kl, C1) >> 2);   x = kl ^ m(y1, C2);   y = y1 ^ (m(x, C3) >> 2);          (y: 62 bits)
+// set = TOP S bits of y (the well-mixed end of the last product), tag = (x, low 62 - S bits of y):
+//   tag.lo = x
+//   tag.hi = [ displaced : 1 (bit 63) | 0 ... | edges : 8 | occupied : 1 | low 62 - S bits of y ]
+// Counters: one u32 per way, in their own region, as for k <= 31.  An empty way is sixteen zero bytes.
+#define MCX_FH2_C1 0x9E3779B97F4A7C15ull
+#define MCX_FH2_C2 0xC2B2AE3D27D4EB4Full
+#define MCX_FH2_C3 0xD6E8FEB86659FD93ull
+struct McxFKey2 { uint64_t x, y; };
+MCX_HD uint64_t mcx_fmix64(uint64_t v, uint64_t c) { return (v ^ (v >> 31)) * c; }
+MCX_HD McxFKey2 mcx_fhash2(uint64_t kh, uint64_t kl)
+{
+  McxFKey2 r;
+  const uint64_t y1 = kh ^ (mcx_fmix64(kl, MCX_FH2_C1) >> 2);
+  r.x = kl ^ mcx_fmix64(y1, MCX_FH2_C2);
+  r.y = y1 ^ (mcx_fmix64(r.x, MCX_FH2_C3) >> 2);
+  return r;
+}
+MCX_HD void mcx_fhash2_inv(uint64_t x, uint64_t y, uint64_t *kh, uint64_t *kl)
+{
+  const uint64_t y1 = y ^ (mcx_fmix64(x, MCX_FH2_C3) >> 2);
+  *kl = x ^ mcx_fmix64(y1, MCX_FH2_C2);
+  *kh = y1 ^ (mcx_fmix64(*kl, MCX_FH2_C1) >> 2);
+}
+struct McxFrontGeom2 { uint32_t S, tshift, eshift; uint64_t occ, mask; }; // mask: tag bits + occupied + displaced
+#define MCX_FRONT2_DISPLACED (1ull << 63)
+MCX_HD McxFrontGeom2 mcx_front_geom2_bits(uint32_t S)
+{
+  McxFrontGeom2 g;
+  g.S = S; g.tshift = 62u - S;
+  g.occ = 1ull << g.tshift;
+  g.mask = ((g.occ << 1) - 1ull) | MCX_FRONT2_DISPLACED;
+  g.eshift = g.tshift + 1u;
+  return g;
+}
+
 // geometry of the tag's hi word for S set bits (16 <= S <= 24)
 struct McxFrontGeom { uint32_t S, setmask, occ, tagmask, eshift; };
 MCX_HD McxFrontGeom mcx_front_geom_bits(uint32_t S)

@@ -22,7 +22,7 @@ struct McxTable {
   uint64_t nslots;      // always even
   uint32_t stride;      // u32 words per slot
   uint32_t ncols;
-  // L2-resident front table (k <= 31; one colour at a time): a dense write-combining cache in front of
+  // L2-resident front table (one colour at a time; k <= 31 here, the 16-byte-tag variant for k > 31 in mcx_device.cuh): a dense write-combining cache in front of
   // the big table.  The big table is >> L2 and a hot k-mer there drags a whole 128-byte L2 line
   // for 16 useful bytes, so on high-coverage input the hot set does not fit L2 (ncu, first
   // kernel: 127 B of DRAM traffic per occurrence, L2 hit rate 30 %).  Layout, the bijective hash
@@ -37,6 +37,7 @@ struct McxTable {
   unsigned int *front_cnt;     // counters: one per slot
   uint32_t front_set_bits;     // log2(number of sets); 0 = no front table
   uint32_t front_colour;       // the ONE colour the front table is counting (it is flushed when the colour changes)
+  uint32_t front_words;        // key words of the build (1: 8-byte tags, four ways per set; 2: 16-byte tags, two ways)
 };
 
 #if defined(__CUDACC__)
@@ -211,8 +212,10 @@ __device__ __forceinline__ int mcx_table_add<2>(const McxTable &t, const McxKmer
     else mcx_ld128(s, c0, c1); // one 16-byte transaction: never a torn view of a 128-bit CAS
     if(c0 == 0) {
       mcx_cas128(s, 0ull, 0ull, k0f, k1, c0, c1);
+      // claimed: the rest of the slot is still all zero as loaded (nothing writes coverage or edges before the key), so the
+      // edge word is known and mcx_edges_or needs no load.  Lost the race: whoever won may have written them since.
       if(c0 == 0) { novel = 1; c0 = k0f; c1 = k1; }
-      have_meta = false;
+      else have_meta = false;
     }
     if(c0 == k0f && c1 == k1) {
       mcx_covg_add(s + 4 + colour, n, may_saturate);
@@ -339,5 +342,56 @@ __device__ __forceinline__ bool mcx_front_hit(const McxFrontGeom &g, unsigned in
   atomicAdd(cnt_set + way, 1u);
   return true;
 }
+
+// ---- front table, 33 <= k <= 63: two 16-byte ways per set (layout: mcx_device.cuh) ------------------------------------
+// v[4] = {lo0, hi0, lo1, hi1} of one set as the caller loaded it.  Same rules as k <= 31: first come, never evicted;
+// a key whose home set is full may live displaced in set ^ 1.
+__device__ __forceinline__ bool mcx_front2_resolve_sector(const McxTable &t, const McxFrontGeom2 &g, uint64_t set, uint64_t x,
+                                                          uint64_t th, uint64_t eb, const uint64_t v[4])
+{
+  unsigned long long *ways = t.front + (set << 2);
+  int w = -1; uint64_t seen_hi = 0;
+#pragma unroll
+  for(int i = 1; i >= 0; i--)
+    if(v[2 * i] == x && ((v[2 * i + 1] ^ th) & g.mask) == 0ull) { w = i; seen_hi = v[2 * i + 1]; }
+  if(w < 0) {
+#pragma unroll
+    for(int i = 0; i < 2; i++) {
+      if(w < 0 && (v[2 * i] | v[2 * i + 1]) == 0ull) {
+        uint64_t olo, ohi;
+        mcx_cas128(ways + 2 * i, 0ull, 0ull, x, th | eb, olo, ohi);
+        if((olo | ohi) == 0ull) { w = i; seen_hi = th | eb; }                         // claimed, edges included
+        else if(olo == x && ((ohi ^ th) & g.mask) == 0ull) { w = i; seen_hi = ohi; }  // lost the race to the same key
+      }
+    }
+    if(w < 0) return false;
+  }
+  atomicAdd(t.front_cnt + (set << 1) + (uint32_t)w, 1u);
+  if((seen_hi & eb) != eb) atomicOr(ways + 2 * w + 1, (unsigned long long)eb);
+  return true;
+}
+static __device__ __noinline__ bool mcx_front2_add_slow(McxTable t, uint64_t kh, uint64_t kl, uint32_t emask)
+{
+  const McxFrontGeom2 g = mcx_front_geom2_bits(t.front_set_bits);
+  const McxFKey2 fk = mcx_fhash2(kh, kl);
+  const uint64_t set = fk.y >> g.tshift, th = (fk.y & (g.occ - 1ull)) | g.occ, eb = (uint64_t)emask << g.eshift;
+  uint64_t a[4], b[4];
+  mcx_ld256(t.front + (set << 2), a[0], a[1], a[2], a[3]);
+  mcx_ld256(t.front + ((set ^ 1ull) << 2), b[0], b[1], b[2], b[3]);
+  if(mcx_front2_resolve_sector(t, g, set, fk.x, th, eb, a)) return true;
+  return mcx_front2_resolve_sector(t, g, set ^ 1ull, fk.x, th | MCX_FRONT2_DISPLACED, eb, b);
+}
+// fast side: one 32-bit RED if the key sits in its home set with the edge bits already there
+__device__ __forceinline__ bool mcx_front2_hit(const McxFrontGeom2 &g, unsigned int *cnt_set, uint64_t x, uint64_t th, uint64_t eb,
+                                               uint64_t lo0, uint64_t hi0, uint64_t lo1, uint64_t hi1)
+{
+  const bool m0 = (lo0 == x) & (((hi0 ^ th) & g.mask) == 0ull);
+  const bool m1 = (lo1 == x) & (((hi1 ^ th) & g.mask) == 0ull);
+  const uint64_t hi = m0 ? hi0 : hi1;
+  if(!(m0 | m1) || (hi & eb) != eb) return false;
+  atomicAdd(cnt_set + (m0 ? 0u : 1u), 1u);
+  return true;
+}
+
 
 #endif // __CUDACC__

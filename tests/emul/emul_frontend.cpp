@@ -261,8 +261,39 @@ static int main_pcr(int argc, char **argv)
   return 0;
 }
 
+// --fhash <n> <seed>: the front tables' key <-> (set, tag) maps are bijections (inverse round trip, both widths) and
+// spread k-mer-like keys over the sets (prints the worst set load for 2^S * 2 keys over 2^S sets, S = 16)
+static int main_fhash(int argc, char **argv)
+{
+  uint64_t n = argc > 2 ? strtoull(argv[2], NULL, 10) : 100000, z = argc > 3 ? strtoull(argv[3], NULL, 10) : 1;
+  auto rnd = [&z]() { z += 0x9E3779B97F4A7C15ull; uint64_t x = z; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31); };
+  const uint32_t S = 16;
+  std::vector<uint32_t> load1(1u << S, 0), load2(1u << S, 0);
+  const McxFrontGeom g1 = mcx_front_geom_bits(S); const McxFrontGeom2 g2 = mcx_front_geom2_bits(S);
+  uint64_t bad = 0;
+  for(uint64_t i = 0; i < n; i++) {
+    // keys the way a graph has them: random, or runs of one base / neighbours that differ in one base
+    uint64_t kh = rnd() >> 2, kl = rnd();
+    if(i % 7 == 3) { kh = 0; kl = i; } else if(i % 7 == 5) { kh = (0x5555555555555555ull * (i & 3)) >> 2; kl = 0x5555555555555555ull * (i & 3) ^ (i << 2); }
+    McxFKey a = mcx_fhash(((kh & 0x3FFFFFFFull) << 32) | (uint32_t)kl);
+    if(mcx_fhash_inv(a.x, a.y) != (((kh & 0x3FFFFFFFull) << 32) | (uint32_t)kl) || (a.y >> 30)) bad++;
+    McxFKey2 b = mcx_fhash2(kh, kl);
+    uint64_t rh, rl; mcx_fhash2_inv(b.x, b.y, &rh, &rl);
+    if(rh != kh || rl != kl || (b.y >> 62)) bad++;
+    // set + tag bits rebuild y exactly
+    const uint64_t set = b.y >> g2.tshift, th = b.y & (g2.occ - 1ull);
+    if(((set << g2.tshift) | th) != b.y || set >> S) bad++;
+    load1[a.y & g1.setmask]++; load2[set]++;
+  }
+  uint32_t m1 = 0, m2 = 0;
+  for(uint32_t i = 0; i < (1u << S); i++) { if(load1[i] > m1) m1 = load1[i]; if(load2[i] > m2) m2 = load2[i]; }
+  printf("bad=%llu max_load1=%u max_load2=%u mean=%.3f\n", (unsigned long long)bad, m1, m2, (double)n / (1u << S));
+  return bad ? 1 : 0;
+}
+
 int main(int argc, char **argv)
 {
+  if(argc > 1 && strcmp(argv[1], "--fhash") == 0) return main_fhash(argc, argv);
   if(argc > 1 && strcmp(argv[1], "--pcr") == 0) return main_pcr(argc, argv);
   if(argc > 1 && strcmp(argv[1], "--lane") == 0) return main_lane(argc, argv);
   if(argc < 5) { fprintf(stderr, "usage: %s <lines-file> <k> <hp> <r_piece>\n", argv[0]); return 2; }

@@ -474,3 +474,14 @@ def test_device_math_fuzz(oracle, emul, tmp_path, block):
             got, cnt = _emul(emul, tmp_path, reads, k, hp=hp, piece=piece)
         assert got == recs, (block, case, k, hp, cut, piece)
         assert cnt["kmers"] == st.num_kmers_loaded and cnt["contigs"] == st.contigs_parsed, (block, case, k, hp, cut)
+
+
+def test_front_table_hashes_are_bijections(emul):
+    """(set, tag) of the L2 front tables identifies the key exactly, k <= 31 and k <= 63 (mcx_fhash / mcx_fhash2 and
+    their inverses, mcx_device.cuh), and k-mer-like keys spread over the sets like random ones."""
+    out = subprocess.check_output([emul, "--fhash", "2000000", "11"]).decode().split()
+    vals = dict(x.split("=") for x in out)
+    assert vals["bad"] == "0"
+    mean = float(vals["mean"])
+    assert int(vals["max_load1"]) < mean + 6 * mean ** 0.5 and int(vals["max_load2"]) < mean + 6 * mean ** 0.5
+
