@@ -331,6 +331,75 @@ template <int W> struct TupleSink {
   __device__ __forceinline__ void begin_chunk() {}
 };
 
+// ---------------------------------------------------------------- contig chain, warp-wide (quality modes)
+// The chain x[i] = ev[i] & (sv[i] | x[i-1]) over the MCX_VW mask words of a chunk, with the carry-in planted at bit cb of
+// word 0 (ev = sv = cin there, everything below cleared) -- what mcx_contig_chain (mcx_chunk.cuh) does serially, word by
+// word.  Each lane owns three consecutive words: it works out its carry-out for carry-in 0 and 1, the 32 two-bit functions
+// are composed by a prefix scan, then every lane redoes its words with its real carry-in.  In place on vm.
+__device__ __forceinline__ void mcx_contig_chain_warp(uint32_t *vm, const uint32_t *sv, uint32_t cb, uint32_t cin, uint32_t lane)
+{
+  constexpr uint32_t WPL = (MCX_VW + 31u) / 32u;
+  uint32_t a[WPL], b[WPL];
+#pragma unroll
+  for(uint32_t i = 0; i < WPL; i++) {
+    const uint32_t w = lane * WPL + i;
+    uint32_t e = w < MCX_VW ? vm[w] : 0u, t = w < MCX_VW ? sv[w] : 0u;
+    if(w == 0) {
+      const uint32_t keep = (~0u << cb) & ~(1u << cb);
+      e = (e & keep) | (cin << cb); t = (t & keep) | (cin << cb);
+    }
+    a[i] = e; b[i] = e & t;
+  }
+  uint32_t f0 = 0u, f1 = 1u; // carry out of this lane's words for carry-in 0 / 1
+#pragma unroll
+  for(uint32_t i = 0; i < WPL; i++) {
+    f0 = (uint32_t)(((uint64_t)a[i] + b[i] + f0) >> 32);
+    f1 = (uint32_t)(((uint64_t)a[i] + b[i] + f1) >> 32);
+  }
+#pragma unroll
+  for(uint32_t d = 1; d < 32u; d <<= 1) { // inclusive scan: (f0, f1) of lanes 0..lane composed
+    const uint32_t l0 = __shfl_up_sync(0xFFFFFFFFu, f0, d), l1 = __shfl_up_sync(0xFFFFFFFFu, f1, d);
+    if(lane >= d) { const uint32_t n0 = l0 ? f1 : f0, n1 = l1 ? f1 : f0; f0 = n0; f1 = n1; }
+  }
+  uint32_t c = __shfl_up_sync(0xFFFFFFFFu, f0, 1);
+  if(lane == 0) c = 0u;
+#pragma unroll
+  for(uint32_t i = 0; i < WPL; i++) {
+    const uint32_t w = lane * WPL + i;
+    const uint64_t sum = (uint64_t)a[i] + b[i] + c;
+    const uint32_t into = (uint32_t)sum ^ a[i] ^ b[i];
+    c = (uint32_t)(sum >> 32) & 1u;
+    if(w < MCX_VW) vm[w] = (into >> 1) | (c << 31);
+  }
+}
+// in_contig of window f for carry-in 0 (bit 0) and 1 (bit 1), without walking the chain: with z = the last window in
+// (cb, f] that cannot extend a contig (ev = 0), window f is in a contig iff some window after z can start one (sv = 1) --
+// or, if there is no such z, iff the carry-in was set.
+__device__ __forceinline__ uint32_t mcx_chunk_summary_warp(const uint32_t *ev, const uint32_t *sv, uint32_t cb, uint32_t f, uint32_t lane)
+{
+  const uint32_t wl = f >> 5;
+  int z = -1;
+  for(uint32_t w = lane; w <= wl; w += 32u) {
+    uint32_t m = ~0u;
+    if(w == 0) m &= ~0u << (cb + 1u);
+    if(w == wl && (f & 31u) != 31u) m &= (1u << ((f & 31u) + 1u)) - 1u;
+    const uint32_t zeros = ~ev[w] & m;
+    if(zeros) z = max(z, (int)(w * 32u + 31u) - (int)__clz(zeros));
+  }
+  z = __reduce_max_sync(0xFFFFFFFFu, z);
+  uint32_t any = 0;
+  for(uint32_t w = lane; w <= wl; w += 32u) {
+    uint32_t m = ~0u;
+    if(w == 0) m &= ~0u << (cb + 1u);
+    if(w == wl && (f & 31u) != 31u) m &= (1u << ((f & 31u) + 1u)) - 1u;
+    if((int)(w * 32u + 31u) <= z) continue;
+    if((int)(w * 32u) <= z) m &= ~0u << (uint32_t)(z - (int)(w * 32u) + 1);
+    any |= sv[w] & m;
+  }
+  const uint32_t out0 = __any_sync(0xFFFFFFFFu, any != 0u) ? 1u : 0u;
+  return out0 | ((out0 | (z < 0 ? 1u : 0u)) << 1);
+}
+
 // ---------------------------------------------------------------- front end
 // One CTA = a persistent worker over chunks c_first + blockIdx.x + j * gridDim.x (j = 0, 1, ...).
 // Software pipeline, ONE barrier per chunk: in step s the CTA runs
@@ -462,27 +531,18 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
     }
 
     if(QUAL && s >= -1 && ch1 < c_last) {
-      // vmask holds ev, svm holds sv of chunk s+1: resolve in_contig = ev & (sv | in_contig(prev))
-      // (one thread, ~68 adds).  The window before the chunk (position LB-1) carries the carry-in.
-      if(tid == 0) {
+      // vmask holds ev, svm holds sv of chunk s+1: resolve in_contig = ev & (sv | in_contig(prev)).  The window before
+      // the chunk (position LB-1) carries the carry-in.  Warp 0 does it (mcx_contig_chain_warp / mcx_chunk_summary_warp):
+      // one thread walking the 70 words kept the other 255 at the barrier for ~1.7 k cycles per chunk, twice that in
+      // the summary pass.
+      if(tid < 32u) {
         const uint32_t mb = (uint32_t)(s + 1) & 1u;
         uint32_t *vm = sm.vmask[mb], *sv = sm.svm[QUAL ? mb : 0];
-        const uint32_t cb = MCX_LB - 1u, keep = ~0u << cb; // cb < 32: lives in word 0
-        const uint32_t ev0 = vm[0] & keep & ~(1u << cb), sv0 = sv[0] & keep & ~(1u << cb);
-        if(MODE == MCX_MODE_QUAL) {
-          const uint32_t cin = sm.carry_in;
-          vm[0] = ev0 | (cin << cb); sv[0] = sv0 | (cin << cb);
-          mcx_contig_chain(vm, sv, MCX_VW, 0u, vm);
-        } else {
+        if(MODE == MCX_MODE_QUAL) mcx_contig_chain_warp(vm, sv, MCX_LB - 1u, sm.carry_in, tid);
+        else {
           // summary of this chunk's own windows: in_contig of its last window for carry-in 0 and 1
-          uint32_t out = 0;
-          for(uint32_t cin = 0; cin < 2u; cin++) {
-            vm[0] = ev0 | (cin << cb); sv[0] = sv0 | (cin << cb);
-            uint32_t x[MCX_VW];
-            mcx_contig_chain(vm, sv, MCX_VW, 0u, x);
-            out |= mcx_get_bit(x, MCX_LB - 1u + MCX_T) << cin;
-          }
-          p.summary[ch1 - c_first] = (uint8_t)out;
+          const uint32_t out = mcx_chunk_summary_warp(vm, sv, MCX_LB - 1u, MCX_LB - 1u + MCX_T, tid);
+          if(tid == 0) p.summary[ch1 - c_first] = (uint8_t)out;
         }
       }
       __syncthreads();
@@ -572,8 +632,11 @@ __global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_contig_summary_k
   NullSink sink;
   mcx_front_end<1, MCX_MODE_QSUM>(p, sink);
 }
+#ifndef MCX_QUAL_MINB
+#define MCX_QUAL_MINB 3
+#endif
 template <int W>
-__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4))
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(MCX_QUAL_MINB))
 mcx_build_fused_qual_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTable t, const __grid_constant__ McxTupleBins nobins)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
