@@ -627,7 +627,7 @@ struct NullSink {
   __device__ __forceinline__ void decide(uint32_t) {}
   __device__ __forceinline__ void begin_chunk() {}
 };
-__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(4)) mcx_contig_summary_kernel(const __grid_constant__ McxBuildParams p)
+__global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(5)) mcx_contig_summary_kernel(const __grid_constant__ McxBuildParams p)
 {
   NullSink sink;
   mcx_front_end<1, MCX_MODE_QSUM>(p, sink);
@@ -830,7 +830,7 @@ cudaError_t mcx_launch_build_fused(const McxBuildParams &p, const McxTable &t, c
 cudaError_t mcx_launch_build_fused_qual(const McxBuildParams &p, const McxTable &t, cudaStream_t st)
 {
   if(p.r_end <= p.r_begin) return cudaSuccess;
-  mcx_contig_summary_kernel<<<grid_for_chunks(p, 4), MCX_THREADS, 0, st>>>(p);
+  mcx_contig_summary_kernel<<<grid_for_chunks(p, resident_ctas(mcx_contig_summary_kernel, 0)), MCX_THREADS, 0, st>>>(p);
   if(p.k <= 31) {
     const size_t smem = queue_smem<1>(mcx_build_fused_qual_kernel<1>);
     mcx_build_fused_qual_kernel<1><<<grid_for_chunks(p, resident_ctas(mcx_build_fused_qual_kernel<1>, smem)), MCX_THREADS, smem, st>>>(p, t, mcx_no_bins());
@@ -845,7 +845,7 @@ cudaError_t mcx_launch_build_fused_qual(const McxBuildParams &p, const McxTable 
 cudaError_t mcx_launch_contig_summary(const McxBuildParams &p, cudaStream_t st)
 {
   if(p.r_end <= p.r_begin) return cudaSuccess;
-  mcx_contig_summary_kernel<<<grid_for_chunks(p, 4), MCX_THREADS, 0, st>>>(p);
+  mcx_contig_summary_kernel<<<grid_for_chunks(p, resident_ctas(mcx_contig_summary_kernel, 0)), MCX_THREADS, 0, st>>>(p);
   return cudaGetLastError();
 }
 
@@ -901,7 +901,7 @@ cudaError_t mcx_launch_build_sharded(const McxBuildParams &p, const McxTable &t,
   if(p.r_end <= p.r_begin) return cudaSuccess;
   unsigned grid = grid_for_chunks(p, 3);
   if(p.qual) { // quality cut-off: summary pass, then the sharded insert pass (the launch starts at a read boundary)
-    mcx_contig_summary_kernel<<<grid_for_chunks(p, 4), MCX_THREADS, 0, st>>>(p);
+    mcx_contig_summary_kernel<<<grid_for_chunks(p, resident_ctas(mcx_contig_summary_kernel, 0)), MCX_THREADS, 0, st>>>(p);
     if(p.k <= 31) {
       const size_t smem = queue_smem<1>(mcx_build_sharded_qual_kernel<1>);
       mcx_build_sharded_qual_kernel<1><<<grid_for_chunks(p, resident_ctas(mcx_build_sharded_qual_kernel<1>, smem)), MCX_THREADS, smem, st>>>(p, t, b);
