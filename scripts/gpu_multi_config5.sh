@@ -3,7 +3,7 @@
 set -u
 N=${1:-8}; R=${2:-37500000}
 mkdir -p gpurun_out
-MCX_BENCH_GENOME=3000000000 MCX_MULTI_BIN_FRAC=1.4 MCX_MULTI_BATCH_READS=2000000 MCX_MULTI_PROFILE=1 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
+MCX_BENCH_GENOME=3000000000 MCX_MULTI_BIN_FRAC=1.4 MCX_MULTI_BATCH_READS=2000000 MCX_MULTI_PROFILE=1 timeout ${INNER_TIMEOUT:-1200} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
   --master-addr 127.0.0.1 --master-port 29620 bench.py --gpus $N --reads $R --steps 2 --warmup 1 > gpurun_out/r2y_config5_n$N.json 2> gpurun_out/r2y_config5_n$N.err; echo "bench rc=$?"
 python3 - <<PY
 import json
