@@ -860,6 +860,11 @@ extern "C" int mcx_graph_load_records(mcx_graph *g, const void *records, uint64_
   if(nkmers_novel) *nkmers_novel = 0;
   if(nrecords == 0 || nmap == 0) return MCX_OK;
   cudaStream_t st = primary(g);
+  // must-exist loads look keys up in the big table: k-mers that so far live only in the front table would count as absent
+  if((flags & MCX_LOAD_MUST_EXIST) && g->table.front_set_bits && g->front_pending && !g->sharded) {
+    CU(flush_front(g, st));
+    g->front_pending = 0;
+  }
   const size_t rec_bytes = 8u * g->W + 5u * (size_t)file_ncols, bytes = rec_bytes * nrecords;
   const size_t map_off = (bytes + 255) & ~(size_t)255;
   const uint8_t *drecs = (const uint8_t *)records;
@@ -886,6 +891,7 @@ extern "C" int mcx_graph_finish_intersect(mcx_graph *g, uint64_t *nkmers)
 {
   if(!g) return MCX_ERR_BAD_ARG;
   if(!g->d_isec) { snprintf(g_err, sizeof(g_err), "graph was not created with MCX_GRAPH_INTERSECT"); return MCX_ERR_BAD_ARG; }
+  CU(cudaSetDevice(g->device));
   int r = sync_all(g); if(r) return r;
   if(g->exp_valid) { mcx_export_free(&g->exp); g->exp_valid = false; }
   cudaStream_t st = primary(g);
