@@ -335,11 +335,12 @@ def own_arm(args):
                 tmpdir = tempfile.mkdtemp(prefix="mcxref", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
                 fasta = os.path.join(tmpdir, "sample.fa")
                 write_fasta_sample(fasta, 0, n_s, genome, SL)
+                run_reference_build(fasta, n_s, threads, tmpdir)   # untimed: the first run of the binary on a box is ~2x slower
                 dt, nk = run_reference_build(fasta, n_s, threads, tmpdir)
                 os.remove(fasta); os.rmdir(tmpdir)
                 cpu = {"value": nk / dt, "unit": "k-mers/s", "cores": threads, "kind": "reference",
-                       "sample": "first %d reads (%d k-mer occurrences) of the workload, `mccortex31 build -t %d`, whole process %.1f s" % (
-                           n_s, nk, threads, dt)}
+                       "sample": "first %d reads (%d k-mer occurrences) of the workload, `mccortex31 build -t %d`, whole process %.1f s "
+                                 "(second of two runs)" % (n_s, nk, threads, dt)}
         except Exception as ex:  # the baseline is informative; never lose the GPU numbers over it
             cpu = {"value": None, "unit": "k-mers/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % ex}
 
