@@ -50,6 +50,28 @@ template <bool QUAL> struct __align__(128) McxChunkSmem {
   unsigned long long red[MCX_NCOUNTERS];
 };
 
+// ---------------------------------------------------------------- compile-time knobs
+// The values are the measured best; scripts/gpu_variants*.sh time alternative builds of the library made
+// with -D<knob>=<value>.  "2" = the two-word (k > 31) kernels.
+#ifndef MCX_FUSED_MINB
+#define MCX_FUSED_MINB 3      /* resident CTAs per SM the fused kernel is built for, k <= 31 */
+#endif
+#ifndef MCX_FUSED_MINB2
+#define MCX_FUSED_MINB2 3     /* ... k > 31 */
+#endif
+#ifndef MCX_QUAL_MINB
+#define MCX_QUAL_MINB 3       /* ... quality cut-off kernels (4 spills and does not fit: 174 ms against 122) */
+#endif
+#ifndef MCX_FUSED_G
+#define MCX_FUSED_G 2         /* front-table probe loads in flight per thread, k <= 31 */
+#endif
+#ifndef MCX_FUSED_G2
+#define MCX_FUSED_G2 2        /* ... k > 31 (1: -4 %, 4: -14 %) */
+#endif
+#ifndef MCX_QCAP2
+#define MCX_QCAP2 (MCX_T + MCX_T / 2u)   /* parked-queue entries, k > 31 */
+#endif
+
 // Occurrences that are not a plain front-table hit (first sight of a k-mer, missing edge bit,
 // count field filling up, k-mer that lives in the big table) are parked here and handled later,
 // one per thread, all lanes busy.  Handling them inline would stall the whole warp on two or
@@ -60,9 +82,6 @@ template <bool QUAL> struct __align__(128) McxChunkSmem {
 // stall samples).
 // k > 31: 16-byte keys, so the queue holds one and a half chunks (three CTAs per SM still fit); with its front table it is
 // drained every fourth chunk or so, without one (or bypassed) after every chunk.
-#ifndef MCX_QCAP2
-#define MCX_QCAP2 (MCX_T + MCX_T / 2u)
-#endif
 #define MCX_QCAP(W) ((W) == 1 ? 2u * MCX_T : MCX_QCAP2)
 template <int W> struct McxSlowQueue {
   uint64_t key[MCX_QCAP(W) * W];
@@ -583,24 +602,12 @@ __device__ __forceinline__ void mcx_front_end(const McxBuildParams &p, Sink &sin
 
 // k <= 31: 3 CTAs x 256 threads per SM, two probe loads in flight per thread (other occupancies / depths were measured in
 // round 1: profiles/r1_exp_occupancy.txt).  k > 31: the same, with the 16-byte-tag front table and a queue of 1.5 chunks.
-#ifndef MCX_FUSED_MINB
-#define MCX_FUSED_MINB 3
-#endif
-#ifndef MCX_FUSED_MINB2
-#define MCX_FUSED_MINB2 3
-#endif
 template <int W>
 __global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(W == 1 ? MCX_FUSED_MINB : MCX_FUSED_MINB2))
 mcx_build_fused_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTable t, const __grid_constant__ McxTupleBins nobins)
 {
   McxSlowQueue<W> *q = mcx_queue<W>();
   if(threadIdx.x == 0) { q->n = 0; q->last_n = q->epoch = q->bypass = 0; }
-#ifndef MCX_FUSED_G
-#define MCX_FUSED_G 2
-#endif
-#ifndef MCX_FUSED_G2
-#define MCX_FUSED_G2 2
-#endif
   FusedSink<W, W == 1 ? MCX_FUSED_G : MCX_FUSED_G2, false> sink{t, nobins, p.colour, p.may_saturate != 0, q, p.counters, false};
   mcx_front_end<W, MCX_MODE_PLAIN>(p, sink);
 }
@@ -632,9 +639,6 @@ __global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(5)) mcx_contig_summary_k
   NullSink sink;
   mcx_front_end<1, MCX_MODE_QSUM>(p, sink);
 }
-#ifndef MCX_QUAL_MINB
-#define MCX_QUAL_MINB 3
-#endif
 template <int W>
 __global__ void __launch_bounds__(MCX_THREADS, MCX_CTAS(MCX_QUAL_MINB))
 mcx_build_fused_qual_kernel(const __grid_constant__ McxBuildParams p, const __grid_constant__ McxTable t, const __grid_constant__ McxTupleBins nobins)
