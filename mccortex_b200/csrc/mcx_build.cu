@@ -3,8 +3,10 @@
 // Kernel A  mcx_build_fused_kernel<W>: reads -> k-mers -> canonical key -> Lookup3 ->
 //           find-or-insert -> covg++ -> edge OR, in one pass (single-GPU path; no tuple
 //           round trip through HBM).
+//           mcx_build_sharded_kernel<W>: the same with owner routing in the parked pass (one shard per GPU).
+//           mcx_build_fused_qual_kernel / mcx_build_sharded_qual_kernel + mcx_contig_summary_kernel: quality cut-off.
 // Kernel B  mcx_kmer_tuples_kernel<W>: same front end, but emits (key, edge-mask) tuples
-//           binned by owning GPU (multi-GPU path, before the all-to-all).
+//           binned by owning GPU (the NCCL baseline of the multi-GPU path).
 // Kernel C  mcx_insert_tuples_kernel<W>: inserts received tuples into the local shard.
 //
 // Replaces the reference's per-read CPU loop (relative to /root/reference):
@@ -14,14 +16,15 @@
 //   bklk3_hashlittle                                                 src/kmer/kmer_hash.h:162-211
 //   hash_table_find_or_insert_mt, db_graph_update_node_mt, db_graph_add_edge_mt
 //
-// Front end (shared by A and B): persistent CTAs walk 2 KB chunks of the batch byte
-// buffer.  One elected thread streams the next chunk global->shared with a 1-D TMA bulk
-// copy (cp.async.bulk + mbarrier complete_tx) while the CTA works on the current one
-// (double buffer).  Phase 1 turns ASCII into 2-bit packed words + validity bit masks
-// (16 bytes per thread, SWAR); phase 2a evaluates the contig rules per window into a
-// valid-window bit mask; phase 2b gives every thread one window per round: funnel-shift
-// the k-mer out of the packed words, reverse-complement with brev, pick the canonical
-// key, hash, build the edge mask from the neighbouring windows' valid bits.
+// Front end (shared by all of them; mcx_front_end): persistent CTAs walk chunks of 2048 window positions of the batch byte
+// buffer.  One elected thread streams chunk j+4 global->shared with a 1-D TMA bulk copy (cp.async.bulk + mbarrier
+// complete_tx) while the CTA, between two barriers, converts chunk j+2 (ASCII -> 2-bit packed words + bad / equal-to-
+// previous bit masks, 16 bytes per thread, SWAR), evaluates the contig rules of chunk j+1 word-parallel into a
+// valid-window mask, and rolls forward / reverse-complement k-mers over eight consecutive windows per thread of chunk j:
+// canonical key, edge mask from the neighbouring windows' valid bits, four keys at a time into the SINK.
+// Sinks: FusedSink (kernel A and the sharded kernels: L2 front table in the hot pass, everything else parked in a
+// per-CTA queue and drained cooperatively -- front-table claim, Lookup3 + big table, or a tuple for the owning shard),
+// TupleSink (kernel B), NullSink (summary pass of the quality cut-off).  DESIGN.md 3.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "mcx_chunk.cuh"
@@ -87,7 +90,7 @@ template <int W> struct McxSlowQueue {
   uint64_t key[MCX_QCAP(W) * W];
   uint8_t emask[MCX_QCAP(W)];
   uint32_t n;
-  // front-table bypass (k <= 31): queue length at the last chunk barrier, chunks done, and the decision -- on data the
+  // front-table bypass: queue length at the last chunk barrier, chunks done, and the decision -- on data the
   // front table cannot absorb (a genome much larger than its 8.4 M ways: every k-mer is seen about once per batch) the
   // tag probe, the claim attempt and the re-probe in the parked pass are pure overhead
   uint32_t last_n, epoch, bypass;
