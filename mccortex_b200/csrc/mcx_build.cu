@@ -354,71 +354,29 @@ template <int W> struct TupleSink {
 };
 
 // ---------------------------------------------------------------- contig chain, warp-wide (quality modes)
-// The chain x[i] = ev[i] & (sv[i] | x[i-1]) over the MCX_VW mask words of a chunk, with the carry-in planted at bit cb of
-// word 0 (ev = sv = cin there, everything below cleared) -- what mcx_contig_chain (mcx_chunk.cuh) does serially, word by
-// word.  Each lane owns three consecutive words: it works out its carry-out for carry-in 0 and 1, the 32 two-bit functions
-// are composed by a prefix scan, then every lane redoes its words with its real carry-in.  In place on vm.
+// The chain x[i] = ev[i] & (sv[i] | x[i-1]) over the MCX_VW mask words of a chunk -- what mcx_contig_chain (mcx_chunk.cuh)
+// does serially, word by word.  Each lane owns three consecutive words: it works out its carry-out for carry-in 0 and 1,
+// the 32 two-bit functions are composed by a prefix scan, then every lane redoes its words with its real carry-in.  In
+// place on vm.  The lane-local pieces are in mcx_chunk.cuh (the CPU emulation runs them too).
 __device__ __forceinline__ void mcx_contig_chain_warp(uint32_t *vm, const uint32_t *sv, uint32_t cb, uint32_t cin, uint32_t lane)
 {
-  constexpr uint32_t WPL = (MCX_VW + 31u) / 32u;
-  uint32_t a[WPL], b[WPL];
-#pragma unroll
-  for(uint32_t i = 0; i < WPL; i++) {
-    const uint32_t w = lane * WPL + i;
-    uint32_t e = w < MCX_VW ? vm[w] : 0u, t = w < MCX_VW ? sv[w] : 0u;
-    if(w == 0) {
-      const uint32_t keep = (~0u << cb) & ~(1u << cb);
-      e = (e & keep) | (cin << cb); t = (t & keep) | (cin << cb);
-    }
-    a[i] = e; b[i] = e & t;
-  }
-  uint32_t f0 = 0u, f1 = 1u; // carry out of this lane's words for carry-in 0 / 1
-#pragma unroll
-  for(uint32_t i = 0; i < WPL; i++) {
-    f0 = (uint32_t)(((uint64_t)a[i] + b[i] + f0) >> 32);
-    f1 = (uint32_t)(((uint64_t)a[i] + b[i] + f1) >> 32);
-  }
+  uint32_t a[MCX_CHAIN_WPL], b[MCX_CHAIN_WPL], f0, f1;
+  mcx_chain_lane_load(vm, sv, cb, cin, lane, a, b);
+  mcx_chain_lane_carry(a, b, &f0, &f1);
 #pragma unroll
   for(uint32_t d = 1; d < 32u; d <<= 1) { // inclusive scan: (f0, f1) of lanes 0..lane composed
     const uint32_t l0 = __shfl_up_sync(0xFFFFFFFFu, f0, d), l1 = __shfl_up_sync(0xFFFFFFFFu, f1, d);
-    if(lane >= d) { const uint32_t n0 = l0 ? f1 : f0, n1 = l1 ? f1 : f0; f0 = n0; f1 = n1; }
+    if(lane >= d) mcx_chain_compose(l0, l1, &f0, &f1);
   }
   uint32_t c = __shfl_up_sync(0xFFFFFFFFu, f0, 1);
   if(lane == 0) c = 0u;
-#pragma unroll
-  for(uint32_t i = 0; i < WPL; i++) {
-    const uint32_t w = lane * WPL + i;
-    const uint64_t sum = (uint64_t)a[i] + b[i] + c;
-    const uint32_t into = (uint32_t)sum ^ a[i] ^ b[i];
-    c = (uint32_t)(sum >> 32) & 1u;
-    if(w < MCX_VW) vm[w] = (into >> 1) | (c << 31);
-  }
+  mcx_chain_lane_store(vm, a, b, c, lane);
 }
-// in_contig of window f for carry-in 0 (bit 0) and 1 (bit 1), without walking the chain: with z = the last window in
-// (cb, f] that cannot extend a contig (ev = 0), window f is in a contig iff some window after z can start one (sv = 1) --
-// or, if there is no such z, iff the carry-in was set.
+// in_contig of window f for carry-in 0 (bit 0) and 1 (bit 1): mcx_summary_lane_* (mcx_chunk.cuh) + a warp max and a vote
 __device__ __forceinline__ uint32_t mcx_chunk_summary_warp(const uint32_t *ev, const uint32_t *sv, uint32_t cb, uint32_t f, uint32_t lane)
 {
-  const uint32_t wl = f >> 5;
-  int z = -1;
-  for(uint32_t w = lane; w <= wl; w += 32u) {
-    uint32_t m = ~0u;
-    if(w == 0) m &= ~0u << (cb + 1u);
-    if(w == wl && (f & 31u) != 31u) m &= (1u << ((f & 31u) + 1u)) - 1u;
-    const uint32_t zeros = ~ev[w] & m;
-    if(zeros) z = max(z, (int)(w * 32u + 31u) - (int)__clz(zeros));
-  }
-  z = __reduce_max_sync(0xFFFFFFFFu, z);
-  uint32_t any = 0;
-  for(uint32_t w = lane; w <= wl; w += 32u) {
-    uint32_t m = ~0u;
-    if(w == 0) m &= ~0u << (cb + 1u);
-    if(w == wl && (f & 31u) != 31u) m &= (1u << ((f & 31u) + 1u)) - 1u;
-    if((int)(w * 32u + 31u) <= z) continue;
-    if((int)(w * 32u) <= z) m &= ~0u << (uint32_t)(z - (int)(w * 32u) + 1);
-    any |= sv[w] & m;
-  }
-  const uint32_t out0 = __any_sync(0xFFFFFFFFu, any != 0u) ? 1u : 0u;
+  const int z = __reduce_max_sync(0xFFFFFFFFu, mcx_summary_lane_last_zero(ev, cb, f, lane));
+  const uint32_t out0 = __any_sync(0xFFFFFFFFu, mcx_summary_lane_starts(sv, cb, f, z, lane) != 0u) ? 1u : 0u;
   return out0 | ((out0 | (z < 0 ? 1u : 0u)) << 1);
 }
 

@@ -84,6 +84,94 @@ MCX_HD uint32_t mcx_contig_chain(const uint32_t *ev, const uint32_t *sv, uint32_
   return cin;
 }
 
+// ---- the same chain, warp-wide: the lane-local pieces (the device wrappers in mcx_build.cu add the shuffles, tests/emul
+// walks the 32 lanes on the CPU).  Lane l owns the MCX_CHAIN_WPL consecutive mask words starting at l * MCX_CHAIN_WPL.
+// The carry-in of the chunk is planted at bit cb of word 0 (ev = sv = cin there, everything below cleared) and the chain
+// itself starts with carry 0 -- exactly what the serial callers of mcx_contig_chain do.
+#define MCX_CHAIN_WPL ((MCX_VW + 31u) / 32u)
+MCX_HD void mcx_chain_lane_load(const uint32_t *vm, const uint32_t *sv, uint32_t cb, uint32_t cin, uint32_t lane,
+                                uint32_t a[MCX_CHAIN_WPL], uint32_t b[MCX_CHAIN_WPL])
+{
+#pragma unroll
+  for(uint32_t i = 0; i < MCX_CHAIN_WPL; i++) {
+    const uint32_t w = lane * MCX_CHAIN_WPL + i;
+    uint32_t e = w < MCX_VW ? vm[w] : 0u, t = w < MCX_VW ? sv[w] : 0u;
+    if(w == 0) {
+      const uint32_t keep = (~0u << cb) & ~(1u << cb);
+      e = (e & keep) | (cin << cb); t = (t & keep) | (cin << cb);
+    }
+    a[i] = e; b[i] = e & t;
+  }
+}
+// carry out of the lane's words for carry-in 0 (*f0) and 1 (*f1)
+MCX_HD void mcx_chain_lane_carry(const uint32_t a[MCX_CHAIN_WPL], const uint32_t b[MCX_CHAIN_WPL], uint32_t *f0, uint32_t *f1)
+{
+  uint32_t c0 = 0u, c1 = 1u;
+#pragma unroll
+  for(uint32_t i = 0; i < MCX_CHAIN_WPL; i++) {
+    c0 = (uint32_t)(((uint64_t)a[i] + b[i] + c0) >> 32);
+    c1 = (uint32_t)(((uint64_t)a[i] + b[i] + c1) >> 32);
+  }
+  *f0 = c0; *f1 = c1;
+}
+// (f0, f1) := this lane's carry function applied after the one of the lanes to its left (l0, l1)
+MCX_HD void mcx_chain_compose(uint32_t l0, uint32_t l1, uint32_t *f0, uint32_t *f1)
+{
+  const uint32_t n0 = l0 ? *f1 : *f0, n1 = l1 ? *f1 : *f0;
+  *f0 = n0; *f1 = n1;
+}
+// the lane's words again, with its real carry-in c: in_contig bits written over vm
+MCX_HD void mcx_chain_lane_store(uint32_t *vm, const uint32_t a[MCX_CHAIN_WPL], const uint32_t b[MCX_CHAIN_WPL], uint32_t c, uint32_t lane)
+{
+#pragma unroll
+  for(uint32_t i = 0; i < MCX_CHAIN_WPL; i++) {
+    const uint32_t w = lane * MCX_CHAIN_WPL + i;
+    const uint64_t sum = (uint64_t)a[i] + b[i] + c;
+    const uint32_t into = (uint32_t)sum ^ a[i] ^ b[i];
+    c = (uint32_t)(sum >> 32) & 1u;
+    if(w < MCX_VW) vm[w] = (into >> 1) | (c << 31);
+  }
+}
+// Chunk summary without walking the chain.  With z = the last window in (cb, f] that cannot extend a contig (ev = 0),
+// window f is in a contig iff some window after z can start one (sv = 1) -- or, if there is no such z, iff the carry-in
+// was set.  Lane l looks at words l, l + 32, ...: its candidate for z (-1: none) ...
+MCX_HD uint32_t mcx_summary_word_mask(uint32_t w, uint32_t cb, uint32_t f)
+{
+  uint32_t m = ~0u;
+  if(w == 0) m &= ~0u << (cb + 1u);
+  if(w == (f >> 5) && (f & 31u) != 31u) m &= (1u << ((f & 31u) + 1u)) - 1u;
+  return m;
+}
+MCX_HD uint32_t mcx_clz32(uint32_t x) // x != 0
+{
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__clz((int)x);
+#else
+  return (uint32_t)__builtin_clz(x);
+#endif
+}
+MCX_HD int mcx_summary_lane_last_zero(const uint32_t *ev, uint32_t cb, uint32_t f, uint32_t lane)
+{
+  int z = -1;
+  for(uint32_t w = lane; w <= (f >> 5); w += 32u) {
+    const uint32_t zeros = ~ev[w] & mcx_summary_word_mask(w, cb, f);
+    if(zeros) { const int c = (int)(w * 32u + 31u) - (int)mcx_clz32(zeros); z = c > z ? c : z; }
+  }
+  return z;
+}
+// ... and, z being the maximum over the lanes, whether one of its words has a start bit after z
+MCX_HD uint32_t mcx_summary_lane_starts(const uint32_t *sv, uint32_t cb, uint32_t f, int z, uint32_t lane)
+{
+  uint32_t any = 0;
+  for(uint32_t w = lane; w <= (f >> 5); w += 32u) {
+    uint32_t m = mcx_summary_word_mask(w, cb, f);
+    if((int)(w * 32u + 31u) <= z) continue;
+    if((int)(w * 32u) <= z) m &= ~0u << (uint32_t)(z - (int)(w * 32u) + 1);
+    any |= sv[w] & m;
+  }
+  return any;
+}
+
 // ---------------------------------------------------------------------------
 // Phase 2a, word-parallel: 32 windows per call instead of one.
 // Masks are indexed by STAGED POSITION q (byte q of raw[]); window q = bases q .. q+k-1.

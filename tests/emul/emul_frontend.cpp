@@ -291,8 +291,56 @@ static int main_fhash(int argc, char **argv)
   return bad ? 1 : 0;
 }
 
+// --chain <n> <seed>: the warp-wide contig chain and the closed-form chunk summary of the quality modes, lane by lane
+// on the CPU (mcx_chain_lane_* / mcx_summary_lane_*, mcx_chunk.cuh -- the pieces the device wrappers in mcx_build.cu
+// glue together with shuffles), against the serial mcx_contig_chain on random masks of every density.
+static int main_chain(int argc, char **argv)
+{
+  uint64_t n = argc > 2 ? strtoull(argv[2], NULL, 10) : 20000, z0 = argc > 3 ? strtoull(argv[3], NULL, 10) : 1;
+  auto rnd = [&z0]() { z0 += 0x9E3779B97F4A7C15ull; uint64_t x = z0; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31); };
+  const uint32_t cb = MCX_LB - 1u, f = MCX_LB - 1u + MCX_T;
+  uint64_t bad = 0, in_contig_f = 0, depends = 0;
+  for(uint64_t it = 0; it < n; it++) {
+    // densities from "almost all set" (long contigs: the interesting carries) to sparse
+    const uint32_t de = (uint32_t)(rnd() % 7), ds = (uint32_t)(rnd() % 7);
+    auto word = [&](uint32_t d) { uint32_t w = (uint32_t)rnd(); for(uint32_t i = 0; i < d; i++) w |= (uint32_t)rnd(); if(d == 6) w = ~0u; return w; };
+    std::vector<uint32_t> ev(MCX_VW), sv(MCX_VW);
+    for(uint32_t w = 0; w < MCX_VW; w++) { ev[w] = word(de); sv[w] = (uint32_t)rnd() & (uint32_t)rnd() & (ds < 3 ? (uint32_t)rnd() : ~0u) & ev[w]; if(ds == 6) sv[w] = 0; }
+    if(it % 5 == 0) for(uint32_t w = (f >> 5) + 1; w < MCX_VW; w++) ev[w] = sv[w] = 0; // what the kernel has beyond the chunk
+    for(uint32_t cin = 0; cin < 2u; cin++) {
+      // serial reference, as the first version of the kernel did it
+      std::vector<uint32_t> e0 = ev, s0 = sv, want(MCX_VW);
+      const uint32_t keep = (~0u << cb) & ~(1u << cb);
+      e0[0] = (e0[0] & keep) | (cin << cb); s0[0] = (s0[0] & keep) | (cin << cb);
+      mcx_contig_chain(e0.data(), s0.data(), MCX_VW, 0u, want.data());
+      // 32 lanes
+      std::vector<uint32_t> vm = ev;
+      uint32_t a[32][MCX_CHAIN_WPL], b[32][MCX_CHAIN_WPL], f0[32], f1[32];
+      for(uint32_t l = 0; l < 32; l++) { mcx_chain_lane_load(vm.data(), sv.data(), cb, cin, l, a[l], b[l]); mcx_chain_lane_carry(a[l], b[l], &f0[l], &f1[l]); }
+      for(uint32_t d = 1; d < 32; d <<= 1) {
+        uint32_t p0[32], p1[32]; memcpy(p0, f0, sizeof(p0)); memcpy(p1, f1, sizeof(p1)); // __shfl_up reads the values before the step
+        for(uint32_t l = d; l < 32; l++) mcx_chain_compose(p0[l - d], p1[l - d], &f0[l], &f1[l]);
+      }
+      for(uint32_t l = 0; l < 32; l++) mcx_chain_lane_store(vm.data(), a[l], b[l], l ? f0[l - 1] : 0u, l);
+      if(vm != want) bad++;
+      // summary: closed form against the chain's bit f
+      int z = -1;
+      for(uint32_t l = 0; l < 32; l++) { int c = mcx_summary_lane_last_zero(ev.data(), cb, f, l); if(c > z) z = c; }
+      uint32_t any = 0;
+      for(uint32_t l = 0; l < 32; l++) any |= mcx_summary_lane_starts(sv.data(), cb, f, z, l);
+      const uint32_t out = (any ? 1u : 0u) | (((any ? 1u : 0u) | (z < 0 ? 1u : 0u)) << 1);
+      if(((out >> cin) & 1u) != mcx_get_bit(want.data(), f)) bad++;
+      in_contig_f += mcx_get_bit(want.data(), f); if(cin == 1u && (out == 2u)) depends++;
+    }
+  }
+  printf("bad=%llu cases=%llu last_window_in_contig=%llu carry_dependent=%llu\n", (unsigned long long)bad, (unsigned long long)(2 * n),
+         (unsigned long long)in_contig_f, (unsigned long long)depends);
+  return bad ? 1 : 0;
+}
+
 int main(int argc, char **argv)
 {
+  if(argc > 1 && strcmp(argv[1], "--chain") == 0) return main_chain(argc, argv);
   if(argc > 1 && strcmp(argv[1], "--fhash") == 0) return main_fhash(argc, argv);
   if(argc > 1 && strcmp(argv[1], "--pcr") == 0) return main_pcr(argc, argv);
   if(argc > 1 && strcmp(argv[1], "--lane") == 0) return main_lane(argc, argv);

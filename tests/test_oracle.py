@@ -485,3 +485,14 @@ def test_front_table_hashes_are_bijections(emul):
     mean = float(vals["mean"])
     assert int(vals["max_load1"]) < mean + 6 * mean ** 0.5 and int(vals["max_load2"]) < mean + 6 * mean ** 0.5
 
+
+def test_warp_contig_chain_and_chunk_summary(emul):
+    """Quality modes: the warp-wide in_contig chain (carry functions composed by a prefix scan) and the closed-form
+    chunk summary -- the lane-local code the device runs (mcx_chain_lane_*, mcx_summary_lane_*, mcx_chunk.cuh), walked
+    lane by lane -- equal the serial mcx_contig_chain (seq_contig_start2 / seq_contig_end2 with a quality cut-off,
+    src/basic/seq_reader.c:61-172) on random masks of every density, for both carry-ins."""
+    out = subprocess.check_output([emul, "--chain", "30000", "17"]).decode().split()
+    vals = dict(x.split("=") for x in out)
+    assert vals["bad"] == "0" and int(vals["cases"]) == 60000
+    assert int(vals["carry_dependent"]) > 100 and int(vals["last_window_in_contig"]) > 10000
+
